@@ -1,0 +1,221 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (where /root/reference is mounted):
+
+    python oracle/make_golden.py
+
+Every fixture stores the instance, the call parameters, the seed given to ``np.random.seed`` /
+``random.seed`` immediately before the call, and the reference's outputs.  ``num_cores=1``
+everywhere (the only reproducible configuration of the reference).  The
+generated files are small (spins are stored as int8) and are committed; the GPU box has no
+/root/reference and reads only these files.
+
+Cases are reduced-size versions of BASELINE.json's five configs (same graph families, same
+call paths, same keyword arguments) plus element-level vectors and known-answer energies.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != _HERE]  # `oracle` must be the package
+sys.path.insert(0, os.path.dirname(_HERE))
+from oracle import oracle as O  # noqa: E402
+from oracle import ref_loader as rl  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+EPS = np.finfo(float).eps
+
+
+def i8(a):
+    a = np.asarray(a)
+    assert np.all(a == np.round(a)) and np.all(np.abs(a) <= 1)
+    return a.astype(np.int8)
+
+
+def save(name, **kw):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **kw)
+    print(f"{name}: {os.path.getsize(path)} bytes")
+
+
+def case_mcmc():
+    """Element level: MCMC (NMC/nmc.py:28-91) on +-J, Gaussian J with h, annealed and fixed beta."""
+    J1, h1 = O.random_pm_graph(48, 0.2, 101)
+    rs = np.random.RandomState(102)
+    N2 = 24
+    J2 = np.zeros((N2, N2))
+    iu = np.triu_indices(N2, 1)
+    J2[iu] = rs.randn(len(iu[0]))
+    J2 += J2.T
+    h2 = rs.randn(N2)
+    out = {}
+    for tag, J, h, beta, anneal, sweeps in (("pm_fixed", J1, h1, 1.1, False, 6), ("pm_anneal", J1, h1, 3.0, True, 9),
+                                            ("gauss_fixed", J2, h2, 0.8, False, 5), ("gauss_anneal", J2, h2, 2.0, True, 7)):
+        obj = rl.nmc().NMC(J, h)
+        rl.seed_all(1000 + sweeps)
+        m0 = np.sign(2 * np.random.rand(len(h)) - 1)
+        M = obj.MCMC(sweeps, m0.copy(), beta, J, h, anneal=anneal)
+        E = np.array([-(M[:, i].T @ J @ M[:, i] / 2 + M[:, i].T @ h) for i in range(sweeps)])
+        out.update({f"{tag}_J": J, f"{tag}_h": h, f"{tag}_beta": beta, f"{tag}_anneal": anneal,
+                    f"{tag}_sweeps": sweeps, f"{tag}_seed": 1000 + sweeps, f"{tag}_M": i8(M), f"{tag}_E": E})
+    save("mcmc_element", **out)
+
+
+def case_lbp():
+    """LBP_convexified (NMC/nmc.py:93-166): marginal of every lambda step and the clusters."""
+    J, h = O.random_pm_graph(60, 0.15, 1)
+    N = 60
+    ref = rl.nmc().NMC(J, h)
+    rl.seed_all(3)
+    ms = np.sign(2 * np.random.rand(N) - 1)
+    epsv = np.abs(h) + np.sum(np.abs(J), axis=1)
+    beta = 3.0
+    with rl.quiet_tmp_cwd():
+        cl, marg_all, _, _, _ = ref.LBP_convexified(3, 0.01, 0.9, ms.copy(), epsv, EPS, 100, 0.9999999, 0.999999, beta)
+    # per-lambda iteration counts, replayed through the reference's own LoopyBeliefPropagation
+    hm = np.zeros((N, N))
+    um = J * ms.reshape(1, -1)
+    iters = []
+    for lam in marg_all.keys():
+        _, _, _, _, it, hm, um = ref.LoopyBeliefPropagation(J, (h + lam * ms * epsv).copy(), beta, hm.copy(), um.copy(), EPS, 100)
+        iters.append(it)
+    save("lbp", J=J, h=h, m_star=i8(ms), beta=beta, lambdas=np.array(list(marg_all.keys())),
+         marginals=np.array([marg_all[k] for k in marg_all.keys()]), iters=np.array(iters),
+         clusters=np.concatenate(cl).astype(np.int64), params=np.array([3, 0.01, 0.9, EPS, 100, 0.9999999, 0.999999]))
+
+
+def case_nmc_run():
+    """C1-shaped: NMC.run on a sparse +-1 random graph (README parameters, sweeps reduced)."""
+    J, h = O.random_pm_graph(60, 0.15, 1)
+    args = (40, 10, 3, 2, 1, 20, 3, 3, 0.01, 0.9, 0.9999999, 0.999999, 100, EPS)
+    rl.seed_all(21)
+    with rl.quiet_tmp_cwd():
+        M, E, mn = rl.nmc().NMC(J, h).run(*args)
+    save("nmc_run_c1", J=J, h=h, args=np.array(args), seed=21, M=i8(M), E=np.asarray(E), min_energy=mn)
+    # the reference unit-test shape: dense Gaussian J with field (NMC/unittests/test_nmc.py:9-17)
+    rs = np.random.RandomState(5)
+    N = 12
+    hg = rs.randn(N)
+    Jg = np.zeros((N, N))
+    iu = np.triu_indices(N, 1)
+    Jg[iu] = rs.randn(len(iu[0]))
+    Jg += Jg.T
+    args2 = (50, 10, 2, 1, 1, 20, 3, 3, 0.01, 0.9, 0.9999999, 0.999999, 10, EPS)
+    rl.seed_all(4)
+    with rl.quiet_tmp_cwd():
+        M, E, mn = rl.nmc().NMC(Jg, hg).run(*args2)
+    save("nmc_run_gauss", J=Jg, h=hg, args=np.array(args2), seed=4, M=i8(M), E=np.asarray(E), min_energy=mn)
+
+
+NPT_KW = dict(num_cycles=2, full_update_frequency=1, M_skip=1, temp_x=20, global_beta=3, lambda_start=3,
+              lambda_end=0.01, lambda_reduction_factor=0.9, threshold_initial=0.9999999,
+              threshold_cutoff=0.999999, max_iterations=100, tolerance=EPS)
+
+
+def case_npt():
+    """C2-shaped: APT_preprocessor ladder then NPT.run on 3D +-J EA with doNMC on the coldest replicas."""
+    A, h = O.ea3d_pm_j(4, 2)
+    J = A.toarray()
+    rl.seed_all(13)
+    with rl.quiet_tmp_cwd():
+        beta, sigma = rl.apt_preprocessor().APT_preprocessor(J.copy(), h.copy()).run(
+            num_sweeps_MCMC=30, num_sweeps_read=20, num_rng=5, beta_start=0.5, alpha=1.25, sigma_E_val=1000,
+            beta_max=4, use_hash_table=0, num_cores=1)
+    save("apt_preprocessor_c2", J=J, h=h, seed=13, args=np.array([30, 20, 5, 0.5, 1.25, 1000, 4]),
+         beta=np.array(beta, dtype=np.float64), sigma=np.array(sigma, dtype=np.float64))
+    betas = np.array(beta, dtype=np.float64)[:4]
+    doNMC = [False, False, True, True]
+    kw = dict(num_sweeps_MCMC=60, num_sweeps_read=20, num_swap_attempts=4, num_swapping_pairs=1, **NPT_KW)
+    rl.seed_all(12)
+    with rl.quiet_tmp_cwd():
+        M, E = rl.npt().NPT(J, h).run(betas, 4, doNMC, num_cores=1, **kw)
+    save("npt_run_c2", J=J, h=h, seed=12, beta_list=betas, doNMC=np.array(doNMC),
+         num_sweeps_MCMC=60, num_sweeps_read=20, num_swap_attempts=4, num_swapping_pairs=1, M=i8(M), E=E)
+
+
+def case_npt_sk():
+    """C3-shaped: dense Gaussian SK, NPT with all doNMC False."""
+    J, h = O.sk_gaussian(40, 3)
+    betas = np.array([0.4, 0.8, 1.2, 1.6, 2.0])
+    rl.seed_all(31)
+    with rl.quiet_tmp_cwd():
+        M, E = rl.npt().NPT(J, h).run(betas, 5, [False] * 5, num_sweeps_MCMC=24, num_sweeps_read=12,
+                                      num_swap_attempts=4, num_swapping_pairs=2, num_cores=1)
+    save("npt_run_c3", J=J, h=h, seed=31, beta_list=betas, num_sweeps_MCMC=24, num_sweeps_read=12,
+         num_swap_attempts=4, num_swapping_pairs=2, M=i8(M), E=E)
+
+
+def case_icm():
+    """C4-shaped: APT_ICM.run on 3D +-J EA (10 sub-replicas per beta, NPT/apt_ICM.py:177)."""
+    A, h = O.ea3d_pm_j(4, 4)
+    J = A.toarray()
+    betas = np.array([0.3, 0.7, 1.1, 1.6])
+    out = {}
+    for tag, nsm, nsr, nsa, npairs, seed in (("a", 12, 8, 4, 1, 14), ("b", 4, 4, 4, 2, 15)):
+        rl.seed_all(seed)
+        with rl.quiet_tmp_cwd():
+            M, E = rl.apt_icm().APT_ICM(J.copy(), h.copy()).run(betas, 4, num_sweeps_MCMC=nsm, num_sweeps_read=nsr,
+                                                                num_swap_attempts=nsa, num_swapping_pairs=npairs)
+        out.update({f"{tag}_args": np.array([nsm, nsr, nsa, npairs]), f"{tag}_seed": seed, f"{tag}_M": i8(M), f"{tag}_E": E})
+    # element level: clusters of two random states
+    rs = np.random.RandomState(77)
+    s1 = rs.choice([-1.0, 1.0], size=64)
+    s2 = rs.choice([-1.0, 1.0], size=64)
+    cl = rl.apt_icm().APT_ICM(J, h).find_disagreement_clusters(s1, s2, J)
+    labels = -np.ones(64, dtype=np.int32)
+    for k, c in enumerate(cl):
+        labels[np.array(c, dtype=int)] = k
+    save("apt_icm_c4", J=J, h=h, beta_list=betas, s1=i8(s1), s2=i8(s2), labels=labels, n_clusters=len(cl), **out)
+
+
+def case_npt_sparse():
+    """C5-shaped: NPT.run given a scipy.sparse J (the reference accepts it when no replica does NMC)."""
+    A, h = O.ea3d_pm_j(6, 5)
+    betas = np.linspace(0.2, 2.0, 6)
+    rl.seed_all(51)
+    with rl.quiet_tmp_cwd():
+        M, E = rl.npt().NPT(A.copy(), h).run(betas, 6, [False] * 6, num_sweeps_MCMC=6, num_sweeps_read=6,
+                                             num_swap_attempts=3, num_swapping_pairs=2, num_cores=1)
+    save("npt_run_c5", L=6, instance_seed=5, seed=51, beta_list=betas, num_sweeps_MCMC=6, num_sweeps_read=6,
+         num_swap_attempts=3, num_swapping_pairs=2, M=i8(M), E=E)
+
+
+def case_known_answers():
+    """Known-answer energies shipped with the reference examples: Wishart
+    planted instances, convention J = -J_file, E = -(m^T J m / 2), reported energy * max|J| = gs."""
+    base = os.path.join(rl.REFERENCE_ROOT, "NMC", "examples", "wishart_small", "wishart_planting_N_10_alpha_0.50")
+    gs = {}
+    with open(os.path.join(base, "gs_energies.txt")) as f:
+        for line in f:
+            if line.strip():
+                name, val = line.split()
+                gs[name] = float(val)
+    Js, Es = [], []
+    for inst in (1, 2, 3):
+        name = f"wishart_planting_N_10_alpha_0.50_inst_{inst}.txt"
+        W = np.zeros((10, 10))
+        with open(os.path.join(base, name)) as f:
+            for line in f:
+                if not line.strip() or line.startswith("#"):
+                    continue
+                a, b, v = line.split()
+                if int(a) != int(b):
+                    W[int(a), int(b)] = float(v)
+                    W[int(b), int(a)] = float(v)
+        Js.append(-W)
+        Es.append(gs[name])
+    save("known_answers_wishart", J=np.array(Js), gs_energy=np.array(Es))
+
+
+if __name__ == "__main__":
+    if not rl.available():
+        sys.exit("reference not mounted; golden vectors can only be generated in the build container")
+    import warnings
+    warnings.simplefilter("ignore")
+    for fn in (case_mcmc, case_lbp, case_nmc_run, case_npt, case_npt_sk, case_icm, case_npt_sparse, case_known_answers):
+        fn()
