@@ -1,0 +1,129 @@
+/*
+ * nlmc_b200.h -- C ABI of libnlmc_b200.so, the sm_100a CUDA implementation of the Monte Carlo hot
+ * path of usra-riacs/Nonlocal-Monte-Carlo.
+ *
+ * The reference has no FFI: its boundary is the Python class API (NMC.run, NPT.run,
+ * APT_preprocessor.run, APT_ICM.run).  The drop-in classes in nonlocal-monte-carlo_b200/nlmc_b200/
+ * keep that API and bind the entry points below with ctypes (INTEGRATION.md shows the stub a
+ * maintainer of the reference would add).  Each entry point cites the reference code it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer argument is HOST memory owned by the caller
+ *     unless its name ends in _dev;
+ *   - all functions return 0 on success and a negative code on failure; nlmc_last_error() gives
+ *     the message of the last failure on the calling thread;
+ *   - handles are opaque; one host thread per handle; the library owns device memory and streams;
+ *   - spins are int8 in {-1, 0, +1} (np.sign can return 0, NMC/nmc.py:87); J and h are the
+ *     NORMALISED values the reference uses inside run() (J / max|J|, NMC/nmc.py:474-476);
+ *   - there is no CPU fallback: every call fails with NLMC_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef NLMC_B200_H
+#define NLMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLMC_OK 0
+#define NLMC_ERR_ARG (-1)
+#define NLMC_ERR_CUDA (-2)
+#define NLMC_ERR_UNSUPPORTED (-3)
+#define NLMC_ERR_STATE (-4)
+
+typedef struct nlmc_instance nlmc_instance; /* one Ising instance (J in CSR, h) resident in HBM */
+typedef struct nlmc_replicas nlmc_replicas; /* R int8 spin configurations of one instance (exact path) */
+typedef struct nlmc_msc nlmc_msc;           /* bit-packed replica lattice for the production path  */
+
+const char *nlmc_last_error(void);
+int nlmc_version(void);
+int nlmc_device_count(void);
+/* name / SM count / free+total bytes of a device; any out pointer may be NULL */
+int nlmc_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor,
+                     uint64_t *free_bytes, uint64_t *total_bytes);
+
+/* ---- instance ---------------------------------------------------------------------------------
+ * Replaces `J = csr_matrix(J)` + `h = asarray(h)` at the top of every MCMC call (NMC/nmc.py:53-54):
+ * the CSR is uploaded once, entries in scipy's csr_matrix(J) order. */
+int nlmc_instance_create(int n, const int32_t *row_ptr, const int32_t *col, const double *val,
+                         const double *h, int device, nlmc_instance **out);
+int nlmc_instance_destroy(nlmc_instance *inst);
+int nlmc_instance_n(const nlmc_instance *inst);
+/* 1 when every stored J value is an integer (then row sums are exact in any order) */
+int nlmc_instance_is_integer(const nlmc_instance *inst);
+
+/* ---- replicas (exact path) ---------------------------------------------------------------- */
+int nlmc_replicas_create(nlmc_instance *inst, int n_replicas, const int8_t *init_spins /*[R][n] or NULL*/,
+                         nlmc_replicas **out);
+int nlmc_replicas_destroy(nlmc_replicas *reps);
+int nlmc_set_spins(nlmc_replicas *reps, int first, int count, const int8_t *spins /*[count][n]*/);
+int nlmc_get_spins(nlmc_replicas *reps, int first, int count, int8_t *out /*[count][n]*/);
+
+/* The (J, h) pair the reference hands to MCMC for replica r during an NMC phase
+ * (NMC/nmc.py:377-385,398-406; NPT/npt.py:406-414,425,441):
+ *   h_eff       the h vector of the phase (h/temp_x on the backbone, +-1e4*m_init on frozen spins), or
+ *               NULL for the instance's own h;
+ *   row_scaled  row_scaled[k] != 0 <=> row k of J is divided by temp_x (J_c[all_clusters,:] / temp_x),
+ *               or NULL for no scaling.
+ * The setting persists until changed. */
+int nlmc_set_phase(nlmc_replicas *reps, int r, const double *h_eff, const uint8_t *row_scaled, double temp_x);
+
+/* K1 sweep_replay -- MCMC with an injected random stream.
+ * Replaces MCMC: NMC/nmc.py:28-91 == NPT/npt.py:47-110, NPT/apt_preprocessor.py:33-74 ==
+ * NPT/apt_ICM.py:52-93.  For replica r and sweep s the kernel visits perm[r][s][0..n) in order and
+ * sets m[k] = sign(tanh(beta[r][s] * (sum_j J_kj m_j + h_k)) - 2*u[r][s][a] + 1), the row sum
+ * accumulated in CSR order exactly as scipy's csr_matvec does.
+ *   perm, u     [R][n_sweeps][n]   one np.random.permutation(n) and n np.random.rand() per sweep
+ *   beta        [R][n_sweeps]      beta_run of NMC/nmc.py:56-69
+ *   tanh_lut    optional [R][n_sweeps][2*lut_half+1]: tanh(beta*f) for integer fields f, computed by the
+ *               caller with numpy's tanh; used where the row is unscaled, J is integer and h_eff[k]==0
+ *               so that the decision is bit-equal to the reference's
+ *   out_M       optional [R][n_sweeps-record_from][n]: state after every sweep >= record_from
+ *               (the reference's M[:, jj] = m, NMC/nmc.py:89)
+ *   out_E       optional [R][n_sweeps]: E = -(m^T J m/2 + m^T h) after every sweep with the instance's
+ *               own J and h (NMC/nmc.py:386-387, NPT/npt.py:40-43, NPT/apt_preprocessor.py:107-110) */
+int nlmc_sweep_replay(nlmc_replicas *reps, int n_sweeps, const int32_t *perm, const double *u,
+                      const double *beta, const double *tanh_lut, int lut_half,
+                      int8_t *out_M, int record_from, double *out_E);
+
+/* K4 energy_csr -- E = -(m^T J m / 2 + m^T h).
+ * Replaces the energy loops NMC/nmc.py:386-387,496; NPT/npt.py:31-45,657-658;
+ * NPT/apt_preprocessor.py:107-110; NPT/apt_ICM.py:36-50,262-263. */
+int nlmc_energy(nlmc_replicas *reps, double *out_E /*[R]*/);
+int nlmc_energy_states(nlmc_instance *inst, int n_states, const int8_t *states /*[n_states][n]*/,
+                       double *out_E /*[n_states]*/);
+
+/* ---- K5 lbp -- loopy belief propagation of the NMC backbone search -----------------------------
+ * Replaces LoopyBeliefPropagation (NMC/nmc.py:168-228 == NPT/npt.py:204-264) as called by
+ * LBP_convexified (NMC/nmc.py:93-166): messages live on the stored entries of J and are warm-started
+ * from one lambda to the next.  The lambda schedule, the divergence rules (nmc.py:142-161) and
+ * find_clusters (nmc.py:257-318) stay on the host (nlmc_b200/nmc_core.py): they are a few scalar
+ * comparisons and set operations per call.
+ *   nlmc_lbp_reset   u_msgs = J * m_star, h_msgs = 0                       (nmc.py:128-129)
+ *   nlmc_lbp_epsilon epsilon_i = |h_i| + sum_j |J_ij|                      (nmc.py:353)
+ *   nlmc_lbp_step    one LoopyBeliefPropagation call with h + lambda*m_star*epsilon (nmc.py:133-139);
+ *                    out_marginal[n] = tanh(beta*(h_lambda + sum_k u[k,i])) (nmc.py:216),
+ *                    *out_iteration = the reference's `iteration` on exit (max_iter-1 <=> "diverged") */
+typedef struct nlmc_lbp nlmc_lbp;
+int nlmc_lbp_create(nlmc_instance *inst, nlmc_lbp **out);
+int nlmc_lbp_destroy(nlmc_lbp *lbp);
+int nlmc_lbp_epsilon(nlmc_lbp *lbp, double *out_eps /*[n]*/);
+int nlmc_lbp_reset(nlmc_lbp *lbp, const double *m_star /*[n]*/);
+int nlmc_lbp_step(nlmc_lbp *lbp, double lambda, double beta, double tol, int max_iter,
+                  double *out_marginal /*[n] or NULL*/, int *out_iteration);
+
+/* ---- K7 icm_components -- Houdayer iso-cluster identification ---------------------------------
+ * Replaces find_disagreement_clusters (NPT/apt_ICM.py:116-143) for n_pairs pairs of states at once:
+ * connected components of the subgraph induced on {i : s1[i]*s2[i] == -1}, adjacency J != 0.
+ * out_labels[p][i] = position of i's cluster in the reference's `clusters` list (clusters ordered by
+ * their smallest site index) or -1 where the states agree; out_n_clusters[p] = len(clusters). */
+int nlmc_icm_clusters(nlmc_instance *inst, int n_pairs, const int8_t *s1 /*[n_pairs][n]*/,
+                      const int8_t *s2 /*[n_pairs][n]*/, int32_t *out_labels /*[n_pairs][n]*/,
+                      int32_t *out_n_clusters /*[n_pairs]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLMC_B200_H */

@@ -1,0 +1,201 @@
+// nlmc_api.cu -- handle management of the C ABI (instances, replicas) and error reporting.
+#include <cmath>
+
+#include "nlmc_common.cuh"
+
+namespace nlmc {
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace nlmc
+
+extern "C" {
+
+const char *nlmc_last_error(void) { return nlmc::g_err; }
+
+int nlmc_version(void) { return 100; }
+
+int nlmc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int nlmc_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor,
+                     uint64_t *free_bytes, uint64_t *total_bytes) {
+    cudaDeviceProp p;
+    NLMC_CUDA(cudaGetDeviceProperties(&p, device));
+    if (name && name_len > 0) {
+        strncpy(name, p.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (free_bytes || total_bytes) {
+        size_t f = 0, t = 0;
+        NLMC_CUDA(cudaSetDevice(device));
+        NLMC_CUDA(cudaMemGetInfo(&f, &t));
+        if (free_bytes) *free_bytes = f;
+        if (total_bytes) *total_bytes = t;
+    }
+    return NLMC_OK;
+}
+
+int nlmc_instance_create(int n, const int32_t *row_ptr, const int32_t *col, const double *val,
+                         const double *h, int device, nlmc_instance **out) {
+    NLMC_REQUIRE(out != nullptr, "nlmc_instance_create: out is NULL");
+    *out = nullptr;
+    NLMC_REQUIRE(n > 0 && row_ptr && h, "nlmc_instance_create: n must be > 0 and row_ptr/h non-NULL");
+    NLMC_REQUIRE(row_ptr[0] == 0, "nlmc_instance_create: row_ptr[0] must be 0");
+    const int nnz = row_ptr[n];
+    NLMC_REQUIRE(nnz >= 0 && (nnz == 0 || (col && val)), "nlmc_instance_create: col/val missing");
+    int max_deg = 0;
+    bool integer_j = true;
+    for (int i = 0; i < n; ++i) {
+        NLMC_REQUIRE(row_ptr[i + 1] >= row_ptr[i], "nlmc_instance_create: row_ptr not monotone at row %d", i);
+        max_deg = std::max(max_deg, row_ptr[i + 1] - row_ptr[i]);
+    }
+    for (int p = 0; p < nnz; ++p) {
+        NLMC_REQUIRE(col[p] >= 0 && col[p] < n, "nlmc_instance_create: column index out of range at entry %d", p);
+        if (val[p] != std::floor(val[p]) || std::fabs(val[p]) > 1e6) integer_j = false;
+    }
+    NLMC_CUDA(cudaSetDevice(device));
+    auto *I = new nlmc_instance();
+    I->device = device;
+    I->n = n;
+    I->nnz = nnz;
+    I->max_deg = max_deg;
+    I->integer_j = integer_j;
+    I->h_row_ptr.assign(row_ptr, row_ptr + n + 1);
+    I->h_col.assign(col, col + nnz);
+    I->h_val.assign(val, val + nnz);
+    I->h_h.assign(h, h + n);
+    auto fail = [&](void) {
+        nlmc_instance_destroy(I);
+        return NLMC_ERR_CUDA;
+    };
+    const size_t nz = (size_t)std::max(nnz, 1);
+    if (cudaStreamCreateWithFlags(&I->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&I->row_ptr, sizeof(int32_t) * (size_t)(n + 1)) != cudaSuccess ||
+        cudaMalloc(&I->col, sizeof(int32_t) * nz) != cudaSuccess ||
+        cudaMalloc(&I->val, sizeof(double) * nz) != cudaSuccess ||
+        cudaMalloc(&I->h, sizeof(double) * (size_t)n) != cudaSuccess ||
+        cudaMemcpy(I->row_ptr, row_ptr, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
+        (nnz && cudaMemcpy(I->col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice) != cudaSuccess) ||
+        (nnz && cudaMemcpy(I->val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice) != cudaSuccess) ||
+        cudaMemcpy(I->h, h, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
+        nlmc::set_error("nlmc_instance_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail();
+    }
+    *out = I;
+    return NLMC_OK;
+}
+
+int nlmc_instance_destroy(nlmc_instance *I) {
+    if (!I) return NLMC_OK;
+    cudaSetDevice(I->device);
+    if (I->row_ptr) cudaFree(I->row_ptr);
+    if (I->col) cudaFree(I->col);
+    if (I->val) cudaFree(I->val);
+    if (I->h) cudaFree(I->h);
+    if (I->rev) cudaFree(I->rev);
+    if (I->stream) cudaStreamDestroy(I->stream);
+    delete I;
+    return NLMC_OK;
+}
+
+int nlmc_instance_n(const nlmc_instance *I) { return I ? I->n : NLMC_ERR_ARG; }
+int nlmc_instance_is_integer(const nlmc_instance *I) { return I ? (I->integer_j ? 1 : 0) : NLMC_ERR_ARG; }
+
+int nlmc_replicas_create(nlmc_instance *I, int R, const int8_t *init_spins, nlmc_replicas **out) {
+    NLMC_REQUIRE(out != nullptr, "nlmc_replicas_create: out is NULL");
+    *out = nullptr;
+    NLMC_REQUIRE(I && R > 0, "nlmc_replicas_create: instance NULL or n_replicas <= 0");
+    NLMC_CUDA(cudaSetDevice(I->device));
+    auto *P = new nlmc_replicas();
+    P->inst = I;
+    P->R = R;
+    P->h_flags.assign((size_t)R, 0);
+    P->h_temp_x.assign((size_t)R, 1.0);
+    const size_t bytes = (size_t)R * (size_t)I->n;
+    if (cudaMalloc(&P->spins, bytes) != cudaSuccess || cudaMalloc(&P->flags, sizeof(int32_t) * (size_t)R) != cudaSuccess ||
+        cudaMalloc(&P->temp_x, sizeof(double) * (size_t)R) != cudaSuccess ||
+        cudaMemset(P->flags, 0, sizeof(int32_t) * (size_t)R) != cudaSuccess ||
+        cudaMemcpy(P->temp_x, P->h_temp_x.data(), sizeof(double) * (size_t)R, cudaMemcpyHostToDevice) != cudaSuccess ||
+        (init_spins ? cudaMemcpy(P->spins, init_spins, bytes, cudaMemcpyHostToDevice)
+                    : cudaMemset(P->spins, 1, bytes)) != cudaSuccess) {
+        nlmc::set_error("nlmc_replicas_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        nlmc_replicas_destroy(P);
+        return NLMC_ERR_CUDA;
+    }
+    *out = P;
+    return NLMC_OK;
+}
+
+int nlmc_replicas_destroy(nlmc_replicas *P) {
+    if (!P) return NLMC_OK;
+    cudaSetDevice(P->inst->device);
+    if (P->spins) cudaFree(P->spins);
+    if (P->h_eff) cudaFree(P->h_eff);
+    if (P->row_scaled) cudaFree(P->row_scaled);
+    if (P->flags) cudaFree(P->flags);
+    if (P->temp_x) cudaFree(P->temp_x);
+    P->s_perm.release();
+    P->s_u.release();
+    P->s_beta.release();
+    P->s_lut.release();
+    P->s_M.release();
+    P->s_E.release();
+    delete P;
+    return NLMC_OK;
+}
+
+int nlmc_set_spins(nlmc_replicas *P, int first, int count, const int8_t *spins) {
+    NLMC_REQUIRE(P && spins && first >= 0 && count >= 0 && first + count <= P->R, "nlmc_set_spins: bad range");
+    NLMC_CUDA(cudaSetDevice(P->inst->device));
+    const size_t n = (size_t)P->inst->n;
+    NLMC_CUDA(cudaMemcpy(P->spins + (size_t)first * n, spins, (size_t)count * n, cudaMemcpyHostToDevice));
+    return NLMC_OK;
+}
+
+int nlmc_get_spins(nlmc_replicas *P, int first, int count, int8_t *out) {
+    NLMC_REQUIRE(P && out && first >= 0 && count >= 0 && first + count <= P->R, "nlmc_get_spins: bad range");
+    NLMC_CUDA(cudaSetDevice(P->inst->device));
+    const size_t n = (size_t)P->inst->n;
+    NLMC_CUDA(cudaStreamSynchronize(P->inst->stream));
+    NLMC_CUDA(cudaMemcpy(out, P->spins + (size_t)first * n, (size_t)count * n, cudaMemcpyDeviceToHost));
+    return NLMC_OK;
+}
+
+int nlmc_set_phase(nlmc_replicas *P, int r, const double *h_eff, const uint8_t *row_scaled, double temp_x) {
+    NLMC_REQUIRE(P && r >= 0 && r < P->R, "nlmc_set_phase: replica index out of range");
+    NLMC_REQUIRE(!row_scaled || temp_x != 0.0, "nlmc_set_phase: temp_x must be non-zero when rows are scaled");
+    NLMC_CUDA(cudaSetDevice(P->inst->device));
+    const size_t n = (size_t)P->inst->n;
+    int flags = 0;
+    if (h_eff) {
+        if (!P->h_eff) NLMC_CUDA(cudaMalloc(&P->h_eff, sizeof(double) * n * (size_t)P->R));
+        NLMC_CUDA(cudaMemcpy(P->h_eff + (size_t)r * n, h_eff, sizeof(double) * n, cudaMemcpyHostToDevice));
+        flags |= 1;
+    }
+    if (row_scaled) {
+        if (!P->row_scaled) NLMC_CUDA(cudaMalloc(&P->row_scaled, n * (size_t)P->R));
+        NLMC_CUDA(cudaMemcpy(P->row_scaled + (size_t)r * n, row_scaled, n, cudaMemcpyHostToDevice));
+        flags |= 2;
+    }
+    P->h_flags[(size_t)r] = flags;
+    P->h_temp_x[(size_t)r] = temp_x;
+    NLMC_CUDA(cudaMemcpy(P->flags + r, &flags, sizeof(int32_t), cudaMemcpyHostToDevice));
+    NLMC_CUDA(cudaMemcpy(P->temp_x + r, &temp_x, sizeof(double), cudaMemcpyHostToDevice));
+    return NLMC_OK;
+}
+
+}  // extern "C"

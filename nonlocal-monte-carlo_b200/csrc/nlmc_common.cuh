@@ -1,0 +1,103 @@
+// nlmc_common.cuh -- shared host/device helpers and the handle layouts behind include/nlmc_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "nlmc_b200.h"
+
+namespace nlmc {
+
+void set_error(const char *fmt, ...);
+
+#define NLMC_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            ::nlmc::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return NLMC_ERR_CUDA;                                                                    \
+        }                                                                                            \
+    } while (0)
+
+#define NLMC_REQUIRE(cond, ...)                \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::nlmc::set_error(__VA_ARGS__);    \
+            return NLMC_ERR_ARG;               \
+        }                                      \
+    } while (0)
+
+// Device scratch buffer that only grows (staging for host arrays passed through the C ABI).
+struct Scratch {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return NLMC_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        NLMC_CUDA(cudaMalloc(&ptr, bytes));
+        cap = bytes;
+        return NLMC_OK;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(ptr); }
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace nlmc
+
+// ------------------------------------------------------------------------------------------------
+// handle layouts (opaque to callers)
+// ------------------------------------------------------------------------------------------------
+struct nlmc_instance {
+    int device = 0;
+    int n = 0;
+    int nnz = 0;
+    int max_deg = 0;
+    bool integer_j = false;   // every stored value is an integer -> row sums exact in any order
+    bool symmetric = false;   // pattern symmetric (rev index available)
+    int32_t *row_ptr = nullptr;  // [n+1]
+    int32_t *col = nullptr;      // [nnz]
+    double *val = nullptr;       // [nnz]
+    double *h = nullptr;         // [n]
+    int32_t *rev = nullptr;      // [nnz] index of the transposed entry (built on demand for LBP)
+    cudaStream_t stream = nullptr;
+    // host mirrors (colouring, validation, MSC packing)
+    std::vector<int32_t> h_row_ptr, h_col;
+    std::vector<double> h_val, h_h;
+};
+
+struct nlmc_replicas {
+    nlmc_instance *inst = nullptr;
+    int R = 0;
+    int8_t *spins = nullptr;        // [R][n]
+    double *h_eff = nullptr;        // [R][n], lazily allocated by nlmc_set_phase
+    uint8_t *row_scaled = nullptr;  // [R][n], lazily allocated by nlmc_set_phase
+    int32_t *flags = nullptr;       // [R] bit0: h_eff row valid, bit1: row_scaled row valid
+    double *temp_x = nullptr;       // [R]
+    std::vector<int32_t> h_flags;
+    std::vector<double> h_temp_x;
+    nlmc::Scratch s_perm, s_u, s_beta, s_lut, s_M, s_E;
+};

@@ -1,0 +1,350 @@
+// nlmc_lbp.cu -- K5: loopy belief propagation of the NMC backbone search on the edges of J.
+//
+// Replaces LoopyBeliefPropagation (NMC/nmc.py:168-228 == NPT/npt.py:204-264), called once per
+// lambda by LBP_convexified (nmc.py:131-161).  The reference keeps dense N x N message matrices;
+// off the edges of J they are trivial (u = 0, h_msgs[i,j] = total_i), so the kernel keeps one
+// message per stored entry of J plus the common off-edge value tot[i] of each h_msgs row, which
+// still enters the reference's convergence maxima (nmc.py:208-209) for rows with an off-diagonal
+// zero.  One LBP call = ONE cooperative launch: the Jacobi iterations, the two relative-change
+// maxima and the convergence test all stay on the device, separated by grid syncs.
+//
+// Bit-level fidelity: the additions reproduce numpy's association order (np.sum over a strided
+// column is pairwise over all N entries, np.sum(axis=0) is sequential; zeros do not change a
+// partial sum so only stored entries are visited).  tanh/atanh are CUDA's, which differ from
+// numpy's in the last place on some arguments; since the reference's stopping rule
+// (tolerance = machine epsilon) waits for an exact floating-point fixed point, iteration counts
+// can differ from the reference's where convergence is marginal -- see DESIGN.md "LBP parity".
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "nlmc_common.cuh"
+
+namespace cg = cooperative_groups;
+
+struct nlmc_lbp {
+    nlmc_instance *inst = nullptr;
+    int32_t *rev = nullptr;     // [nnz] entry (j,i) for entry (i,j)
+    double *u[2] = {nullptr, nullptr};  // [nnz] u messages, double buffered
+    double *hm = nullptr;       // [nnz] h messages
+    double *tot = nullptr;      // [n]   off-edge value of each h_msgs row
+    double *eps = nullptr;      // [n]   |h_i| + sum_j |J_ij|   (nmc.py:353)
+    double *mstar = nullptr;    // [n]
+    double *marg = nullptr;     // [n]
+    uint8_t *offedge = nullptr; // [n]   row has an off-diagonal zero
+    unsigned long long *red = nullptr;  // [4] du, su, dh, sh as ordered bit patterns
+    int *iter_out = nullptr;
+    int cur = 0;
+    int grid = 0;
+};
+
+namespace nlmc {
+
+// numpy's DOUBLE_pairwise_sum over a dense vector of length n whose only non-zeros are at the
+// sorted positions pos[0..cnt) with values v[...].  Explicit-stack post-order walk of numpy's
+// recursion; ranges without stored entries are pruned (their sum is 0 and x + 0 == x).
+template <typename GetV>
+__device__ double pairwise_sparse(int n, const int32_t *__restrict__ pos, int cnt, GetV v) {
+    int st_lo[32], st_n[32];
+    double st_acc[32];
+    int8_t st_stage[32];
+    int sp = 0, cur = 0;
+    st_lo[0] = 0; st_n[0] = n; st_stage[0] = 0; st_acc[0] = 0.0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        const int lo = st_lo[sp], len = st_n[sp];
+        if (st_stage[sp] == 0) {
+            if (cur >= cnt || pos[cur] >= lo + len) {  // no stored entry in range
+                ret = 0.0; --sp; continue;
+            }
+            if (len < 8) {
+                double res = 0.0;
+                while (cur < cnt && pos[cur] < lo + len) { res = __dadd_rn(res, v(cur)); ++cur; }
+                ret = res; --sp; continue;
+            }
+            if (len <= 128) {
+                double r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                const int body_end = lo + len - (len % 8);
+                while (cur < cnt && pos[cur] < body_end) {
+                    const int j = (pos[cur] - lo) & 7;
+                    const double x = v(cur);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) if (q == j) r[q] = __dadd_rn(r[q], x);
+                    ++cur;
+                }
+                double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                       __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+                while (cur < cnt && pos[cur] < lo + len) { res = __dadd_rn(res, v(cur)); ++cur; }
+                ret = res; --sp; continue;
+            }
+            int n2 = len / 2;
+            n2 -= n2 % 8;
+            st_stage[sp] = 1;
+            ++sp;
+            st_lo[sp] = lo; st_n[sp] = n2; st_stage[sp] = 0;
+            continue;
+        }
+        if (st_stage[sp] == 1) {  // left child done
+            int n2 = len / 2;
+            n2 -= n2 % 8;
+            st_acc[sp] = ret;
+            st_stage[sp] = 2;
+            ++sp;
+            st_lo[sp] = lo + n2; st_n[sp] = len - n2; st_stage[sp] = 0;
+            continue;
+        }
+        ret = __dadd_rn(st_acc[sp], ret);  // both children done
+        --sp;
+    }
+    return ret;
+}
+
+__device__ __forceinline__ double atanh_saturated(double x) {  // nmc.py:230-255 (tanh(19.06) == 1.0)
+    const double e = 2.220446049250313e-16;
+    x = fmin(fmax(x, -1.0 + e), 1.0 - e);
+    return atanh(x);
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(unsigned long long *addr, double v) {
+    // non-negative doubles order like their bit patterns; NaN (0x7ff8...) sorts above everything
+    atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+
+__device__ __forceinline__ void block_max2(double &a, double &b, double *sm) {
+    a = warp_max(a);
+    b = warp_max(b);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) { sm[w] = a; sm[32 + w] = b; }
+    __syncthreads();
+    if (w == 0) {
+        a = lane < nw ? sm[lane] : 0.0;
+        b = lane < nw ? sm[32 + lane] : 0.0;
+        a = warp_max(a);
+        b = warp_max(b);
+    }
+}
+
+struct LbpArgs {
+    int n, nnz, max_iter;
+    double beta, lambda, tol;
+    const int32_t *rp, *ci, *rev;
+    const double *val, *h, *eps, *mstar;
+    double *u0, *u1, *hm, *tot, *marg;
+    const uint8_t *offedge;
+    unsigned long long *red;
+    int *iter_out;  // [0] iteration on exit, [1] index of the buffer holding the final u
+};
+
+__global__ void __launch_bounds__(256) lbp_kernel(LbpArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[64];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    const double inv_beta = __ddiv_rn(1.0, a.beta);
+    double *u_old = a.u0, *u_new = a.u1;
+    int iteration = 0;
+    bool converged = false;
+    for (iteration = 0; iteration < a.max_iter; ++iteration) {
+        if (tid == 0) { a.red[0] = 0ull; a.red[1] = 0ull; a.red[2] = 0ull; a.red[3] = 0ull; }
+        grid.sync();
+        // ---- gather: total_i = hl_i + sum_k u[k,i];  hm[i,j] = total_i - u[j,i]   (nmc.py:200-203)
+        double dh = 0.0, sh = 0.0;
+        for (int i = tid; i < a.n; i += nthreads) {
+            const int b = a.rp[i], cnt = a.rp[i + 1] - b;
+            const double hl = __dadd_rn(a.h[i], __dmul_rn(__dmul_rn(a.lambda, a.mstar[i]), a.eps[i]));  // nmc.py:133-134
+            const double total = __dadd_rn(hl, pairwise_sparse(a.n, a.ci + b, cnt,
+                                                             [&](int q) { return u_old[a.rev[b + q]]; }));
+            for (int q = 0; q < cnt; ++q) {
+                const double hnew = (a.ci[b + q] == i) ? 0.0 : __dsub_rn(total, u_old[a.rev[b + q]]);
+                const double hold = a.hm[b + q];
+                dh = fmax(dh, fabs(__dsub_rn(hnew, hold)));
+                sh = fmax(sh, __dadd_rn(fabs(hnew), fabs(hold)));
+                a.hm[b + q] = hnew;
+            }
+            if (a.offedge[i]) {
+                const double told = a.tot[i];
+                dh = fmax(dh, fabs(__dsub_rn(total, told)));
+                sh = fmax(sh, __dadd_rn(fabs(total), fabs(told)));
+            }
+            a.tot[i] = total;
+        }
+        block_max2(dh, sh, sm);
+        if (threadIdx.x == 0) { atomic_max_nonneg(a.red + 2, dh); atomic_max_nonneg(a.red + 3, sh); }
+        grid.sync();
+        // ---- update: u = (1/beta) * atanh_sat(tanh(beta J) * tanh(beta h_msgs))       (nmc.py:205)
+        double du = 0.0, su = 0.0;
+        for (int p = tid; p < a.nnz; p += nthreads) {
+            const double tj = tanh(__dmul_rn(a.beta, a.val[p]));
+            const double th = tanh(__dmul_rn(a.beta, a.hm[p]));
+            const double un = __dmul_rn(inv_beta, atanh_saturated(__dmul_rn(tj, th)));
+            const double uo = u_old[p];
+            du = fmax(du, fabs(__dsub_rn(un, uo)));
+            su = fmax(su, __dadd_rn(fabs(un), fabs(uo)));
+            u_new[p] = un;
+        }
+        block_max2(du, su, sm);
+        if (threadIdx.x == 0) { atomic_max_nonneg(a.red + 0, du); atomic_max_nonneg(a.red + 1, su); }
+        grid.sync();
+        double *t = u_old; u_old = u_new; u_new = t;  // u_old now holds the newest messages
+        const double gdu = __longlong_as_double((long long)a.red[0]), gsu = __longlong_as_double((long long)a.red[1]);
+        const double gdh = __longlong_as_double((long long)a.red[2]), gsh = __longlong_as_double((long long)a.red[3]);
+        const double u_change = __ddiv_rn(gdu, gsu), h_change = __ddiv_rn(gdh, gsh);  // 0/0 = nan -> not converged
+        converged = (u_change < a.tol) && (h_change < a.tol);  // nmc.py:212
+        if (converged) break;
+        grid.sync();  // everyone has read red[] before the next iteration clears it
+    }
+    if (!converged) iteration = a.max_iter - 1;  // python loop variable after exhaustion
+    // marginal_i = tanh(beta * (hl_i + sum_k u[k,i])), rows accumulated in order   (nmc.py:216)
+    for (int i = tid; i < a.n; i += nthreads) {
+        const double hl = __dadd_rn(a.h[i], __dmul_rn(__dmul_rn(a.lambda, a.mstar[i]), a.eps[i]));
+        double acc = 0.0;
+        for (int p = a.rp[i]; p < a.rp[i + 1]; ++p) acc = __dadd_rn(acc, u_old[a.rev[p]]);
+        a.marg[i] = tanh(__dmul_rn(a.beta, __dadd_rn(hl, acc)));
+    }
+    if (tid == 0) { a.iter_out[0] = iteration; a.iter_out[1] = (u_old == a.u0) ? 0 : 1; }
+}
+
+// u = J * m_star (nmc.py:129), h_msgs = 0 (nmc.py:128)
+__global__ void lbp_reset_kernel(int n, int nnz, const int32_t *ci, const double *val, const double *mstar,
+                                 double *u, double *hm, double *tot) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int p = tid; p < nnz; p += nt) { u[p] = __dmul_rn(val[p], mstar[ci[p]]); hm[p] = 0.0; }
+    for (int i = tid; i < n; i += nt) tot[i] = 0.0;
+}
+
+// epsilon_i = |h_i| + np.sum(np.abs(J), axis=1)[i]  (pairwise along the contiguous row, nmc.py:353)
+__global__ void lbp_eps_kernel(int n, const int32_t *rp, const int32_t *ci, const double *val, const double *h,
+                               double *eps, uint8_t *offedge) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = rp[i], cnt = rp[i + 1] - b;
+    const double s = pairwise_sparse(n, ci + b, cnt, [&](int q) { return fabs(val[b + q]); });
+    eps[i] = __dadd_rn(fabs(h[i]), s);
+    int stored_off = 0;
+    for (int q = 0; q < cnt; ++q) stored_off += (ci[b + q] != i);
+    offedge[i] = stored_off < n - 1;
+}
+
+}  // namespace nlmc
+
+extern "C" {
+
+int nlmc_lbp_destroy(nlmc_lbp *L) {
+    if (!L) return NLMC_OK;
+    cudaSetDevice(L->inst->device);
+    void *ptrs[] = {L->rev, L->u[0], L->u[1], L->hm, L->tot, L->eps, L->mstar, L->marg, L->offedge, L->red, L->iter_out};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete L;
+    return NLMC_OK;
+}
+
+int nlmc_lbp_create(nlmc_instance *I, nlmc_lbp **out) {
+    using namespace nlmc;
+    NLMC_REQUIRE(I && out, "nlmc_lbp_create: NULL argument");
+    *out = nullptr;
+    const int n = I->n, nnz = I->nnz;
+    // reverse-entry index (requires a symmetric sparsity pattern, as the reference's J is)
+    std::vector<int32_t> rev((size_t)std::max(nnz, 1));
+    for (int i = 0; i < n; ++i) {
+        for (int p = I->h_row_ptr[i]; p < I->h_row_ptr[i + 1]; ++p) {
+            const int j = I->h_col[p];
+            const int32_t *b = I->h_col.data() + I->h_row_ptr[j], *e = I->h_col.data() + I->h_row_ptr[j + 1];
+            const int32_t *it = std::lower_bound(b, e, i);
+            if (it == e || *it != i) {  // unsorted rows: fall back to a linear scan
+                it = std::find(b, e, i);
+                NLMC_REQUIRE(it != e, "nlmc_lbp_create: J must have a symmetric sparsity pattern (entry %d,%d)", i, j);
+            }
+            rev[(size_t)p] = (int32_t)(it - I->h_col.data());
+        }
+    }
+    NLMC_CUDA(cudaSetDevice(I->device));
+    auto *L = new nlmc_lbp();
+    L->inst = I;
+    const size_t nz = (size_t)std::max(nnz, 1);
+    bool ok = cudaMalloc(&L->rev, sizeof(int32_t) * nz) == cudaSuccess &&
+              cudaMalloc(&L->u[0], sizeof(double) * nz) == cudaSuccess &&
+              cudaMalloc(&L->u[1], sizeof(double) * nz) == cudaSuccess &&
+              cudaMalloc(&L->hm, sizeof(double) * nz) == cudaSuccess &&
+              cudaMalloc(&L->tot, sizeof(double) * (size_t)n) == cudaSuccess &&
+              cudaMalloc(&L->eps, sizeof(double) * (size_t)n) == cudaSuccess &&
+              cudaMalloc(&L->mstar, sizeof(double) * (size_t)n) == cudaSuccess &&
+              cudaMalloc(&L->marg, sizeof(double) * (size_t)n) == cudaSuccess &&
+              cudaMalloc(&L->offedge, (size_t)n) == cudaSuccess &&
+              cudaMalloc(&L->red, sizeof(unsigned long long) * 4) == cudaSuccess &&
+              cudaMalloc(&L->iter_out, sizeof(int) * 2) == cudaSuccess &&
+              cudaMemcpy(L->rev, rev.data(), sizeof(int32_t) * nz, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        set_error("nlmc_lbp_create: CUDA allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        nlmc_lbp_destroy(L);
+        return NLMC_ERR_CUDA;
+    }
+    lbp_eps_kernel<<<(n + 127) / 128, 128, 0, I->stream>>>(n, I->row_ptr, I->col, I->val, I->h, L->eps, L->offedge);
+    NLMC_CUDA(cudaGetLastError());
+    // cooperative grid: as many CTAs as are co-resident, capped by the work
+    int dev_sms = 0, per_sm = 0, coop = 0;
+    NLMC_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, I->device));
+    if (!coop) {
+        set_error("nlmc_lbp_create: device does not support cooperative launch");
+        nlmc_lbp_destroy(L);
+        return NLMC_ERR_UNSUPPORTED;
+    }
+    NLMC_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, I->device));
+    NLMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_kernel, 256, 0));
+    const int want = std::max(1, (std::max(nnz, n) + 255) / 256);
+    L->grid = std::max(1, std::min(want, dev_sms * std::max(per_sm, 1)));
+    NLMC_CUDA(cudaStreamSynchronize(I->stream));
+    *out = L;
+    return NLMC_OK;
+}
+
+int nlmc_lbp_epsilon(nlmc_lbp *L, double *out_eps) {
+    NLMC_REQUIRE(L && out_eps, "nlmc_lbp_epsilon: NULL argument");
+    NLMC_CUDA(cudaSetDevice(L->inst->device));
+    NLMC_CUDA(cudaMemcpy(out_eps, L->eps, sizeof(double) * (size_t)L->inst->n, cudaMemcpyDeviceToHost));
+    return NLMC_OK;
+}
+
+int nlmc_lbp_reset(nlmc_lbp *L, const double *m_star) {
+    using namespace nlmc;
+    NLMC_REQUIRE(L && m_star, "nlmc_lbp_reset: NULL argument");
+    nlmc_instance *I = L->inst;
+    NLMC_CUDA(cudaSetDevice(I->device));
+    NLMC_CUDA(cudaMemcpyAsync(L->mstar, m_star, sizeof(double) * (size_t)I->n, cudaMemcpyHostToDevice, I->stream));
+    L->cur = 0;
+    lbp_reset_kernel<<<std::max(1, std::min(1024, (std::max(I->nnz, I->n) + 255) / 256)), 256, 0, I->stream>>>(
+        I->n, I->nnz, I->col, I->val, L->mstar, L->u[0], L->hm, L->tot);
+    NLMC_CUDA(cudaGetLastError());
+    NLMC_CUDA(cudaStreamSynchronize(I->stream));
+    return NLMC_OK;
+}
+
+int nlmc_lbp_step(nlmc_lbp *L, double lambda, double beta, double tol, int max_iter, double *out_marginal,
+                  int *out_iteration) {
+    using namespace nlmc;
+    NLMC_REQUIRE(L && out_iteration, "nlmc_lbp_step: NULL argument");
+    NLMC_REQUIRE(max_iter >= 1, "nlmc_lbp_step: max_iterations must be >= 1");
+    nlmc_instance *I = L->inst;
+    NLMC_CUDA(cudaSetDevice(I->device));
+    LbpArgs a;
+    a.n = I->n; a.nnz = I->nnz; a.max_iter = max_iter;
+    a.beta = beta; a.lambda = lambda; a.tol = tol;
+    a.rp = I->row_ptr; a.ci = I->col; a.rev = L->rev;
+    a.val = I->val; a.h = I->h; a.eps = L->eps; a.mstar = L->mstar;
+    a.u0 = L->u[L->cur]; a.u1 = L->u[1 - L->cur];
+    a.hm = L->hm; a.tot = L->tot; a.marg = L->marg; a.offedge = L->offedge;
+    a.red = L->red; a.iter_out = L->iter_out;
+    void *args[] = {&a};
+    NLMC_CUDA(cudaLaunchCooperativeKernel((void *)lbp_kernel, dim3((unsigned)L->grid), dim3(256), args, 0, I->stream));
+    int res[2] = {0, 0};
+    NLMC_CUDA(cudaMemcpyAsync(res, L->iter_out, sizeof(res), cudaMemcpyDeviceToHost, I->stream));
+    if (out_marginal)
+        NLMC_CUDA(cudaMemcpyAsync(out_marginal, L->marg, sizeof(double) * (size_t)I->n, cudaMemcpyDeviceToHost, I->stream));
+    NLMC_CUDA(cudaStreamSynchronize(I->stream));
+    *out_iteration = res[0];
+    if (res[1] == 1) L->cur = 1 - L->cur;  // the newest messages ended up in the other buffer
+    return NLMC_OK;
+}
+
+}  // extern "C"

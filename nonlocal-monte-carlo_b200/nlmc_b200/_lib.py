@@ -1,0 +1,248 @@
+"""ctypes binding of libnlmc_b200.so (the C ABI declared in include/nlmc_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is usable, every
+entry point raises.  The library is built in-tree by ``nonlocal-monte-carlo_b200/build.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnlmc_b200.so")
+_lib = None
+
+
+class NlmcError(RuntimeError):
+    pass
+
+
+_i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f64 = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i8 = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
+_u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_u32 = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+_int = C.c_int
+_dbl = C.c_double
+_u64 = C.c_uint64
+
+# name -> (argtypes); every function returns int except where noted below
+_SIGNATURES = {
+    "nlmc_version": [],
+    "nlmc_device_count": [],
+    "nlmc_device_info": [_int, C.c_char_p, _int, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int),
+                         C.POINTER(_u64), C.POINTER(_u64)],
+    "nlmc_instance_create": [_int, _i32, _i32, _f64, _f64, _int, C.POINTER(_vp)],
+    "nlmc_instance_destroy": [_vp],
+    "nlmc_instance_n": [_vp],
+    "nlmc_instance_is_integer": [_vp],
+    "nlmc_replicas_create": [_vp, _int, _vp, C.POINTER(_vp)],
+    "nlmc_replicas_destroy": [_vp],
+    "nlmc_set_spins": [_vp, _int, _int, _i8],
+    "nlmc_get_spins": [_vp, _int, _int, _i8],
+    "nlmc_set_phase": [_vp, _int, _vp, _vp, _dbl],
+    "nlmc_sweep_replay": [_vp, _int, _i32, _f64, _f64, _vp, _int, _vp, _int, _vp],
+    "nlmc_energy": [_vp, _f64],
+    "nlmc_energy_states": [_vp, _int, _i8, _f64],
+    "nlmc_lbp_create": [_vp, C.POINTER(_vp)],
+    "nlmc_lbp_destroy": [_vp],
+    "nlmc_lbp_epsilon": [_vp, _f64],
+    "nlmc_lbp_reset": [_vp, _f64],
+    "nlmc_lbp_step": [_vp, _dbl, _dbl, _dbl, _int, _vp, C.POINTER(_int)],
+    "nlmc_icm_clusters": [_vp, _int, _i8, _i8, _i32, _i32],
+}
+
+
+def exported_symbols():
+    """Names include/nlmc_b200.h declares (used by the CPU-side symbol test)."""
+    return ["nlmc_last_error"] + list(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NlmcError(f"{LIB_PATH} is missing: build it with `python nonlocal-monte-carlo_b200/build.py` "
+                            "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.nlmc_last_error.restype = C.c_char_p
+        L.nlmc_last_error.argtypes = []
+        for name, args in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = C.c_int
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc < 0:
+        msg = lib().nlmc_last_error().decode(errors="replace")
+        raise NlmcError(f"{what or 'nlmc call'} failed ({rc}): {msg}")
+    return rc
+
+
+def require_device(device: int = 0):
+    n = lib().nlmc_device_count()
+    if n <= device:
+        raise NlmcError(f"CUDA device {device} not available ({n} visible); nlmc_b200 has no CPU fallback")
+    return n
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Instance:
+    """Device-resident instance: normalised J in CSR (scipy csr_matrix order) and h."""
+
+    def __init__(self, rp, ci, val, h, device: int = 0):
+        require_device(device)
+        self.rp = np.ascontiguousarray(rp, dtype=np.int32)
+        self.ci = np.ascontiguousarray(ci, dtype=np.int32)
+        self.val = np.ascontiguousarray(val, dtype=np.float64)
+        self.h = np.ascontiguousarray(np.asarray(h, dtype=np.float64).reshape(-1))
+        self.n = len(self.rp) - 1
+        self.device = device
+        if len(self.h) != self.n:
+            raise ValueError(f"h has {len(self.h)} entries, J has {self.n} rows")
+        ci_arg = self.ci if len(self.ci) else np.zeros(1, np.int32)
+        val_arg = self.val if len(self.val) else np.zeros(1, np.float64)
+        handle = _vp()
+        check(lib().nlmc_instance_create(self.n, self.rp, ci_arg, val_arg, self.h, device, C.byref(handle)),
+              "nlmc_instance_create")
+        self._h = handle
+        self.is_integer = bool(lib().nlmc_instance_is_integer(self._h))
+
+    def energy_states(self, states) -> np.ndarray:
+        states = np.ascontiguousarray(states, dtype=np.int8).reshape(-1, self.n)
+        out = np.empty(states.shape[0], dtype=np.float64)
+        check(lib().nlmc_energy_states(self._h, states.shape[0], states, out), "nlmc_energy_states")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nlmc_instance_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Lbp:
+    """Device state of the LBP backbone search (K5) for one instance."""
+
+    def __init__(self, inst: Instance):
+        self.inst = inst
+        handle = _vp()
+        check(lib().nlmc_lbp_create(inst._h, C.byref(handle)), "nlmc_lbp_create")
+        self._h = handle
+
+    def epsilon(self) -> np.ndarray:
+        out = np.empty(self.inst.n, dtype=np.float64)
+        check(lib().nlmc_lbp_epsilon(self._h, out), "nlmc_lbp_epsilon")
+        return out
+
+    def reset(self, m_star):
+        m = np.ascontiguousarray(np.asarray(m_star, dtype=np.float64).reshape(-1))
+        check(lib().nlmc_lbp_reset(self._h, m), "nlmc_lbp_reset")
+
+    def step(self, lam: float, beta: float, tol: float, max_iter: int):
+        """One LoopyBeliefPropagation call; returns (marginal [n], iteration)."""
+        marg = np.empty(self.inst.n, dtype=np.float64)
+        it = _int(0)
+        check(lib().nlmc_lbp_step(self._h, float(lam), float(beta), float(tol), int(max_iter), marg.ctypes.data,
+                                  C.byref(it)), "nlmc_lbp_step")
+        return marg, it.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nlmc_lbp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def icm_clusters(inst: Instance, s1, s2):
+    """K7 for a batch of state pairs: returns (labels int32 [P][n], n_clusters int32 [P])."""
+    s1 = np.ascontiguousarray(s1, dtype=np.int8).reshape(-1, inst.n)
+    s2 = np.ascontiguousarray(s2, dtype=np.int8).reshape(-1, inst.n)
+    P = s1.shape[0]
+    labels = np.empty((P, inst.n), dtype=np.int32)
+    counts = np.empty(P, dtype=np.int32)
+    check(lib().nlmc_icm_clusters(inst._h, P, s1, s2, labels, counts), "nlmc_icm_clusters")
+    return labels, counts
+
+
+class Replicas:
+    """R int8 spin configurations of one instance on the device (exact-replay path)."""
+
+    def __init__(self, inst: Instance, n_replicas: int, init_spins=None):
+        self.inst = inst
+        self.R = int(n_replicas)
+        self.n = inst.n
+        init = None
+        if init_spins is not None:
+            init = np.ascontiguousarray(init_spins, dtype=np.int8).reshape(self.R, self.n)
+        handle = _vp()
+        check(lib().nlmc_replicas_create(inst._h, self.R, _ptr(init), C.byref(handle)), "nlmc_replicas_create")
+        self._h = handle
+
+    def set_spins(self, spins, first: int = 0):
+        spins = np.ascontiguousarray(spins, dtype=np.int8).reshape(-1, self.n)
+        check(lib().nlmc_set_spins(self._h, first, spins.shape[0], spins), "nlmc_set_spins")
+
+    def get_spins(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.R - first if count is None else count
+        out = np.empty((count, self.n), dtype=np.int8)
+        check(lib().nlmc_get_spins(self._h, first, count, out), "nlmc_get_spins")
+        return out
+
+    def set_phase(self, r: int, h_eff=None, row_scaled=None, temp_x: float = 1.0):
+        he = None if h_eff is None else np.ascontiguousarray(np.asarray(h_eff, dtype=np.float64).reshape(-1))
+        rs = None if row_scaled is None else np.ascontiguousarray(row_scaled, dtype=np.uint8).reshape(-1)
+        check(lib().nlmc_set_phase(self._h, r, _ptr(he), _ptr(rs), float(temp_x)), "nlmc_set_phase")
+
+    def sweep_replay(self, perm, u, beta, tanh_lut=None, lut_half: int = 0, record_from: int | None = 0,
+                     want_energy: bool = True):
+        """perm,u: [R][S][n]; beta: [R][S].  Returns (M int8 [R][S-record_from][n] or None, E [R][S] or None)."""
+        perm = np.ascontiguousarray(perm, dtype=np.int32).reshape(self.R, -1, self.n)
+        S = perm.shape[1]
+        u = np.ascontiguousarray(u, dtype=np.float64).reshape(self.R, S, self.n)
+        beta = np.ascontiguousarray(beta, dtype=np.float64).reshape(self.R, S)
+        lut = None
+        if tanh_lut is not None:
+            lut = np.ascontiguousarray(tanh_lut, dtype=np.float64).reshape(self.R, S, 2 * lut_half + 1)
+        M = None
+        if record_from is not None:
+            M = np.empty((self.R, S - record_from, self.n), dtype=np.int8)
+        E = np.empty((self.R, S), dtype=np.float64) if want_energy else None
+        check(lib().nlmc_sweep_replay(self._h, S, perm, u, beta, _ptr(lut), int(lut_half), _ptr(M),
+                                      int(record_from or 0), _ptr(E)), "nlmc_sweep_replay")
+        return M, E
+
+    def energy(self) -> np.ndarray:
+        out = np.empty(self.R, dtype=np.float64)
+        check(lib().nlmc_energy(self._h, out), "nlmc_energy")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nlmc_replicas_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -43,6 +43,43 @@ def save(name, **kw):
     print(f"{name}: {os.path.getsize(path)} bytes")
 
 
+class record_backbones:
+    """Records the clusters every LBP_convexified call of the reference returns (in call order), also
+    from the forked pool worker of NPT.run: the wrapper appends to a file."""
+
+    def __init__(self, cls):
+        self.cls = cls
+
+    def __enter__(self):
+        import tempfile
+        self.path = tempfile.mktemp(suffix=".backbones")
+        orig = self.orig = self.cls.LBP_convexified
+        path = self.path
+
+        def wrapped(obj, *a, **k):
+            out = orig(obj, *a, **k)
+            cl = np.concatenate(out[0]).astype(int) if out[0] else np.array([], dtype=int)
+            with open(path, "a") as f:
+                f.write(" ".join(str(int(v)) for v in cl) + "\n")
+            return out
+
+        self.cls.LBP_convexified = wrapped
+        return self
+
+    def __exit__(self, *exc):
+        self.cls.LBP_convexified = self.orig
+
+    def result(self):
+        """(flat indices, sizes) of all recorded backbones"""
+        rows = []
+        if os.path.exists(self.path):
+            with open(self.path) as f:
+                rows = [np.array([int(v) for v in line.split()], dtype=np.int64) for line in f]
+            os.remove(self.path)
+        flat = np.concatenate(rows) if rows else np.array([], dtype=np.int64)
+        return flat, np.array([len(r) for r in rows], dtype=np.int64)
+
+
 def case_mcmc():
     """Element level: MCMC (NMC/nmc.py:28-91) on +-J, Gaussian J with h, annealed and fixed beta."""
     J1, h1 = O.random_pm_graph(48, 0.2, 101)
@@ -94,9 +131,11 @@ def case_nmc_run():
     J, h = O.random_pm_graph(60, 0.15, 1)
     args = (40, 10, 3, 2, 1, 20, 3, 3, 0.01, 0.9, 0.9999999, 0.999999, 100, EPS)
     rl.seed_all(21)
-    with rl.quiet_tmp_cwd():
+    with rl.quiet_tmp_cwd(), record_backbones(rl.nmc().NMC) as rec:
         M, E, mn = rl.nmc().NMC(J, h).run(*args)
-    save("nmc_run_c1", J=J, h=h, args=np.array(args), seed=21, M=i8(M), E=np.asarray(E), min_energy=mn)
+    flat, sizes = rec.result()
+    save("nmc_run_c1", J=J, h=h, args=np.array(args), seed=21, M=i8(M), E=np.asarray(E), min_energy=mn,
+         backbone_flat=flat, backbone_sizes=sizes)
     # the reference unit-test shape: dense Gaussian J with field (NMC/unittests/test_nmc.py:9-17)
     rs = np.random.RandomState(5)
     N = 12
@@ -107,9 +146,11 @@ def case_nmc_run():
     Jg += Jg.T
     args2 = (50, 10, 2, 1, 1, 20, 3, 3, 0.01, 0.9, 0.9999999, 0.999999, 10, EPS)
     rl.seed_all(4)
-    with rl.quiet_tmp_cwd():
+    with rl.quiet_tmp_cwd(), record_backbones(rl.nmc().NMC) as rec:
         M, E, mn = rl.nmc().NMC(Jg, hg).run(*args2)
-    save("nmc_run_gauss", J=Jg, h=hg, args=np.array(args2), seed=4, M=i8(M), E=np.asarray(E), min_energy=mn)
+    flat, sizes = rec.result()
+    save("nmc_run_gauss", J=Jg, h=hg, args=np.array(args2), seed=4, M=i8(M), E=np.asarray(E), min_energy=mn,
+         backbone_flat=flat, backbone_sizes=sizes)
 
 
 NPT_KW = dict(num_cycles=2, full_update_frequency=1, M_skip=1, temp_x=20, global_beta=3, lambda_start=3,
@@ -132,10 +173,12 @@ def case_npt():
     doNMC = [False, False, True, True]
     kw = dict(num_sweeps_MCMC=60, num_sweeps_read=20, num_swap_attempts=4, num_swapping_pairs=1, **NPT_KW)
     rl.seed_all(12)
-    with rl.quiet_tmp_cwd():
+    with rl.quiet_tmp_cwd(), record_backbones(rl.npt().NPT) as rec:
         M, E = rl.npt().NPT(J, h).run(betas, 4, doNMC, num_cores=1, **kw)
+    flat, sizes = rec.result()
     save("npt_run_c2", J=J, h=h, seed=12, beta_list=betas, doNMC=np.array(doNMC),
-         num_sweeps_MCMC=60, num_sweeps_read=20, num_swap_attempts=4, num_swapping_pairs=1, M=i8(M), E=E)
+         num_sweeps_MCMC=60, num_sweeps_read=20, num_swap_attempts=4, num_swapping_pairs=1, M=i8(M), E=E,
+         backbone_flat=flat, backbone_sizes=sizes)
 
 
 def case_npt_sk():

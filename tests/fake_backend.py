@@ -1,0 +1,112 @@
+"""TEST INFRASTRUCTURE ONLY: oracle-backed stand-ins for the ctypes classes of nlmc_b200._lib, so that
+the HOST logic of the drop-in classes (random-stream bookkeeping, phase set-up, swap rules, output
+assembly) can be tested on a machine without a GPU.  Installed by the `fake_device` fixture only;
+the product never sees it."""
+import numpy as np
+
+from oracle import oracle as O
+
+
+class FakeInstance:
+    def __init__(self, rp, ci, val, h, device=0):
+        self.csr = O.Csr.__new__(O.Csr)
+        self.csr.n = len(rp) - 1
+        self.csr.rp = np.ascontiguousarray(rp, dtype=np.int32)
+        self.csr.ci = np.ascontiguousarray(ci, dtype=np.int32)
+        self.csr.val = np.ascontiguousarray(val, dtype=np.float64)
+        self.csr._rev = None
+        self.h = np.asarray(h, dtype=np.float64).reshape(-1)
+        self.n = self.csr.n
+        self.is_integer = bool(np.all(self.csr.val == np.floor(self.csr.val)))
+
+    def energy_states(self, states):
+        return O.energy(self.csr, self.h, states)
+
+    def close(self):
+        pass
+
+
+class FakeReplicas:
+    def __init__(self, inst, n_replicas, init_spins=None):
+        self.inst, self.R, self.n = inst, int(n_replicas), inst.n
+        self.spins = np.ones((self.R, self.n), dtype=np.int8)
+        if init_spins is not None:
+            self.spins[:] = np.asarray(init_spins, dtype=np.int8).reshape(self.R, self.n)
+        self.phase = [(None, None, 1.0)] * self.R
+
+    def set_spins(self, spins, first=0):
+        spins = np.asarray(spins, dtype=np.int8).reshape(-1, self.n)
+        self.spins[first:first + len(spins)] = spins
+
+    def get_spins(self, first=0, count=None):
+        count = self.R - first if count is None else count
+        return self.spins[first:first + count].copy()
+
+    def set_phase(self, r, h_eff=None, row_scaled=None, temp_x=1.0):
+        self.phase[r] = (None if h_eff is None else np.asarray(h_eff, dtype=np.float64).copy(),
+                         None if row_scaled is None else np.asarray(row_scaled).astype(bool), float(temp_x))
+
+    def sweep_replay(self, perm, u, beta, tanh_lut=None, lut_half=0, record_from=0, want_energy=True):
+        perm = np.asarray(perm).reshape(self.R, -1, self.n)
+        S = perm.shape[1]
+        u = np.asarray(u).reshape(self.R, S, self.n)
+        beta = np.asarray(beta, dtype=np.float64).reshape(self.R, S)
+        M = np.empty((self.R, S - (record_from or 0), self.n), dtype=np.int8)
+        E = np.empty((self.R, S))
+        csr = self.inst.csr
+        rows = csr.row_of
+        for r in range(self.R):
+            h_eff, scaled, tx = self.phase[r]
+            c = csr if scaled is None else csr.with_values(np.where(scaled[rows], csr.val / tx, csr.val))
+            Mo, last = O.mcmc(c, self.inst.h if h_eff is None else h_eff, self.spins[r], beta[r], perm=perm[r], u=u[r])
+            self.spins[r] = last
+            M[r] = Mo[record_from or 0:]
+            E[r] = O.energy(csr, self.inst.h, Mo) if S else np.zeros(0)
+        return (None if record_from is None else M), (E if want_energy else None)
+
+    def energy(self):
+        return O.energy(self.inst.csr, self.inst.h, self.spins)
+
+    def close(self):
+        pass
+
+
+class FakeLbp:
+    def __init__(self, inst):
+        self.inst = inst
+        self.eps = np.abs(inst.h) + O._pairwise_rowsum_abs(inst.csr)
+
+    def epsilon(self):
+        return self.eps.copy()
+
+    def reset(self, m_star):
+        c = self.inst.csr
+        self.ms = np.asarray(m_star, dtype=np.float64).reshape(-1)
+        self.u = np.ascontiguousarray(c.val * self.ms[c.ci])
+        self.hm = np.zeros_like(self.u)
+        self.tot = np.zeros(c.n)
+
+    def step(self, lam, beta, tol, max_iter):
+        hl = np.ascontiguousarray(self.inst.h + lam * self.ms * self.eps)
+        return O.lbp(self.inst.csr, hl, beta, self.u, self.hm, self.tot, tol, max_iter)
+
+    def close(self):
+        pass
+
+
+def fake_icm_clusters(inst, s1, s2):
+    s1 = np.asarray(s1, dtype=np.int8).reshape(-1, inst.n)
+    s2 = np.asarray(s2, dtype=np.int8).reshape(-1, inst.n)
+    labels = np.empty((len(s1), inst.n), dtype=np.int32)
+    counts = np.empty(len(s1), dtype=np.int32)
+    for p in range(len(s1)):
+        labels[p], counts[p] = O.disagreement_clusters(inst.csr, s1[p], s2[p])
+    return labels, counts
+
+
+def install(monkeypatch):
+    from nlmc_b200 import _lib
+    monkeypatch.setattr(_lib, "Instance", FakeInstance)
+    monkeypatch.setattr(_lib, "Replicas", FakeReplicas)
+    monkeypatch.setattr(_lib, "Lbp", FakeLbp)
+    monkeypatch.setattr(_lib, "icm_clusters", fake_icm_clusters)
