@@ -123,6 +123,48 @@ int nlmc_icm_clusters(nlmc_instance *inst, int n_pairs, const int8_t *s1 /*[n_pa
                       const int8_t *s2 /*[n_pairs][n]*/, int32_t *out_labels /*[n_pairs][n]*/,
                       int32_t *out_n_clusters /*[n_pairs]*/);
 
+/* ---- K2 / K4' / K6: production path (bit-packed multi-spin coding) ------------------------------
+ * For +-J instances with h = 0 and even degrees <= 6 (the 3D EA configs).  n_ladders independent NPT
+ * runs ("ladders", one replica per beta each) are packed 32 to a word, all bits of a word at the same
+ * beta; n_ladders is rounded up to a multiple of 128 (nlmc_msc_info reports the padded count).
+ *
+ *   nlmc_msc_sweep      heat-bath sweeps, graph-coloured parallel updates, Philox4x32-10 randoms.
+ *                       Replaces MCMC (NMC/nmc.py:28-91 and copies) for every replica of every ladder;
+ *                       same single-site conditional distribution, different (coloured) visiting order.
+ *   nlmc_msc_energies   E = -(m^T J m/2) of every replica, exact integers (NPT/npt.py:31-45,657-658).
+ *                       out_E [n_beta][n_ladders_padded] or NULL to leave them on the device.
+ *   nlmc_msc_round      one swap round of NPT.run (NPT/npt.py:617-680) for all ladders: n_sweeps sweeps,
+ *                       energies, then per ladder num_swapping_pairs non-overlapping adjacent pairs
+ *                       (NPT/npt.py:514-533) accepted with min(1, exp(dBeta*dE)) (npt.py:668-671) and
+ *                       the two configurations exchanged (npt.py:677-678).  out_E (optional) receives the
+ *                       energies of the states before the exchange.
+ *   nlmc_msc_round_host the same through HOST buffers: packed states in ([n][n_words] uint32, NULL = keep
+ *                       the device state), packed states and energies out (either may be NULL).
+ *   nlmc_msc_set/get_spins     one replica (beta_idx, ladder) as int8 +-1.
+ *   nlmc_msc_timer_*    CUDA-event timing on the handle's stream (mark 0 = start, 1 = stop). */
+int nlmc_msc_create(nlmc_instance *inst, int n_beta, const double *betas, int n_ladders,
+                    unsigned long long seed, nlmc_msc **out);
+int nlmc_msc_destroy(nlmc_msc *msc);
+int nlmc_msc_info(const nlmc_msc *msc, int *n_words, int *n_ladders_padded, int *n_colours, long long *n_bonds);
+int nlmc_msc_set_seed(nlmc_msc *msc, unsigned long long seed, unsigned sweep_counter);
+/* new inverse temperatures for the existing words (APT_preprocessor walks its ladder one beta at a time,
+ * warm-starting from the previous beta's final states, NPT/apt_preprocessor.py:154-166) */
+int nlmc_msc_set_betas(nlmc_msc *msc, const double *betas /*[n_beta]*/);
+int nlmc_msc_init_random(nlmc_msc *msc, unsigned stream_id);
+int nlmc_msc_set_spins(nlmc_msc *msc, int beta_idx, int ladder, const int8_t *spins /*[n]*/);
+int nlmc_msc_get_spins(nlmc_msc *msc, int beta_idx, int ladder, int8_t *out /*[n]*/);
+int nlmc_msc_set_packed(nlmc_msc *msc, const uint32_t *packed /*[n][n_words]*/);
+int nlmc_msc_get_packed(nlmc_msc *msc, uint32_t *packed /*[n][n_words]*/);
+int nlmc_msc_sweep(nlmc_msc *msc, int n_sweeps);
+int nlmc_msc_energies(nlmc_msc *msc, double *out_E);
+int nlmc_msc_round(nlmc_msc *msc, int n_sweeps, int num_swapping_pairs, double *out_E);
+int nlmc_msc_round_host(nlmc_msc *msc, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,
+                        uint32_t *packed_out, double *out_E);
+int nlmc_msc_swap_count(nlmc_msc *msc, int *out_accepted, int reset);
+int nlmc_msc_sync(nlmc_msc *msc);
+int nlmc_msc_timer_mark(nlmc_msc *msc, int which);
+int nlmc_msc_timer_elapsed_ms(nlmc_msc *msc, float *out_ms);
+
 #ifdef __cplusplus
 }
 #endif

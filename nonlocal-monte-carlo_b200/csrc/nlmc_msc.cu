@@ -1,0 +1,683 @@
+// nlmc_msc.cu -- K2 production path: multi-spin-coded heat-bath sweeps, bit-sliced energies (K4') and
+// replica-exchange swaps (K6) for +-J instances with h = 0 and even degrees <= 6 (2D/3D lattices,
+// the EA configs C2/C4/C5 of BASELINE.json).
+//
+// Layout.  A "ladder" is one NPT run (one replica per inverse temperature).  32 independent ladders
+// share a 32-bit word, one bit each (bit = 1 <=> spin +1); all bits of a word sit at the SAME beta,
+// so the heat-bath thresholds are uniform across a word.  S[site][w], w = b*G + g (beta index b,
+// ladder group g, G = n_ladders/32, n_ladders a multiple of 128 so that a thread's four consecutive
+// words share one beta).  For C5 (L=64, 32 betas x 128 ladders = 4096 replicas) a site row is
+// 128 words = 512 B: one warp owns one site, each lane one uint4 (LDG.128, fully coalesced), and the
+// whole state is 134 MB.
+//
+// Update rule (same distribution as the reference's sign(tanh(beta*x) - 2u + 1), NMC/nmc.py:87):
+// with c = number of neighbours with J_ij*s_j = +1 and field f = 2c - 6,
+//     s_i <- [f > 0] XOR g,   g ~ Bernoulli(q(|f|)),  q(0) = 1/2,  q(a) = 1/(1 + exp(2*beta*a)).
+// c is formed for 32 ladders at once with bit-sliced full adders (LOP3), and g is drawn for 32
+// ladders at once by a bit-serial comparison of a uniform with the 32-bit threshold of each lane's
+// |f| level, most significant bit first; lanes drop out as soon as their comparison is decided, so
+// on average ~2 random bits per attempt are consumed.  Random words are Philox4x32-10 keyed by
+// (seed; site, word-quad, sweep, bit step): results do not depend on the launch geometry or on how
+// ladders are sharded over GPUs.  Sites are updated colour by colour (checkerboard on bipartite
+// lattices, greedy colouring otherwise), all sites of a colour in parallel.
+#include <algorithm>
+#include <cmath>
+
+#include "nlmc_common.cuh"
+
+struct nlmc_msc {
+    nlmc_instance *inst = nullptr;
+    int n = 0, W = 0, n_beta = 0, n_ladders = 0, G = 0, n_colours = 0;
+    long long n_bonds = 0;
+    uint32_t *S = nullptr;        // [n][W]
+    int32_t *nbr = nullptr;       // [n][6]  (-1 = padding)
+    uint32_t *meta = nullptr;     // [n] bit d: J_{i,nbr d} < 0
+    int32_t *site_list = nullptr; // [n] sites sorted by colour
+    std::vector<int> colour_ptr;  // [n_colours+1]
+    uint32_t *thr = nullptr;      // [n_beta][4] thresholds of |f| = 0,2,4,6
+    double *betas = nullptr;      // [n_beta]
+    int32_t *E_acc = nullptr;     // [W*32] sum_i (unsatisfied bonds at i) per (word, lane)
+    double *E = nullptr;          // [n_beta][n_ladders]
+    uint32_t *swapmask = nullptr; // [n_beta-1][G]
+    int32_t *accepted = nullptr;  // [1]
+    int8_t *scratch_spins = nullptr;  // [n]
+    unsigned long long seed = 0;
+    uint32_t sweep_counter = 0, round_counter = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<double> h_betas;
+};
+
+namespace nlmc {
+
+constexpr uint32_t kTagSweep = 0x53574550u, kTagInit = 0x494e4954u, kTagSwap = 0x53574150u;
+
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+            const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ a;
+            const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ b;
+            c1 = (uint32_t)p1;
+            c3 = (uint32_t)p0;
+            c0 = n0;
+            c2 = n2;
+            a += 0x9E3779B9u;
+            b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+
+struct MscDev {
+    int n, W, G, n_beta;
+    uint32_t *S;
+    const int32_t *nbr;
+    const uint32_t *meta;
+    const int32_t *site_list;
+    const uint32_t *thr;
+    uint32_t seed_lo, seed_hi;
+};
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
+
+// bit-sliced population count of six one-bit inputs -> (c0, c1, c2)
+__device__ __forceinline__ void count6(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                       uint32_t &c0, uint32_t &c1, uint32_t &c2) {
+    const uint32_t s1 = a0 ^ a1 ^ a2, k1 = maj3(a0, a1, a2);
+    const uint32_t s2 = a3 ^ a4 ^ a5, k2 = maj3(a3, a4, a5);
+    c0 = s1 ^ s2;
+    const uint32_t k3 = s1 & s2;
+    c1 = k1 ^ k2 ^ k3;
+    c2 = maj3(k1, k2, k3);
+}
+
+__device__ __forceinline__ uint32_t comp(const uint4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+
+// One colour of one sweep: a warp per (site, 128-word chunk), a lane per four consecutive words.
+__global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int n_sites, uint32_t sweep) {
+    const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    const int chunks = (a.W + 127) >> 7;
+    if (warp >= n_sites * chunks) return;
+    const int site = __ldg(a.site_list + first + warp / chunks);
+    const int word0 = (warp % chunks) * 128 + lane * 4;
+    if (word0 >= a.W) return;
+
+    const uint32_t meta = __ldg(a.meta + site);
+    uint4 x[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        const int j = __ldg(a.nbr + (size_t)site * 6 + d);
+        if (j >= 0) {
+            x[d] = *reinterpret_cast<const uint4 *>(a.S + (size_t)j * a.W + word0);
+            if ((meta >> d) & 1u) { x[d].x = ~x[d].x; x[d].y = ~x[d].y; x[d].z = ~x[d].z; x[d].w = ~x[d].w; }
+        } else {  // padding comes in (+1, -1) pairs: even degrees only
+            const uint32_t v = (d & 1) ? 0u : 0xffffffffu;
+            x[d] = make_uint4(v, v, v, v);
+        }
+    }
+    uint32_t m0[4], m1[4], pos[4], res[4], und[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t c0, c1, c2;
+        count6(comp(x[0], k), comp(x[1], k), comp(x[2], k), comp(x[3], k), comp(x[4], k), comp(x[5], k), c0, c1, c2);
+        // |f|/2 = |c - 3| as two bit planes (m1 m0); sign plane pos = [c >= 4]
+        m0[k] = ~c0;
+        m1[k] = (c2 & (c1 | c0)) | (~c2 & ~c1);
+        pos[k] = c2;
+        res[k] = 0u;
+        und[k] = 0xffffffffu;
+    }
+    const int b = word0 / a.G;  // the four words of a lane share one beta (G % 4 == 0)
+    const uint32_t T1 = __ldg(a.thr + b * 4 + 1), T2 = __ldg(a.thr + b * 4 + 2), T3 = __ldg(a.thr + b * 4 + 3);
+    const Philox rng{a.seed_lo, a.seed_hi ^ kTagSweep};
+    for (int p = 0; p < 32; ++p) {
+        // bit p (MSB first) of each level's threshold, spread to a full mask
+        const uint32_t L0 = p == 0 ? 0xffffffffu : 0u;  // q(0) = 1/2 = 0x80000000 / 2^32
+        const uint32_t L1 = (uint32_t)((int32_t)(T1 << p) >> 31);
+        const uint32_t L2 = (uint32_t)((int32_t)(T2 << p) >> 31);
+        const uint32_t L3 = (uint32_t)((int32_t)(T3 << p) >> 31);
+        const uint4 r4 = rng((uint32_t)site, (uint32_t)(word0 >> 2), sweep, (uint32_t)p);
+        uint32_t any = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t r = comp(r4, k);
+            const uint32_t lo = (m0[k] & L1) | (~m0[k] & L0);
+            const uint32_t hi = (m0[k] & L3) | (~m0[k] & L2);
+            const uint32_t t = (m1[k] & hi) | (~m1[k] & lo);
+            res[k] |= und[k] & ~r & t;   // uniform bit 0, threshold bit 1  -> u < T decided
+            und[k] &= ~(r ^ t);          // still equal on this prefix
+            any |= und[k];
+        }
+        if (any == 0u) break;
+    }
+    uint4 out;
+    out.x = pos[0] ^ res[0];
+    out.y = pos[1] ^ res[1];
+    out.z = pos[2] ^ res[2];
+    out.w = pos[3] ^ res[3];
+    *reinterpret_cast<uint4 *>(a.S + (size_t)site * a.W + word0) = out;
+}
+
+// Uniform random initial spins (the production counterpart of sign(2*rand-1), NPT/npt.py:612).
+__global__ void msc_init_kernel(MscDev a, uint32_t stream_id) {
+    const size_t quad = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t n_quads = (size_t)a.n * a.W / 4;
+    if (quad >= n_quads) return;
+    const Philox rng{a.seed_lo, a.seed_hi ^ kTagInit};
+    const uint4 r = rng((uint32_t)quad, (uint32_t)(quad >> 32), stream_id, 0u);
+    reinterpret_cast<uint4 *>(a.S)[quad] = r;
+}
+
+// K4': per (word, lane) sum over sites of the number of unsatisfied bonds at the site, with bit-sliced
+// vertical counters (10 bit planes) flushed every kEnergyChunk sites.  E = sum_i unsat_i - n_bonds.
+constexpr int kEnergyChunk = 128;  // 128 sites * 6 bonds < 2^10
+__global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_acc) {
+    const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    const int chunks = (a.W + 127) >> 7;
+    const int site_chunks = (a.n + kEnergyChunk - 1) / kEnergyChunk;
+    if (warp >= site_chunks * chunks) return;
+    const int word0 = (warp % chunks) * 128 + lane * 4;
+    if (word0 >= a.W) return;
+    const int s_begin = (warp / chunks) * kEnergyChunk, s_end = min(a.n, s_begin + kEnergyChunk);
+    uint32_t v[4][10];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int bb = 0; bb < 10; ++bb) v[k][bb] = 0u;
+    for (int site = s_begin; site < s_end; ++site) {
+        const uint32_t meta = __ldg(a.meta + site);
+        const uint4 own = *reinterpret_cast<const uint4 *>(a.S + (size_t)site * a.W + word0);
+        uint4 x[6];
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+            const int j = __ldg(a.nbr + (size_t)site * 6 + d);
+            if (j >= 0) {
+                x[d] = *reinterpret_cast<const uint4 *>(a.S + (size_t)j * a.W + word0);
+                const uint32_t neg = ((meta >> d) & 1u) ? 0xffffffffu : 0u;
+                // unsatisfied <=> J*s_i*s_j = -1 <=> s_i xor s_j xor [J<0]
+                x[d].x ^= own.x ^ neg; x[d].y ^= own.y ^ neg; x[d].z ^= own.z ^ neg; x[d].w ^= own.w ^ neg;
+            } else {
+                x[d] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t c0, c1, c2;
+            count6(comp(x[0], k), comp(x[1], k), comp(x[2], k), comp(x[3], k), comp(x[4], k), comp(x[5], k), c0, c1, c2);
+            // ripple-add the 3-bit count into the 10-bit vertical counter
+            uint32_t carry = v[k][0] & c0;
+            v[k][0] ^= c0;
+            uint32_t t = v[k][1] ^ c1 ^ carry;
+            carry = maj3(v[k][1], c1, carry);
+            v[k][1] = t;
+            t = v[k][2] ^ c2 ^ carry;
+            carry = maj3(v[k][2], c2, carry);
+            v[k][2] = t;
+#pragma unroll
+            for (int bb = 3; bb < 10; ++bb) {
+                t = v[k][bb] & carry;
+                v[k][bb] ^= carry;
+                carry = t;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        for (int l = 0; l < 32; ++l) {
+            int val = 0;
+#pragma unroll
+            for (int bb = 0; bb < 10; ++bb) val |= (int)((v[k][bb] >> l) & 1u) << bb;
+            if (val) atomicAdd(E_acc + (size_t)(word0 + k) * 32 + l, val);
+        }
+    }
+}
+
+__global__ void msc_energy_finish_kernel(int W, int G, int n_ladders, long long n_bonds, const int32_t *E_acc, double *E) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (word, lane)
+    if (idx >= W * 32) return;
+    const int w = idx >> 5, l = idx & 31;
+    const int b = w / G, g = w % G;
+    E[(size_t)b * n_ladders + g * 32 + l] = (double)E_acc[idx] - (double)n_bonds;
+}
+
+// K6: replica exchange, one thread per ladder.  Pair selection and acceptance follow the reference
+// (NPT/npt.py:514-533,652-680): num_pairs non-overlapping adjacent pairs drawn one after the other
+// uniformly from the pairs still available; accept with min(1, exp((b_next-b_sel)*(E_next-E_sel))).
+// Accepted exchanges are recorded as lane masks per temperature boundary and applied to the
+// configurations by msc_swap_apply_kernel (the reference swaps configurations, not labels).
+constexpr int kMaxBeta = 128;
+__global__ void msc_swap_decide_kernel(int n_beta, int n_ladders, int G, int num_pairs, const double *betas, double *E,
+                                       uint32_t *swapmask, int32_t *accepted, uint32_t seed_lo, uint32_t seed_hi,
+                                       uint32_t round) {
+    const int ladder = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ladder >= n_ladders) return;
+    const Philox rng{seed_lo, seed_hi ^ kTagSwap};
+    uint8_t avail[kMaxBeta];  // avail[i] = 1: pair (i, i+1) still selectable
+    int n_avail = n_beta - 1;
+    for (int i = 0; i < n_beta - 1; ++i) avail[i] = 1;
+    int acc = 0;
+    for (int k = 0; k < num_pairs && n_avail > 0; ++k) {
+        const uint4 r = rng((uint32_t)ladder, round, (uint32_t)k, 0u);
+        int pick = (int)(((unsigned long long)r.x * (unsigned)n_avail) >> 32);
+        int i = 0;
+        for (;; ++i)
+            if (avail[i] && pick-- == 0) break;
+        // remove the pair and its overlapping neighbours
+        for (int j = max(0, i - 1); j <= min(n_beta - 2, i + 1); ++j)
+            if (avail[j]) { avail[j] = 0; --n_avail; }
+        const double E_sel = E[(size_t)i * n_ladders + ladder], E_next = E[(size_t)(i + 1) * n_ladders + ladder];
+        const double x = (betas[i + 1] - betas[i]) * (E_next - E_sel);
+        const double u = ((double)r.y * 4294967296.0 + (double)r.z + 0.5) * (1.0 / 18446744073709551616.0);
+        if (u < fmin(1.0, exp(x))) {
+            ++acc;
+            atomicOr(swapmask + (size_t)i * G + (ladder >> 5), 1u << (ladder & 31));
+            E[(size_t)i * n_ladders + ladder] = E_next;
+            E[(size_t)(i + 1) * n_ladders + ladder] = E_sel;
+        }
+    }
+    if (acc) atomicAdd(accepted, acc);
+}
+
+__global__ void msc_swap_apply_kernel(MscDev a, const uint32_t *swapmask) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // (site, g)
+    if (idx >= (size_t)a.n * a.G) return;
+    const int g = (int)(idx % a.G);
+    uint32_t *row = a.S + (idx / a.G) * (size_t)a.W + g;
+    uint32_t A = row[0];
+    bool A_dirty = false;
+    for (int b = 0; b + 1 < a.n_beta; ++b) {
+        uint32_t B = row[(size_t)(b + 1) * a.G];
+        bool B_dirty = false;
+        const uint32_t mask = __ldg(swapmask + (size_t)b * a.G + g);
+        if (mask) {
+            const uint32_t t = (A ^ B) & mask;  // lanes whose two configurations differ at this site
+            if (t) {
+                A ^= t;
+                B ^= t;
+                A_dirty = B_dirty = true;
+            }
+        }
+        if (A_dirty) row[(size_t)b * a.G] = A;
+        A = B;
+        A_dirty = B_dirty;
+    }
+    if (A_dirty) row[(size_t)(a.n_beta - 1) * a.G] = A;
+}
+
+__global__ void msc_unpack_kernel(MscDev a, int w, int lane, int8_t *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) out[i] = ((a.S[(size_t)i * a.W + w] >> lane) & 1u) ? 1 : -1;
+}
+
+__global__ void msc_pack_kernel(MscDev a, int w, int lane, const int8_t *in) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    uint32_t *p = a.S + (size_t)i * a.W + w;
+    const uint32_t bit = 1u << lane;
+    *p = in[i] > 0 ? (*p | bit) : (*p & ~bit);  // one thread per site: no other writer of this word
+}
+
+// 32-bit thresholds of q(|f|) = 1/(1 + exp(2*beta*|f|)) for |f| = 0, 2, 4, 6
+static std::vector<uint32_t> msc_thresholds(int n_beta, const double *betas) {
+    std::vector<uint32_t> thr((size_t)n_beta * 4);
+    for (int b = 0; b < n_beta; ++b) {
+        thr[(size_t)b * 4] = 0x80000000u;
+        for (int a = 1; a < 4; ++a) {
+            const double q = 1.0 / (1.0 + std::exp(2.0 * betas[b] * (2.0 * a)));
+            thr[(size_t)b * 4 + a] = (uint32_t)std::min(4294967295.0, std::floor(q * 4294967296.0));
+        }
+    }
+    return thr;
+}
+
+static MscDev dev_view(const nlmc_msc *M) {
+    MscDev d;
+    d.n = M->n; d.W = M->W; d.G = M->G; d.n_beta = M->n_beta;
+    d.S = M->S; d.nbr = M->nbr; d.meta = M->meta; d.site_list = M->site_list; d.thr = M->thr;
+    d.seed_lo = (uint32_t)M->seed; d.seed_hi = (uint32_t)(M->seed >> 32);
+    return d;
+}
+
+static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
+    const MscDev d = dev_view(M);
+    const int chunks = (M->W + 127) / 128;
+    for (int s = 0; s < n_sweeps; ++s) {
+        for (int c = 0; c < M->n_colours; ++c) {
+            const int first = M->colour_ptr[c], cnt = M->colour_ptr[c + 1] - first;
+            if (cnt == 0) continue;
+            const long long warps = (long long)cnt * chunks;
+            const unsigned blocks = (unsigned)((warps + 7) / 8);
+            msc_sweep_kernel<<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter);
+        }
+        ++M->sweep_counter;
+    }
+    NLMC_CUDA(cudaGetLastError());
+    return NLMC_OK;
+}
+
+static int launch_energy(nlmc_msc *M) {
+    const MscDev d = dev_view(M);
+    const int chunks = (M->W + 127) / 128;
+    const int site_chunks = (M->n + kEnergyChunk - 1) / kEnergyChunk;
+    NLMC_CUDA(cudaMemsetAsync(M->E_acc, 0, sizeof(int32_t) * (size_t)M->W * 32, M->stream));
+    const long long warps = (long long)site_chunks * chunks;
+    msc_energy_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, M->stream>>>(d, M->E_acc);
+    msc_energy_finish_kernel<<<(M->W * 32 + 255) / 256, 256, 0, M->stream>>>(M->W, M->G, M->n_ladders, M->n_bonds,
+                                                                            M->E_acc, M->E);
+    NLMC_CUDA(cudaGetLastError());
+    return NLMC_OK;
+}
+
+static int launch_swap(nlmc_msc *M, int num_pairs) {
+    const MscDev d = dev_view(M);
+    if (M->n_beta < 2 || num_pairs <= 0) return NLMC_OK;
+    NLMC_CUDA(cudaMemsetAsync(M->swapmask, 0, sizeof(uint32_t) * (size_t)(M->n_beta - 1) * M->G, M->stream));
+    msc_swap_decide_kernel<<<(M->n_ladders + 127) / 128, 128, 0, M->stream>>>(
+        M->n_beta, M->n_ladders, M->G, num_pairs, M->betas, M->E, M->swapmask, M->accepted, d.seed_lo, d.seed_hi,
+        M->round_counter);
+    const size_t items = (size_t)M->n * M->G;
+    msc_swap_apply_kernel<<<(unsigned)((items + 255) / 256), 256, 0, M->stream>>>(d, M->swapmask);
+    ++M->round_counter;
+    NLMC_CUDA(cudaGetLastError());
+    return NLMC_OK;
+}
+
+}  // namespace nlmc
+
+extern "C" {
+
+int nlmc_msc_destroy(nlmc_msc *M) {
+    if (!M) return NLMC_OK;
+    cudaSetDevice(M->inst->device);
+    void *ptrs[] = {M->S, M->nbr, M->meta, M->site_list, M->thr, M->betas, M->E_acc, M->E, M->swapmask, M->accepted,
+                    M->scratch_spins};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (M->ev0) cudaEventDestroy(M->ev0);
+    if (M->ev1) cudaEventDestroy(M->ev1);
+    if (M->stream) cudaStreamDestroy(M->stream);
+    delete M;
+    return NLMC_OK;
+}
+
+int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_ladders, unsigned long long seed,
+                    nlmc_msc **out) {
+    using namespace nlmc;
+    NLMC_REQUIRE(I && out && betas, "nlmc_msc_create: NULL argument");
+    *out = nullptr;
+    NLMC_REQUIRE(n_beta >= 1 && n_beta <= kMaxBeta, "nlmc_msc_create: n_beta must be in [1, %d]", kMaxBeta);
+    NLMC_REQUIRE(n_ladders >= 1, "nlmc_msc_create: n_ladders must be >= 1");
+    const int n = I->n;
+    // eligibility: J in {-1,+1} off the diagonal, h = 0, even degrees <= 6
+    std::vector<int32_t> nbr((size_t)n * 6, -1);
+    std::vector<uint32_t> meta((size_t)n, 0u);
+    long long n_entries = 0;
+    for (int i = 0; i < n; ++i) {
+        if (I->h_h[(size_t)i] != 0.0) {
+            set_error("nlmc_msc_create: the bit-packed path needs h = 0 (h[%d] = %g)", i, I->h_h[(size_t)i]);
+            return NLMC_ERR_UNSUPPORTED;
+        }
+        int d = 0;
+        for (int p = I->h_row_ptr[i]; p < I->h_row_ptr[i + 1]; ++p) {
+            const double v = I->h_val[(size_t)p];
+            const int j = I->h_col[(size_t)p];
+            if (v == 0.0) continue;
+            if (j == i || (v != 1.0 && v != -1.0)) {
+                set_error("nlmc_msc_create: the bit-packed path needs J in {-1,+1} with zero diagonal (J[%d,%d] = %g)", i, j, v);
+                return NLMC_ERR_UNSUPPORTED;
+            }
+            if (d == 6) {
+                set_error("nlmc_msc_create: the bit-packed path supports degrees <= 6 (site %d)", i);
+                return NLMC_ERR_UNSUPPORTED;
+            }
+            nbr[(size_t)i * 6 + d] = j;
+            if (v < 0) meta[(size_t)i] |= 1u << d;
+            ++d;
+        }
+        if (d & 1) {
+            set_error("nlmc_msc_create: the bit-packed path supports even degrees only (site %d has %d)", i, d);
+            return NLMC_ERR_UNSUPPORTED;
+        }
+        n_entries += d;
+    }
+    // greedy colouring in site order (checkerboard on bipartite lattices with even L)
+    std::vector<int> colour((size_t)n, -1);
+    int n_colours = 0;
+    for (int i = 0; i < n; ++i) {
+        unsigned used = 0;
+        for (int d = 0; d < 6; ++d) {
+            const int j = nbr[(size_t)i * 6 + d];
+            if (j >= 0 && colour[(size_t)j] >= 0) used |= 1u << colour[(size_t)j];
+        }
+        int c = 0;
+        while (used & (1u << c)) ++c;
+        colour[(size_t)i] = c;
+        n_colours = std::max(n_colours, c + 1);
+    }
+    // symmetric adjacency is required for a valid colouring / detailed balance
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d < 6; ++d) {
+            const int j = nbr[(size_t)i * 6 + d];
+            if (j < 0) continue;
+            bool back = false;
+            for (int e = 0; e < 6; ++e) back |= nbr[(size_t)j * 6 + e] == i;
+            NLMC_REQUIRE(back, "nlmc_msc_create: J must be symmetric (entry %d,%d has no transpose)", i, j);
+        }
+    std::vector<int32_t> site_list((size_t)n);
+    std::vector<int> colour_ptr((size_t)n_colours + 1, 0);
+    for (int i = 0; i < n; ++i) ++colour_ptr[(size_t)colour[(size_t)i] + 1];
+    for (int c = 0; c < n_colours; ++c) colour_ptr[(size_t)c + 1] += colour_ptr[(size_t)c];
+    {
+        std::vector<int> fill(colour_ptr.begin(), colour_ptr.end() - 1);
+        for (int i = 0; i < n; ++i) site_list[(size_t)fill[(size_t)colour[(size_t)i]]++] = i;
+    }
+    NLMC_CUDA(cudaSetDevice(I->device));
+    auto *M = new nlmc_msc();
+    M->inst = I;
+    M->n = n;
+    M->n_beta = n_beta;
+    M->n_ladders = ((n_ladders + 127) / 128) * 128;
+    M->G = M->n_ladders / 32;
+    M->W = n_beta * M->G;
+    M->n_colours = n_colours;
+    M->n_bonds = n_entries / 2;
+    M->colour_ptr = colour_ptr;
+    M->seed = seed;
+    M->h_betas.assign(betas, betas + n_beta);
+    const std::vector<uint32_t> thr = nlmc::msc_thresholds(n_beta, betas);
+    const size_t words = (size_t)n * M->W;
+    bool ok = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&M->ev0) == cudaSuccess && cudaEventCreate(&M->ev1) == cudaSuccess &&
+              cudaMalloc(&M->S, sizeof(uint32_t) * words) == cudaSuccess &&
+              cudaMalloc(&M->nbr, sizeof(int32_t) * (size_t)n * 6) == cudaSuccess &&
+              cudaMalloc(&M->meta, sizeof(uint32_t) * (size_t)n) == cudaSuccess &&
+              cudaMalloc(&M->site_list, sizeof(int32_t) * (size_t)n) == cudaSuccess &&
+              cudaMalloc(&M->thr, sizeof(uint32_t) * thr.size()) == cudaSuccess &&
+              cudaMalloc(&M->betas, sizeof(double) * (size_t)n_beta) == cudaSuccess &&
+              cudaMalloc(&M->E_acc, sizeof(int32_t) * (size_t)M->W * 32) == cudaSuccess &&
+              cudaMalloc(&M->E, sizeof(double) * (size_t)n_beta * M->n_ladders) == cudaSuccess &&
+              cudaMalloc(&M->swapmask, sizeof(uint32_t) * (size_t)std::max(1, n_beta - 1) * M->G) == cudaSuccess &&
+              cudaMalloc(&M->accepted, sizeof(int32_t)) == cudaSuccess &&
+              cudaMalloc(&M->scratch_spins, (size_t)n) == cudaSuccess &&
+              cudaMemcpy(M->nbr, nbr.data(), sizeof(int32_t) * nbr.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(M->meta, meta.data(), sizeof(uint32_t) * meta.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(M->site_list, site_list.data(), sizeof(int32_t) * site_list.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(M->thr, thr.data(), sizeof(uint32_t) * thr.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(M->betas, betas, sizeof(double) * (size_t)n_beta, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemset(M->accepted, 0, sizeof(int32_t)) == cudaSuccess;
+    if (!ok) {
+        set_error("nlmc_msc_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        nlmc_msc_destroy(M);
+        return NLMC_ERR_CUDA;
+    }
+    *out = M;
+    return nlmc_msc_init_random(M, 0);
+}
+
+int nlmc_msc_init_random(nlmc_msc *M, unsigned stream_id) {
+    using namespace nlmc;
+    NLMC_REQUIRE(M, "nlmc_msc_init_random: NULL handle");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    const size_t quads = (size_t)M->n * M->W / 4;
+    msc_init_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, M->stream>>>(dev_view(M), stream_id);
+    NLMC_CUDA(cudaGetLastError());
+    return NLMC_OK;
+}
+
+int nlmc_msc_info(const nlmc_msc *M, int *n_words, int *n_ladders_padded, int *n_colours, long long *n_bonds) {
+    NLMC_REQUIRE(M, "nlmc_msc_info: NULL handle");
+    if (n_words) *n_words = M->W;
+    if (n_ladders_padded) *n_ladders_padded = M->n_ladders;
+    if (n_colours) *n_colours = M->n_colours;
+    if (n_bonds) *n_bonds = M->n_bonds;
+    return NLMC_OK;
+}
+
+int nlmc_msc_set_betas(nlmc_msc *M, const double *betas) {
+    NLMC_REQUIRE(M && betas, "nlmc_msc_set_betas: NULL argument");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    const std::vector<uint32_t> thr = nlmc::msc_thresholds(M->n_beta, betas);
+    M->h_betas.assign(betas, betas + M->n_beta);
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    NLMC_CUDA(cudaMemcpy(M->thr, thr.data(), sizeof(uint32_t) * thr.size(), cudaMemcpyHostToDevice));
+    NLMC_CUDA(cudaMemcpy(M->betas, betas, sizeof(double) * (size_t)M->n_beta, cudaMemcpyHostToDevice));
+    return NLMC_OK;
+}
+
+int nlmc_msc_set_seed(nlmc_msc *M, unsigned long long seed, unsigned sweep_counter) {
+    NLMC_REQUIRE(M, "nlmc_msc_set_seed: NULL handle");
+    M->seed = seed;
+    M->sweep_counter = sweep_counter;
+    M->round_counter = 0;
+    return NLMC_OK;
+}
+
+int nlmc_msc_set_spins(nlmc_msc *M, int beta_idx, int ladder, const int8_t *spins) {
+    using namespace nlmc;
+    NLMC_REQUIRE(M && spins && beta_idx >= 0 && beta_idx < M->n_beta && ladder >= 0 && ladder < M->n_ladders,
+                 "nlmc_msc_set_spins: index out of range");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    NLMC_CUDA(cudaMemcpyAsync(M->scratch_spins, spins, (size_t)M->n, cudaMemcpyHostToDevice, M->stream));
+    msc_pack_kernel<<<(M->n + 255) / 256, 256, 0, M->stream>>>(dev_view(M), beta_idx * M->G + ladder / 32, ladder % 32,
+                                                               M->scratch_spins);
+    NLMC_CUDA(cudaGetLastError());
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    return NLMC_OK;
+}
+
+int nlmc_msc_get_spins(nlmc_msc *M, int beta_idx, int ladder, int8_t *out) {
+    using namespace nlmc;
+    NLMC_REQUIRE(M && out && beta_idx >= 0 && beta_idx < M->n_beta && ladder >= 0 && ladder < M->n_ladders,
+                 "nlmc_msc_get_spins: index out of range");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    msc_unpack_kernel<<<(M->n + 255) / 256, 256, 0, M->stream>>>(dev_view(M), beta_idx * M->G + ladder / 32, ladder % 32,
+                                                                 M->scratch_spins);
+    NLMC_CUDA(cudaGetLastError());
+    NLMC_CUDA(cudaMemcpyAsync(out, M->scratch_spins, (size_t)M->n, cudaMemcpyDeviceToHost, M->stream));
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    return NLMC_OK;
+}
+
+int nlmc_msc_set_packed(nlmc_msc *M, const uint32_t *packed) {
+    NLMC_REQUIRE(M && packed, "nlmc_msc_set_packed: NULL argument");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    NLMC_CUDA(cudaMemcpyAsync(M->S, packed, sizeof(uint32_t) * (size_t)M->n * M->W, cudaMemcpyHostToDevice, M->stream));
+    return NLMC_OK;
+}
+
+int nlmc_msc_get_packed(nlmc_msc *M, uint32_t *packed) {
+    NLMC_REQUIRE(M && packed, "nlmc_msc_get_packed: NULL argument");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    NLMC_CUDA(cudaMemcpyAsync(packed, M->S, sizeof(uint32_t) * (size_t)M->n * M->W, cudaMemcpyDeviceToHost, M->stream));
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    return NLMC_OK;
+}
+
+int nlmc_msc_sweep(nlmc_msc *M, int n_sweeps) {
+    NLMC_REQUIRE(M && n_sweeps >= 0, "nlmc_msc_sweep: bad arguments");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    return nlmc::launch_sweeps(M, n_sweeps);
+}
+
+int nlmc_msc_energies(nlmc_msc *M, double *out_E) {
+    NLMC_REQUIRE(M, "nlmc_msc_energies: NULL handle");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    int rc = nlmc::launch_energy(M);
+    if (rc) return rc;
+    if (out_E) {
+        NLMC_CUDA(cudaMemcpyAsync(out_E, M->E, sizeof(double) * (size_t)M->n_beta * M->n_ladders, cudaMemcpyDeviceToHost,
+                                  M->stream));
+        NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    }
+    return NLMC_OK;
+}
+
+int nlmc_msc_round(nlmc_msc *M, int n_sweeps, int num_swapping_pairs, double *out_E) {
+    NLMC_REQUIRE(M && n_sweeps >= 0, "nlmc_msc_round: bad arguments");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    int rc;
+    if ((rc = nlmc::launch_sweeps(M, n_sweeps))) return rc;
+    if ((rc = nlmc::launch_energy(M))) return rc;
+    if (out_E)  // energies of the states the sweeps produced (before the exchange), as the reference reads them
+        NLMC_CUDA(cudaMemcpyAsync(out_E, M->E, sizeof(double) * (size_t)M->n_beta * M->n_ladders, cudaMemcpyDeviceToHost,
+                                  M->stream));
+    if ((rc = nlmc::launch_swap(M, num_swapping_pairs))) return rc;
+    if (out_E) NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    return NLMC_OK;
+}
+
+int nlmc_msc_round_host(nlmc_msc *M, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,
+                        uint32_t *packed_out, double *out_E) {
+    NLMC_REQUIRE(M && n_sweeps >= 0, "nlmc_msc_round_host: bad arguments");
+    int rc;
+    if (packed_in && (rc = nlmc_msc_set_packed(M, packed_in))) return rc;
+    if ((rc = nlmc_msc_round(M, n_sweeps, num_swapping_pairs, nullptr))) return rc;
+    if (out_E)
+        NLMC_CUDA(cudaMemcpyAsync(out_E, M->E, sizeof(double) * (size_t)M->n_beta * M->n_ladders, cudaMemcpyDeviceToHost,
+                                  M->stream));
+    if (packed_out)
+        NLMC_CUDA(cudaMemcpyAsync(packed_out, M->S, sizeof(uint32_t) * (size_t)M->n * M->W, cudaMemcpyDeviceToHost,
+                                  M->stream));
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    return NLMC_OK;
+}
+
+int nlmc_msc_swap_count(nlmc_msc *M, int *out_accepted, int reset) {
+    NLMC_REQUIRE(M && out_accepted, "nlmc_msc_swap_count: NULL argument");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    NLMC_CUDA(cudaMemcpyAsync(out_accepted, M->accepted, sizeof(int32_t), cudaMemcpyDeviceToHost, M->stream));
+    if (reset) NLMC_CUDA(cudaMemsetAsync(M->accepted, 0, sizeof(int32_t), M->stream));
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    return NLMC_OK;
+}
+
+int nlmc_msc_sync(nlmc_msc *M) {
+    NLMC_REQUIRE(M, "nlmc_msc_sync: NULL handle");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    return NLMC_OK;
+}
+
+/* CUDA-event timing on the library's own stream (bench.py): mark 0 = start, mark 1 = stop. */
+int nlmc_msc_timer_mark(nlmc_msc *M, int which) {
+    NLMC_REQUIRE(M && (which == 0 || which == 1), "nlmc_msc_timer_mark: bad arguments");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    NLMC_CUDA(cudaEventRecord(which == 0 ? M->ev0 : M->ev1, M->stream));
+    return NLMC_OK;
+}
+
+int nlmc_msc_timer_elapsed_ms(nlmc_msc *M, float *out_ms) {
+    NLMC_REQUIRE(M && out_ms, "nlmc_msc_timer_elapsed_ms: NULL argument");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    NLMC_CUDA(cudaEventSynchronize(M->ev1));
+    NLMC_CUDA(cudaEventElapsedTime(out_ms, M->ev0, M->ev1));
+    return NLMC_OK;
+}
+
+}  // extern "C"

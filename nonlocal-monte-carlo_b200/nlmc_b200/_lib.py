@@ -53,6 +53,24 @@ _SIGNATURES = {
     "nlmc_lbp_reset": [_vp, _f64],
     "nlmc_lbp_step": [_vp, _dbl, _dbl, _dbl, _int, _vp, C.POINTER(_int)],
     "nlmc_icm_clusters": [_vp, _int, _i8, _i8, _i32, _i32],
+    "nlmc_msc_create": [_vp, _int, _f64, _int, C.c_ulonglong, C.POINTER(_vp)],
+    "nlmc_msc_destroy": [_vp],
+    "nlmc_msc_info": [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), C.POINTER(C.c_longlong)],
+    "nlmc_msc_set_seed": [_vp, C.c_ulonglong, C.c_uint],
+    "nlmc_msc_set_betas": [_vp, _f64],
+    "nlmc_msc_init_random": [_vp, C.c_uint],
+    "nlmc_msc_set_spins": [_vp, _int, _int, _i8],
+    "nlmc_msc_get_spins": [_vp, _int, _int, _i8],
+    "nlmc_msc_set_packed": [_vp, _vp],
+    "nlmc_msc_get_packed": [_vp, _vp],
+    "nlmc_msc_sweep": [_vp, _int],
+    "nlmc_msc_energies": [_vp, _vp],
+    "nlmc_msc_round": [_vp, _int, _int, _vp],
+    "nlmc_msc_round_host": [_vp, _vp, _int, _int, _vp, _vp],
+    "nlmc_msc_swap_count": [_vp, C.POINTER(_int), _int],
+    "nlmc_msc_sync": [_vp],
+    "nlmc_msc_timer_mark": [_vp, _int],
+    "nlmc_msc_timer_elapsed_ms": [_vp, C.POINTER(C.c_float)],
 }
 
 
@@ -239,6 +257,104 @@ class Replicas:
     def close(self):
         if getattr(self, "_h", None):
             lib().nlmc_replicas_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Msc:
+    """Bit-packed production state (K2/K4'/K6): n_beta x n_ladders replicas of a +-J instance."""
+
+    def __init__(self, inst: Instance, betas, n_ladders: int, seed: int = 0):
+        self.inst = inst
+        self.n = inst.n
+        self.betas = np.ascontiguousarray(betas, dtype=np.float64).reshape(-1)
+        self.n_beta = len(self.betas)
+        handle = _vp()
+        check(lib().nlmc_msc_create(inst._h, self.n_beta, self.betas, int(n_ladders), int(seed) & (2**64 - 1),
+                                    C.byref(handle)), "nlmc_msc_create")
+        self._h = handle
+        w, lad, col, nb = _int(), _int(), _int(), C.c_longlong()
+        check(lib().nlmc_msc_info(self._h, C.byref(w), C.byref(lad), C.byref(col), C.byref(nb)), "nlmc_msc_info")
+        self.n_words, self.n_ladders, self.n_colours, self.n_bonds = w.value, lad.value, col.value, nb.value
+        self.n_ladders_requested = int(n_ladders)
+
+    def set_seed(self, seed: int, sweep_counter: int = 0):
+        check(lib().nlmc_msc_set_seed(self._h, int(seed) & (2**64 - 1), int(sweep_counter)), "nlmc_msc_set_seed")
+
+    def set_betas(self, betas):
+        b = np.ascontiguousarray(betas, dtype=np.float64).reshape(-1)
+        assert len(b) == self.n_beta
+        check(lib().nlmc_msc_set_betas(self._h, b), "nlmc_msc_set_betas")
+        self.betas = b
+
+    def init_random(self, stream_id: int = 0):
+        check(lib().nlmc_msc_init_random(self._h, int(stream_id)), "nlmc_msc_init_random")
+
+    def set_spins(self, beta_idx: int, ladder: int, spins):
+        s = np.ascontiguousarray(np.asarray(spins).reshape(-1), dtype=np.int8)
+        check(lib().nlmc_msc_set_spins(self._h, int(beta_idx), int(ladder), s), "nlmc_msc_set_spins")
+
+    def get_spins(self, beta_idx: int, ladder: int) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.int8)
+        check(lib().nlmc_msc_get_spins(self._h, int(beta_idx), int(ladder), out), "nlmc_msc_get_spins")
+        return out
+
+    def packed_shape(self):
+        return (self.n, self.n_words)
+
+    def set_packed(self, packed: np.ndarray):
+        assert packed.dtype == np.uint32 and packed.shape == self.packed_shape() and packed.flags.c_contiguous
+        check(lib().nlmc_msc_set_packed(self._h, packed.ctypes.data), "nlmc_msc_set_packed")
+        self.sync()
+
+    def get_packed(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.packed_shape(), dtype=np.uint32)
+        check(lib().nlmc_msc_get_packed(self._h, out.ctypes.data), "nlmc_msc_get_packed")
+        return out
+
+    def sweep(self, n_sweeps: int):
+        check(lib().nlmc_msc_sweep(self._h, int(n_sweeps)), "nlmc_msc_sweep")
+
+    def energies(self, fetch: bool = True):
+        out = np.empty((self.n_beta, self.n_ladders), dtype=np.float64) if fetch else None
+        check(lib().nlmc_msc_energies(self._h, _ptr(out)), "nlmc_msc_energies")
+        return out
+
+    def round(self, n_sweeps: int, num_swapping_pairs: int, fetch_energies: bool = False):
+        out = np.empty((self.n_beta, self.n_ladders), dtype=np.float64) if fetch_energies else None
+        check(lib().nlmc_msc_round(self._h, int(n_sweeps), int(num_swapping_pairs), _ptr(out)), "nlmc_msc_round")
+        return out
+
+    def round_host(self, packed_in_ptr, n_sweeps: int, num_swapping_pairs: int, packed_out_ptr, out_E_ptr):
+        """Raw-pointer variant for pinned host buffers (bench.py's end-to-end leg)."""
+        check(lib().nlmc_msc_round_host(self._h, packed_in_ptr, int(n_sweeps), int(num_swapping_pairs),
+                                        packed_out_ptr, out_E_ptr), "nlmc_msc_round_host")
+
+    def swap_count(self, reset: bool = False) -> int:
+        v = _int()
+        check(lib().nlmc_msc_swap_count(self._h, C.byref(v), int(reset)), "nlmc_msc_swap_count")
+        return v.value
+
+    def sync(self):
+        check(lib().nlmc_msc_sync(self._h), "nlmc_msc_sync")
+
+    def timer_mark(self, which: int):
+        check(lib().nlmc_msc_timer_mark(self._h, int(which)), "nlmc_msc_timer_mark")
+
+    def timer_elapsed_ms(self) -> float:
+        v = C.c_float()
+        check(lib().nlmc_msc_timer_elapsed_ms(self._h, C.byref(v)), "nlmc_msc_timer_elapsed_ms")
+        return float(v.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nlmc_msc_destroy(self._h)
             self._h = None
 
     def __del__(self):

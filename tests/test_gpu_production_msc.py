@@ -1,0 +1,258 @@
+"""GPU tests of the production path (bit-packed multi-spin coding, K2/K4'/K6) through the C ABI.
+
+Production mode is statistically -- not bit -- equivalent to the reference, so the checks are:
+exactness where the domain offers it (pack/unpack round trip, integer energies vs the oracle, swap
+bookkeeping), the single-site conditional distribution of the heat-bath rule, agreement with the
+EXACT Boltzmann distribution of small systems (full enumeration), and agreement of per-beta mean
+energy and |magnetisation| with samples of the reference algorithm (oracle) within 3-4 sigma
+(north_star: "per-beta mean energy and magnetisation within 3 sigma")."""
+import itertools
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nl():
+    from nlmc_b200 import _lib, host
+    return type("NL", (), dict(lib=_lib, host=host))
+
+
+def lattice_2d(L, seed):
+    rs = np.random.RandomState(seed)
+    N = L * L
+    idx = np.arange(N)
+    x, y = idx % L, idx // L
+    rows, cols, vals = [], [], []
+    for nb in (((x + 1) % L) + L * y, x + L * ((y + 1) % L)):
+        v = rs.choice([-1.0, 1.0], size=N)
+        rows += [idx, nb]
+        cols += [nb, idx]
+        vals += [v, v]
+    A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(N, N)).tocsr()
+    return A, np.zeros(N)
+
+
+def exact_mean_energy(A, betas):
+    """<E>, <E^2> of the Boltzmann distribution by full enumeration (N <= 16)."""
+    from oracle import oracle as O
+    n = A.shape[0]
+    states = np.array(list(itertools.product([-1, 1], repeat=n)), dtype=np.int8)
+    E = O.energy(O.Csr(A), np.zeros(n), states)
+    out = []
+    for b in betas:
+        w = np.exp(-b * (E - E.min()))
+        w /= w.sum()
+        m1 = (w * E).sum()
+        out.append((m1, (w * E * E).sum() - m1 * m1))
+    return out
+
+
+def test_pack_unpack_and_exact_energies(nl):
+    from oracle import oracle as O
+    A, h = O.ea3d_pm_j(6, 3)
+    csr = O.Csr(A)
+    prob = nl.host.Problem(A, h)
+    betas = np.array([0.3, 0.9, 1.5])
+    msc = nl.lib.Msc(prob.inst, betas, 130, seed=5)  # 130 -> padded to 256 ladders
+    assert msc.n_ladders == 256 and msc.n_words == 3 * 8 and msc.n_colours == 2 and msc.n_bonds == 3 * 216
+    rs = np.random.RandomState(0)
+    picks = [(0, 0), (1, 31), (2, 32), (1, 129), (2, 255)]
+    states = {k: rs.choice([-1, 1], size=csr.n).astype(np.int8) for k in picks}
+    for (b, lad), s in states.items():
+        msc.set_spins(b, lad, s)
+    for (b, lad), s in states.items():
+        assert np.array_equal(msc.get_spins(b, lad), s)
+    E = msc.energies()
+    assert E.shape == (3, 256)
+    for (b, lad), s in states.items():
+        assert E[b, lad] == O.energy(csr, h, s)[0]
+    # every replica, after some sweeps: device energies == oracle energies of the unpacked states (exact)
+    msc.sweep(3)
+    E = msc.energies()
+    for b in range(3):
+        for lad in (0, 17, 100, 255):
+            assert E[b, lad] == O.energy(csr, h, msc.get_spins(b, lad))[0]
+    # packed round trip through host buffers
+    P = msc.get_packed()
+    assert P.shape == (216, 24) and P.dtype == np.uint32
+    msc.sweep(1)
+    msc.set_packed(P)
+    assert np.array_equal(msc.get_packed(), P)
+    bit = (P[:, 1 * 8 + 129 // 32] >> (129 % 32)) & 1  # word = beta*G + ladder//32
+    assert np.array_equal(np.where(bit == 1, 1, -1).astype(np.int8), msc.get_spins(1, 129))
+
+
+def test_unsupported_instances_fail_loudly(nl):
+    from oracle import oracle as O
+    J, h = O.sk_gaussian(16, 1)
+    with pytest.raises(nl.lib.NlmcError, match="J in"):
+        nl.lib.Msc(nl.host.Problem(J, h).inst, [1.0], 1)
+    A, h = O.ea3d_pm_j(4, 1)
+    with pytest.raises(nl.lib.NlmcError, match="h = 0"):
+        nl.lib.Msc(nl.host.Problem(A, np.ones(64)).inst, [1.0], 1)
+    J, h = O.random_pm_graph(40, 0.5, 2)
+    with pytest.raises(nl.lib.NlmcError, match="degree"):
+        nl.lib.Msc(nl.host.Problem(J, h).inst, [1.0], 1)
+
+
+def test_single_site_conditional_distribution(nl):
+    """All 4096 lanes start from the same state S0.  After one sweep the colour-0 sites were drawn from
+    P(+1) = 1/(1+exp(-2 beta f(S0))) with f read from S0's (unchanged) colour-1 neighbours."""
+    from oracle import oracle as O
+    A, h = O.ea3d_pm_j(8, 7)
+    csr = O.Csr(A)
+    n = csr.n
+    betas = np.array([0.25, 0.6, 1.1])
+    prob = nl.host.Problem(A, h)
+    msc = nl.lib.Msc(prob.inst, betas, 1024, seed=99)
+    rs = np.random.RandomState(4)
+    s0 = rs.choice([-1, 1], size=n).astype(np.int8)
+    P = np.where(s0[:, None] > 0, np.uint32(0xffffffff), np.uint32(0)) * np.ones((1, msc.n_words), dtype=np.uint32)
+    msc.set_packed(np.ascontiguousarray(P.astype(np.uint32)))
+    msc.sweep(1)
+    out = msc.get_packed()
+    idx = np.arange(n)
+    colour0 = ((idx % 8) + (idx // 8) % 8 + idx // 64) % 2 == 0
+    f0 = np.asarray(A @ s0.astype(float))  # field from S0 (colour-1 neighbours did not move yet)
+    G = msc.n_ladders // 32
+    for b, beta in enumerate(betas):
+        words = out[:, b * G:(b + 1) * G]
+        ups = np.zeros(n)
+        for g in range(G):
+            ups += np.array([bin(int(v)).count("1") for v in words[:, g]])
+        for f in (-6, -4, -2, 0, 2, 4, 6):
+            sel = colour0 & (f0 == f)
+            trials = sel.sum() * msc.n_ladders
+            if trials == 0:
+                continue
+            p = 1.0 / (1.0 + np.exp(-2 * beta * f))
+            sigma = np.sqrt(trials * p * (1 - p))
+            assert abs(ups[sel].sum() - trials * p) <= 4.5 * sigma + 1, (beta, f, ups[sel].sum(), trials * p, sigma)
+
+
+@pytest.mark.parametrize("with_swaps", [False, True])
+def test_exact_boltzmann_small_lattice(nl, with_swaps):
+    """2D 4x4 periodic +-J (degree 4: exercises the neutral-pair padding).  Long runs over 1024 ladders must
+    reproduce the exact <E>(beta) from full enumeration, with and without replica exchange."""
+    A, h = lattice_2d(4, 11)
+    betas = np.array([0.2, 0.5, 0.9, 1.4])
+    exact = exact_mean_energy(A, betas)
+    prob = nl.host.Problem(A, h)
+    msc = nl.lib.Msc(prob.inst, betas, 1024, seed=2024 + with_swaps)
+    assert msc.n_colours == 2
+    for _ in range(40):  # equilibrate
+        msc.round(5, 2 if with_swaps else 0)
+    samples = []
+    for _ in range(60):
+        msc.round(4, 2 if with_swaps else 0)
+        samples.append(msc.energies())
+    S = np.array(samples)  # [t][beta][ladder]
+    if with_swaps:
+        assert msc.swap_count() > 0
+    for b in range(len(betas)):
+        per_ladder = S[:, b, :].mean(axis=0)  # ladders are independent -> honest error bar
+        mean, err = per_ladder.mean(), per_ladder.std(ddof=1) / np.sqrt(per_ladder.size)
+        assert abs(mean - exact[b][0]) <= 4.5 * err + 1e-9, (betas[b], mean, exact[b][0], err)
+
+
+def test_swap_bookkeeping_is_exact(nl):
+    """After an exchange the energies the swap kernel carried along must equal freshly computed energies of
+    the exchanged configurations, and the multiset of configurations of every ladder is conserved."""
+    from oracle import oracle as O
+    A, h = O.ea3d_pm_j(4, 5)
+    betas = np.linspace(0.1, 1.2, 6)
+    prob = nl.host.Problem(A, h)
+    msc = nl.lib.Msc(prob.inst, betas, 128, seed=8)
+    msc.sweep(3)
+    before = {lad: [msc.get_spins(b, lad).tobytes() for b in range(6)] for lad in (0, 5, 77)}
+    E_before = msc.energies()
+    msc.round(0, 2)  # no sweeps: energies + exchange only
+    accepted = msc.swap_count()
+    assert accepted > 0
+    E_after = msc.energies()
+    assert np.array_equal(np.sort(E_before, axis=0), np.sort(E_after, axis=0))  # energies permuted within ladders
+    assert np.count_nonzero(E_before != E_after) > 0
+    for lad, confs in before.items():
+        after = [msc.get_spins(b, lad).tobytes() for b in range(6)]
+        assert sorted(confs) == sorted(after)
+    moved = sum(before[lad][b] != msc.get_spins(b, lad).tobytes() for lad in before for b in range(6))
+    assert moved % 2 == 0
+
+
+def test_statistical_equivalence_with_reference_sampler(nl):
+    """3D +-J L=6: per-beta <E> and <|m|> of the production kernel vs the reference algorithm (oracle MCMC,
+    random-permutation sequential heat bath) -- within 3 sigma of the combined error (north_star)."""
+    from oracle import oracle as O
+    A, h = O.ea3d_pm_j(6, 21)
+    csr = O.Csr(A)
+    n = csr.n
+    betas = np.array([0.3, 0.6, 0.9])
+    prob = nl.host.Problem(A, h)
+    msc = nl.lib.Msc(prob.inst, betas, 256, seed=31)
+    msc.sweep(300)
+    acc_E, acc_m = [], []
+    for _ in range(20):
+        msc.sweep(20)
+        acc_E.append(msc.energies())
+        P = msc.get_packed()
+        G = msc.n_ladders // 32
+        mags = np.zeros((len(betas), msc.n_ladders))
+        for b in range(len(betas)):
+            for g in range(G):
+                w = P[:, b * G + g]
+                bits = (w[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1
+                mags[b, g * 32:(g + 1) * 32] = np.abs(2.0 * bits.sum(axis=0) - n) / n
+        acc_m.append(mags)
+    E_gpu = np.array(acc_E).mean(axis=0)  # [beta][ladder]
+    m_gpu = np.array(acc_m).mean(axis=0)
+    rs = np.random.RandomState(3)
+    chains = 24
+    for b, beta in enumerate(betas):
+        Es, ms = [], []
+        for c in range(chains):
+            m0 = rs.choice([-1, 1], size=n).astype(np.int8)
+            M, _ = O.mcmc(csr, h, m0, np.full(700, beta), rng=rs)
+            tail = M[300::20]
+            Es.append(O.energy(csr, h, tail).mean())
+            ms.append(np.abs(tail.sum(axis=1)).mean() / n)
+        for gpu, ref in ((E_gpu[b], np.array(Es)), (m_gpu[b], np.array(ms))):
+            err = np.hypot(gpu.std(ddof=1) / np.sqrt(gpu.size), ref.std(ddof=1) / np.sqrt(ref.size))
+            assert abs(gpu.mean() - ref.mean()) <= 3.5 * err, (beta, gpu.mean(), ref.mean(), err)
+
+
+def test_determinism_and_seed_dependence(nl):
+    from oracle import oracle as O
+    A, h = O.ea3d_pm_j(4, 2)
+    prob = nl.host.Problem(A, h)
+    outs = []
+    for seed in (7, 7, 8):
+        msc = nl.lib.Msc(prob.inst, [0.5, 1.0], 128, seed=seed)
+        msc.round(6, 1)
+        outs.append(msc.get_packed())
+        msc.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert not np.array_equal(outs[0], outs[2])
+
+
+def test_npt_production_mode_api(nl, tmp_cwd):
+    """Drop-in NPT in production mode: shapes/dtypes of the reference contract, energies consistent with M."""
+    from nlmc_b200 import NPT
+    from oracle import oracle as O
+    A, h = O.ea3d_pm_j(4, 6)
+    betas = np.array([0.3, 0.7, 1.1, 1.5])
+    np.random.seed(5)
+    obj = NPT(A, h, mode="production")
+    obj.num_runs = 3
+    M, E = obj.run(betas, 4, [False] * 4, num_sweeps_MCMC=40, num_sweeps_read=20, num_swap_attempts=4,
+                   num_swapping_pairs=1)
+    assert M.shape == (64 * 4, 10) and M.dtype == np.float64 and E.shape == (4,)
+    assert np.all(np.abs(M) == 1)
+    csr = O.Csr(A)
+    for r in range(4):
+        Er = O.energy(csr, h, M[r * 64:(r + 1) * 64, :5].T.astype(np.int8))
+        assert E[r] == Er.min()
+    assert obj.energies_all_runs.shape == (4, 3)
