@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of nlmc_b200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): spin-flip attempts/s.  Workload: config C5 -- 3D +-J Edwards-Anderson L=64
+(262,144 spins), NPT with 32 inverse temperatures x 128 independent ladders = 4096 replicas per GPU.
+A "step" is one swap round of NPT.run for all ladders: `spm` heat-bath sweeps of every replica, the
+energies of every replica, and the replica-exchange step (NPT/npt.py:617-680).
+
+  value   attempts/s with the state resident in HBM, CUDA events on the library's stream, max over ranks.
+  e2e     the same step through the C-ABI entry point that takes HOST buffers (nlmc_msc_round_host):
+          packed spins in from pinned host memory, packed spins + energies back out, copies inside the
+          timed region (the reference ships m_start to its workers and M back every round, npt.py:625-644).
+  N > 1   one process per GPU (torchrun); ladders are independent, so every rank runs its own 128 ladders
+          (weak scaling, no data-path collective); only the timing is reduced (max) over NCCL.
+  --impl reference   the reference algorithm on the host cores: the oracle C port of MCMC
+          (oracle/nlmc_oracle.c; the reference itself is pure Python and cannot travel to the GPU box),
+          all host threads, a bounded sample of the same workload per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "nonlocal-monte-carlo_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "spin_flip_attempts_per_s"
+UNIT = "attempts/s"
+SURVEY_BYTES_PER_ATTEMPT = 42.0  # B_alg = 6 + 6*deg for +-J int8 CSR, deg = 6
+
+
+def ea3d_csr(L: int, seed: int):
+    """3D periodic +-J EA instance of SURVEY.md 8(d) as CSR arrays (site i = x + L*(y + L*z))."""
+    import scipy.sparse as sp
+    rs = np.random.RandomState(seed)
+    N = L ** 3
+    idx = np.arange(N)
+    x, y, z = idx % L, (idx // L) % L, idx // (L * L)
+    nbr = [((x + 1) % L) + L * (y + L * z), x + L * (((y + 1) % L) + L * z), x + L * (y + L * ((z + 1) % L))]
+    v = rs.choice([-1.0, 1.0], size=(3, N)).reshape(-1)
+    rows, cols = np.concatenate([idx, idx, idx]), np.concatenate(nbr)
+    A = sp.coo_matrix((np.concatenate([v, v]), (np.concatenate([rows, cols]), np.concatenate([cols, rows]))),
+                      shape=(N, N)).tocsr()
+    A.sum_duplicates()
+    A.sort_indices()
+    return A
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={device_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows]
+        try:
+            sm = [float(r[0]) for r in rows]
+            reasons = []
+            for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+                if any(r[col].lower().startswith("active") for r in rows):
+                    reasons.append(name)
+            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                    "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+        except Exception:
+            return None
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_rate(L: int, betas, reps: int, sweeps: int, threads: int, seed: int = 5):
+    """attempts/s of the oracle C port (reference algorithm: random-permutation sequential heat bath with an
+    injected MT19937 stream) on `threads` host threads; one call = reps x sweeps sweeps of an L^3 lattice."""
+    from oracle import oracle as O
+    A = ea3d_csr(L, seed)
+    csr = O.Csr(A)
+    n = csr.n
+    rs = np.random.RandomState(1)
+    perm = np.empty((reps, sweeps, n), dtype=np.int32)
+    u = np.empty((reps, sweeps, n), dtype=np.float64)
+    for r in range(reps):
+        for s in range(sweeps):
+            perm[r, s] = rs.permutation(n)
+        u[r] = rs.rand(sweeps, n)
+    m = rs.choice([-1, 1], size=(reps, n)).astype(np.int8)
+    beta_run = np.repeat(np.resize(np.asarray(betas, dtype=np.float64), reps)[:, None], sweeps, axis=1).copy()
+    h = np.zeros(n)
+
+    def once():
+        t0 = time.perf_counter()
+        used = O.lib().nlmc_oracle_mcmc_many(reps, n, csr.rp, csr.ci, csr.val, h, sweeps, beta_run, perm, u, m, threads)
+        return time.perf_counter() - t0, used
+
+    return once, reps * sweeps * n
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    L = args.L
+    cores = os.cpu_count() or 1
+    reps = max(1, min(cores, 64))
+    sweeps = max(1, args.ref_sweeps)
+    betas = np.linspace(0.2, 2.0, args.n_beta)
+    once, attempts = cpu_port_rate(L, betas, reps, sweeps, cores)
+    for _ in range(args.warmup):
+        once()
+    t = 0.0
+    used = cores
+    for _ in range(args.steps):
+        dt, used = once()
+        t += dt
+    value = attempts * args.steps / t
+    sample = f"{reps} replicas x {sweeps} sweeps of the L={L} lattice per step ({attempts:.3g} attempts)"
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args, world, reference=True),
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, world, reference=False):
+    return {"workload": f"C5: 3D +-J Edwards-Anderson L={args.L} ({args.L ** 3} spins) NPT, {args.n_beta} betas x "
+                        f"{args.n_ladders} ladders = {args.n_beta * args.n_ladders} replicas per GPU, "
+                        f"{args.spm} sweeps per swap round, {args.pairs} swapping pairs per ladder",
+            "L": args.L, "n_beta": args.n_beta, "n_ladders_per_gpu": args.n_ladders, "sweeps_per_step": args.spm,
+            "replicas_total": args.n_beta * args.n_ladders * world, "beta_range": [0.2, 2.0],
+            "parallelism": f"replicas: {world} x {args.n_ladders} independent ladders, no data-path collective",
+            "l2": "state (n x words x 4 B) is larger than the 126 MB L2 at the default size; no flush needed"
+            if not reference else "n/a (host)"}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from nlmc_b200 import _lib, host
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank
+    _lib.require_device(device)
+    L, n_beta, n_ladders, spm, pairs = args.L, args.n_beta, args.n_ladders, args.spm, args.pairs
+    betas = np.linspace(0.2, 2.0, n_beta)
+    A = ea3d_csr(L, 5)
+    prob = host.Problem(A, np.zeros(A.shape[0]), device=device)
+    msc = _lib.Msc(prob.inst, betas, n_ladders, seed=1000 + rank)
+    n = prob.n
+    replicas = n_beta * msc.n_ladders
+    attempts_per_step = replicas * n * spm
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- device-resident throughput --------------------------------------------------------------
+    for _ in range(args.warmup):
+        msc.round(spm, pairs)
+    msc.sync()
+    barrier()
+    sampler = ClockSampler(device) if rank == 0 else None
+    t_wall0 = time.perf_counter()
+    msc.timer_mark(0)
+    for _ in range(args.steps):
+        msc.round(spm, pairs)
+    msc.timer_mark(1)
+    msc.sync()
+    ms = msc.timer_elapsed_ms()
+    t_wall1 = time.perf_counter()
+    barrier()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    if dist is not None:
+        t = torch.tensor([ms], device=f"cuda:{device}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = attempts_per_step * world * args.steps / (ms * 1e-3)
+    launches = args.steps * (spm * msc.n_colours + 4)  # sweeps + energy(2) + swap(2) kernels per step
+
+    # ---- dominant kernel alone: the colour sweep ---------------------------------------------------
+    n_time = max(4, spm)
+    msc.sweep(2)
+    msc.sync()
+    msc.timer_mark(0)
+    msc.sweep(n_time)
+    msc.timer_mark(1)
+    msc.sync()
+    sweep_ms = msc.timer_elapsed_ms() / (n_time * msc.n_colours)  # average launch duration
+    attempts_per_launch = replicas * n / msc.n_colours
+    peak, peak_src = measured_peaks()
+    survey_bytes = SURVEY_BYTES_PER_ATTEMPT * attempts_per_launch
+    packed_bytes = 2.0 * (n / msc.n_colours) * msc.n_words * 4  # read the other colour once + write this colour
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": "msc_sweep_kernel (one colour of one sweep)",
+                "achieved": survey_bytes / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": survey_bytes / (sweep_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                "launch_ms": sweep_ms, "attempts_per_launch": attempts_per_launch,
+                "bytes_per_attempt": SURVEY_BYTES_PER_ATTEMPT,
+                "note": "achieved uses SURVEY.md 8(d)'s generic-CSR figure (42 B/attempt); the kernel is bit-packed "
+                        "(32 ladders per word), so its own traffic is far lower -- see roofline_packed and DESIGN.md",
+                "share_of_step": (sweep_ms * spm * msc.n_colours) / (ms / args.steps)}
+    roofline_packed = {"bound": "hbm", "achieved": packed_bytes / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": packed_bytes / (sweep_ms * 1e-3) / 1e9 / peak,
+                       "bytes_per_attempt": packed_bytes / attempts_per_launch,
+                       "note": "bit-packed layout: 0.25 B/attempt compulsory traffic; the kernel is ALU/issue bound "
+                               "(Philox + bit-sliced logic), not HBM bound"}
+
+    # ---- end to end through the host-buffer entry point -------------------------------------------
+    shape = msc.packed_shape()
+    h_in = torch.empty(shape, dtype=torch.int32, pin_memory=True)
+    h_out = torch.empty(shape, dtype=torch.int32, pin_memory=True)
+    h_E = torch.empty((n_beta, msc.n_ladders), dtype=torch.float64, pin_memory=True)
+    msc.get_packed(h_in.numpy().view(np.uint32))  # current device state -> pinned host buffer
+    for _ in range(max(1, args.warmup // 2)):
+        msc.round_host(h_in.data_ptr(), spm, pairs, h_out.data_ptr(), h_E.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        msc.round_host(h_in.data_ptr(), spm, pairs, h_out.data_ptr(), h_E.data_ptr())  # returns after the D2H copies
+        h_in, h_out = h_out, h_in
+    torch.cuda.synchronize(device)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=f"cuda:{device}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": attempts_per_step * world * args.steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(h_in.numel() * 4), "d2h_bytes_per_step": int(h_out.numel() * 4 + h_E.numel() * 8),
+           "ms_per_step": 1e3 * e2e_s / args.steps, "api": "nlmc_msc_round_host (C ABI, pinned host buffers)",
+           "mean_energy_coldest": float(h_E[-1].mean())}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample --------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        reps, sw = max(1, min(cores, 64)), max(1, args.ref_sweeps)
+        once, attempts = cpu_port_rate(L, betas, reps, sw, cores)
+        once()
+        dt, used = once()
+        cpu = {"value": attempts / dt, "unit": UNIT, "cores": used, "kind": "port",
+               "sample": f"{reps} replicas x {sw} sweeps of the L={L} lattice ({attempts:.3g} attempts), "
+                         "oracle/nlmc_oracle.c (reference algorithm, injected MT19937 stream)"}
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "u32 bit-planes (1 bit per spin, 32 ladders per word)", "data": "synthetic",
+               "config": workload_config(args, world), "roofline": roofline, "roofline_packed": roofline_packed,
+               "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+               "per_gpu_value": value / world, "ps_per_attempt": 1e12 / (value / world)}
+        print(json.dumps(out), flush=True)
+    msc.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--L", type=int, default=64)
+    ap.add_argument("--n-beta", dest="n_beta", type=int, default=32)
+    ap.add_argument("--n-ladders", dest="n_ladders", type=int, default=128)
+    ap.add_argument("--spm", type=int, default=16, help="sweeps per swap round (one step)")
+    ap.add_argument("--pairs", type=int, default=10, help="swapping pairs per ladder per round (round(0.3*32), README)")
+    ap.add_argument("--ref-sweeps", dest="ref_sweeps", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        sys.exit("--gpus N > 1 must be launched with torchrun (one process per GPU), e.g.\n"
+                 "  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 "
+                 "--master-port 29500 bench.py --gpus N")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,7 @@
 // lattices, greedy colouring otherwise), all sites of a colour in parallel.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "nlmc_common.cuh"
 
@@ -43,6 +44,7 @@ struct nlmc_msc {
     int8_t *scratch_spins = nullptr;  // [n]
     unsigned long long seed = 0;
     uint32_t sweep_counter = 0, round_counter = 0;
+    int k_steps = 6;  // unconditional bit steps of the Bernoulli comparison (tuning knob NLMC_MSC_STEPS)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<double> h_betas;
@@ -99,6 +101,14 @@ __device__ __forceinline__ void count6(uint32_t a0, uint32_t a1, uint32_t a2, ui
 __device__ __forceinline__ uint32_t comp(const uint4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
 
 // One colour of one sweep: a warp per (site, 128-word chunk), a lane per four consecutive words.
+//
+// The Bernoulli draw g ~ B(q(|f|)) of all 128 lanes of a thread is a bit-serial comparison u < T_level,
+// most significant bit first.  kSteps steps run unconditionally (fully unrolled: no exit test, no
+// divergence); after them a lane is still undecided with probability 2^-kSteps, and those few lanes
+// are finished one by one against the remaining threshold bits with a fresh 32-bit uniform each
+// (exactly the conditional probability).  ncu on the first version (early-exit loop) showed the kernel
+// ALU-pipe bound with 29% of the lanes idle in the loop tail; see profiles/.
+template <int kSteps>
 __global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int n_sites, uint32_t sweep) {
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -121,40 +131,62 @@ __global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int
             x[d] = make_uint4(v, v, v, v);
         }
     }
-    uint32_t m0[4], m1[4], pos[4], res[4], und[4];
+    // lane sets of the |f| levels 1..3 (|f| = 2, 4, 6), level 0 being the rest; sign plane pos = [c >= 4]
+    uint32_t I1[4], I2[4], I3[4], pos[4], res[4], und[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         uint32_t c0, c1, c2;
         count6(comp(x[0], k), comp(x[1], k), comp(x[2], k), comp(x[3], k), comp(x[4], k), comp(x[5], k), c0, c1, c2);
-        // |f|/2 = |c - 3| as two bit planes (m1 m0); sign plane pos = [c >= 4]
-        m0[k] = ~c0;
-        m1[k] = (c2 & (c1 | c0)) | (~c2 & ~c1);
+        const uint32_t m0 = ~c0;                                 // |c - 3| = (m1 m0)
+        const uint32_t m1 = (c2 & (c1 | c0)) | (~c2 & ~c1);
+        I1[k] = ~m1 & m0;
+        I2[k] = m1 & ~m0;
+        I3[k] = m1 & m0;
         pos[k] = c2;
-        res[k] = 0u;
-        und[k] = 0xffffffffu;
     }
     const int b = word0 / a.G;  // the four words of a lane share one beta (G % 4 == 0)
     const uint32_t T1 = __ldg(a.thr + b * 4 + 1), T2 = __ldg(a.thr + b * 4 + 2), T3 = __ldg(a.thr + b * 4 + 3);
     const Philox rng{a.seed_lo, a.seed_hi ^ kTagSweep};
-    for (int p = 0; p < 32; ++p) {
-        // bit p (MSB first) of each level's threshold, spread to a full mask
-        const uint32_t L0 = p == 0 ? 0xffffffffu : 0u;  // q(0) = 1/2 = 0x80000000 / 2^32
-        const uint32_t L1 = (uint32_t)((int32_t)(T1 << p) >> 31);
-        const uint32_t L2 = (uint32_t)((int32_t)(T2 << p) >> 31);
-        const uint32_t L3 = (uint32_t)((int32_t)(T3 << p) >> 31);
-        const uint4 r4 = rng((uint32_t)site, (uint32_t)(word0 >> 2), sweep, (uint32_t)p);
-        uint32_t any = 0u;
+    {   // step 0: level-0 lanes (q = 1/2) are decided by the first bit alone: g = ~r
+        const uint4 r4 = rng((uint32_t)site, (uint32_t)(word0 >> 2), sweep, 0u);
+        const bool p1 = (T1 >> 31) & 1u, p2 = (T2 >> 31) & 1u, p3 = (T3 >> 31) & 1u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t r = comp(r4, k);
-            const uint32_t lo = (m0[k] & L1) | (~m0[k] & L0);
-            const uint32_t hi = (m0[k] & L3) | (~m0[k] & L2);
-            const uint32_t t = (m1[k] & hi) | (~m1[k] & lo);
+            const uint32_t I0 = ~(I1[k] | I2[k] | I3[k]);
+            const uint32_t t = (p1 ? I1[k] : 0u) | (p2 ? I2[k] : 0u) | (p3 ? I3[k] : 0u);
+            res[k] = ~r & (t | I0);
+            und[k] = ~(r ^ t) & ~I0;
+        }
+    }
+#pragma unroll
+    for (int p = 1; p < kSteps; ++p) {
+        const uint4 r4 = rng((uint32_t)site, (uint32_t)(word0 >> 2), sweep, (uint32_t)p);
+        const bool p1 = (T1 >> (31 - p)) & 1u, p2 = (T2 >> (31 - p)) & 1u, p3 = (T3 >> (31 - p)) & 1u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t r = comp(r4, k);
+            const uint32_t t = (p1 ? I1[k] : 0u) | (p2 ? I2[k] : 0u) | (p3 ? I3[k] : 0u);
             res[k] |= und[k] & ~r & t;   // uniform bit 0, threshold bit 1  -> u < T decided
             und[k] &= ~(r ^ t);          // still equal on this prefix
-            any |= und[k];
         }
-        if (any == 0u) break;
+    }
+    // stragglers: each gets a fresh 32-bit uniform against the remaining threshold bits.  One Philox call
+    // serves the lowest undecided lane of each of the four words, so the warp iterates
+    // max-over-threads-and-words(#undecided per word) times (about 1.3 at kSteps = 8).
+    if (und[0] | und[1] | und[2] | und[3]) {
+        const uint32_t R1 = T1 << kSteps, R2 = T2 << kSteps, R3 = T3 << kSteps;
+        uint32_t call = 32u;
+        do {
+            const uint4 r4 = rng((uint32_t)site, (uint32_t)(word0 >> 2), sweep, call++);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t bit = und[k] & (0u - und[k]);  // 0 when the word has no straggler
+                const uint32_t rem = (I3[k] & bit) ? R3 : (I2[k] & bit) ? R2 : R1;  // level 0 never gets here
+                if (comp(r4, k) < rem) res[k] |= bit;
+                und[k] ^= bit;
+            }
+        } while (und[0] | und[1] | und[2] | und[3]);
     }
     uint4 out;
     out.x = pos[0] ^ res[0];
@@ -354,7 +386,17 @@ static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
             if (cnt == 0) continue;
             const long long warps = (long long)cnt * chunks;
             const unsigned blocks = (unsigned)((warps + 7) / 8);
-            msc_sweep_kernel<<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter);
+            switch (M->k_steps) {
+                case 3: msc_sweep_kernel<3><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
+                case 4: msc_sweep_kernel<4><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
+                case 5: msc_sweep_kernel<5><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
+                case 9: msc_sweep_kernel<9><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
+                case 7: msc_sweep_kernel<7><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
+                case 8: msc_sweep_kernel<8><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
+                case 10: msc_sweep_kernel<10><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
+                case 12: msc_sweep_kernel<12><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
+                default: msc_sweep_kernel<6><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
+            }
         }
         ++M->sweep_counter;
     }
@@ -490,6 +532,7 @@ int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_lad
     M->colour_ptr = colour_ptr;
     M->seed = seed;
     M->h_betas.assign(betas, betas + n_beta);
+    if (const char *e = getenv("NLMC_MSC_STEPS")) M->k_steps = atoi(e);
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(n_beta, betas);
     const size_t words = (size_t)n * M->W;
     bool ok = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking) == cudaSuccess &&
