@@ -67,7 +67,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={device_index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -194,7 +194,8 @@ def run_ours(args, rank, world, local_rank):
     betas = np.linspace(0.2, 2.0, n_beta)
     A = ea3d_csr(L, 5)
     prob = host.Problem(A, np.zeros(A.shape[0]), device=device)
-    msc = _lib.Msc(prob.inst, betas, n_ladders, seed=1000 + rank)
+    # every rank owns its own block of ladders; streams are keyed by the global ladder index
+    msc = _lib.Msc(prob.inst, betas, n_ladders, seed=1000, ladder_offset=rank * (((n_ladders + 127) // 128) * 128))
     n = prob.n
     replicas = n_beta * msc.n_ladders
     attempts_per_step = replicas * n * spm
@@ -308,7 +309,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--L", type=int, default=64)

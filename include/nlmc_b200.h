@@ -142,7 +142,10 @@ int nlmc_icm_clusters(nlmc_instance *inst, int n_pairs, const int8_t *s1 /*[n_pa
  *                       the device state), packed states and energies out (either may be NULL).
  *   nlmc_msc_set/get_spins     one replica (beta_idx, ladder) as int8 +-1.
  *   nlmc_msc_timer_*    CUDA-event timing on the handle's stream (mark 0 = start, 1 = stop). */
-int nlmc_msc_create(nlmc_instance *inst, int n_beta, const double *betas, int n_ladders,
+/* ladder_offset: global index of this handle's first ladder (a multiple of 128).  Every random stream is
+ * keyed by (seed, beta index, GLOBAL ladder index, site, sweep), so a set of ladders evolves identically
+ * whether it lives in one handle or is sharded over several handles / GPUs. */
+int nlmc_msc_create(nlmc_instance *inst, int n_beta, const double *betas, int n_ladders, int ladder_offset,
                     unsigned long long seed, nlmc_msc **out);
 int nlmc_msc_destroy(nlmc_msc *msc);
 int nlmc_msc_info(const nlmc_msc *msc, int *n_words, int *n_ladders_padded, int *n_colours, long long *n_bonds);

@@ -29,6 +29,7 @@
 struct nlmc_msc {
     nlmc_instance *inst = nullptr;
     int n = 0, W = 0, n_beta = 0, n_ladders = 0, G = 0, n_colours = 0;
+    int ladder_offset = 0;        // global index of this handle's first ladder (multiple of 128)
     long long n_bonds = 0;
     uint32_t *S = nullptr;        // [n][W]
     int32_t *nbr = nullptr;       // [n][6]  (-1 = padding)
@@ -76,7 +77,7 @@ struct Philox {
 };
 
 struct MscDev {
-    int n, W, G, n_beta;
+    int n, W, G, n_beta, quad_offset;  // quad_offset = ladder_offset / 128: global index of ladder quad 0
     uint32_t *S;
     const int32_t *nbr;
     const uint32_t *meta;
@@ -147,8 +148,10 @@ __global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int
     const int b = word0 / a.G;  // the four words of a lane share one beta (G % 4 == 0)
     const uint32_t T1 = __ldg(a.thr + b * 4 + 1), T2 = __ldg(a.thr + b * 4 + 2), T3 = __ldg(a.thr + b * 4 + 3);
     const Philox rng{a.seed_lo, a.seed_hi ^ kTagSweep};
+    // stream id = (beta index, GLOBAL ladder quad): independent of how ladders are sharded over handles/GPUs
+    const uint32_t sid = ((uint32_t)b << 20) | (uint32_t)(a.quad_offset + ((word0 - b * a.G) >> 2));
     {   // step 0: level-0 lanes (q = 1/2) are decided by the first bit alone: g = ~r
-        const uint4 r4 = rng((uint32_t)site, (uint32_t)(word0 >> 2), sweep, 0u);
+        const uint4 r4 = rng((uint32_t)site, sid, sweep, 0u);
         const bool p1 = (T1 >> 31) & 1u, p2 = (T2 >> 31) & 1u, p3 = (T3 >> 31) & 1u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int
     }
 #pragma unroll
     for (int p = 1; p < kSteps; ++p) {
-        const uint4 r4 = rng((uint32_t)site, (uint32_t)(word0 >> 2), sweep, (uint32_t)p);
+        const uint4 r4 = rng((uint32_t)site, sid, sweep, (uint32_t)p);
         const bool p1 = (T1 >> (31 - p)) & 1u, p2 = (T2 >> (31 - p)) & 1u, p3 = (T3 >> (31 - p)) & 1u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int
         const uint32_t R1 = T1 << kSteps, R2 = T2 << kSteps, R3 = T3 << kSteps;
         uint32_t call = 32u;
         do {
-            const uint4 r4 = rng((uint32_t)site, (uint32_t)(word0 >> 2), sweep, call++);
+            const uint4 r4 = rng((uint32_t)site, sid, sweep, call++);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t bit = und[k] & (0u - und[k]);  // 0 when the word has no straggler
@@ -198,12 +201,14 @@ __global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int
 
 // Uniform random initial spins (the production counterpart of sign(2*rand-1), NPT/npt.py:612).
 __global__ void msc_init_kernel(MscDev a, uint32_t stream_id) {
-    const size_t quad = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const size_t n_quads = (size_t)a.n * a.W / 4;
-    if (quad >= n_quads) return;
+    const size_t quad = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // (site, word quad)
+    const int qpr = a.W / 4;  // quads per site row
+    if (quad >= (size_t)a.n * qpr) return;
+    const int site = (int)(quad / qpr), word0 = (int)(quad % qpr) * 4;
+    const int b = word0 / a.G;
+    const uint32_t sid = ((uint32_t)b << 20) | (uint32_t)(a.quad_offset + ((word0 - b * a.G) >> 2));
     const Philox rng{a.seed_lo, a.seed_hi ^ kTagInit};
-    const uint4 r = rng((uint32_t)quad, (uint32_t)(quad >> 32), stream_id, 0u);
-    reinterpret_cast<uint4 *>(a.S)[quad] = r;
+    reinterpret_cast<uint4 *>(a.S)[quad] = rng((uint32_t)site, sid, stream_id, 0u);
 }
 
 // K4': per (word, lane) sum over sites of the number of unsatisfied bonds at the site, with bit-sliced
@@ -287,7 +292,7 @@ __global__ void msc_energy_finish_kernel(int W, int G, int n_ladders, long long 
 constexpr int kMaxBeta = 128;
 __global__ void msc_swap_decide_kernel(int n_beta, int n_ladders, int G, int num_pairs, const double *betas, double *E,
                                        uint32_t *swapmask, int32_t *accepted, uint32_t seed_lo, uint32_t seed_hi,
-                                       uint32_t round) {
+                                       uint32_t round, int ladder_offset) {
     const int ladder = blockIdx.x * blockDim.x + threadIdx.x;
     if (ladder >= n_ladders) return;
     const Philox rng{seed_lo, seed_hi ^ kTagSwap};
@@ -296,7 +301,7 @@ __global__ void msc_swap_decide_kernel(int n_beta, int n_ladders, int G, int num
     for (int i = 0; i < n_beta - 1; ++i) avail[i] = 1;
     int acc = 0;
     for (int k = 0; k < num_pairs && n_avail > 0; ++k) {
-        const uint4 r = rng((uint32_t)ladder, round, (uint32_t)k, 0u);
+        const uint4 r = rng((uint32_t)(ladder + ladder_offset), round, (uint32_t)k, 0u);
         int pick = (int)(((unsigned long long)r.x * (unsigned)n_avail) >> 32);
         int i = 0;
         for (;; ++i)
@@ -371,7 +376,7 @@ static std::vector<uint32_t> msc_thresholds(int n_beta, const double *betas) {
 
 static MscDev dev_view(const nlmc_msc *M) {
     MscDev d;
-    d.n = M->n; d.W = M->W; d.G = M->G; d.n_beta = M->n_beta;
+    d.n = M->n; d.W = M->W; d.G = M->G; d.n_beta = M->n_beta; d.quad_offset = M->ladder_offset / 128;
     d.S = M->S; d.nbr = M->nbr; d.meta = M->meta; d.site_list = M->site_list; d.thr = M->thr;
     d.seed_lo = (uint32_t)M->seed; d.seed_hi = (uint32_t)(M->seed >> 32);
     return d;
@@ -423,7 +428,7 @@ static int launch_swap(nlmc_msc *M, int num_pairs) {
     NLMC_CUDA(cudaMemsetAsync(M->swapmask, 0, sizeof(uint32_t) * (size_t)(M->n_beta - 1) * M->G, M->stream));
     msc_swap_decide_kernel<<<(M->n_ladders + 127) / 128, 128, 0, M->stream>>>(
         M->n_beta, M->n_ladders, M->G, num_pairs, M->betas, M->E, M->swapmask, M->accepted, d.seed_lo, d.seed_hi,
-        M->round_counter);
+        M->round_counter, M->ladder_offset);
     const size_t items = (size_t)M->n * M->G;
     msc_swap_apply_kernel<<<(unsigned)((items + 255) / 256), 256, 0, M->stream>>>(d, M->swapmask);
     ++M->round_counter;
@@ -448,13 +453,14 @@ int nlmc_msc_destroy(nlmc_msc *M) {
     return NLMC_OK;
 }
 
-int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_ladders, unsigned long long seed,
-                    nlmc_msc **out) {
+int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_ladders, int ladder_offset,
+                    unsigned long long seed, nlmc_msc **out) {
     using namespace nlmc;
     NLMC_REQUIRE(I && out && betas, "nlmc_msc_create: NULL argument");
     *out = nullptr;
     NLMC_REQUIRE(n_beta >= 1 && n_beta <= kMaxBeta, "nlmc_msc_create: n_beta must be in [1, %d]", kMaxBeta);
     NLMC_REQUIRE(n_ladders >= 1, "nlmc_msc_create: n_ladders must be >= 1");
+    NLMC_REQUIRE(ladder_offset >= 0 && ladder_offset % 128 == 0, "nlmc_msc_create: ladder_offset must be a multiple of 128");
     const int n = I->n;
     // eligibility: J in {-1,+1} off the diagonal, h = 0, even degrees <= 6
     std::vector<int32_t> nbr((size_t)n * 6, -1);
@@ -525,6 +531,7 @@ int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_lad
     M->n = n;
     M->n_beta = n_beta;
     M->n_ladders = ((n_ladders + 127) / 128) * 128;
+    M->ladder_offset = ladder_offset;
     M->G = M->n_ladders / 32;
     M->W = n_beta * M->G;
     M->n_colours = n_colours;

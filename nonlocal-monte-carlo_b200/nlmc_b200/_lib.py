@@ -53,7 +53,7 @@ _SIGNATURES = {
     "nlmc_lbp_reset": [_vp, _f64],
     "nlmc_lbp_step": [_vp, _dbl, _dbl, _dbl, _int, _vp, C.POINTER(_int)],
     "nlmc_icm_clusters": [_vp, _int, _i8, _i8, _i32, _i32],
-    "nlmc_msc_create": [_vp, _int, _f64, _int, C.c_ulonglong, C.POINTER(_vp)],
+    "nlmc_msc_create": [_vp, _int, _f64, _int, _int, C.c_ulonglong, C.POINTER(_vp)],
     "nlmc_msc_destroy": [_vp],
     "nlmc_msc_info": [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), C.POINTER(C.c_longlong)],
     "nlmc_msc_set_seed": [_vp, C.c_ulonglong, C.c_uint],
@@ -269,14 +269,15 @@ class Replicas:
 class Msc:
     """Bit-packed production state (K2/K4'/K6): n_beta x n_ladders replicas of a +-J instance."""
 
-    def __init__(self, inst: Instance, betas, n_ladders: int, seed: int = 0):
+    def __init__(self, inst: Instance, betas, n_ladders: int, seed: int = 0, ladder_offset: int = 0):
         self.inst = inst
+        self.ladder_offset = int(ladder_offset)
         self.n = inst.n
         self.betas = np.ascontiguousarray(betas, dtype=np.float64).reshape(-1)
         self.n_beta = len(self.betas)
         handle = _vp()
-        check(lib().nlmc_msc_create(inst._h, self.n_beta, self.betas, int(n_ladders), int(seed) & (2**64 - 1),
-                                    C.byref(handle)), "nlmc_msc_create")
+        check(lib().nlmc_msc_create(inst._h, self.n_beta, self.betas, int(n_ladders), self.ladder_offset,
+                                    int(seed) & (2**64 - 1), C.byref(handle)), "nlmc_msc_create")
         self._h = handle
         w, lad, col, nb = _int(), _int(), _int(), C.c_longlong()
         check(lib().nlmc_msc_info(self._h, C.byref(w), C.byref(lad), C.byref(col), C.byref(nb)), "nlmc_msc_info")

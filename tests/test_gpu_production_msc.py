@@ -256,3 +256,24 @@ def test_npt_production_mode_api(nl, tmp_cwd):
         Er = O.energy(csr, h, M[r * 64:(r + 1) * 64, :5].T.astype(np.int8))
         assert E[r] == Er.min()
     assert obj.energies_all_runs.shape == (4, 3)
+
+
+def test_sharding_invariance(nl):
+    """256 ladders in one handle evolve bit-identically to two handles of 128 ladders with ladder offsets 0 and
+    128 (same seed): the property that makes N-GPU results identical to 1-GPU results."""
+    from oracle import oracle as O
+    A, h = O.ea3d_pm_j(6, 9)
+    prob = nl.host.Problem(A, h)
+    betas = np.array([0.4, 0.8, 1.2])
+    whole = nl.lib.Msc(prob.inst, betas, 256, seed=77)
+    parts = [nl.lib.Msc(prob.inst, betas, 128, seed=77, ladder_offset=off) for off in (0, 128)]
+    for m in [whole] + parts:
+        for _ in range(3):
+            m.round(4, 1)
+    Pw = whole.get_packed().reshape(prob.n, 3, 8)  # [site][beta][group]
+    Ew = whole.energies()
+    for i, part in enumerate(parts):
+        Pp = part.get_packed().reshape(prob.n, 3, 4)
+        assert np.array_equal(Pw[:, :, 4 * i:4 * i + 4], Pp)
+        assert np.array_equal(Ew[:, 128 * i:128 * (i + 1)], part.energies())
+    assert whole.swap_count() == sum(p.swap_count() for p in parts) > 0
