@@ -36,6 +36,7 @@ extern "C" {
 typedef struct nlmc_instance nlmc_instance; /* one Ising instance (J in CSR, h) resident in HBM */
 typedef struct nlmc_replicas nlmc_replicas; /* R int8 spin configurations of one instance (exact path) */
 typedef struct nlmc_msc nlmc_msc;           /* bit-packed replica lattice for the production path  */
+typedef struct nlmc_dense nlmc_dense;       /* dense-J production path (tensor-core field contraction) */
 
 const char *nlmc_last_error(void);
 int nlmc_version(void);
@@ -167,6 +168,29 @@ int nlmc_msc_swap_count(nlmc_msc *msc, int *out_accepted, int reset);
 int nlmc_msc_sync(nlmc_msc *msc);
 int nlmc_msc_timer_mark(nlmc_msc *msc, int which);
 int nlmc_msc_timer_elapsed_ms(nlmc_msc *msc, float *out_ms);
+
+/* ---- K3: dense-J production path (config C3, Sherrington-Kirkpatrick) ---------------------------
+ * The reference evaluates x = J.dot(m) + h for every attempt (NMC/nmc.py:86).  Here all replicas share J, so
+ * the fields of a block of 128 sites for ALL replicas are one tensor-core GEMM H_blk = S . J[:, blk]
+ * (tcgen05.mma, bf16 spins -- exact -- times J split into n_split bf16 pieces, fp32 accumulation in TMEM);
+ * a sweep visits the blocks in order and updates the sites of a block sequentially per replica with the
+ * in-block flips corrected on CUDA cores: a fixed-order sequential heat-bath sweep, Philox randoms.
+ *   betas [n_replicas]: one inverse temperature per replica (PT exchanges swap these labels);
+ *   nlmc_dense_fields    full recompute H = S . J (out_H [R][n], optional) -- 2*R*n^2*n_split flop;
+ *   nlmc_dense_energies  E = -(m^T J m/2 + m^T h) from those fields (fp32 products, fp64 accumulation);
+ *   nlmc_dense_time_*    CUDA-event timings of the GEMM / of whole sweeps (ms per call). */
+int nlmc_dense_create(nlmc_instance *inst, int n_replicas, const double *betas, int n_split,
+                      unsigned long long seed, nlmc_dense **out);
+int nlmc_dense_destroy(nlmc_dense *d);
+int nlmc_dense_set_betas(nlmc_dense *d, const double *betas /*[n_replicas]*/);
+int nlmc_dense_set_spins(nlmc_dense *d, const int8_t *spins /*[n_replicas][n]*/);
+int nlmc_dense_get_spins(nlmc_dense *d, int8_t *out /*[n_replicas][n]*/);
+int nlmc_dense_fields(nlmc_dense *d, float *out_H /*[n_replicas][n] or NULL*/);
+int nlmc_dense_sweep(nlmc_dense *d, int n_sweeps);
+int nlmc_dense_energies(nlmc_dense *d, double *out_E /*[n_replicas]*/);
+int nlmc_dense_sync(nlmc_dense *d);
+int nlmc_dense_time_fields(nlmc_dense *d, int repeats, float *out_ms);
+int nlmc_dense_time_sweeps(nlmc_dense *d, int n_sweeps, float *out_ms);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,17 @@ _SIGNATURES = {
     "nlmc_msc_sync": [_vp],
     "nlmc_msc_timer_mark": [_vp, _int],
     "nlmc_msc_timer_elapsed_ms": [_vp, C.POINTER(C.c_float)],
+    "nlmc_dense_create": [_vp, _int, _f64, _int, C.c_ulonglong, C.POINTER(_vp)],
+    "nlmc_dense_destroy": [_vp],
+    "nlmc_dense_set_betas": [_vp, _f64],
+    "nlmc_dense_set_spins": [_vp, _i8],
+    "nlmc_dense_get_spins": [_vp, _i8],
+    "nlmc_dense_fields": [_vp, _vp],
+    "nlmc_dense_sweep": [_vp, _int],
+    "nlmc_dense_energies": [_vp, _f64],
+    "nlmc_dense_sync": [_vp],
+    "nlmc_dense_time_fields": [_vp, _int, C.POINTER(C.c_float)],
+    "nlmc_dense_time_sweeps": [_vp, _int, C.POINTER(C.c_float)],
 }
 
 
@@ -356,6 +367,73 @@ class Msc:
     def close(self):
         if getattr(self, "_h", None):
             lib().nlmc_msc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Dense:
+    """Dense-J production state (K3): R replicas, field contraction H = S.J on tcgen05 tensor cores."""
+
+    def __init__(self, inst: Instance, betas, n_split: int = 3, seed: int = 0):
+        self.inst = inst
+        self.n = inst.n
+        self.betas = np.ascontiguousarray(betas, dtype=np.float64).reshape(-1)
+        self.R = len(self.betas)
+        self.n_split = int(n_split)
+        handle = _vp()
+        check(lib().nlmc_dense_create(inst._h, self.R, self.betas, self.n_split, int(seed) & (2**64 - 1),
+                                      C.byref(handle)), "nlmc_dense_create")
+        self._h = handle
+
+    def set_betas(self, betas):
+        b = np.ascontiguousarray(betas, dtype=np.float64).reshape(-1)
+        assert len(b) == self.R
+        check(lib().nlmc_dense_set_betas(self._h, b), "nlmc_dense_set_betas")
+        self.betas = b
+
+    def set_spins(self, spins):
+        s = np.ascontiguousarray(spins, dtype=np.int8).reshape(self.R, self.n)
+        check(lib().nlmc_dense_set_spins(self._h, s), "nlmc_dense_set_spins")
+
+    def get_spins(self) -> np.ndarray:
+        out = np.empty((self.R, self.n), dtype=np.int8)
+        check(lib().nlmc_dense_get_spins(self._h, out), "nlmc_dense_get_spins")
+        return out
+
+    def fields(self, fetch: bool = True):
+        out = np.empty((self.R, self.n), dtype=np.float32) if fetch else None
+        check(lib().nlmc_dense_fields(self._h, _ptr(out)), "nlmc_dense_fields")
+        return out
+
+    def sweep(self, n_sweeps: int):
+        check(lib().nlmc_dense_sweep(self._h, int(n_sweeps)), "nlmc_dense_sweep")
+
+    def energies(self) -> np.ndarray:
+        out = np.empty(self.R, dtype=np.float64)
+        check(lib().nlmc_dense_energies(self._h, out), "nlmc_dense_energies")
+        return out
+
+    def sync(self):
+        check(lib().nlmc_dense_sync(self._h), "nlmc_dense_sync")
+
+    def time_fields(self, repeats: int = 10) -> float:
+        v = C.c_float()
+        check(lib().nlmc_dense_time_fields(self._h, int(repeats), C.byref(v)), "nlmc_dense_time_fields")
+        return float(v.value)
+
+    def time_sweeps(self, n_sweeps: int = 2) -> float:
+        v = C.c_float()
+        check(lib().nlmc_dense_time_sweeps(self._h, int(n_sweeps), C.byref(v)), "nlmc_dense_time_sweeps")
+        return float(v.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nlmc_dense_destroy(self._h)
             self._h = None
 
     def __del__(self):
