@@ -188,6 +188,14 @@ int nlmc_dense_get_spins(nlmc_dense *d, int8_t *out /*[n_replicas][n]*/);
 int nlmc_dense_fields(nlmc_dense *d, float *out_H /*[n_replicas][n] or NULL*/);
 int nlmc_dense_sweep(nlmc_dense *d, int n_sweeps);
 int nlmc_dense_energies(nlmc_dense *d, double *out_E /*[n_replicas]*/);
+/* NMC phases on the dense path (NMC/nmc.py:377-385,398-406): modes [n_replicas][n], 0 = normal, 1 = backbone at
+ * beta/temp_x (the reference divides the backbone rows of J and h by temp_x), 2 = frozen (the reference pins
+ * the spin with h = +-1e4); NULL switches the modes off. */
+int nlmc_dense_set_site_modes(nlmc_dense *d, const uint8_t *modes, double temp_x);
+/* m_init = M[:, argmin E] bookkeeping on the device (first minimum wins, nmc.py:394-395) */
+int nlmc_dense_best_reset(nlmc_dense *d);
+int nlmc_dense_best_update(nlmc_dense *d, double *out_E /*[n_replicas] or NULL*/);
+int nlmc_dense_best_get(nlmc_dense *d, int8_t *out_spins /*[n_replicas][n] or NULL*/, double *out_E /*or NULL*/);
 int nlmc_dense_sync(nlmc_dense *d);
 int nlmc_dense_time_fields(nlmc_dense *d, int repeats, float *out_ms);
 int nlmc_dense_time_sweeps(nlmc_dense *d, int n_sweeps, float *out_ms);

@@ -266,6 +266,11 @@ struct nlmc_dense {
     float *Ht = nullptr;               // [n_pad][R_pad] fields, transposed
     float *beta = nullptr;             // [R_pad]
     double *E = nullptr;               // [R_pad]
+    double *bestE = nullptr;           // [R_pad] lowest energy seen since nlmc_dense_best_reset
+    uint16_t *bestS = nullptr;         // [R_pad][n_pad] configuration of that energy
+    uint8_t *modes = nullptr;          // [R_pad][n_pad] per-site NMC phase mode: 0 normal, 1 hot (beta/temp_x), 2 frozen
+    bool modes_on = false;
+    float temp_x = 1.0f;
     CUtensorMap map_S, map_J[3];
     unsigned long long seed = 0;
     uint32_t *d_sweep = nullptr;       // [1] sweep counter on the device (read by the kernels of the captured graph)
@@ -336,7 +341,8 @@ __global__ void __launch_bounds__(128) dense_block_update_kernel(int n, int n_pa
                                                                  const float *__restrict__ Jf, const float *__restrict__ hf,
                                                                  const float *__restrict__ beta, uint16_t *S,
                                                                  uint32_t seed_lo, uint32_t seed_hi,
-                                                                 const uint32_t *__restrict__ sweep_ptr, float *Ht_zero) {
+                                                                 const uint32_t *__restrict__ sweep_ptr, float *Ht_zero,
+                                                                 const uint8_t *__restrict__ modes, float temp_x) {
     extern __shared__ __align__(16) uint8_t dsm[];
     const uint32_t sweep = *sweep_ptr;
     float *Jt = reinterpret_cast<float *>(dsm);                        // [kBlk j][kBlk k] = J[c0+k][c0+j] (transposed)
@@ -363,6 +369,7 @@ __global__ void __launch_bounds__(128) dense_block_update_kernel(int n, int n_pa
         for (int i = tid; i < kRepPerCta * kBlk; i += 128) Ht_zero[(size_t)(i / kRepPerCta) * R_pad + r0 + (i % kRepPerCta)] = 0.f;
     __syncthreads();
     const float inv2b = 0.5f / beta[r];
+    const uint8_t *mrow = modes ? modes + (size_t)r * n_pad + c0 : nullptr;
     const PhiloxD rng{seed_lo, seed_hi ^ 0x44454e53u};
     const int k_end = min(kBlk, n - c0);
     float *frow = fld + rep * kBlk;
@@ -391,11 +398,20 @@ __global__ void __launch_bounds__(128) dense_block_update_kernel(int n, int n_pa
             const float u = ((float)(ub[i] >> 8) + 0.5f) * (1.0f / 16777216.0f);
             theta[i] = (__logf(u) - __logf(1.0f - u)) * inv2b;
         }
+        uint32_t frozen = 0;  // NMC phases: frozen sites keep their spin (the reference pins them with h = +-1e4)
+        if (mrow != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint8_t md = mrow[base + i];
+                if (md == 1) theta[i] *= temp_x;
+                frozen |= (uint32_t)(md == 2) << i;
+            }
+        }
         uint32_t newbits = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const bool live = base + i < k_end;
-            const bool up = F[i] > theta[i];
+            const bool live = (base + i < k_end) && !((frozen >> i) & 1u);
+            const bool up = live ? (F[i] > theta[i]) : (dp[i] == 0.0f);  // not live: keep the old spin
             d[i] = live ? (up ? dp[i] : dm[i]) : 0.0f;
             newbits |= (uint32_t)up << i;
 #pragma unroll
@@ -454,6 +470,25 @@ __global__ void dense_energy_kernel(int n, int n_pad, int R_pad, const float *__
 
 __global__ void dense_bump_kernel(uint32_t *counter) { *counter += 1u; }
 
+// NMC bookkeeping m_init = M[:, argmin E] (first minimum wins, NMC/nmc.py:394-395): one CTA per replica copies
+// the row when the current energy is strictly below the best seen since the last reset.
+__global__ void dense_best_kernel(int n_pad, const double *__restrict__ E, double *bestE, const uint16_t *__restrict__ S,
+                                  uint16_t *bestS) {
+    const int r = blockIdx.x;
+    const bool better = E[r] < bestE[r];
+    if (better) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(S + (size_t)r * n_pad);
+        uint4 *dst = reinterpret_cast<uint4 *>(bestS + (size_t)r * n_pad);
+        for (int i = threadIdx.x; i < n_pad / 8; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (better && threadIdx.x == 0) bestE[r] = E[r];
+}
+__global__ void dense_fill_kernel(int count, double *p, double v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) p[i] = v;
+}
+
 __global__ void dense_pack_kernel(int n, int n_pad, int R, const int8_t *in, uint16_t *S) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= (size_t)R * n) return;
@@ -485,7 +520,7 @@ extern "C" {
 int nlmc_dense_destroy(nlmc_dense *D) {
     if (!D) return NLMC_OK;
     cudaSetDevice(D->inst->device);
-    void *ptrs[] = {D->S, D->Jp[0], D->Jp[1], D->Jp[2], D->Jf, D->hf, D->Ht, D->beta, D->E, D->d_sweep};
+    void *ptrs[] = {D->S, D->Jp[0], D->Jp[1], D->Jp[2], D->Jf, D->hf, D->Ht, D->beta, D->E, D->d_sweep, D->bestE, D->bestS, D->modes};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (D->sweep_graph) cudaGraphExecDestroy(D->sweep_graph);
     if (D->ev0) cudaEventDestroy(D->ev0);
@@ -647,7 +682,7 @@ static int enqueue_sweep(nlmc_dense *D, int k_splits) {
         float *zero_next = (k_splits > 1 && c0 + kBlk < D->n) ? D->Ht + (size_t)(c0 + kBlk) * D->R_pad : nullptr;
         dense_block_update_kernel<<<(unsigned)(D->R_pad / kRepPerCta), 128, kUpdateSmem, D->stream>>>(
             D->n, D->n_pad, D->R_pad, c0, D->Ht, D->Jf, D->hf, D->beta, D->S, (uint32_t)D->seed, (uint32_t)(D->seed >> 32),
-            D->d_sweep, zero_next);
+            D->d_sweep, zero_next, D->modes_on ? D->modes : nullptr, D->temp_x);
     }
     dense_bump_kernel<<<1, 1, 0, D->stream>>>(D->d_sweep);
     NLMC_CUDA(cudaGetLastError());
@@ -693,6 +728,83 @@ int nlmc_dense_energies(nlmc_dense *D, double *out_E) {
     NLMC_CUDA(cudaGetLastError());
     NLMC_CUDA(cudaMemcpyAsync(out_E, D->E, sizeof(double) * (size_t)D->R, cudaMemcpyDeviceToHost, D->stream));
     NLMC_CUDA(cudaStreamSynchronize(D->stream));
+    return NLMC_OK;
+}
+
+int nlmc_dense_set_site_modes(nlmc_dense *D, const uint8_t *modes, double temp_x) {
+    NLMC_REQUIRE(D, "nlmc_dense_set_site_modes: NULL handle");
+    NLMC_REQUIRE(!modes || temp_x > 0.0, "nlmc_dense_set_site_modes: temp_x must be positive");
+    NLMC_CUDA(cudaSetDevice(D->inst->device));
+    const bool was_on = D->modes_on;
+    if (!modes) {
+        D->modes_on = false;
+    } else {
+        if (!D->modes) {
+            NLMC_CUDA(cudaMalloc(&D->modes, (size_t)D->R_pad * D->n_pad));
+            NLMC_CUDA(cudaMemset(D->modes, 0, (size_t)D->R_pad * D->n_pad));
+        }
+        NLMC_CUDA(cudaMemcpy2DAsync(D->modes, (size_t)D->n_pad, modes, (size_t)D->n, (size_t)D->n, (size_t)D->R,
+                                    cudaMemcpyHostToDevice, D->stream));
+        NLMC_CUDA(cudaStreamSynchronize(D->stream));
+        D->modes_on = true;
+        D->temp_x = (float)temp_x;
+    }
+    if (D->sweep_graph && (was_on != D->modes_on || modes)) {  // kernel arguments are baked into the captured graph
+        cudaGraphExecDestroy(D->sweep_graph);
+        D->sweep_graph = nullptr;
+    }
+    return NLMC_OK;
+}
+
+int nlmc_dense_best_reset(nlmc_dense *D) {
+    using namespace nlmc;
+    NLMC_REQUIRE(D, "nlmc_dense_best_reset: NULL handle");
+    NLMC_CUDA(cudaSetDevice(D->inst->device));
+    if (!D->bestE) {
+        NLMC_CUDA(cudaMalloc(&D->bestE, sizeof(double) * (size_t)D->R_pad));
+        NLMC_CUDA(cudaMalloc(&D->bestS, sizeof(uint16_t) * (size_t)D->R_pad * D->n_pad));
+    }
+    dense_fill_kernel<<<(D->R_pad + 127) / 128, 128, 0, D->stream>>>(D->R_pad, D->bestE, 1e300);
+    NLMC_CUDA(cudaGetLastError());
+    return NLMC_OK;
+}
+
+/* energies of the current states (returned if out_E != NULL) and best-state tracking in one call */
+int nlmc_dense_best_update(nlmc_dense *D, double *out_E) {
+    using namespace nlmc;
+    NLMC_REQUIRE(D && D->bestE, "nlmc_dense_best_update: call nlmc_dense_best_reset first");
+    NLMC_CUDA(cudaSetDevice(D->inst->device));
+    int rc = launch_fields(D, 0, D->n_pad, 1);
+    if (rc) return rc;
+    dense_energy_kernel<<<(D->R_pad + 127) / 128, 128, 0, D->stream>>>(D->n, D->n_pad, D->R_pad, D->Ht, D->hf, D->S, D->E);
+    dense_best_kernel<<<(unsigned)D->R_pad, 128, 0, D->stream>>>(D->n_pad, D->E, D->bestE, D->S, D->bestS);
+    NLMC_CUDA(cudaGetLastError());
+    if (out_E) {
+        NLMC_CUDA(cudaMemcpyAsync(out_E, D->E, sizeof(double) * (size_t)D->R, cudaMemcpyDeviceToHost, D->stream));
+        NLMC_CUDA(cudaStreamSynchronize(D->stream));
+    }
+    return NLMC_OK;
+}
+
+int nlmc_dense_best_get(nlmc_dense *D, int8_t *out_spins, double *out_E) {
+    using namespace nlmc;
+    NLMC_REQUIRE(D && D->bestE, "nlmc_dense_best_get: call nlmc_dense_best_reset first");
+    NLMC_CUDA(cudaSetDevice(D->inst->device));
+    if (out_spins) {
+        int8_t *tmp = nullptr;
+        const size_t cnt = (size_t)D->R * D->n;
+        NLMC_CUDA(cudaMalloc(&tmp, cnt));
+        dense_unpack_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, D->stream>>>(D->n, D->n_pad, D->R, D->bestS, tmp);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_spins, tmp, cnt, cudaMemcpyDeviceToHost, D->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(D->stream);
+        cudaFree(tmp);
+        if (e != cudaSuccess) { set_error("nlmc_dense_best_get: %s", cudaGetErrorString(e)); return NLMC_ERR_CUDA; }
+    }
+    if (out_E) {
+        NLMC_CUDA(cudaMemcpyAsync(out_E, D->bestE, sizeof(double) * (size_t)D->R, cudaMemcpyDeviceToHost, D->stream));
+        NLMC_CUDA(cudaStreamSynchronize(D->stream));
+    }
     return NLMC_OK;
 }
 

@@ -79,6 +79,10 @@ _SIGNATURES = {
     "nlmc_dense_fields": [_vp, _vp],
     "nlmc_dense_sweep": [_vp, _int],
     "nlmc_dense_energies": [_vp, _f64],
+    "nlmc_dense_set_site_modes": [_vp, _vp, _dbl],
+    "nlmc_dense_best_reset": [_vp],
+    "nlmc_dense_best_update": [_vp, _vp],
+    "nlmc_dense_best_get": [_vp, _vp, _vp],
     "nlmc_dense_sync": [_vp],
     "nlmc_dense_time_fields": [_vp, _int, C.POINTER(C.c_float)],
     "nlmc_dense_time_sweeps": [_vp, _int, C.POINTER(C.c_float)],
@@ -417,6 +421,24 @@ class Dense:
         out = np.empty(self.R, dtype=np.float64)
         check(lib().nlmc_dense_energies(self._h, out), "nlmc_dense_energies")
         return out
+
+    def set_site_modes(self, modes, temp_x: float = 1.0):
+        m = None if modes is None else np.ascontiguousarray(modes, dtype=np.uint8).reshape(self.R, self.n)
+        check(lib().nlmc_dense_set_site_modes(self._h, _ptr(m), float(temp_x)), "nlmc_dense_set_site_modes")
+
+    def best_reset(self):
+        check(lib().nlmc_dense_best_reset(self._h), "nlmc_dense_best_reset")
+
+    def best_update(self, fetch: bool = True):
+        out = np.empty(self.R, dtype=np.float64) if fetch else None
+        check(lib().nlmc_dense_best_update(self._h, _ptr(out)), "nlmc_dense_best_update")
+        return out
+
+    def best_get(self):
+        spins = np.empty((self.R, self.n), dtype=np.int8)
+        E = np.empty(self.R, dtype=np.float64)
+        check(lib().nlmc_dense_best_get(self._h, spins.ctypes.data, E.ctypes.data), "nlmc_dense_best_get")
+        return spins, E
 
     def sync(self):
         check(lib().nlmc_dense_sync(self._h), "nlmc_dense_sync")

@@ -35,7 +35,12 @@ class NMC:
         self.h = self.h / norm_factor
         if self.mode != "replay":
             from .production import nmc_run_production
-            return nmc_run_production(self, locals())
+            return nmc_run_production(self, dict(
+                num_sweeps_initial=num_sweeps_initial, num_sweeps_per_NMC_phase=num_sweeps_per_NMC_phase,
+                num_NMC_cycles=num_NMC_cycles, full_update_frequency=full_update_frequency, M_skip=M_skip,
+                temp_x=temp_x, global_beta=global_beta, lambda_start=lambda_start, lambda_end=lambda_end,
+                lambda_reduction_factor=lambda_reduction_factor, threshold_initial=threshold_initial,
+                threshold_cutoff=threshold_cutoff, max_iterations=max_iterations, tolerance=tolerance))
         N = len(self.h)
         if num_sweeps_initial < 0 or num_sweeps_per_NMC_phase < 0:
             raise ValueError("negative dimensions are not allowed")

@@ -30,14 +30,29 @@ def _require_msc(prob: host.Problem, betas, n_ladders: int, seed: int) -> "_lib.
             f"(2D/3D lattices); use mode='replay' for this instance ({e})") from e
 
 
+def _msc_eligible(prob: host.Problem) -> bool:
+    """+-J, h = 0, even degrees <= 6: the bit-packed path applies (csrc/nlmc_msc.cu)."""
+    if not prob.is_integer or np.any(prob.h != 0) or len(prob.val) == 0:
+        return False
+    if not np.all(np.abs(prob.val) == 1) or np.any(prob.ci == prob.row_of):
+        return False
+    deg = np.diff(prob.rp)
+    return bool(np.all(deg <= 6) and np.all(deg % 2 == 0))
+
+
 def npt_run_production(obj, beta_list, nmc_kw):
-    """NPT.run (NPT/npt.py:535-700) on the bit-packed path.  Returns (M, Energy, count) for run 0."""
-    if any(obj.doNMC):
-        raise NotImplementedError("mode='production' does not run doNMC replicas yet; use mode='replay'")
+    """NPT.run (NPT/npt.py:535-700) in production mode.  +-J lattices without NMC replicas take the bit-packed
+    path; everything else (real-valued or dense J, fields, doNMC replicas) takes the dense tensor-core path."""
+    prob = obj._problem()
+    if _msc_eligible(prob) and not any(obj.doNMC):
+        return _npt_run_msc(obj, prob, beta_list)
+    return _npt_run_dense(obj, prob, beta_list, nmc_kw)
+
+
+def _npt_run_msc(obj, prob, beta_list):
     R = obj.num_replicas
     spm, spr = obj.num_sweeps_MCMC_per_swap, obj.num_sweeps_read_per_swap
     num_runs = int(getattr(obj, "num_runs", 1))
-    prob = obj._problem()
     n = prob.n
     msc = _require_msc(prob, beta_list[:R], num_runs, _seed_from_numpy())
     count = np.zeros(obj.num_swap_attempts)
@@ -70,6 +85,162 @@ def npt_run_production(obj, beta_list, nmc_kw):
     return M, Energy, count
 
 
+# ---------------------------------------------------------------------------------------------------
+# dense engine (K3): one row per replica, beta per row, NMC phases as per-site modes
+# ---------------------------------------------------------------------------------------------------
+def _backbones(prob, states, global_beta, nmc_kw):
+    """LBP backbone (K5 + host lambda schedule) of every state in `states` [G][n] -> list of index arrays."""
+    from .nmc_core import lbp_convexified
+    lbp = _lib.Lbp(prob.inst)
+    out = []
+    for m_star in states:
+        cl = lbp_convexified(prob, lbp, m_star.astype(np.float64), nmc_kw["lambda_start"], nmc_kw["lambda_end"],
+                             nmc_kw["lambda_reduction_factor"], nmc_kw["tolerance"], nmc_kw["max_iterations"],
+                             nmc_kw["threshold_initial"], nmc_kw["threshold_cutoff"], global_beta)
+        out.append(np.concatenate(cl).astype(int) if cl else np.array([], dtype=int))
+    lbp.close()
+    return out
+
+
+def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True):
+    """NMC_subroutine (NMC/nmc.py:320-440 / NPT/npt.py:357-477) for all rows of the dense handle `d` in lock
+    step.  Returns (M_overall [n][cols] of row 0 per row?, ...) -- see callers; rows are independent chains."""
+    G, n = d.R, prob.n
+    num_cycles, phase = nmc_kw["num_cycles"], nmc_kw["phase_sweeps"]
+    fuf, M_skip, temp_x = nmc_kw["full_update_frequency"], nmc_kw["M_skip"], nmc_kw["temp_x"]
+    m_init = np.asarray(m_star, dtype=np.int8).reshape(G, n).copy()
+    m_star = m_init.copy()
+    cols = [[] for _ in range(G)]   # recorded states per row (every M_skip-th sweep of every phase)
+    ens = [[] for _ in range(G)]
+    clusters = None
+
+    def run_phase(modes):
+        nonlocal m_init
+        d.set_spins(m_init)
+        d.set_site_modes(modes, temp_x)
+        d.best_reset()
+        for j in range(phase):
+            d.sweep(1)
+            E = d.best_update()
+            if j % M_skip == 0:
+                S = d.get_spins()
+                for g in range(G):
+                    cols[g].append(S[g].copy())
+                    ens[g].append(E[g])
+        m_init, _ = d.best_get()  # m_init = M[:, argmin E], first minimum wins (nmc.py:394-395)
+
+    if variant == "npt":
+        clusters = _backbones(prob, m_star, nmc_kw["global_beta"], nmc_kw)
+    for cycle in range(num_cycles):
+        if variant == "nmc":
+            clusters = _backbones(prob, m_star, nmc_kw["global_beta"], nmc_kw)
+        in_cl = np.zeros((G, n), dtype=bool)
+        for g in range(G):
+            in_cl[g, clusters[g]] = True
+        run_phase(np.where(in_cl, 1, 2).astype(np.uint8))   # C: backbone hot, the rest frozen (nmc.py:377-385)
+        run_phase(np.where(in_cl, 2, 0).astype(np.uint8))   # NC: backbone frozen (nmc.py:398-406)
+        if cycle % fuf == 0:
+            run_phase(None)                                  # ALL (nmc.py:419-433)
+            if variant == "nmc":
+                m_star = m_init.copy()
+    d.set_site_modes(None)
+    out = []
+    for g in range(G):
+        Mo = np.array(cols[g], dtype=np.float64).T if cols[g] else np.zeros((n, 0))
+        Eo = np.array(ens[g], dtype=np.float64)
+        out.append((Mo, Eo, clusters[g] if clusters else np.array([], dtype=int)))
+    return out
+
+
+def _npt_run_dense(obj, prob, beta_list, nmc_kw):
+    """Dense-engine NPT: plain replicas and doNMC replicas live in two handles (their sweep counts per round
+    differ, NPT/npt.py:577-580); exchanges are done on the host on the 2 x n spins of each accepted pair."""
+    import random as _random
+    R, n = obj.num_replicas, prob.n
+    spm, spr = obj.num_sweeps_MCMC_per_swap, obj.num_sweeps_read_per_swap
+    mc_ids = [r for r in range(R) if not obj.doNMC[r]]
+    nmc_ids = [r for r in range(R) if obj.doNMC[r]]
+    seed = _seed_from_numpy()
+    d_mc = _lib.Dense(prob.inst, beta_list[mc_ids], n_split=3, seed=seed) if mc_ids else None
+    d_nmc = _lib.Dense(prob.inst, np.full(len(nmc_ids), float(nmc_kw["global_beta"])), n_split=3, seed=seed + 1) \
+        if nmc_ids else None  # doNMC replicas run at global_beta, not beta_list[i] (NPT/npt.py:630-637, SURVEY D6)
+    state = np.sign(2 * np.random.rand(R, n) - 1).astype(np.int8)  # NPT/npt.py:612
+    M = np.zeros((R * n, spm))
+    E_cols = np.zeros((R, spm))
+    count = np.zeros(obj.num_swap_attempts)
+    all_pairs = [(i, i + 1) for i in range(1, R)]
+    for ii in range(obj.num_swap_attempts):
+        last = ii == obj.num_swap_attempts - 1
+        if mc_ids:
+            d_mc.set_spins(state[mc_ids])
+            if last:
+                for j in range(spm):
+                    d_mc.sweep(1)
+                    E = d_mc.energies()
+                    S = d_mc.get_spins()
+                    for g, r in enumerate(mc_ids):
+                        M[r * n:(r + 1) * n, j] = S[g]
+                        E_cols[r, j] = E[g]
+            else:
+                d_mc.sweep(spm)
+                E_cols[mc_ids, -1] = d_mc.energies()
+            state[mc_ids] = d_mc.get_spins()
+        if nmc_ids:
+            res = _nmc_cycles_dense(prob, d_nmc, state[nmc_ids], nmc_kw, "npt")
+            for g, r in enumerate(nmc_ids):
+                Mo, Eo, _ = res[g]
+                M[r * n:(r + 1) * n, :] = Mo[:, -spm:]
+                E_cols[r] = Eo[-spm:]
+                state[r] = Mo[:, -1].astype(np.int8)
+        for sel, nxt in host.select_non_overlapping_pairs(all_pairs, obj.num_swapping_pairs):
+            dE = E_cols[nxt - 1, -1] - E_cols[sel - 1, -1]
+            dB = beta_list[nxt - 1] - beta_list[sel - 1]
+            if np.random.rand() < min(1, np.exp(dB * dE)):
+                count[ii] += 1
+                state[[sel - 1, nxt - 1]] = state[[nxt - 1, sel - 1]]
+                E_cols[[sel - 1, nxt - 1], -1] = E_cols[[nxt - 1, sel - 1], -1]
+    Energy = np.zeros(R)
+    obj._EE1_list = []
+    for r in range(R):
+        EE1 = E_cols[r, :spr].copy()
+        Energy[r] = np.min(EE1) if len(EE1) else 0.0
+        obj._EE1_list.append(EE1)
+    obj.energies_all_runs = None
+    for d in (d_mc, d_nmc):
+        if d is not None:
+            d.close()
+    return M, Energy, count
+
+
+def nmc_run_production(obj, kw):
+    """NMC.run (NMC/nmc.py:442-520) on the dense engine: annealed MCMC from beta 0 to global_beta with the best
+    state tracked on the device, then NMC cycles (LBP backbone K5, hot-backbone / frozen phases as site modes)."""
+    prob = host.Problem(obj.J, obj.h, obj.device)
+    n = prob.n
+    global_beta = kw["global_beta"]
+    d = _lib.Dense(prob.inst, [float(global_beta)], n_split=3, seed=_seed_from_numpy())
+    d.set_spins(np.sign(2 * np.random.rand(n) - 1).astype(np.int8)[None, :])  # nmc.py:487
+    sched = host.beta_schedule(kw["num_sweeps_initial"], global_beta, anneal=True, sweeps_per_beta=1, initial_beta=0)
+    d.best_reset()
+    for b in sched:
+        d.set_betas([max(float(b), 1e-12)])
+        d.sweep(1)
+        d.best_update(fetch=False)
+    d.set_betas([float(global_beta)])
+    m_star, E_star = d.best_get()
+    if obj.verbose:
+        print(f'\ninitial m_star energy = {E_star[0]:.8f}')
+    nmc_kw = dict(num_cycles=kw["num_NMC_cycles"], phase_sweeps=kw["num_sweeps_per_NMC_phase"],
+                  full_update_frequency=kw["full_update_frequency"], M_skip=kw["M_skip"], global_beta=global_beta,
+                  temp_x=kw["temp_x"], lambda_start=kw["lambda_start"], lambda_end=kw["lambda_end"],
+                  lambda_reduction_factor=kw["lambda_reduction_factor"], threshold_initial=kw["threshold_initial"],
+                  threshold_cutoff=kw["threshold_cutoff"], max_iterations=kw["max_iterations"], tolerance=kw["tolerance"])
+    Mo, Eo, clusters = _nmc_cycles_dense(prob, d, m_star, nmc_kw, "nmc")[0]
+    d.close()
+    obj.all_clusters = clusters
+    return Mo, Eo, float(np.min(Eo))
+
+
 def apt_preprocessor_chains_production(prob, reps, iter, saved_state, beta, num_sweeps_MCMC, num_sweeps_read,
                                        num_rng):
     """One beta iteration of APT_preprocessor.run (NPT/apt_preprocessor.py:158-179): num_rng independent
@@ -87,10 +258,6 @@ def apt_preprocessor_chains_production(prob, reps, iter, saved_state, beta, num_
         state.sweep(1)
         Energy[:, t] = state.energies()[0, :num_rng]
     return Energy, saved_state
-
-
-def nmc_run_production(obj, kw):
-    raise NotImplementedError("NMC.run has no production mode yet; use mode='replay'")
 
 
 def apt_icm_run_production(obj, beta_list):

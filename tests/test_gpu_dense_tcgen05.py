@@ -108,3 +108,97 @@ def test_sweep_multi_block_vs_reference_sampler(nl):
         ref = np.array(ref)
         err = np.hypot(E_gpu[b].std(ddof=1) / np.sqrt(per), ref.std(ddof=1) / np.sqrt(ref.size))
         assert abs(E_gpu[b].mean() - ref.mean()) <= 3.5 * err, (beta, E_gpu[b].mean(), ref.mean(), err)
+
+
+def test_site_modes_frozen_and_hot(nl):
+    """NMC phase modes on the dense path: frozen sites never move; a hot site set at (beta, temp_x) samples the same
+    distribution as a normal one at beta/temp_x (the reference divides the backbone rows of J and h by temp_x)."""
+    n, per = 96, 256
+    J, h = gaussian_instance(n, 13, with_field=True)
+    prob = nl.host.Problem(J, h)
+    rs = np.random.RandomState(0)
+    d = nl.lib.Dense(prob.inst, np.full(2 * per, 2.0), n_split=3, seed=21)
+    S0 = rs.choice([-1, 1], size=(2 * per, n)).astype(np.int8)
+    d.set_spins(S0)
+    modes = np.zeros((2 * per, n), dtype=np.uint8)
+    frozen = rs.rand(n) < 0.4
+    modes[:per, frozen] = 2          # first half: a frozen subset, the rest normal
+    modes[per:, :] = 1               # second half: every site hot with temp_x = 4  (effective beta 0.5)
+    d.set_site_modes(modes, 4.0)
+    d.sweep(60)
+    S1 = d.get_spins()
+    assert np.array_equal(S1[:per][:, frozen], S0[:per][:, frozen])
+    assert np.mean(S1[:per][:, ~frozen] != S0[:per][:, ~frozen]) > 0.05
+    acc = []
+    for _ in range(30):
+        d.sweep(4)
+        acc.append(d.energies()[per:])
+    E_hot = np.array(acc).mean(axis=0)
+    ref = nl.lib.Dense(prob.inst, np.full(per, 0.5), n_split=3, seed=22)
+    ref.sweep(60)
+    acc = []
+    for _ in range(30):
+        ref.sweep(4)
+        acc.append(ref.energies())
+    E_ref = np.array(acc).mean(axis=0)
+    err = np.hypot(E_hot.std(ddof=1), E_ref.std(ddof=1)) / np.sqrt(per)
+    assert abs(E_hot.mean() - E_ref.mean()) <= 4.5 * err, (E_hot.mean(), E_ref.mean(), err)
+    # modes off again: frozen sites move
+    d.set_site_modes(None)
+    d.sweep(20)
+    assert np.mean(d.get_spins()[:per][:, frozen] != S0[:per][:, frozen]) > 0.05
+
+
+def test_best_state_tracking(nl):
+    from oracle import oracle as O
+    n = 64
+    J, h = gaussian_instance(n, 17)
+    prob = nl.host.Problem(J, h)
+    d = nl.lib.Dense(prob.inst, np.full(130, 1.0), n_split=3, seed=5)
+    d.best_reset()
+    seen = []
+    for _ in range(12):
+        d.sweep(1)
+        seen.append(d.best_update())
+    spins, E = d.best_get()
+    seen = np.array(seen)
+    np.testing.assert_allclose(E, seen.min(axis=0), rtol=0, atol=1e-9)
+    np.testing.assert_allclose(O.energy(O.Csr(J), h, spins), E, rtol=1e-5, atol=1e-4)
+
+
+def test_nmc_production_mode(nl, tmp_cwd):
+    """NMC.run(mode='production') on a C1-shaped instance: reference return contract, energies consistent with
+    the returned states, and the search actually descends."""
+    from nlmc_b200 import NMC
+    from oracle import oracle as O
+    J, h = O.random_pm_graph(80, 0.12, 3)
+    np.random.seed(2)
+    eps = np.finfo(float).eps
+    M, E, mn = NMC(J, h, mode="production").run(60, 12, 2, 1, 1, 20, 3, 3, 0.01, 0.9, 0.9999999, 0.999999, 100, eps)
+    assert M.shape == (80, 2 * 3 * 12) and np.all(np.abs(M) == 1)
+    assert isinstance(mn, float) and mn == E.min()
+    norm = np.max(np.abs(J))
+    np.testing.assert_allclose(O.energy(O.Csr(J / norm), h / norm, M.T.astype(np.int8)), E, rtol=1e-5, atol=1e-3)
+    rs = np.random.RandomState(0)
+    E_rand = O.energy(O.Csr(J / norm), h / norm, rs.choice([-1, 1], size=(64, 80)).astype(np.int8))
+    assert mn < E_rand.min() - 10
+
+
+def test_npt_production_dense_with_nmc_replicas(nl, tmp_cwd):
+    from nlmc_b200 import NPT
+    from oracle import oracle as O
+    J, h = gaussian_instance(48, 23, with_field=True)
+    betas = np.array([0.5, 1.0, 1.5, 2.0])
+    np.random.seed(1)
+    import random
+    random.seed(1)
+    M, E = NPT(J, h, mode="production").run(betas, 4, [False, False, True, True], num_sweeps_MCMC=60, num_sweeps_read=30,
+                                            num_swap_attempts=3, num_swapping_pairs=1, num_cycles=2, global_beta=3,
+                                            lambda_start=3, threshold_initial=0.9999999, threshold_cutoff=0.999999,
+                                            max_iterations=100)
+    assert M.shape == (48 * 4, 20) and E.shape == (4,) and np.all(np.abs(M) == 1)
+    norm = np.max(np.abs(J))
+    csr = O.Csr(J / norm)
+    for r in range(4):
+        Er = O.energy(csr, h / norm, M[r * 48:(r + 1) * 48, :10].T.astype(np.int8))
+        assert abs(E[r] - Er.min()) < 1e-3
