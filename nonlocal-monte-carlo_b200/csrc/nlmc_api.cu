@@ -95,6 +95,23 @@ int nlmc_instance_create(int n, const int32_t *row_ptr, const int32_t *col, cons
         nlmc::set_error("nlmc_instance_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail();
     }
+    // compact copies for the shared-memory replay kernel (integer J only)
+    bool small_int = integer_j && nnz > 0;
+    for (int p = 0; p < nnz && small_int; ++p) small_int = std::fabs(val[p]) <= 127.0;
+    if (small_int) {
+        std::vector<int8_t> v8((size_t)nnz);
+        std::vector<uint16_t> c16((size_t)nnz);
+        for (int p = 0; p < nnz; ++p) { v8[(size_t)p] = (int8_t)val[p]; c16[(size_t)p] = (uint16_t)col[p]; }
+        bool ok = cudaMalloc(&I->int_val, (size_t)nnz) == cudaSuccess &&
+                  cudaMemcpy(I->int_val, v8.data(), (size_t)nnz, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (ok && n <= 65535)
+            ok = cudaMalloc(&I->col16, sizeof(uint16_t) * (size_t)nnz) == cudaSuccess &&
+                 cudaMemcpy(I->col16, c16.data(), sizeof(uint16_t) * (size_t)nnz, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!ok) {
+            nlmc::set_error("nlmc_instance_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail();
+        }
+    }
     *out = I;
     return NLMC_OK;
 }
@@ -107,6 +124,8 @@ int nlmc_instance_destroy(nlmc_instance *I) {
     if (I->val) cudaFree(I->val);
     if (I->h) cudaFree(I->h);
     if (I->rev) cudaFree(I->rev);
+    if (I->int_val) cudaFree(I->int_val);
+    if (I->col16) cudaFree(I->col16);
     if (I->stream) cudaStreamDestroy(I->stream);
     delete I;
     return NLMC_OK;

@@ -83,6 +83,8 @@ struct nlmc_instance {
     double *val = nullptr;       // [nnz]
     double *h = nullptr;         // [n]
     int32_t *rev = nullptr;      // [nnz] index of the transposed entry (built on demand for LBP)
+    int8_t *int_val = nullptr;   // [nnz] J as int8 when every value is an integer in [-127,127] (K1-int), else NULL
+    uint16_t *col16 = nullptr;   // [nnz] 16-bit column indices when n <= 65535
     cudaStream_t stream = nullptr;
     // host mirrors (colouring, validation, MSC packing)
     std::vector<int32_t> h_row_ptr, h_col;

@@ -15,6 +15,7 @@
 // exact integers and the lanes reduce them in parallel; otherwise the products are formed in
 // parallel and accumulated in storage order by shuffles, which keeps the rounding identical.
 #include <cmath>
+#include <cstdlib>
 
 #include "nlmc_common.cuh"
 
@@ -48,8 +49,31 @@ __device__ __forceinline__ void st_spin(int8_t *m, int i, int v) {
     else *reinterpret_cast<volatile int8_t *>(m + i) = (int8_t)v;
 }
 
+// tanh(y) in fp64; |y| > 20 saturates to exactly +-1 in IEEE double (numpy and CUDA agree: tanh(19.07) == 1.0),
+// which is the case of every spin frozen by h = +-1e4 in the NMC phases (nmc.py:381,400).
+__device__ __forceinline__ double tanh_sat(double y) { return fabs(y) > 20.0 ? copysign(1.0, y) : tanh(y); }
+
+// Storage-order accumulation of 32 per-lane products: the lanes park them in shared memory, then every lane
+// reads all 32 back (loads issued together, not interleaved with the adds) and runs the same dependent add chain
+// -- the only part that is inherently sequential for a bit-exact emulation of scipy's csr_matvec row sum.
+__device__ __forceinline__ double ordered_sum32(double acc, double prod, int count, double *scratch, int lane) {
+    scratch[lane] = prod;
+    __syncwarp();
+    double2 v[16];
+#pragma unroll
+    for (int l = 0; l < 16; ++l) v[l] = reinterpret_cast<const double2 *>(scratch)[l];
+#pragma unroll
+    for (int l = 0; l < 16; ++l) {
+        if (2 * l < count) acc = __dadd_rn(acc, v[l].x);
+        if (2 * l + 1 < count) acc = __dadd_rn(acc, v[l].y);
+    }
+    __syncwarp();
+    return acc;
+}
+
 template <bool kSmem>
 __global__ void __launch_bounds__(32) sweep_replay_kernel(ReplayArgs a) {
+    __shared__ __align__(16) double scratch[32];
     extern __shared__ __align__(16) int8_t smem_spins[];
     const int r = blockIdx.x;
     const int lane = threadIdx.x;
@@ -113,8 +137,7 @@ __global__ void __launch_bounds__(32) sweep_replay_kernel(ReplayArgs a) {
                             if (sc) v = __ddiv_rn(v, temp_x);  // J_c[all_clusters,:] / temp_x  (nmc.py:379)
                             prod = __dmul_rn(v, (double)ld_spin<kSmem>(m, __ldg(a.ci + p)));
                         }
-                        const int c = min(32, re - pb);
-                        for (int l = 0; l < c; ++l) rowsum = __dadd_rn(rowsum, __shfl_sync(0xffffffffu, prod, l));
+                        rowsum = ordered_sum32(rowsum, prod, min(32, re - pb), scratch, lane);
                     }
                 }
                 const double x = __dadd_rn(rowsum, h_k);
@@ -122,7 +145,7 @@ __global__ void __launch_bounds__(32) sweep_replay_kernel(ReplayArgs a) {
                 if (lut != nullptr && exact && h_k == 0.0 && fabs(rowsum) <= (double)a.lut_half)
                     t = lut[(int)rowsum + a.lut_half];
                 else
-                    t = tanh(__dmul_rn(beta, x));
+                    t = tanh_sat(__dmul_rn(beta, x));
                 // np.sign(np.tanh(beta*x) - 2*rand() + 1)   (nmc.py:87)
                 const double v = __dadd_rn(__dsub_rn(t, __dmul_rn(2.0, u_a)), 1.0);
                 const int nw = (v > 0.0) - (v < 0.0);
@@ -155,6 +178,120 @@ __global__ void __launch_bounds__(32) sweep_replay_kernel(ReplayArgs a) {
         __syncwarp();
         for (int i = lane; i < n; i += 32) g_spins[i] = m[i];
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1-int: the same exact replay for integer-valued J (+-J instances) when the instance fits in shared
+// memory.  Spins, CSR (int16/int32 columns, int8 values), the tanh LUT of the sweep and INCREMENTALLY
+// maintained integer local fields f_k = sum_j J_kj m_j live in shared memory: an attempt reads f_k, looks
+// tanh(beta*f_k) up, decides, and only when the spin changes walks its row to update the neighbours' fields
+// (lanes over the row entries).  Integer sums are exact, so the decisions are bit-identical to the general
+// kernel's.  Rows that an NMC phase rescales (J/temp_x is not an integer) still take the sequential
+// storage-order sum, and sites with an effective field h_eff != 0 (frozen by +-1e4, or a real h) use
+// tanh(beta*(f + h_eff)) directly.  Energies per sweep come from the fields: E = -(sum m_k f_k)/2 - sum h_k m_k.
+template <typename ColT>
+__global__ void __launch_bounds__(32) sweep_replay_int_kernel(ReplayArgs a, const ColT *__restrict__ g_col,
+                                                              const int8_t *__restrict__ g_val, int nnz) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    __shared__ __align__(16) double scratch[32];
+    __shared__ double div_tab[256];  // fl(v / temp_x) for every int8 coupling value v: no fp64 division per entry
+    const int n = a.n;
+    const int lut_w = 2 * a.lut_half + 1;
+    // carve: lut (double) | fields (int32) | row_ptr (int32) | col | val (int8) | spins (int8) | mode (uint8)
+    double *lut_s = reinterpret_cast<double *>(sm_raw);
+    int32_t *fld = reinterpret_cast<int32_t *>(lut_s + (a.lut ? lut_w : 0));
+    int32_t *rp_s = fld + n;
+    ColT *col_s = reinterpret_cast<ColT *>(rp_s + n + 1);
+    int8_t *val_s = reinterpret_cast<int8_t *>(col_s + nnz + (nnz & 1));
+    int8_t *m = val_s + nnz;
+    uint8_t *mode = reinterpret_cast<uint8_t *>(m + n);
+    const int r = blockIdx.x, lane = threadIdx.x;
+    int8_t *g_spins = a.spins + (size_t)r * n;
+    const int flags = a.flags[r];
+    const double *h_eff = (flags & 1) ? a.h_eff + (size_t)r * n : a.h_inst;
+    const uint8_t *scaled = (flags & 2) ? a.row_scaled + (size_t)r * n : nullptr;
+    const double temp_x = a.temp_x[r];
+    for (int i = lane; i < 256; i += 32) div_tab[i] = __ddiv_rn((double)(i - 128), temp_x);  // J_c = J / temp_x (nmc.py:379)
+    for (int i = lane; i <= n; i += 32) rp_s[i] = a.rp[i];
+    for (int i = lane; i < nnz; i += 32) { col_s[i] = g_col[i]; val_s[i] = g_val[i]; }
+    for (int i = lane; i < n; i += 32) {
+        m[i] = g_spins[i];
+        mode[i] = (uint8_t)((h_eff[i] != 0.0 ? 1 : 0) | ((scaled && scaled[i]) ? 2 : 0));
+    }
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) {  // initial fields
+        int f = 0;
+        for (int p = rp_s[k]; p < rp_s[k + 1]; ++p) f += (int)val_s[p] * (int)m[col_s[p]];
+        fld[k] = f;
+    }
+    __syncwarp();
+    const int n_rec = a.n_sweeps - a.record_from;
+    for (int s = 0; s < a.n_sweeps; ++s) {
+        const size_t rs = (size_t)r * a.n_sweeps + s;
+        const double beta = a.beta[rs];
+        const int32_t *perm = a.perm + rs * n;
+        const double *uu = a.u + rs * n;
+        if (a.lut) {
+            for (int i = lane; i < lut_w; i += 32) lut_s[i] = a.lut[rs * lut_w + i];
+            __syncwarp();
+        }
+        for (int base = 0; base < n; base += 32) {
+            const int idx = base + lane;
+            int my_k = 0;
+            double my_u = 0.0;
+            if (idx < n) { my_k = perm[idx]; my_u = uu[idx]; }
+            const int cnt = min(32, n - base);
+            for (int j = 0; j < cnt; ++j) {
+                const int k = __shfl_sync(0xffffffffu, my_k, j);
+                const double u_a = __shfl_sync(0xffffffffu, my_u, j);
+                const int md = mode[k];
+                const int f = fld[k];
+                const int old = m[k];
+                double t;
+                if (md == 0 && a.lut && abs(f) <= a.lut_half) {
+                    t = lut_s[f + a.lut_half];
+                } else if (!(md & 2)) {
+                    const double h_k = (md & 1) ? h_eff[k] : 0.0;
+                    t = tanh_sat(__dmul_rn(beta, __dadd_rn((double)f, h_k)));
+                } else {  // rescaled row: storage-order sum of fl(J/temp_x)*m, as the reference forms it
+                    double x = 0.0;
+                    const int re = rp_s[k + 1];
+                    for (int pb = rp_s[k]; pb < re; pb += 32) {
+                        const int p = pb + lane;
+                        double prod = 0.0;
+                        if (p < re) prod = __dmul_rn(div_tab[(int)val_s[p] + 128], (double)m[col_s[p]]);
+                        x = ordered_sum32(x, prod, min(32, re - pb), scratch, lane);
+                    }
+                    t = tanh_sat(__dmul_rn(beta, __dadd_rn(x, h_eff[k])));
+                }
+                const double v = __dadd_rn(__dsub_rn(t, __dmul_rn(2.0, u_a)), 1.0);  // nmc.py:87
+                const int nw = (v > 0.0) - (v < 0.0);
+                if (nw != old) {  // warp-uniform: walk the row, lanes over its entries
+                    const int dm = nw - old;
+                    const int re = rp_s[k + 1];
+                    for (int p = rp_s[k] + lane; p < re; p += 32) fld[col_s[p]] += (int)val_s[p] * dm;
+                    if (lane == 0) m[k] = (int8_t)nw;
+                    __syncwarp();
+                }
+            }
+        }
+        if (a.out_M != nullptr && s >= a.record_from) {
+            int8_t *dst = a.out_M + ((size_t)r * n_rec + (s - a.record_from)) * n;
+            for (int i = lane; i < n; i += 32) dst[i] = m[i];
+        }
+        if (a.out_E != nullptr) {
+            double quad = 0.0, lin = 0.0;
+            for (int k = lane; k < n; k += 32) {
+                quad += (double)((int)m[k] * fld[k]);
+                lin += (double)m[k] * __ldg(a.h_inst + k);
+            }
+            quad = warp_sum(quad);
+            lin = warp_sum(lin);
+            if (lane == 0) a.out_E[rs] = -(quad / 2.0 + lin);
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) g_spins[i] = m[i];
 }
 
 // K4: one CTA per state; E = -(m^T J m / 2 + m^T h).  Integer J and h give exact integer sums.
@@ -246,7 +383,20 @@ int nlmc_sweep_replay(nlmc_replicas *P, int n_sweeps, const int32_t *perm, const
     a.out_M = (out_M && n_rec) ? P->s_M.as<int8_t>() : nullptr;
     a.out_E = out_E ? P->s_E.as<double>() : nullptr;
 
-    if (I->n <= kSmemSpinLimit) {
+    // integer instances that fit in shared memory take the incremental-field kernel
+    const size_t lut_bytes = tanh_lut ? sizeof(double) * lut_w : 0;
+    const bool small_cols = I->n <= 65535;
+    const size_t nnz_s = (size_t)I->nnz;
+    const size_t int_smem = lut_bytes + sizeof(int32_t) * (2 * n + 1) + (small_cols ? 2 : 4) * (nnz_s + (nnz_s & 1)) + nnz_s + 2 * n + 32;
+    if (I->integer_j && I->int_val && int_smem <= 217 * 1024 && !getenv("NLMC_REPLAY_GENERAL")) {
+        if (small_cols) {
+            NLMC_CUDA(cudaFuncSetAttribute(sweep_replay_int_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)int_smem));
+            sweep_replay_int_kernel<uint16_t><<<(unsigned)R, 32, int_smem, st>>>(a, I->col16, I->int_val, I->nnz);
+        } else {
+            NLMC_CUDA(cudaFuncSetAttribute(sweep_replay_int_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)int_smem));
+            sweep_replay_int_kernel<int32_t><<<(unsigned)R, 32, int_smem, st>>>(a, I->col, I->int_val, I->nnz);
+        }
+    } else if (I->n <= kSmemSpinLimit) {
         const size_t smem = (n + 15) & ~(size_t)15;
         NLMC_CUDA(cudaFuncSetAttribute(sweep_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         sweep_replay_kernel<true><<<(unsigned)R, 32, smem, st>>>(a);

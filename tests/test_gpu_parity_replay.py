@@ -302,3 +302,41 @@ def test_nmc_run_golden(nl, tmp_cwd, name, inject):
         prob = nl.host.Problem(g["J"] / norm, g["h"] / norm)
         np.testing.assert_allclose(prob.inst.energy_states(M.T.astype(np.int8)), E, rtol=1e-9, atol=1e-12)
         pytest.xfail("LBP divergence point differs from the reference at a marginal lambda step")
+
+
+def test_k1_int_kernel_equals_general_kernel(nl, monkeypatch):
+    """The shared-memory incremental-field kernel (integer J) and the general kernel must agree bit for bit,
+    including NMC phase settings (rescaled rows, frozen spins), a real-valued h and zeros in the state."""
+    from oracle import oracle as O
+    rs = np.random.RandomState(11)
+    J, h = O.random_pm_graph(300, 0.08, 31)
+    J[5, 9] = J[9, 5] = 3.0  # an integer coupling other than +-1
+    h = np.where(rs.rand(300) < 0.2, rs.randn(300), 0.0)
+    prob = nl.host.Problem(J, h)
+    R, S, n = 6, 5, 300
+    m0 = rs.choice([-1, 1], size=(R, n)).astype(np.int8)
+    m0[2, :4] = 0
+    sched = np.repeat(np.linspace(0.2, 3.0, R)[:, None], S, axis=1)
+    perm = np.stack([np.stack([rs.permutation(n) for _ in range(S)]) for _ in range(R)]).astype(np.int32)
+    u = rs.rand(R, S, n)
+    outs = []
+    for force_general in (False, True):
+        if force_general:
+            monkeypatch.setenv("NLMC_REPLAY_GENERAL", "1")
+        reps = nl.lib.Replicas(prob.inst, R, m0)
+        for r in (1, 4):
+            in_cl = np.random.RandomState(r).rand(n) < 0.3
+            he = h.copy()
+            he[in_cl] /= 20
+            he[~in_cl] = m0[r][~in_cl] * 10000.0
+            reps.set_phase(r, he, in_cl.astype(np.uint8), 20)
+        M, E = reps.sweep_replay(perm, u, sched, prob.tanh_lut(sched), prob.lut_half)
+        outs.append((M, E, reps.get_spins()))
+    monkeypatch.delenv("NLMC_REPLAY_GENERAL")
+    assert np.array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=1e-12, atol=1e-9)
+    assert np.array_equal(outs[0][2], outs[1][2])
+    # and both equal the oracle
+    csr = O.Csr(J)
+    Mo, _ = O.mcmc(csr, h, m0[0], sched[0], perm=perm[0], u=u[0])
+    assert np.array_equal(outs[0][0][0], Mo)
