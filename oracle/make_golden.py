@@ -255,10 +255,22 @@ def case_known_answers():
     save("known_answers_wishart", J=np.array(Js), gs_energy=np.array(Es))
 
 
+def case_chimera_known_answer():
+    """Chimera droplet instance 001 (128 spins, real-valued J with fields) with its shipped ground state
+    (`groundstates_otn2d.txt`: energy and bit string; s = 2b-1, J = -J_file, h = -h_file)."""
+    base = os.path.join(rl.REFERENCE_ROOT, "NMC", "examples", "Chimera_droplet_instances", "chimera128_spinglass_power")
+    text = open(os.path.join(base, "001.txt")).read()
+    gs_line = [l for l in open(os.path.join(base, "groundstates_otn2d.txt")) if l.startswith("001.txt")][0]
+    parts = gs_line.split(":")[1].split()
+    save("known_answer_chimera128", instance_text=np.array(text), gs_energy=float(parts[0]),
+         gs_bits=np.array([int(b) for b in parts[1:]], dtype=np.int8))
+
+
 if __name__ == "__main__":
     if not rl.available():
         sys.exit("reference not mounted; golden vectors can only be generated in the build container")
     import warnings
     warnings.simplefilter("ignore")
-    for fn in (case_mcmc, case_lbp, case_nmc_run, case_npt, case_npt_sk, case_icm, case_npt_sparse, case_known_answers):
+    for fn in (case_mcmc, case_lbp, case_nmc_run, case_npt, case_npt_sk, case_icm, case_npt_sparse, case_known_answers,
+               case_chimera_known_answer):
         fn()
