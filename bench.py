@@ -296,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "u32 bit-planes (1 bit per spin, 32 ladders per word)", "data": "synthetic",
+               "vs_baseline": None, "dtype": "u32", "dtype_note": "bit planes: 1 bit per spin, 32 ladders per 32-bit word", "data": "synthetic",
                "config": workload_config(args, world), "roofline": roofline, "roofline_packed": roofline_packed,
                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                "per_gpu_value": value / world, "ps_per_attempt": 1e12 / (value / world)}
