@@ -260,5 +260,116 @@ def apt_preprocessor_chains_production(prob, reps, iter, saved_state, beta, num_
     return Energy, saved_state
 
 
+class _IcmEngine:
+    """The R x 10 chains of APT_ICM on whichever production engine fits the instance: the bit-packed path
+    (sub-replica s of beta b = lane s of the words of beta b) or the dense tensor-core path (row b*S + s)."""
+
+    def __init__(self, prob, betas, S, seed):
+        self.R, self.S, self.n = len(betas), S, prob.n
+        self.msc = _msc_eligible(prob)
+        if self.msc:
+            self.eng = _lib.Msc(prob.inst, betas, S, seed)
+        else:
+            self.eng = _lib.Dense(prob.inst, np.repeat(betas, S), n_split=3, seed=seed)
+
+    def sweep(self, k):
+        self.eng.sweep(k)
+
+    def energies(self):  # [R][S]
+        E = self.eng.energies()
+        return E[:, :self.S].copy() if self.msc else E.reshape(self.R, self.S)
+
+    def get_states(self):  # int8 [R][S][n]
+        if self.msc:
+            return np.stack([np.stack([self.eng.get_spins(b, s) for s in range(self.S)]) for b in range(self.R)])
+        return self.eng.get_spins().reshape(self.R, self.S, self.n)
+
+    def set_states(self, X):
+        if self.msc:
+            for b in range(self.R):
+                for s in range(self.S):
+                    self.eng.set_spins(b, s, X[b, s])
+        else:
+            self.eng.set_spins(X.reshape(self.R * self.S, self.n))
+
+    def close(self):
+        self.eng.close()
+
+
 def apt_icm_run_production(obj, beta_list):
-    raise NotImplementedError("APT_ICM.run has no production mode yet; use mode='replay'")
+    """APT_ICM.run (NPT/apt_ICM.py:145-305) in production mode, reference semantics: the Houdayer move edits the
+    FIRST column of each sub-replica's block of M while the exchange reads the LAST one and the chains continue
+    from the unedited states, so the edits feed back only when there is one sweep per swap."""
+    S = 10  # num_subreplicas, apt_ICM.py:177
+    R, spm, spr = obj.num_replicas, obj.num_sweeps_MCMC_per_swap, obj.num_sweeps_read_per_swap
+    if spm < 1:
+        raise ValueError("num_sweeps_MCMC must be at least num_swap_attempts")
+    prob = host.Problem(obj.J, obj.h, obj.device)
+    n = prob.n
+    eng = _IcmEngine(prob, beta_list[:R], S, _seed_from_numpy())
+    all_pairs = [(i, i + 1) for i in range(1, R)]
+    M = np.zeros((n * R, spm * S))
+    E_cols = np.zeros((R, S, spm))
+    count = np.zeros(obj.num_swap_attempts)
+    for ii in range(int(obj.num_swap_attempts)):
+        last_round = ii == obj.num_swap_attempts - 1
+        need_first = last_round or spm == 1   # the Houdayer edit is only observable in these cases
+        first = E_first = None
+        cols, ens = [], []
+        if need_first:
+            eng.sweep(1)
+            first, E_first = eng.get_states(), eng.energies()
+            cols, ens = [first], [E_first]
+            for j in range(1, spm):
+                eng.sweep(1)
+                if last_round:  # every column of the returned M
+                    cols.append(eng.get_states())
+                    ens.append(eng.energies())
+        else:
+            eng.sweep(spm)
+        E_last = eng.energies() if spm > 1 else None
+        if need_first:  # Houdayer move on the first column (apt_ICM.py:216-246)
+            for r in range(R):
+                shuffled = np.random.permutation(S)
+                pairs = [(int(shuffled[2 * p]), int(shuffled[2 * p + 1])) for p in range(S // 2)]
+                s1 = np.stack([first[r, a] for a, _ in pairs])
+                s2 = np.stack([first[r, b] for _, b in pairs])
+                labels, counts = _lib.icm_clusters(prob.inst, s1, s2)
+                for p, (a, b) in enumerate(pairs):
+                    if not counts[p]:
+                        continue
+                    members = labels[p] == np.random.randint(int(counts[p]))
+                    if int(members.sum()) > n // 2:        # Katzgraber rule (apt_ICM.py:236-237)
+                        first[r, a] = -first[r, a]
+                    else:
+                        first[r, a][members], first[r, b][members] = s2[p][members], s1[p][members]
+            E_first = prob.inst.energy_states(first.reshape(R * S, n)).reshape(R, S)
+            ens[0] = E_first
+            if spm == 1:
+                E_last = E_first
+        if last_round:
+            for j in range(spm):
+                for s in range(S):
+                    M[:, s * spm + j] = cols[j][:, s, :].reshape(-1)
+                E_cols[:, :, j] = ens[j]
+        # exchange per sub-replica on the last column (apt_ICM.py:251-285); the chains continue from it
+        accepted = []
+        for sel, nxt in host.select_non_overlapping_pairs(all_pairs, obj.num_swapping_pairs):
+            dB = beta_list[nxt - 1] - beta_list[sel - 1]
+            for s in range(S):
+                dE = E_last[nxt - 1, s] - E_last[sel - 1, s]
+                if np.random.rand() < min(1, np.exp(dB * dE)):
+                    accepted.append((sel - 1, nxt - 1, s))
+        count[ii] = len(accepted)
+        if not last_round and (accepted or spm == 1):
+            # with one sweep per swap the (edited) first column IS the last column the chains continue from
+            X = first if spm == 1 else eng.get_states()
+            for a, b, s in accepted:
+                X[[a, b], s] = X[[b, a], s]
+            eng.set_states(X)
+    eng.close()
+    Energy = np.zeros(R)
+    E_flat = E_cols.reshape(R, S * spm)
+    for r in range(R):
+        Energy[r] = np.min(E_flat[r, :spr]) if spr else 0.0
+    return M, Energy

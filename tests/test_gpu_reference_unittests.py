@@ -146,3 +146,29 @@ def test_edge_cases_vs_oracle():
     assert Mo2.shape == (9, 2 * 3 * 3) and len(Eo2) == 18
     norm = np.max(np.abs(Jg))
     np.testing.assert_allclose(O.energy(O.Csr(Jg / norm), hg / norm, Mo2.T.astype(np.int8)), Eo2, rtol=1e-9)
+
+
+@pytest.mark.parametrize("lattice", [True, False])
+@pytest.mark.parametrize("spm", [1, 3])
+def test_apt_icm_production_mode(lattice, spm):
+    """APT_ICM in production mode on both engines (bit-packed for +-J lattices, dense otherwise): the reference's
+    return contract, states of +-1, and energies that are the minimum over the first columns of the returned M."""
+    from nlmc_b200 import APT_ICM
+    from oracle import oracle as O
+    if lattice:
+        A, h = O.ea3d_pm_j(4, 8)
+        J = A.toarray()
+    else:
+        J, h = generate_random_J_h(20, column_h=False)
+        J = J / np.max(np.abs(J)); h = h / 4
+    n = J.shape[0]
+    betas = np.array([0.4, 0.8, 1.2])
+    obj = APT_ICM(J, h, mode="production")
+    M, E = obj.run(betas, 3, num_sweeps_MCMC=4 * spm, num_sweeps_read=2 * spm, num_swap_attempts=4, num_swapping_pairs=1)
+    assert M.shape == (n * 3, spm * 10) and E.shape == (3,) and np.all(np.abs(M) == 1)
+    spr = (2 * spm) // 4
+    csr = O.Csr(J)
+    for r in range(3):
+        if spr:
+            Er = O.energy(csr, np.asarray(h).reshape(-1), M[r * n:(r + 1) * n, :spr].T.astype(np.int8))
+            assert abs(E[r] - Er.min()) < 1e-3
