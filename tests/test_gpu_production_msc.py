@@ -277,3 +277,33 @@ def test_sharding_invariance(nl):
         assert np.array_equal(Pw[:, :, 4 * i:4 * i + 4], Pp)
         assert np.array_equal(Ew[:, 128 * i:128 * (i + 1)], part.energies())
     assert whole.swap_count() == sum(p.swap_count() for p in parts) > 0
+
+
+def test_npt_production_energy_distribution_matches_reference(nl, tmp_cwd):
+    """north_star: 'same best-found energy distribution'.  Whole NPT runs (sweeps + exchanges) on a 64-spin +-J
+    lattice: the coldest replica's final energy over 128 production ladders vs 48 runs of the reference algorithm
+    (oracle NPT restatement, bit-identical to the reference): means within 3.5 sigma, and the same ground level."""
+    import random
+    from nlmc_b200 import NPT
+    from oracle import oracle as O
+    A, h = O.ea3d_pm_j(4, 12)
+    J = A.toarray()
+    csr = O.Csr(A)
+    betas = np.array([0.4, 0.8, 1.2, 1.6])
+    kw = dict(num_sweeps_MCMC=120, num_sweeps_read=40, num_swap_attempts=12, num_swapping_pairs=1)
+    np.random.seed(3)
+    obj = NPT(A, h, mode="production")
+    obj.num_runs = 128
+    obj.run(betas, 4, [False] * 4, **kw)
+    E_gpu = obj.energies_all_runs[-1]          # coldest replica, all 128 ladders, after the last sweep
+    E_ref = []
+    for s in range(48):
+        np.random.seed(1000 + s)
+        random.seed(1000 + s)
+        M, _ = O.npt_run(J, h, betas, 4, [False] * 4, **kw)
+        E_ref.append(O.energy(csr, h, M[3 * 64:, -1].astype(np.int8))[0])
+    E_ref = np.array(E_ref)
+    err = np.hypot(E_gpu.std(ddof=1) / np.sqrt(E_gpu.size), E_ref.std(ddof=1) / np.sqrt(E_ref.size))
+    assert abs(E_gpu.mean() - E_ref.mean()) <= 3.5 * err, (E_gpu.mean(), E_ref.mean(), err)
+    assert E_gpu.min() == E_ref.min() or abs(E_gpu.min() - E_ref.min()) <= 4  # both reach the lowest levels
+    assert abs(E_gpu.std(ddof=1) - E_ref.std(ddof=1)) <= 0.5 * max(E_gpu.std(ddof=1), E_ref.std(ddof=1)) + 1
