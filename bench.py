@@ -252,7 +252,9 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = attempts_per_step * world * args.steps / (ms * 1e-3)
-    launches = args.steps * (spm * msc.n_colours + 4)  # sweeps + energy(2) + swap(2) kernels per step
+    # per step: spm x (colour kernels + sweep-counter bump) + energy (2) + exchange (2) + round-counter bump,
+    # replayed from one captured CUDA graph
+    launches = args.steps * (spm * (msc.n_colours + 1) + 5)
 
     # ---- dominant kernel alone: the colour sweep ---------------------------------------------------
     n_time = max(4, spm)

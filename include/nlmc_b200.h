@@ -161,6 +161,10 @@ int nlmc_msc_set_packed(nlmc_msc *msc, const uint32_t *packed /*[n][n_words]*/);
 int nlmc_msc_get_packed(nlmc_msc *msc, uint32_t *packed /*[n][n_words]*/);
 int nlmc_msc_sweep(nlmc_msc *msc, int n_sweeps);
 int nlmc_msc_energies(nlmc_msc *msc, double *out_E);
+/* n_sweeps sweeps, recording after every sweep the state of one ladder (out_M [n_sweeps][n_beta][n], the reference's
+ * M[:, jj] = m, NMC/nmc.py:89) and/or the energies of all replicas (out_E [n_sweeps][n_beta][n_ladders_padded],
+ * NPT/npt.py:40-43, NPT/apt_preprocessor.py:107-110) on the device; one copy back at the end */
+int nlmc_msc_sweep_record(nlmc_msc *msc, int n_sweeps, int ladder, int8_t *out_M, double *out_E);
 int nlmc_msc_round(nlmc_msc *msc, int n_sweeps, int num_swapping_pairs, double *out_E);
 int nlmc_msc_round_host(nlmc_msc *msc, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,
                         uint32_t *packed_out, double *out_E);

@@ -44,8 +44,11 @@ struct nlmc_msc {
     int32_t *accepted = nullptr;  // [1]
     int8_t *scratch_spins = nullptr;  // [n]
     unsigned long long seed = 0;
-    uint32_t sweep_counter = 0, round_counter = 0;
+    uint32_t *d_counters = nullptr;  // [2] sweep counter, round counter: on the device so that captured graphs replay
     int k_steps = 6;  // unconditional bit steps of the Bernoulli comparison (tuning knob NLMC_MSC_STEPS)
+    struct RoundGraph { int n_sweeps, pairs; bool with_energy_swap; cudaGraphExec_t exec; };
+    std::vector<RoundGraph> graphs;  // whole rounds captured once per (n_sweeps, pairs) and replayed
+    bool use_graphs = true;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<double> h_betas;
@@ -110,7 +113,8 @@ __device__ __forceinline__ uint32_t comp(const uint4 &v, int k) { return k == 0 
 // (exactly the conditional probability).  ncu on the first version (early-exit loop) showed the kernel
 // ALU-pipe bound with 29% of the lanes idle in the loop tail; see profiles/.
 template <int kSteps>
-__global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int n_sites, uint32_t sweep) {
+__global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int n_sites, const uint32_t *__restrict__ counters) {
+    const uint32_t sweep = counters[0];
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     const int chunks = (a.W + 127) >> 7;
@@ -213,16 +217,16 @@ __global__ void msc_init_kernel(MscDev a, uint32_t stream_id) {
 
 // K4': per (word, lane) sum over sites of the number of unsatisfied bonds at the site, with bit-sliced
 // vertical counters (10 bit planes) flushed every kEnergyChunk sites.  E = sum_i unsat_i - n_bonds.
-constexpr int kEnergyChunk = 128;  // 128 sites * 6 bonds < 2^10
-__global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_acc) {
+constexpr int kEnergyChunk = 128;  // at most 128 sites per warp: 128 sites * 6 bonds < 2^10
+__global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_acc, int chunk) {
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     const int chunks = (a.W + 127) >> 7;
-    const int site_chunks = (a.n + kEnergyChunk - 1) / kEnergyChunk;
+    const int site_chunks = (a.n + chunk - 1) / chunk;
     if (warp >= site_chunks * chunks) return;
     const int word0 = (warp % chunks) * 128 + lane * 4;
     if (word0 >= a.W) return;
-    const int s_begin = (warp / chunks) * kEnergyChunk, s_end = min(a.n, s_begin + kEnergyChunk);
+    const int s_begin = (warp / chunks) * chunk, s_end = min(a.n, s_begin + chunk);
     uint32_t v[4][10];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -292,7 +296,8 @@ __global__ void msc_energy_finish_kernel(int W, int G, int n_ladders, long long 
 constexpr int kMaxBeta = 128;
 __global__ void msc_swap_decide_kernel(int n_beta, int n_ladders, int G, int num_pairs, const double *betas, double *E,
                                        uint32_t *swapmask, int32_t *accepted, uint32_t seed_lo, uint32_t seed_hi,
-                                       uint32_t round, int ladder_offset) {
+                                       const uint32_t *__restrict__ counters, int ladder_offset) {
+    const uint32_t round = counters[1];
     const int ladder = blockIdx.x * blockDim.x + threadIdx.x;
     if (ladder >= n_ladders) return;
     const Philox rng{seed_lo, seed_hi ^ kTagSwap};
@@ -348,6 +353,14 @@ __global__ void msc_swap_apply_kernel(MscDev a, const uint32_t *swapmask) {
     if (A_dirty) row[(size_t)(a.n_beta - 1) * a.G] = A;
 }
 
+__global__ void msc_bump_kernel(uint32_t *counters, int which) { counters[which] += 1u; }
+
+// all replicas (every beta) of one ladder as int8 +-1: out[b][site]
+__global__ void msc_unpack_ladder_kernel(MscDev a, int g, int lane, int8_t *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i < a.n) out[(size_t)b * a.n + i] = ((a.S[(size_t)i * a.W + b * a.G + g] >> lane) & 1u) ? 1 : -1;
+}
+
 __global__ void msc_unpack_kernel(MscDev a, int w, int lane, int8_t *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) out[i] = ((a.S[(size_t)i * a.W + w] >> lane) & 1u) ? 1 : -1;
@@ -392,18 +405,18 @@ static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
             const long long warps = (long long)cnt * chunks;
             const unsigned blocks = (unsigned)((warps + 7) / 8);
             switch (M->k_steps) {
-                case 3: msc_sweep_kernel<3><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
-                case 4: msc_sweep_kernel<4><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
-                case 5: msc_sweep_kernel<5><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
-                case 9: msc_sweep_kernel<9><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
-                case 7: msc_sweep_kernel<7><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
-                case 8: msc_sweep_kernel<8><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
-                case 10: msc_sweep_kernel<10><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
-                case 12: msc_sweep_kernel<12><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
-                default: msc_sweep_kernel<6><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->sweep_counter); break;
+                case 3: msc_sweep_kernel<3><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
+                case 4: msc_sweep_kernel<4><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
+                case 5: msc_sweep_kernel<5><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
+                case 9: msc_sweep_kernel<9><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
+                case 7: msc_sweep_kernel<7><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
+                case 8: msc_sweep_kernel<8><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
+                case 10: msc_sweep_kernel<10><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
+                case 12: msc_sweep_kernel<12><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
+                default: msc_sweep_kernel<6><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
             }
         }
-        ++M->sweep_counter;
+        msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 0);
     }
     NLMC_CUDA(cudaGetLastError());
     return NLMC_OK;
@@ -412,10 +425,14 @@ static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
 static int launch_energy(nlmc_msc *M) {
     const MscDev d = dev_view(M);
     const int chunks = (M->W + 127) / 128;
-    const int site_chunks = (M->n + kEnergyChunk - 1) / kEnergyChunk;
+    // sites per warp: as many as the 10-bit counters allow on big lattices, fewer on small ones so that the
+    // grid still fills the GPU (about 8 warps per SM)
+    const int sites_for_fill = (int)(((long long)M->n * chunks + 148 * 8 - 1) / (148 * 8));
+    const int chunk = std::max(16, std::min(kEnergyChunk, sites_for_fill));
+    const int site_chunks = (M->n + chunk - 1) / chunk;
     NLMC_CUDA(cudaMemsetAsync(M->E_acc, 0, sizeof(int32_t) * (size_t)M->W * 32, M->stream));
     const long long warps = (long long)site_chunks * chunks;
-    msc_energy_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, M->stream>>>(d, M->E_acc);
+    msc_energy_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, M->stream>>>(d, M->E_acc, chunk);
     msc_energy_finish_kernel<<<(M->W * 32 + 255) / 256, 256, 0, M->stream>>>(M->W, M->G, M->n_ladders, M->n_bonds,
                                                                             M->E_acc, M->E);
     NLMC_CUDA(cudaGetLastError());
@@ -428,12 +445,58 @@ static int launch_swap(nlmc_msc *M, int num_pairs) {
     NLMC_CUDA(cudaMemsetAsync(M->swapmask, 0, sizeof(uint32_t) * (size_t)(M->n_beta - 1) * M->G, M->stream));
     msc_swap_decide_kernel<<<(M->n_ladders + 127) / 128, 128, 0, M->stream>>>(
         M->n_beta, M->n_ladders, M->G, num_pairs, M->betas, M->E, M->swapmask, M->accepted, d.seed_lo, d.seed_hi,
-        M->round_counter, M->ladder_offset);
+        M->d_counters, M->ladder_offset);
     const size_t items = (size_t)M->n * M->G;
     msc_swap_apply_kernel<<<(unsigned)((items + 255) / 256), 256, 0, M->stream>>>(d, M->swapmask);
-    ++M->round_counter;
+    msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 1);
     NLMC_CUDA(cudaGetLastError());
     return NLMC_OK;
+}
+
+// sweeps [+ energies + exchange] as one graph launch; graphs are captured once per shape and cached
+static int run_round(nlmc_msc *M, int n_sweeps, int num_pairs, bool with_energy_swap) {
+    const long long launches = (long long)n_sweeps * (M->n_colours + 1);
+    if (!M->use_graphs || launches < 4 || launches > 4096) {  // tiny or huge rounds: plain launches
+        int rc = launch_sweeps(M, n_sweeps);
+        if (!rc && with_energy_swap) rc = launch_energy(M);
+        if (!rc && with_energy_swap) rc = launch_swap(M, num_pairs);
+        return rc;
+    }
+    for (auto &g : M->graphs)
+        if (g.n_sweeps == n_sweeps && g.pairs == num_pairs && g.with_energy_swap == with_energy_swap) {
+            NLMC_CUDA(cudaGraphLaunch(g.exec, M->stream));
+            return NLMC_OK;
+        }
+    cudaGraph_t graph = nullptr;
+    NLMC_CUDA(cudaStreamBeginCapture(M->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = launch_sweeps(M, n_sweeps);
+    if (!rc && with_energy_swap) rc = launch_energy(M);
+    if (!rc && with_energy_swap) rc = launch_swap(M, num_pairs);
+    const cudaError_t e = cudaStreamEndCapture(M->stream, &graph);
+    if (rc || e != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        if (!rc) set_error("nlmc_msc: stream capture failed: %s", cudaGetErrorString(e));
+        return rc ? rc : NLMC_ERR_CUDA;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) {
+        set_error("nlmc_msc: cudaGraphInstantiate failed: %s", cudaGetErrorString(e2));
+        return NLMC_ERR_CUDA;
+    }
+    if (M->graphs.size() >= 8) {  // keep the cache small
+        cudaGraphExecDestroy(M->graphs.front().exec);
+        M->graphs.erase(M->graphs.begin());
+    }
+    M->graphs.push_back({n_sweeps, num_pairs, with_energy_swap, exec});
+    NLMC_CUDA(cudaGraphLaunch(exec, M->stream));
+    return NLMC_OK;
+}
+
+static void drop_graphs(nlmc_msc *M) {
+    for (auto &g : M->graphs) cudaGraphExecDestroy(g.exec);
+    M->graphs.clear();
 }
 
 }  // namespace nlmc
@@ -443,8 +506,9 @@ extern "C" {
 int nlmc_msc_destroy(nlmc_msc *M) {
     if (!M) return NLMC_OK;
     cudaSetDevice(M->inst->device);
+    nlmc::drop_graphs(M);
     void *ptrs[] = {M->S, M->nbr, M->meta, M->site_list, M->thr, M->betas, M->E_acc, M->E, M->swapmask, M->accepted,
-                    M->scratch_spins};
+                    M->scratch_spins, M->d_counters};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (M->ev0) cudaEventDestroy(M->ev0);
     if (M->ev1) cudaEventDestroy(M->ev1);
@@ -540,6 +604,7 @@ int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_lad
     M->seed = seed;
     M->h_betas.assign(betas, betas + n_beta);
     if (const char *e = getenv("NLMC_MSC_STEPS")) M->k_steps = atoi(e);
+    if (const char *e = getenv("NLMC_MSC_GRAPHS")) M->use_graphs = atoi(e) != 0;
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(n_beta, betas);
     const size_t words = (size_t)n * M->W;
     bool ok = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -554,6 +619,8 @@ int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_lad
               cudaMalloc(&M->E, sizeof(double) * (size_t)n_beta * M->n_ladders) == cudaSuccess &&
               cudaMalloc(&M->swapmask, sizeof(uint32_t) * (size_t)std::max(1, n_beta - 1) * M->G) == cudaSuccess &&
               cudaMalloc(&M->accepted, sizeof(int32_t)) == cudaSuccess &&
+              cudaMalloc(&M->d_counters, 2 * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMemset(M->d_counters, 0, 2 * sizeof(uint32_t)) == cudaSuccess &&
               cudaMalloc(&M->scratch_spins, (size_t)n) == cudaSuccess &&
               cudaMemcpy(M->nbr, nbr.data(), sizeof(int32_t) * nbr.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(M->meta, meta.data(), sizeof(uint32_t) * meta.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
@@ -602,9 +669,12 @@ int nlmc_msc_set_betas(nlmc_msc *M, const double *betas) {
 
 int nlmc_msc_set_seed(nlmc_msc *M, unsigned long long seed, unsigned sweep_counter) {
     NLMC_REQUIRE(M, "nlmc_msc_set_seed: NULL handle");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
     M->seed = seed;
-    M->sweep_counter = sweep_counter;
-    M->round_counter = 0;
+    nlmc::drop_graphs(M);  // the seed is a kernel argument of the captured launches
+    const uint32_t c[2] = {sweep_counter, 0u};
+    NLMC_CUDA(cudaMemcpy(M->d_counters, c, sizeof(c), cudaMemcpyHostToDevice));
     return NLMC_OK;
 }
 
@@ -652,7 +722,7 @@ int nlmc_msc_get_packed(nlmc_msc *M, uint32_t *packed) {
 int nlmc_msc_sweep(nlmc_msc *M, int n_sweeps) {
     NLMC_REQUIRE(M && n_sweeps >= 0, "nlmc_msc_sweep: bad arguments");
     NLMC_CUDA(cudaSetDevice(M->inst->device));
-    return nlmc::launch_sweeps(M, n_sweeps);
+    return nlmc::run_round(M, n_sweeps, 0, false);
 }
 
 int nlmc_msc_energies(nlmc_msc *M, double *out_E) {
@@ -672,13 +742,61 @@ int nlmc_msc_round(nlmc_msc *M, int n_sweeps, int num_swapping_pairs, double *ou
     NLMC_REQUIRE(M && n_sweeps >= 0, "nlmc_msc_round: bad arguments");
     NLMC_CUDA(cudaSetDevice(M->inst->device));
     int rc;
-    if ((rc = nlmc::launch_sweeps(M, n_sweeps))) return rc;
-    if ((rc = nlmc::launch_energy(M))) return rc;
-    if (out_E)  // energies of the states the sweeps produced (before the exchange), as the reference reads them
+    if (out_E) {  // energies of the states the sweeps produced (before the exchange), as the reference reads them
+        if ((rc = nlmc::run_round(M, n_sweeps, 0, false))) return rc;
+        if ((rc = nlmc::launch_energy(M))) return rc;
         NLMC_CUDA(cudaMemcpyAsync(out_E, M->E, sizeof(double) * (size_t)M->n_beta * M->n_ladders, cudaMemcpyDeviceToHost,
                                   M->stream));
-    if ((rc = nlmc::launch_swap(M, num_swapping_pairs))) return rc;
-    if (out_E) NLMC_CUDA(cudaStreamSynchronize(M->stream));
+        if ((rc = nlmc::launch_swap(M, num_swapping_pairs))) return rc;
+        NLMC_CUDA(cudaStreamSynchronize(M->stream));
+        return NLMC_OK;
+    }
+    return nlmc::run_round(M, n_sweeps, num_swapping_pairs, true);
+}
+
+/* n_sweeps sweeps with the state of one ladder (all betas) and/or the energies of all replicas recorded after
+ * every sweep ON THE DEVICE and copied back once: the reference's M[:, jj] = m (NMC/nmc.py:89) and per-sweep energy
+ * loops (NPT/npt.py:40-43, NPT/apt_preprocessor.py:107-110) without a host round trip per sweep. */
+int nlmc_msc_sweep_record(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, double *out_E) {
+    using namespace nlmc;
+    NLMC_REQUIRE(M && n_sweeps >= 0, "nlmc_msc_sweep_record: bad arguments");
+    NLMC_REQUIRE(!out_M || (ladder >= 0 && ladder < M->n_ladders), "nlmc_msc_sweep_record: ladder out of range");
+    if (n_sweeps == 0) return NLMC_OK;
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    const size_t m_stride = (size_t)M->n_beta * M->n, e_stride = (size_t)M->n_beta * M->n_ladders;
+    int8_t *recM = nullptr;
+    double *recE = nullptr;
+    if (out_M) NLMC_CUDA(cudaMalloc(&recM, m_stride * (size_t)n_sweeps));
+    if (out_E && cudaMalloc(&recE, sizeof(double) * e_stride * (size_t)n_sweeps) != cudaSuccess) {
+        if (recM) cudaFree(recM);
+        set_error("nlmc_msc_sweep_record: cudaMalloc failed");
+        return NLMC_ERR_CUDA;
+    }
+    const MscDev d = dev_view(M);
+    int rc = NLMC_OK;
+    cudaError_t e = cudaSuccess;
+    for (int s = 0; s < n_sweeps && !rc && e == cudaSuccess; ++s) {
+        rc = launch_sweeps(M, 1);
+        if (!rc && recM)
+            msc_unpack_ladder_kernel<<<dim3((unsigned)((M->n + 255) / 256), (unsigned)M->n_beta), 256, 0, M->stream>>>(
+                d, ladder / 32, ladder % 32, recM + (size_t)s * m_stride);
+        if (!rc && recE) {
+            rc = launch_energy(M);
+            if (!rc) e = cudaMemcpyAsync(recE + (size_t)s * e_stride, M->E, sizeof(double) * e_stride, cudaMemcpyDeviceToDevice, M->stream);
+        }
+    }
+    if (!rc && e == cudaSuccess) e = cudaGetLastError();
+    if (!rc && e == cudaSuccess && recM) e = cudaMemcpyAsync(out_M, recM, m_stride * (size_t)n_sweeps, cudaMemcpyDeviceToHost, M->stream);
+    if (!rc && e == cudaSuccess && recE)
+        e = cudaMemcpyAsync(out_E, recE, sizeof(double) * e_stride * (size_t)n_sweeps, cudaMemcpyDeviceToHost, M->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(M->stream);
+    if (recM) cudaFree(recM);
+    if (recE) cudaFree(recE);
+    if (rc) return rc;
+    if (e != cudaSuccess) {
+        set_error("nlmc_msc_sweep_record: %s", cudaGetErrorString(e));
+        return NLMC_ERR_CUDA;
+    }
     return NLMC_OK;
 }
 

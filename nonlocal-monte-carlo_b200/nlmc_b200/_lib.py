@@ -65,6 +65,7 @@ _SIGNATURES = {
     "nlmc_msc_get_packed": [_vp, _vp],
     "nlmc_msc_sweep": [_vp, _int],
     "nlmc_msc_energies": [_vp, _vp],
+    "nlmc_msc_sweep_record": [_vp, _int, _int, _vp, _vp],
     "nlmc_msc_round": [_vp, _int, _int, _vp],
     "nlmc_msc_round_host": [_vp, _vp, _int, _int, _vp, _vp],
     "nlmc_msc_swap_count": [_vp, C.POINTER(_int), _int],
@@ -341,6 +342,15 @@ class Msc:
         out = np.empty((self.n_beta, self.n_ladders), dtype=np.float64) if fetch else None
         check(lib().nlmc_msc_energies(self._h, _ptr(out)), "nlmc_msc_energies")
         return out
+
+    def sweep_record(self, n_sweeps: int, ladder: int | None = 0, energies: bool = True):
+        """n_sweeps sweeps recorded on the device: (M int8 [n_sweeps][n_beta][n] of `ladder` or None,
+        E float64 [n_sweeps][n_beta][n_ladders] or None)."""
+        Mrec = np.empty((n_sweeps, self.n_beta, self.n), dtype=np.int8) if ladder is not None else None
+        Erec = np.empty((n_sweeps, self.n_beta, self.n_ladders), dtype=np.float64) if energies else None
+        check(lib().nlmc_msc_sweep_record(self._h, int(n_sweeps), int(ladder or 0), _ptr(Mrec), _ptr(Erec)),
+              "nlmc_msc_sweep_record")
+        return Mrec, Erec
 
     def round(self, n_sweeps: int, num_swapping_pairs: int, fetch_energies: bool = False):
         out = np.empty((self.n_beta, self.n_ladders), dtype=np.float64) if fetch_energies else None

@@ -65,12 +65,11 @@ def _npt_run_msc(obj, prob, beta_list):
     M = np.zeros((R * n, spm))
     E_cols = np.zeros((R, spm))
     E_all = None
-    for j in range(spm):
-        msc.sweep(1)
-        E_all = msc.energies()
-        E_cols[:, j] = E_all[:, 0]
-        for r in range(R):
-            M[r * n:(r + 1) * n, j] = msc.get_spins(r, 0)
+    if spm > 0:
+        Mrec, Erec = msc.sweep_record(spm, ladder=0, energies=True)  # recorded on the device, one copy back
+        M[:] = Mrec.transpose(1, 2, 0).reshape(R * n, spm)
+        E_cols[:] = Erec[:, :, 0].T
+        E_all = Erec[-1]
     if obj.num_swap_attempts > 0 and spm > 0:
         msc.round(0, obj.num_swapping_pairs)  # the reference still attempts the exchange after the last round
         count[-1] = msc.swap_count(reset=True)
@@ -253,10 +252,9 @@ def apt_preprocessor_chains_production(prob, reps, iter, saved_state, beta, num_
         state.set_betas([beta])
     burn = max(0, num_sweeps_MCMC - num_sweeps_read)
     state.sweep(burn)
-    Energy = np.zeros((num_rng, min(num_sweeps_read, num_sweeps_MCMC)))
-    for t in range(Energy.shape[1]):
-        state.sweep(1)
-        Energy[:, t] = state.energies()[0, :num_rng]
+    n_read = min(num_sweeps_read, num_sweeps_MCMC)
+    _, Erec = state.sweep_record(n_read, ladder=None, energies=True)  # [n_read][1][ladders], recorded on the device
+    Energy = np.ascontiguousarray(Erec[:, 0, :num_rng].T) if n_read else np.zeros((num_rng, 0))
     return Energy, saved_state
 
 
