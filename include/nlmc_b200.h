@@ -37,6 +37,7 @@ typedef struct nlmc_instance nlmc_instance; /* one Ising instance (J in CSR, h) 
 typedef struct nlmc_replicas nlmc_replicas; /* R int8 spin configurations of one instance (exact path) */
 typedef struct nlmc_msc nlmc_msc;           /* bit-packed replica lattice for the production path  */
 typedef struct nlmc_dense nlmc_dense;       /* dense-J production path (tensor-core field contraction) */
+typedef struct nlmc_col nlmc_col;           /* sparse production path: graph-coloured updates, one CTA per replica */
 
 const char *nlmc_last_error(void);
 int nlmc_version(void);
@@ -203,6 +204,31 @@ int nlmc_dense_best_get(nlmc_dense *d, int8_t *out_spins /*[n_replicas][n] or NU
 int nlmc_dense_sync(nlmc_dense *d);
 int nlmc_dense_time_fields(nlmc_dense *d, int repeats, float *out_ms);
 int nlmc_dense_time_sweeps(nlmc_dense *d, int n_sweeps, float *out_ms);
+
+/* ---- K2a: sparse production path (any J, any h) -- graph-coloured parallel heat bath ---------------
+ * Replaces MCMC (NMC/nmc.py:28-91 and copies) in production mode on arbitrary sparse instances: one CTA per
+ * replica with spins, incrementally maintained local fields and (when it fits) the CSR in shared memory;
+ * sites of one colour are updated in parallel, colours in order; Philox4x32-10 keyed by
+ * (seed; replica_offset + replica, site, sweep).
+ *   nlmc_col_sweep  n_sweeps sweeps in ONE launch; beta_sched [n_sweeps][R] (optional) is the annealing schedule
+ *                   beta_run (nmc.py:56-69); out_E [n_sweeps][R] (optional) the energy after every sweep
+ *                   (nmc.py:386-387); out_spins [ceil(n_sweeps/record_every)][R][n] (optional) the recorded states
+ *                   M[:, ::M_skip] (nmc.py:390); track_best keeps m_init = M[:, argmin E] (nmc.py:394-395) on the device.
+ *   site modes      0 normal, 1 backbone at beta/temp_x, 2 frozen (NMC phases, nmc.py:377-385,398-406). */
+int nlmc_col_create(nlmc_instance *inst, int n_replicas, const double *betas, int replica_offset,
+                    unsigned long long seed, nlmc_col **out);
+int nlmc_col_destroy(nlmc_col *c);
+int nlmc_col_info(const nlmc_col *c, int *n_colours, int *csr_in_smem);
+int nlmc_col_set_betas(nlmc_col *c, const double *betas /*[R]*/);
+int nlmc_col_set_spins(nlmc_col *c, const int8_t *spins /*[R][n]*/);
+int nlmc_col_get_spins(nlmc_col *c, int8_t *out /*[R][n]*/);
+int nlmc_col_set_site_modes(nlmc_col *c, const uint8_t *modes /*[R][n] or NULL*/, double temp_x);
+int nlmc_col_best_reset(nlmc_col *c);
+int nlmc_col_best_get(nlmc_col *c, int8_t *out_spins /*[R][n] or NULL*/, double *out_E /*[R] or NULL*/);
+int nlmc_col_sweep(nlmc_col *c, int n_sweeps, const double *beta_sched, int record_every, int8_t *out_spins,
+                   double *out_E, int track_best);
+int nlmc_col_energies(nlmc_col *c, double *out_E /*[R]*/);
+int nlmc_col_sync(nlmc_col *c);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,490 @@
+// nlmc_col.cu -- K2a: production heat-bath sweeps for ARBITRARY sparse instances (any J values, any h) with
+// graph-coloured parallel updates, one CTA per replica.
+//
+// Replaces MCMC (NMC/nmc.py:28-91 and copies) in production mode where the bit-packed path does not apply
+// (non-lattice graphs such as config C1's random graph, real-valued couplings, fields, NMC phases).  Sites are
+// greedily coloured on the host; sites of one colour have no coupling between them, so they are updated in
+// parallel (the conditional distribution of each is untouched by the others) and the colours are visited in
+// order -- a valid Gibbs sweep with the same single-site rule as the reference:
+//     s_i <- +1 with probability 1/(1 + exp(-2 beta f_i)),  f_i = sum_j J_ij s_j + h_i   (== nmc.py:86-87)
+// Per replica everything lives in shared memory: spins (int8), the local fields f_i (double, maintained
+// INCREMENTALLY: a flip adds 2 J_ij s_i to its neighbours' fields with shared-memory atomics), the NMC phase
+// modes, and the CSR itself when it fits (uint16/int32 columns, fp32 values).  A whole batch of sweeps is one
+// launch: per-sweep energies E = -1/2 sum_i s_i (f_i + h_i) (block reduction, exact for integer J), optional
+// recording of every k-th state (the reference's M[:, ::M_skip]) and tracking of the lowest-energy state
+// (m_init = M[:, argmin E], nmc.py:394-395) all happen inside the kernel.  Fields are recomputed from the spins
+// every kRefresh sweeps so that rounding cannot accumulate.  Random numbers: Philox4x32-10 keyed by
+// (seed; global replica id, site, sweep).
+#include <algorithm>
+#include <cmath>
+
+#include "nlmc_common.cuh"
+
+struct nlmc_col {
+    nlmc_instance *inst = nullptr;
+    int n = 0, R = 0, n_colours = 0, replica_offset = 0;
+    bool csr_in_smem = false, small_cols = false;
+    int32_t *site_order = nullptr;  // [n] sites sorted by colour
+    int32_t *colour_ptr = nullptr;  // [n_colours+1]
+    uint16_t *col16 = nullptr;      // [nnz] (when n <= 65535)
+    float *val32 = nullptr;         // [nnz]
+    int8_t *spins = nullptr;        // [R][n]
+    double *beta = nullptr;         // [R]
+    uint8_t *modes = nullptr;       // [R][n] 0 normal, 1 hot (beta/temp_x), 2 frozen
+    bool modes_on = false;
+    double temp_x = 1.0;
+    double *bestE = nullptr;        // [R]
+    int8_t *bestS = nullptr;        // [R][n]
+    uint32_t sweep_counter = 0;
+    unsigned long long seed = 0;
+    size_t smem_bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+namespace nlmc {
+
+constexpr int kColThreads = 256;
+constexpr int kRefresh = 128;
+
+struct PhiloxC {
+    uint32_t k0, k1;
+    __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+            const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ a;
+            const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ b;
+            c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+
+struct ColArgs {
+    int n, nnz, n_colours, n_sweeps, record_every, replica_offset;
+    const int32_t *rp, *ci;
+    const double *val, *h;
+    const uint16_t *col16;
+    const float *val32;
+    const int32_t *site_order, *colour_ptr;
+    int8_t *spins;
+    const double *beta;
+    const double *beta_sched;  // optional [n_sweeps][R]: annealing (beta_run of nmc.py:56-69)
+    const uint8_t *modes;
+    double temp_x;
+    uint32_t seed_lo, seed_hi, sweep0;
+    int8_t *out_spins;   // [n_rec][R][n] or null
+    double *out_E;       // [n_sweeps][R] or null
+    double *bestE;       // [R] or null
+    int8_t *bestS;       // [R][n]
+    int R;
+};
+
+template <bool kSmemCsr, typename ColT>
+__global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    __shared__ double red[kColThreads / 32];
+    __shared__ double s_E;
+    const int n = a.n, tid = threadIdx.x, r = blockIdx.x;
+    double *fld = reinterpret_cast<double *>(sm);
+    int32_t *rp_s = reinterpret_cast<int32_t *>(fld + n);
+    float *val_s = reinterpret_cast<float *>(rp_s + (kSmemCsr ? n + 1 : 0));
+    ColT *col_s = reinterpret_cast<ColT *>(val_s + (kSmemCsr ? a.nnz : 0));
+    int8_t *spin = reinterpret_cast<int8_t *>(col_s + (kSmemCsr ? a.nnz + (a.nnz & 1) : 0));
+    uint8_t *mode = reinterpret_cast<uint8_t *>(spin + n);
+
+    int8_t *g_spin = a.spins + (size_t)r * n;
+    const uint8_t *g_mode = a.modes ? a.modes + (size_t)r * n : nullptr;
+    if (kSmemCsr) {
+        for (int i = tid; i <= n; i += kColThreads) rp_s[i] = a.rp[i];
+        for (int p = tid; p < a.nnz; p += kColThreads) {
+            val_s[p] = a.val32[p];
+            col_s[p] = sizeof(ColT) == 2 ? (ColT)a.col16[p] : (ColT)a.ci[p];
+        }
+    }
+    for (int i = tid; i < n; i += kColThreads) {
+        spin[i] = g_spin[i];
+        mode[i] = g_mode ? g_mode[i] : 0;
+    }
+    __syncthreads();
+    auto row_begin = [&](int i) { return kSmemCsr ? rp_s[i] : a.rp[i]; };
+    auto col_of = [&](int p) -> int { return kSmemCsr ? (int)col_s[p] : a.ci[p]; };
+    auto val_of = [&](int p) -> double { return kSmemCsr ? (double)val_s[p] : a.val[p]; };
+    auto refresh_fields = [&]() {
+        for (int i = tid; i < n; i += kColThreads) {
+            double f = a.h[i];
+            const int e = row_begin(i + 1);
+            for (int p = row_begin(i); p < e; ++p) f += val_of(p) * (double)spin[col_of(p)];
+            fld[i] = f;
+        }
+        __syncthreads();
+    };
+    refresh_fields();
+
+    double beta = a.beta[r];
+    double beta_hot = beta / a.temp_x;
+    const PhiloxC rng{a.seed_lo, a.seed_hi ^ 0x434f4c52u};
+    const uint32_t rid = (uint32_t)(a.replica_offset + r);
+    double best = a.bestE ? a.bestE[r] : 0.0;
+    int n_rec = 0;
+    for (int s = 0; s < a.n_sweeps; ++s) {
+        const uint32_t sweep = a.sweep0 + (uint32_t)s;
+        if (a.beta_sched) {
+            beta = a.beta_sched[(size_t)s * a.R + r];
+            beta_hot = beta / a.temp_x;
+        }
+        for (int c = 0; c < a.n_colours; ++c) {
+            const int cb = a.colour_ptr[c], ce = a.colour_ptr[c + 1];
+            for (int idx = cb + tid; idx < ce; idx += kColThreads) {
+                const int i = a.site_order[idx];
+                const int md = mode[i];
+                if (md == 2) continue;  // frozen (the reference pins these spins with h = +-1e4, nmc.py:381,400)
+                const double b = md == 1 ? beta_hot : beta;  // backbone rows of J, h divided by temp_x (nmc.py:379-380)
+                const uint4 rnd = rng(rid, (uint32_t)i, sweep, 0u);
+                const double u = ((double)rnd.x * 4294967296.0 + (double)rnd.y + 0.5) * (1.0 / 18446744073709551616.0);
+                const double p_up = 1.0 / (1.0 + exp(-2.0 * b * fld[i]));
+                const int s_new = u < p_up ? 1 : -1;
+                const int s_old = spin[i];
+                if (s_new != s_old) {
+                    spin[i] = (int8_t)s_new;
+                    const double d = (double)(s_new - s_old);
+                    const int e = row_begin(i + 1);
+                    for (int p = row_begin(i); p < e; ++p) atomicAdd(&fld[col_of(p)], val_of(p) * d);
+                }
+            }
+            __syncthreads();
+        }
+        if ((s + 1) % kRefresh == 0) refresh_fields();
+        const bool want_E = a.out_E != nullptr || a.bestE != nullptr;
+        if (want_E) {  // E = -(m^T J m / 2 + m^T h) = -1/2 sum_i s_i (f_i + h_i)
+            double part = 0.0;
+            for (int i = tid; i < n; i += kColThreads) part += (double)spin[i] * (fld[i] + a.h[i]);
+            part = warp_sum(part);
+            if ((tid & 31) == 0) red[tid >> 5] = part;
+            __syncthreads();
+            if (tid < 32) {
+                double v = tid < kColThreads / 32 ? red[tid] : 0.0;
+                v = warp_sum(v);
+                if (tid == 0) s_E = -0.5 * v;
+            }
+            __syncthreads();
+            const double E = s_E;
+            if (a.out_E && tid == 0) a.out_E[(size_t)s * a.R + r] = E;
+            if (a.bestE && E < best) {  // strict improvement: the first minimum wins, like np.argmin
+                best = E;
+                int8_t *dst = a.bestS + (size_t)r * n;
+                for (int i = tid; i < n; i += kColThreads) dst[i] = spin[i];
+            }
+        }
+        if (a.out_spins && a.record_every > 0 && s % a.record_every == 0) {
+            int8_t *dst = a.out_spins + ((size_t)n_rec * a.R + r) * n;
+            for (int i = tid; i < n; i += kColThreads) dst[i] = spin[i];
+            ++n_rec;
+        }
+        __syncthreads();  // copies of this sweep's state are done before the next sweep changes it
+    }
+    for (int i = tid; i < n; i += kColThreads) g_spin[i] = spin[i];
+    if (a.bestE && tid == 0) a.bestE[r] = best;
+}
+
+__global__ void col_energy_kernel(int n, const int32_t *__restrict__ rp, const int32_t *__restrict__ ci,
+                                  const double *__restrict__ val, const double *__restrict__ h,
+                                  const int8_t *__restrict__ spins, double *E) {
+    __shared__ double red[8];
+    const int8_t *m = spins + (size_t)blockIdx.x * n;
+    double part = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double x = 0.0;
+        for (int p = rp[i]; p < rp[i + 1]; ++p) x += val[p] * (double)m[ci[p]];
+        part += (double)m[i] * (0.5 * x + h[i]);
+    }
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) E[blockIdx.x] = -v;
+    }
+}
+
+__global__ void col_init_kernel(size_t count, int n, int replica_offset, int8_t *spins, uint32_t seed_lo, uint32_t seed_hi) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const PhiloxC rng{seed_lo, seed_hi ^ 0x494e4954u};
+    const uint4 x = rng((uint32_t)(replica_offset + i / n), (uint32_t)(i % n), 0u, 7u);
+    spins[i] = (x.x & 1u) ? 1 : -1;
+}
+
+__global__ void col_fill_kernel(int count, double *p, double v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) p[i] = v;
+}
+
+}  // namespace nlmc
+
+extern "C" {
+
+int nlmc_col_destroy(nlmc_col *Cc) {
+    if (!Cc) return NLMC_OK;
+    cudaSetDevice(Cc->inst->device);
+    void *ptrs[] = {Cc->site_order, Cc->colour_ptr, Cc->col16, Cc->val32, Cc->spins, Cc->beta, Cc->modes, Cc->bestE, Cc->bestS};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (Cc->stream) cudaStreamDestroy(Cc->stream);
+    delete Cc;
+    return NLMC_OK;
+}
+
+int nlmc_col_set_betas(nlmc_col *Cc, const double *betas) {
+    NLMC_REQUIRE(Cc && betas, "nlmc_col_set_betas: NULL argument");
+    NLMC_CUDA(cudaSetDevice(Cc->inst->device));
+    NLMC_CUDA(cudaMemcpyAsync(Cc->beta, betas, sizeof(double) * (size_t)Cc->R, cudaMemcpyHostToDevice, Cc->stream));
+    NLMC_CUDA(cudaStreamSynchronize(Cc->stream));
+    return NLMC_OK;
+}
+
+int nlmc_col_create(nlmc_instance *I, int n_replicas, const double *betas, int replica_offset, unsigned long long seed,
+                    nlmc_col **out) {
+    using namespace nlmc;
+    NLMC_REQUIRE(I && out && betas && n_replicas >= 1, "nlmc_col_create: bad arguments");
+    *out = nullptr;
+    const int n = I->n, nnz = I->nnz;
+    // greedy colouring in site order; a site's colour must differ from all its neighbours' (both directions)
+    std::vector<std::vector<int>> adj((size_t)n);
+    for (int i = 0; i < n; ++i)
+        for (int p = I->h_row_ptr[i]; p < I->h_row_ptr[i + 1]; ++p) {
+            const int j = I->h_col[(size_t)p];
+            if (j == i || I->h_val[(size_t)p] == 0.0) continue;
+            adj[(size_t)i].push_back(j);
+            adj[(size_t)j].push_back(i);
+        }
+    std::vector<int> colour((size_t)n, -1), mark;
+    int n_colours = 0;
+    for (int i = 0; i < n; ++i) {
+        mark.assign((size_t)n_colours + 1, 0);
+        for (int j : adj[(size_t)i]) if (colour[(size_t)j] >= 0) mark[(size_t)colour[(size_t)j]] = 1;
+        int c = 0;
+        while (c < n_colours && mark[(size_t)c]) ++c;
+        colour[(size_t)i] = c;
+        n_colours = std::max(n_colours, c + 1);
+    }
+    std::vector<int32_t> order((size_t)n), cptr((size_t)n_colours + 1, 0);
+    for (int i = 0; i < n; ++i) ++cptr[(size_t)colour[(size_t)i] + 1];
+    for (int c = 0; c < n_colours; ++c) cptr[(size_t)c + 1] += cptr[(size_t)c];
+    {
+        std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1);
+        for (int i = 0; i < n; ++i) order[(size_t)fill[(size_t)colour[(size_t)i]]++] = i;
+    }
+    NLMC_CUDA(cudaSetDevice(I->device));
+    auto *Cc = new nlmc_col();
+    Cc->inst = I;
+    Cc->n = n;
+    Cc->R = n_replicas;
+    Cc->n_colours = n_colours;
+    Cc->replica_offset = replica_offset;
+    Cc->seed = seed;
+    Cc->small_cols = n <= 65535;
+    const size_t base = sizeof(double) * (size_t)n + 2 * (size_t)n + 64;
+    const size_t with_csr = base + sizeof(int32_t) * (size_t)(n + 1) + sizeof(float) * (size_t)nnz +
+                            (Cc->small_cols ? 2 : 4) * ((size_t)nnz + ((size_t)nnz & 1));
+    Cc->csr_in_smem = with_csr <= 220 * 1024;
+    Cc->smem_bytes = Cc->csr_in_smem ? with_csr : base;
+    if (Cc->smem_bytes > 220 * 1024) {
+        set_error("nlmc_col_create: %d spins do not fit in shared memory (one CTA per replica)", n);
+        delete Cc;
+        return NLMC_ERR_UNSUPPORTED;
+    }
+    std::vector<float> v32((size_t)std::max(nnz, 1));
+    std::vector<uint16_t> c16((size_t)std::max(nnz, 1));
+    for (int p = 0; p < nnz; ++p) { v32[(size_t)p] = (float)I->h_val[(size_t)p]; c16[(size_t)p] = (uint16_t)I->h_col[(size_t)p]; }
+    const size_t rn = (size_t)n_replicas * n;
+    bool ok = cudaStreamCreateWithFlags(&Cc->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&Cc->site_order, sizeof(int32_t) * (size_t)n) == cudaSuccess &&
+              cudaMalloc(&Cc->colour_ptr, sizeof(int32_t) * cptr.size()) == cudaSuccess &&
+              cudaMalloc(&Cc->col16, sizeof(uint16_t) * c16.size()) == cudaSuccess &&
+              cudaMalloc(&Cc->val32, sizeof(float) * v32.size()) == cudaSuccess &&
+              cudaMalloc(&Cc->spins, rn) == cudaSuccess && cudaMalloc(&Cc->beta, sizeof(double) * (size_t)n_replicas) == cudaSuccess &&
+              cudaMalloc(&Cc->bestE, sizeof(double) * (size_t)n_replicas) == cudaSuccess && cudaMalloc(&Cc->bestS, rn) == cudaSuccess &&
+              cudaMemcpy(Cc->site_order, order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(Cc->colour_ptr, cptr.data(), sizeof(int32_t) * cptr.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(Cc->col16, c16.data(), sizeof(uint16_t) * c16.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(Cc->val32, v32.data(), sizeof(float) * v32.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        set_error("nlmc_col_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        nlmc_col_destroy(Cc);
+        return NLMC_ERR_CUDA;
+    }
+    int rc = nlmc_col_set_betas(Cc, betas);
+    if (!rc) {
+        col_init_kernel<<<(unsigned)((rn + 255) / 256), 256, 0, Cc->stream>>>(rn, n, replica_offset, Cc->spins, (uint32_t)seed,
+                                                                             (uint32_t)(seed >> 32));
+        col_fill_kernel<<<(n_replicas + 127) / 128, 128, 0, Cc->stream>>>(n_replicas, Cc->bestE, 1e300);
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(Cc->stream) != cudaSuccess) {
+            set_error("nlmc_col_create: init kernels failed");
+            rc = NLMC_ERR_CUDA;
+        }
+    }
+    if (rc) {
+        nlmc_col_destroy(Cc);
+        return rc;
+    }
+    *out = Cc;
+    return NLMC_OK;
+}
+
+int nlmc_col_info(const nlmc_col *Cc, int *n_colours, int *csr_in_smem) {
+    NLMC_REQUIRE(Cc, "nlmc_col_info: NULL handle");
+    if (n_colours) *n_colours = Cc->n_colours;
+    if (csr_in_smem) *csr_in_smem = Cc->csr_in_smem ? 1 : 0;
+    return NLMC_OK;
+}
+
+int nlmc_col_set_spins(nlmc_col *Cc, const int8_t *spins) {
+    NLMC_REQUIRE(Cc && spins, "nlmc_col_set_spins: NULL argument");
+    NLMC_CUDA(cudaSetDevice(Cc->inst->device));
+    NLMC_CUDA(cudaMemcpyAsync(Cc->spins, spins, (size_t)Cc->R * Cc->n, cudaMemcpyHostToDevice, Cc->stream));
+    NLMC_CUDA(cudaStreamSynchronize(Cc->stream));
+    return NLMC_OK;
+}
+
+int nlmc_col_get_spins(nlmc_col *Cc, int8_t *out) {
+    NLMC_REQUIRE(Cc && out, "nlmc_col_get_spins: NULL argument");
+    NLMC_CUDA(cudaSetDevice(Cc->inst->device));
+    NLMC_CUDA(cudaMemcpyAsync(out, Cc->spins, (size_t)Cc->R * Cc->n, cudaMemcpyDeviceToHost, Cc->stream));
+    NLMC_CUDA(cudaStreamSynchronize(Cc->stream));
+    return NLMC_OK;
+}
+
+int nlmc_col_set_site_modes(nlmc_col *Cc, const uint8_t *modes, double temp_x) {
+    NLMC_REQUIRE(Cc, "nlmc_col_set_site_modes: NULL handle");
+    NLMC_REQUIRE(!modes || temp_x > 0.0, "nlmc_col_set_site_modes: temp_x must be positive");
+    NLMC_CUDA(cudaSetDevice(Cc->inst->device));
+    if (!modes) {
+        Cc->modes_on = false;
+        return NLMC_OK;
+    }
+    const size_t rn = (size_t)Cc->R * Cc->n;
+    if (!Cc->modes) NLMC_CUDA(cudaMalloc(&Cc->modes, rn));
+    NLMC_CUDA(cudaMemcpyAsync(Cc->modes, modes, rn, cudaMemcpyHostToDevice, Cc->stream));
+    NLMC_CUDA(cudaStreamSynchronize(Cc->stream));
+    Cc->modes_on = true;
+    Cc->temp_x = temp_x;
+    return NLMC_OK;
+}
+
+int nlmc_col_best_reset(nlmc_col *Cc) {
+    NLMC_REQUIRE(Cc, "nlmc_col_best_reset: NULL handle");
+    NLMC_CUDA(cudaSetDevice(Cc->inst->device));
+    nlmc::col_fill_kernel<<<(Cc->R + 127) / 128, 128, 0, Cc->stream>>>(Cc->R, Cc->bestE, 1e300);
+    NLMC_CUDA(cudaGetLastError());
+    return NLMC_OK;
+}
+
+int nlmc_col_best_get(nlmc_col *Cc, int8_t *out_spins, double *out_E) {
+    NLMC_REQUIRE(Cc, "nlmc_col_best_get: NULL handle");
+    NLMC_CUDA(cudaSetDevice(Cc->inst->device));
+    if (out_spins) NLMC_CUDA(cudaMemcpyAsync(out_spins, Cc->bestS, (size_t)Cc->R * Cc->n, cudaMemcpyDeviceToHost, Cc->stream));
+    if (out_E) NLMC_CUDA(cudaMemcpyAsync(out_E, Cc->bestE, sizeof(double) * (size_t)Cc->R, cudaMemcpyDeviceToHost, Cc->stream));
+    NLMC_CUDA(cudaStreamSynchronize(Cc->stream));
+    return NLMC_OK;
+}
+
+/* n_sweeps sweeps in ONE launch.  out_E [n_sweeps][R] (optional): energy after every sweep.  out_spins
+ * [ceil(n_sweeps/record_every)][R][n] (optional): the state after sweeps 0, record_every, ... (the reference's
+ * M[:, ::M_skip]).  track_best != 0: keep the lowest-energy state since nlmc_col_best_reset. */
+int nlmc_col_sweep(nlmc_col *Cc, int n_sweeps, const double *beta_sched, int record_every, int8_t *out_spins,
+                   double *out_E, int track_best) {
+    using namespace nlmc;
+    NLMC_REQUIRE(Cc && n_sweeps >= 0, "nlmc_col_sweep: bad arguments");
+    NLMC_REQUIRE(!out_spins || record_every >= 1, "nlmc_col_sweep: record_every must be >= 1 when recording");
+    if (n_sweeps == 0) return NLMC_OK;
+    nlmc_instance *I = Cc->inst;
+    NLMC_CUDA(cudaSetDevice(I->device));
+    const size_t R = (size_t)Cc->R, n = (size_t)Cc->n;
+    const size_t n_rec = out_spins ? ((size_t)n_sweeps + record_every - 1) / record_every : 0;
+    int8_t *d_rec = nullptr;
+    double *d_E = nullptr, *d_sched = nullptr;
+    if (beta_sched) {
+        NLMC_CUDA(cudaMalloc(&d_sched, sizeof(double) * (size_t)n_sweeps * R));
+        if (cudaMemcpyAsync(d_sched, beta_sched, sizeof(double) * (size_t)n_sweeps * R, cudaMemcpyHostToDevice, Cc->stream) != cudaSuccess) {
+            cudaFree(d_sched);
+            set_error("nlmc_col_sweep: copy of the beta schedule failed");
+            return NLMC_ERR_CUDA;
+        }
+    }
+    if (out_spins && cudaMalloc(&d_rec, n_rec * R * n) != cudaSuccess) {
+        if (d_sched) cudaFree(d_sched);
+        set_error("nlmc_col_sweep: cudaMalloc failed");
+        return NLMC_ERR_CUDA;
+    }
+    if (out_E && cudaMalloc(&d_E, sizeof(double) * (size_t)n_sweeps * R) != cudaSuccess) {
+        if (d_rec) cudaFree(d_rec);
+        if (d_sched) cudaFree(d_sched);
+        set_error("nlmc_col_sweep: cudaMalloc failed");
+        return NLMC_ERR_CUDA;
+    }
+    ColArgs a;
+    a.n = Cc->n; a.nnz = I->nnz; a.n_colours = Cc->n_colours; a.n_sweeps = n_sweeps; a.record_every = record_every;
+    a.replica_offset = Cc->replica_offset;
+    a.rp = I->row_ptr; a.ci = I->col; a.val = I->val; a.h = I->h; a.col16 = Cc->col16; a.val32 = Cc->val32;
+    a.site_order = Cc->site_order; a.colour_ptr = Cc->colour_ptr;
+    a.spins = Cc->spins; a.beta = Cc->beta; a.beta_sched = d_sched; a.modes = Cc->modes_on ? Cc->modes : nullptr; a.temp_x = Cc->temp_x;
+    a.seed_lo = (uint32_t)Cc->seed; a.seed_hi = (uint32_t)(Cc->seed >> 32); a.sweep0 = Cc->sweep_counter;
+    a.out_spins = d_rec; a.out_E = d_E; a.bestE = track_best ? Cc->bestE : nullptr; a.bestS = Cc->bestS; a.R = Cc->R;
+    cudaError_t e = cudaSuccess;
+    const int smem = (int)Cc->smem_bytes;
+    if (Cc->csr_in_smem && Cc->small_cols) {
+        e = cudaFuncSetAttribute(col_sweep_kernel<true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) col_sweep_kernel<true, uint16_t><<<(unsigned)R, kColThreads, smem, Cc->stream>>>(a);
+    } else if (Cc->csr_in_smem) {
+        e = cudaFuncSetAttribute(col_sweep_kernel<true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) col_sweep_kernel<true, int32_t><<<(unsigned)R, kColThreads, smem, Cc->stream>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(col_sweep_kernel<false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) col_sweep_kernel<false, int32_t><<<(unsigned)R, kColThreads, smem, Cc->stream>>>(a);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    Cc->sweep_counter += (uint32_t)n_sweeps;
+    if (e == cudaSuccess && d_rec) e = cudaMemcpyAsync(out_spins, d_rec, n_rec * R * n, cudaMemcpyDeviceToHost, Cc->stream);
+    if (e == cudaSuccess && d_E) e = cudaMemcpyAsync(out_E, d_E, sizeof(double) * (size_t)n_sweeps * R, cudaMemcpyDeviceToHost, Cc->stream);
+    if (e == cudaSuccess && (d_rec || d_E || d_sched)) e = cudaStreamSynchronize(Cc->stream);
+    if (d_rec) cudaFree(d_rec);
+    if (d_E) cudaFree(d_E);
+    if (d_sched) cudaFree(d_sched);
+    if (e != cudaSuccess) {
+        set_error("nlmc_col_sweep: %s", cudaGetErrorString(e));
+        return NLMC_ERR_CUDA;
+    }
+    return NLMC_OK;
+}
+
+int nlmc_col_energies(nlmc_col *Cc, double *out_E) {
+    using namespace nlmc;
+    NLMC_REQUIRE(Cc && out_E, "nlmc_col_energies: NULL argument");
+    nlmc_instance *I = Cc->inst;
+    NLMC_CUDA(cudaSetDevice(I->device));
+    double *d_E = nullptr;
+    NLMC_CUDA(cudaMalloc(&d_E, sizeof(double) * (size_t)Cc->R));
+    col_energy_kernel<<<(unsigned)Cc->R, 256, 0, Cc->stream>>>(Cc->n, I->row_ptr, I->col, I->val, I->h, Cc->spins, d_E);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_E, d_E, sizeof(double) * (size_t)Cc->R, cudaMemcpyDeviceToHost, Cc->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(Cc->stream);
+    cudaFree(d_E);
+    if (e != cudaSuccess) {
+        set_error("nlmc_col_energies: %s", cudaGetErrorString(e));
+        return NLMC_ERR_CUDA;
+    }
+    return NLMC_OK;
+}
+
+int nlmc_col_sync(nlmc_col *Cc) {
+    NLMC_REQUIRE(Cc, "nlmc_col_sync: NULL handle");
+    NLMC_CUDA(cudaSetDevice(Cc->inst->device));
+    NLMC_CUDA(cudaStreamSynchronize(Cc->stream));
+    return NLMC_OK;
+}
+
+}  // extern "C"

@@ -72,6 +72,18 @@ _SIGNATURES = {
     "nlmc_msc_sync": [_vp],
     "nlmc_msc_timer_mark": [_vp, _int],
     "nlmc_msc_timer_elapsed_ms": [_vp, C.POINTER(C.c_float)],
+    "nlmc_col_create": [_vp, _int, _f64, _int, C.c_ulonglong, C.POINTER(_vp)],
+    "nlmc_col_destroy": [_vp],
+    "nlmc_col_info": [_vp, C.POINTER(_int), C.POINTER(_int)],
+    "nlmc_col_set_betas": [_vp, _f64],
+    "nlmc_col_set_spins": [_vp, _i8],
+    "nlmc_col_get_spins": [_vp, _i8],
+    "nlmc_col_set_site_modes": [_vp, _vp, _dbl],
+    "nlmc_col_best_reset": [_vp],
+    "nlmc_col_best_get": [_vp, _vp, _vp],
+    "nlmc_col_sweep": [_vp, _int, _vp, _int, _vp, _vp, _int],
+    "nlmc_col_energies": [_vp, _f64],
+    "nlmc_col_sync": [_vp],
     "nlmc_dense_create": [_vp, _int, _f64, _int, C.c_ulonglong, C.POINTER(_vp)],
     "nlmc_dense_destroy": [_vp],
     "nlmc_dense_set_betas": [_vp, _f64],
@@ -466,6 +478,86 @@ class Dense:
     def close(self):
         if getattr(self, "_h", None):
             lib().nlmc_dense_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Col:
+    """Sparse production state (K2a): R replicas, graph-coloured parallel heat bath, one CTA per replica."""
+
+    def __init__(self, inst: Instance, betas, seed: int = 0, replica_offset: int = 0):
+        self.inst = inst
+        self.n = inst.n
+        self.betas = np.ascontiguousarray(betas, dtype=np.float64).reshape(-1)
+        self.R = len(self.betas)
+        handle = _vp()
+        check(lib().nlmc_col_create(inst._h, self.R, self.betas, int(replica_offset), int(seed) & (2**64 - 1),
+                                    C.byref(handle)), "nlmc_col_create")
+        self._h = handle
+        nc, sm = _int(), _int()
+        check(lib().nlmc_col_info(self._h, C.byref(nc), C.byref(sm)), "nlmc_col_info")
+        self.n_colours, self.csr_in_smem = nc.value, bool(sm.value)
+
+    def set_betas(self, betas):
+        b = np.ascontiguousarray(betas, dtype=np.float64).reshape(-1)
+        assert len(b) == self.R
+        check(lib().nlmc_col_set_betas(self._h, b), "nlmc_col_set_betas")
+        self.betas = b
+
+    def set_spins(self, spins):
+        s = np.ascontiguousarray(spins, dtype=np.int8).reshape(self.R, self.n)
+        check(lib().nlmc_col_set_spins(self._h, s), "nlmc_col_set_spins")
+
+    def get_spins(self) -> np.ndarray:
+        out = np.empty((self.R, self.n), dtype=np.int8)
+        check(lib().nlmc_col_get_spins(self._h, out), "nlmc_col_get_spins")
+        return out
+
+    def set_site_modes(self, modes, temp_x: float = 1.0):
+        m = None if modes is None else np.ascontiguousarray(modes, dtype=np.uint8).reshape(self.R, self.n)
+        check(lib().nlmc_col_set_site_modes(self._h, _ptr(m), float(temp_x)), "nlmc_col_set_site_modes")
+
+    def best_reset(self):
+        check(lib().nlmc_col_best_reset(self._h), "nlmc_col_best_reset")
+
+    def best_get(self):
+        spins = np.empty((self.R, self.n), dtype=np.int8)
+        E = np.empty(self.R, dtype=np.float64)
+        check(lib().nlmc_col_best_get(self._h, spins.ctypes.data, E.ctypes.data), "nlmc_col_best_get")
+        return spins, E
+
+    def sweep(self, n_sweeps: int):
+        check(lib().nlmc_col_sweep(self._h, int(n_sweeps), None, 0, None, None, 0), "nlmc_col_sweep")
+
+    def sweep_record(self, n_sweeps: int, record_every: int = 1, track_best: bool = False, beta_sched=None,
+                     want_states: bool = True, want_energies: bool = True):
+        """n_sweeps sweeps in one launch -> (states int8 [n_rec][R][n] or None, E [n_sweeps][R] or None)."""
+        n_rec = (n_sweeps + record_every - 1) // record_every if want_states else 0
+        states = np.empty((n_rec, self.R, self.n), dtype=np.int8) if want_states else None
+        E = np.empty((n_sweeps, self.R), dtype=np.float64) if want_energies else None
+        sched = None
+        if beta_sched is not None:
+            sched = np.ascontiguousarray(beta_sched, dtype=np.float64).reshape(n_sweeps, self.R)
+        check(lib().nlmc_col_sweep(self._h, int(n_sweeps), _ptr(sched), int(record_every), _ptr(states), _ptr(E),
+                                   int(track_best)), "nlmc_col_sweep")
+        return states, E
+
+    def energies(self) -> np.ndarray:
+        out = np.empty(self.R, dtype=np.float64)
+        check(lib().nlmc_col_energies(self._h, out), "nlmc_col_energies")
+        return out
+
+    def sync(self):
+        check(lib().nlmc_col_sync(self._h), "nlmc_col_sync")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nlmc_col_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -10,6 +10,8 @@ energies in ``self.energies_all_runs`` ([n_beta][num_runs]).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import _lib, host
@@ -85,8 +87,22 @@ def _npt_run_msc(obj, prob, beta_list):
 
 
 # ---------------------------------------------------------------------------------------------------
-# dense engine (K3): one row per replica, beta per row, NMC phases as per-site modes
+# generic engines: sparse graph-coloured (K2a) or dense tensor-core (K3); one row per replica, beta per row,
+# NMC phases as per-site modes
 # ---------------------------------------------------------------------------------------------------
+def _generic_engine(prob: host.Problem, betas, seed: int):
+    """Sparse instances (mean degree <= 128, fits one CTA's shared memory) take the graph-coloured kernel; dense
+    ones (SK) the tensor-core path, where a colouring would degenerate to one site per colour."""
+    betas = np.asarray(betas, dtype=np.float64)
+    mean_degree = len(prob.val) / max(prob.n, 1)
+    if mean_degree <= 128 and not os.environ.get("NLMC_FORCE_DENSE"):
+        try:
+            return _lib.Col(prob.inst, betas, seed=seed)
+        except _lib.NlmcError:
+            pass
+    return _lib.Dense(prob.inst, betas, n_split=3, seed=seed)
+
+
 def _backbones(prob, states, global_beta, nmc_kw):
     """LBP backbone (K5 + host lambda schedule) of every state in `states` [G][n] -> list of index arrays."""
     from .nmc_core import lbp_convexified
@@ -118,6 +134,13 @@ def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True):
         d.set_spins(m_init)
         d.set_site_modes(modes, temp_x)
         d.best_reset()
+        if hasattr(d, "sweep_record"):  # K2a: the whole phase is one launch, recording and argmin on the device
+            states, E = d.sweep_record(phase, record_every=M_skip, track_best=True)
+            for g in range(G):
+                cols[g].extend(states[:, g])
+                ens[g].extend(E[::M_skip, g])
+            m_init, _ = d.best_get()
+            return
         for j in range(phase):
             d.sweep(1)
             E = d.best_update()
@@ -160,8 +183,8 @@ def _npt_run_dense(obj, prob, beta_list, nmc_kw):
     mc_ids = [r for r in range(R) if not obj.doNMC[r]]
     nmc_ids = [r for r in range(R) if obj.doNMC[r]]
     seed = _seed_from_numpy()
-    d_mc = _lib.Dense(prob.inst, beta_list[mc_ids], n_split=3, seed=seed) if mc_ids else None
-    d_nmc = _lib.Dense(prob.inst, np.full(len(nmc_ids), float(nmc_kw["global_beta"])), n_split=3, seed=seed + 1) \
+    d_mc = _generic_engine(prob, beta_list[mc_ids], seed) if mc_ids else None
+    d_nmc = _generic_engine(prob, np.full(len(nmc_ids), float(nmc_kw["global_beta"])), seed + 1) \
         if nmc_ids else None  # doNMC replicas run at global_beta, not beta_list[i] (NPT/npt.py:630-637)
     state = np.sign(2 * np.random.rand(R, n) - 1).astype(np.int8)  # NPT/npt.py:612
     M = np.zeros((R * n, spm))
@@ -172,7 +195,12 @@ def _npt_run_dense(obj, prob, beta_list, nmc_kw):
         last = ii == obj.num_swap_attempts - 1
         if mc_ids:
             d_mc.set_spins(state[mc_ids])
-            if last:
+            if last and hasattr(d_mc, "sweep_record"):
+                states, E = d_mc.sweep_record(spm, record_every=1)
+                for g, r in enumerate(mc_ids):
+                    M[r * n:(r + 1) * n, :] = states[:, g].T
+                    E_cols[r] = E[:, g]
+            elif last:
                 for j in range(spm):
                     d_mc.sweep(1)
                     E = d_mc.energies()
@@ -217,15 +245,19 @@ def nmc_run_production(obj, kw):
     prob = host.Problem(obj.J, obj.h, obj.device)
     n = prob.n
     global_beta = kw["global_beta"]
-    d = _lib.Dense(prob.inst, [float(global_beta)], n_split=3, seed=_seed_from_numpy())
+    d = _generic_engine(prob, [float(global_beta)], _seed_from_numpy())
     d.set_spins(np.sign(2 * np.random.rand(n) - 1).astype(np.int8)[None, :])  # nmc.py:487
     sched = host.beta_schedule(kw["num_sweeps_initial"], global_beta, anneal=True, sweeps_per_beta=1, initial_beta=0)
     d.best_reset()
-    for b in sched:
-        d.set_betas([max(float(b), 1e-12)])
-        d.sweep(1)
-        d.best_update(fetch=False)
-    d.set_betas([float(global_beta)])
+    if hasattr(d, "sweep_record"):  # the whole annealing leg is one launch
+        if len(sched):
+            d.sweep_record(len(sched), track_best=True, beta_sched=sched[:, None], want_states=False, want_energies=False)
+    else:
+        for b in sched:
+            d.set_betas([max(float(b), 1e-12)])
+            d.sweep(1)
+            d.best_update(fetch=False)
+        d.set_betas([float(global_beta)])
     m_star, E_star = d.best_get()
     if obj.verbose:
         print(f'\ninitial m_star energy = {E_star[0]:.8f}')
@@ -268,7 +300,7 @@ class _IcmEngine:
         if self.msc:
             self.eng = _lib.Msc(prob.inst, betas, S, seed)
         else:
-            self.eng = _lib.Dense(prob.inst, np.repeat(betas, S), n_split=3, seed=seed)
+            self.eng = _generic_engine(prob, np.repeat(betas, S), seed)
 
     def sweep(self, k):
         self.eng.sweep(k)
