@@ -7,14 +7,17 @@
 // parallel (the conditional distribution of each is untouched by the others) and the colours are visited in
 // order -- a valid Gibbs sweep with the same single-site rule as the reference:
 //     s_i <- +1 with probability 1/(1 + exp(-2 beta f_i)),  f_i = sum_j J_ij s_j + h_i   (== nmc.py:86-87)
-// Per replica everything lives in shared memory: spins (int8), the local fields f_i (double, maintained
-// INCREMENTALLY: a flip adds 2 J_ij s_i to its neighbours' fields with shared-memory atomics), the NMC phase
-// modes, and the CSR itself when it fits (uint16/int32 columns, fp32 values).  A whole batch of sweeps is one
-// launch: per-sweep energies E = -1/2 sum_i s_i (f_i + h_i) (block reduction, exact for integer J), optional
-// recording of every k-th state (the reference's M[:, ::M_skip]) and tracking of the lowest-energy state
-// (m_init = M[:, argmin E], nmc.py:394-395) all happen inside the kernel.  Fields are recomputed from the spins
-// every kRefresh sweeps so that rounding cannot accumulate.  Random numbers: Philox4x32-10 keyed by
-// (seed; global replica id, site, sweep).
+// Per replica everything lives in shared memory: spins (int8), the local fields f_i, the NMC phase modes, and the
+// CSR itself when it fits (uint16/int32 columns, int32 values).  Fields are INT32 FIXED POINT (scale 2^s with s
+// chosen so that max_i(|h_i| + sum_j |J_ij|) * 2^s < 2^30) and are maintained INCREMENTALLY: a flip adds
+// 2 J_ij s_i to its neighbours' fields with ATOMS.ADD -- the only shared-memory atomic add the hardware has
+// natively (fp64, u64 and fp32 adds compile to CAS spin loops; checked in SASS).  Integer arithmetic means no
+// drift and, for integer J, exact fields and energies.  Each site is served by a group of lanes (a power of two,
+// chosen so that one colour fills the CTA): every lane of the group takes the same decision and the lanes split
+// the neighbour list of a flip.  A whole batch of sweeps is one launch: per-sweep energies
+// E = -1/2 sum_i s_i (f_i + h_i), optional recording of every k-th state (the reference's M[:, ::M_skip]) and
+// tracking of the lowest-energy state (m_init = M[:, argmin E], nmc.py:394-395) all happen inside the kernel.
+// Random numbers: Philox4x32-10 keyed by (seed; global replica id, site, sweep).
 #include <algorithm>
 #include <cmath>
 
@@ -27,7 +30,8 @@ struct nlmc_col {
     int32_t *site_order = nullptr;  // [n] sites sorted by colour
     int32_t *colour_ptr = nullptr;  // [n_colours+1]
     uint16_t *col16 = nullptr;      // [nnz] (when n <= 65535)
-    float *val32 = nullptr;         // [nnz]
+    int32_t *valfx = nullptr;       // [nnz] J in fixed point (scale 2^fx_shift)
+    int fx_shift = 0, group = 1;    // fixed-point shift; lanes per site
     int8_t *spins = nullptr;        // [R][n]
     double *beta = nullptr;         // [R]
     uint8_t *modes = nullptr;       // [R][n] 0 normal, 1 hot (beta/temp_x), 2 frozen
@@ -44,7 +48,6 @@ struct nlmc_col {
 namespace nlmc {
 
 constexpr int kColThreads = 256;
-constexpr int kRefresh = 128;
 
 struct PhiloxC {
     uint32_t k0, k1;
@@ -64,11 +67,12 @@ struct PhiloxC {
 };
 
 struct ColArgs {
-    int n, nnz, n_colours, n_sweeps, record_every, replica_offset;
+    int n, nnz, n_colours, n_sweeps, record_every, replica_offset, group;
+    double scale;  // 2^fx_shift
     const int32_t *rp, *ci;
     const double *val, *h;
     const uint16_t *col16;
-    const float *val32;
+    const int32_t *valfx;
     const int32_t *site_order, *colour_ptr;
     int8_t *spins;
     const double *beta;
@@ -86,12 +90,13 @@ struct ColArgs {
 template <bool kSmemCsr, typename ColT>
 __global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
     extern __shared__ __align__(16) uint8_t sm[];
-    __shared__ double red[kColThreads / 32];
+    __shared__ long long red[kColThreads / 32];
     __shared__ double s_E;
     const int n = a.n, tid = threadIdx.x, r = blockIdx.x;
-    double *fld = reinterpret_cast<double *>(sm);
-    int32_t *rp_s = reinterpret_cast<int32_t *>(fld + n);
-    float *val_s = reinterpret_cast<float *>(rp_s + (kSmemCsr ? n + 1 : 0));
+    int32_t *fld = reinterpret_cast<int32_t *>(sm);                    // [n] fixed-point local fields (incl. h)
+    int32_t *hfx = fld + n;                                            // [n] fixed-point h
+    int32_t *rp_s = hfx + n;
+    int32_t *val_s = rp_s + (kSmemCsr ? n + 1 : 0);
     ColT *col_s = reinterpret_cast<ColT *>(val_s + (kSmemCsr ? a.nnz : 0));
     int8_t *spin = reinterpret_cast<int8_t *>(col_s + (kSmemCsr ? a.nnz + (a.nnz & 1) : 0));
     uint8_t *mode = reinterpret_cast<uint8_t *>(spin + n);
@@ -101,74 +106,73 @@ __global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
     if (kSmemCsr) {
         for (int i = tid; i <= n; i += kColThreads) rp_s[i] = a.rp[i];
         for (int p = tid; p < a.nnz; p += kColThreads) {
-            val_s[p] = a.val32[p];
+            val_s[p] = a.valfx[p];
             col_s[p] = sizeof(ColT) == 2 ? (ColT)a.col16[p] : (ColT)a.ci[p];
         }
     }
     for (int i = tid; i < n; i += kColThreads) {
         spin[i] = g_spin[i];
         mode[i] = g_mode ? g_mode[i] : 0;
+        hfx[i] = __double2int_rn(a.h[i] * a.scale);
     }
     __syncthreads();
     auto row_begin = [&](int i) { return kSmemCsr ? rp_s[i] : a.rp[i]; };
     auto col_of = [&](int p) -> int { return kSmemCsr ? (int)col_s[p] : a.ci[p]; };
-    auto val_of = [&](int p) -> double { return kSmemCsr ? (double)val_s[p] : a.val[p]; };
-    auto refresh_fields = [&]() {
-        for (int i = tid; i < n; i += kColThreads) {
-            double f = a.h[i];
-            const int e = row_begin(i + 1);
-            for (int p = row_begin(i); p < e; ++p) f += val_of(p) * (double)spin[col_of(p)];
-            fld[i] = f;
-        }
-        __syncthreads();
-    };
-    refresh_fields();
+    auto val_of = [&](int p) -> int { return kSmemCsr ? val_s[p] : a.valfx[p]; };
+    for (int i = tid; i < n; i += kColThreads) {  // initial fields, exact integer arithmetic
+        int f = hfx[i];
+        const int e = row_begin(i + 1);
+        for (int p = row_begin(i); p < e; ++p) f += val_of(p) * (int)spin[col_of(p)];
+        fld[i] = f;
+    }
+    __syncthreads();
 
-    double beta = a.beta[r];
-    double beta_hot = beta / a.temp_x;
+    const float inv_scale = (float)(1.0 / a.scale);
+    float m2b = -2.0f * (float)a.beta[r];
+    const float inv_tx = (float)(1.0 / a.temp_x);
     const PhiloxC rng{a.seed_lo, a.seed_hi ^ 0x434f4c52u};
     const uint32_t rid = (uint32_t)(a.replica_offset + r);
+    const int G = a.group, gl = tid & (G - 1), sites_per_pass = kColThreads / G;
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((tid & 31) & ~(G - 1));
     double best = a.bestE ? a.bestE[r] : 0.0;
     int n_rec = 0;
     for (int s = 0; s < a.n_sweeps; ++s) {
         const uint32_t sweep = a.sweep0 + (uint32_t)s;
-        if (a.beta_sched) {
-            beta = a.beta_sched[(size_t)s * a.R + r];
-            beta_hot = beta / a.temp_x;
-        }
+        if (a.beta_sched) m2b = -2.0f * (float)a.beta_sched[(size_t)s * a.R + r];
         for (int c = 0; c < a.n_colours; ++c) {
             const int cb = a.colour_ptr[c], ce = a.colour_ptr[c + 1];
-            for (int idx = cb + tid; idx < ce; idx += kColThreads) {
+            for (int idx = cb + tid / G; idx < ce; idx += sites_per_pass) {
                 const int i = a.site_order[idx];
                 const int md = mode[i];
                 if (md == 2) continue;  // frozen (the reference pins these spins with h = +-1e4, nmc.py:381,400)
-                const double b = md == 1 ? beta_hot : beta;  // backbone rows of J, h divided by temp_x (nmc.py:379-380)
+                // backbone rows of J and h are divided by temp_x (nmc.py:379-380) <=> beta/temp_x for this site
+                const float x = (md == 1 ? m2b * inv_tx : m2b) * ((float)fld[i] * inv_scale);
                 const uint4 rnd = rng(rid, (uint32_t)i, sweep, 0u);
-                const double u = ((double)rnd.x * 4294967296.0 + (double)rnd.y + 0.5) * (1.0 / 18446744073709551616.0);
-                const double p_up = 1.0 / (1.0 + exp(-2.0 * b * fld[i]));
-                const int s_new = u < p_up ? 1 : -1;
+                const float u = ((float)(rnd.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                const int s_new = u * (1.0f + __expf(x)) < 1.0f ? 1 : -1;   // u < 1/(1+exp(-2 beta f))
                 const int s_old = spin[i];
+                __syncwarp(gmask);  // every lane of the group has read spin[i] and fld[i]
                 if (s_new != s_old) {
-                    spin[i] = (int8_t)s_new;
-                    const double d = (double)(s_new - s_old);
+                    if (gl == 0) spin[i] = (int8_t)s_new;
+                    const int d = s_new - s_old;
                     const int e = row_begin(i + 1);
-                    for (int p = row_begin(i); p < e; ++p) atomicAdd(&fld[col_of(p)], val_of(p) * d);
+                    for (int p = row_begin(i) + gl; p < e; p += G) atomicAdd(&fld[col_of(p)], val_of(p) * d);
                 }
             }
             __syncthreads();
         }
-        if ((s + 1) % kRefresh == 0) refresh_fields();
         const bool want_E = a.out_E != nullptr || a.bestE != nullptr;
-        if (want_E) {  // E = -(m^T J m / 2 + m^T h) = -1/2 sum_i s_i (f_i + h_i)
-            double part = 0.0;
-            for (int i = tid; i < n; i += kColThreads) part += (double)spin[i] * (fld[i] + a.h[i]);
-            part = warp_sum(part);
+        if (want_E) {  // E = -(m^T J m / 2 + m^T h) = -1/2 sum_i s_i (f_i + h_i), exact in fixed point
+            long long part = 0;
+            for (int i = tid; i < n; i += kColThreads) part += (long long)spin[i] * ((long long)fld[i] + (long long)hfx[i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             if ((tid & 31) == 0) red[tid >> 5] = part;
             __syncthreads();
-            if (tid < 32) {
-                double v = tid < kColThreads / 32 ? red[tid] : 0.0;
-                v = warp_sum(v);
-                if (tid == 0) s_E = -0.5 * v;
+            if (tid == 0) {
+                long long v = 0;
+                for (int w = 0; w < kColThreads / 32; ++w) v += red[w];
+                s_E = -0.5 * (double)v / a.scale;
             }
             __syncthreads();
             const double E = s_E;
@@ -231,7 +235,7 @@ extern "C" {
 int nlmc_col_destroy(nlmc_col *Cc) {
     if (!Cc) return NLMC_OK;
     cudaSetDevice(Cc->inst->device);
-    void *ptrs[] = {Cc->site_order, Cc->colour_ptr, Cc->col16, Cc->val32, Cc->spins, Cc->beta, Cc->modes, Cc->bestE, Cc->bestS};
+    void *ptrs[] = {Cc->site_order, Cc->colour_ptr, Cc->col16, Cc->valfx, Cc->spins, Cc->beta, Cc->modes, Cc->bestE, Cc->bestS};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (Cc->stream) cudaStreamDestroy(Cc->stream);
     delete Cc;
@@ -287,8 +291,20 @@ int nlmc_col_create(nlmc_instance *I, int n_replicas, const double *betas, int r
     Cc->replica_offset = replica_offset;
     Cc->seed = seed;
     Cc->small_cols = n <= 65535;
-    const size_t base = sizeof(double) * (size_t)n + 2 * (size_t)n + 64;
-    const size_t with_csr = base + sizeof(int32_t) * (size_t)(n + 1) + sizeof(float) * (size_t)nnz +
+    // fixed-point scale: the largest |field| (sum_j |J_ij| + |h_i|) must stay below 2^30
+    double max_row = 1e-300;
+    int max_colour = 1;
+    for (int c = 0; c < n_colours; ++c) max_colour = std::max(max_colour, (int)(cptr[(size_t)c + 1] - cptr[(size_t)c]));
+    for (int i = 0; i < n; ++i) {
+        double srow = std::fabs(I->h_h[(size_t)i]);
+        for (int p = I->h_row_ptr[i]; p < I->h_row_ptr[i + 1]; ++p) srow += std::fabs(I->h_val[(size_t)p]);
+        max_row = std::max(max_row, srow);
+    }
+    Cc->fx_shift = std::max(0, std::min(30, (int)std::floor(std::log2(1073741824.0 / max_row))));
+    Cc->group = 1;
+    while (Cc->group < 32 && Cc->group * 2 * max_colour <= kColThreads) Cc->group *= 2;
+    const size_t base = 2 * sizeof(int32_t) * (size_t)n + 2 * (size_t)n + 64;
+    const size_t with_csr = base + sizeof(int32_t) * (size_t)(n + 1) + sizeof(int32_t) * (size_t)nnz +
                             (Cc->small_cols ? 2 : 4) * ((size_t)nnz + ((size_t)nnz & 1));
     Cc->csr_in_smem = with_csr <= 220 * 1024;
     Cc->smem_bytes = Cc->csr_in_smem ? with_csr : base;
@@ -297,21 +313,25 @@ int nlmc_col_create(nlmc_instance *I, int n_replicas, const double *betas, int r
         delete Cc;
         return NLMC_ERR_UNSUPPORTED;
     }
-    std::vector<float> v32((size_t)std::max(nnz, 1));
+    std::vector<int32_t> v32((size_t)std::max(nnz, 1));
     std::vector<uint16_t> c16((size_t)std::max(nnz, 1));
-    for (int p = 0; p < nnz; ++p) { v32[(size_t)p] = (float)I->h_val[(size_t)p]; c16[(size_t)p] = (uint16_t)I->h_col[(size_t)p]; }
+    const double scale = std::ldexp(1.0, Cc->fx_shift);
+    for (int p = 0; p < nnz; ++p) {
+        v32[(size_t)p] = (int32_t)std::llrint(I->h_val[(size_t)p] * scale);
+        c16[(size_t)p] = (uint16_t)I->h_col[(size_t)p];
+    }
     const size_t rn = (size_t)n_replicas * n;
     bool ok = cudaStreamCreateWithFlags(&Cc->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&Cc->site_order, sizeof(int32_t) * (size_t)n) == cudaSuccess &&
               cudaMalloc(&Cc->colour_ptr, sizeof(int32_t) * cptr.size()) == cudaSuccess &&
               cudaMalloc(&Cc->col16, sizeof(uint16_t) * c16.size()) == cudaSuccess &&
-              cudaMalloc(&Cc->val32, sizeof(float) * v32.size()) == cudaSuccess &&
+              cudaMalloc(&Cc->valfx, sizeof(int32_t) * v32.size()) == cudaSuccess &&
               cudaMalloc(&Cc->spins, rn) == cudaSuccess && cudaMalloc(&Cc->beta, sizeof(double) * (size_t)n_replicas) == cudaSuccess &&
               cudaMalloc(&Cc->bestE, sizeof(double) * (size_t)n_replicas) == cudaSuccess && cudaMalloc(&Cc->bestS, rn) == cudaSuccess &&
               cudaMemcpy(Cc->site_order, order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(Cc->colour_ptr, cptr.data(), sizeof(int32_t) * cptr.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(Cc->col16, c16.data(), sizeof(uint16_t) * c16.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMemcpy(Cc->val32, v32.data(), sizeof(float) * v32.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+              cudaMemcpy(Cc->valfx, v32.data(), sizeof(int32_t) * v32.size(), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         set_error("nlmc_col_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         nlmc_col_destroy(Cc);
@@ -429,7 +449,8 @@ int nlmc_col_sweep(nlmc_col *Cc, int n_sweeps, const double *beta_sched, int rec
     ColArgs a;
     a.n = Cc->n; a.nnz = I->nnz; a.n_colours = Cc->n_colours; a.n_sweeps = n_sweeps; a.record_every = record_every;
     a.replica_offset = Cc->replica_offset;
-    a.rp = I->row_ptr; a.ci = I->col; a.val = I->val; a.h = I->h; a.col16 = Cc->col16; a.val32 = Cc->val32;
+    a.rp = I->row_ptr; a.ci = I->col; a.val = I->val; a.h = I->h; a.col16 = Cc->col16; a.valfx = Cc->valfx;
+    a.group = Cc->group; a.scale = std::ldexp(1.0, Cc->fx_shift);
     a.site_order = Cc->site_order; a.colour_ptr = Cc->colour_ptr;
     a.spins = Cc->spins; a.beta = Cc->beta; a.beta_sched = d_sched; a.modes = Cc->modes_on ? Cc->modes : nullptr; a.temp_x = Cc->temp_x;
     a.seed_lo = (uint32_t)Cc->seed; a.seed_hi = (uint32_t)(Cc->seed >> 32); a.sweep0 = Cc->sweep_counter;
