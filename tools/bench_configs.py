@@ -87,6 +87,21 @@ def c2():
     emit(config="C2", what="one swap round (1000 sweeps + energies + exchange), device only", seconds=dt,
          attempts_per_s=128 * R * n * 1000 / dt)
     msc.close()
+    # the config as BASELINE.json states it: doNMC on the 5 coldest replicas, README NMC parameters
+    nmc_kw = dict(num_cycles=10, full_update_frequency=1, M_skip=1, temp_x=20, global_beta=1 / 0.366838 * 5, lambda_start=3,
+                  lambda_end=0.01, lambda_reduction_factor=0.9, threshold_initial=0.9999999, threshold_cutoff=0.999999,
+                  max_iterations=100, tolerance=EPS)
+    doNMC = [False] * (R - 5) + [True] * 5
+    for mode, sweeps in (("production", 10000), ("replay", 300)):
+        np.random.seed(5); random.seed(5)
+        t0 = time.perf_counter()
+        M, E = NPT(A, h, mode=mode).run(betas, R, doNMC, num_sweeps_MCMC=sweeps, num_sweeps_read=100, num_swap_attempts=10,
+                                        num_swapping_pairs=round(0.3 * R), **nmc_kw)
+        dt = time.perf_counter() - t0
+        phase = int(np.ceil(sweeps / 10 / 3 / 10))
+        att = n * 10 * ((R - 5) * (sweeps // 10) + 5 * 30 * phase)
+        emit(config="C2", what=f"NPT.run {mode}, doNMC on the 5 coldest, num_sweeps_MCMC={sweeps}", seconds=dt, attempts=att,
+             attempts_per_s=att / dt, best_energy=float(E.min()))
     np.random.seed(3); random.seed(3)
     t0 = time.perf_counter()
     M, E = NPT(A, h, mode="replay").run(betas, R, [False] * R, num_sweeps_MCMC=200, num_sweeps_read=100,
