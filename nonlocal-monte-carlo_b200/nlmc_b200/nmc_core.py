@@ -27,35 +27,48 @@ def nmc_phase_count(num_cycles: int, full_update_frequency: int) -> int:
     return sum(2 + (1 if cycle % full_update_frequency == 0 else 0) for cycle in range(num_cycles))
 
 
+def _adjacency(prob):
+    """Per site the sorted distinct neighbours with a non-zero coupling (np.where(J[i, :] != 0)[0]), cached."""
+    adj = getattr(prob, "_adjacency_lists", None)
+    if adj is None:
+        adj = []
+        for i in range(prob.n):
+            b, e = prob.rp[i], prob.rp[i + 1]
+            adj.append(sorted(set(prob.ci[b:e][prob.val[b:e] != 0].tolist())))
+        try:
+            prob._adjacency_lists = adj
+        except AttributeError:
+            pass
+    return adj
+
+
 def find_clusters(prob: host.Problem, magnetizations, threshold_initial, threshold_cutoff, threshold_step):
     """Backbone seeds and growth with the semantics of find_clusters (NMC/nmc.py:257-318): seeds are the
     spins with |marginal| >= threshold_initial; a seed not yet clustered opens a cluster with its
-    unclustered seed neighbours; clusters then grow over unclustered neighbours whose |marginal| is
-    above a threshold lowered by threshold_step until it reaches threshold_cutoff."""
-    mag = np.asarray(magnetizations)
-    seeds = np.flatnonzero(np.abs(mag) >= threshold_initial)
-    is_seed = np.zeros(prob.n, dtype=bool)
-    is_seed[seeds] = True
-    clustered = np.zeros(prob.n, dtype=bool)
+    unclustered seed neighbours (in increasing index order); clusters then grow over unclustered neighbours
+    whose |marginal| is above a threshold lowered by threshold_step until it reaches threshold_cutoff."""
+    absm = np.abs(np.asarray(magnetizations, dtype=np.float64))
+    adj = _adjacency(prob)
+    is_seed = (absm >= threshold_initial).tolist()
+    clustered = [False] * prob.n
     clusters = []
-    for seed in seeds:
+    for seed in np.flatnonzero(absm >= threshold_initial).tolist():
         if clustered[seed]:
             continue
-        nb = np.unique(prob.neighbours(seed))
-        nb = nb[~clustered[nb]]
-        members = np.append(seed, nb[is_seed[nb]])
+        members = [seed] + [j for j in adj[seed] if is_seed[j] and not clustered[j]]
+        for j in members:
+            clustered[j] = True
         clusters.append(members)
-        clustered[members] = True
     current = threshold_initial - threshold_step
     while current > threshold_cutoff:
         for i, members in enumerate(clusters):
-            nb = np.unique(np.concatenate([prob.neighbours(k) for k in members])) if len(members) else np.array([], int)
-            nb = nb[~clustered[nb]]
-            grown = nb[np.abs(mag[nb]) >= current]
-            clusters[i] = np.append(members, grown)
-            clustered[grown] = True
+            cand = sorted({j for k in members for j in adj[k] if not clustered[j]})
+            grown = [j for j in cand if absm[j] >= current]
+            for j in grown:
+                clustered[j] = True
+            clusters[i] = members + grown
         current -= threshold_step
-    return clusters
+    return [np.array(c, dtype=int) for c in clusters]
 
 
 def lbp_convexified(prob: host.Problem, lbp: "_lib.Lbp", m_star, lambda_start, lambda_end, lambda_reduction_factor,
