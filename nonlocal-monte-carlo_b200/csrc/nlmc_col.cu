@@ -31,6 +31,8 @@ struct nlmc_col {
     int32_t *colour_ptr = nullptr;  // [n_colours+1]
     uint16_t *col16 = nullptr;      // [nnz] (when n <= 65535)
     int32_t *valfx = nullptr;       // [nnz] J in fixed point (scale 2^fx_shift)
+    int8_t *val8 = nullptr;         // [nnz] J itself when every value is an integer in [-127,127] (shifted at use)
+    bool int8_vals = false;
     int fx_shift = 0, group = 1;    // fixed-point shift; lanes per site
     int8_t *spins = nullptr;        // [R][n]
     double *beta = nullptr;         // [R]
@@ -41,7 +43,8 @@ struct nlmc_col {
     int8_t *bestS = nullptr;        // [R][n]
     uint32_t sweep_counter = 0;
     unsigned long long seed = 0;
-    size_t smem_bytes = 0;
+    size_t smem_bytes = 0, smem_bytes_nocsr = 0;
+    int sm_count = 148;
     cudaStream_t stream = nullptr;
 };
 
@@ -73,6 +76,8 @@ struct ColArgs {
     const double *val, *h;
     const uint16_t *col16;
     const int32_t *valfx;
+    const int8_t *val8;
+    int shift;
     const int32_t *site_order, *colour_ptr;
     int8_t *spins;
     const double *beta;
@@ -87,8 +92,9 @@ struct ColArgs {
     int R;
 };
 
-template <bool kSmemCsr, typename ColT>
+template <bool kSmemCsr, typename ColT, typename ValT>
 __global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
+    constexpr bool kVal8 = sizeof(ValT) == 1;  // integer couplings stored as int8 and shifted into fixed point at use
     extern __shared__ __align__(16) uint8_t sm[];
     __shared__ long long red[kColThreads / 32];
     __shared__ double s_E;
@@ -96,9 +102,9 @@ __global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
     int32_t *fld = reinterpret_cast<int32_t *>(sm);                    // [n] fixed-point local fields (incl. h)
     int32_t *hfx = fld + n;                                            // [n] fixed-point h
     int32_t *rp_s = hfx + n;
-    int32_t *val_s = rp_s + (kSmemCsr ? n + 1 : 0);
-    ColT *col_s = reinterpret_cast<ColT *>(val_s + (kSmemCsr ? a.nnz : 0));
-    int8_t *spin = reinterpret_cast<int8_t *>(col_s + (kSmemCsr ? a.nnz + (a.nnz & 1) : 0));
+    ColT *col_s = reinterpret_cast<ColT *>(rp_s + (kSmemCsr ? n + 1 : 0));
+    ValT *val_s = reinterpret_cast<ValT *>(col_s + (kSmemCsr ? a.nnz + (a.nnz & 1) : 0));
+    int8_t *spin = reinterpret_cast<int8_t *>(val_s + (kSmemCsr ? a.nnz + ((4 - (a.nnz & 3)) & 3) : 0));
     uint8_t *mode = reinterpret_cast<uint8_t *>(spin + n);
 
     int8_t *g_spin = a.spins + (size_t)r * n;
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
     if (kSmemCsr) {
         for (int i = tid; i <= n; i += kColThreads) rp_s[i] = a.rp[i];
         for (int p = tid; p < a.nnz; p += kColThreads) {
-            val_s[p] = a.valfx[p];
+            val_s[p] = kVal8 ? (ValT)a.val8[p] : (ValT)a.valfx[p];
             col_s[p] = sizeof(ColT) == 2 ? (ColT)a.col16[p] : (ColT)a.ci[p];
         }
     }
@@ -118,7 +124,10 @@ __global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
     __syncthreads();
     auto row_begin = [&](int i) { return kSmemCsr ? rp_s[i] : a.rp[i]; };
     auto col_of = [&](int p) -> int { return kSmemCsr ? (int)col_s[p] : a.ci[p]; };
-    auto val_of = [&](int p) -> int { return kSmemCsr ? val_s[p] : a.valfx[p]; };
+    auto val_of = [&](int p) -> int {
+        if (kVal8) return (int)(kSmemCsr ? (int)val_s[p] : (int)a.val8[p]) << a.shift;
+        return kSmemCsr ? (int)val_s[p] : a.valfx[p];
+    };
     for (int i = tid; i < n; i += kColThreads) {  // initial fields, exact integer arithmetic
         int f = hfx[i];
         const int e = row_begin(i + 1);
@@ -235,7 +244,7 @@ extern "C" {
 int nlmc_col_destroy(nlmc_col *Cc) {
     if (!Cc) return NLMC_OK;
     cudaSetDevice(Cc->inst->device);
-    void *ptrs[] = {Cc->site_order, Cc->colour_ptr, Cc->col16, Cc->valfx, Cc->spins, Cc->beta, Cc->modes, Cc->bestE, Cc->bestS};
+    void *ptrs[] = {Cc->site_order, Cc->colour_ptr, Cc->col16, Cc->valfx, Cc->val8, Cc->spins, Cc->beta, Cc->modes, Cc->bestE, Cc->bestS};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (Cc->stream) cudaStreamDestroy(Cc->stream);
     delete Cc;
@@ -304,10 +313,21 @@ int nlmc_col_create(nlmc_instance *I, int n_replicas, const double *betas, int r
     Cc->group = 1;
     while (Cc->group < 32 && Cc->group * 2 * max_colour <= kColThreads) Cc->group *= 2;
     const size_t base = 2 * sizeof(int32_t) * (size_t)n + 2 * (size_t)n + 64;
-    const size_t with_csr = base + sizeof(int32_t) * (size_t)(n + 1) + sizeof(int32_t) * (size_t)nnz +
+    bool all_small_int = nnz > 0;
+    for (int p = 0; p < nnz && all_small_int; ++p) {
+        const double v = I->h_val[(size_t)p];
+        all_small_int = v == std::floor(v) && std::fabs(v) <= 127.0;
+    }
+    Cc->int8_vals = all_small_int;
+    const size_t with_csr = base + sizeof(int32_t) * (size_t)(n + 1) + (all_small_int ? 1 : 4) * ((size_t)nnz + 4) +
                             (Cc->small_cols ? 2 : 4) * ((size_t)nnz + ((size_t)nnz & 1));
-    Cc->csr_in_smem = with_csr <= 220 * 1024;
+    // CSR in shared memory only when it fits AND the replicas are few: with many replicas the small footprint of
+    // the L2-resident variant (8 CTAs per SM instead of 1) hides latency better (measured on the C1 graph:
+    // 27 vs 41 us per sweep for one replica, but 9e9 vs 2.1e10 attempts/s for 1184 replicas)
+    cudaDeviceGetAttribute(&Cc->sm_count, cudaDevAttrMultiProcessorCount, I->device);
+    Cc->csr_in_smem = with_csr <= 220 * 1024 && n_replicas <= 2 * Cc->sm_count;
     Cc->smem_bytes = Cc->csr_in_smem ? with_csr : base;
+    Cc->smem_bytes_nocsr = base;
     if (Cc->smem_bytes > 220 * 1024) {
         set_error("nlmc_col_create: %d spins do not fit in shared memory (one CTA per replica)", n);
         delete Cc;
@@ -315,8 +335,10 @@ int nlmc_col_create(nlmc_instance *I, int n_replicas, const double *betas, int r
     }
     std::vector<int32_t> v32((size_t)std::max(nnz, 1));
     std::vector<uint16_t> c16((size_t)std::max(nnz, 1));
+    std::vector<int8_t> v8((size_t)std::max(nnz, 1));
     const double scale = std::ldexp(1.0, Cc->fx_shift);
     for (int p = 0; p < nnz; ++p) {
+        if (Cc->int8_vals) v8[(size_t)p] = (int8_t)I->h_val[(size_t)p];
         v32[(size_t)p] = (int32_t)std::llrint(I->h_val[(size_t)p] * scale);
         c16[(size_t)p] = (uint16_t)I->h_col[(size_t)p];
     }
@@ -326,6 +348,8 @@ int nlmc_col_create(nlmc_instance *I, int n_replicas, const double *betas, int r
               cudaMalloc(&Cc->colour_ptr, sizeof(int32_t) * cptr.size()) == cudaSuccess &&
               cudaMalloc(&Cc->col16, sizeof(uint16_t) * c16.size()) == cudaSuccess &&
               cudaMalloc(&Cc->valfx, sizeof(int32_t) * v32.size()) == cudaSuccess &&
+              cudaMalloc(&Cc->val8, v8.size()) == cudaSuccess &&
+              cudaMemcpy(Cc->val8, v8.data(), v8.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMalloc(&Cc->spins, rn) == cudaSuccess && cudaMalloc(&Cc->beta, sizeof(double) * (size_t)n_replicas) == cudaSuccess &&
               cudaMalloc(&Cc->bestE, sizeof(double) * (size_t)n_replicas) == cudaSuccess && cudaMalloc(&Cc->bestS, rn) == cudaSuccess &&
               cudaMemcpy(Cc->site_order, order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess &&
@@ -450,23 +474,26 @@ int nlmc_col_sweep(nlmc_col *Cc, int n_sweeps, const double *beta_sched, int rec
     a.n = Cc->n; a.nnz = I->nnz; a.n_colours = Cc->n_colours; a.n_sweeps = n_sweeps; a.record_every = record_every;
     a.replica_offset = Cc->replica_offset;
     a.rp = I->row_ptr; a.ci = I->col; a.val = I->val; a.h = I->h; a.col16 = Cc->col16; a.valfx = Cc->valfx;
-    a.group = Cc->group; a.scale = std::ldexp(1.0, Cc->fx_shift);
+    a.group = Cc->group; a.scale = std::ldexp(1.0, Cc->fx_shift); a.val8 = Cc->val8; a.shift = Cc->fx_shift;
     a.site_order = Cc->site_order; a.colour_ptr = Cc->colour_ptr;
     a.spins = Cc->spins; a.beta = Cc->beta; a.beta_sched = d_sched; a.modes = Cc->modes_on ? Cc->modes : nullptr; a.temp_x = Cc->temp_x;
     a.seed_lo = (uint32_t)Cc->seed; a.seed_hi = (uint32_t)(Cc->seed >> 32); a.sweep0 = Cc->sweep_counter;
     a.out_spins = d_rec; a.out_E = d_E; a.bestE = track_best ? Cc->bestE : nullptr; a.bestS = Cc->bestS; a.R = Cc->R;
     cudaError_t e = cudaSuccess;
     const int smem = (int)Cc->smem_bytes;
+#define NLMC_COL_LAUNCH(SMEM, COLT, VALT)                                                                              \
+    do {                                                                                                              \
+        e = cudaFuncSetAttribute(col_sweep_kernel<SMEM, COLT, VALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e == cudaSuccess) col_sweep_kernel<SMEM, COLT, VALT><<<(unsigned)R, kColThreads, smem, Cc->stream>>>(a);  \
+    } while (0)
     if (Cc->csr_in_smem && Cc->small_cols) {
-        e = cudaFuncSetAttribute(col_sweep_kernel<true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) col_sweep_kernel<true, uint16_t><<<(unsigned)R, kColThreads, smem, Cc->stream>>>(a);
+        if (Cc->int8_vals) NLMC_COL_LAUNCH(true, uint16_t, int8_t); else NLMC_COL_LAUNCH(true, uint16_t, int32_t);
     } else if (Cc->csr_in_smem) {
-        e = cudaFuncSetAttribute(col_sweep_kernel<true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) col_sweep_kernel<true, int32_t><<<(unsigned)R, kColThreads, smem, Cc->stream>>>(a);
+        if (Cc->int8_vals) NLMC_COL_LAUNCH(true, int32_t, int8_t); else NLMC_COL_LAUNCH(true, int32_t, int32_t);
     } else {
-        e = cudaFuncSetAttribute(col_sweep_kernel<false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) col_sweep_kernel<false, int32_t><<<(unsigned)R, kColThreads, smem, Cc->stream>>>(a);
+        if (Cc->int8_vals) NLMC_COL_LAUNCH(false, int32_t, int8_t); else NLMC_COL_LAUNCH(false, int32_t, int32_t);
     }
+#undef NLMC_COL_LAUNCH
     if (e == cudaSuccess) e = cudaGetLastError();
     Cc->sweep_counter += (uint32_t)n_sweeps;
     if (e == cudaSuccess && d_rec) e = cudaMemcpyAsync(out_spins, d_rec, n_rec * R * n, cudaMemcpyDeviceToHost, Cc->stream);

@@ -132,12 +132,20 @@ def test_statistical_equivalence_with_reference_sampler_c1_shape(nl):
 
 
 def test_large_sparse_instance_csr_in_global(nl):
-    """An instance whose CSR does not fit in shared memory still runs (CSR read from global memory)."""
+    """An instance whose CSR does not fit in shared memory still runs (CSR read from global memory), and the two
+    CSR placements give identical trajectories."""
     from oracle import oracle as O
-    A, h = O.ea3d_pm_j(20, 3)  # 8000 spins, 48000 entries -> CSR stays in global memory
+    A, h = O.ea3d_pm_j(28, 3)  # 21952 spins, 131712 entries -> CSR stays in global memory
     prob = nl.host.Problem(A, h)
     c = nl.lib.Col(prob.inst, [0.5, 1.5], seed=1)
     assert c.n_colours == 2 and not c.csr_in_smem
+    Jg, hg = O.random_pm_graph(120, 0.1, 4)
+    pg = nl.host.Problem(Jg, hg)
+    few = nl.lib.Col(pg.inst, np.full(4, 0.7), seed=9)                 # CSR in shared memory
+    many = nl.lib.Col(pg.inst, np.full(400, 0.7), seed=9)              # CSR in L2 (many replicas)
+    assert few.csr_in_smem and not many.csr_in_smem
+    few.sweep(25); many.sweep(25)
+    assert np.array_equal(few.get_spins(), many.get_spins()[:4])
     _, E = c.sweep_record(5, want_states=False)
     assert np.array_equal(O.energy(O.Csr(A), h, c.get_spins()), E[-1])
     assert E[-1, 1] < E[-1, 0] < 0
