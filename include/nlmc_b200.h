@@ -107,7 +107,16 @@ int nlmc_energy_states(nlmc_instance *inst, int n_states, const int8_t *states /
  *   nlmc_lbp_epsilon epsilon_i = |h_i| + sum_j |J_ij|                      (nmc.py:353)
  *   nlmc_lbp_step    one LoopyBeliefPropagation call with h + lambda*m_star*epsilon (nmc.py:133-139);
  *                    out_marginal[n] = tanh(beta*(h_lambda + sum_k u[k,i])) (nmc.py:216),
- *                    *out_iteration = the reference's `iteration` on exit (max_iter-1 <=> "diverged") */
+ *                    *out_iteration = the reference's `iteration` on exit (max_iter-1 <=> "diverged")
+ *   nlmc_lbp_run     the same call with a caller-supplied field h[n] (the public method
+ *                    LoopyBeliefPropagation(J, h, beta, h_msgs, u_msgs, tolerance, max_iterations), nmc.py:168)
+ *   nlmc_lbp_set_messages / nlmc_lbp_get_messages
+ *                    h_msgs / u_msgs on the stored entries of J (CSR entry order) plus tot[i], the common value
+ *                    of row i of h_msgs off the stored entries (the reference's dense matrices are exactly this:
+ *                    u_msgs = 0 and h_msgs[i,j] = tot[i] off the entries, h_msgs[i,i] = 0)
+ *   nlmc_lbp_byproducts
+ *                    correlations, h_tilde, J_tilde of the last call (nmc.py:217-226); dense [n][n] row-major like
+ *                    the reference's return values; any pointer may be NULL */
 typedef struct nlmc_lbp nlmc_lbp;
 int nlmc_lbp_create(nlmc_instance *inst, nlmc_lbp **out);
 int nlmc_lbp_destroy(nlmc_lbp *lbp);
@@ -115,6 +124,14 @@ int nlmc_lbp_epsilon(nlmc_lbp *lbp, double *out_eps /*[n]*/);
 int nlmc_lbp_reset(nlmc_lbp *lbp, const double *m_star /*[n]*/);
 int nlmc_lbp_step(nlmc_lbp *lbp, double lambda, double beta, double tol, int max_iter,
                   double *out_marginal /*[n] or NULL*/, int *out_iteration);
+int nlmc_lbp_run(nlmc_lbp *lbp, const double *h_field /*[n]*/, double beta, double tol, int max_iter,
+                 double *out_marginal /*[n] or NULL*/, int *out_iteration);
+int nlmc_lbp_set_messages(nlmc_lbp *lbp, const double *h_edge /*[nnz]*/, const double *u_edge /*[nnz]*/,
+                          const double *tot /*[n]*/);
+int nlmc_lbp_get_messages(nlmc_lbp *lbp, double *out_h_edge /*[nnz] or NULL*/, double *out_u_edge /*[nnz] or NULL*/,
+                          double *out_tot /*[n] or NULL*/);
+int nlmc_lbp_byproducts(nlmc_lbp *lbp, double beta, double *out_corr /*[n*n] or NULL*/,
+                        double *out_h_tilde /*[n] or NULL*/, double *out_J_tilde /*[n*n] or NULL*/);
 
 /* ---- K7 icm_components -- Houdayer iso-cluster identification ---------------------------------
  * Replaces find_disagreement_clusters (NPT/apt_ICM.py:116-143) for n_pairs pairs of states at once:

@@ -32,6 +32,9 @@ struct nlmc_lbp {
     double *eps = nullptr;      // [n]   |h_i| + sum_j |J_ij|   (nmc.py:353)
     double *mstar = nullptr;    // [n]
     double *marg = nullptr;     // [n]
+    double *hfield = nullptr;   // [n]   caller-supplied field of nlmc_lbp_run
+    double *dense[2] = {nullptr, nullptr};  // [n*n] correlations / J_tilde of nlmc_lbp_byproducts (on demand)
+    double *htilde = nullptr;   // [n]
     uint8_t *offedge = nullptr; // [n]   row has an off-diagonal zero
     unsigned long long *red = nullptr;  // [4] du, su, dh, sh as ordered bit patterns
     int *iter_out = nullptr;
@@ -131,6 +134,7 @@ struct LbpArgs {
     double beta, lambda, tol;
     const int32_t *rp, *ci, *rev;
     const double *val, *h, *eps, *mstar;
+    const double *h_field;  // non-NULL: use this field instead of h + lambda*m_star*eps (nlmc_lbp_run)
     double *u0, *u1, *hm, *tot, *marg;
     const uint8_t *offedge;
     unsigned long long *red;
@@ -153,7 +157,8 @@ __global__ void __launch_bounds__(256) lbp_kernel(LbpArgs a) {
         double dh = 0.0, sh = 0.0;
         for (int i = tid; i < a.n; i += nthreads) {
             const int b = a.rp[i], cnt = a.rp[i + 1] - b;
-            const double hl = __dadd_rn(a.h[i], __dmul_rn(__dmul_rn(a.lambda, a.mstar[i]), a.eps[i]));  // nmc.py:133-134
+            const double hl = a.h_field ? a.h_field[i]
+                                        : __dadd_rn(a.h[i], __dmul_rn(__dmul_rn(a.lambda, a.mstar[i]), a.eps[i]));  // nmc.py:133-134
             const double total = __dadd_rn(hl, pairwise_sparse(a.n, a.ci + b, cnt,
                                                              [&](int q) { return u_old[a.rev[b + q]]; }));
             for (int q = 0; q < cnt; ++q) {
@@ -198,7 +203,8 @@ __global__ void __launch_bounds__(256) lbp_kernel(LbpArgs a) {
     if (!converged) iteration = a.max_iter - 1;  // python loop variable after exhaustion
     // marginal_i = tanh(beta * (hl_i + sum_k u[k,i])), rows accumulated in order   (nmc.py:216)
     for (int i = tid; i < a.n; i += nthreads) {
-        const double hl = __dadd_rn(a.h[i], __dmul_rn(__dmul_rn(a.lambda, a.mstar[i]), a.eps[i]));
+        const double hl = a.h_field ? a.h_field[i]
+                                    : __dadd_rn(a.h[i], __dmul_rn(__dmul_rn(a.lambda, a.mstar[i]), a.eps[i]));
         double acc = 0.0;
         for (int p = a.rp[i]; p < a.rp[i + 1]; ++p) acc = __dadd_rn(acc, u_old[a.rev[p]]);
         a.marg[i] = tanh(__dmul_rn(a.beta, __dadd_rn(hl, acc)));
@@ -227,6 +233,47 @@ __global__ void lbp_eps_kernel(int n, const int32_t *rp, const int32_t *ci, cons
     offedge[i] = stored_off < n - 1;
 }
 
+// By-products of one LBP call (nmc.py:217-226), dense like the reference's.  Off the stored entries of J
+// tanh(beta*J) = 0 and h_msgs[i,j] = tot[i], so correlations[i,j] = tanh(beta tot_i) tanh(beta tot_j) / (1 + 1e-10);
+// the diagonal is removed (nmc.py:221).  Stored entries are overwritten by lbp_byproducts_edges_kernel.
+__global__ void lbp_byproducts_fill_kernel(int n, double beta, const double *tot, double *corr, double *jt) {
+    const int j = blockIdx.y * blockDim.x + threadIdx.x, i = blockIdx.x;
+    if (j >= n) return;
+    const double inv_beta = __ddiv_rn(1.0, beta);
+    double c = 0.0;
+    if (i != j) {
+        const double ti = tanh(__dmul_rn(beta, tot[i])), tj = tanh(__dmul_rn(beta, tot[j]));
+        c = __ddiv_rn(__dmul_rn(ti, tj), __dadd_rn(1.0, 1e-10));
+    }
+    if (corr) corr[(size_t)i * n + j] = c;
+    if (jt) jt[(size_t)i * n + j] = __dmul_rn(inv_beta, atanh_saturated(c));
+}
+
+__global__ void lbp_byproducts_edges_kernel(int n, int nnz, double beta, const int32_t *rp, const int32_t *ci,
+                                            const int32_t *rev, const double *val, const double *hm, double *corr,
+                                            double *jt) {
+    const int i = blockIdx.x;
+    const double inv_beta = __ddiv_rn(1.0, beta);
+    for (int p = rp[i] + threadIdx.x; p < rp[i + 1]; p += blockDim.x) {
+        const int j = ci[p];
+        double c = 0.0;
+        if (i != j) {
+            const double tJ = tanh(__dmul_rn(beta, val[p]));
+            const double th = tanh(__dmul_rn(beta, hm[p])), tht = tanh(__dmul_rn(beta, hm[rev[p]]));
+            const double num = __dadd_rn(tJ, __dmul_rn(th, tht));
+            const double den = __dadd_rn(__dadd_rn(1.0, __dmul_rn(__dmul_rn(tJ, th), tht)), 1e-10);
+            c = __ddiv_rn(num, den);
+        }
+        if (corr) corr[(size_t)i * n + j] = c;
+        if (jt) jt[(size_t)i * n + j] = __dmul_rn(inv_beta, atanh_saturated(c));
+    }
+}
+
+__global__ void lbp_htilde_kernel(int n, double beta, const double *marg, double *ht) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ht[i] = __dmul_rn(__ddiv_rn(1.0, beta), atanh_saturated(marg[i]));
+}
+
 }  // namespace nlmc
 
 extern "C" {
@@ -234,7 +281,8 @@ extern "C" {
 int nlmc_lbp_destroy(nlmc_lbp *L) {
     if (!L) return NLMC_OK;
     cudaSetDevice(L->inst->device);
-    void *ptrs[] = {L->rev, L->u[0], L->u[1], L->hm, L->tot, L->eps, L->mstar, L->marg, L->offedge, L->red, L->iter_out};
+    void *ptrs[] = {L->rev, L->u[0], L->u[1], L->hm, L->tot, L->eps, L->mstar, L->marg, L->offedge, L->red, L->iter_out,
+                    L->hfield, L->dense[0], L->dense[1], L->htilde};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete L;
     return NLMC_OK;
@@ -271,6 +319,8 @@ int nlmc_lbp_create(nlmc_instance *I, nlmc_lbp **out) {
               cudaMalloc(&L->eps, sizeof(double) * (size_t)n) == cudaSuccess &&
               cudaMalloc(&L->mstar, sizeof(double) * (size_t)n) == cudaSuccess &&
               cudaMalloc(&L->marg, sizeof(double) * (size_t)n) == cudaSuccess &&
+              cudaMalloc(&L->hfield, sizeof(double) * (size_t)n) == cudaSuccess &&
+              cudaMalloc(&L->htilde, sizeof(double) * (size_t)n) == cudaSuccess &&
               cudaMalloc(&L->offedge, (size_t)n) == cudaSuccess &&
               cudaMalloc(&L->red, sizeof(unsigned long long) * 4) == cudaSuccess &&
               cudaMalloc(&L->iter_out, sizeof(int) * 2) == cudaSuccess &&
@@ -320,18 +370,16 @@ int nlmc_lbp_reset(nlmc_lbp *L, const double *m_star) {
     return NLMC_OK;
 }
 
-int nlmc_lbp_step(nlmc_lbp *L, double lambda, double beta, double tol, int max_iter, double *out_marginal,
-                  int *out_iteration) {
+static int lbp_launch(nlmc_lbp *L, const double *h_field_dev, double lambda, double beta, double tol, int max_iter,
+                      double *out_marginal, int *out_iteration) {
     using namespace nlmc;
-    NLMC_REQUIRE(L && out_iteration, "nlmc_lbp_step: NULL argument");
-    NLMC_REQUIRE(max_iter >= 1, "nlmc_lbp_step: max_iterations must be >= 1");
     nlmc_instance *I = L->inst;
-    NLMC_CUDA(cudaSetDevice(I->device));
     LbpArgs a;
     a.n = I->n; a.nnz = I->nnz; a.max_iter = max_iter;
     a.beta = beta; a.lambda = lambda; a.tol = tol;
     a.rp = I->row_ptr; a.ci = I->col; a.rev = L->rev;
     a.val = I->val; a.h = I->h; a.eps = L->eps; a.mstar = L->mstar;
+    a.h_field = h_field_dev;
     a.u0 = L->u[L->cur]; a.u1 = L->u[1 - L->cur];
     a.hm = L->hm; a.tot = L->tot; a.marg = L->marg; a.offedge = L->offedge;
     a.red = L->red; a.iter_out = L->iter_out;
@@ -344,6 +392,83 @@ int nlmc_lbp_step(nlmc_lbp *L, double lambda, double beta, double tol, int max_i
     NLMC_CUDA(cudaStreamSynchronize(I->stream));
     *out_iteration = res[0];
     if (res[1] == 1) L->cur = 1 - L->cur;  // the newest messages ended up in the other buffer
+    return NLMC_OK;
+}
+
+int nlmc_lbp_step(nlmc_lbp *L, double lambda, double beta, double tol, int max_iter, double *out_marginal,
+                  int *out_iteration) {
+    NLMC_REQUIRE(L && out_iteration, "nlmc_lbp_step: NULL argument");
+    NLMC_REQUIRE(max_iter >= 1, "nlmc_lbp_step: max_iterations must be >= 1");
+    NLMC_CUDA(cudaSetDevice(L->inst->device));
+    return lbp_launch(L, nullptr, lambda, beta, tol, max_iter, out_marginal, out_iteration);
+}
+
+int nlmc_lbp_run(nlmc_lbp *L, const double *h_field, double beta, double tol, int max_iter, double *out_marginal,
+                 int *out_iteration) {
+    NLMC_REQUIRE(L && h_field && out_iteration, "nlmc_lbp_run: NULL argument");
+    NLMC_REQUIRE(max_iter >= 1, "nlmc_lbp_run: max_iterations must be >= 1");
+    nlmc_instance *I = L->inst;
+    NLMC_CUDA(cudaSetDevice(I->device));
+    NLMC_CUDA(cudaMemcpyAsync(L->hfield, h_field, sizeof(double) * (size_t)I->n, cudaMemcpyHostToDevice, I->stream));
+    return lbp_launch(L, L->hfield, 0.0, beta, tol, max_iter, out_marginal, out_iteration);
+}
+
+int nlmc_lbp_set_messages(nlmc_lbp *L, const double *h_edge, const double *u_edge, const double *tot) {
+    NLMC_REQUIRE(L && h_edge && u_edge && tot, "nlmc_lbp_set_messages: NULL argument");
+    nlmc_instance *I = L->inst;
+    NLMC_CUDA(cudaSetDevice(I->device));
+    const size_t nz = sizeof(double) * (size_t)I->nnz;
+    NLMC_CUDA(cudaMemcpyAsync(L->hm, h_edge, nz, cudaMemcpyHostToDevice, I->stream));
+    NLMC_CUDA(cudaMemcpyAsync(L->u[L->cur], u_edge, nz, cudaMemcpyHostToDevice, I->stream));
+    NLMC_CUDA(cudaMemcpyAsync(L->tot, tot, sizeof(double) * (size_t)I->n, cudaMemcpyHostToDevice, I->stream));
+    NLMC_CUDA(cudaStreamSynchronize(I->stream));
+    return NLMC_OK;
+}
+
+int nlmc_lbp_get_messages(nlmc_lbp *L, double *out_h_edge, double *out_u_edge, double *out_tot) {
+    NLMC_REQUIRE(L, "nlmc_lbp_get_messages: NULL argument");
+    nlmc_instance *I = L->inst;
+    NLMC_CUDA(cudaSetDevice(I->device));
+    const size_t nz = sizeof(double) * (size_t)I->nnz;
+    if (out_h_edge) NLMC_CUDA(cudaMemcpyAsync(out_h_edge, L->hm, nz, cudaMemcpyDeviceToHost, I->stream));
+    if (out_u_edge) NLMC_CUDA(cudaMemcpyAsync(out_u_edge, L->u[L->cur], nz, cudaMemcpyDeviceToHost, I->stream));
+    if (out_tot) NLMC_CUDA(cudaMemcpyAsync(out_tot, L->tot, sizeof(double) * (size_t)I->n, cudaMemcpyDeviceToHost, I->stream));
+    NLMC_CUDA(cudaStreamSynchronize(I->stream));
+    return NLMC_OK;
+}
+
+int nlmc_lbp_byproducts(nlmc_lbp *L, double beta, double *out_corr, double *out_h_tilde, double *out_J_tilde) {
+    using namespace nlmc;
+    NLMC_REQUIRE(L, "nlmc_lbp_byproducts: NULL argument");
+    nlmc_instance *I = L->inst;
+    const int n = I->n;
+    NLMC_CUDA(cudaSetDevice(I->device));
+    const size_t dense_bytes = sizeof(double) * (size_t)n * (size_t)n;
+    double *d_corr = nullptr, *d_jt = nullptr;
+    if (out_corr) {
+        if (!L->dense[0]) NLMC_CUDA(cudaMalloc(&L->dense[0], dense_bytes));
+        d_corr = L->dense[0];
+    }
+    if (out_J_tilde) {
+        if (!L->dense[1]) NLMC_CUDA(cudaMalloc(&L->dense[1], dense_bytes));
+        d_jt = L->dense[1];
+    }
+    if ((d_corr || d_jt) && n > 0) {
+        lbp_byproducts_fill_kernel<<<dim3((unsigned)n, (unsigned)((n + 255) / 256)), 256, 0, I->stream>>>(
+            n, beta, L->tot, d_corr, d_jt);
+        NLMC_CUDA(cudaGetLastError());
+        lbp_byproducts_edges_kernel<<<(unsigned)n, 64, 0, I->stream>>>(n, I->nnz, beta, I->row_ptr, I->col, L->rev,
+                                                                       I->val, L->hm, d_corr, d_jt);
+        NLMC_CUDA(cudaGetLastError());
+        if (out_corr) NLMC_CUDA(cudaMemcpyAsync(out_corr, d_corr, dense_bytes, cudaMemcpyDeviceToHost, I->stream));
+        if (out_J_tilde) NLMC_CUDA(cudaMemcpyAsync(out_J_tilde, d_jt, dense_bytes, cudaMemcpyDeviceToHost, I->stream));
+    }
+    if (out_h_tilde && n > 0) {
+        lbp_htilde_kernel<<<(n + 255) / 256, 256, 0, I->stream>>>(n, beta, L->marg, L->htilde);
+        NLMC_CUDA(cudaGetLastError());
+        NLMC_CUDA(cudaMemcpyAsync(out_h_tilde, L->htilde, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, I->stream));
+    }
+    NLMC_CUDA(cudaStreamSynchronize(I->stream));
     return NLMC_OK;
 }
 

@@ -52,6 +52,10 @@ _SIGNATURES = {
     "nlmc_lbp_epsilon": [_vp, _f64],
     "nlmc_lbp_reset": [_vp, _f64],
     "nlmc_lbp_step": [_vp, _dbl, _dbl, _dbl, _int, _vp, C.POINTER(_int)],
+    "nlmc_lbp_run": [_vp, _f64, _dbl, _dbl, _int, _vp, C.POINTER(_int)],
+    "nlmc_lbp_set_messages": [_vp, _f64, _f64, _f64],
+    "nlmc_lbp_get_messages": [_vp, _vp, _vp, _vp],
+    "nlmc_lbp_byproducts": [_vp, _dbl, _vp, _vp, _vp],
     "nlmc_icm_clusters": [_vp, _int, _i8, _i8, _i32, _i32],
     "nlmc_msc_create": [_vp, _int, _f64, _int, _int, C.c_ulonglong, C.POINTER(_vp)],
     "nlmc_msc_destroy": [_vp],
@@ -152,6 +156,7 @@ class Instance:
         self.val = np.ascontiguousarray(val, dtype=np.float64)
         self.h = np.ascontiguousarray(np.asarray(h, dtype=np.float64).reshape(-1))
         self.n = len(self.rp) - 1
+        self.nnz = len(self.ci)
         self.device = device
         if len(self.h) != self.n:
             raise ValueError(f"h has {len(self.h)} entries, J has {self.n} rows")
@@ -206,6 +211,42 @@ class Lbp:
         check(lib().nlmc_lbp_step(self._h, float(lam), float(beta), float(tol), int(max_iter), marg.ctypes.data,
                                   C.byref(it)), "nlmc_lbp_step")
         return marg, it.value
+
+    def run(self, h_field, beta: float, tol: float, max_iter: int):
+        """One LoopyBeliefPropagation call with the caller's field h[n]; returns (marginal [n], iteration)."""
+        hf = np.ascontiguousarray(np.asarray(h_field, dtype=np.float64).reshape(-1))
+        assert len(hf) == self.inst.n
+        marg = np.empty(self.inst.n, dtype=np.float64)
+        it = _int(0)
+        check(lib().nlmc_lbp_run(self._h, hf, float(beta), float(tol), int(max_iter), marg.ctypes.data,
+                                 C.byref(it)), "nlmc_lbp_run")
+        return marg, it.value
+
+    def set_messages(self, h_edge, u_edge, tot):
+        he = np.ascontiguousarray(h_edge, dtype=np.float64).reshape(-1)
+        ue = np.ascontiguousarray(u_edge, dtype=np.float64).reshape(-1)
+        t = np.ascontiguousarray(tot, dtype=np.float64).reshape(-1)
+        assert len(he) == len(ue) == self.inst.nnz and len(t) == self.inst.n
+        check(lib().nlmc_lbp_set_messages(self._h, he, ue, t), "nlmc_lbp_set_messages")
+
+    def get_messages(self):
+        """(h_edge [nnz], u_edge [nnz], tot [n]): messages on the stored entries plus the off-entry row value."""
+        he = np.empty(self.inst.nnz, dtype=np.float64)
+        ue = np.empty(self.inst.nnz, dtype=np.float64)
+        t = np.empty(self.inst.n, dtype=np.float64)
+        check(lib().nlmc_lbp_get_messages(self._h, he.ctypes.data, ue.ctypes.data, t.ctypes.data),
+              "nlmc_lbp_get_messages")
+        return he, ue, t
+
+    def byproducts(self, beta: float, want_corr: bool = True, want_J_tilde: bool = True):
+        """(correlations [n][n] | None, h_tilde [n], J_tilde [n][n] | None) of the last call (NMC/nmc.py:217-226)."""
+        n = self.inst.n
+        corr = np.empty((n, n), dtype=np.float64) if want_corr else None
+        jt = np.empty((n, n), dtype=np.float64) if want_J_tilde else None
+        ht = np.empty(n, dtype=np.float64)
+        check(lib().nlmc_lbp_byproducts(self._h, float(beta), _ptr(corr), ht.ctypes.data, _ptr(jt)),
+              "nlmc_lbp_byproducts")
+        return corr, ht, jt
 
     def close(self):
         if getattr(self, "_h", None):

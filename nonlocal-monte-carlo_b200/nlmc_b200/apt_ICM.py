@@ -9,9 +9,10 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib, host
+from .path_methods import EnergyMethods, SweepMethodsFixedInstance
 
 
-class APT_ICM:
+class APT_ICM(SweepMethodsFixedInstance, EnergyMethods):
     """Reference: NPT/apt_ICM.py:14-34."""
 
     def __init__(self, J, h, *, mode: str = "replay", device: int = 0, verbose: bool = False):
@@ -33,7 +34,7 @@ class APT_ICM:
     def find_disagreement_clusters(self, state_1, state_2, J=None):
         """apt_ICM.py:116-143 through kernel K7; returns the reference's list of lists (clusters ordered
         by smallest site index; members listed in increasing order)."""
-        prob = host.Problem(self.J, self.h, self.device)
+        prob = self._problem_for(self.J if J is None else J, self.h)
         labels, counts = _lib.icm_clusters(prob.inst, host.as_spins_i8(state_1), host.as_spins_i8(state_2))
         return [list(np.flatnonzero(labels[0] == k)) for k in range(int(counts[0]))]
 
@@ -136,4 +137,24 @@ class APT_ICM:
         if self.verbose:
             print(f"\nLatest energy from each replica = {Energy}")
             print(f"Swap acceptance rate = {np.count_nonzero(count) / max(count.size, 1) * 100:.2f} per cent\n")
+        self.plot_energies(self._EE1_list, beta_list)
         return M, Energy
+
+    def plot_energies(self, EE1_list, beta_list):
+        """'APT_ICM_energy..png' (NPT/apt_ICM.py:307-322, the reference's file name); written only when matplotlib
+        is importable."""
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+        except Exception:
+            return
+        plt.figure()
+        for i, EE1 in enumerate(EE1_list):
+            plt.plot(EE1, label=f"Replica {i + 1} (β={beta_list[i]:.2f})")
+        plt.xlabel('Sweeps')
+        plt.ylabel('Energy')
+        plt.title('Energy traces for different replicas')
+        plt.legend()
+        plt.savefig('APT_ICM_energy..png')
+        plt.close()

@@ -11,9 +11,10 @@ from copy import deepcopy
 import numpy as np
 
 from . import _lib, host
+from .path_methods import SweepMethodsFixedInstance
 
 
-class APT_preprocessor:
+class APT_preprocessor(SweepMethodsFixedInstance):
     """Reference: NPT/apt_preprocessor.py:12-31."""
 
     def __init__(self, J, h, *, mode: str = "replay", device: int = 0, verbose: bool = False):
@@ -29,6 +30,17 @@ class APT_preprocessor:
         self.mode = mode
         self.device = device
         self.verbose = verbose
+
+    def MCMC_task(self, m_start, beta, num_sweeps_MCMC, num_sweeps_read, use_hash_table=0):
+        """One chain of the preprocessor (NPT/apt_preprocessor.py:76-113): (Energy of the last num_sweeps_read
+        sweeps, final state as a (1, N) row).  The table of the reference is a memoisation and is not needed."""
+        M = self.MCMC(num_sweeps_MCMC, np.asarray(m_start).copy(), beta)
+        mm = M[:, -num_sweeps_read:]
+        if mm.shape[1] != num_sweeps_read:  # the reference indexes column kk of a narrower matrix
+            raise IndexError(f"index {mm.shape[1]} is out of bounds for axis 1 with size {mm.shape[1]}")
+        prob = self._problem_for(self.J, self.h)
+        Energy = prob.inst.energy_states(np.ascontiguousarray(mm.T, dtype=np.int8))
+        return Energy, mm[:, -1].copy().reshape(1, -1)
 
     def run(self, num_sweeps_MCMC=1000, num_sweeps_read=1000, num_rng=100,
             beta_start=0.5, alpha=1.25, sigma_E_val=1000, beta_max=30, use_hash_table=1, num_cores=8):

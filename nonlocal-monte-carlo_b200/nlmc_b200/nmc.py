@@ -8,10 +8,14 @@ import numpy as np
 
 from . import _lib, host
 from .nmc_core import nmc_phase_count, nmc_subroutine_replay
+from .path_methods import LbpMethods, SweepMethods
 
 
-class NMC:
-    """Reference: NMC/nmc.py:13-26."""
+class NMC(SweepMethods, LbpMethods):
+    """Reference: NMC/nmc.py:13-26.  MCMC, LBP_convexified, LoopyBeliefPropagation, atanh_saturated, find_clusters and
+    NMC_subroutine come from the mixins in path_methods.py."""
+
+    _nmc_variant = "nmc"
 
     def __init__(self, J, h, *, mode: str = "replay", device: int = 0, verbose: bool = False):
         self.J = J

@@ -16,9 +16,10 @@ import numpy as np
 
 from . import _lib, host
 from .nmc_core import nmc_phase_count, nmc_subroutine_replay
+from .path_methods import EnergyMethods, LbpMethods, SweepMethods
 
 
-class NPT:
+class NPT(SweepMethods, LbpMethods, EnergyMethods):
     """Non-equilibrium Monte Carlo + Adaptive Parallel Tempering (reference: NPT/npt.py:15-29)."""
 
     def __init__(self, J, h, *, mode: str = "replay", device: int = 0, verbose: bool = False):
@@ -32,11 +33,22 @@ class NPT:
         self.verbose = verbose
 
     # ------------------------------------------------------------------------------------------
-    def replica_energy(self, M, num_sweeps):
-        """NPT/npt.py:31-45: (min energy, energies) of the first num_sweeps columns of M (N x S)."""
-        prob = self._problem()
-        EE1 = prob.inst.energy_states(np.ascontiguousarray(np.asarray(M)[:, :num_sweeps].T, dtype=np.int8))
-        return np.min(EE1), EE1
+    _nmc_variant = "npt"
+
+    def MCMC_task(self, replica_i, num_sweeps_MCMC, m_start, beta_list, use_hash_table=False, hash_table=None):
+        """NPT/npt.py:112-127: plain sweeps of replica `replica_i` (1-based) at beta_list[replica_i - 1]."""
+        return self.MCMC(num_sweeps_MCMC, np.asarray(m_start).copy(), beta_list[replica_i - 1], self.J, self.h,
+                         hash_table=hash_table, use_hash_table=use_hash_table)
+
+    def NMC_task(self, m_start, num_cycles, num_sweeps_per_NMC_phase, full_update_frequency, M_skip, global_beta,
+                 temp_x, lambda_start, lambda_end, lambda_reduction_factor, threshold_initial, threshold_cutoff,
+                 max_iterations, tolerance, use_hash_table=False, hash_table=None):
+        """NPT/npt.py:479-512: NMC_subroutine, returning only M_overall."""
+        M_overall, _, _, _ = self.NMC_subroutine(
+            m_start, num_cycles, num_sweeps_per_NMC_phase, full_update_frequency, M_skip, global_beta, temp_x,
+            lambda_start, lambda_end, lambda_reduction_factor, threshold_initial, threshold_cutoff, max_iterations,
+            tolerance, hash_table=hash_table, use_hash_table=use_hash_table)
+        return M_overall
 
     def select_non_overlapping_pairs(self, all_pairs):
         return host.select_non_overlapping_pairs(all_pairs, self.num_swapping_pairs)

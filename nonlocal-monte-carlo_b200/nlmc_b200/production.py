@@ -117,7 +117,7 @@ def _backbones(prob, states, global_beta, nmc_kw):
     return out
 
 
-def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True):
+def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True, all_clusters=None):
     """NMC_subroutine (NMC/nmc.py:320-440 / NPT/npt.py:357-477) for all rows of the dense handle `d` in lock
     step.  Returns (M_overall [n][cols] of row 0 per row?, ...) -- see callers; rows are independent chains."""
     G, n = d.R, prob.n
@@ -151,10 +151,12 @@ def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True):
                     ens[g].append(E[g])
         m_init, _ = d.best_get()  # m_init = M[:, argmin E], first minimum wins (nmc.py:394-395)
 
-    if variant == "npt":
+    if all_clusters is not None:  # clusters provided by the caller: no LBP (nmc.py:357,367)
+        clusters = [np.asarray(all_clusters, dtype=int)] * G
+    elif variant == "npt":
         clusters = _backbones(prob, m_star, nmc_kw["global_beta"], nmc_kw)
     for cycle in range(num_cycles):
-        if variant == "nmc":
+        if variant == "nmc" and all_clusters is None:
             clusters = _backbones(prob, m_star, nmc_kw["global_beta"], nmc_kw)
         in_cl = np.zeros((G, n), dtype=bool)
         for g in range(G):
@@ -270,6 +272,19 @@ def nmc_run_production(obj, kw):
     d.close()
     obj.all_clusters = clusters
     return Mo, Eo, float(np.min(Eo))
+
+
+def nmc_subroutine_production(obj, prob, m_star, phase_sweeps, kw, variant, all_clusters=None):
+    """The public NMC_subroutine method in production mode: one chain on the generic engine.  Returns the
+    reference's tuple (M_overall, energy_overall, min_energy, all_clusters)."""
+    d = _generic_engine(prob, [float(kw["global_beta"])], _seed_from_numpy())
+    try:
+        nmc_kw = dict(kw, phase_sweeps=phase_sweeps)
+        Mo, Eo, clusters = _nmc_cycles_dense(prob, d, np.asarray(m_star).reshape(1, -1), nmc_kw, variant,
+                                             all_clusters=all_clusters)[0]
+    finally:
+        d.close()
+    return Mo, Eo, (float(np.min(Eo)) if len(Eo) else 0.0), clusters
 
 
 def apt_preprocessor_chains_production(prob, reps, iter, saved_state, beta, num_sweeps_MCMC, num_sweeps_read,

@@ -266,11 +266,94 @@ def case_chimera_known_answer():
          gs_bits=np.array([int(b) for b in parts[1:]], dtype=np.int8))
 
 
+def case_public_methods():
+    """The classes' element-level public methods besides run(): LoopyBeliefPropagation with all its by-products,
+    LBP_convexified's dictionaries, NMC_subroutine with provided clusters (both variants), MCMC_task / NMC_task,
+    replica_energy, and the APT classes' MCMC."""
+    N = 40
+    J, h0 = O.random_pm_graph(N, 0.15, 11)
+    rs = np.random.RandomState(12)
+    h = 0.1 * rs.randn(N)
+    out = {"J": J, "h": h}
+    nmc, npt = rl.nmc().NMC(J, h), rl.npt().NPT(J, h)
+    # one LBP call from the reference's own initial messages
+    ms = np.sign(rs.rand(N) - 0.5)
+    epsv = np.abs(h) + np.sum(np.abs(J), axis=1)
+    out.update(lbp_field1=h + 0.7 * ms * epsv, lbp_field2=h + 0.5 * ms * epsv)
+    res = nmc.LoopyBeliefPropagation(J, h + 0.7 * ms * epsv, 1.5, np.zeros((N, N)), J * ms.reshape(1, -1), 1e-10, 200)
+    out.update(lbp_m_star=i8(ms), lbp_beta=1.5, lbp_tol=1e-10, lbp_max_iter=200)
+    for k, v in zip(("marg", "corr", "h_tilde", "J_tilde", "iteration", "h_msgs", "u_msgs"), res):
+        out["lbp_" + k] = np.asarray(v)
+    # a second call warm-started from the first one's messages (row-constant h_msgs off the entries of J)
+    res2 = nmc.LoopyBeliefPropagation(J, h + 0.5 * ms * epsv, 1.5, res[5].copy(), res[6].copy(), 1e-10, 200)
+    for k, v in zip(("marg", "corr", "h_tilde", "J_tilde", "iteration", "h_msgs", "u_msgs"), res2):
+        out["lbp2_" + k] = np.asarray(v)
+    # arbitrary dense initial messages, 3 iterations (exercises messages off the entries of J)
+    hm0, um0 = rs.randn(N, N), 0.2 * rs.randn(N, N)
+    res3 = nmc.LoopyBeliefPropagation(J, h.copy(), 1.5, hm0.copy(), um0.copy(), 1e-10, 3)
+    out.update(lbp3_h0=hm0, lbp3_u0=um0)
+    for k, v in zip(("marg", "corr", "h_tilde", "J_tilde", "iteration", "h_msgs", "u_msgs"), res3):
+        out["lbp3_" + k] = np.asarray(v)
+    # LBP_convexified with a loose tolerance (iteration counts insensitive to last-place differences)
+    with rl.quiet_tmp_cwd():
+        cl, marg_all, mean_all, ht_all, jt_all = nmc.LBP_convexified(2.0, 0.05, 0.8, ms.copy(), epsv, 1e-9, 300, 0.99, 0.9, 2.0)
+    lams = list(marg_all.keys())
+    out.update(conv_args=np.array([2.0, 0.05, 0.8, 1e-9, 300, 0.99, 0.9, 2.0]), conv_lambdas=np.array(lams),
+               conv_marginals=np.array([marg_all[k] for k in lams]), conv_means=np.array([mean_all[k] for k in lams]),
+               conv_h_tilde=np.array([ht_all[k] for k in lams]), conv_J_tilde_last=jt_all[lams[-1]],
+               conv_clusters_flat=np.concatenate(cl).astype(np.int64) if cl else np.array([], dtype=np.int64),
+               conv_cluster_sizes=np.array([len(c) for c in cl], dtype=np.int64))
+    # NMC_subroutine with provided clusters (no LBP -> exact), both variants
+    clusters = np.array([1, 4, 5, 9, 17, 23, 30, 31])
+    sub_args = (3, 6, 2, 2, 1.7, 10.0, 0.5, 0.01, 0.9, 0.9999, 0.999, 50, EPS)
+    for tag, obj in (("nmc", nmc), ("npt", npt)):
+        rl.seed_all(77)
+        with rl.quiet_tmp_cwd():
+            M, E, mn, ac = obj.NMC_subroutine(ms.copy(), *sub_args, all_clusters=clusters.copy())
+        out.update({f"sub_{tag}_M": i8(M), f"sub_{tag}_E": E, f"sub_{tag}_min": mn, f"sub_{tag}_clusters": np.asarray(ac)})
+    out.update(sub_args=np.array(sub_args), sub_clusters=clusters, sub_seed=77)
+    # NPT.MCMC_task / NMC_task (backbone of the task recorded) / replica_energy
+    betas = np.array([0.4, 0.9, 1.6])
+    rl.seed_all(78)
+    Mt = npt.MCMC_task(2, 6, ms.copy(), betas)
+    out.update(task_seed=78, task_betas=betas, task_M=i8(Mt))
+    mn_e, EE1 = npt.replica_energy(Mt, 4)
+    out.update(rep_min=mn_e, rep_EE1=EE1)
+    rl.seed_all(79)
+    with record_backbones(rl.npt().NPT) as rec, rl.quiet_tmp_cwd():
+        Mn = npt.NMC_task(ms.copy(), 2, 4, 1, 1, 2.0, 10.0, 2.0, 0.05, 0.8, 0.99, 0.9, 300, 1e-9)
+    flat, sizes = rec.result()
+    out.update(nmctask_seed=79, nmctask_args=np.array([2, 4, 1, 1, 2.0, 10.0, 2.0, 0.05, 0.8, 0.99, 0.9, 300, 1e-9]),
+               nmctask_M=i8(Mn), nmctask_backbone_flat=flat, nmctask_backbone_sizes=sizes)
+    # APT classes: MCMC with (N,1) h, MCMC_task, replica_energy
+    prep, icm = rl.apt_preprocessor().APT_preprocessor(J, h), rl.apt_icm().APT_ICM(J, h)
+    rl.seed_all(80)
+    Mp = prep.MCMC(5, ms.copy(), 1.2)
+    En, mlast = prep.MCMC_task(ms.copy(), 0.8, 7, 3)
+    Mi = icm.MCMC(4, ms.copy(), 0.6)
+    with warnings_ignored():
+        mn_i, EE_i = icm.replica_energy(Mi, 4)
+    out.update(apt_seed=80, prep_M=i8(Mp), prep_task_E=En, prep_task_m=i8(mlast), icm_M=i8(Mi), icm_rep_min=mn_i,
+               icm_rep_EE1=EE_i)
+    save("public_methods", **out)
+
+
+class warnings_ignored:
+    def __enter__(self):
+        import warnings
+        self.c = warnings.catch_warnings()
+        self.c.__enter__()
+        warnings.simplefilter("ignore")
+
+    def __exit__(self, *a):
+        return self.c.__exit__(*a)
+
+
 if __name__ == "__main__":
     if not rl.available():
         sys.exit("reference not mounted; golden vectors can only be generated in the build container")
     import warnings
     warnings.simplefilter("ignore")
     for fn in (case_mcmc, case_lbp, case_nmc_run, case_npt, case_npt_sk, case_icm, case_npt_sparse, case_known_answers,
-               case_chimera_known_answer):
+               case_chimera_known_answer, case_public_methods):
         fn()

@@ -318,6 +318,47 @@ def lbp(csr: Csr, hl, beta, u, hm, tot, tol, max_iter):
     return np.tanh(beta * (hl + acc)), iteration
 
 
+def lbp_byproducts(csr: Csr, beta, hm, tot, marginal):
+    """correlations, h_tilde, J_tilde of one LBP call, dense like the reference's (NMC/nmc.py:217-226).
+    Off the stored entries h_msgs[i, j] = tot[i] (j != i) and the diagonal of h_msgs is 0 (nmc.py:203)."""
+    n = csr.n
+    Jd = np.zeros((n, n))
+    Jd[csr.row_of, csr.ci] = csr.val
+    H = np.repeat(np.asarray(tot, dtype=np.float64)[:, None], n, axis=1)
+    np.fill_diagonal(H, 0.0)
+    H[csr.row_of, csr.ci] = hm
+    tJ, tH = np.tanh(beta * Jd), np.tanh(beta * H)
+    corr = (tJ + tH * tH.T) / (1 + tJ * tH * tH.T + 1e-10)
+    corr = corr - np.diag(np.diag(corr))
+    return corr, (1 / beta) * _atanh_saturated(marginal), (1 / beta) * _atanh_saturated(corr)
+
+
+def lbp_dense(J, h, beta, h_msgs, u_msgs, tol, max_iter):
+    """LoopyBeliefPropagation with the reference's dense arguments and return tuple (NMC/nmc.py:168-228), for
+    message matrices of the form the reference itself produces (u_msgs zero and h_msgs row-constant off J's entries)."""
+    csr = Csr(J)
+    n = csr.n
+    r, c = csr.row_of, csr.ci
+    h_msgs, u_msgs = np.asarray(h_msgs, dtype=np.float64), np.asarray(u_msgs, dtype=np.float64)
+    off = np.ones((n, n), dtype=bool)
+    off[r, c] = False
+    np.fill_diagonal(off, False)
+    assert not np.any(u_msgs[off]), "u_msgs must vanish off the entries of J"
+    tot = np.where(off.any(axis=1), h_msgs[np.arange(n), np.argmax(off, axis=1)], 0.0)
+    assert np.all(h_msgs[off] == np.repeat(tot[:, None], n, axis=1)[off]), "h_msgs rows must be constant off J"
+    u = np.ascontiguousarray(u_msgs[r, c])
+    hm = np.ascontiguousarray(h_msgs[r, c])
+    hl = np.ascontiguousarray(np.asarray(h, dtype=np.float64).reshape(-1))
+    marg, it = lbp(csr, hl, beta, u, hm, tot, tol, max_iter)
+    corr, ht, jt = lbp_byproducts(csr, beta, hm, tot, marg)
+    H = np.repeat(tot[:, None], n, axis=1)
+    np.fill_diagonal(H, 0.0)
+    H[r, c] = hm
+    U = np.zeros((n, n))
+    U[r, c] = u
+    return marg, corr, ht, jt, it, H, U
+
+
 def lbp_convexified(csr: Csr, h, m_star, epsilon, lambda_start, lambda_end, factor, tol, max_iter,
                     thr_init, thr_cut, beta):
     """lambda-annealed LBP (NMC/nmc.py:93-166).  Returns (clusters, marginal, n_lambda_steps)."""
@@ -353,7 +394,7 @@ def lbp_convexified(csr: Csr, h, m_star, epsilon, lambda_start, lambda_end, fact
 # ----------------------------------------------------------------------------------------------
 def nmc_subroutine(csr: Csr, h, m_star, num_cycles, phase_sweeps, full_update_frequency, M_skip, global_beta,
                    temp_x, lambda_start, lambda_end, factor, thr_init, thr_cut, max_iter, tol,
-                   variant: str, rng=None):
+                   variant: str, rng=None, all_clusters=None):
     rng = rng if rng is not None else np.random
     n = csr.n
     h = np.asarray(h, dtype=np.float64).reshape(-1)
@@ -383,11 +424,11 @@ def nmc_subroutine(csr: Csr, h, m_star, num_cycles, phase_sweeps, full_update_fr
         m_init = Mf[:, int(np.argmin(E))].copy()
         return E
 
-    all_cl = None
-    if variant == "npt":
+    all_cl = None if all_clusters is None else np.asarray(all_clusters, dtype=int)
+    if variant == "npt" and all_clusters is None:
         all_cl = backbone(m_star)
     for cycle in range(num_cycles):
-        if variant == "nmc":
+        if variant == "nmc" and all_clusters is None:
             all_cl = backbone(m_star)
         non_cl = np.setdiff1d(np.arange(n), all_cl)
         in_cl = np.zeros(n, dtype=bool)

@@ -17,6 +17,7 @@ class FakeInstance:
         self.csr._rev = None
         self.h = np.asarray(h, dtype=np.float64).reshape(-1)
         self.n = self.csr.n
+        self.nnz = len(self.csr.ci)
         self.is_integer = bool(np.all(self.csr.val == np.floor(self.csr.val)))
 
     def energy_states(self, states):
@@ -88,7 +89,25 @@ class FakeLbp:
 
     def step(self, lam, beta, tol, max_iter):
         hl = np.ascontiguousarray(self.inst.h + lam * self.ms * self.eps)
-        return O.lbp(self.inst.csr, hl, beta, self.u, self.hm, self.tot, tol, max_iter)
+        self.marg, it = O.lbp(self.inst.csr, hl, beta, self.u, self.hm, self.tot, tol, max_iter)
+        return self.marg, it
+
+    def run(self, h_field, beta, tol, max_iter):
+        hl = np.ascontiguousarray(np.asarray(h_field, dtype=np.float64).reshape(-1))
+        self.marg, it = O.lbp(self.inst.csr, hl, beta, self.u, self.hm, self.tot, tol, max_iter)
+        return self.marg, it
+
+    def set_messages(self, h_edge, u_edge, tot):
+        self.hm = np.array(h_edge, dtype=np.float64)
+        self.u = np.array(u_edge, dtype=np.float64)
+        self.tot = np.array(tot, dtype=np.float64)
+
+    def get_messages(self):
+        return self.hm.copy(), self.u.copy(), self.tot.copy()
+
+    def byproducts(self, beta, want_corr=True, want_J_tilde=True):
+        corr, ht, jt = O.lbp_byproducts(self.inst.csr, beta, self.hm, self.tot, self.marg)
+        return (corr if want_corr else None), ht, (jt if want_J_tilde else None)
 
     def close(self):
         pass

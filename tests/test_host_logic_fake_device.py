@@ -93,3 +93,82 @@ def test_apt_icm(fake_device, tag):
     assert np.array_equal(M, g[f"{tag}_M"].astype(float)) and np.array_equal(E, g[f"{tag}_E"])
     cl = obj.find_disagreement_clusters(g["s1"], g["s2"], g["J"])
     assert len(cl) == int(g["n_clusters"])
+
+
+# ------------------------------------------------------------------ element-level public methods (path_methods.py)
+def test_public_mcmc_and_tasks(fake_device):
+    from nlmc_b200 import NMC, NPT, APT_ICM, APT_preprocessor
+    e = golden("mcmc_element")
+    for tag in ("pm_anneal", "gauss_fixed"):
+        J, h = e[f"{tag}_J"], e[f"{tag}_h"]
+        seed_all(int(e[f"{tag}_seed"]))
+        m0 = np.sign(2 * np.random.rand(len(h)) - 1)
+        M = NMC(J, h).MCMC(int(e[f"{tag}_sweeps"]), m0, float(e[f"{tag}_beta"]), J, h, anneal=bool(e[f"{tag}_anneal"]))
+        assert np.array_equal(M, e[f"{tag}_M"])
+    g = golden("public_methods")
+    J, h, ms = g["J"], g["h"], g["lbp_m_star"].astype(float)
+    npt = NPT(J, h)
+    seed_all(int(g["task_seed"]))
+    Mt = npt.MCMC_task(2, 6, ms.copy(), g["task_betas"])
+    assert np.array_equal(Mt, g["task_M"])
+    mn, EE1 = npt.replica_energy(Mt, 4)
+    np.testing.assert_allclose(EE1, g["rep_EE1"], rtol=1e-12)
+    a = g["nmctask_args"]
+    seed_all(int(g["nmctask_seed"]))
+    Mn = npt.NMC_task(ms.copy(), int(a[0]), int(a[1]), int(a[2]), int(a[3]), a[4], a[5], a[6], a[7], a[8], a[9], a[10],
+                      int(a[11]), a[12])
+    assert np.array_equal(Mn, g["nmctask_M"])
+    prep, icm = APT_preprocessor(J, h), APT_ICM(J, h)
+    seed_all(int(g["apt_seed"]))
+    Mp = prep.MCMC(5, ms.copy(), 1.2)
+    En, mlast = prep.MCMC_task(ms.copy(), 0.8, 7, 3)
+    Mi = icm.MCMC(4, ms.copy(), 0.6)
+    assert np.array_equal(Mp, g["prep_M"]) and np.array_equal(Mi, g["icm_M"]) and np.array_equal(mlast, g["prep_task_m"])
+    np.testing.assert_allclose(En, g["prep_task_E"], rtol=1e-12)
+    np.testing.assert_allclose(icm.replica_energy(Mi, 4)[1], g["icm_rep_EE1"], rtol=1e-12)
+    with pytest.raises(ValueError, match="LRUCache"):
+        npt.MCMC(2, ms, 1.0, J, h, hash_table=object(), use_hash_table=True)
+
+
+@pytest.mark.parametrize("tag,field,init", [("lbp", "lbp_field1", "cold"), ("lbp2", "lbp_field2", "warm"),
+                                            ("lbp3", None, "dense")])
+def test_public_loopy_belief_propagation(fake_device, tag, field, init):
+    """The dense <-> edge conversion around K5, including messages off the entries of J (explicit-zero pattern)."""
+    from nlmc_b200 import NMC
+    g = golden("public_methods")
+    J, ms = g["J"], g["lbp_m_star"].astype(float)
+    n = len(ms)
+    if init == "cold":
+        h0, u0, hf, it_max = np.zeros((n, n)), J * ms.reshape(1, -1), g[field], int(g["lbp_max_iter"])
+    elif init == "warm":
+        h0, u0, hf, it_max = g["lbp_h_msgs"], g["lbp_u_msgs"], g[field], int(g["lbp_max_iter"])
+    else:
+        h0, u0, hf, it_max = g["lbp3_h0"], g["lbp3_u0"], g["h"], 3
+    out = NMC(J, g["h"]).LoopyBeliefPropagation(J, hf, 1.5, h0.copy(), u0.copy(), 1e-10, it_max)
+    assert out[4] == int(g[f"{tag}_iteration"])
+    for got, key in zip(out, ("marg", "corr", "h_tilde", "J_tilde", None, "h_msgs", "u_msgs")):
+        if key:
+            np.testing.assert_allclose(got, g[f"{tag}_{key}"], rtol=1e-12, atol=1e-13, err_msg=key)
+
+
+def test_public_lbp_convexified_and_subroutine(fake_device):
+    from nlmc_b200 import NMC, NPT
+    g = golden("public_methods")
+    J, h, ms = g["J"], g["h"], g["lbp_m_star"].astype(float)
+    a = g["conv_args"]
+    epsv = np.abs(h) + np.sum(np.abs(J), axis=1)
+    cl, marg, mean, ht, jt = NMC(J, h).LBP_convexified(a[0], a[1], a[2], ms.copy(), epsv, a[3], int(a[4]), a[5], a[6], a[7])
+    lams = list(marg.keys())
+    assert np.array_equal(np.array(lams), g["conv_lambdas"])
+    assert np.array_equal(np.array([marg[k] for k in lams]), g["conv_marginals"])
+    np.testing.assert_allclose(np.array([ht[k] for k in lams]), g["conv_h_tilde"], rtol=1e-12)
+    np.testing.assert_allclose(jt[lams[-1]], g["conv_J_tilde_last"], rtol=1e-12, atol=1e-14)
+    assert np.array_equal(np.concatenate(cl), g["conv_clusters_flat"])
+    s = g["sub_args"]
+    for variant, cls in (("nmc", NMC), ("npt", NPT)):
+        seed_all(int(g["sub_seed"]))
+        M, E, mn, ac = cls(J, h).NMC_subroutine(ms.copy(), int(s[0]), int(s[1]), int(s[2]), int(s[3]), s[4], s[5], s[6],
+                                                s[7], s[8], s[9], s[10], int(s[11]), s[12],
+                                                all_clusters=g["sub_clusters"].copy())
+        assert np.array_equal(M, g[f"sub_{variant}_M"]) and np.array_equal(ac, g[f"sub_{variant}_clusters"])
+        np.testing.assert_allclose(E, g[f"sub_{variant}_E"], rtol=1e-12)

@@ -132,3 +132,35 @@ def test_known_answer_wishart_ground_states():
         norm = np.max(np.abs(J))
         E = O.energy(O.Csr(J / norm), np.zeros(10), states)
         assert np.isclose(E.min() * norm, gs, rtol=0, atol=1e-9)
+
+
+# ------------------------------------------------------------------ public element-level methods
+@pytest.mark.parametrize("tag,field,warm", [("lbp", "lbp_field1", False), ("lbp2", "lbp_field2", True)])
+def test_lbp_dense_call_and_byproducts(tag, field, warm):
+    """LoopyBeliefPropagation's full return tuple (NMC/nmc.py:168-228): marginals, correlations, h_tilde, J_tilde,
+    iteration and both message matrices."""
+    g = golden("public_methods")
+    J, ms = g["J"], g["lbp_m_star"].astype(float)
+    n = len(ms)
+    h0, u0 = (g["lbp_h_msgs"], g["lbp_u_msgs"]) if warm else (np.zeros((n, n)), J * ms.reshape(1, -1))
+    marg, corr, ht, jt, it, H, U = O.lbp_dense(J, g[field], float(g["lbp_beta"]), h0, u0, float(g["lbp_tol"]),
+                                               int(g["lbp_max_iter"]))
+    assert it == int(g[f"{tag}_iteration"])
+    assert np.array_equal(marg, g[f"{tag}_marg"])
+    assert np.array_equal(H, g[f"{tag}_h_msgs"]) and np.array_equal(U, g[f"{tag}_u_msgs"])
+    np.testing.assert_allclose(corr, g[f"{tag}_corr"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(ht, g[f"{tag}_h_tilde"], rtol=1e-13)
+    np.testing.assert_allclose(jt, g[f"{tag}_J_tilde"], rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("variant", ["nmc", "npt"])
+def test_nmc_subroutine_with_provided_clusters(variant):
+    g = golden("public_methods")
+    a = g["sub_args"]
+    seed_all(int(g["sub_seed"]))
+    M, E, mn, cl = O.nmc_subroutine(O.Csr(g["J"]), g["h"], g["lbp_m_star"].astype(float), int(a[0]), int(a[1]),
+                                    int(a[2]), int(a[3]), a[4], a[5], a[6], a[7], a[8], a[9], a[10], int(a[11]), a[12],
+                                    variant, all_clusters=g["sub_clusters"])
+    assert np.array_equal(M, g[f"sub_{variant}_M"])
+    np.testing.assert_allclose(E, g[f"sub_{variant}_E"], rtol=1e-12)
+    assert np.array_equal(cl, g[f"sub_{variant}_clusters"])
