@@ -102,6 +102,18 @@ __device__ __forceinline__ void count6(uint32_t a0, uint32_t a1, uint32_t a2, ui
     c2 = maj3(k1, k2, k3);
 }
 
+// Threshold bit of every lane's |f| level: t = (p1 ? I1 : 0) | (p2 ? I2 : 0) | (p3 ? I3 : 0) with p in {0, 1}.  The lane
+// sets are disjoint, so the ORs are sums and the selects are products: three integer multiply-adds on the FMA pipe
+// instead of five select/logic operations on the ALU pipe, which is the limiter of this kernel (ncu: alu 68 %,
+// fma 26 % before the change).  Inline PTX so that the compiler does not turn them back into selects.
+__device__ __forceinline__ uint32_t level_select(uint32_t i1, uint32_t i2, uint32_t i3, uint32_t p1, uint32_t p2,
+                                                 uint32_t p3) {
+    uint32_t t;
+    asm("{\n\t.reg .u32 a;\n\tmul.lo.u32 a, %1, %4;\n\tmad.lo.u32 a, %2, %5, a;\n\tmad.lo.u32 %0, %3, %6, a;\n\t}"
+        : "=r"(t) : "r"(i1), "r"(i2), "r"(i3), "r"(p1), "r"(p2), "r"(p3));
+    return t;
+}
+
 __device__ __forceinline__ uint32_t comp(const uint4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
 
 // One colour of one sweep: a warp per (site, 128-word chunk), a lane per four consecutive words.
@@ -154,30 +166,37 @@ __global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int
     const Philox rng{a.seed_lo, a.seed_hi ^ kTagSweep};
     // stream id = (beta index, GLOBAL ladder quad): independent of how ladders are sharded over handles/GPUs
     const uint32_t sid = ((uint32_t)b << 20) | (uint32_t)(a.quad_offset + ((word0 - b * a.G) >> 2));
-    {   // step 0: level-0 lanes (q = 1/2) are decided by the first bit alone: g = ~r
+    // Bit-serial comparison state per word: und = lanes whose uniform still equals the threshold on the prefix seen so
+    // far; v = the uniform's bit at the last step a lane was undecided, i.e. for a decided lane the bit at its first
+    // difference (v = 0 there <=> uniform < threshold <=> g = 1).  Two 3-input logic ops per word and step; the level
+    // select runs on the FMA pipe.  g = ~v & ~und is formed once after the last step.
+    uint32_t v[4];
+    {   // step 0: level-0 lanes (q = 1/2) are decided by the first bit alone (g = ~r, so v = r fits them too)
         const uint4 r4 = rng((uint32_t)site, sid, sweep, 0u);
-        const bool p1 = (T1 >> 31) & 1u, p2 = (T2 >> 31) & 1u, p3 = (T3 >> 31) & 1u;
+        const uint32_t p1 = T1 >> 31, p2 = T2 >> 31, p3 = T3 >> 31;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t r = comp(r4, k);
             const uint32_t I0 = ~(I1[k] | I2[k] | I3[k]);
-            const uint32_t t = (p1 ? I1[k] : 0u) | (p2 ? I2[k] : 0u) | (p3 ? I3[k] : 0u);
-            res[k] = ~r & (t | I0);
+            const uint32_t t = level_select(I1[k], I2[k], I3[k], p1, p2, p3);
+            v[k] = r;
             und[k] = ~(r ^ t) & ~I0;
         }
     }
 #pragma unroll
     for (int p = 1; p < kSteps; ++p) {
         const uint4 r4 = rng((uint32_t)site, sid, sweep, (uint32_t)p);
-        const bool p1 = (T1 >> (31 - p)) & 1u, p2 = (T2 >> (31 - p)) & 1u, p3 = (T3 >> (31 - p)) & 1u;
+        const uint32_t p1 = (T1 >> (31 - p)) & 1u, p2 = (T2 >> (31 - p)) & 1u, p3 = (T3 >> (31 - p)) & 1u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t r = comp(r4, k);
-            const uint32_t t = (p1 ? I1[k] : 0u) | (p2 ? I2[k] : 0u) | (p3 ? I3[k] : 0u);
-            res[k] |= und[k] & ~r & t;   // uniform bit 0, threshold bit 1  -> u < T decided
-            und[k] &= ~(r ^ t);          // still equal on this prefix
+            const uint32_t t = level_select(I1[k], I2[k], I3[k], p1, p2, p3);
+            v[k] = (und[k] & r) | (~und[k] & v[k]);  // undecided lanes take this step's bit
+            und[k] &= ~(r ^ t);                      // still equal on this prefix
         }
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) res[k] = ~v[k] & ~und[k];
     // stragglers: each gets a fresh 32-bit uniform against the remaining threshold bits.  One Philox call
     // serves the lowest undecided lane of each of the four words, so the warp iterates
     // max-over-threads-and-words(#undecided per word) times (about 1.3 at kSteps = 8).
