@@ -159,6 +159,10 @@ int nlmc_icm_clusters(nlmc_instance *inst, int n_pairs, const int8_t *s1 /*[n_pa
  *                       energies of the states before the exchange.
  *   nlmc_msc_round_host the same through HOST buffers: packed states in ([n][n_words] uint32, NULL = keep
  *                       the device state), packed states and energies out (either may be NULL).
+ *   nlmc_msc_round_host_async  the same without waiting: copies and kernels are queued on the handle's own stream
+ *                       and the call returns; the outputs are valid after nlmc_msc_sync.  With pinned host buffers
+ *                       and two handles used alternately, one batch's copies overlap the other's sweeps (the
+ *                       reference ships m_start to its workers and M back every round, NPT/npt.py:625-644).
  *   nlmc_msc_set/get_spins     one replica (beta_idx, ladder) as int8 +-1.
  *   nlmc_msc_timer_*    CUDA-event timing on the handle's stream (mark 0 = start, 1 = stop). */
 /* ladder_offset: global index of this handle's first ladder (a multiple of 128).  Every random stream is
@@ -186,6 +190,8 @@ int nlmc_msc_sweep_record(nlmc_msc *msc, int n_sweeps, int ladder, int8_t *out_M
 int nlmc_msc_round(nlmc_msc *msc, int n_sweeps, int num_swapping_pairs, double *out_E);
 int nlmc_msc_round_host(nlmc_msc *msc, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,
                         uint32_t *packed_out, double *out_E);
+int nlmc_msc_round_host_async(nlmc_msc *msc, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,
+                              uint32_t *packed_out, double *out_E);
 int nlmc_msc_swap_count(nlmc_msc *msc, int *out_accepted, int reset);
 int nlmc_msc_sync(nlmc_msc *msc);
 int nlmc_msc_timer_mark(nlmc_msc *msc, int which);

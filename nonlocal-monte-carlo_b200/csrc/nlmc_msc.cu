@@ -819,8 +819,8 @@ int nlmc_msc_sweep_record(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, 
     return NLMC_OK;
 }
 
-int nlmc_msc_round_host(nlmc_msc *M, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,
-                        uint32_t *packed_out, double *out_E) {
+int nlmc_msc_round_host_async(nlmc_msc *M, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,
+                              uint32_t *packed_out, double *out_E) {
     NLMC_REQUIRE(M && n_sweeps >= 0, "nlmc_msc_round_host: bad arguments");
     int rc;
     if (packed_in && (rc = nlmc_msc_set_packed(M, packed_in))) return rc;
@@ -831,6 +831,13 @@ int nlmc_msc_round_host(nlmc_msc *M, const uint32_t *packed_in, int n_sweeps, in
     if (packed_out)
         NLMC_CUDA(cudaMemcpyAsync(packed_out, M->S, sizeof(uint32_t) * (size_t)M->n * M->W, cudaMemcpyDeviceToHost,
                                   M->stream));
+    return NLMC_OK;
+}
+
+int nlmc_msc_round_host(nlmc_msc *M, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,
+                        uint32_t *packed_out, double *out_E) {
+    const int rc = nlmc_msc_round_host_async(M, packed_in, n_sweeps, num_swapping_pairs, packed_out, out_E);
+    if (rc) return rc;
     NLMC_CUDA(cudaStreamSynchronize(M->stream));
     return NLMC_OK;
 }

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "nlmc_msc_sweep_record": [_vp, _int, _int, _vp, _vp],
     "nlmc_msc_round": [_vp, _int, _int, _vp],
     "nlmc_msc_round_host": [_vp, _vp, _int, _int, _vp, _vp],
+    "nlmc_msc_round_host_async": [_vp, _vp, _int, _int, _vp, _vp],
     "nlmc_msc_swap_count": [_vp, C.POINTER(_int), _int],
     "nlmc_msc_sync": [_vp],
     "nlmc_msc_timer_mark": [_vp, _int],
@@ -414,6 +415,12 @@ class Msc:
         """Raw-pointer variant for pinned host buffers (bench.py's end-to-end leg)."""
         check(lib().nlmc_msc_round_host(self._h, packed_in_ptr, int(n_sweeps), int(num_swapping_pairs),
                                         packed_out_ptr, out_E_ptr), "nlmc_msc_round_host")
+
+    def round_host_async(self, packed_in_ptr, n_sweeps: int, num_swapping_pairs: int, packed_out_ptr, out_E_ptr):
+        """round_host without the final wait: outputs are valid after sync().  Two handles used alternately with
+        pinned buffers overlap one batch's copies with the other's sweeps."""
+        check(lib().nlmc_msc_round_host_async(self._h, packed_in_ptr, int(n_sweeps), int(num_swapping_pairs),
+                                              packed_out_ptr, out_E_ptr), "nlmc_msc_round_host_async")
 
     def swap_count(self, reset: bool = False) -> int:
         v = _int()
