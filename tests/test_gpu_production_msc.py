@@ -238,6 +238,37 @@ def test_determinism_and_seed_dependence(nl):
     assert not np.array_equal(outs[0], outs[2])
 
 
+def test_round_host_sync_async_and_device_round_agree(nl):
+    """The three ways to run a swap round -- device-resident (nlmc_msc_round), host buffers (nlmc_msc_round_host) and
+    host buffers without waiting (nlmc_msc_round_host_async + nlmc_msc_sync, two handles in flight at once) -- give
+    the same states and energies for the same seed."""
+    from oracle import oracle as O
+    A, h = O.ea3d_pm_j(6, 3)
+    prob = nl.host.Problem(A, h)
+    betas = [0.4, 0.8, 1.2]
+    ms = [nl.lib.Msc(prob.inst, betas, 128, seed=21) for _ in range(3)]
+    start = ms[0].get_packed()
+    shape = ms[0].packed_shape()
+    ms[0].round(5, 1)
+    ref_state = ms[0].get_packed()
+    ref_E = ms[0].energies()
+    out1, E1 = np.empty(shape, np.uint32), np.empty((3, 128))
+    ms[1].round_host(start.ctypes.data, 5, 1, out1.ctypes.data, E1.ctypes.data)
+    out2, E2 = np.empty(shape, np.uint32), np.empty((3, 128))
+    other = nl.lib.Msc(prob.inst, betas, 128, seed=99)  # a second batch in flight on its own stream
+    out3, E3 = np.empty(shape, np.uint32), np.empty((3, 128))
+    ms[2].round_host_async(start.ctypes.data, 5, 1, out2.ctypes.data, E2.ctypes.data)
+    other.round_host_async(start.ctypes.data, 5, 1, out3.ctypes.data, E3.ctypes.data)
+    ms[2].sync(); other.sync()
+    assert np.array_equal(out1, ref_state) and np.array_equal(out2, ref_state)
+    assert not np.array_equal(out3, ref_state)
+    # energies returned with the states are those of the returned states (after the exchange)
+    assert np.array_equal(np.sort(E1, axis=0), np.sort(E2, axis=0))
+    assert np.array_equal(E1, ref_E) and np.array_equal(E2, ref_E)
+    for m in ms + [other]:
+        m.close()
+
+
 def test_npt_production_mode_api(nl, tmp_cwd):
     """Drop-in NPT in production mode: shapes/dtypes of the reference contract, energies consistent with M."""
     from nlmc_b200 import NPT
