@@ -320,6 +320,18 @@ class _IcmEngine:
     def sweep(self, k):
         self.eng.sweep(k)
 
+    def device_round(self, spm, num_pairs):
+        """spm sweeps, energies and the exchange entirely on the device (K2 + K4' + K6); returns the number of
+        accepted exchanges among the S sub-replicas, or None when the engine has no device-side exchange.  K6 draws
+        the non-overlapping pairs per chain (the reference draws one set per round and tests it for each of the 10
+        sub-replicas, apt_ICM.py:249-285): every chain sees the same selection and acceptance law."""
+        if not self.msc:
+            return None
+        self.eng.swap_count(reset=True)
+        self.eng.round(spm, num_pairs)
+        # the handle pads the S chains to 128 lanes; report the share of the S real ones
+        return self.eng.swap_count(reset=True) * self.S / self.eng.n_ladders
+
     def energies(self):  # [R][S]
         E = self.eng.energies()
         return E[:, :self.S].copy() if self.msc else E.reshape(self.R, self.S)
@@ -361,6 +373,11 @@ def apt_icm_run_production(obj, beta_list):
         need_first = last_round or spm == 1   # the Houdayer edit is only observable in these cases
         first = E_first = None
         cols, ens = [], []
+        if not need_first:
+            acc = eng.device_round(spm, obj.num_swapping_pairs)
+            if acc is not None:  # nothing of this round is observable on the host: it stays on the device
+                count[ii] = acc
+                continue
         if need_first:
             eng.sweep(1)
             first, E_first = eng.get_states(), eng.energies()

@@ -144,6 +144,18 @@ def c4():
     att = 8 * 10 * 32768 * 4
     emit(config="C4", what="APT_ICM.run replay: 8 betas x 10 sub-replicas, 2 rounds x 2 sweeps, 80 Houdayer pairs",
          seconds=dt, attempts=att, attempts_per_s=att / dt, energies=[float(e) for e in E])
+    betas32 = np.linspace(0.2, 1.6, 32)
+    np.random.seed(4); random.seed(4)
+    os.chdir("/tmp")
+    for warm in (True, False):  # first call creates handles/graphs
+        t0 = time.perf_counter()
+        M, E = APT_ICM(A, h, mode="production").run(betas32, 32, num_sweeps_MCMC=1000, num_sweeps_read=1000,
+                                                   num_swap_attempts=100, num_swapping_pairs=10)
+        dt = time.perf_counter() - t0
+    os.chdir(cwd)
+    att = 32 * 10 * 32768 * 1000
+    emit(config="C4", what="APT_ICM.run production: 32 betas x 10 sub-replicas, 100 rounds x 10 sweeps, device-resident rounds",
+         seconds=dt, attempts=att, attempts_per_s=att / dt, min_energy=float(E.min()), M_shape=list(M.shape))
     rs = np.random.RandomState(1)
     s1 = rs.choice([-1, 1], size=(40, 32768)).astype(np.int8)
     s2 = np.where(rs.rand(40, 32768) < 0.3, -s1, s1).astype(np.int8)
