@@ -338,6 +338,35 @@ def case_public_methods():
     save("public_methods", **out)
 
 
+def case_contrived_generator():
+    """contrived_instance_generator.py (Wishart backbone + trees): adjacency, weights, cross connections, edge removal,
+    fields and the instance text, produced by the reference's own functions for one seed."""
+    import importlib.util
+    import tempfile
+    import types
+    rl.nmc()  # installs the matplotlib stub
+    sys.modules.setdefault("seaborn", types.ModuleType("seaborn"))
+    base = os.path.join(rl.REFERENCE_ROOT, "NMC", "examples", "contrived_wishart_backbone")
+    spec = importlib.util.spec_from_file_location("cig", os.path.join(base, "contrived_instance_generator.py"))
+    cig = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cig)
+    Jw, _ = cig.txt_to_A_wishart(os.path.join(base, "wishart_planting_N_10_alpha_0.20",
+                                              "wishart_planting_N_10_alpha_0.20_inst_1.txt"))
+    Jw = -Jw.toarray()
+    b, levels, n_cross, n_remove, seed = 10, 2, 20, 3, 77
+    np.random.seed(seed)
+    A = cig.generate_adjacency(b, levels)
+    A = cig.assign_random_weights(A, b, -1, 1, -10, 10)
+    A = cig.add_cross_connections(A, b, n_cross, -1, 1)
+    A = cig.remove_random_backbone_edges(A, b, n_remove)
+    A[0:b, 0:b] = 10 * Jw / np.max(np.abs(Jw))
+    h = (np.random.rand(len(A)) - 0.5) * 2 * 0.2 * 10
+    path = os.path.join(tempfile.mkdtemp(), "inst.txt")
+    cig.save_to_txt(A, h, path)
+    save("contrived_generator", J_backbone=Jw, args=np.array([levels, 0.2, 1, 10, n_cross, 1, n_remove]), seed=seed,
+         J=A, h=h, text=np.array(open(path).read()), adjacency_4_1=cig.generate_adjacency(4, 1))
+
+
 class warnings_ignored:
     def __enter__(self):
         import warnings
@@ -355,5 +384,5 @@ if __name__ == "__main__":
     import warnings
     warnings.simplefilter("ignore")
     for fn in (case_mcmc, case_lbp, case_nmc_run, case_npt, case_npt_sk, case_icm, case_npt_sparse, case_known_answers,
-               case_chimera_known_answer, case_public_methods):
+               case_chimera_known_answer, case_public_methods, case_contrived_generator):
         fn()

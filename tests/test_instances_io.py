@@ -64,3 +64,24 @@ def test_parsers_match_reference(script, func, ours, pattern):
         Jo, ho = getattr(instances, ours)(f, flip_sign=False)
         assert Jr.shape == Jo.shape and (Jr != Jo).nnz == 0
         assert np.array_equal(np.asarray(hr).reshape(-1), ho.reshape(-1))
+
+
+def test_contrived_wishart_tree_generator_matches_reference(tmp_path):
+    """The contrived 'Wishart backbone + trees' generator (contrived_instance_generator.py) reproduced draw for draw:
+    adjacency, weights, cross connections, edge removal, fields and the written instance text."""
+    from conftest import golden
+    from nlmc_b200 import instances as I
+    g = golden("contrived_generator")
+    a = g["args"]
+    assert np.array_equal(I.tree_backbone_adjacency(4, 1), g["adjacency_4_1"])
+    np.random.seed(int(g["seed"]))
+    J, h = I.contrived_wishart_tree(g["J_backbone"], int(a[0]), a[1], a[2], a[3], int(a[4]), a[5], int(a[6]))
+    assert np.array_equal(J, g["J"]) and np.array_equal(h, g["h"])
+    assert np.array_equal(J, J.T)
+    path = tmp_path / "inst.txt"
+    I.write_instance(J, h, str(path))
+    assert path.read_text() == str(g["text"])
+    # and back through the parser of the contrived example (sign convention: the file holds -J, -h)
+    J2, h2 = I.read_contrived_wishart(str(path))
+    np.testing.assert_allclose(J2.toarray(), J, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(h2.reshape(-1), h, rtol=0, atol=1e-15)
