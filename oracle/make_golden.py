@@ -338,6 +338,17 @@ def case_public_methods():
     save("public_methods", **out)
 
 
+def case_dcl_known_answer():
+    """DCL (deceptive cluster loops) instance C8/00 with the planted minimum energy of its `_sol.txt` (`min_energy`);
+    convention J = -J_file, E = -(m^T J m / 2) (NMC/examples/DCL_example.py:48-54).  The file rounds 1/7 to 0.14286, so the
+    energy of the file's couplings is -389.43032 against the stated -389.42857."""
+    base = os.path.join(rl.REFERENCE_ROOT, "NMC", "examples", "DCL_instances", "C8")
+    text = open(os.path.join(base, "00.txt")).read()
+    sol = dict(line.split() for line in open(os.path.join(base, "00_sol.txt")) if line.strip())
+    save("known_answer_dcl_c8", instance_text=np.array(text), min_energy=float(sol["min_energy"]),
+         n_active=int(sol["nq"]))
+
+
 def case_contrived_generator():
     """contrived_instance_generator.py (Wishart backbone + trees): adjacency, weights, cross connections, edge removal,
     fields and the instance text, produced by the reference's own functions for one seed."""
@@ -384,5 +395,5 @@ if __name__ == "__main__":
     import warnings
     warnings.simplefilter("ignore")
     for fn in (case_mcmc, case_lbp, case_nmc_run, case_npt, case_npt_sk, case_icm, case_npt_sparse, case_known_answers,
-               case_chimera_known_answer, case_public_methods, case_contrived_generator):
+               case_chimera_known_answer, case_public_methods, case_contrived_generator, case_dcl_known_answer):
         fn()
