@@ -237,21 +237,24 @@ __global__ void msc_init_kernel(MscDev a, uint32_t stream_id) {
 // K4': per (word, lane) sum over sites of the number of unsatisfied bonds at the site, with bit-sliced
 // vertical counters (10 bit planes) flushed every kEnergyChunk sites.  E = sum_i unsat_i - n_bonds.
 constexpr int kEnergyChunk = 128;  // at most 128 sites per warp: 128 sites * 6 bonds < 2^10
-__global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_acc, int chunk) {
+// On a two-colourable graph every bond joins the two colour classes, so the sites of ONE class see every bond exactly
+// once: the launcher then passes only that class (n_list sites of site_list) and the finish kernel doubles the sum.
+__global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_acc, int chunk, int n_list) {
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     const int chunks = (a.W + 127) >> 7;
-    const int site_chunks = (a.n + chunk - 1) / chunk;
+    const int site_chunks = (n_list + chunk - 1) / chunk;
     if (warp >= site_chunks * chunks) return;
     const int word0 = (warp % chunks) * 128 + lane * 4;
     if (word0 >= a.W) return;
-    const int s_begin = (warp / chunks) * chunk, s_end = min(a.n, s_begin + chunk);
+    const int s_begin = (warp / chunks) * chunk, s_end = min(n_list, s_begin + chunk);
     uint32_t v[4][10];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int bb = 0; bb < 10; ++bb) v[k][bb] = 0u;
-    for (int site = s_begin; site < s_end; ++site) {
+    for (int s = s_begin; s < s_end; ++s) {
+        const int site = __ldg(a.site_list + s);
         const uint32_t meta = __ldg(a.meta + site);
         const uint4 own = *reinterpret_cast<const uint4 *>(a.S + (size_t)site * a.W + word0);
         uint4 x[6];
@@ -299,12 +302,13 @@ __global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_ac
     }
 }
 
-__global__ void msc_energy_finish_kernel(int W, int G, int n_ladders, long long n_bonds, const int32_t *E_acc, double *E) {
+__global__ void msc_energy_finish_kernel(int W, int G, int n_ladders, long long n_bonds, int factor, const int32_t *E_acc,
+                                         double *E) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (word, lane)
     if (idx >= W * 32) return;
     const int w = idx >> 5, l = idx & 31;
     const int b = w / G, g = w % G;
-    E[(size_t)b * n_ladders + g * 32 + l] = (double)E_acc[idx] - (double)n_bonds;
+    E[(size_t)b * n_ladders + g * 32 + l] = (double)factor * (double)E_acc[idx] - (double)n_bonds;
 }
 
 // K6: replica exchange, one thread per ladder.  Pair selection and acceptance follow the reference
@@ -446,14 +450,16 @@ static int launch_energy(nlmc_msc *M) {
     const int chunks = (M->W + 127) / 128;
     // sites per warp: as many as the 10-bit counters allow on big lattices, fewer on small ones so that the
     // grid still fills the GPU (about 8 warps per SM)
-    const int sites_for_fill = (int)(((long long)M->n * chunks + 148 * 8 - 1) / (148 * 8));
+    const bool bipartite = M->n_colours == 2;  // one colour class sees every bond once
+    const int n_list = bipartite ? M->colour_ptr[1] : M->n;
+    const int sites_for_fill = (int)(((long long)n_list * chunks + 148 * 8 - 1) / (148 * 8));
     const int chunk = std::max(16, std::min(kEnergyChunk, sites_for_fill));
-    const int site_chunks = (M->n + chunk - 1) / chunk;
+    const int site_chunks = (n_list + chunk - 1) / chunk;
     NLMC_CUDA(cudaMemsetAsync(M->E_acc, 0, sizeof(int32_t) * (size_t)M->W * 32, M->stream));
     const long long warps = (long long)site_chunks * chunks;
-    msc_energy_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, M->stream>>>(d, M->E_acc, chunk);
+    msc_energy_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, M->stream>>>(d, M->E_acc, chunk, n_list);
     msc_energy_finish_kernel<<<(M->W * 32 + 255) / 256, 256, 0, M->stream>>>(M->W, M->G, M->n_ladders, M->n_bonds,
-                                                                            M->E_acc, M->E);
+                                                                            bipartite ? 2 : 1, M->E_acc, M->E);
     NLMC_CUDA(cudaGetLastError());
     return NLMC_OK;
 }

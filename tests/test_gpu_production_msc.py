@@ -86,6 +86,24 @@ def test_pack_unpack_and_exact_energies(nl):
     assert np.array_equal(np.where(bit == 1, 1, -1).astype(np.int8), msc.get_spins(1, 129))
 
 
+@pytest.mark.parametrize("L,two_colourable", [(5, False), (6, True)])
+def test_energies_exact_on_bipartite_and_frustrated_colourings(nl, L, two_colourable):
+    """K4' sums the unsatisfied bonds seen from one colour class when the graph is two-colourable (every bond joins
+    the two classes) and from all sites otherwise (odd L: the periodic lattice needs more colours): exact both ways."""
+    from oracle import oracle as O
+    A, h = O.ea3d_pm_j(L, 11)
+    csr = O.Csr(A)
+    prob = nl.host.Problem(A, h)
+    msc = nl.lib.Msc(prob.inst, [0.4, 1.1], 128, seed=2)
+    assert (msc.n_colours == 2) == two_colourable
+    msc.sweep(4)
+    E = msc.energies()
+    for b in range(2):
+        for lad in (0, 31, 32, 127):
+            assert E[b, lad] == O.energy(csr, h, msc.get_spins(b, lad))[0]
+    msc.close()
+
+
 def test_unsupported_instances_fail_loudly(nl):
     from oracle import oracle as O
     J, h = O.sk_gaussian(16, 1)
