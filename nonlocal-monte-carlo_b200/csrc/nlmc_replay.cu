@@ -253,16 +253,24 @@ __global__ void __launch_bounds__(32) sweep_replay_int_kernel(ReplayArgs a, cons
                 } else if (!(md & 2)) {
                     const double h_k = (md & 1) ? h_eff[k] : 0.0;
                     t = tanh_sat(__dmul_rn(beta, __dadd_rn((double)f, h_k)));
-                } else {  // rescaled row: storage-order sum of fl(J/temp_x)*m, as the reference forms it
-                    double x = 0.0;
-                    const int re = rp_s[k + 1];
-                    for (int pb = rp_s[k]; pb < re; pb += 32) {
-                        const int p = pb + lane;
-                        double prod = 0.0;
-                        if (p < re) prod = __dmul_rn(div_tab[(int)val_s[p] + 128], (double)m[col_s[p]]);
-                        x = ordered_sum32(x, prod, min(32, re - pb), scratch, lane);
+                } else {
+                    // Rescaled row (NMC backbone at beta/temp_x).  The reference's field is the storage-order sum of
+                    // fl(J/temp_x)*m; it differs from f/temp_x (f = the exact integer field) by a few ulps only, so the
+                    // decision sign(t - 2u + 1) is screened with f/temp_x first and the dependent fp64 add chain over
+                    // the row is walked only when u lies within 1e-9 of the threshold (where those ulps could matter).
+                    const double xa = __dadd_rn(__ddiv_rn((double)f, temp_x), h_eff[k]);
+                    t = tanh_sat(__dmul_rn(beta, xa));
+                    if (fabs(__dadd_rn(__dsub_rn(t, __dmul_rn(2.0, u_a)), 1.0)) <= 1e-9) {
+                        double x = 0.0;
+                        const int re = rp_s[k + 1];
+                        for (int pb = rp_s[k]; pb < re; pb += 32) {
+                            const int p = pb + lane;
+                            double prod = 0.0;
+                            if (p < re) prod = __dmul_rn(div_tab[(int)val_s[p] + 128], (double)m[col_s[p]]);
+                            x = ordered_sum32(x, prod, min(32, re - pb), scratch, lane);
+                        }
+                        t = tanh_sat(__dmul_rn(beta, __dadd_rn(x, h_eff[k])));
                     }
-                    t = tanh_sat(__dmul_rn(beta, __dadd_rn(x, h_eff[k])));
                 }
                 const double v = __dadd_rn(__dsub_rn(t, __dmul_rn(2.0, u_a)), 1.0);  // nmc.py:87
                 const int nw = (v > 0.0) - (v < 0.0);
