@@ -32,8 +32,7 @@ struct nlmc_msc {
     int ladder_offset = 0;        // global index of this handle's first ladder (multiple of 128)
     long long n_bonds = 0;
     uint32_t *S = nullptr;        // [n][W]
-    int32_t *nbr = nullptr;       // [n][6]  (-1 = padding)
-    uint32_t *meta = nullptr;     // [n] bit d: J_{i,nbr d} < 0
+    int32_t *rec = nullptr;       // [n][8] site record: 6 neighbours (-1 = padding), sign bits (bit d: J_{i,nbr d} < 0), 0
     int32_t *site_list = nullptr; // [n] sites sorted by colour
     std::vector<int> colour_ptr;  // [n_colours+1]
     uint32_t *thr = nullptr;      // [n_beta][4] thresholds of |f| = 0,2,4,6
@@ -82,12 +81,16 @@ struct Philox {
 struct MscDev {
     int n, W, G, n_beta, quad_offset;  // quad_offset = ladder_offset / 128: global index of ladder quad 0
     uint32_t *S;
-    const int32_t *nbr;
-    const uint32_t *meta;
+    const int4 *rec;      // [n][2]: {nbr0..3}, {nbr4, nbr5, sign bits, 0} -- two 16-byte loads per site
+    uint32_t g_magic;     // ceil(2^32 / G): word / G == __umulhi(word, g_magic) for word * G < 2^32 (0: divide)
     const int32_t *site_list;
     const uint32_t *thr;
     uint32_t seed_lo, seed_hi;
 };
+
+__device__ __forceinline__ int beta_index(const MscDev &a, int word0) {
+    return a.g_magic ? (int)__umulhi((uint32_t)word0, a.g_magic) : word0 / a.G;
+}
 
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
 
@@ -127,19 +130,20 @@ __device__ __forceinline__ uint32_t comp(const uint4 &v, int k) { return k == 0 
 template <int kSteps>
 __global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int n_sites, const uint32_t *__restrict__ counters) {
     const uint32_t sweep = counters[0];
-    const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);  // site of this colour
     const int lane = threadIdx.x & 31;
-    const int chunks = (a.W + 127) >> 7;
-    if (warp >= n_sites * chunks) return;
-    const int site = __ldg(a.site_list + first + warp / chunks);
-    const int word0 = (warp % chunks) * 128 + lane * 4;
+    if (warp >= n_sites) return;
+    const int site = __ldg(a.site_list + first + warp);
+    const int word0 = (int)blockIdx.y * 128 + lane * 4;  // grid.y = 128-word chunks of the row
     if (word0 >= a.W) return;
 
-    const uint32_t meta = __ldg(a.meta + site);
+    const int4 r0 = __ldg(a.rec + (size_t)site * 2), r1 = __ldg(a.rec + (size_t)site * 2 + 1);
+    const int nb[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+    const uint32_t meta = (uint32_t)r1.z;
     uint4 x[6];
 #pragma unroll
     for (int d = 0; d < 6; ++d) {
-        const int j = __ldg(a.nbr + (size_t)site * 6 + d);
+        const int j = nb[d];
         if (j >= 0) {
             x[d] = *reinterpret_cast<const uint4 *>(a.S + (size_t)j * a.W + word0);
             if ((meta >> d) & 1u) { x[d].x = ~x[d].x; x[d].y = ~x[d].y; x[d].z = ~x[d].z; x[d].w = ~x[d].w; }
@@ -161,8 +165,9 @@ __global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int
         I3[k] = m1 & m0;
         pos[k] = c2;
     }
-    const int b = word0 / a.G;  // the four words of a lane share one beta (G % 4 == 0)
-    const uint32_t T1 = __ldg(a.thr + b * 4 + 1), T2 = __ldg(a.thr + b * 4 + 2), T3 = __ldg(a.thr + b * 4 + 3);
+    const int b = beta_index(a, word0);  // the four words of a lane share one beta (G % 4 == 0)
+    const uint4 thr4 = __ldg(reinterpret_cast<const uint4 *>(a.thr) + b);
+    const uint32_t T1 = thr4.y, T2 = thr4.z, T3 = thr4.w;
     const Philox rng{a.seed_lo, a.seed_hi ^ kTagSweep};
     // stream id = (beta index, GLOBAL ladder quad): independent of how ladders are sharded over handles/GPUs
     const uint32_t sid = ((uint32_t)b << 20) | (uint32_t)(a.quad_offset + ((word0 - b * a.G) >> 2));
@@ -255,12 +260,14 @@ __global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_ac
         for (int bb = 0; bb < 10; ++bb) v[k][bb] = 0u;
     for (int s = s_begin; s < s_end; ++s) {
         const int site = __ldg(a.site_list + s);
-        const uint32_t meta = __ldg(a.meta + site);
+        const int4 r0 = __ldg(a.rec + (size_t)site * 2), r1 = __ldg(a.rec + (size_t)site * 2 + 1);
+        const int nb[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+        const uint32_t meta = (uint32_t)r1.z;
         const uint4 own = *reinterpret_cast<const uint4 *>(a.S + (size_t)site * a.W + word0);
         uint4 x[6];
 #pragma unroll
         for (int d = 0; d < 6; ++d) {
-            const int j = __ldg(a.nbr + (size_t)site * 6 + d);
+            const int j = nb[d];
             if (j >= 0) {
                 x[d] = *reinterpret_cast<const uint4 *>(a.S + (size_t)j * a.W + word0);
                 const uint32_t neg = ((meta >> d) & 1u) ? 0xffffffffu : 0u;
@@ -413,7 +420,9 @@ static std::vector<uint32_t> msc_thresholds(int n_beta, const double *betas) {
 static MscDev dev_view(const nlmc_msc *M) {
     MscDev d;
     d.n = M->n; d.W = M->W; d.G = M->G; d.n_beta = M->n_beta; d.quad_offset = M->ladder_offset / 128;
-    d.S = M->S; d.nbr = M->nbr; d.meta = M->meta; d.site_list = M->site_list; d.thr = M->thr;
+    d.S = M->S; d.rec = reinterpret_cast<const int4 *>(M->rec); d.site_list = M->site_list; d.thr = M->thr;
+    d.g_magic = ((unsigned long long)M->W * (unsigned long long)M->G < (1ull << 32))
+                    ? (uint32_t)(((1ull << 32) + (unsigned long long)M->G - 1) / (unsigned long long)M->G) : 0u;
     d.seed_lo = (uint32_t)M->seed; d.seed_hi = (uint32_t)(M->seed >> 32);
     return d;
 }
@@ -425,8 +434,7 @@ static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
         for (int c = 0; c < M->n_colours; ++c) {
             const int first = M->colour_ptr[c], cnt = M->colour_ptr[c + 1] - first;
             if (cnt == 0) continue;
-            const long long warps = (long long)cnt * chunks;
-            const unsigned blocks = (unsigned)((warps + 7) / 8);
+            const dim3 blocks((unsigned)((cnt + 7) / 8), (unsigned)chunks);
             switch (M->k_steps) {
                 case 3: msc_sweep_kernel<3><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
                 case 4: msc_sweep_kernel<4><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
@@ -532,7 +540,7 @@ int nlmc_msc_destroy(nlmc_msc *M) {
     if (!M) return NLMC_OK;
     cudaSetDevice(M->inst->device);
     nlmc::drop_graphs(M);
-    void *ptrs[] = {M->S, M->nbr, M->meta, M->site_list, M->thr, M->betas, M->E_acc, M->E, M->swapmask, M->accepted,
+    void *ptrs[] = {M->S, M->rec, M->site_list, M->thr, M->betas, M->E_acc, M->E, M->swapmask, M->accepted,
                     M->scratch_spins, M->d_counters};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (M->ev0) cudaEventDestroy(M->ev0);
@@ -631,12 +639,16 @@ int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_lad
     if (const char *e = getenv("NLMC_MSC_STEPS")) M->k_steps = atoi(e);
     if (const char *e = getenv("NLMC_MSC_GRAPHS")) M->use_graphs = atoi(e) != 0;
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(n_beta, betas);
+    std::vector<int32_t> rec((size_t)n * 8, 0);  // site records: 6 neighbours, sign bits, 0
+    for (int i = 0; i < n; ++i) {
+        for (int d = 0; d < 6; ++d) rec[(size_t)i * 8 + d] = nbr[(size_t)i * 6 + d];
+        rec[(size_t)i * 8 + 6] = (int32_t)meta[(size_t)i];
+    }
     const size_t words = (size_t)n * M->W;
     bool ok = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&M->ev0) == cudaSuccess && cudaEventCreate(&M->ev1) == cudaSuccess &&
               cudaMalloc(&M->S, sizeof(uint32_t) * words) == cudaSuccess &&
-              cudaMalloc(&M->nbr, sizeof(int32_t) * (size_t)n * 6) == cudaSuccess &&
-              cudaMalloc(&M->meta, sizeof(uint32_t) * (size_t)n) == cudaSuccess &&
+              cudaMalloc(&M->rec, sizeof(int32_t) * (size_t)n * 8) == cudaSuccess &&
               cudaMalloc(&M->site_list, sizeof(int32_t) * (size_t)n) == cudaSuccess &&
               cudaMalloc(&M->thr, sizeof(uint32_t) * thr.size()) == cudaSuccess &&
               cudaMalloc(&M->betas, sizeof(double) * (size_t)n_beta) == cudaSuccess &&
@@ -647,8 +659,7 @@ int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_lad
               cudaMalloc(&M->d_counters, 2 * sizeof(uint32_t)) == cudaSuccess &&
               cudaMemset(M->d_counters, 0, 2 * sizeof(uint32_t)) == cudaSuccess &&
               cudaMalloc(&M->scratch_spins, (size_t)n) == cudaSuccess &&
-              cudaMemcpy(M->nbr, nbr.data(), sizeof(int32_t) * nbr.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMemcpy(M->meta, meta.data(), sizeof(uint32_t) * meta.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(M->rec, rec.data(), sizeof(int32_t) * rec.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(M->site_list, site_list.data(), sizeof(int32_t) * site_list.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(M->thr, thr.data(), sizeof(uint32_t) * thr.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(M->betas, betas, sizeof(double) * (size_t)n_beta, cudaMemcpyHostToDevice) == cudaSuccess &&
