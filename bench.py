@@ -285,6 +285,20 @@ def run_ours(args, rank, world, local_rank):
                        "note": "bit-packed layout: 0.25 B/attempt compulsory traffic; the kernel is ALU/issue bound "
                                "(Philox + bit-sliced logic), not HBM bound"}
 
+    # what actually bounds the kernel: warp-instruction issue (integer pipes).  The instruction count per launch is a
+    # property of the code (ncu smsp__inst_executed.sum of the committed capture); the launch duration is measured here.
+    roofline_issue = None
+    if traffic and traffic.get("warp_instructions_per_launch") and traffic.get("attempts_per_launch") == attempts_per_launch:
+        props = torch.cuda.get_device_properties(device)
+        sm_clock_hz = 1e6 * (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965.0)
+        issue_peak = props.multi_processor_count * 4 * sm_clock_hz          # one warp instruction per scheduler and clock
+        achieved = traffic["warp_instructions_per_launch"] / (sweep_ms * 1e-3)
+        roofline_issue = {"bound": "issue", "achieved": achieved / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-inst/s",
+                          "frac": achieved / issue_peak,
+                          "warp_instructions_per_attempt": traffic["warp_instructions_per_launch"] / attempts_per_launch,
+                          "note": "SMs x 4 schedulers x SM clock under load; instruction count from the committed ncu capture "
+                                  "(profiles/traffic.json), duration measured live"}
+
     # ---- end to end through the host-buffer entry point -------------------------------------------
     # Every step ships one batch of packed states from pinned host memory to the device, runs the round and
     # ships states + energies back.  NH handles are used in turn (nlmc_msc_round_host_async + nlmc_msc_sync), so
@@ -354,7 +368,7 @@ def run_ours(args, rank, world, local_rank):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "u32", "dtype_note": "bit planes: 1 bit per spin, 32 ladders per 32-bit word", "data": "synthetic",
-               "config": workload_config(args, world), "roofline": roofline, "roofline_packed": roofline_packed,
+               "config": workload_config(args, world), "roofline": roofline, "roofline_packed": roofline_packed, "roofline_issue": roofline_issue,
                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                "per_gpu_value": value / world, "ps_per_attempt": 1e12 / (value / world)}
         print(json.dumps(out), flush=True)

@@ -32,7 +32,8 @@ struct nlmc_msc {
     int ladder_offset = 0;        // global index of this handle's first ladder (multiple of 128)
     long long n_bonds = 0;
     uint32_t *S = nullptr;        // [n][W]
-    int32_t *rec = nullptr;       // [n][8] site record: 6 neighbours (-1 = padding), sign bits (bit d: J_{i,nbr d} < 0), 0
+    int32_t *rec = nullptr;       // [n][8] record of the site at position p of site_list (sites sorted by colour):
+                                  // 6 neighbours (-1 = padding), sign bits (bit d: J_{i,nbr d} < 0), site index
     int32_t *site_list = nullptr; // [n] sites sorted by colour
     std::vector<int> colour_ptr;  // [n_colours+1]
     uint32_t *thr = nullptr;      // [n_beta][4] thresholds of |f| = 0,2,4,6
@@ -81,7 +82,8 @@ struct Philox {
 struct MscDev {
     int n, W, G, n_beta, quad_offset;  // quad_offset = ladder_offset / 128: global index of ladder quad 0
     uint32_t *S;
-    const int4 *rec;      // [n][2]: {nbr0..3}, {nbr4, nbr5, sign bits, 0} -- two 16-byte loads per site
+    const int4 *rec;      // [n][2] by position in site_list: {nbr0..3}, {nbr4, nbr5, sign bits, site} -- two 16-byte
+                          // loads replace the chain site_list -> neighbour table -> sign bits
     uint32_t g_magic;     // ceil(2^32 / G): word / G == __umulhi(word, g_magic) for word * G < 2^32 (0: divide)
     const int32_t *site_list;
     const uint32_t *thr;
@@ -133,13 +135,13 @@ __global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);  // site of this colour
     const int lane = threadIdx.x & 31;
     if (warp >= n_sites) return;
-    const int site = __ldg(a.site_list + first + warp);
     const int word0 = (int)blockIdx.y * 128 + lane * 4;  // grid.y = 128-word chunks of the row
     if (word0 >= a.W) return;
 
-    const int4 r0 = __ldg(a.rec + (size_t)site * 2), r1 = __ldg(a.rec + (size_t)site * 2 + 1);
+    const int4 r0 = __ldg(a.rec + (size_t)(first + warp) * 2), r1 = __ldg(a.rec + (size_t)(first + warp) * 2 + 1);
     const int nb[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
     const uint32_t meta = (uint32_t)r1.z;
+    const int site = r1.w;
     uint4 x[6];
 #pragma unroll
     for (int d = 0; d < 6; ++d) {
@@ -259,10 +261,10 @@ __global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_ac
 #pragma unroll
         for (int bb = 0; bb < 10; ++bb) v[k][bb] = 0u;
     for (int s = s_begin; s < s_end; ++s) {
-        const int site = __ldg(a.site_list + s);
-        const int4 r0 = __ldg(a.rec + (size_t)site * 2), r1 = __ldg(a.rec + (size_t)site * 2 + 1);
+        const int4 r0 = __ldg(a.rec + (size_t)s * 2), r1 = __ldg(a.rec + (size_t)s * 2 + 1);
         const int nb[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
         const uint32_t meta = (uint32_t)r1.z;
+        const int site = r1.w;
         const uint4 own = *reinterpret_cast<const uint4 *>(a.S + (size_t)site * a.W + word0);
         uint4 x[6];
 #pragma unroll
@@ -639,10 +641,12 @@ int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_lad
     if (const char *e = getenv("NLMC_MSC_STEPS")) M->k_steps = atoi(e);
     if (const char *e = getenv("NLMC_MSC_GRAPHS")) M->use_graphs = atoi(e) != 0;
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(n_beta, betas);
-    std::vector<int32_t> rec((size_t)n * 8, 0);  // site records: 6 neighbours, sign bits, 0
-    for (int i = 0; i < n; ++i) {
-        for (int d = 0; d < 6; ++d) rec[(size_t)i * 8 + d] = nbr[(size_t)i * 6 + d];
-        rec[(size_t)i * 8 + 6] = (int32_t)meta[(size_t)i];
+    std::vector<int32_t> rec((size_t)n * 8, 0);  // records in site_list order: 6 neighbours, sign bits, site
+    for (int p = 0; p < n; ++p) {
+        const int i = site_list[(size_t)p];
+        for (int d = 0; d < 6; ++d) rec[(size_t)p * 8 + d] = nbr[(size_t)i * 6 + d];
+        rec[(size_t)p * 8 + 6] = (int32_t)meta[(size_t)i];
+        rec[(size_t)p * 8 + 7] = i;
     }
     const size_t words = (size_t)n * M->W;
     bool ok = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking) == cudaSuccess &&
