@@ -130,7 +130,7 @@ __device__ __forceinline__ uint32_t comp(const uint4 &v, int k) { return k == 0 
 // (exactly the conditional probability).  ncu on the first version (early-exit loop) showed the kernel
 // ALU-pipe bound with 29% of the lanes idle in the loop tail; see profiles/.
 template <int kSteps>
-__global__ void __launch_bounds__(256) msc_sweep_kernel(MscDev a, int first, int n_sites, const uint32_t *__restrict__ counters) {
+__global__ void __launch_bounds__(256, 5) msc_sweep_kernel(MscDev a, int first, int n_sites, const uint32_t *__restrict__ counters) {
     const uint32_t sweep = counters[0];
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);  // site of this colour
     const int lane = threadIdx.x & 31;
