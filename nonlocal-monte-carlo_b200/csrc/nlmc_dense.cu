@@ -335,7 +335,9 @@ struct PhiloxD {
 //   2. the 8 flips are propagated to the fields of the later sites of the block, lane t taking the sites
 //      k' = 8m + t (conflict-free reads of the transposed J_bb, 8 FMAs each).
 constexpr int kRepPerCta = 16;
-constexpr size_t kUpdateSmem = sizeof(float) * ((size_t)kBlk * kBlk + (size_t)kRepPerCta * kBlk) + (size_t)kRepPerCta * kBlk;
+constexpr int kFldStride = kBlk + 8;    // floats per replica row: the 4 replicas of a warp fall into disjoint bank groups
+constexpr int kSpinStride = kBlk + 32;  // bytes per replica row, same reason
+constexpr size_t kUpdateSmem = sizeof(float) * ((size_t)kBlk * kBlk + (size_t)kRepPerCta * kFldStride) + (size_t)kRepPerCta * kSpinStride;
 
 __global__ void __launch_bounds__(128) dense_block_update_kernel(int n, int n_pad, int R_pad, int c0, const float *__restrict__ Ht,
                                                                  const float *__restrict__ Jf, const float *__restrict__ hf,
@@ -347,33 +349,53 @@ __global__ void __launch_bounds__(128) dense_block_update_kernel(int n, int n_pa
     const uint32_t sweep = *sweep_ptr;
     float *Jt = reinterpret_cast<float *>(dsm);                        // [kBlk j][kBlk k] = J[c0+k][c0+j] (transposed)
     float *fld = Jt + (size_t)kBlk * kBlk;                             // [kRepPerCta][kBlk]   running fields
-    int8_t *spin = reinterpret_cast<int8_t *>(fld + (size_t)kRepPerCta * kBlk);  // [kRepPerCta][kBlk]
+    int8_t *spin = reinterpret_cast<int8_t *>(fld + (size_t)kRepPerCta * kFldStride);  // [kRepPerCta][kSpinStride]
     const int tid = threadIdx.x;
     const int rep = tid >> 3, t = tid & 7;     // replica within the CTA, lane within the replica's group
     const int r0 = blockIdx.x * kRepPerCta;
     const int r = r0 + rep;
     // stage J_bb transposed, Jt[j][k] = J[c0+k][c0+j], from the transposed copy of J kept in global memory
     // (JfT[a][b] = J[b][a]): coalesced float4 reads, conflict-free float4 writes
+    // asynchronous 16-byte copies (no register staging): all 64 KB are in flight at once and overlap the field/spin
+    // loads below; ncu showed 40 % of this kernel's time in the prologue's load latency
     for (int i = tid; i < kBlk * kBlk / 4; i += 128) {
         const int j = i / (kBlk / 4), k4 = i % (kBlk / 4);
-        reinterpret_cast<float4 *>(Jt)[i] = *reinterpret_cast<const float4 *>(Jf + (size_t)(c0 + j) * n_pad + c0 + k4 * 4);
+        const uint32_t dst = smem_u32(reinterpret_cast<float4 *>(Jt) + i);
+        const float *src = Jf + (size_t)(c0 + j) * n_pad + c0 + k4 * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
-    for (int i = tid; i < kRepPerCta * kBlk; i += 128) {
-        const int k = i / kRepPerCta, rr = i % kRepPerCta;  // consecutive threads -> consecutive replicas (coalesced Ht row)
-        fld[rr * kBlk + k] = Ht[(size_t)(c0 + k) * R_pad + r0 + rr] + hf[c0 + k];
-        const uint16_t b16 = S[(size_t)(r0 + rr) * n_pad + c0 + k];
-        spin[rr * kBlk + k] = (b16 == 0) ? 0 : ((b16 & 0x8000u) ? -1 : 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    {   // all 16 field / spin loads of a thread are issued before the first use (one exposed round trip, not 16)
+        constexpr int kPer = kRepPerCta * kBlk / 128;
+        float hv[kPer], fv[kPer];
+        uint16_t sv[kPer];
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const int i = tid + q * 128;
+            const int k = i / kRepPerCta, rr = i % kRepPerCta;  // consecutive threads -> consecutive replicas (coalesced Ht row)
+            hv[q] = Ht[(size_t)(c0 + k) * R_pad + r0 + rr];
+            fv[q] = hf[c0 + k];
+            sv[q] = S[(size_t)(r0 + rr) * n_pad + c0 + k];
+        }
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const int i = tid + q * 128;
+            const int k = i / kRepPerCta, rr = i % kRepPerCta;
+            fld[rr * kFldStride + k] = hv[q] + fv[q];
+            spin[rr * kSpinStride + k] = (sv[q] == 0) ? 0 : ((sv[q] & 0x8000u) ? -1 : 1);
+        }
     }
     // the next block's split-K GEMM accumulates with atomics: clear its field rows for this CTA's replicas
     if (Ht_zero != nullptr)
         for (int i = tid; i < kRepPerCta * kBlk; i += 128) Ht_zero[(size_t)(i / kRepPerCta) * R_pad + r0 + (i % kRepPerCta)] = 0.f;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     const float inv2b = 0.5f / beta[r];
     const uint8_t *mrow = modes ? modes + (size_t)r * n_pad + c0 : nullptr;
     const PhiloxD rng{seed_lo, seed_hi ^ 0x44454e53u};
     const int k_end = min(kBlk, n - c0);
-    float *frow = fld + rep * kBlk;
-    int8_t *srow = spin + rep * kBlk;
+    float *frow = fld + rep * kFldStride;
+    int8_t *srow = spin + rep * kSpinStride;
     for (int base = 0; base < k_end; base += 8) {
         // ---- 1. the sub-block, sequentially, in registers (identical in the 8 lanes of the replica).
         // up  <=>  u < 1/(1+exp(-2 beta f))  <=>  f > logit(u)/(2 beta) =: theta, which depends on the random
@@ -442,7 +464,7 @@ __global__ void __launch_bounds__(128) dense_block_update_kernel(int n, int n_pa
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
                 const int k = seg + e + h2;
-                const int sv = k < k_end ? spin[rep * kBlk + k] : 0;
+                const int sv = k < k_end ? spin[rep * kSpinStride + k] : 0;
                 pair |= (sv > 0 ? 0x3F80u : (sv < 0 ? 0xBF80u : 0u)) << (16 * h2);
             }
             w[e >> 1] = pair;
