@@ -445,11 +445,14 @@ __global__ void __launch_bounds__(128) dense_block_update_kernel(int n, int n_pa
                 if (base + i < k_end) srow[base + i] = (int8_t)(((newbits >> i) & 1u) ? 1 : -1);
         }
         // ---- 2. propagate the 8 flips to the later sites of the block: lane t owns k' = 8m + t
-        for (int kp = base + 8 + t; kp < k_end; kp += 8) {
-            float a = frow[kp];
+        for (int kp = base + 8 + t; kp < k_end; kp += 8) {  // two independent FMA chains: half the dependent latency
+            float a = frow[kp], b = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a = fmaf(Jt[(base + j) * kBlk + kp], d[j], a);
-            frow[kp] = a;
+            for (int j = 0; j < 4; ++j) {
+                a = fmaf(Jt[(base + j) * kBlk + kp], d[j], a);
+                b = fmaf(Jt[(base + 4 + j) * kBlk + kp], d[4 + j], b);
+            }
+            frow[kp] = a + b;
         }
         __syncwarp();
     }
