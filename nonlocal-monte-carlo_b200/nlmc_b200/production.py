@@ -289,17 +289,38 @@ def nmc_subroutine_production(obj, prob, m_star, phase_sweeps, kw, variant, all_
 
 def apt_preprocessor_chains_production(prob, reps, iter, saved_state, beta, num_sweeps_MCMC, num_sweeps_read,
                                        num_rng):
-    """One beta iteration of APT_preprocessor.run (NPT/apt_preprocessor.py:158-179): num_rng independent
-    chains in the bit lanes, warm-started from the previous beta's final states (kept on the device)."""
+    """One beta iteration of APT_preprocessor.run (NPT/apt_preprocessor.py:158-179): num_rng independent chains,
+    warm-started from the previous beta's final states (kept on the device).  +-J lattices ride in the bit lanes (K2);
+    every other instance (real-valued J, fields, any degree) runs one chain per row of the generic engine (K2a / K3)."""
+    burn = max(0, num_sweeps_MCMC - num_sweeps_read)
+    n_read = min(num_sweeps_read, num_sweeps_MCMC)
+    if not _msc_eligible(prob):
+        state = getattr(prob, "_prep_gen", None)
+        if state is None or state.R != num_rng:
+            state = _generic_engine(prob, np.full(num_rng, float(beta)), _seed_from_numpy())
+            state.set_spins(np.sign(2. * np.random.rand(num_rng, prob.n) - 1).astype(np.int8))  # apt_preprocessor.py:164
+            prob._prep_gen = state
+        else:
+            state.set_betas(np.full(num_rng, float(beta)))
+        if burn:
+            state.sweep(burn)
+        if n_read == 0:
+            return np.zeros((num_rng, 0)), saved_state
+        if hasattr(state, "sweep_record"):  # K2a: per-sweep energies recorded inside the launch
+            _, E = state.sweep_record(n_read, want_states=False, want_energies=True)
+            return np.ascontiguousarray(E.T), saved_state
+        Energy = np.empty((num_rng, n_read))
+        for j in range(n_read):
+            state.sweep(1)
+            Energy[:, j] = state.energies()
+        return Energy, saved_state
     state = getattr(prob, "_prep_msc", None)
     if state is None or state.n_ladders_requested != num_rng:
         state = _require_msc(prob, [beta], num_rng, _seed_from_numpy())  # random start, as in iteration 1
         prob._prep_msc = state
     else:
         state.set_betas([beta])
-    burn = max(0, num_sweeps_MCMC - num_sweeps_read)
     state.sweep(burn)
-    n_read = min(num_sweeps_read, num_sweeps_MCMC)
     _, Erec = state.sweep_record(n_read, ladder=None, energies=True)  # [n_read][1][ladders], recorded on the device
     Energy = np.ascontiguousarray(Erec[:, 0, :num_rng].T) if n_read else np.zeros((num_rng, 0))
     return Energy, saved_state

@@ -38,3 +38,58 @@ def test_known_answer_energy_conventions(ttt):
     s = (2 * g["gs_bits"].astype(np.int8) - 1)[None, :]
     E = prob.inst.energy_states(s)[0]          # K4 on the shipped ground-state bit string
     assert abs(E - target) < 1e-6
+
+
+def test_reference_example_flow_on_chimera_droplet(ttt, tmp_cwd):
+    """The flow of NPT/examples/chimera_example.py through the drop-in classes in production mode: parse the instance,
+    adaptive ladder from APT_preprocessor, then NPT with NMC on the five coldest replicas -- the shipped ground-state
+    energy is a lower bound that the cold replicas approach (within 10 % after these shortened runs; `Energy` is the
+    minimum over the first sweeps of the last round only, npt.py:682-690) and the side-effect files appear."""
+    import os
+    import tempfile
+    from nlmc_b200 import APT_preprocessor, NPT, instances
+    g = np.load(os.path.join(ROOT, "tests", "golden", "known_answer_chimera128.npz"))
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        f.write(str(g["instance_text"]))
+    J, h = instances.read_chimera_droplet(f.name)          # J = -J_file, h = -h_file (chimera_example.py:49-50)
+    os.unlink(f.name)
+    np.random.seed(11)
+    apt_prep = APT_preprocessor(J.copy(), h.copy(), mode="production")
+    beta, sigma = apt_prep.run(num_sweeps_MCMC=300, num_sweeps_read=300, num_rng=64, beta_start=0.5, alpha=1.25,
+                               sigma_E_val=1000, beta_max=64, use_hash_table=0, num_cores=8)
+    beta_list = np.array(beta)
+    assert 5 < len(beta_list) < 200 and np.all(np.diff(beta_list) > 0) and len(sigma) in (len(beta), len(beta) - 1)
+    assert os.path.exists("beta_list_python.npy")
+    R = len(beta_list)
+    npt = NPT(J.toarray(), h, mode="production")
+    M, Energy = npt.run(beta_list=beta_list, num_replicas=R, doNMC=[False] * (R - 5) + [True] * 5,
+                        num_sweeps_MCMC=2000, num_sweeps_read=100, num_swap_attempts=10,
+                        num_swapping_pairs=round(0.3 * R), num_cycles=10, full_update_frequency=1, M_skip=1, temp_x=20,
+                        global_beta=1 / 0.366838 * 5, lambda_start=3, lambda_end=0.01, lambda_reduction_factor=0.9,
+                        threshold_initial=0.9999999, threshold_cutoff=0.999999, max_iterations=100,
+                        tolerance=np.finfo(float).eps, use_hash_table=False, num_cores=8)
+    n = J.shape[0]
+    assert M.shape == (R * n, 200) and Energy.shape == (R,)
+    norm = abs(J).max()                                   # run() normalises by max |J| (npt.py:588-590)
+    gs = float(g["gs_energy"]) / norm
+    assert Energy.min() >= gs - 1e-6                      # nothing below the true ground state
+    assert Energy.min() <= gs * 0.9                       # gs < 0: within 10 % of it
+
+
+def test_preprocessor_production_matches_replay_on_real_couplings(ttt, tmp_cwd):
+    """sigma_E(beta) is a property of the Boltzmann distribution: on an instance with real couplings and fields (generic
+    production engine, not the bit-packed one) the production ladder follows the exact-replay ladder within the
+    statistical error of 64 chains x 300 sweeps."""
+    from nlmc_b200 import APT_preprocessor
+    Jn, hn, _, _, _ = ttt.load("chimera128")
+    out = {}
+    for mode in ("replay", "production"):
+        np.random.seed(5)
+        obj = APT_preprocessor(Jn.copy(), hn.copy(), mode=mode)
+        out[mode] = obj.run(num_sweeps_MCMC=300, num_sweeps_read=300, num_rng=64, beta_start=0.5, alpha=1.25,
+                            sigma_E_val=1000, beta_max=3.0, use_hash_table=0, num_cores=1)
+    (b_r, s_r), (b_p, s_p) = out["replay"], out["production"]
+    k = min(len(s_r), len(s_p), 4)
+    assert k >= 3
+    np.testing.assert_allclose(s_p[:k], s_r[:k], rtol=0.15)
+    np.testing.assert_allclose(b_p[:k], b_r[:k], rtol=0.15)
