@@ -42,6 +42,11 @@ def _msc_eligible(prob: host.Problem) -> bool:
     return bool(np.all(deg <= 6) and np.all(deg % 2 == 0))
 
 
+def _engine_energies_exact(prob: host.Problem) -> bool:
+    """Integer couplings and fields: the engines' fixed-point / fp32 energies are exact, no fp64 recomputation needed."""
+    return bool(prob.is_integer and np.all(prob.h == np.round(prob.h)))
+
+
 def npt_run_production(obj, beta_list, nmc_kw):
     """NPT.run (NPT/npt.py:535-700) in production mode.  +-J lattices without NMC replicas take the bit-packed
     path; everything else (real-valued or dense J, fields, doNMC replicas) takes the dense tensor-core path."""
@@ -172,6 +177,10 @@ def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True, all_cl
     for g in range(G):
         Mo = np.array(cols[g], dtype=np.float64).T if cols[g] else np.zeros((n, 0))
         Eo = np.array(ens[g], dtype=np.float64)
+        if cols[g] and not _engine_energies_exact(prob):
+            # the engines' own energies are fixed-point (K2a) or fp32 (K3): good enough to steer the run, but the
+            # RETURNED energies are those of the returned states in fp64 (kernel K4), as the reference's are
+            Eo = prob.inst.energy_states(np.array(cols[g], dtype=np.int8))
         out.append((Mo, Eo, clusters[g] if clusters else np.array([], dtype=int)))
     return out
 
@@ -199,6 +208,8 @@ def _npt_run_dense(obj, prob, beta_list, nmc_kw):
             d_mc.set_spins(state[mc_ids])
             if last and hasattr(d_mc, "sweep_record"):
                 states, E = d_mc.sweep_record(spm, record_every=1)
+                if not _engine_energies_exact(prob):  # returned energies in fp64 from the returned states (K4)
+                    E = prob.inst.energy_states(states.reshape(-1, n)).reshape(spm, len(mc_ids))
                 for g, r in enumerate(mc_ids):
                     M[r * n:(r + 1) * n, :] = states[:, g].T
                     E_cols[r] = E[:, g]
@@ -207,6 +218,8 @@ def _npt_run_dense(obj, prob, beta_list, nmc_kw):
                     d_mc.sweep(1)
                     E = d_mc.energies()
                     S = d_mc.get_spins()
+                    if not _engine_energies_exact(prob):
+                        E = prob.inst.energy_states(S)
                     for g, r in enumerate(mc_ids):
                         M[r * n:(r + 1) * n, j] = S[g]
                         E_cols[r, j] = E[g]

@@ -93,3 +93,32 @@ def test_preprocessor_production_matches_replay_on_real_couplings(ttt, tmp_cwd):
     assert k >= 3
     np.testing.assert_allclose(s_p[:k], s_r[:k], rtol=0.15)
     np.testing.assert_allclose(b_p[:k], b_r[:k], rtol=0.15)
+
+
+@pytest.mark.parametrize("mode", ["production", "replay"])
+def test_nmc_example_flow_on_dcl(ttt, tmp_cwd, mode):
+    """NMC/examples/DCL_example.py through the drop-in NMC (sweeps reduced): dense J from the parser, positional
+    arguments as in the example, energies consistent with the returned states and bounded by the planted minimum."""
+    import os
+    import tempfile
+    from nlmc_b200 import NMC, instances
+    from oracle import oracle as O
+    g = np.load(os.path.join(ROOT, "tests", "golden", "known_answer_dcl_c8.npz"))
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        f.write(str(g["instance_text"]))
+    J, h = instances.read_dcl(f.name)                     # J = -J_file (DCL_example.py:52-53)
+    os.unlink(f.name)
+    np.random.seed(3)
+    sweeps = 300 if mode == "production" else 60
+    nmc = NMC(J.toarray(), h, mode=mode)
+    M, E, min_energy = nmc.run(sweeps, sweeps, 2, 1, 1, 20, 3, 3, 0.01, 0.9, 0.9999999, 0.999999, 100,
+                               np.finfo(float).eps, use_hash_table=False)
+    n = J.shape[0]
+    assert M.shape == (n, 2 * 3 * sweeps) and E.shape == (2 * 3 * sweeps,) and min_energy == E.min()
+    csr = O.Csr(J)
+    cols = [0, len(E) // 2, len(E) - 1]
+    np.testing.assert_allclose(E[cols], O.energy(csr, np.zeros(n), M[:, cols].T.astype(np.int8)), rtol=1e-9)
+    target = float(g["min_energy"])
+    assert min_energy >= target - 0.01                    # the file rounds 1/7: its optimum is 0.00175 below the stated one
+    if mode == "production":
+        assert min_energy <= 0.9 * target
