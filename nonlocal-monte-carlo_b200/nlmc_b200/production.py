@@ -122,9 +122,11 @@ def _backbones(prob, states, global_beta, nmc_kw):
     return out
 
 
-def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True, all_clusters=None):
-    """NMC_subroutine (NMC/nmc.py:320-440 / NPT/npt.py:357-477) for all rows of the dense handle `d` in lock
-    step.  Returns (M_overall [n][cols] of row 0 per row?, ...) -- see callers; rows are independent chains."""
+def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True, all_clusters=None, keep_states=True):
+    """NMC_subroutine (NMC/nmc.py:320-440 / NPT/npt.py:357-477) for all rows of the engine handle `d` in lock step;
+    rows are independent chains.  Returns per row (M_overall [n][cols], energy_overall [cols], clusters).  With
+    keep_states=False only the energies are recorded and M_overall holds the final state as its single column (the
+    rounds of NPT.run before the last one need nothing else)."""
     G, n = d.R, prob.n
     num_cycles, phase = nmc_kw["num_cycles"], nmc_kw["phase_sweeps"]
     fuf, M_skip, temp_x = nmc_kw["full_update_frequency"], nmc_kw["M_skip"], nmc_kw["temp_x"]
@@ -140,9 +142,10 @@ def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True, all_cl
         d.set_site_modes(modes, temp_x)
         d.best_reset()
         if hasattr(d, "sweep_record"):  # K2a: the whole phase is one launch, recording and argmin on the device
-            states, E = d.sweep_record(phase, record_every=M_skip, track_best=True)
+            states, E = d.sweep_record(phase, record_every=M_skip, track_best=True, want_states=keep_states)
             for g in range(G):
-                cols[g].extend(states[:, g])
+                if keep_states:
+                    cols[g].extend(states[:, g])
                 ens[g].extend(E[::M_skip, g])
             m_init, _ = d.best_get()
             return
@@ -150,9 +153,10 @@ def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True, all_cl
             d.sweep(1)
             E = d.best_update()
             if j % M_skip == 0:
-                S = d.get_spins()
+                S = d.get_spins() if keep_states else None
                 for g in range(G):
-                    cols[g].append(S[g].copy())
+                    if keep_states:
+                        cols[g].append(S[g].copy())
                     ens[g].append(E[g])
         m_init, _ = d.best_get()  # m_init = M[:, argmin E], first minimum wins (nmc.py:394-395)
 
@@ -174,7 +178,12 @@ def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True, all_cl
                 m_star = m_init.copy()
     d.set_site_modes(None)
     out = []
+    final = None if keep_states else d.get_spins()
     for g in range(G):
+        if not keep_states:
+            out.append((final[g].astype(np.float64)[:, None], np.array(ens[g], dtype=np.float64),
+                        clusters[g] if clusters else np.array([], dtype=int)))
+            continue
         Mo = np.array(cols[g], dtype=np.float64).T if cols[g] else np.zeros((n, 0))
         Eo = np.array(ens[g], dtype=np.float64)
         if cols[g] and not _engine_energies_exact(prob):
@@ -210,9 +219,8 @@ def _npt_run_dense(obj, prob, beta_list, nmc_kw):
                 states, E = d_mc.sweep_record(spm, record_every=1)
                 if not _engine_energies_exact(prob):  # returned energies in fp64 from the returned states (K4)
                     E = prob.inst.energy_states(states.reshape(-1, n)).reshape(spm, len(mc_ids))
-                for g, r in enumerate(mc_ids):
-                    M[r * n:(r + 1) * n, :] = states[:, g].T
-                    E_cols[r] = E[:, g]
+                M.reshape(R, n, spm)[mc_ids] = np.ascontiguousarray(states.transpose(1, 2, 0))  # blocked transpose in int8
+                E_cols[mc_ids] = E.T
             elif last:
                 for j in range(spm):
                     d_mc.sweep(1)
@@ -228,10 +236,11 @@ def _npt_run_dense(obj, prob, beta_list, nmc_kw):
                 E_cols[mc_ids, -1] = d_mc.energies()
             state[mc_ids] = d_mc.get_spins()
         if nmc_ids:
-            res = _nmc_cycles_dense(prob, d_nmc, state[nmc_ids], nmc_kw, "npt")
+            res = _nmc_cycles_dense(prob, d_nmc, state[nmc_ids], nmc_kw, "npt", keep_states=last)
             for g, r in enumerate(nmc_ids):
                 Mo, Eo, _ = res[g]
-                M[r * n:(r + 1) * n, :] = Mo[:, -spm:]
+                if last:
+                    M[r * n:(r + 1) * n, :] = Mo[:, -spm:]
                 E_cols[r] = Eo[-spm:]
                 state[r] = Mo[:, -1].astype(np.int8)
         for sel, nxt in host.select_non_overlapping_pairs(all_pairs, obj.num_swapping_pairs):
