@@ -166,7 +166,6 @@ class LbpMethods(_ProblemCache):
         P |= eye & (h_msgs != 0)  # the diagonal of h_msgs is treated as 0 unless stored
         for _ in range(2):  # symmetrising can only add entries, so two passes settle it
             off = ~P & ~eye
-            has_off = off.any(axis=1)
             rep = h_msgs[np.arange(n), np.argmax(off, axis=1)]
             P |= off & (h_msgs != rep[:, None])
             P |= P.T

@@ -197,7 +197,6 @@ def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True, all_cl
 def _npt_run_dense(obj, prob, beta_list, nmc_kw):
     """Dense-engine NPT: plain replicas and doNMC replicas live in two handles (their sweep counts per round
     differ, NPT/npt.py:577-580); exchanges are done on the host on the 2 x n spins of each accepted pair."""
-    import random as _random
     R, n = obj.num_replicas, prob.n
     spm, spr = obj.num_sweeps_MCMC_per_swap, obj.num_sweeps_read_per_swap
     mc_ids = [r for r in range(R) if not obj.doNMC[r]]

@@ -1,6 +1,6 @@
 """Dev tool: run the four classes in both modes on the instance kinds of the reference's example scripts and report
 exceptions (used to find unsupported combinations)."""
-import os, sys, tempfile, traceback, random
+import os, sys, tempfile, random
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "nonlocal-monte-carlo_b200"))
 import numpy as np
