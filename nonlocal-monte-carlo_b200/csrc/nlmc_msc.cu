@@ -44,7 +44,12 @@ struct nlmc_msc {
     int32_t *accepted = nullptr;  // [1]
     int8_t *scratch_spins = nullptr;  // [n]
     unsigned long long seed = 0;
-    uint32_t *d_counters = nullptr;  // [2] sweep counter, round counter: on the device so that captured graphs replay
+    uint32_t *d_counters = nullptr;  // [4] sweep counter, round counter, record slot: on the device so that captured graphs replay
+    int8_t *recM = nullptr;          // grow-only record buffers of nlmc_msc_sweep_record
+    double *recE = nullptr;
+    size_t recM_cap = 0, recE_cap = 0;
+    struct RecGraph { int ladder; bool has_M, has_E; cudaGraphExec_t exec; };
+    std::vector<RecGraph> rec_graphs;  // one recorded sweep (sweep + unpack + energies + slot bump), replayed per sweep
     int k_steps = 6;  // unconditional bit steps of the Bernoulli comparison (tuning knob NLMC_MSC_STEPS)
     struct RoundGraph { int n_sweeps, pairs; bool with_energy_swap; cudaGraphExec_t exec; };
     std::vector<RoundGraph> graphs;  // whole rounds captured once per (n_sweeps, pairs) and replayed
@@ -393,6 +398,20 @@ __global__ void msc_unpack_ladder_kernel(MscDev a, int g, int lane, int8_t *out)
     if (i < a.n) out[(size_t)b * a.n + i] = ((a.S[(size_t)i * a.W + b * a.G + g] >> lane) & 1u) ? 1 : -1;
 }
 
+// the same into slot counters[2] of a record buffer (captured once, replayed per recorded sweep)
+__global__ void msc_unpack_ladder_rec_kernel(MscDev a, int g, int lane, int8_t *base, size_t stride,
+                                             const uint32_t *__restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    int8_t *out = base + (size_t)counters[2] * stride;
+    if (i < a.n) out[(size_t)b * a.n + i] = ((a.S[(size_t)i * a.W + b * a.G + g] >> lane) & 1u) ? 1 : -1;
+}
+
+__global__ void msc_record_energy_kernel(const double *__restrict__ E, double *base, size_t stride,
+                                         const uint32_t *__restrict__ counters) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < stride) base[(size_t)counters[2] * stride + i] = E[i];
+}
+
 __global__ void msc_unpack_kernel(MscDev a, int w, int lane, int8_t *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < a.n) out[i] = ((a.S[(size_t)i * a.W + w] >> lane) & 1u) ? 1 : -1;
@@ -532,6 +551,26 @@ static int run_round(nlmc_msc *M, int n_sweeps, int num_pairs, bool with_energy_
 static void drop_graphs(nlmc_msc *M) {
     for (auto &g : M->graphs) cudaGraphExecDestroy(g.exec);
     M->graphs.clear();
+    for (auto &g : M->rec_graphs) cudaGraphExecDestroy(g.exec);
+    M->rec_graphs.clear();
+}
+
+// one recorded sweep: sweep, the ladder's states and / or all energies into slot counters[2] of the record buffers
+static int launch_recorded_sweep(nlmc_msc *M, int ladder, bool has_M, bool has_E, size_t m_stride, size_t e_stride) {
+    const MscDev d = dev_view(M);
+    int rc = launch_sweeps(M, 1);
+    if (rc) return rc;
+    if (has_M)
+        msc_unpack_ladder_rec_kernel<<<dim3((unsigned)((M->n + 255) / 256), (unsigned)M->n_beta), 256, 0, M->stream>>>(
+            d, ladder / 32, ladder % 32, M->recM, m_stride, M->d_counters);
+    if (has_E) {
+        if ((rc = launch_energy(M))) return rc;
+        msc_record_energy_kernel<<<(unsigned)((e_stride + 255) / 256), 256, 0, M->stream>>>(M->E, M->recE, e_stride,
+                                                                                        M->d_counters);
+    }
+    msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 2);
+    NLMC_CUDA(cudaGetLastError());
+    return NLMC_OK;
 }
 
 }  // namespace nlmc
@@ -543,7 +582,7 @@ int nlmc_msc_destroy(nlmc_msc *M) {
     cudaSetDevice(M->inst->device);
     nlmc::drop_graphs(M);
     void *ptrs[] = {M->S, M->rec, M->site_list, M->thr, M->betas, M->E_acc, M->E, M->swapmask, M->accepted,
-                    M->scratch_spins, M->d_counters};
+                    M->scratch_spins, M->d_counters, M->recM, M->recE};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (M->ev0) cudaEventDestroy(M->ev0);
     if (M->ev1) cudaEventDestroy(M->ev1);
@@ -660,8 +699,8 @@ int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_lad
               cudaMalloc(&M->E, sizeof(double) * (size_t)n_beta * M->n_ladders) == cudaSuccess &&
               cudaMalloc(&M->swapmask, sizeof(uint32_t) * (size_t)std::max(1, n_beta - 1) * M->G) == cudaSuccess &&
               cudaMalloc(&M->accepted, sizeof(int32_t)) == cudaSuccess &&
-              cudaMalloc(&M->d_counters, 2 * sizeof(uint32_t)) == cudaSuccess &&
-              cudaMemset(M->d_counters, 0, 2 * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMalloc(&M->d_counters, 4 * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMemset(M->d_counters, 0, 4 * sizeof(uint32_t)) == cudaSuccess &&
               cudaMalloc(&M->scratch_spins, (size_t)n) == cudaSuccess &&
               cudaMemcpy(M->rec, rec.data(), sizeof(int32_t) * rec.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(M->site_list, site_list.data(), sizeof(int32_t) * site_list.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
@@ -804,39 +843,62 @@ int nlmc_msc_sweep_record(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, 
     if (n_sweeps == 0) return NLMC_OK;
     NLMC_CUDA(cudaSetDevice(M->inst->device));
     const size_t m_stride = (size_t)M->n_beta * M->n, e_stride = (size_t)M->n_beta * M->n_ladders;
-    int8_t *recM = nullptr;
-    double *recE = nullptr;
-    if (out_M) NLMC_CUDA(cudaMalloc(&recM, m_stride * (size_t)n_sweeps));
-    if (out_E && cudaMalloc(&recE, sizeof(double) * e_stride * (size_t)n_sweeps) != cudaSuccess) {
-        if (recM) cudaFree(recM);
-        set_error("nlmc_msc_sweep_record: cudaMalloc failed");
-        return NLMC_ERR_CUDA;
-    }
-    const MscDev d = dev_view(M);
-    int rc = NLMC_OK;
-    cudaError_t e = cudaSuccess;
-    for (int s = 0; s < n_sweeps && !rc && e == cudaSuccess; ++s) {
-        rc = launch_sweeps(M, 1);
-        if (!rc && recM)
-            msc_unpack_ladder_kernel<<<dim3((unsigned)((M->n + 255) / 256), (unsigned)M->n_beta), 256, 0, M->stream>>>(
-                d, ladder / 32, ladder % 32, recM + (size_t)s * m_stride);
-        if (!rc && recE) {
-            rc = launch_energy(M);
-            if (!rc) e = cudaMemcpyAsync(recE + (size_t)s * e_stride, M->E, sizeof(double) * e_stride, cudaMemcpyDeviceToDevice, M->stream);
+    const bool has_M = out_M != nullptr, has_E = out_E != nullptr;
+    // grow-only record buffers; the captured graphs hold their addresses, so a reallocation drops the graphs
+    const size_t need_M = has_M ? m_stride * (size_t)n_sweeps : 0, need_E = has_E ? e_stride * (size_t)n_sweeps : 0;
+    if (need_M > M->recM_cap || need_E > M->recE_cap) {
+        NLMC_CUDA(cudaStreamSynchronize(M->stream));
+        for (auto &g : M->rec_graphs) cudaGraphExecDestroy(g.exec);
+        M->rec_graphs.clear();
+        if (need_M > M->recM_cap) {
+            if (M->recM) cudaFree(M->recM);
+            M->recM = nullptr; M->recM_cap = 0;
+            NLMC_CUDA(cudaMalloc(&M->recM, need_M));
+            M->recM_cap = need_M;
+        }
+        if (need_E > M->recE_cap) {
+            if (M->recE) cudaFree(M->recE);
+            M->recE = nullptr; M->recE_cap = 0;
+            NLMC_CUDA(cudaMalloc(&M->recE, sizeof(double) * need_E));
+            M->recE_cap = need_E;
         }
     }
-    if (!rc && e == cudaSuccess) e = cudaGetLastError();
-    if (!rc && e == cudaSuccess && recM) e = cudaMemcpyAsync(out_M, recM, m_stride * (size_t)n_sweeps, cudaMemcpyDeviceToHost, M->stream);
-    if (!rc && e == cudaSuccess && recE)
-        e = cudaMemcpyAsync(out_E, recE, sizeof(double) * e_stride * (size_t)n_sweeps, cudaMemcpyDeviceToHost, M->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(M->stream);
-    if (recM) cudaFree(recM);
-    if (recE) cudaFree(recE);
-    if (rc) return rc;
-    if (e != cudaSuccess) {
-        set_error("nlmc_msc_sweep_record: %s", cudaGetErrorString(e));
-        return NLMC_ERR_CUDA;
+    NLMC_CUDA(cudaMemsetAsync(M->d_counters + 2, 0, sizeof(uint32_t), M->stream));  // record slot 0
+    int rc = NLMC_OK;
+    if (M->use_graphs && n_sweeps >= 4) {
+        cudaGraphExec_t exec = nullptr;
+        for (auto &g : M->rec_graphs)
+            if (g.ladder == (has_M ? ladder : -1) && g.has_M == has_M && g.has_E == has_E) exec = g.exec;
+        if (!exec) {
+            cudaGraph_t graph = nullptr;
+            NLMC_CUDA(cudaStreamBeginCapture(M->stream, cudaStreamCaptureModeThreadLocal));
+            rc = launch_recorded_sweep(M, ladder, has_M, has_E, m_stride, e_stride);
+            const cudaError_t e = cudaStreamEndCapture(M->stream, &graph);
+            if (rc || e != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                if (!rc) set_error("nlmc_msc_sweep_record: stream capture failed: %s", cudaGetErrorString(e));
+                return rc ? rc : NLMC_ERR_CUDA;
+            }
+            const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e2 != cudaSuccess) {
+                set_error("nlmc_msc_sweep_record: cudaGraphInstantiate failed: %s", cudaGetErrorString(e2));
+                return NLMC_ERR_CUDA;
+            }
+            if (M->rec_graphs.size() >= 4) {
+                cudaGraphExecDestroy(M->rec_graphs.front().exec);
+                M->rec_graphs.erase(M->rec_graphs.begin());
+            }
+            M->rec_graphs.push_back({has_M ? ladder : -1, has_M, has_E, exec});
+        }
+        for (int s = 0; s < n_sweeps; ++s) NLMC_CUDA(cudaGraphLaunch(exec, M->stream));
+    } else {
+        for (int s = 0; s < n_sweeps && !rc; ++s) rc = launch_recorded_sweep(M, ladder, has_M, has_E, m_stride, e_stride);
+        if (rc) return rc;
     }
+    if (has_M) NLMC_CUDA(cudaMemcpyAsync(out_M, M->recM, need_M, cudaMemcpyDeviceToHost, M->stream));
+    if (has_E) NLMC_CUDA(cudaMemcpyAsync(out_E, M->recE, sizeof(double) * need_E, cudaMemcpyDeviceToHost, M->stream));
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
     return NLMC_OK;
 }
 
