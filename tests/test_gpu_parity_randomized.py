@@ -88,3 +88,35 @@ def test_k7_random_pairs(block):
         for p in range(P):
             lab_o, cnt_o = O.disagreement_clusters(csr, s1[p], s2[p])
             assert counts[p] == cnt_o and np.array_equal(labels[p], lab_o), f"case {case} pair {p} n={n}"
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_production_engines_on_ragged_instances(block):
+    """K2a (graph-coloured sparse) and K3 (dense tensor-core path) on the same ragged instances: no crash on n = 1,
+    empty rows or isolated spins, states stay +-1, and the engines' energies are those of the states they return
+    (fixed-point on K2a, bf16-split fields on K3: tolerances, not bit-exactness -- the returned fp64 energies of the
+    drop-in classes come from K4)."""
+    from nlmc_b200 import _lib, host
+    from oracle import oracle as O
+    rs = np.random.RandomState(3000 + block)
+    for case in range(block * 6, block * 6 + 6):
+        J, h, kind = random_instance(rs, case)
+        n = J.shape[0]
+        norm = max(np.max(np.abs(J)), 1e-30) if np.any(J) else 1.0
+        J, h = J / norm, h / norm
+        csr = O.Csr(J)
+        prob = host.Problem(J, h)
+        betas = np.linspace(0.3, 2.0, 5)
+        col = _lib.Col(prob.inst, betas, seed=case)
+        states, E = col.sweep_record(4)
+        assert states.shape == (4, 5, n) and set(np.unique(states)) <= {-1, 1}
+        Eo = O.energy(csr, h, states.reshape(-1, n)).reshape(4, 5)
+        np.testing.assert_allclose(E, Eo, rtol=1e-6, atol=1e-6 * max(1, n), err_msg=f"K2a case {case} n={n}")
+        col.close()
+        d = _lib.Dense(prob.inst, betas, n_split=3, seed=case)
+        d.sweep(3)
+        S = d.get_spins()
+        assert S.shape == (5, n) and set(np.unique(S)) <= {-1, 1}
+        np.testing.assert_allclose(d.energies(), O.energy(csr, h, S), rtol=1e-4, atol=1e-4 * max(1, n),
+                                   err_msg=f"K3 case {case} n={n}")
+        d.close()
