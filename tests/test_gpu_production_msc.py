@@ -177,6 +177,27 @@ def test_exact_boltzmann_small_lattice(nl, with_swaps):
         assert abs(mean - exact[b][0]) <= 4.5 * err + 1e-9, (betas[b], mean, exact[b][0], err)
 
 
+def test_exact_boltzmann_three_colour_lattice(nl):
+    """2D 3x3 periodic +-J: odd cycles, so the colouring needs more than two classes (one launch per class and the
+    all-sites energy path).  <E>(beta) from full enumeration of the 512 states."""
+    A, h = lattice_2d(3, 5)
+    betas = np.array([0.3, 0.8, 1.5])
+    exact = exact_mean_energy(A, betas)
+    prob = nl.host.Problem(A, h)
+    msc = nl.lib.Msc(prob.inst, betas, 1024, seed=77)
+    assert msc.n_colours >= 3
+    msc.sweep(200)
+    samples = []
+    for _ in range(60):
+        msc.sweep(4)
+        samples.append(msc.energies())
+    S = np.array(samples)
+    for b in range(len(betas)):
+        per_ladder = S[:, b, :].mean(axis=0)
+        mean, err = per_ladder.mean(), per_ladder.std(ddof=1) / np.sqrt(per_ladder.size)
+        assert abs(mean - exact[b][0]) <= 4.5 * err + 1e-9, (betas[b], mean, exact[b][0], err)
+
+
 def test_swap_bookkeeping_is_exact(nl):
     """After an exchange the energies the swap kernel carried along must equal freshly computed energies of
     the exchanged configurations, and the multiset of configurations of every ladder is conserved."""
