@@ -19,6 +19,7 @@ LIB = os.path.join(HERE, "nlmc_b200", "libnlmc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+FLAGS += os.environ.get("NLMC_NVCC_EXTRA", "").split()  # e.g. -DNLMC_PHILOX_ROUNDS=7 for an experiment build
 
 
 def sources():

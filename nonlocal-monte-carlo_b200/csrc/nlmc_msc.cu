@@ -63,12 +63,15 @@ namespace nlmc {
 
 constexpr uint32_t kTagSweep = 0x53574550u, kTagInit = 0x494e4954u, kTagSwap = 0x53574150u;
 
+#ifndef NLMC_PHILOX_ROUNDS
+#define NLMC_PHILOX_ROUNDS 10  // Philox4x32-10 (the Random123 / cuRAND default); 7 is the smallest Crush-resistant count
+#endif
 struct Philox {
     uint32_t k0, k1;
     __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
         uint32_t a = k0, b = k1;
 #pragma unroll
-        for (int i = 0; i < 10; ++i) {
+        for (int i = 0; i < NLMC_PHILOX_ROUNDS; ++i) {
             const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
             const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
             const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ a;
