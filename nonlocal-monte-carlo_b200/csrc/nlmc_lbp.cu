@@ -28,6 +28,13 @@ struct nlmc_lbp {
     int32_t *rev = nullptr;     // [nnz] entry (j,i) for entry (i,j)
     double *u[2] = {nullptr, nullptr};  // [nnz] u messages, double buffered
     double *hm = nullptr;       // [nnz] h messages
+    double *tj = nullptr;       // [nnz] tanh(beta J), refreshed at the start of every launch
+    double *uin = nullptr;      // [nnz] uin[(i,j)] = u[(j,i)]: the message entry (i,j) gathers, stored where row i reads it
+    int32_t *prog = nullptr;    // summation programs: numpy's pairwise order of each column sum, resolved on the host
+    int32_t *prog_ptr = nullptr;  // [n+1]
+    int warp_rows = 0;          // 1: a warp per row in the gather (rows of >= ~12 entries), 0: a thread per row
+    int row_cap = 0;            // longest row (entries) when warp_rows is set: sizes the per-warp shared staging
+    size_t smem_bytes = 0;
     double *tot = nullptr;      // [n]   off-edge value of each h_msgs row
     double *eps = nullptr;      // [n]   |h_i| + sum_j |J_ij|   (nmc.py:353)
     double *mstar = nullptr;    // [n]
@@ -36,7 +43,7 @@ struct nlmc_lbp {
     double *dense[2] = {nullptr, nullptr};  // [n*n] correlations / J_tilde of nlmc_lbp_byproducts (on demand)
     double *htilde = nullptr;   // [n]
     uint8_t *offedge = nullptr; // [n]   row has an off-diagonal zero
-    unsigned long long *red = nullptr;  // [4] du, su, dh, sh as ordered bit patterns
+    unsigned long long *red = nullptr;  // [2][4] du, su, dh, sh as ordered bit patterns, double buffered by iteration parity
     int *iter_out = nullptr;
     int cur = 0;
     int grid = 0;
@@ -129,13 +136,75 @@ __device__ __forceinline__ void block_max2(double &a, double &b, double *sm) {
     }
 }
 
+// The order in which numpy's pairwise sum associates the additions depends only on the positions of the non-zeros,
+// i.e. on the sparsity pattern of J: it is resolved ONCE on the host into a postfix program per row
+// (op >= 0: push the row's op-th incoming message, op == -1: add the two topmost values) and replayed here.
+// The per-iteration gather is then a short dependent chain instead of a walk over numpy's recursion tree
+// (ncu: 83 % of the kernel's samples were CTAs waiting at the grid barrier for the slowest such walk).
+constexpr int kProgStack = 40;
+__device__ __forceinline__ double run_sum_program(const int32_t *__restrict__ prog, int len, const double *__restrict__ row) {
+    double st[kProgStack];
+    int sp = 0;
+    for (int k = 0; k < len; ++k) {
+        const int op = prog[k];
+        if (op >= 0) {
+            st[sp++] = row[op];
+        } else {
+            --sp;
+            st[sp - 1] = __dadd_rn(st[sp - 1], st[sp]);
+        }
+    }
+    return sp ? st[0] : 0.0;
+}
+
+// host: emit the program of pairwise_sparse(n, pos[0..cnt)) -- same association, zero operands skipped (x + 0 == x)
+struct SumProgramBuilder {
+    const int32_t *pos;
+    int cnt, cur = 0, depth = 0, max_depth = 0;
+    std::vector<int32_t> *out;
+    const int32_t *entry = nullptr;  // entry index within the row of the q-th smallest column (NULL: identity)
+    void push(int q) { out->push_back(entry ? entry[q] : q); max_depth = std::max(max_depth, ++depth); }
+    void add() { out->push_back(-1); --depth; }
+    bool chain(bool have, int q) {  // res += v(q)
+        push(q);
+        if (have) add();
+        return true;
+    }
+    bool emit(int lo, int len) {
+        if (cur >= cnt || pos[cur] >= lo + len) return false;
+        if (len < 8) {
+            bool have = false;
+            while (cur < cnt && pos[cur] < lo + len) have = chain(have, cur++);
+            return have;
+        }
+        if (len <= 128) {
+            const int body_end = lo + len - (len % 8);
+            std::vector<int> acc[8];
+            while (cur < cnt && pos[cur] < body_end) { acc[(pos[cur] - lo) & 7].push_back(cur); ++cur; }
+            auto leaf = [&](int j) { bool have = false; for (int q : acc[j]) have = chain(have, q); return have; };
+            auto pair = [&](int j) { const bool a = leaf(j), b = leaf(j + 1); if (a && b) add(); return a || b; };
+            auto quad = [&](int j) { const bool a = pair(j), b = pair(j + 2); if (a && b) add(); return a || b; };
+            const bool a = quad(0), b = quad(4);
+            if (a && b) add();
+            bool have = a || b;
+            while (cur < cnt && pos[cur] < lo + len) have = chain(have, cur++);
+            return have;
+        }
+        int n2 = len / 2;
+        n2 -= n2 % 8;
+        const bool a = emit(lo, n2), b = emit(lo + n2, len - n2);
+        if (a && b) add();
+        return a || b;
+    }
+};
+
 struct LbpArgs {
-    int n, nnz, max_iter;
+    int n, nnz, max_iter, warp_rows, row_cap;
     double beta, lambda, tol;
-    const int32_t *rp, *ci, *rev;
+    const int32_t *rp, *ci, *rev, *prog, *prog_ptr;
     const double *val, *h, *eps, *mstar;
     const double *h_field;  // non-NULL: use this field instead of h + lambda*m_star*eps (nlmc_lbp_run)
-    double *u0, *u1, *hm, *tot, *marg;
+    double *u0, *u1, *hm, *uin, *tot, *marg, *tj;
     const uint8_t *offedge;
     unsigned long long *red;
     int *iter_out;  // [0] iteration on exit, [1] index of the buffer holding the final u
@@ -143,6 +212,7 @@ struct LbpArgs {
 
 __global__ void __launch_bounds__(256) lbp_kernel(LbpArgs a) {
     cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) double lbp_dyn[];  // warp-per-row staging (empty in the thread-per-row mode)
     __shared__ double sm[64];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
@@ -150,19 +220,63 @@ __global__ void __launch_bounds__(256) lbp_kernel(LbpArgs a) {
     double *u_old = a.u0, *u_new = a.u1;
     int iteration = 0;
     bool converged = false;
+    // two grid-wide syncs per iteration: the reduction slots alternate with the iteration parity, and the slots of
+    // the NEXT iteration are cleared during this one's update phase (nobody touches them in between)
+    if (tid < 8) a.red[tid] = 0ull;
+    for (int p = tid; p < a.nnz; p += nthreads) a.tj[p] = tanh(__dmul_rn(a.beta, a.val[p]));  // constant over the iterations
+    grid.sync();
     for (iteration = 0; iteration < a.max_iter; ++iteration) {
-        if (tid == 0) { a.red[0] = 0ull; a.red[1] = 0ull; a.red[2] = 0ull; a.red[3] = 0ull; }
-        grid.sync();
+        unsigned long long *red = a.red + 4 * (iteration & 1), *red_next = a.red + 4 * ((iteration + 1) & 1);
         // ---- gather: total_i = hl_i + sum_k u[k,i];  hm[i,j] = total_i - u[j,i]   (nmc.py:200-203)
+        // uin holds u[j,i] at entry (i,j), so a row reads its incoming messages contiguously
         double dh = 0.0, sh = 0.0;
+        if (a.warp_rows) {
+            // a warp per row: the lanes stage the row's incoming messages and its summation program in shared memory
+            // with one round of coalesced loads, lane 0 replays the program out of shared memory, then the lanes
+            // update the row's h messages in parallel (a thread per row spends ~2 us PER ENTRY in dependent L2 loads
+            // when only a few hundred rows exist)
+            const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+            double *vals = lbp_dyn + (size_t)wib * a.row_cap;
+            int32_t *pr = reinterpret_cast<int32_t *>(lbp_dyn + (size_t)(blockDim.x >> 5) * a.row_cap) + (size_t)wib * 2 * a.row_cap;
+            for (int i = tid >> 5; i < a.n; i += nthreads >> 5) {
+                const int b = a.rp[i], cnt = a.rp[i + 1] - b;
+                const int pp = a.prog_ptr[i], plen = a.prog_ptr[i + 1] - pp;
+                for (int q = lane; q < cnt; q += 32) vals[q] = a.uin[b + q];
+                for (int k = lane; k < plen; k += 32) pr[k] = a.prog[pp + k];
+                __syncwarp();
+                double total = 0.0;
+                if (lane == 0) {
+                    const double hl = a.h_field ? a.h_field[i]
+                                                : __dadd_rn(a.h[i], __dmul_rn(__dmul_rn(a.lambda, a.mstar[i]), a.eps[i]));
+                    total = __dadd_rn(hl, run_sum_program(pr, plen, vals));
+                }
+                total = __shfl_sync(0xffffffffu, total, 0);
+                for (int q = lane; q < cnt; q += 32) {
+                    const double hnew = (a.ci[b + q] == i) ? 0.0 : __dsub_rn(total, vals[q]);
+                    const double hold = a.hm[b + q];
+                    dh = fmax(dh, fabs(__dsub_rn(hnew, hold)));
+                    sh = fmax(sh, __dadd_rn(fabs(hnew), fabs(hold)));
+                    a.hm[b + q] = hnew;
+                }
+                if (lane == 0) {
+                    if (a.offedge[i]) {
+                        const double told = a.tot[i];
+                        dh = fmax(dh, fabs(__dsub_rn(total, told)));
+                        sh = fmax(sh, __dadd_rn(fabs(total), fabs(told)));
+                    }
+                    a.tot[i] = total;
+                }
+                __syncwarp();
+            }
+        } else
         for (int i = tid; i < a.n; i += nthreads) {
             const int b = a.rp[i], cnt = a.rp[i + 1] - b;
             const double hl = a.h_field ? a.h_field[i]
                                         : __dadd_rn(a.h[i], __dmul_rn(__dmul_rn(a.lambda, a.mstar[i]), a.eps[i]));  // nmc.py:133-134
-            const double total = __dadd_rn(hl, pairwise_sparse(a.n, a.ci + b, cnt,
-                                                             [&](int q) { return u_old[a.rev[b + q]]; }));
+            const double *uin_row = a.uin + b;
+            const double total = __dadd_rn(hl, run_sum_program(a.prog + a.prog_ptr[i], a.prog_ptr[i + 1] - a.prog_ptr[i], uin_row));
             for (int q = 0; q < cnt; ++q) {
-                const double hnew = (a.ci[b + q] == i) ? 0.0 : __dsub_rn(total, u_old[a.rev[b + q]]);
+                const double hnew = (a.ci[b + q] == i) ? 0.0 : __dsub_rn(total, uin_row[q]);
                 const double hold = a.hm[b + q];
                 dh = fmax(dh, fabs(__dsub_rn(hnew, hold)));
                 sh = fmax(sh, __dadd_rn(fabs(hnew), fabs(hold)));
@@ -176,29 +290,30 @@ __global__ void __launch_bounds__(256) lbp_kernel(LbpArgs a) {
             a.tot[i] = total;
         }
         block_max2(dh, sh, sm);
-        if (threadIdx.x == 0) { atomic_max_nonneg(a.red + 2, dh); atomic_max_nonneg(a.red + 3, sh); }
+        if (threadIdx.x == 0) { atomic_max_nonneg(red + 2, dh); atomic_max_nonneg(red + 3, sh); }
         grid.sync();
         // ---- update: u = (1/beta) * atanh_sat(tanh(beta J) * tanh(beta h_msgs))       (nmc.py:205)
+        if (tid < 4) red_next[tid] = 0ull;
         double du = 0.0, su = 0.0;
         for (int p = tid; p < a.nnz; p += nthreads) {
-            const double tj = tanh(__dmul_rn(a.beta, a.val[p]));
+            const double tj = a.tj[p];
             const double th = tanh(__dmul_rn(a.beta, a.hm[p]));
             const double un = __dmul_rn(inv_beta, atanh_saturated(__dmul_rn(tj, th)));
             const double uo = u_old[p];
             du = fmax(du, fabs(__dsub_rn(un, uo)));
             su = fmax(su, __dadd_rn(fabs(un), fabs(uo)));
             u_new[p] = un;
+            a.uin[a.rev[p]] = un;  // what the transposed entry gathers next
         }
         block_max2(du, su, sm);
-        if (threadIdx.x == 0) { atomic_max_nonneg(a.red + 0, du); atomic_max_nonneg(a.red + 1, su); }
+        if (threadIdx.x == 0) { atomic_max_nonneg(red + 0, du); atomic_max_nonneg(red + 1, su); }
         grid.sync();
         double *t = u_old; u_old = u_new; u_new = t;  // u_old now holds the newest messages
-        const double gdu = __longlong_as_double((long long)a.red[0]), gsu = __longlong_as_double((long long)a.red[1]);
-        const double gdh = __longlong_as_double((long long)a.red[2]), gsh = __longlong_as_double((long long)a.red[3]);
+        const double gdu = __longlong_as_double((long long)red[0]), gsu = __longlong_as_double((long long)red[1]);
+        const double gdh = __longlong_as_double((long long)red[2]), gsh = __longlong_as_double((long long)red[3]);
         const double u_change = __ddiv_rn(gdu, gsu), h_change = __ddiv_rn(gdh, gsh);  // 0/0 = nan -> not converged
         converged = (u_change < a.tol) && (h_change < a.tol);  // nmc.py:212
         if (converged) break;
-        grid.sync();  // everyone has read red[] before the next iteration clears it
     }
     if (!converged) iteration = a.max_iter - 1;  // python loop variable after exhaustion
     // marginal_i = tanh(beta * (hl_i + sum_k u[k,i])), rows accumulated in order   (nmc.py:216)
@@ -206,17 +321,22 @@ __global__ void __launch_bounds__(256) lbp_kernel(LbpArgs a) {
         const double hl = a.h_field ? a.h_field[i]
                                     : __dadd_rn(a.h[i], __dmul_rn(__dmul_rn(a.lambda, a.mstar[i]), a.eps[i]));
         double acc = 0.0;
-        for (int p = a.rp[i]; p < a.rp[i + 1]; ++p) acc = __dadd_rn(acc, u_old[a.rev[p]]);
+        for (int p = a.rp[i]; p < a.rp[i + 1]; ++p) acc = __dadd_rn(acc, a.uin[p]);
         a.marg[i] = tanh(__dmul_rn(a.beta, __dadd_rn(hl, acc)));
     }
     if (tid == 0) { a.iter_out[0] = iteration; a.iter_out[1] = (u_old == a.u0) ? 0 : 1; }
 }
 
 // u = J * m_star (nmc.py:129), h_msgs = 0 (nmc.py:128)
-__global__ void lbp_reset_kernel(int n, int nnz, const int32_t *ci, const double *val, const double *mstar,
-                                 double *u, double *hm, double *tot) {
+__global__ void lbp_reset_kernel(int n, int nnz, const int32_t *ci, const int32_t *rev, const double *val,
+                                 const double *mstar, double *u, double *uin, double *hm, double *tot) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-    for (int p = tid; p < nnz; p += nt) { u[p] = __dmul_rn(val[p], mstar[ci[p]]); hm[p] = 0.0; }
+    for (int p = tid; p < nnz; p += nt) {
+        const double v = __dmul_rn(val[p], mstar[ci[p]]);
+        u[p] = v;
+        uin[rev[p]] = v;
+        hm[p] = 0.0;
+    }
     for (int i = tid; i < n; i += nt) tot[i] = 0.0;
 }
 
@@ -274,6 +394,12 @@ __global__ void lbp_htilde_kernel(int n, double beta, const double *marg, double
     if (i < n) ht[i] = __dmul_rn(__ddiv_rn(1.0, beta), atanh_saturated(marg[i]));
 }
 
+// uin[rev[p]] = u[p] (after nlmc_lbp_set_messages)
+__global__ void lbp_transpose_kernel(int nnz, const int32_t *rev, const double *u, double *uin) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < nnz) uin[rev[p]] = u[p];
+}
+
 }  // namespace nlmc
 
 extern "C" {
@@ -281,7 +407,7 @@ extern "C" {
 int nlmc_lbp_destroy(nlmc_lbp *L) {
     if (!L) return NLMC_OK;
     cudaSetDevice(L->inst->device);
-    void *ptrs[] = {L->rev, L->u[0], L->u[1], L->hm, L->tot, L->eps, L->mstar, L->marg, L->offedge, L->red, L->iter_out,
+    void *ptrs[] = {L->rev, L->prog, L->prog_ptr, L->u[0], L->u[1], L->hm, L->tj, L->uin, L->tot, L->eps, L->mstar, L->marg, L->offedge, L->red, L->iter_out,
                     L->hfield, L->dense[0], L->dense[1], L->htilde};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete L;
@@ -307,6 +433,29 @@ int nlmc_lbp_create(nlmc_instance *I, nlmc_lbp **out) {
             rev[(size_t)p] = (int32_t)(it - I->h_col.data());
         }
     }
+    // summation programs (rows must be sorted by column, as scipy's csr_matrix(J) delivers them)
+    std::vector<int32_t> prog, prog_ptr((size_t)n + 1, 0);
+    prog.reserve((size_t)2 * (size_t)std::max(nnz, 1));
+    for (int i = 0; i < n; ++i) {
+        const int b = I->h_row_ptr[i], cnt = I->h_row_ptr[i + 1] - b;
+        const int32_t *cols = I->h_col.data() + b;
+        std::vector<int32_t> sorted_cols, order;
+        if (!std::is_sorted(cols, cols + cnt)) {  // numpy sums the dense column in index order whatever the storage order
+            order.resize((size_t)cnt);
+            for (int q = 0; q < cnt; ++q) order[(size_t)q] = q;
+            std::sort(order.begin(), order.end(), [&](int x, int y) { return cols[x] < cols[y]; });
+            sorted_cols.resize((size_t)cnt);
+            for (int q = 0; q < cnt; ++q) sorted_cols[(size_t)q] = cols[order[(size_t)q]];
+            cols = sorted_cols.data();
+        }
+        SumProgramBuilder sb{cols, cnt};
+        sb.out = &prog;
+        sb.entry = order.empty() ? nullptr : order.data();
+        sb.emit(0, n);
+        NLMC_REQUIRE(sb.max_depth <= kProgStack, "nlmc_lbp_create: summation program of row %d is too deep (%d)", i, sb.max_depth);
+        prog_ptr[(size_t)i + 1] = (int32_t)prog.size();
+    }
+    if (prog.empty()) prog.push_back(0);
     NLMC_CUDA(cudaSetDevice(I->device));
     auto *L = new nlmc_lbp();
     L->inst = I;
@@ -315,6 +464,8 @@ int nlmc_lbp_create(nlmc_instance *I, nlmc_lbp **out) {
               cudaMalloc(&L->u[0], sizeof(double) * nz) == cudaSuccess &&
               cudaMalloc(&L->u[1], sizeof(double) * nz) == cudaSuccess &&
               cudaMalloc(&L->hm, sizeof(double) * nz) == cudaSuccess &&
+              cudaMalloc(&L->uin, sizeof(double) * nz) == cudaSuccess &&
+              cudaMalloc(&L->tj, sizeof(double) * nz) == cudaSuccess &&
               cudaMalloc(&L->tot, sizeof(double) * (size_t)n) == cudaSuccess &&
               cudaMalloc(&L->eps, sizeof(double) * (size_t)n) == cudaSuccess &&
               cudaMalloc(&L->mstar, sizeof(double) * (size_t)n) == cudaSuccess &&
@@ -322,9 +473,13 @@ int nlmc_lbp_create(nlmc_instance *I, nlmc_lbp **out) {
               cudaMalloc(&L->hfield, sizeof(double) * (size_t)n) == cudaSuccess &&
               cudaMalloc(&L->htilde, sizeof(double) * (size_t)n) == cudaSuccess &&
               cudaMalloc(&L->offedge, (size_t)n) == cudaSuccess &&
-              cudaMalloc(&L->red, sizeof(unsigned long long) * 4) == cudaSuccess &&
+              cudaMalloc(&L->red, sizeof(unsigned long long) * 8) == cudaSuccess &&
               cudaMalloc(&L->iter_out, sizeof(int) * 2) == cudaSuccess &&
-              cudaMemcpy(L->rev, rev.data(), sizeof(int32_t) * nz, cudaMemcpyHostToDevice) == cudaSuccess;
+              cudaMemcpy(L->rev, rev.data(), sizeof(int32_t) * nz, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMalloc(&L->prog, sizeof(int32_t) * prog.size()) == cudaSuccess &&
+              cudaMalloc(&L->prog_ptr, sizeof(int32_t) * prog_ptr.size()) == cudaSuccess &&
+              cudaMemcpy(L->prog, prog.data(), sizeof(int32_t) * prog.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(L->prog_ptr, prog_ptr.data(), sizeof(int32_t) * prog_ptr.size(), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         set_error("nlmc_lbp_create: CUDA allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         nlmc_lbp_destroy(L);
@@ -341,9 +496,24 @@ int nlmc_lbp_create(nlmc_instance *I, nlmc_lbp **out) {
         return NLMC_ERR_UNSUPPORTED;
     }
     NLMC_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, I->device));
-    NLMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_kernel, 256, 0));
+    // rows of a dozen entries or more get a warp each in the gather, if the staging of the longest row fits
+    L->row_cap = I->max_deg;
+    L->warp_rows = (nnz >= 12 * n && (size_t)I->max_deg * 128 <= 160 * 1024) ? 1 : 0;
+    L->smem_bytes = L->warp_rows ? (size_t)8 * ((size_t)I->max_deg * sizeof(double) + (size_t)2 * I->max_deg * sizeof(int32_t)) : 0;
+    if (L->smem_bytes > 48 * 1024 &&
+        cudaFuncSetAttribute(lbp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L->smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        L->warp_rows = 0;
+        L->smem_bytes = 0;
+    }
+    NLMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbp_kernel, 256, L->smem_bytes));
+    if (per_sm < 1) {
+        set_error("nlmc_lbp_create: the LBP kernel does not fit on an SM");
+        nlmc_lbp_destroy(L);
+        return NLMC_ERR_UNSUPPORTED;
+    }
     const int want = std::max(1, (std::max(nnz, n) + 255) / 256);
-    L->grid = std::max(1, std::min(want, dev_sms * std::max(per_sm, 1)));
+    L->grid = std::max(1, std::min(want, dev_sms));  // at most one CTA per SM: the grid-wide syncs stay cheap
     NLMC_CUDA(cudaStreamSynchronize(I->stream));
     *out = L;
     return NLMC_OK;
@@ -364,7 +534,7 @@ int nlmc_lbp_reset(nlmc_lbp *L, const double *m_star) {
     NLMC_CUDA(cudaMemcpyAsync(L->mstar, m_star, sizeof(double) * (size_t)I->n, cudaMemcpyHostToDevice, I->stream));
     L->cur = 0;
     lbp_reset_kernel<<<std::max(1, std::min(1024, (std::max(I->nnz, I->n) + 255) / 256)), 256, 0, I->stream>>>(
-        I->n, I->nnz, I->col, I->val, L->mstar, L->u[0], L->hm, L->tot);
+        I->n, I->nnz, I->col, L->rev, I->val, L->mstar, L->u[0], L->uin, L->hm, L->tot);
     NLMC_CUDA(cudaGetLastError());
     NLMC_CUDA(cudaStreamSynchronize(I->stream));
     return NLMC_OK;
@@ -375,16 +545,16 @@ static int lbp_launch(nlmc_lbp *L, const double *h_field_dev, double lambda, dou
     using namespace nlmc;
     nlmc_instance *I = L->inst;
     LbpArgs a;
-    a.n = I->n; a.nnz = I->nnz; a.max_iter = max_iter;
+    a.n = I->n; a.nnz = I->nnz; a.max_iter = max_iter; a.warp_rows = L->warp_rows; a.row_cap = L->row_cap;
     a.beta = beta; a.lambda = lambda; a.tol = tol;
-    a.rp = I->row_ptr; a.ci = I->col; a.rev = L->rev;
+    a.rp = I->row_ptr; a.ci = I->col; a.rev = L->rev; a.prog = L->prog; a.prog_ptr = L->prog_ptr;
     a.val = I->val; a.h = I->h; a.eps = L->eps; a.mstar = L->mstar;
     a.h_field = h_field_dev;
     a.u0 = L->u[L->cur]; a.u1 = L->u[1 - L->cur];
-    a.hm = L->hm; a.tot = L->tot; a.marg = L->marg; a.offedge = L->offedge;
+    a.hm = L->hm; a.tj = L->tj; a.uin = L->uin; a.tot = L->tot; a.marg = L->marg; a.offedge = L->offedge;
     a.red = L->red; a.iter_out = L->iter_out;
     void *args[] = {&a};
-    NLMC_CUDA(cudaLaunchCooperativeKernel((void *)lbp_kernel, dim3((unsigned)L->grid), dim3(256), args, 0, I->stream));
+    NLMC_CUDA(cudaLaunchCooperativeKernel((void *)lbp_kernel, dim3((unsigned)L->grid), dim3(256), args, L->smem_bytes, I->stream));
     int res[2] = {0, 0};
     NLMC_CUDA(cudaMemcpyAsync(res, L->iter_out, sizeof(res), cudaMemcpyDeviceToHost, I->stream));
     if (out_marginal)
@@ -421,6 +591,10 @@ int nlmc_lbp_set_messages(nlmc_lbp *L, const double *h_edge, const double *u_edg
     NLMC_CUDA(cudaMemcpyAsync(L->hm, h_edge, nz, cudaMemcpyHostToDevice, I->stream));
     NLMC_CUDA(cudaMemcpyAsync(L->u[L->cur], u_edge, nz, cudaMemcpyHostToDevice, I->stream));
     NLMC_CUDA(cudaMemcpyAsync(L->tot, tot, sizeof(double) * (size_t)I->n, cudaMemcpyHostToDevice, I->stream));
+    if (I->nnz > 0) {
+        nlmc::lbp_transpose_kernel<<<(I->nnz + 255) / 256, 256, 0, I->stream>>>(I->nnz, L->rev, L->u[L->cur], L->uin);
+        NLMC_CUDA(cudaGetLastError());
+    }
     NLMC_CUDA(cudaStreamSynchronize(I->stream));
     return NLMC_OK;
 }
