@@ -34,7 +34,7 @@ for name, (J, h), beta in (("EA L=16", O.ea3d_pm_j(16, 2), 1 / 0.366838 * 5), ("
     iters = sum(t[1] + 1 for t in trace)
     nnz = len(prob.val)
     emit(kernel="K5 lbp_kernel", instance=name, lambda_steps=len(trace), iterations=iters, seconds=dt, us_per_iteration=dt / iters * 1e6,
-         algorithmic_GBps=iters * 32 * nnz / dt / 1e9, note="3 grid-wide syncs per iteration: latency-bound on these sizes")
+         algorithmic_GBps=iters * 32 * nnz / dt / 1e9, note="2 grid-wide syncs per iteration: latency-bound on these sizes")
 # K7: Houdayer clusters
 A, h = O.ea3d_pm_j(32, 4)
 prob = host.Problem(A, h)
