@@ -111,14 +111,15 @@ def _generic_engine(prob: host.Problem, betas, seed: int):
 def _backbones(prob, states, global_beta, nmc_kw):
     """LBP backbone (K5 + host lambda schedule) of every state in `states` [G][n] -> list of index arrays."""
     from .nmc_core import lbp_convexified
-    lbp = _lib.Lbp(prob.inst)
+    lbp = getattr(prob, "_lbp_handle", None)  # reverse-entry index and summation programs are built once per instance
+    if lbp is None:
+        lbp = prob._lbp_handle = _lib.Lbp(prob.inst)
     out = []
     for m_star in states:
         cl = lbp_convexified(prob, lbp, m_star.astype(np.float64), nmc_kw["lambda_start"], nmc_kw["lambda_end"],
                              nmc_kw["lambda_reduction_factor"], nmc_kw["tolerance"], nmc_kw["max_iterations"],
                              nmc_kw["threshold_initial"], nmc_kw["threshold_cutoff"], global_beta)
         out.append(np.concatenate(cl).astype(int) if cl else np.array([], dtype=int))
-    lbp.close()
     return out
 
 
