@@ -42,58 +42,9 @@ SURVEY_BYTES_PER_ATTEMPT = 42.0  # B_alg = 6 + 6*deg for +-J int
 
 
 def ea3d_csr(L: int, seed: int):
-    """3D periodic +-J EA instance of SURVEY.md 8(d) as CSR arrays (site i = x + L*(y + L*z))."""
-    import scipy.sparse as sp
-    rs = np.random.RandomState(seed)
-    N = L ** 3
-    idx = np.arange(N)
-    x, y, z = idx % L, (idx // L) % L, idx // (L * L)
-    nbr = [((x + 1) % L) + L * (y + L * z), x + L * (((y + 1) % L) + L * z), x + L * (y + L * ((z + 1) % L))]
-    v = rs.choice([-1.0, 1.0], size=(3, N)).reshape(-1)
-    rows, cols = np.concatenate([idx, idx, idx]), np.concatenate(nbr)
-    A = sp.coo_matrix((np.concatenate([v, v]), (np.concatenate([rows, cols]), np.concatenate([cols, rows]))),
-                      shape=(N, N)).tocsr()
-    A.sum_duplicates()
-    A.sort_indices()
-    return A
-
-
-class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, device_index: int):
-        self.rows, self.proc = [], None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={device_index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
-
-    def stop(self, t0: float, t1: float):
-        if self.proc is None:
-            return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows]
-        try:
-            sm = [float(r[0]) for r in rows]
-            reasons = []
-            for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-                if any(r[col].lower().startswith("active") for r in rows):
-                    reasons.append(name)
-            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
-                    "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
-        except Exception:
-            return None
+    """3D periodic +-J EA instance of SURVEY.md 8(d) as scipy CSR (site i = x + L*(y + L*z))."""
+    from nlmc_b200 import instances
+    return instances.ea3d_pm_j(L, seed)[0]
 
 
 def measured_peaks():

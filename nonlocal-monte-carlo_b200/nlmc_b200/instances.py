@@ -142,3 +142,45 @@ def write_instance(J, h, filename: str) -> None:
             hv = np.asarray(h).reshape(-1)
             for i in np.flatnonzero(hv):
                 f.write(f"{i} {i} {-hv[i]}\n")
+
+
+# ---------------------------------------------------------------------------------------------------
+# Synthetic benchmark instances of the five configurations; seeded with
+# np.random.RandomState(seed), couplings already normalised to max |J| = 1, h = 0.
+# ---------------------------------------------------------------------------------------------------
+def ea3d_pm_j(L: int, seed: int):
+    """3D periodic +-J Edwards-Anderson lattice (configs C2, C4, C5): site i = x + L*(y + L*z), three forward bonds
+    per site, +-1 equiprobable.  Returns (J as scipy CSR, h = zeros(N))."""
+    rs = np.random.RandomState(seed)
+    N = L ** 3
+    idx = np.arange(N)
+    x, y, z = idx % L, (idx // L) % L, idx // (L * L)
+    fwd = [((x + 1) % L) + L * (y + L * z), x + L * (((y + 1) % L) + L * z), x + L * (y + L * ((z + 1) % L))]
+    v = rs.choice([-1.0, 1.0], size=(3, N)).reshape(-1)
+    rows, cols = np.concatenate([idx, idx, idx]), np.concatenate(fwd)
+    A = sp.coo_matrix((np.concatenate([v, v]), (np.concatenate([rows, cols]), np.concatenate([cols, rows]))),
+                      shape=(N, N)).tocsr()  # duplicates (L = 2) are summed, as a dense J += J.T would
+    A.sum_duplicates()
+    A.sort_indices()
+    return A, np.zeros(N)
+
+
+def random_pm_graph(N: int, p: float, seed: int):
+    """Config C1: every pair i < j present with probability p, value +-1.  Returns (dense J, h = zeros(N))."""
+    rs = np.random.RandomState(seed)
+    iu = np.triu_indices(N, 1)
+    keep = rs.rand(len(iu[0])) < p
+    J = np.zeros((N, N))
+    J[iu[0][keep], iu[1][keep]] = rs.choice([-1.0, 1.0], size=int(keep.sum()))
+    J += J.T
+    return J, np.zeros(N)
+
+
+def sk_gaussian(N: int, seed: int):
+    """Config C3: Sherrington-Kirkpatrick, J_ij ~ N(0, 1) / sqrt(N), symmetric, zero diagonal (not normalised)."""
+    rs = np.random.RandomState(seed)
+    iu = np.triu_indices(N, 1)
+    J = np.zeros((N, N))
+    J[iu] = rs.randn(len(iu[0])) / np.sqrt(N)
+    J += J.T
+    return J, np.zeros(N)

@@ -85,3 +85,17 @@ def test_contrived_wishart_tree_generator_matches_reference(tmp_path):
     J2, h2 = I.read_contrived_wishart(str(path))
     np.testing.assert_allclose(J2.toarray(), J, rtol=0, atol=1e-15)
     np.testing.assert_allclose(h2.reshape(-1), h, rtol=0, atol=1e-15)
+
+
+def test_synthetic_generators_match_the_oracle_definitions():
+    """The product's generators of the benchmark instances and the oracle's are the same instances."""
+    from nlmc_b200 import instances as I
+    from oracle import oracle as O
+    for L, seed in ((2, 1), (4, 3), (6, 5)):
+        A, h = I.ea3d_pm_j(L, seed)
+        B, _ = O.ea3d_pm_j(L, seed)
+        assert (A != B).nnz == 0 and np.array_equal(A.indices, B.indices) and not h.any()
+    J, _ = I.random_pm_graph(60, 0.1, 7)
+    assert np.array_equal(J, O.random_pm_graph(60, 0.1, 7)[0])
+    K, _ = I.sk_gaussian(30, 9)
+    assert np.array_equal(K, O.sk_gaussian(30, 9)[0])

@@ -15,7 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "nonlocal-monte-carlo_b200"))
-from nlmc_b200 import APT_ICM, NMC, NPT, APT_preprocessor, _lib, host  # noqa: E402
+from nlmc_b200 import APT_ICM, NMC, NPT, APT_preprocessor, _lib, host, instances  # noqa: E402
 from oracle import oracle as O  # noqa: E402  (CPU baseline legs only)
 
 EPS = np.finfo(float).eps
@@ -36,7 +36,7 @@ def cpu_mcmc_rate(csr, h, beta, sweeps=2):
 
 def c1():
     """NMC.run, N=800 random +-1 graph (6% density), README parameters with sweeps cut to 1e3."""
-    J, h = O.random_pm_graph(800, 0.06, 1)
+    J, h = instances.random_pm_graph(800, 0.06, 1)
     args = (1000, 1000, 10, 1, 1, 20, 3, 3, 0.01, 0.9, 0.9999999, 0.999999, 100, EPS)
     attempts = (1000 + 30 * 1000) * 800
     for mode in ("replay", "production"):
@@ -55,7 +55,7 @@ def c1():
 
 def c2():
     """APT_preprocessor ladder + NPT on 3D +-J EA L=16, ~30 replicas."""
-    A, h = O.ea3d_pm_j(16, 2)
+    A, h = instances.ea3d_pm_j(16, 2)
     n = 4096
     cwd = os.getcwd(); os.chdir("/tmp")
     np.random.seed(2); random.seed(2)
@@ -116,7 +116,7 @@ def c2():
 
 def c3():
     """SK N=2000 dense Gaussian, 64 betas x 32 runs = 2048 replicas on the tensor-core path."""
-    J, h = O.sk_gaussian(2000, 3)
+    J, h = instances.sk_gaussian(2000, 3)
     J = J / np.max(np.abs(J))
     prob = host.Problem(J, h)
     betas = np.tile(np.linspace(0.2, 3.0, 64), 32)
@@ -132,7 +132,7 @@ def c3():
 
 def c4():
     """APT_ICM on 3D +-J EA L=32, reference semantics (10 sub-replicas per beta), reduced sweeps."""
-    A, h = O.ea3d_pm_j(32, 4)
+    A, h = instances.ea3d_pm_j(32, 4)
     betas = np.linspace(0.3, 1.5, 8)
     np.random.seed(4); random.seed(4)
     cwd = os.getcwd(); os.chdir("/tmp")

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "nonlocal-monte-
 import numpy as np
 import scipy.sparse as sp
 from nlmc_b200 import NMC, NPT, APT_preprocessor, APT_ICM
-from oracle import oracle as O
+from nlmc_b200 import instances as O  # generators of the benchmark instances
 os.chdir(tempfile.mkdtemp())
 eps = np.finfo(float).eps
 

@@ -6,8 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "nonlocal-monte-
 import json
 import numpy as np
 from nlmc_b200 import _lib, host, nmc_core
-from oracle import oracle as O
-
+from nlmc_b200 import instances as O  # generators of the benchmark instances
 def emit(**kw): print(json.dumps(kw), flush=True)
 eps = np.finfo(float).eps
 host.Problem(np.array([[0.0, 1.0], [1.0, 0.0]]), np.zeros(2))  # CUDA context

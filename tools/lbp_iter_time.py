@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "nonlocal-monte-carlo_b200"))
 import numpy as np
 from nlmc_b200 import _lib, host
-from oracle import oracle as O
+from nlmc_b200 import instances as O  # generators of the benchmark instances
 for name, (J, h), beta in (("EA L=16", O.ea3d_pm_j(16, 2), 13.6), ("C1 N=800", O.random_pm_graph(800, 0.06, 1), 3.0), ("EA L=32", O.ea3d_pm_j(32, 4), 3.0)):
     prob = host.Problem(J, h)
     lbp = _lib.Lbp(prob.inst)

@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "nonlocal-monte-carlo_b200"))
 import numpy as np
 from nlmc_b200 import NMC, _lib, nmc_core
-from oracle import oracle as O
+from nlmc_b200 import instances as O  # generators of the benchmark instances
 J, h = O.random_pm_graph(800, 0.06, 1)
 orig = _lib.Replicas.sweep_replay
 orig_phase = _lib.Replicas.set_phase

@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "nonlocal-monte-carlo_b200"))
 import numpy as np
 from nlmc_b200 import NPT, host
-from oracle import oracle as O
+from nlmc_b200 import instances as O  # generators of the benchmark instances
 A, h = O.ea3d_pm_j(16, 2)
 betas = np.linspace(0.5, 3.0, 30)
 host.Problem(np.array([[0.0, 1.0], [1.0, 0.0]]), np.zeros(2))

@@ -3,7 +3,7 @@ import sys
 sys.path.insert(0, "nonlocal-monte-carlo_b200"); sys.path.insert(0, ".")
 import numpy as np
 from nlmc_b200 import _lib, host
-from oracle import oracle as O
+from nlmc_b200 import instances as O  # generators of the benchmark instances
 n_split = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 J, h = O.sk_gaussian(2000, 3); J = J / np.max(np.abs(J))
 prob = host.Problem(J, h)

@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "nonlocal-monte-carlo_b200"))
 import numpy as np
 from nlmc_b200 import _lib, host, nmc_core
-from oracle import oracle as O
+from nlmc_b200 import instances as O  # generators of the benchmark instances
 eps = np.finfo(float).eps
 for name, (J, h), beta in (("EA L=16", O.ea3d_pm_j(16, 2), 1 / 0.366838 * 5), ("C1 N=800", O.random_pm_graph(800, 0.06, 1), 3.0)):
     prob = host.Problem(J, h)

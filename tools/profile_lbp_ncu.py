@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "nonlocal-monte-carlo_b200"))
 import numpy as np
 from nlmc_b200 import _lib, host
-from oracle import oracle as O
+from nlmc_b200 import instances as O  # generators of the benchmark instances
 which = sys.argv[1] if len(sys.argv) > 1 else "ea"
 J, h = O.ea3d_pm_j(16, 2) if which == "ea" else O.random_pm_graph(800, 0.06, 1)
 beta = 1 / 0.366838 * 5 if which == "ea" else 3.0
