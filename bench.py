@@ -47,6 +47,44 @@ def ea3d_csr(L: int, seed: int):
     return instances.ea3d_pm_j(L, seed)[0]
 
 
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={device_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows]
+        try:
+            sm = [float(r[0]) for r in rows]
+            reasons = []
+            for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+                if any(r[col].lower().startswith("active") for r in rows):
+                    reasons.append(name)
+            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                    "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+        except Exception:
+            return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -169,6 +207,7 @@ def run_ours(args, rank, world, local_rank):
     numa_node = bind_to_gpu_numa_node(device) if world > 1 else None
     L, n_beta, n_ladders, spm, pairs = args.L, args.n_beta, args.n_ladders, args.spm, args.pairs
     betas = np.linspace(0.2, 2.0, n_beta)
+    sampler = ClockSampler(device) if rank == 0 else None  # started early: nvidia-smi needs ~0.1 s before its first row
     A = ea3d_csr(L, 5)
     prob = host.Problem(A, np.zeros(A.shape[0]), device=device)
     # every rank owns its own block of ladders; streams are keyed by the global ladder index
@@ -187,7 +226,6 @@ def run_ours(args, rank, world, local_rank):
         msc.round(spm, pairs)
     msc.sync()
     barrier()
-    sampler = ClockSampler(device) if rank == 0 else None
     t_wall0 = time.perf_counter()
     msc.timer_mark(0)
     for _ in range(args.steps):
