@@ -105,3 +105,27 @@ def test_find_clusters_matches_oracle():
         a = nmc_core.find_clusters(P(), marg, thr_i, thr_c, 0.01)
         b = O.find_clusters(csr, marg, thr_i, thr_c, 0.01)
         assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_bench_module_is_whole_and_reference_arm_runs():
+    """bench.py keeps every piece of its contract (a past edit once dropped the clock sampler) and its reference arm
+    -- the oracle port on the host cores -- prints the contract's JSON line on a tiny workload."""
+    import importlib.util
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name in ("ClockSampler", "ea3d_csr", "measured_peaks", "ncu_traffic", "cpu_port_rate", "run_reference",
+                 "workload_config", "run_ours", "main"):
+        assert hasattr(mod, name), name
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--L", "8", "--n-beta", "4",
+                          "--steps", "1", "--warmup", "1", "--ref-sweeps", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
