@@ -45,12 +45,14 @@ struct nlmc_col {
     unsigned long long seed = 0;
     size_t smem_bytes = 0, smem_bytes_nocsr = 0;
     int sm_count = 148;
+    int threads = 256;  // CTA size of the sweep kernel (kColThreads or kColThreadsFew)
     cudaStream_t stream = nullptr;
 };
 
 namespace nlmc {
 
-constexpr int kColThreads = 256;
+constexpr int kColThreads = 256;       // threads per CTA when many replicas share the GPU
+constexpr int kColThreadsFew = 1024;   // ... and when replicas are few: more sites of a colour per pass, shorter sweeps
 
 struct PhiloxC {
     uint32_t k0, k1;
@@ -93,12 +95,12 @@ struct ColArgs {
 };
 
 template <bool kSmemCsr, typename ColT, typename ValT>
-__global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
+__global__ void __launch_bounds__(kColThreadsFew) col_sweep_kernel(ColArgs a) {
     constexpr bool kVal8 = sizeof(ValT) == 1;  // integer couplings stored as int8 and shifted into fixed point at use
     extern __shared__ __align__(16) uint8_t sm[];
-    __shared__ long long red[kColThreads / 32];
+    __shared__ long long red[kColThreadsFew / 32];
     __shared__ double s_E;
-    const int n = a.n, tid = threadIdx.x, r = blockIdx.x;
+    const int n = a.n, tid = threadIdx.x, r = blockIdx.x, nthr = (int)blockDim.x;
     int32_t *fld = reinterpret_cast<int32_t *>(sm);                    // [n] fixed-point local fields (incl. h)
     int32_t *hfx = fld + n;                                            // [n] fixed-point h
     int32_t *rp_s = hfx + n;
@@ -110,13 +112,13 @@ __global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
     int8_t *g_spin = a.spins + (size_t)r * n;
     const uint8_t *g_mode = a.modes ? a.modes + (size_t)r * n : nullptr;
     if (kSmemCsr) {
-        for (int i = tid; i <= n; i += kColThreads) rp_s[i] = a.rp[i];
-        for (int p = tid; p < a.nnz; p += kColThreads) {
+        for (int i = tid; i <= n; i += nthr) rp_s[i] = a.rp[i];
+        for (int p = tid; p < a.nnz; p += nthr) {
             val_s[p] = kVal8 ? (ValT)a.val8[p] : (ValT)a.valfx[p];
             col_s[p] = sizeof(ColT) == 2 ? (ColT)a.col16[p] : (ColT)a.ci[p];
         }
     }
-    for (int i = tid; i < n; i += kColThreads) {
+    for (int i = tid; i < n; i += nthr) {
         spin[i] = g_spin[i];
         mode[i] = g_mode ? g_mode[i] : 0;
         hfx[i] = __double2int_rn(a.h[i] * a.scale);
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
         if (kVal8) return (int)(kSmemCsr ? (int)val_s[p] : (int)a.val8[p]) << a.shift;
         return kSmemCsr ? (int)val_s[p] : a.valfx[p];
     };
-    for (int i = tid; i < n; i += kColThreads) {  // initial fields, exact integer arithmetic
+    for (int i = tid; i < n; i += nthr) {  // initial fields, exact integer arithmetic
         int f = hfx[i];
         const int e = row_begin(i + 1);
         for (int p = row_begin(i); p < e; ++p) f += val_of(p) * (int)spin[col_of(p)];
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
     const float inv_tx = (float)(1.0 / a.temp_x);
     const PhiloxC rng{a.seed_lo, a.seed_hi ^ 0x434f4c52u};
     const uint32_t rid = (uint32_t)(a.replica_offset + r);
-    const int G = a.group, gl = tid & (G - 1), sites_per_pass = kColThreads / G;
+    const int G = a.group, gl = tid & (G - 1), sites_per_pass = nthr / G;
     const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((tid & 31) & ~(G - 1));
     double best = a.bestE ? a.bestE[r] : 0.0;
     int n_rec = 0;
@@ -173,14 +175,14 @@ __global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
         const bool want_E = a.out_E != nullptr || a.bestE != nullptr;
         if (want_E) {  // E = -(m^T J m / 2 + m^T h) = -1/2 sum_i s_i (f_i + h_i), exact in fixed point
             long long part = 0;
-            for (int i = tid; i < n; i += kColThreads) part += (long long)spin[i] * ((long long)fld[i] + (long long)hfx[i]);
+            for (int i = tid; i < n; i += nthr) part += (long long)spin[i] * ((long long)fld[i] + (long long)hfx[i]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             if ((tid & 31) == 0) red[tid >> 5] = part;
             __syncthreads();
             if (tid == 0) {
                 long long v = 0;
-                for (int w = 0; w < kColThreads / 32; ++w) v += red[w];
+                for (int w = 0; w < nthr / 32; ++w) v += red[w];
                 s_E = -0.5 * (double)v / a.scale;
             }
             __syncthreads();
@@ -189,17 +191,17 @@ __global__ void __launch_bounds__(kColThreads) col_sweep_kernel(ColArgs a) {
             if (a.bestE && E < best) {  // strict improvement: the first minimum wins, like np.argmin
                 best = E;
                 int8_t *dst = a.bestS + (size_t)r * n;
-                for (int i = tid; i < n; i += kColThreads) dst[i] = spin[i];
+                for (int i = tid; i < n; i += nthr) dst[i] = spin[i];
             }
         }
         if (a.out_spins && a.record_every > 0 && s % a.record_every == 0) {
             int8_t *dst = a.out_spins + ((size_t)n_rec * a.R + r) * n;
-            for (int i = tid; i < n; i += kColThreads) dst[i] = spin[i];
+            for (int i = tid; i < n; i += nthr) dst[i] = spin[i];
             ++n_rec;
         }
         __syncthreads();  // copies of this sweep's state are done before the next sweep changes it
     }
-    for (int i = tid; i < n; i += kColThreads) g_spin[i] = spin[i];
+    for (int i = tid; i < n; i += nthr) g_spin[i] = spin[i];
     if (a.bestE && tid == 0) a.bestE[r] = best;
 }
 
@@ -310,8 +312,6 @@ int nlmc_col_create(nlmc_instance *I, int n_replicas, const double *betas, int r
         max_row = std::max(max_row, srow);
     }
     Cc->fx_shift = std::max(0, std::min(30, (int)std::floor(std::log2(1073741824.0 / max_row))));
-    Cc->group = 1;
-    while (Cc->group < 32 && Cc->group * 2 * max_colour <= kColThreads) Cc->group *= 2;
     const size_t base = 2 * sizeof(int32_t) * (size_t)n + 2 * (size_t)n + 64;
     bool all_small_int = nnz > 0;
     for (int p = 0; p < nnz && all_small_int; ++p) {
@@ -327,6 +327,10 @@ int nlmc_col_create(nlmc_instance *I, int n_replicas, const double *betas, int r
     cudaDeviceGetAttribute(&Cc->sm_count, cudaDevAttrMultiProcessorCount, I->device);
     Cc->csr_in_smem = with_csr <= 220 * 1024 && n_replicas <= 2 * Cc->sm_count;
     Cc->smem_bytes = Cc->csr_in_smem ? with_csr : base;
+    // few replicas: one big CTA per replica (all sites of a colour in one or two passes); many: small CTAs, more per SM
+    Cc->threads = n_replicas <= 2 * Cc->sm_count ? kColThreadsFew : kColThreads;
+    Cc->group = 1;
+    while (Cc->group < 32 && Cc->group * 2 * max_colour <= Cc->threads) Cc->group *= 2;
     Cc->smem_bytes_nocsr = base;
     if (Cc->smem_bytes > 220 * 1024) {
         set_error("nlmc_col_create: %d spins do not fit in shared memory (one CTA per replica)", n);
@@ -484,7 +488,7 @@ int nlmc_col_sweep(nlmc_col *Cc, int n_sweeps, const double *beta_sched, int rec
 #define NLMC_COL_LAUNCH(SMEM, COLT, VALT)                                                                              \
     do {                                                                                                              \
         e = cudaFuncSetAttribute(col_sweep_kernel<SMEM, COLT, VALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-        if (e == cudaSuccess) col_sweep_kernel<SMEM, COLT, VALT><<<(unsigned)R, kColThreads, smem, Cc->stream>>>(a);  \
+        if (e == cudaSuccess) col_sweep_kernel<SMEM, COLT, VALT><<<(unsigned)R, (unsigned)Cc->threads, smem, Cc->stream>>>(a);  \
     } while (0)
     if (Cc->csr_in_smem && Cc->small_cols) {
         if (Cc->int8_vals) NLMC_COL_LAUNCH(true, uint16_t, int8_t); else NLMC_COL_LAUNCH(true, uint16_t, int32_t);
