@@ -19,6 +19,7 @@
 // tracking of the lowest-energy state (m_init = M[:, argmin E], nmc.py:394-395) all happen inside the kernel.
 // Random numbers: Philox4x32-10 keyed by (seed; global replica id, site, sweep).
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 
 #include "nlmc_common.cuh"
@@ -46,6 +47,9 @@ struct nlmc_col {
     size_t smem_bytes = 0, smem_bytes_nocsr = 0;
     int sm_count = 148;
     int threads = 256;  // CTA size of the sweep kernel (kColThreads or kColThreadsFew)
+    bool state_global = false;   // n too large for shared memory: fields / spins / modes of each replica live in global memory
+    uint8_t *state_ws = nullptr; // [R][state_stride] workspace of that variant
+    size_t state_stride = 0;
     cudaStream_t stream = nullptr;
 };
 
@@ -73,6 +77,8 @@ struct PhiloxC {
 
 struct ColArgs {
     int n, nnz, n_colours, n_sweeps, record_every, replica_offset, group;
+    uint8_t *state_ws;      // NULL: state in shared memory
+    size_t state_stride;
     double scale;  // 2^fx_shift
     const int32_t *rp, *ci;
     const double *val, *h;
@@ -101,7 +107,10 @@ __global__ void __launch_bounds__(kColThreadsFew) col_sweep_kernel(ColArgs a) {
     __shared__ long long red[kColThreadsFew / 32];
     __shared__ double s_E;
     const int n = a.n, tid = threadIdx.x, r = blockIdx.x, nthr = (int)blockDim.x;
-    int32_t *fld = reinterpret_cast<int32_t *>(sm);                    // [n] fixed-point local fields (incl. h)
+    // state of this replica: shared memory, or (instances too large for it) a slice of a global workspace -- same code,
+    // the atomics on the fields then go to L2
+    uint8_t *state = a.state_ws ? a.state_ws + (size_t)blockIdx.x * a.state_stride : sm;
+    int32_t *fld = reinterpret_cast<int32_t *>(state);                 // [n] fixed-point local fields (incl. h)
     int32_t *hfx = fld + n;                                            // [n] fixed-point h
     int32_t *rp_s = hfx + n;
     ColT *col_s = reinterpret_cast<ColT *>(rp_s + (kSmemCsr ? n + 1 : 0));
@@ -124,6 +133,10 @@ __global__ void __launch_bounds__(kColThreadsFew) col_sweep_kernel(ColArgs a) {
         hfx[i] = __double2int_rn(a.h[i] * a.scale);
     }
     __syncthreads();
+    // in the global-workspace variant other threads' atomics and stores land in L2: read around the (incoherent) L1
+    const bool gstate = a.state_ws != nullptr;
+    auto ld_fld = [&](int i) -> int { return gstate ? __ldcg(fld + i) : fld[i]; };
+    auto ld_spin = [&](int i) -> int { return gstate ? (int)__ldcg(reinterpret_cast<const signed char *>(spin) + i) : (int)spin[i]; };
     auto row_begin = [&](int i) { return kSmemCsr ? rp_s[i] : a.rp[i]; };
     auto col_of = [&](int p) -> int { return kSmemCsr ? (int)col_s[p] : a.ci[p]; };
     auto val_of = [&](int p) -> int {
@@ -133,7 +146,7 @@ __global__ void __launch_bounds__(kColThreadsFew) col_sweep_kernel(ColArgs a) {
     for (int i = tid; i < n; i += nthr) {  // initial fields, exact integer arithmetic
         int f = hfx[i];
         const int e = row_begin(i + 1);
-        for (int p = row_begin(i); p < e; ++p) f += val_of(p) * (int)spin[col_of(p)];
+        for (int p = row_begin(i); p < e; ++p) f += val_of(p) * ld_spin(col_of(p));
         fld[i] = f;
     }
     __syncthreads();
@@ -157,11 +170,11 @@ __global__ void __launch_bounds__(kColThreadsFew) col_sweep_kernel(ColArgs a) {
                 const int md = mode[i];
                 if (md == 2) continue;  // frozen (the reference pins these spins with h = +-1e4, nmc.py:381,400)
                 // backbone rows of J and h are divided by temp_x (nmc.py:379-380) <=> beta/temp_x for this site
-                const float x = (md == 1 ? m2b * inv_tx : m2b) * ((float)fld[i] * inv_scale);
+                const float x = (md == 1 ? m2b * inv_tx : m2b) * ((float)ld_fld(i) * inv_scale);
                 const uint4 rnd = rng(rid, (uint32_t)i, sweep, 0u);
                 const float u = ((float)(rnd.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
                 const int s_new = u * (1.0f + __expf(x)) < 1.0f ? 1 : -1;   // u < 1/(1+exp(-2 beta f))
-                const int s_old = spin[i];
+                const int s_old = ld_spin(i);
                 __syncwarp(gmask);  // every lane of the group has read spin[i] and fld[i]
                 if (s_new != s_old) {
                     if (gl == 0) spin[i] = (int8_t)s_new;
@@ -175,7 +188,7 @@ __global__ void __launch_bounds__(kColThreadsFew) col_sweep_kernel(ColArgs a) {
         const bool want_E = a.out_E != nullptr || a.bestE != nullptr;
         if (want_E) {  // E = -(m^T J m / 2 + m^T h) = -1/2 sum_i s_i (f_i + h_i), exact in fixed point
             long long part = 0;
-            for (int i = tid; i < n; i += nthr) part += (long long)spin[i] * ((long long)fld[i] + (long long)hfx[i]);
+            for (int i = tid; i < n; i += nthr) part += (long long)ld_spin(i) * ((long long)ld_fld(i) + (long long)hfx[i]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             if ((tid & 31) == 0) red[tid >> 5] = part;
@@ -191,17 +204,17 @@ __global__ void __launch_bounds__(kColThreadsFew) col_sweep_kernel(ColArgs a) {
             if (a.bestE && E < best) {  // strict improvement: the first minimum wins, like np.argmin
                 best = E;
                 int8_t *dst = a.bestS + (size_t)r * n;
-                for (int i = tid; i < n; i += nthr) dst[i] = spin[i];
+                for (int i = tid; i < n; i += nthr) dst[i] = (int8_t)ld_spin(i);
             }
         }
         if (a.out_spins && a.record_every > 0 && s % a.record_every == 0) {
             int8_t *dst = a.out_spins + ((size_t)n_rec * a.R + r) * n;
-            for (int i = tid; i < n; i += nthr) dst[i] = spin[i];
+            for (int i = tid; i < n; i += nthr) dst[i] = (int8_t)ld_spin(i);
             ++n_rec;
         }
         __syncthreads();  // copies of this sweep's state are done before the next sweep changes it
     }
-    for (int i = tid; i < n; i += nthr) g_spin[i] = spin[i];
+    for (int i = tid; i < n; i += nthr) g_spin[i] = (int8_t)ld_spin(i);
     if (a.bestE && tid == 0) a.bestE[r] = best;
 }
 
@@ -246,7 +259,8 @@ extern "C" {
 int nlmc_col_destroy(nlmc_col *Cc) {
     if (!Cc) return NLMC_OK;
     cudaSetDevice(Cc->inst->device);
-    void *ptrs[] = {Cc->site_order, Cc->colour_ptr, Cc->col16, Cc->valfx, Cc->val8, Cc->spins, Cc->beta, Cc->modes, Cc->bestE, Cc->bestS};
+    void *ptrs[] = {Cc->site_order, Cc->colour_ptr, Cc->col16, Cc->valfx, Cc->val8, Cc->spins, Cc->beta, Cc->modes, Cc->bestE, Cc->bestS,
+                    Cc->state_ws};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (Cc->stream) cudaStreamDestroy(Cc->stream);
     delete Cc;
@@ -332,10 +346,14 @@ int nlmc_col_create(nlmc_instance *I, int n_replicas, const double *betas, int r
     Cc->group = 1;
     while (Cc->group < 32 && Cc->group * 2 * max_colour <= Cc->threads) Cc->group *= 2;
     Cc->smem_bytes_nocsr = base;
-    if (Cc->smem_bytes > 220 * 1024) {
-        set_error("nlmc_col_create: %d spins do not fit in shared memory (one CTA per replica)", n);
-        delete Cc;
-        return NLMC_ERR_UNSUPPORTED;
+    if (Cc->smem_bytes > 220 * 1024 || getenv("NLMC_COL_FORCE_GLOBAL")) {  // state does not fit in shared memory: keep it in a global workspace (slower, any n)
+        Cc->state_global = true;
+        Cc->csr_in_smem = false;
+        Cc->state_stride = (base + 255) & ~(size_t)255;
+        Cc->smem_bytes = 64;
+        Cc->threads = kColThreadsFew;
+        Cc->group = 1;
+        while (Cc->group < 32 && Cc->group * 2 * max_colour <= Cc->threads) Cc->group *= 2;
     }
     std::vector<int32_t> v32((size_t)std::max(nnz, 1));
     std::vector<uint16_t> c16((size_t)std::max(nnz, 1));
@@ -359,7 +377,8 @@ int nlmc_col_create(nlmc_instance *I, int n_replicas, const double *betas, int r
               cudaMemcpy(Cc->site_order, order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(Cc->colour_ptr, cptr.data(), sizeof(int32_t) * cptr.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(Cc->col16, c16.data(), sizeof(uint16_t) * c16.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMemcpy(Cc->valfx, v32.data(), sizeof(int32_t) * v32.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+              cudaMemcpy(Cc->valfx, v32.data(), sizeof(int32_t) * v32.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              (!Cc->state_global || cudaMalloc(&Cc->state_ws, Cc->state_stride * (size_t)n_replicas) == cudaSuccess);
     if (!ok) {
         set_error("nlmc_col_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         nlmc_col_destroy(Cc);
@@ -478,6 +497,7 @@ int nlmc_col_sweep(nlmc_col *Cc, int n_sweeps, const double *beta_sched, int rec
     a.n = Cc->n; a.nnz = I->nnz; a.n_colours = Cc->n_colours; a.n_sweeps = n_sweeps; a.record_every = record_every;
     a.replica_offset = Cc->replica_offset;
     a.rp = I->row_ptr; a.ci = I->col; a.val = I->val; a.h = I->h; a.col16 = Cc->col16; a.valfx = Cc->valfx;
+    a.state_ws = Cc->state_ws; a.state_stride = Cc->state_stride;
     a.group = Cc->group; a.scale = std::ldexp(1.0, Cc->fx_shift); a.val8 = Cc->val8; a.shift = Cc->fx_shift;
     a.site_order = Cc->site_order; a.colour_ptr = Cc->colour_ptr;
     a.spins = Cc->spins; a.beta = Cc->beta; a.beta_sched = d_sched; a.modes = Cc->modes_on ? Cc->modes : nullptr; a.temp_x = Cc->temp_x;

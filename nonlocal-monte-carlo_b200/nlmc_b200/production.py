@@ -96,8 +96,9 @@ def _npt_run_msc(obj, prob, beta_list):
 # NMC phases as per-site modes
 # ---------------------------------------------------------------------------------------------------
 def _generic_engine(prob: host.Problem, betas, seed: int):
-    """Sparse instances (mean degree <= 128, fits one CTA's shared memory) take the graph-coloured kernel; dense
-    ones (SK) the tensor-core path, where a colouring would degenerate to one site per colour."""
+    """Sparse instances (mean degree <= 128) take the graph-coloured kernel (state in shared memory, or in a global
+    workspace when it does not fit); dense ones (SK) the tensor-core path, where a colouring would degenerate to one
+    site per colour."""
     betas = np.asarray(betas, dtype=np.float64)
     mean_degree = len(prob.val) / max(prob.n, 1)
     if mean_degree <= 128 and not os.environ.get("NLMC_FORCE_DENSE"):

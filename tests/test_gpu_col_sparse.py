@@ -149,3 +149,46 @@ def test_large_sparse_instance_csr_in_global(nl):
     _, E = c.sweep_record(5, want_states=False)
     assert np.array_equal(O.energy(O.Csr(A), h, c.get_spins()), E[-1])
     assert E[-1, 1] < E[-1, 0] < 0
+
+
+def test_global_workspace_variant_equals_shared_memory_variant(nl, monkeypatch):
+    """Instances whose state does not fit in shared memory keep fields / spins in a global workspace (same kernel, atomics
+    in L2).  Forced here on a small instance: trajectories, energies and best states must equal the shared-memory run;
+    and a 60,000-spin sparse graph (too large for shared memory) runs through it."""
+    from nlmc_b200 import instances
+    J, h = instances.random_pm_graph(150, 0.08, 3)
+    h = 0.25 * np.random.RandomState(1).randn(150)
+    prob = nl.host.Problem(J, h)
+    betas = np.linspace(0.4, 1.6, 6)
+    out = []
+    for force in (False, True):
+        if force:
+            monkeypatch.setenv("NLMC_COL_FORCE_GLOBAL", "1")
+        c = nl.lib.Col(prob.inst, betas, seed=11)
+        c.best_reset()
+        states, E = c.sweep_record(12, track_best=True)
+        out.append((states, E, c.best_get(), c.get_spins()))
+        c.close()
+    monkeypatch.delenv("NLMC_COL_FORCE_GLOBAL")
+    for a, b in zip(out[0], out[1]):
+        if isinstance(a, tuple):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        else:
+            assert np.array_equal(a, b)
+    # a sparse ring-with-chords graph of 60,000 spins: 10 n bytes of state > 227 KB
+    import scipy.sparse as sp
+    n = 60000
+    rs = np.random.RandomState(5)
+    i = np.arange(n)
+    rows = np.concatenate([i, i]); cols = np.concatenate([(i + 1) % n, (i + 7919) % n])
+    v = rs.choice([-1.0, 1.0], size=2 * n)
+    A = sp.coo_matrix((np.concatenate([v, v]), (np.concatenate([rows, cols]), np.concatenate([cols, rows]))), shape=(n, n)).tocsr()
+    big = nl.host.Problem(A, np.zeros(n))
+    c = nl.lib.Col(big.inst, [0.5, 1.5], seed=2)
+    E0 = c.energies()
+    c.sweep(20)
+    E1 = c.energies()
+    S = c.get_spins()
+    assert set(np.unique(S)) <= {-1, 1} and np.all(E1 < E0)
+    np.testing.assert_array_equal(E1, big.inst.energy_states(S))   # integer couplings: exact
+    c.close()
