@@ -103,6 +103,8 @@ int nlmc_energy_states(nlmc_instance *inst, int n_states, const int8_t *states /
  * from one lambda to the next.  The lambda schedule, the divergence rules (nmc.py:142-161) and
  * find_clusters (nmc.py:257-318) stay on the host (nlmc_b200/nmc_core.py): they are a few scalar
  * comparisons and set operations per call.
+ *   nlmc_lbp_create  requires a symmetric sparsity pattern and rows sorted by column (numpy sums the reference's dense
+ *                    rows and columns in index order; csr_matrix(dense J) delivers exactly that)
  *   nlmc_lbp_reset   u_msgs = J * m_star, h_msgs = 0                       (nmc.py:128-129)
  *   nlmc_lbp_epsilon epsilon_i = |h_i| + sum_j |J_ij|                      (nmc.py:353)
  *   nlmc_lbp_step    one LoopyBeliefPropagation call with h + lambda*m_star*epsilon (nmc.py:133-139);

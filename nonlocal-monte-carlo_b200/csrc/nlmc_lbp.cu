@@ -162,8 +162,7 @@ struct SumProgramBuilder {
     const int32_t *pos;
     int cnt, cur = 0, depth = 0, max_depth = 0;
     std::vector<int32_t> *out;
-    const int32_t *entry = nullptr;  // entry index within the row of the q-th smallest column (NULL: identity)
-    void push(int q) { out->push_back(entry ? entry[q] : q); max_depth = std::max(max_depth, ++depth); }
+    void push(int q) { out->push_back(q); max_depth = std::max(max_depth, ++depth); }
     void add() { out->push_back(-1); --depth; }
     bool chain(bool have, int q) {  // res += v(q)
         push(q);
@@ -439,18 +438,11 @@ int nlmc_lbp_create(nlmc_instance *I, nlmc_lbp **out) {
     for (int i = 0; i < n; ++i) {
         const int b = I->h_row_ptr[i], cnt = I->h_row_ptr[i + 1] - b;
         const int32_t *cols = I->h_col.data() + b;
-        std::vector<int32_t> sorted_cols, order;
-        if (!std::is_sorted(cols, cols + cnt)) {  // numpy sums the dense column in index order whatever the storage order
-            order.resize((size_t)cnt);
-            for (int q = 0; q < cnt; ++q) order[(size_t)q] = q;
-            std::sort(order.begin(), order.end(), [&](int x, int y) { return cols[x] < cols[y]; });
-            sorted_cols.resize((size_t)cnt);
-            for (int q = 0; q < cnt; ++q) sorted_cols[(size_t)q] = cols[order[(size_t)q]];
-            cols = sorted_cols.data();
-        }
+        // numpy sums dense rows / columns in index order: epsilon, the gather and the marginals all assume sorted rows
+        NLMC_REQUIRE(std::is_sorted(cols, cols + cnt),
+                     "nlmc_lbp_create: row %d of J is not sorted by column (scipy: A.sort_indices() on a copy)", i);
         SumProgramBuilder sb{cols, cnt};
         sb.out = &prog;
-        sb.entry = order.empty() ? nullptr : order.data();
         sb.emit(0, n);
         NLMC_REQUIRE(sb.max_depth <= kProgStack, "nlmc_lbp_create: summation program of row %d is too deep (%d)", i, sb.max_depth);
         prog_ptr[(size_t)i + 1] = (int32_t)prog.size();

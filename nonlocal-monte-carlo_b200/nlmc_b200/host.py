@@ -39,6 +39,20 @@ class Problem:
         else:
             self.lut_half = 0
 
+    def lbp_instance(self):
+        """Instance for the belief-propagation kernel (K5), which needs rows sorted by column (numpy sums the reference's
+        dense rows and columns in index order): the instance itself when scipy delivered sorted rows -- always the case
+        for the dense J the reference's LBP requires -- otherwise a sorted twin, built once."""
+        if getattr(self, "_lbp_inst", None) is None:
+            A = sp.csr_matrix((self.val, self.ci, self.rp), shape=(self.n, self.n))
+            if A.has_sorted_indices:
+                self._lbp_inst = self.inst
+            else:
+                A = A.copy()
+                A.sort_indices()
+                self._lbp_inst = _lib.Instance(A.indptr, A.indices, A.data, self.h, self.inst.device)
+        return self._lbp_inst
+
     def tanh_lut(self, beta_sched: np.ndarray):
         """tanh(beta*f) for every integer field f, computed with numpy's own tanh so that decisions on
         +-J instances are bit-equal to the reference's np.tanh(beta_run[jj] * x[kk]) (NMC/nmc.py:87).

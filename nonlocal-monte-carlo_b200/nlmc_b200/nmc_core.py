@@ -131,7 +131,7 @@ def nmc_subroutine_replay(prob: host.Problem, reps: "_lib.Replicas", m_star, *, 
         if BACKBONE_OVERRIDE is not None:
             return np.asarray(BACKBONE_OVERRIDE.pop(0), dtype=int)
         if lbp is None:
-            lbp = _lib.Lbp(prob.inst)
+            lbp = _lib.Lbp(prob.lbp_instance())
         cl = lbp_convexified(prob, lbp, m_star[g], lambda_start, lambda_end, lambda_reduction_factor, tolerance,
                              max_iterations, threshold_initial, threshold_cutoff, global_beta)
         if verbose:

@@ -186,7 +186,7 @@ class LbpMethods(_ProblemCache):
         rows, cols = np.nonzero(P)
         A = sp.csr_matrix((Jd[rows, cols], (rows, cols)), shape=(n, n))  # keeps explicit zeros
         prob = self._problem_for_pattern(A, h)
-        lbp = _lib.Lbp(prob.inst)
+        lbp = _lib.Lbp(prob.lbp_instance())
         try:
             r_of, c_of = prob.row_of, prob.ci
             lbp.set_messages(h_in[r_of, c_of], u_in[r_of, c_of], rep)
@@ -217,7 +217,7 @@ class LbpMethods(_ProblemCache):
         epsilon = np.asarray(epsilon, dtype=np.float64).reshape(-1)
         prob = self._problem_for(self.J, self.h)
         marginals, means, h_tildes, J_tildes = (defaultdict(list) for _ in range(4))
-        lbp = _lib.Lbp(prob.inst)
+        lbp = _lib.Lbp(prob.lbp_instance())
         try:
             lbp.reset(m_star)  # h_msgs = 0, u_msgs = J * m_star (nmc.py:128-129)
             lambda_val = lambda_start

@@ -114,7 +114,7 @@ def _backbones(prob, states, global_beta, nmc_kw):
     from .nmc_core import lbp_convexified
     lbp = getattr(prob, "_lbp_handle", None)  # reverse-entry index and summation programs are built once per instance
     if lbp is None:
-        lbp = prob._lbp_handle = _lib.Lbp(prob.inst)
+        lbp = prob._lbp_handle = _lib.Lbp(prob.lbp_instance())
     out = []
     for m_star in states:
         cl = lbp_convexified(prob, lbp, m_star.astype(np.float64), nmc_kw["lambda_start"], nmc_kw["lambda_end"],

@@ -188,3 +188,36 @@ def test_production_mode_methods_run(pkg, g):
                                         all_clusters=g["sub_clusters"])
     assert Mo.shape == (len(h), 18) and len(Eo) == 18 and mn == Eo.min()
     np.testing.assert_allclose(Eo, [-(Mo[:, i] @ J @ Mo[:, i] / 2 + Mo[:, i] @ h) for i in range(18)], rtol=1e-9)
+
+
+def test_lbp_on_csr_with_unsorted_rows(g):
+    """K5 needs rows sorted by column (numpy sums the reference's dense rows and columns in index order); the C ABI
+    says so, and the host hands it a sorted twin of an instance whose CSR is stored in another order -- the replay
+    sweeps keep the caller's storage order (scipy's J.dot order), the backbone search is independent of it."""
+    import scipy.sparse as sp
+    from nlmc_b200 import _lib, host, nmc_core
+    J, h, ms = g["J"], g["h"], g["lbp_m_star"].astype(float)
+    A = sp.csr_matrix(J)
+    rs = np.random.RandomState(0)
+    indices, data = A.indices.copy(), A.data.copy()
+    for i in range(A.shape[0]):
+        b, e = A.indptr[i], A.indptr[i + 1]
+        p = rs.permutation(e - b)
+        indices[b:e], data[b:e] = indices[b:e][p], data[b:e][p]
+    B = sp.csr_matrix((data, indices, A.indptr.copy()), shape=A.shape)
+    pa, pb = host.Problem(A, h), host.Problem(B, h)
+    assert np.array_equal(pb.ci, indices) and pa.lbp_instance() is pa.inst and pb.lbp_instance() is not pb.inst
+    with pytest.raises(_lib.NlmcError, match="not sorted"):
+        _lib.Lbp(pb.inst)
+    a = g["conv_args"]
+    outs = []
+    for prob in (pa, pb):
+        lbp = _lib.Lbp(prob.lbp_instance())
+        trace = []
+        cl = nmc_core.lbp_convexified(prob, lbp, ms, a[0], a[1], a[2], a[3], int(a[4]), a[5], a[6], a[7], trace=trace)
+        outs.append((cl, trace))
+        lbp.close()
+    (cla, ta), (clb, tb) = outs
+    assert [list(c) for c in cla] == [list(c) for c in clb] and len(ta) == len(tb)
+    for (la, ia, ma), (lb, ib, mb) in zip(ta, tb):
+        assert la == lb and ia == ib and np.array_equal(ma, mb)
