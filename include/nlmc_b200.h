@@ -232,7 +232,8 @@ int nlmc_dense_time_sweeps(nlmc_dense *d, int n_sweeps, float *out_ms);
 
 /* ---- K2a: sparse production path (any J, any h) -- graph-coloured parallel heat bath ---------------
  * Replaces MCMC (NMC/nmc.py:28-91 and copies) in production mode on arbitrary sparse instances: one CTA per
- * replica with spins, incrementally maintained local fields and (when it fits) the CSR in shared memory;
+ * replica with spins, incrementally maintained local fields and (when it fits) the CSR in shared memory -- or, for
+ * instances above ~22,000 spins, spins and fields in a global workspace (same kernel, any size);
  * sites of one colour are updated in parallel, colours in order; Philox4x32-10 keyed by
  * (seed; replica_offset + replica, site, sweep).
  *   nlmc_col_sweep  n_sweeps sweeps in ONE launch; beta_sched [n_sweeps][R] (optional) is the annealing schedule
