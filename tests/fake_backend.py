@@ -129,3 +129,72 @@ def install(monkeypatch):
     monkeypatch.setattr(_lib, "Replicas", FakeReplicas)
     monkeypatch.setattr(_lib, "Lbp", FakeLbp)
     monkeypatch.setattr(_lib, "icm_clusters", fake_icm_clusters)
+
+
+class FakeEngine:
+    """Oracle-backed stand-in for the production engines (_lib.Col / _lib.Dense API): R rows, sequential heat-bath
+    sweeps from a private RandomState, per-site NMC modes, best-state tracking -- statistically the same sampler, used
+    to exercise the HOST logic of production.py without a GPU."""
+
+    def __init__(self, prob, betas, seed):
+        self.prob, self.csr, self.h = prob, prob.inst.csr, prob.inst.h
+        self.betas = np.asarray(betas, dtype=np.float64).reshape(-1).copy()
+        self.R, self.n = len(self.betas), prob.n
+        self.rs = np.random.RandomState(seed % (2 ** 31))
+        self.spins = self.rs.choice([-1, 1], size=(self.R, self.n)).astype(np.int8)
+        self.modes, self.temp_x = None, 1.0
+        self.best_E, self.best_S = np.full(self.R, np.inf), self.spins.copy()
+
+    def set_betas(self, betas):
+        self.betas = np.asarray(betas, dtype=np.float64).reshape(-1).copy()
+
+    def set_spins(self, spins):
+        self.spins = np.asarray(spins, dtype=np.int8).reshape(self.R, self.n).copy()
+
+    def get_spins(self):
+        return self.spins.copy()
+
+    def set_site_modes(self, modes, temp_x=1.0):
+        self.modes = None if modes is None else np.asarray(modes, dtype=np.uint8).reshape(self.R, self.n).copy()
+        self.temp_x = float(temp_x)
+
+    def best_reset(self):
+        self.best_E[:] = np.inf
+
+    def best_get(self):
+        return self.best_S.copy(), self.best_E.copy()
+
+    def energies(self):
+        return O.energy(self.csr, self.h, self.spins)
+
+    def _one_sweep(self, betas):
+        c = self.csr
+        for r in range(self.R):
+            s = self.spins[r]
+            for i in self.rs.permutation(self.n):
+                md = 0 if self.modes is None else self.modes[r, i]
+                if md == 2:
+                    continue
+                b, e = c.rp[i], c.rp[i + 1]
+                f = float(c.val[b:e] @ s[c.ci[b:e]]) + self.h[i]
+                beta = betas[r] / self.temp_x if md == 1 else betas[r]
+                s[i] = 1 if self.rs.rand() < 1.0 / (1.0 + np.exp(-2.0 * beta * f)) else -1
+
+    def sweep(self, n_sweeps):
+        for _ in range(int(n_sweeps)):
+            self._one_sweep(self.betas)
+
+    def sweep_record(self, n_sweeps, record_every=1, track_best=False, beta_sched=None, want_states=True, want_energies=True):
+        states, E = [], np.empty((n_sweeps, self.R))
+        for j in range(int(n_sweeps)):
+            self._one_sweep(self.betas if beta_sched is None else np.asarray(beta_sched).reshape(n_sweeps, self.R)[j])
+            E[j] = self.energies()
+            if track_best:
+                better = E[j] < self.best_E
+                self.best_E[better], self.best_S[better] = E[j][better], self.spins[better]
+            if want_states and j % record_every == 0:
+                states.append(self.spins.copy())
+        return (np.array(states, dtype=np.int8).reshape(-1, self.R, self.n) if want_states else None), (E if want_energies else None)
+
+    def close(self):
+        pass

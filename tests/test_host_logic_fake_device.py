@@ -172,3 +172,58 @@ def test_public_lbp_convexified_and_subroutine(fake_device):
                                                 all_clusters=g["sub_clusters"].copy())
         assert np.array_equal(M, g[f"sub_{variant}_M"]) and np.array_equal(ac, g[f"sub_{variant}_clusters"])
         np.testing.assert_allclose(E, g[f"sub_{variant}_E"], rtol=1e-12)
+
+
+# ------------------------------------------------------------------ production-mode host logic (production.py)
+@pytest.fixture
+def fake_engines(fake_device, monkeypatch):
+    from nlmc_b200 import production
+    monkeypatch.setattr(production, "_generic_engine", lambda prob, betas, seed: fake_backend.FakeEngine(prob, betas, seed))
+    monkeypatch.setattr(production, "_msc_eligible", lambda prob: False)  # everything through the generic host path
+
+
+def test_production_host_logic_npt_and_nmc(fake_engines):
+    """NPT.run / NMC.run in production mode on a stand-in engine: return contracts, energies that belong to the returned
+    states, NMC replicas at global_beta, and only the last round recorded."""
+    from nlmc_b200 import NMC, NPT
+    from oracle import oracle as O
+    J, h = O.random_pm_graph(24, 0.25, 3)
+    h = 0.2 * np.random.RandomState(1).randn(24)
+    csr = O.Csr(J)
+    seed_all(4)
+    betas = np.array([0.4, 0.8, 1.2, 1.6])
+    M, E = NPT(J, h, mode="production").run(betas, 4, [False, False, True, True], num_sweeps_MCMC=24, num_sweeps_read=12,
+                                            num_swap_attempts=3, num_swapping_pairs=1, num_cycles=2, global_beta=2.0,
+                                            lambda_start=3, threshold_initial=0.99, threshold_cutoff=0.9,
+                                            max_iterations=50, tolerance=1e-9)
+    n, spm = 24, 8
+    assert M.shape == (4 * n, spm) and E.shape == (4,) and np.all(np.abs(M) == 1)
+    for r in range(4):
+        Er = O.energy(csr, h, M[r * n:(r + 1) * n, :4].T.astype(np.int8))   # num_sweeps_read // num_swap_attempts = 4
+        assert E[r] == pytest.approx(Er.min(), rel=1e-9)
+    seed_all(5)
+    Mo, Eo, mn = NMC(J, h, mode="production").run(10, 6, 2, 1, 2, 10.0, 2.0, 3, 0.01, 0.9, 0.99, 0.9, 50, 1e-9)
+    assert Mo.shape == (n, 2 * 3 * 3) and Eo.shape == (18,) and mn == Eo.min()
+    np.testing.assert_allclose(Eo, O.energy(csr, h, Mo.T.astype(np.int8)), rtol=1e-9)
+
+
+def test_production_host_logic_preprocessor_and_icm(fake_engines):
+    from nlmc_b200 import APT_ICM, APT_preprocessor
+    from oracle import oracle as O
+    J, h = O.random_pm_graph(20, 0.3, 7)
+    seed_all(6)
+    beta, sigma = APT_preprocessor(J, h, mode="production").run(num_sweeps_MCMC=12, num_sweeps_read=8, num_rng=5,
+                                                               beta_start=0.5, alpha=1.25, sigma_E_val=1000, beta_max=2.0,
+                                                               use_hash_table=0, num_cores=1)
+    assert len(beta) >= 2 and np.all(np.diff(beta) > 0) and len(sigma) in (len(beta), len(beta) - 1)
+    assert os.path.exists("beta_list_python.npy") and os.path.exists(os.path.join("Results", "data", "Energy_iter_1.npy"))
+    assert np.load(os.path.join("Results", "data", "Energy_iter_1.npy")).shape == (5, 8)
+    seed_all(7)
+    for spm in (1, 2):
+        M, E = APT_ICM(J, h, mode="production").run(np.array([0.4, 0.9, 1.4]), 3, num_sweeps_MCMC=3 * spm,
+                                                   num_sweeps_read=3 * spm, num_swap_attempts=3, num_swapping_pairs=1)
+        assert M.shape == (3 * 20, spm * 10) and E.shape == (3,) and np.all(np.abs(M) == 1)
+        csr = O.Csr(J)
+        for r in range(3):
+            Er = O.energy(csr, np.zeros(20), M[r * 20:(r + 1) * 20, :spm].T.astype(np.int8))
+            assert E[r] == pytest.approx(Er.min(), rel=1e-9)
