@@ -198,3 +198,84 @@ class FakeEngine:
 
     def close(self):
         pass
+
+
+class FakeMsc:
+    """Stand-in for _lib.Msc (bit-packed engine): n_beta x n_ladders replicas as plain int8 arrays, sequential heat-bath
+    sweeps, energies, replica exchange with the reference's pair selection -- for the HOST logic of the bit-packed
+    production paths (NPT.run without NMC replicas, APT_preprocessor, APT_ICM on lattices)."""
+
+    def __init__(self, inst, betas, n_ladders, seed=0, ladder_offset=0):
+        self.inst, self.csr, self.h = inst, inst.csr, inst.h
+        self.betas = np.asarray(betas, dtype=np.float64).reshape(-1).copy()
+        self.n_beta, self.n = len(self.betas), inst.n
+        self.n_ladders_requested = int(n_ladders)
+        self.n_ladders = ((int(n_ladders) + 127) // 128) * 128
+        self.live = min(self.n_ladders, max(1, int(n_ladders)))   # only the requested ladders are simulated
+        self.rs = np.random.RandomState(seed % (2 ** 31))
+        self.S = self.rs.choice([-1, 1], size=(self.n_beta, self.live, self.n)).astype(np.int8)
+        self.accepted = 0
+
+    def set_betas(self, betas):
+        self.betas = np.asarray(betas, dtype=np.float64).reshape(-1).copy()
+
+    def get_spins(self, b, lad):
+        return self.S[b, lad].copy()
+
+    def set_spins(self, b, lad, spins):
+        self.S[b, lad] = np.asarray(spins, dtype=np.int8)
+
+    def _sweep_once(self):
+        c = self.csr
+        for b in range(self.n_beta):
+            for lad in range(self.live):
+                s = self.S[b, lad]
+                for i in self.rs.permutation(self.n):
+                    lo, hi = c.rp[i], c.rp[i + 1]
+                    f = float(c.val[lo:hi] @ s[c.ci[lo:hi]]) + self.h[i]
+                    s[i] = 1 if self.rs.rand() < 1.0 / (1.0 + np.exp(-2.0 * self.betas[b] * f)) else -1
+
+    def sweep(self, n_sweeps):
+        for _ in range(int(n_sweeps)):
+            self._sweep_once()
+
+    def energies(self):
+        E = np.zeros((self.n_beta, self.n_ladders))
+        E[:, :self.live] = O.energy(self.csr, self.h, self.S.reshape(-1, self.n)).reshape(self.n_beta, self.live)
+        return E
+
+    def round(self, n_sweeps, num_pairs, fetch_energies=False):
+        self.sweep(n_sweeps)
+        E = self.energies()
+        for lad in range(self.live):
+            avail = list(range(self.n_beta - 1))
+            for _ in range(num_pairs):
+                if not avail:
+                    break
+                i = avail[self.rs.randint(len(avail))]
+                avail = [j for j in avail if abs(j - i) > 1]
+                if self.rs.rand() < min(1.0, np.exp((self.betas[i + 1] - self.betas[i]) * (E[i + 1, lad] - E[i, lad]))):
+                    self.S[[i, i + 1], lad] = self.S[[i + 1, i], lad]
+                    E[[i, i + 1], lad] = E[[i + 1, i], lad]
+                    self.accepted += 1
+        return E if fetch_energies else None
+
+    def swap_count(self, reset=False):
+        v = self.accepted
+        if reset:
+            self.accepted = 0
+        return v
+
+    def sweep_record(self, n_sweeps, ladder=0, energies=True):
+        Mrec = np.empty((n_sweeps, self.n_beta, self.n), dtype=np.int8) if ladder is not None else None
+        Erec = np.empty((n_sweeps, self.n_beta, self.n_ladders)) if energies else None
+        for j in range(int(n_sweeps)):
+            self._sweep_once()
+            if Mrec is not None:
+                Mrec[j] = self.S[:, ladder]
+            if Erec is not None:
+                Erec[j] = self.energies()
+        return Mrec, Erec
+
+    def close(self):
+        pass

@@ -227,3 +227,32 @@ def test_production_host_logic_preprocessor_and_icm(fake_engines):
         for r in range(3):
             Er = O.energy(csr, np.zeros(20), M[r * 20:(r + 1) * 20, :spm].T.astype(np.int8))
             assert E[r] == pytest.approx(Er.min(), rel=1e-9)
+
+
+def test_production_host_logic_bit_packed_paths(fake_device, monkeypatch):
+    """The host side of the bit-packed production paths (NPT.run without NMC replicas incl. num_runs, APT_preprocessor,
+    APT_ICM on a lattice) on a stand-in for _lib.Msc."""
+    from nlmc_b200 import APT_ICM, APT_preprocessor, NPT, _lib
+    from oracle import oracle as O
+    monkeypatch.setattr(_lib, "Msc", fake_backend.FakeMsc)
+    A, h = O.ea3d_pm_j(3, 2)
+    n = 27
+    csr = O.Csr(A)
+    betas = np.array([0.4, 0.9, 1.4])
+    seed_all(8)
+    obj = NPT(A, h, mode="production")
+    obj.num_runs = 2
+    M, E = obj.run(betas, 3, [False] * 3, num_sweeps_MCMC=12, num_sweeps_read=6, num_swap_attempts=3, num_swapping_pairs=1)
+    assert M.shape == (3 * n, 4) and E.shape == (3,) and obj.energies_all_runs.shape == (3, 2)
+    for r in range(3):
+        assert E[r] == O.energy(csr, h, M[r * n:(r + 1) * n, :2].T.astype(np.int8)).min()
+    seed_all(9)
+    beta, sigma = APT_preprocessor(A, h, mode="production").run(num_sweeps_MCMC=8, num_sweeps_read=6, num_rng=3, beta_start=0.5,
+                                                               alpha=1.25, sigma_E_val=1000, beta_max=1.5, use_hash_table=0)
+    assert len(beta) >= 2 and np.all(np.diff(beta) > 0)
+    seed_all(10)
+    M, E = APT_ICM(A.toarray(), h, mode="production").run(betas, 3, num_sweeps_MCMC=6, num_sweeps_read=6, num_swap_attempts=3,
+                                                         num_swapping_pairs=1)
+    assert M.shape == (3 * n, 2 * 10) and np.all(np.abs(M) == 1)
+    for r in range(3):
+        assert E[r] == O.energy(csr, np.zeros(n), M[r * n:(r + 1) * n, :2].T.astype(np.int8)).min()
