@@ -340,3 +340,37 @@ def test_k1_int_kernel_equals_general_kernel(nl, monkeypatch):
     csr = O.Csr(J)
     Mo, _ = O.mcmc(csr, h, m0[0], sched[0], perm=perm[0], u=u[0])
     assert np.array_equal(outs[0][0][0], Mo)
+
+
+@pytest.mark.parametrize("n,p,mode", [(300, 0.1, "warp"), (1100, 0.005, "thread"), (2500, 0.02, "warp"), (129, 0.5, "warp")])
+def test_k5_gather_reproduces_numpy_summation_order_beyond_one_block(nl, n, p, mode):
+    """numpy's pairwise sum recurses for more than 128 elements; the per-row summation programs K5 replays (resolved on
+    the host from the sparsity pattern) must reproduce that association exactly.  After ONE iteration from identical
+    inputs the column totals and the h messages are pure additions -- compared bit for bit with the oracle, which uses
+    numpy's own order -- on sizes that need 2-5 levels of the recursion, in both gather modes."""
+    from oracle import oracle as O
+    rs = np.random.RandomState(n)
+    iu = np.triu_indices(n, 1)
+    keep = rs.rand(len(iu[0])) < p
+    J = np.zeros((n, n))
+    J[iu[0][keep], iu[1][keep]] = rs.randn(int(keep.sum()))
+    J += J.T
+    h = 0.1 * rs.randn(n)
+    ms = rs.choice([-1.0, 1.0], size=n)
+    csr = O.Csr(J)
+    prob = nl.host.Problem(J, h)
+    assert (len(prob.val) >= 12 * n) == (mode == "warp")
+    lbp = nl.lib.Lbp(prob.inst)
+    eps_o = np.abs(h) + O._pairwise_rowsum_abs(csr)
+    assert np.array_equal(lbp.epsilon(), eps_o)
+    assert np.array_equal(eps_o, np.abs(h) + np.sum(np.abs(J), axis=1))        # the oracle itself against numpy
+    lbp.reset(ms)
+    lbp.step(0.8, 1.3, -1.0, 1)                                                  # tolerance < 0: exactly one iteration
+    hm, _, tot = lbp.get_messages()
+    u = np.ascontiguousarray(csr.val * ms[csr.ci]); hm_o = np.zeros_like(u); tot_o = np.zeros(n)
+    O.lbp(csr, np.ascontiguousarray(h + 0.8 * ms * eps_o), 1.3, u, hm_o, tot_o, -1.0, 1)
+    assert np.array_equal(tot, tot_o) and np.array_equal(hm, hm_o)
+    # and the dense numpy expression itself for the totals: h_lambda + np.sum(u_msgs[:, i]) over the strided column
+    U0 = J * ms.reshape(1, -1)
+    ref = np.array([(h + 0.8 * ms * eps_o)[i] + np.sum(U0[:, i]) for i in range(n)])
+    assert np.array_equal(tot, ref)
