@@ -374,3 +374,20 @@ def test_k5_gather_reproduces_numpy_summation_order_beyond_one_block(nl, n, p, m
     U0 = J * ms.reshape(1, -1)
     ref = np.array([(h + 0.8 * ms * eps_o)[i] + np.sum(U0[:, i]) for i in range(n)])
     assert np.array_equal(tot, ref)
+
+
+def test_k7_clusters_at_config_c4_size(nl):
+    """Houdayer disagreement clusters at the size of config C4 (3D EA L = 32, 32,768 spins) and on a random graph of
+    degree ~48: labels and cluster order identical to the oracle's breadth-first search."""
+    from nlmc_b200 import instances
+    from oracle import oracle as O
+    for J, h in (instances.ea3d_pm_j(32, 4), instances.random_pm_graph(800, 0.06, 1)):
+        csr = O.Csr(J)
+        prob = nl.host.Problem(J, h)
+        rs = np.random.RandomState(11)
+        s1 = rs.choice([-1, 1], size=(4, csr.n)).astype(np.int8)
+        s2 = np.where(rs.rand(4, csr.n) < np.array([0.02, 0.2, 0.45, 0.7])[:, None], -s1, s1).astype(np.int8)
+        labels, counts = nl.lib.icm_clusters(prob.inst, s1, s2)
+        for p in range(4):
+            lo, ko = O.disagreement_clusters(csr, s1[p], s2[p])
+            assert counts[p] == ko and np.array_equal(labels[p], lo), (csr.n, p)
