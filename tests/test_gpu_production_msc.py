@@ -377,3 +377,33 @@ def test_npt_production_energy_distribution_matches_reference(nl, tmp_cwd):
     assert abs(E_gpu.mean() - E_ref.mean()) <= 3.5 * err, (E_gpu.mean(), E_ref.mean(), err)
     assert E_gpu.min() == E_ref.min() or abs(E_gpu.min() - E_ref.min()) <= 4  # both reach the lowest levels
     assert abs(E_gpu.std(ddof=1) - E_ref.std(ddof=1)) <= 0.5 * max(E_gpu.std(ddof=1), E_ref.std(ddof=1)) + 1
+
+
+def test_full_size_c5_properties(nl):
+    """Config C5 at full size (3D +-J EA L = 64: 262,144 spins, 32 betas x 128 ladders = 4096 replicas): properties that
+    do not need an oracle run -- bit-sliced energies equal the fp64 energy kernel on unpacked replicas (exact integers),
+    a pure exchange step permutes each ladder's energies (checksum of sorted energies unchanged) and keeps the state a
+    permutation of itself, and two handles with one seed stay bit-identical (checksum of the packed state)."""
+    from nlmc_b200 import instances
+    A, h = instances.ea3d_pm_j(64, 5)
+    prob = nl.host.Problem(A, h)
+    betas = np.linspace(0.2, 2.0, 32)
+    a = nl.lib.Msc(prob.inst, betas, 128, seed=1000)
+    b = nl.lib.Msc(prob.inst, betas, 128, seed=1000)
+    assert a.n_words == 128 and a.n_colours == 2 and a.n_bonds == 3 * 64 ** 3
+    for m in (a, b):
+        m.round(3, 10)
+    Pa = a.get_packed()
+    assert np.array_equal(Pa, b.get_packed())                          # determinism at full size
+    E = a.energies()
+    assert E.shape == (32, 128) and np.all(E == np.round(E)) and np.all(E[-1] < E[0])   # colder is lower
+    picks = [(0, 0), (7, 31), (15, 64), (31, 127)]
+    S = np.stack([a.get_spins(bi, lad) for bi, lad in picks])
+    assert np.array_equal(prob.inst.energy_states(S), np.array([E[bi, lad] for bi, lad in picks]))
+    # exchange only: energies are permuted within each ladder, spin content is conserved
+    ones_before = int(np.unpackbits(Pa.view(np.uint8)).sum())
+    a.round(0, 10)
+    E2 = a.energies()
+    assert np.array_equal(np.sort(E2, axis=0), np.sort(E, axis=0)) and a.swap_count() > 0
+    assert int(np.unpackbits(a.get_packed().view(np.uint8)).sum()) == ones_before
+    a.close(); b.close()
