@@ -202,3 +202,33 @@ def test_npt_production_dense_with_nmc_replicas(nl, tmp_cwd):
     for r in range(4):
         Er = O.energy(csr, h / norm, M[r * 48:(r + 1) * 48, :10].T.astype(np.int8))
         assert abs(E[r] - Er.min()) < 1e-3
+
+
+def test_full_size_c3_properties(nl):
+    """Config C3 at full size (SK, N = 2000, 2048 replicas = 64 betas x 32 runs): the tensor-core fields against fp64 on
+    a sample of replicas, the engine's energies against the fp64 energy kernel (K4) on the states it returns, sweeps lower
+    the energy at every beta, and two handles with one seed stay identical."""
+    from nlmc_b200 import instances
+    J, h = instances.sk_gaussian(2000, 3)
+    J = J / np.max(np.abs(J))
+    prob = nl.host.Problem(J, h)
+    betas = np.tile(np.linspace(0.2, 3.0, 64), 32)
+    a = nl.lib.Dense(prob.inst, betas, n_split=3, seed=5)
+    b = nl.lib.Dense(prob.inst, betas, n_split=3, seed=5)
+    rs = np.random.RandomState(0)
+    S0 = rs.choice([-1, 1], size=(2048, 2000)).astype(np.int8)
+    for d in (a, b):
+        d.set_spins(S0)
+    H = a.fields()
+    rows = [0, 777, 2047]
+    exact = S0[rows].astype(np.float64) @ J.T
+    assert np.max(np.abs(H[rows] - exact)) <= 2.0 ** -17 * np.sqrt(2000) * 4
+    E0 = a.energies()
+    for d in (a, b):
+        d.sweep(3)
+    Sa = a.get_spins()
+    assert np.array_equal(Sa, b.get_spins()) and set(np.unique(Sa)) <= {-1, 1}
+    E1 = a.energies()
+    np.testing.assert_allclose(E1[rows], prob.inst.energy_states(Sa[rows]), rtol=1e-4)
+    assert np.all(E1.reshape(32, 64).mean(axis=0) < E0.reshape(32, 64).mean(axis=0))
+    a.close(); b.close()
