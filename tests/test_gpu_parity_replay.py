@@ -391,3 +391,34 @@ def test_k7_clusters_at_config_c4_size(nl):
         for p in range(4):
             lo, ko = O.disagreement_clusters(csr, s1[p], s2[p])
             assert counts[p] == ko and np.array_equal(labels[p], lo), (csr.n, p)
+
+
+@pytest.mark.parametrize("config", ["C1", "C2", "C4"])
+def test_k1_replay_at_config_sizes(nl, config):
+    """K1 against the oracle at the native sizes of the configs (C1: N = 800 random +-1 graph of degree ~48; C2: 3D EA
+    L = 16; C4: 3D EA L = 32), a plain replica and one in an NMC phase (rows at beta/temp_x, the rest frozen)."""
+    from nlmc_b200 import instances
+    from oracle import oracle as O
+    J, h = {"C1": lambda: instances.random_pm_graph(800, 0.06, 1), "C2": lambda: instances.ea3d_pm_j(16, 2),
+            "C4": lambda: instances.ea3d_pm_j(32, 4)}[config]()
+    csr = O.Csr(J)
+    n = csr.n
+    prob = nl.host.Problem(J, h)
+    rs = np.random.RandomState(17)
+    R, S = 2, 3
+    reps = nl.lib.Replicas(prob.inst, R)
+    m0 = rs.choice([-1, 1], size=(R, n)).astype(np.int8)
+    sched = np.array([[0.7] * S, [2.5] * S])
+    perm = np.stack([np.stack([rs.permutation(n) for _ in range(S)]) for _ in range(R)]).astype(np.int32)
+    u = rs.rand(R, S, n)
+    in_cl = rs.rand(n) < 0.6
+    he = np.zeros(n)
+    he[~in_cl] = m0[1][~in_cl] * 10000.0
+    reps.set_phase(1, he, in_cl.astype(np.uint8), 20)
+    reps.set_spins(m0)
+    M, E = reps.sweep_replay(perm, u, sched, prob.tanh_lut(sched), prob.lut_half)
+    Mo0, _ = O.mcmc(csr, h, m0[0], sched[0], perm=perm[0], u=u[0])
+    c1 = csr.with_values(np.where(in_cl[csr.row_of], csr.val / 20, csr.val))
+    Mo1, _ = O.mcmc(c1, he, m0[1], sched[1], perm=perm[1], u=u[1])
+    assert np.array_equal(M[0], Mo0) and np.array_equal(M[1], Mo1)
+    assert np.array_equal(E[0], O.energy(csr, h, Mo0)) and np.array_equal(E[1], O.energy(csr, h, Mo1))
