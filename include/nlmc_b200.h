@@ -97,6 +97,13 @@ int nlmc_energy(nlmc_replicas *reps, double *out_E /*[R]*/);
 int nlmc_energy_states(nlmc_instance *inst, int n_states, const int8_t *states /*[n_states][n]*/,
                        double *out_E /*[n_states]*/);
 
+/* ---- numpy-equivalent float64 tanh / arctanh ------------------------------------------------------
+ * out[i] = np.tanh(x[i]) / np.arctanh(x[i]) evaluated on the device by the functions the LBP and replay
+ * kernels use (csrc/nlmc_npmath.h: numpy's simd_tanh_f64 and the SVML routine behind np.arctanh, restated
+ * operation for operation).  Replaces the np.tanh / np.arctanh calls of NMC/nmc.py:87,205,216,252. */
+int nlmc_np_tanh(const double *x, double *out, int64_t n, int device);
+int nlmc_np_arctanh(const double *x, double *out, int64_t n, int device);
+
 /* ---- K5 lbp -- loopy belief propagation of the NMC backbone search -----------------------------
  * Replaces LoopyBeliefPropagation (NMC/nmc.py:168-228 == NPT/npt.py:204-264) as called by
  * LBP_convexified (NMC/nmc.py:93-166): messages live on the stored entries of J and are warm-started

@@ -10,16 +10,18 @@
 //
 // Bit-level fidelity: the additions reproduce numpy's association order (np.sum over a strided
 // column is pairwise over all N entries, np.sum(axis=0) is sequential; zeros do not change a
-// partial sum so only stored entries are visited).  tanh/atanh are CUDA's, which differ from
-// numpy's in the last place on some arguments; since the reference's stopping rule
-// (tolerance = machine epsilon) waits for an exact floating-point fixed point, iteration counts
-// can differ from the reference's where convergence is marginal -- see DESIGN.md "LBP parity".
+// partial sum so only stored entries are visited).  tanh/arctanh are the restatements of numpy's
+// own float64 routines in nlmc_npmath.h (bit-equal to np.tanh / np.arctanh of the AVX-512 numpy
+// build the goldens come from): the reference's stopping rule (tolerance = machine epsilon) waits
+// for an exact floating-point fixed point, so iteration counts, divergence points and the backbone
+// depend on the last bit of those two functions -- see DESIGN.md "LBP parity".
 #include <cooperative_groups.h>
 
 #include <algorithm>
 #include <cmath>
 
 #include "nlmc_common.cuh"
+#include "nlmc_npmath.h"
 
 namespace cg = cooperative_groups;
 
@@ -113,7 +115,7 @@ __device__ double pairwise_sparse(int n, const int32_t *__restrict__ pos, int cn
 __device__ __forceinline__ double atanh_saturated(double x) {  // nmc.py:230-255 (tanh(19.06) == 1.0)
     const double e = 2.220446049250313e-16;
     x = fmin(fmax(x, -1.0 + e), 1.0 - e);
-    return atanh(x);
+    return nlmc_np_arctanh(x);
 }
 
 __device__ __forceinline__ void atomic_max_nonneg(unsigned long long *addr, double v) {
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(256) lbp_kernel(LbpArgs a) {
     // two grid-wide syncs per iteration: the reduction slots alternate with the iteration parity, and the slots of
     // the NEXT iteration are cleared during this one's update phase (nobody touches them in between)
     if (tid < 8) a.red[tid] = 0ull;
-    for (int p = tid; p < a.nnz; p += nthreads) a.tj[p] = tanh(__dmul_rn(a.beta, a.val[p]));  // constant over the iterations
+    for (int p = tid; p < a.nnz; p += nthreads) a.tj[p] = nlmc_np_tanh(__dmul_rn(a.beta, a.val[p]));  // constant over the iterations
     grid.sync();
     for (iteration = 0; iteration < a.max_iter; ++iteration) {
         unsigned long long *red = a.red + 4 * (iteration & 1), *red_next = a.red + 4 * ((iteration + 1) & 1);
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(256) lbp_kernel(LbpArgs a) {
         double du = 0.0, su = 0.0;
         for (int p = tid; p < a.nnz; p += nthreads) {
             const double tj = a.tj[p];
-            const double th = tanh(__dmul_rn(a.beta, a.hm[p]));
+            const double th = nlmc_np_tanh(__dmul_rn(a.beta, a.hm[p]));
             const double un = __dmul_rn(inv_beta, atanh_saturated(__dmul_rn(tj, th)));
             const double uo = u_old[p];
             du = fmax(du, fabs(__dsub_rn(un, uo)));
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(256) lbp_kernel(LbpArgs a) {
                                     : __dadd_rn(a.h[i], __dmul_rn(__dmul_rn(a.lambda, a.mstar[i]), a.eps[i]));
         double acc = 0.0;
         for (int p = a.rp[i]; p < a.rp[i + 1]; ++p) acc = __dadd_rn(acc, a.uin[p]);
-        a.marg[i] = tanh(__dmul_rn(a.beta, __dadd_rn(hl, acc)));
+        a.marg[i] = nlmc_np_tanh(__dmul_rn(a.beta, __dadd_rn(hl, acc)));
     }
     if (tid == 0) { a.iter_out[0] = iteration; a.iter_out[1] = (u_old == a.u0) ? 0 : 1; }
 }
@@ -361,7 +363,7 @@ __global__ void lbp_byproducts_fill_kernel(int n, double beta, const double *tot
     const double inv_beta = __ddiv_rn(1.0, beta);
     double c = 0.0;
     if (i != j) {
-        const double ti = tanh(__dmul_rn(beta, tot[i])), tj = tanh(__dmul_rn(beta, tot[j]));
+        const double ti = nlmc_np_tanh(__dmul_rn(beta, tot[i])), tj = nlmc_np_tanh(__dmul_rn(beta, tot[j]));
         c = __ddiv_rn(__dmul_rn(ti, tj), __dadd_rn(1.0, 1e-10));
     }
     if (corr) corr[(size_t)i * n + j] = c;
@@ -377,8 +379,8 @@ __global__ void lbp_byproducts_edges_kernel(int n, int nnz, double beta, const i
         const int j = ci[p];
         double c = 0.0;
         if (i != j) {
-            const double tJ = tanh(__dmul_rn(beta, val[p]));
-            const double th = tanh(__dmul_rn(beta, hm[p])), tht = tanh(__dmul_rn(beta, hm[rev[p]]));
+            const double tJ = nlmc_np_tanh(__dmul_rn(beta, val[p]));
+            const double th = nlmc_np_tanh(__dmul_rn(beta, hm[p])), tht = nlmc_np_tanh(__dmul_rn(beta, hm[rev[p]]));
             const double num = __dadd_rn(tJ, __dmul_rn(th, tht));
             const double den = __dadd_rn(__dadd_rn(1.0, __dmul_rn(__dmul_rn(tJ, th), tht)), 1e-10);
             c = __ddiv_rn(num, den);

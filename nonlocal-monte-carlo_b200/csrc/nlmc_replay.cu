@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "nlmc_common.cuh"
+#include "nlmc_npmath.h"
 
 namespace nlmc {
 
@@ -49,9 +50,9 @@ __device__ __forceinline__ void st_spin(int8_t *m, int i, int v) {
     else *reinterpret_cast<volatile int8_t *>(m + i) = (int8_t)v;
 }
 
-// tanh(y) in fp64; |y| > 20 saturates to exactly +-1 in IEEE double (numpy and CUDA agree: tanh(19.07) == 1.0),
-// which is the case of every spin frozen by h = +-1e4 in the NMC phases (nmc.py:381,400).
-__device__ __forceinline__ double tanh_sat(double y) { return fabs(y) > 20.0 ? copysign(1.0, y) : tanh(y); }
+// np.tanh(y) in fp64, bit for bit (nlmc_npmath.h restates numpy's float64 routine).  For |y| >= 24 it is exactly
+// +-1, which is the case of every spin frozen by h = +-1e4 in the NMC phases (nmc.py:381,400).
+__device__ __forceinline__ double tanh_sat(double y) { return nlmc_np_tanh(y); }
 
 // Storage-order accumulation of 32 per-lane products: the lanes park them in shared memory, then every lane
 // reads all 32 back (loads issued together, not interleaved with the adds) and runs the same dependent add chain

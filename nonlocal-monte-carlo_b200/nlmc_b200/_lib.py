@@ -47,6 +47,8 @@ _SIGNATURES = {
     "nlmc_sweep_replay": [_vp, _int, _i32, _f64, _f64, _vp, _int, _vp, _int, _vp],
     "nlmc_energy": [_vp, _f64],
     "nlmc_energy_states": [_vp, _int, _i8, _f64],
+    "nlmc_np_tanh": [_f64, _f64, C.c_int64, _int],
+    "nlmc_np_arctanh": [_f64, _f64, C.c_int64, _int],
     "nlmc_lbp_create": [_vp, C.POINTER(_vp)],
     "nlmc_lbp_destroy": [_vp],
     "nlmc_lbp_epsilon": [_vp, _f64],
@@ -141,6 +143,22 @@ def require_device(device: int = 0):
     if n <= device:
         raise NlmcError(f"CUDA device {device} not available ({n} visible); nlmc_b200 has no CPU fallback")
     return n
+
+
+def np_tanh(x, device: int = 0) -> np.ndarray:
+    """np.tanh(x) for float64, evaluated on the device (bit-equal to numpy's AVX-512 routine)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    check(lib().nlmc_np_tanh(x.reshape(-1), out.reshape(-1), x.size, device), "nlmc_np_tanh")
+    return out
+
+
+def np_arctanh(x, device: int = 0) -> np.ndarray:
+    """np.arctanh(x) for float64, evaluated on the device (bit-equal to the routine numpy dispatches to)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    check(lib().nlmc_np_arctanh(x.reshape(-1), out.reshape(-1), x.size, device), "nlmc_np_arctanh")
+    return out
 
 
 def _ptr(a):

@@ -14,14 +14,6 @@ import numpy as np
 from . import _lib, host
 
 
-# Test hook (the run()-level counterpart of the reference's `all_clusters` argument of NMC_subroutine,
-# NMC/nmc.py:322): when set to a list of index arrays, every backbone search pops the next entry
-# instead of running LBP.  Used by the parity tests to show that, given the reference's backbones,
-# whole runs are bit-exact (the reference's tolerance=eps stopping rule makes the LBP divergence
-# point depend on the last bit of tanh/atanh, see DESIGN.md "LBP parity").
-BACKBONE_OVERRIDE = None
-
-
 def nmc_phase_count(num_cycles: int, full_update_frequency: int) -> int:
     """Number of MCMC phases one NMC_subroutine call executes (NMC/nmc.py:365-421)."""
     return sum(2 + (1 if cycle % full_update_frequency == 0 else 0) for cycle in range(num_cycles))
@@ -128,8 +120,6 @@ def nmc_subroutine_replay(prob: host.Problem, reps: "_lib.Replicas", m_star, *, 
 
     def backbone(g):
         nonlocal lbp
-        if BACKBONE_OVERRIDE is not None:
-            return np.asarray(BACKBONE_OVERRIDE.pop(0), dtype=int)
         if lbp is None:
             lbp = _lib.Lbp(prob.lbp_instance())
         cl = lbp_convexified(prob, lbp, m_star[g], lambda_start, lambda_end, lambda_reduction_factor, tolerance,

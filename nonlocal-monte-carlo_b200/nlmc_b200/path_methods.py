@@ -143,10 +143,12 @@ class LbpMethods(_ProblemCache):
     _nmc_variant = "nmc"
 
     def atanh_saturated(self, x):
-        """np.arctanh with the argument clipped to +-(1 - eps) (NMC/nmc.py:230-255); a scalar helper kept for
-        API parity -- the kernels use their own device version."""
+        """np.arctanh with the argument clipped to +-(1 - eps) (NMC/nmc.py:230-255), evaluated by the same device
+        function the LBP kernel uses (bit-equal to np.arctanh)."""
         eps = np.finfo(float).eps
-        return np.arctanh(np.clip(x, np.tanh(-19.06) + eps, np.tanh(19.06) - eps))
+        xc = np.clip(x, -1.0 + eps, 1.0 - eps)              # tanh(+-19.06) == +-1.0 exactly
+        out = _lib.np_arctanh(xc)
+        return out if np.ndim(x) else np.float64(out)
 
     def find_clusters(self, magnetizations, threshold_initial, threshold_cutoff, threshold_step):
         """NMC/nmc.py:257-318 on the adjacency of self.J."""

@@ -35,8 +35,9 @@ _i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
 def build(force: bool = False) -> str:
     """Compile the C restatement (gcc, no other dependency)."""
     so = os.path.join(_HERE, "libnlmc_oracle.so")
-    src = os.path.join(_HERE, "nlmc_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "nlmc_oracle.c"), os.path.join(_HERE, "npmath_host.c"),
+            os.path.join(_HERE, "..", "nonlocal-monte-carlo_b200", "csrc", "nlmc_npmath.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B"])
     return so
 
@@ -59,8 +60,20 @@ def lib():
         L.nlmc_oracle_lbp_gather.argtypes = [C.c_int, _i32p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p]
         L.nlmc_oracle_lbp_colsum.restype = C.c_int
         L.nlmc_oracle_lbp_colsum.argtypes = [C.c_int, _i32p, _i32p, _f64p, _f64p]
+        for name in ("nlmc_oracle_np_tanh", "nlmc_oracle_np_arctanh"):
+            getattr(L, name).restype = None
+            getattr(L, name).argtypes = [_f64p, _f64p, C.c_long]
         _LIB = L
     return _LIB
+
+
+def npmath_host(which: str, x) -> np.ndarray:
+    """Host build of the product's restated np.tanh / np.arctanh (oracle/npmath_host.c); ``which`` is
+    'tanh' or 'arctanh'.  Used by tests/test_npmath.py to pin the restatement against numpy without a GPU."""
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+    out = np.empty_like(x)
+    getattr(lib(), "nlmc_oracle_np_" + which)(x, out, x.size)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

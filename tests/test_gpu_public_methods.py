@@ -157,7 +157,6 @@ def test_npt_tasks_and_replica_energy(pkg, g):
     seed_all(int(g["nmctask_seed"]))
     Mn = obj.NMC_task(ms.copy(), *args)
     assert np.array_equal(Mn, g["nmctask_M"])
-    assert nmc_core.BACKBONE_OVERRIDE is None
 
 
 def test_apt_classes_mcmc_and_task(pkg, g):
