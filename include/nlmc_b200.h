@@ -55,6 +55,10 @@ int nlmc_instance_destroy(nlmc_instance *inst);
 int nlmc_instance_n(const nlmc_instance *inst);
 /* 1 when every stored J value is an integer (then row sums are exact in any order) */
 int nlmc_instance_is_integer(const nlmc_instance *inst);
+/* 1 when J_ij == J_ji for every stored entry and no row repeats a column: required by the production engines
+ * (nlmc_col_create / nlmc_dense_create fail with NLMC_ERR_ARG otherwise); the replay path accepts any J, as the
+ * reference does (J.dot(m), NMC/nmc.py:86), and only takes its incremental-field kernel when this holds */
+int nlmc_instance_is_symmetric(const nlmc_instance *inst);
 
 /* ---- replicas (exact path) ---------------------------------------------------------------- */
 int nlmc_replicas_create(nlmc_instance *inst, int n_replicas, const int8_t *init_spins /*[R][n] or NULL*/,

@@ -1,5 +1,7 @@
 // nlmc_api.cu -- handle management of the C ABI (instances, replicas) and error reporting.
+#include <algorithm>
 #include <cmath>
+#include <utility>
 
 #include "nlmc_common.cuh"
 
@@ -67,9 +69,32 @@ int nlmc_instance_create(int n, const int32_t *row_ptr, const int32_t *col, cons
         NLMC_REQUIRE(col[p] >= 0 && col[p] < n, "nlmc_instance_create: column index out of range at entry %d", p);
         if (val[p] != std::floor(val[p]) || std::fabs(val[p]) > 1e6) integer_j = false;
     }
+    // J_ij == J_ji with no repeated column in a row: what the incremental-field kernels (K1-int, K2a, K3) rely on when a
+    // flip of site k pushes J_kj into the field of j.  The general replay kernel does not need it (the reference
+    // accepts any J through J.dot(m), NMC/nmc.py:86).
+    bool value_symmetric = true;
+    {
+        std::vector<std::pair<int32_t, double>> row;
+        std::vector<std::vector<std::pair<int32_t, double>>> rows((size_t)n);
+        for (int i = 0; i < n; ++i) {
+            auto &r = rows[(size_t)i];
+            for (int p = row_ptr[i]; p < row_ptr[i + 1]; ++p) r.emplace_back(col[p], val[p]);
+            std::sort(r.begin(), r.end());
+            for (size_t q = 1; q < r.size() && value_symmetric; ++q)
+                if (r[q].first == r[q - 1].first) value_symmetric = false;
+        }
+        for (int i = 0; i < n && value_symmetric; ++i)
+            for (const auto &e : rows[(size_t)i]) {
+                if (e.second == 0.0) continue;
+                const auto &rj = rows[(size_t)e.first];
+                auto it = std::lower_bound(rj.begin(), rj.end(), std::make_pair((int32_t)i, -1e300));
+                if (it == rj.end() || it->first != i || it->second != e.second) { value_symmetric = false; break; }
+            }
+    }
     NLMC_CUDA(cudaSetDevice(device));
     auto *I = new nlmc_instance();
     I->device = device;
+    I->value_symmetric = value_symmetric;
     I->n = n;
     I->nnz = nnz;
     I->max_deg = max_deg;
@@ -133,6 +158,7 @@ int nlmc_instance_destroy(nlmc_instance *I) {
 
 int nlmc_instance_n(const nlmc_instance *I) { return I ? I->n : NLMC_ERR_ARG; }
 int nlmc_instance_is_integer(const nlmc_instance *I) { return I ? (I->integer_j ? 1 : 0) : NLMC_ERR_ARG; }
+int nlmc_instance_is_symmetric(const nlmc_instance *I) { return I ? (I->value_symmetric ? 1 : 0) : NLMC_ERR_ARG; }
 
 int nlmc_replicas_create(nlmc_instance *I, int R, const int8_t *init_spins, nlmc_replicas **out) {
     NLMC_REQUIRE(out != nullptr, "nlmc_replicas_create: out is NULL");

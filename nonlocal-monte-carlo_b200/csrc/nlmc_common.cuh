@@ -78,6 +78,7 @@ struct nlmc_instance {
     int max_deg = 0;
     bool integer_j = false;   // every stored value is an integer -> row sums exact in any order
     bool symmetric = false;   // pattern symmetric (rev index available)
+    bool value_symmetric = false;  // J_ij == J_ji for every stored entry and no column appears twice in a row
     int32_t *row_ptr = nullptr;  // [n+1]
     int32_t *col = nullptr;      // [nnz]
     double *val = nullptr;       // [nnz]

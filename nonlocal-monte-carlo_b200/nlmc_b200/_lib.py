@@ -39,6 +39,7 @@ _SIGNATURES = {
     "nlmc_instance_destroy": [_vp],
     "nlmc_instance_n": [_vp],
     "nlmc_instance_is_integer": [_vp],
+    "nlmc_instance_is_symmetric": [_vp],
     "nlmc_replicas_create": [_vp, _int, _vp, C.POINTER(_vp)],
     "nlmc_replicas_destroy": [_vp],
     "nlmc_set_spins": [_vp, _int, _int, _i8],

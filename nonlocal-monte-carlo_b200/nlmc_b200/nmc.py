@@ -60,9 +60,10 @@ class NMC(SweepMethods, LbpMethods):
         if self.verbose:
             print(f'\ninitial m_star energy = {Energy_star:.8f}')
 
-        S = nmc_phase_count(num_NMC_cycles, full_update_frequency) * num_sweeps_per_NMC_phase
-        perm, u = host.draw_sweeps(np.random, S, N)  # the phases' draws do not depend on the spins
-        res = nmc_subroutine_replay(prob, reps, m_star[None, :], variant="nmc", perm=perm[None], u=u[None],
+        # the phases' draws do not depend on the spins: each phase draws its own sweeps (same stream order as the
+        # reference, one phase of permutations and uniforms in host memory at a time)
+        res = nmc_subroutine_replay(prob, reps, m_star[None, :], variant="nmc", perm=None, u=None,
+                                    draw=lambda n_sweeps: host.draw_sweeps(np.random, n_sweeps, N),
                                     num_cycles=num_NMC_cycles, phase_sweeps=num_sweeps_per_NMC_phase,
                                     full_update_frequency=full_update_frequency, M_skip=M_skip,
                                     global_beta=global_beta, temp_x=temp_x, lambda_start=lambda_start,

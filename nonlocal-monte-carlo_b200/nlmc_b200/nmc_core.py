@@ -95,12 +95,14 @@ def lbp_convexified(prob: host.Problem, lbp: "_lib.Lbp", m_star, lambda_start, l
 def nmc_subroutine_replay(prob: host.Problem, reps: "_lib.Replicas", m_star, *, variant: str, perm, u,
                           num_cycles, phase_sweeps, full_update_frequency, M_skip, global_beta, temp_x,
                           lambda_start, lambda_end, lambda_reduction_factor, threshold_initial, threshold_cutoff,
-                          max_iterations, tolerance, all_clusters=None, verbose=False):
+                          max_iterations, tolerance, all_clusters=None, verbose=False, draw=None):
     """NMC_subroutine for a batch of G chains in lock step (exact-replay mode).
 
     variant "nmc": NMC/nmc.py:320-440 (LBP inside the cycle loop, m_star follows the ALL phase);
     variant "npt": NPT/npt.py:357-477 (LBP once, before the loop).
-    perm/u [G][n_phases*phase_sweeps][n]: the reference's draws for chain g, in phase order.
+    perm/u [G][n_phases*phase_sweeps][n]: the reference's draws for chain g, in phase order; or None with
+    draw(n_sweeps) -> (perm, u) [n_sweeps][n], called once per phase (single chain only: the draws do not depend
+    on the spins, so drawing a phase at a time consumes the stream in the same order with one phase in memory).
     Returns a list of (M_overall float64 [n][cols], energy_overall, min_energy, all_clusters) per chain.
     """
     G, n = reps.R, prob.n
@@ -130,9 +132,14 @@ def nmc_subroutine_replay(prob: host.Problem, reps: "_lib.Replicas", m_star, *, 
 
     def run_phase():
         nonlocal phase_no, M_index, m_init
-        sl = slice(phase_no * phase_sweeps, (phase_no + 1) * phase_sweeps)
         reps.set_spins(m_init)
-        Mi8, E = reps.sweep_replay(perm[:, sl], u[:, sl], beta_sched, lut, prob.lut_half)
+        if perm is None:
+            assert G == 1 and draw is not None
+            p1, u1 = draw(phase_sweeps)
+            Mi8, E = reps.sweep_replay(p1[None], u1[None], beta_sched, lut, prob.lut_half)
+        else:
+            sl = slice(phase_no * phase_sweeps, (phase_no + 1) * phase_sweeps)
+            Mi8, E = reps.sweep_replay(perm[:, sl], u[:, sl], beta_sched, lut, prob.lut_half)
         phase_no += 1
         for g in range(G):
             Mg = Mi8[g].T.astype(np.float64)

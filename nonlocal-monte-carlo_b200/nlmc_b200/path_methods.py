@@ -148,7 +148,7 @@ class LbpMethods(_ProblemCache):
         eps = np.finfo(float).eps
         xc = np.clip(x, -1.0 + eps, 1.0 - eps)              # tanh(+-19.06) == +-1.0 exactly
         out = _lib.np_arctanh(xc)
-        return out if np.ndim(x) else np.float64(out)
+        return out if np.ndim(x) else np.float64(out.reshape(-1)[0])
 
     def find_clusters(self, magnetizations, threshold_initial, threshold_cutoff, threshold_step):
         """NMC/nmc.py:257-318 on the adjacency of self.J."""

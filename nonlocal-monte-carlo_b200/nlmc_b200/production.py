@@ -249,8 +249,7 @@ def _npt_run_dense(obj, prob, beta_list, nmc_kw):
             dB = beta_list[nxt - 1] - beta_list[sel - 1]
             if np.random.rand() < min(1, np.exp(dB * dE)):
                 count[ii] += 1
-                state[[sel - 1, nxt - 1]] = state[[nxt - 1, sel - 1]]
-                E_cols[[sel - 1, nxt - 1], -1] = E_cols[[nxt - 1, sel - 1], -1]
+                state[[sel - 1, nxt - 1]] = state[[nxt - 1, sel - 1]]  # only m_start is exchanged (npt.py:677-678)
     Energy = np.zeros(R)
     obj._EE1_list = []
     for r in range(R):

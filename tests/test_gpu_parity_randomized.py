@@ -120,3 +120,41 @@ def test_production_engines_on_ragged_instances(block):
         np.testing.assert_allclose(d.energies(), O.energy(csr, h, S), rtol=1e-4, atol=1e-4 * max(1, n),
                                    err_msg=f"K3 case {case} n={n}")
         d.close()
+
+
+@pytest.mark.parametrize("kind", ["upper_int", "asym_int", "asym_real"])
+def test_k1_asymmetric_j(kind):
+    """The reference takes any J through J.dot(m) (NMC/nmc.py:86): an integer J that is not symmetric must not take
+    the incremental-field kernel (which pushes J_kj into field j); the production engines refuse it."""
+    from nlmc_b200 import _lib, host
+    from oracle import oracle as O
+    rs = np.random.RandomState({"upper_int": 1, "asym_int": 2, "asym_real": 3}[kind])
+    n = 40
+    U = rs.rand(n, n) < 0.3
+    np.fill_diagonal(U, False)
+    V = rs.randn(n, n) if kind == "asym_real" else rs.choice([-2.0, -1.0, 1.0, 3.0], size=(n, n))
+    J = np.where(U, V, 0.0)
+    if kind == "upper_int":
+        J = np.triu(J)
+    h = rs.randint(-1, 2, size=n).astype(float)
+    csr = O.Csr(J)
+    prob = host.Problem(J, h)
+    assert _lib.lib().nlmc_instance_is_symmetric(prob.inst._h) == 0
+    R, S = 2, 3
+    reps = _lib.Replicas(prob.inst, R)
+    m0 = rs.choice([-1, 1], size=(R, n)).astype(np.int8)
+    sched = np.array([[0.8] * S, [1.7] * S])
+    perm = np.stack([np.stack([rs.permutation(n) for _ in range(S)]) for _ in range(R)]).astype(np.int32)
+    u = rs.rand(R, S, n)
+    reps.set_spins(m0)
+    M, E = reps.sweep_replay(perm, u, sched, prob.tanh_lut(sched) if prob.lut_half else None, prob.lut_half)
+    for r in range(R):
+        Mo, _ = O.mcmc(csr, h, m0[r], sched[r], perm=perm[r], u=u[r])
+        assert np.array_equal(M[r], Mo)
+        np.testing.assert_allclose(E[r], O.energy(csr, h, Mo), rtol=1e-9, atol=1e-12)
+    for make in (lambda: _lib.Col(prob.inst, np.array([1.0]), seed=0), lambda: _lib.Dense(prob.inst, np.array([1.0]), seed=0)):
+        with pytest.raises(_lib.NlmcError):
+            make()
+    # the symmetric part alone is accepted again
+    Js = J + J.T
+    assert _lib.lib().nlmc_instance_is_symmetric(host.Problem(Js, h).inst._h) == 1

@@ -389,3 +389,75 @@ def test_k1_replay_at_config_sizes(nl, config):
     Mo1, _ = O.mcmc(c1, he, m0[1], sched[1], perm=perm[1], u=u[1])
     assert np.array_equal(M[0], Mo0) and np.array_equal(M[1], Mo1)
     assert np.array_equal(E[0], O.energy(csr, h, Mo0)) and np.array_equal(E[1], O.energy(csr, h, Mo1))
+
+
+@pytest.mark.parametrize("config", ["C3", "C5"])
+def test_k1_replay_at_config_sizes_c3_c5(nl, config):
+    """K1 against the oracle at the native sizes of C3 (SK N = 2000, dense Gaussian J: storage-order fp64 row sums over
+    1999 entries, energies to 1e-9) and C5 (3D EA L = 64, 262,144 spins: global-memory variant), a plain replica and
+    one in an NMC phase (rows at beta/temp_x, the rest frozen)."""
+    from nlmc_b200 import instances
+    from oracle import oracle as O
+    J, h = instances.sk_gaussian(2000, 3) if config == "C3" else instances.ea3d_pm_j(64, 5)
+    csr = O.Csr(J)
+    n = csr.n
+    prob = nl.host.Problem(J, h)
+    rs = np.random.RandomState(23)
+    R, S = 2, (2 if config == "C3" else 1)
+    reps = nl.lib.Replicas(prob.inst, R)
+    m0 = rs.choice([-1, 1], size=(R, n)).astype(np.int8)
+    sched = np.array([[0.9] * S, [2.5] * S])
+    perm = np.stack([np.stack([rs.permutation(n) for _ in range(S)]) for _ in range(R)]).astype(np.int32)
+    u = rs.rand(R, S, n)
+    in_cl = rs.rand(n) < 0.5
+    he = np.zeros(n)
+    he[~in_cl] = m0[1][~in_cl] * 10000.0
+    reps.set_phase(1, he, in_cl.astype(np.uint8), 20)
+    reps.set_spins(m0)
+    lut = prob.tanh_lut(sched) if prob.lut_half else None
+    M, E = reps.sweep_replay(perm, u, sched, lut, prob.lut_half)
+    Mo0, _ = O.mcmc(csr, h, m0[0], sched[0], perm=perm[0], u=u[0])
+    c1 = csr.with_values(np.where(in_cl[csr.row_of], csr.val / 20, csr.val))
+    Mo1, _ = O.mcmc(c1, he, m0[1], sched[1], perm=perm[1], u=u[1])
+    assert np.array_equal(M[0], Mo0) and np.array_equal(M[1], Mo1)
+    if config == "C5":
+        assert np.array_equal(E[0], O.energy(csr, h, Mo0)) and np.array_equal(E[1], O.energy(csr, h, Mo1))
+    else:
+        np.testing.assert_allclose(E[0], O.energy(csr, h, Mo0), rtol=1e-9)
+        np.testing.assert_allclose(E[1], O.energy(csr, h, Mo1), rtol=1e-9)
+
+
+def test_nmc_run_at_config_c1_size_vs_oracle(nl, tmp_cwd):
+    """Whole NMC.run on the C1 instance (N = 800, +-1 graph of degree ~48, README parameters, sweeps cut to 20 and
+    3 cycles) against the oracle's nmc_run on the same seeds: anneal, three free-running LBP backbone searches at
+    tolerance = machine epsilon, nine phases -- states bit for bit, energies exact (integer J)."""
+    from nlmc_b200 import instances
+    from oracle import oracle as O
+    J, h = instances.random_pm_graph(800, 0.06, 1)
+    args = (20, 20, 3, 1, 1, 20, 3, 3, 0.01, 0.9, 0.9999999, 0.999999, 100, EPS)
+    seed_all(3)
+    Mo, Eo, mno = O.nmc_run(J, h, *args)
+    seed_all(3)
+    M, E, mn = nl.pkg.NMC(J.toarray() if hasattr(J, "toarray") else J, h).run(*args)
+    assert M.shape == (800, 180)
+    assert np.array_equal(M, Mo)
+    assert np.array_equal(np.asarray(E), Eo) and mn == mno
+
+
+def test_npt_run_at_config_c2_size_vs_oracle(nl, tmp_cwd):
+    """Whole NPT.run on the C2 lattice (3D EA L = 16, 4096 spins), 6 replicas with doNMC on the 2 coldest, against
+    the oracle's npt_run on the same seeds (free-running LBP, swaps, forked worker stream): bit for bit."""
+    from nlmc_b200 import instances
+    from oracle import oracle as O
+    J, h = instances.ea3d_pm_j(16, 2)
+    bl = np.linspace(0.3, 2.5, 6)
+    kw = dict(num_sweeps_MCMC=24, num_sweeps_read=24, num_swap_attempts=2, num_swapping_pairs=2, num_cycles=2,
+              global_beta=3.0, lambda_start=3.0, lambda_end=0.01, threshold_initial=0.9999999,
+              threshold_cutoff=0.999999)
+    doNMC = [False] * 4 + [True] * 2
+    seed_all(4)
+    Mo, Eo = O.npt_run(J, h, bl, 6, doNMC, **kw)
+    seed_all(4)
+    M, E = nl.pkg.NPT(J, h).run(bl, 6, doNMC, num_cores=1, **kw)
+    assert M.shape == (6 * 4096, 12)
+    assert np.array_equal(M, Mo) and np.array_equal(E, Eo)
