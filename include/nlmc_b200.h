@@ -206,6 +206,29 @@ int nlmc_msc_round_host(nlmc_msc *msc, const uint32_t *packed_in, int n_sweeps, 
 int nlmc_msc_round_host_async(nlmc_msc *msc, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,
                               uint32_t *packed_out, double *out_E);
 int nlmc_msc_swap_count(nlmc_msc *msc, int *out_accepted, int reset);
+/* accepted exchanges of each of the last n_rounds (<= 4096) rounds, oldest first, counted per round on the device
+ * (the reference's `count[ii]`, NPT/npt.py:664-680) */
+int nlmc_msc_swap_counts(nlmc_msc *msc, int n_rounds, int *out_counts);
+
+/* ---- replica exchange by beta labels, and a ladder's beta range sharded over GPUs (north_star 4) ----
+ * Replaces the swap block NPT/npt.py:649-680 in the form SURVEY D4 describes: configurations never move; every
+ * (slot, ladder) carries the index of the temperature it is simulated at, and an accepted exchange swaps two labels.
+ * A handle owns the slots [slot_begin, slot_begin + slot_count) of a ladder of n_beta_total temperatures.  Random
+ * streams are keyed by the GLOBAL slot and ladder indices, so a ladder sharded over several handles / GPUs evolves
+ * bit for bit like the single handle that owns all its slots.
+ *   slot_count == n_beta_total : self-contained, nlmc_msc_round does sweeps + energies + label exchange on the device.
+ *   a block of a sharded ladder: per round  nlmc_msc_sweep -> nlmc_msc_energies_dev (into the caller's all-gather
+ *       send buffer) -> [the caller all-gathers the energies of all blocks, 8 bytes per replica, e.g. ncclAllGather]
+ *       -> nlmc_msc_exchange_labels (identical Philox-keyed decisions on every rank).
+ *   nlmc_msc_set_stream  runs the handle on the caller's CUDA stream (the one the collective is ordered on);
+ *   nlmc_msc_get_labels  labels[slot][ladder] (uint8, [n_beta_total][n_ladders_padded]) to reorder outputs to beta order. */
+int nlmc_msc_create_labelled(nlmc_instance *inst, int n_beta_total, const double *betas_total, int slot_begin,
+                             int slot_count, int n_ladders, int ladder_offset, unsigned long long seed, nlmc_msc **out);
+int nlmc_msc_set_stream(nlmc_msc *msc, void *cuda_stream);
+int nlmc_msc_energies_dev(nlmc_msc *msc, double *out_E_dev /*[slot_count][n_ladders_padded], device*/);
+int nlmc_msc_exchange_labels(nlmc_msc *msc, const double *E_full_dev /*[n_beta_total][n_ladders_padded], device*/,
+                             int num_swapping_pairs);
+int nlmc_msc_get_labels(nlmc_msc *msc, uint8_t *out_labels);
 int nlmc_msc_sync(nlmc_msc *msc);
 int nlmc_msc_timer_mark(nlmc_msc *msc, int which);
 int nlmc_msc_timer_elapsed_ms(nlmc_msc *msc, float *out_ms);

@@ -30,6 +30,18 @@ struct nlmc_msc {
     nlmc_instance *inst = nullptr;
     int n = 0, W = 0, n_beta = 0, n_ladders = 0, G = 0, n_colours = 0;
     int ladder_offset = 0;        // global index of this handle's first ladder (multiple of 128)
+    // beta-label exchange (north_star 4): the handle owns the slots [slot_begin, slot_begin + n_beta) of a ladder of
+    // n_beta_total temperatures; configurations never move, every (slot, ladder) carries the index of the beta it is
+    // currently simulated at.  label_mode = 0: the classic layout (slot b is at betas[b], exchanges move bits).
+    int label_mode = 0, n_beta_total = 0, slot_begin = 0;
+    uint8_t *labels = nullptr;    // [n_beta_total][n_ladders] beta index held by (slot, ladder) -- replicated on every rank
+    uint8_t *slot_of = nullptr;   // [n_beta_total][n_ladders] inverse: slot holding beta index i of the ladder
+    uint32_t *thr_total = nullptr;  // [n_beta_total][4] thresholds of every temperature
+    double *betas_total = nullptr;  // [n_beta_total]
+    uint32_t *thrbits = nullptr;  // [k_steps][3][W] bit planes: bit l of word w = bit (31-p) of the level-L threshold of lane l
+    uint32_t *thr_lane = nullptr; // [W][32][4] full thresholds of every lane (levels 1..3), for the stragglers
+    int32_t *accepted_rounds = nullptr;  // [kRoundLog] accepted exchanges of the last rounds (slot = round % kRoundLog)
+    bool own_stream = true;
     long long n_bonds = 0;
     uint32_t *S = nullptr;        // [n][W]
     int32_t *rec = nullptr;       // [n][8] record of the site at position p of site_list (sites sorted by colour):
@@ -89,6 +101,10 @@ struct Philox {
 
 struct MscDev {
     int n, W, G, n_beta, quad_offset;  // quad_offset = ladder_offset / 128: global index of ladder quad 0
+    int slot_begin;       // global index of slot 0 (label mode; 0 otherwise): random streams are keyed by the GLOBAL slot
+    int qpc, spw;         // sub-warp mapping for W < 128: quads (4 words) per site row, sites per warp
+    const uint32_t *thrbits;    // label mode: [kSteps][3][W]
+    const uint4 *thr_lane;      // label mode: [W][32] thresholds {-, T1, T2, T3} of every lane
     uint32_t *S;
     const int4 *rec;      // [n][2] by position in site_list: {nbr0..3}, {nbr4, nbr5, sign bits, site} -- two 16-byte
                           // loads replace the chain site_list -> neighbour table -> sign bits
@@ -137,13 +153,29 @@ __device__ __forceinline__ uint32_t comp(const uint4 &v, int k) { return k == 0 
 // are finished one by one against the remaining threshold bits with a fresh 32-bit uniform each
 // (exactly the conditional probability).  ncu on the first version (early-exit loop) showed the kernel
 // ALU-pipe bound with 29% of the lanes idle in the loop tail; see profiles/.
-template <int kSteps>
-__global__ void __launch_bounds__(256, 5) msc_sweep_kernel(MscDev a, int first, int n_sites, const uint32_t *__restrict__ counters) {
+//
+// kPerBit (beta-label exchange): the lanes of a word sit at DIFFERENT temperatures, so the threshold bit of a lane
+// comes from per-word bit planes thrbits[p][level][w] (rebuilt after every exchange) instead of three scalars;
+// stragglers look their threshold up through the lane's label.  kSubWarp: site rows shorter than 128 words (a beta
+// block of a ladder sharded over GPUs) put several sites into one warp, lane = (site of the warp, word quad).
+template <int kSteps, bool kPerBit, bool kSubWarp>
+#ifndef NLMC_PERBIT_CTAS
+#define NLMC_PERBIT_CTAS 4  // resident CTAs per SM of the bit-plane variant (64 registers: no spills)
+#endif
+__global__ void __launch_bounds__(256, kPerBit ? NLMC_PERBIT_CTAS : 5) msc_sweep_kernel(MscDev a, int first, int n_sites, const uint32_t *__restrict__ counters) {
     const uint32_t sweep = counters[0];
-    const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);  // site of this colour
+    int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);  // site of this colour
     const int lane = threadIdx.x & 31;
+    int word0;
+    if (kSubWarp) {
+        const int sub = lane / a.qpc;
+        if (sub >= a.spw) return;
+        warp = warp * a.spw + sub;
+        word0 = (lane - sub * a.qpc) * 4;
+    } else {
+        word0 = (int)blockIdx.y * 128 + lane * 4;  // grid.y = 128-word chunks of the row
+    }
     if (warp >= n_sites) return;
-    const int word0 = (int)blockIdx.y * 128 + lane * 4;  // grid.y = 128-word chunks of the row
     if (word0 >= a.W) return;
 
     const int4 r0 = __ldg(a.rec + (size_t)(first + warp) * 2), r1 = __ldg(a.rec + (size_t)(first + warp) * 2 + 1);
@@ -175,39 +207,47 @@ __global__ void __launch_bounds__(256, 5) msc_sweep_kernel(MscDev a, int first, 
         I3[k] = m1 & m0;
         pos[k] = c2;
     }
-    const int b = beta_index(a, word0);  // the four words of a lane share one beta (G % 4 == 0)
-    const uint4 thr4 = __ldg(reinterpret_cast<const uint4 *>(a.thr) + b);
-    const uint32_t T1 = thr4.y, T2 = thr4.z, T3 = thr4.w;
+    const int b = beta_index(a, word0);  // the four words of a lane share one slot (G % 4 == 0)
+    uint32_t T1 = 0, T2 = 0, T3 = 0;
+    if (!kPerBit) {
+        const uint4 thr4 = __ldg(reinterpret_cast<const uint4 *>(a.thr) + b);
+        T1 = thr4.y; T2 = thr4.z; T3 = thr4.w;
+    }
     const Philox rng{a.seed_lo, a.seed_hi ^ kTagSweep};
-    // stream id = (beta index, GLOBAL ladder quad): independent of how ladders are sharded over handles/GPUs
-    const uint32_t sid = ((uint32_t)b << 20) | (uint32_t)(a.quad_offset + ((word0 - b * a.G) >> 2));
+    // stream id = (GLOBAL slot index, GLOBAL ladder quad): independent of how ladders / beta blocks are sharded
+    const uint32_t sid = ((uint32_t)(b + a.slot_begin) << 20) | (uint32_t)(a.quad_offset + ((word0 - b * a.G) >> 2));
     // Bit-serial comparison state per word: und = lanes whose uniform still equals the threshold on the prefix seen so
     // far; v = the uniform's bit at the last step a lane was undecided, i.e. for a decided lane the bit at its first
     // difference (v = 0 there <=> uniform < threshold <=> g = 1).  Two 3-input logic ops per word and step; the level
-    // select runs on the FMA pipe.  g = ~v & ~und is formed once after the last step.
+    // select runs on the FMA pipe (scalar thresholds) or is three more logic ops (bit planes).
+    // g = ~v & ~und is formed once after the last step.
     uint32_t v[4];
-    {   // step 0: level-0 lanes (q = 1/2) are decided by the first bit alone (g = ~r, so v = r fits them too)
-        const uint4 r4 = rng((uint32_t)site, sid, sweep, 0u);
-        const uint32_t p1 = T1 >> 31, p2 = T2 >> 31, p3 = T3 >> 31;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t r = comp(r4, k);
-            const uint32_t I0 = ~(I1[k] | I2[k] | I3[k]);
-            const uint32_t t = level_select(I1[k], I2[k], I3[k], p1, p2, p3);
-            v[k] = r;
-            und[k] = ~(r ^ t) & ~I0;
-        }
-    }
-#pragma unroll
-    for (int p = 1; p < kSteps; ++p) {
+    for (int p = 0; p < kSteps; ++p) {
         const uint4 r4 = rng((uint32_t)site, sid, sweep, (uint32_t)p);
-        const uint32_t p1 = (T1 >> (31 - p)) & 1u, p2 = (T2 >> (31 - p)) & 1u, p3 = (T3 >> (31 - p)) & 1u;
+        uint4 A1, A2, A3;
+        uint32_t p1 = 0, p2 = 0, p3 = 0;
+        if (kPerBit) {
+            const uint32_t *tb = a.thrbits + (size_t)p * 3 * a.W + word0;
+            A1 = __ldg(reinterpret_cast<const uint4 *>(tb));
+            A2 = __ldg(reinterpret_cast<const uint4 *>(tb + a.W));
+            A3 = __ldg(reinterpret_cast<const uint4 *>(tb + 2 * a.W));
+        } else {
+            p1 = (T1 >> (31 - p)) & 1u; p2 = (T2 >> (31 - p)) & 1u; p3 = (T3 >> (31 - p)) & 1u;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t r = comp(r4, k);
-            const uint32_t t = level_select(I1[k], I2[k], I3[k], p1, p2, p3);
-            v[k] = (und[k] & r) | (~und[k] & v[k]);  // undecided lanes take this step's bit
-            und[k] &= ~(r ^ t);                      // still equal on this prefix
+            const uint32_t t = kPerBit ? ((I1[k] & comp(A1, k)) | (I2[k] & comp(A2, k)) | (I3[k] & comp(A3, k)))
+                                       : level_select(I1[k], I2[k], I3[k], p1, p2, p3);
+            if (p == 0) {  // level-0 lanes (q = 1/2) are decided by the first bit alone (g = ~r, so v = r fits them too)
+                const uint32_t I0 = ~(I1[k] | I2[k] | I3[k]);
+                v[k] = r;
+                und[k] = ~(r ^ t) & ~I0;
+            } else {
+                v[k] = (und[k] & r) | (~und[k] & v[k]);  // undecided lanes take this step's bit
+                und[k] &= ~(r ^ t);                      // still equal on this prefix
+            }
         }
     }
 #pragma unroll
@@ -223,7 +263,16 @@ __global__ void __launch_bounds__(256, 5) msc_sweep_kernel(MscDev a, int first, 
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t bit = und[k] & (0u - und[k]);  // 0 when the word has no straggler
-                const uint32_t rem = (I3[k] & bit) ? R3 : (I2[k] & bit) ? R2 : R1;  // level 0 never gets here
+                uint32_t rem;
+                if (kPerBit) {
+                    rem = 0u;
+                    if (bit) {
+                        const uint4 tl = __ldg(a.thr_lane + (size_t)(word0 + k) * 32 + (__ffs((int)bit) - 1));
+                        rem = ((I3[k] & bit) ? tl.w : (I2[k] & bit) ? tl.z : tl.y) << kSteps;
+                    }
+                } else {
+                    rem = (I3[k] & bit) ? R3 : (I2[k] & bit) ? R2 : R1;  // level 0 never gets here
+                }
                 if (comp(r4, k) < rem) res[k] |= bit;
                 und[k] ^= bit;
             }
@@ -244,7 +293,7 @@ __global__ void msc_init_kernel(MscDev a, uint32_t stream_id) {
     if (quad >= (size_t)a.n * qpr) return;
     const int site = (int)(quad / qpr), word0 = (int)(quad % qpr) * 4;
     const int b = word0 / a.G;
-    const uint32_t sid = ((uint32_t)b << 20) | (uint32_t)(a.quad_offset + ((word0 - b * a.G) >> 2));
+    const uint32_t sid = ((uint32_t)(b + a.slot_begin) << 20) | (uint32_t)(a.quad_offset + ((word0 - b * a.G) >> 2));
     const Philox rng{a.seed_lo, a.seed_hi ^ kTagInit};
     reinterpret_cast<uint4 *>(a.S)[quad] = rng((uint32_t)site, sid, stream_id, 0u);
 }
@@ -255,12 +304,20 @@ constexpr int kEnergyChunk = 128;  // at most 128 sites per warp: 128 sites * 6 
 // On a two-colourable graph every bond joins the two colour classes, so the sites of ONE class see every bond exactly
 // once: the launcher then passes only that class (n_list sites of site_list) and the finish kernel doubles the sum.
 __global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_acc, int chunk, int n_list) {
-    const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     const int chunks = (a.W + 127) >> 7;
     const int site_chunks = (n_list + chunk - 1) / chunk;
+    int word0;
+    if (a.W < 128) {  // short rows: the sub-groups of a warp take different site chunks (chunks == 1)
+        const int sub = lane / a.qpc;
+        if (sub >= a.spw) return;
+        warp = warp * a.spw + sub;
+        word0 = (lane - sub * a.qpc) * 4;
+    } else {
+        word0 = (warp % chunks) * 128 + lane * 4;
+    }
     if (warp >= site_chunks * chunks) return;
-    const int word0 = (warp % chunks) * 128 + lane * 4;
     if (word0 >= a.W) return;
     const int s_begin = (warp / chunks) * chunk, s_end = min(n_list, s_begin + chunk);
     uint32_t v[4][10];
@@ -334,9 +391,10 @@ __global__ void msc_energy_finish_kernel(int W, int G, int n_ladders, long long 
 // Accepted exchanges are recorded as lane masks per temperature boundary and applied to the
 // configurations by msc_swap_apply_kernel (the reference swaps configurations, not labels).
 constexpr int kMaxBeta = 128;
+constexpr int kRoundLog = 4096;  // per-round acceptance counts kept for the last kRoundLog rounds
 __global__ void msc_swap_decide_kernel(int n_beta, int n_ladders, int G, int num_pairs, const double *betas, double *E,
-                                       uint32_t *swapmask, int32_t *accepted, uint32_t seed_lo, uint32_t seed_hi,
-                                       const uint32_t *__restrict__ counters, int ladder_offset) {
+                                       uint32_t *swapmask, int32_t *accepted, int32_t *accepted_rounds, uint32_t seed_lo,
+                                       uint32_t seed_hi, const uint32_t *__restrict__ counters, int ladder_offset) {
     const uint32_t round = counters[1];
     const int ladder = blockIdx.x * blockDim.x + threadIdx.x;
     if (ladder >= n_ladders) return;
@@ -364,7 +422,10 @@ __global__ void msc_swap_decide_kernel(int n_beta, int n_ladders, int G, int num
             E[(size_t)(i + 1) * n_ladders + ladder] = E_sel;
         }
     }
-    if (acc) atomicAdd(accepted, acc);
+    if (acc) {
+        atomicAdd(accepted, acc);
+        atomicAdd(accepted_rounds + (round % kRoundLog), acc);
+    }
 }
 
 __global__ void msc_swap_apply_kernel(MscDev a, const uint32_t *swapmask) {
@@ -391,6 +452,77 @@ __global__ void msc_swap_apply_kernel(MscDev a, const uint32_t *swapmask) {
         A_dirty = B_dirty;
     }
     if (A_dirty) row[(size_t)(a.n_beta - 1) * a.G] = A;
+}
+
+// K6, beta-label form (north_star 4): configurations stay in their slots, every (slot, ladder) carries the
+// index of the temperature it is simulated at.  E[slot][ladder] holds the energies of ALL slots of the ladder set
+// (gathered over the ranks when the beta range is sharded); every rank runs this kernel on identical inputs and
+// arrives at the identical permutation -- only 8 bytes per replica ever cross the GPUs.  Pair selection and
+// acceptance as in msc_swap_decide_kernel (NPT/npt.py:514-533,652-680), pairs being adjacent TEMPERATURES.
+__global__ void msc_label_swap_kernel(int n_beta, int n_ladders, int num_pairs, const double *betas, const double *E,
+                                      uint8_t *labels, uint8_t *slot_of, int32_t *accepted, int32_t *accepted_rounds,
+                                      uint32_t seed_lo, uint32_t seed_hi, const uint32_t *__restrict__ counters,
+                                      int ladder_offset) {
+    const uint32_t round = counters[1];
+    const int ladder = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ladder >= n_ladders) return;
+    const Philox rng{seed_lo, seed_hi ^ kTagSwap};
+    uint8_t avail[kMaxBeta];
+    int n_avail = n_beta - 1;
+    for (int i = 0; i < n_beta - 1; ++i) avail[i] = 1;
+    int acc = 0;
+    for (int k = 0; k < num_pairs && n_avail > 0; ++k) {
+        const uint4 r = rng((uint32_t)(ladder + ladder_offset), round, (uint32_t)k, 0u);
+        int pick = (int)(((unsigned long long)r.x * (unsigned)n_avail) >> 32);
+        int i = 0;
+        for (;; ++i)
+            if (avail[i] && pick-- == 0) break;
+        for (int j = max(0, i - 1); j <= min(n_beta - 2, i + 1); ++j)
+            if (avail[j]) { avail[j] = 0; --n_avail; }
+        const int sa = slot_of[(size_t)i * n_ladders + ladder], sb = slot_of[(size_t)(i + 1) * n_ladders + ladder];
+        const double E_sel = E[(size_t)sa * n_ladders + ladder], E_next = E[(size_t)sb * n_ladders + ladder];
+        const double x = (betas[i + 1] - betas[i]) * (E_next - E_sel);
+        const double u = ((double)r.y * 4294967296.0 + (double)r.z + 0.5) * (1.0 / 18446744073709551616.0);
+        if (u < fmin(1.0, exp(x))) {
+            ++acc;
+            labels[(size_t)sa * n_ladders + ladder] = (uint8_t)(i + 1);
+            labels[(size_t)sb * n_ladders + ladder] = (uint8_t)i;
+            slot_of[(size_t)i * n_ladders + ladder] = (uint8_t)sb;
+            slot_of[(size_t)(i + 1) * n_ladders + ladder] = (uint8_t)sa;
+        }
+    }
+    if (acc) {
+        atomicAdd(accepted, acc);
+        atomicAdd(accepted_rounds + (round % kRoundLog), acc);
+    }
+}
+
+// Threshold bit planes of this handle's slots from the labels: one thread per (step p, level, word).
+__global__ void msc_thrbits_kernel(int k_steps, int W, int G, const uint8_t *__restrict__ labels_local,
+                                   const uint32_t *__restrict__ thr_total, uint32_t *thrbits, uint4 *thr_lane) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < W * 32) {  // full thresholds of lane (w, l)
+        const int w = idx >> 5, l = idx & 31;
+        const int lab = labels_local[(size_t)(w / G) * (G * 32) + (w % G) * 32 + l];
+        thr_lane[idx] = *reinterpret_cast<const uint4 *>(thr_total + lab * 4);
+    }
+    if (idx >= k_steps * 3 * W) return;
+    const int w = idx % W, lev = (idx / W) % 3 + 1, p = idx / (3 * W);
+    const int b = w / G, g = w % G;
+    const uint8_t *lab = labels_local + (size_t)b * (G * 32) + g * 32;
+    uint32_t word = 0u;
+    for (int l = 0; l < 32; ++l) word |= ((thr_total[lab[l] * 4 + lev] >> (31 - p)) & 1u) << l;
+    thrbits[idx] = word;
+}
+
+__global__ void msc_labels_identity_kernel(int n_beta, int n_ladders, uint8_t *labels, uint8_t *slot_of) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_beta * n_ladders) return;
+    labels[idx] = slot_of[idx] = (uint8_t)(idx / n_ladders);
+}
+
+__global__ void msc_clear_round_slot_kernel(int32_t *accepted_rounds, const uint32_t *__restrict__ counters) {
+    accepted_rounds[counters[1] % kRoundLog] = 0;
 }
 
 __global__ void msc_bump_kernel(uint32_t *counters, int which) { counters[which] += 1u; }
@@ -448,27 +580,41 @@ static MscDev dev_view(const nlmc_msc *M) {
     d.g_magic = ((unsigned long long)M->W * (unsigned long long)M->G < (1ull << 32))
                     ? (uint32_t)(((1ull << 32) + (unsigned long long)M->G - 1) / (unsigned long long)M->G) : 0u;
     d.seed_lo = (uint32_t)M->seed; d.seed_hi = (uint32_t)(M->seed >> 32);
+    d.slot_begin = M->slot_begin;
+    d.qpc = std::min(M->W, 128) / 4;
+    d.spw = std::max(1, 32 / d.qpc);
+    d.thrbits = M->thrbits;
+    d.thr_lane = reinterpret_cast<const uint4 *>(M->thr_lane);
     return d;
+}
+
+template <int kSteps>
+static void launch_colour(const nlmc_msc *M, const MscDev &d, int first, int cnt) {
+    const bool sub = M->W < 128;
+    const int chunks = (M->W + 127) / 128;
+    const int warps = sub ? (cnt + d.spw - 1) / d.spw : cnt;
+    const dim3 blocks((unsigned)((warps + 7) / 8), (unsigned)chunks);
+    if (M->label_mode) {
+        if (sub) msc_sweep_kernel<kSteps, true, true><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters);
+        else msc_sweep_kernel<kSteps, true, false><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters);
+    } else {
+        if (sub) msc_sweep_kernel<kSteps, false, true><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters);
+        else msc_sweep_kernel<kSteps, false, false><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters);
+    }
 }
 
 static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
     const MscDev d = dev_view(M);
-    const int chunks = (M->W + 127) / 128;
     for (int s = 0; s < n_sweeps; ++s) {
         for (int c = 0; c < M->n_colours; ++c) {
             const int first = M->colour_ptr[c], cnt = M->colour_ptr[c + 1] - first;
             if (cnt == 0) continue;
-            const dim3 blocks((unsigned)((cnt + 7) / 8), (unsigned)chunks);
             switch (M->k_steps) {
-                case 3: msc_sweep_kernel<3><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
-                case 4: msc_sweep_kernel<4><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
-                case 5: msc_sweep_kernel<5><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
-                case 9: msc_sweep_kernel<9><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
-                case 7: msc_sweep_kernel<7><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
-                case 8: msc_sweep_kernel<8><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
-                case 10: msc_sweep_kernel<10><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
-                case 12: msc_sweep_kernel<12><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
-                default: msc_sweep_kernel<6><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters); break;
+                case 4: launch_colour<4>(M, d, first, cnt); break;
+                case 5: launch_colour<5>(M, d, first, cnt); break;
+                case 7: launch_colour<7>(M, d, first, cnt); break;
+                case 8: launch_colour<8>(M, d, first, cnt); break;
+                default: launch_colour<6>(M, d, first, cnt); break;
             }
         }
         msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 0);
@@ -484,11 +630,13 @@ static int launch_energy(nlmc_msc *M) {
     // grid still fills the GPU (about 8 warps per SM)
     const bool bipartite = M->n_colours == 2;  // one colour class sees every bond once
     const int n_list = bipartite ? M->colour_ptr[1] : M->n;
-    const int sites_for_fill = (int)(((long long)n_list * chunks + 148 * 8 - 1) / (148 * 8));
+    const int groups = 148 * 8 * (M->W < 128 ? d.spw : 1);  // short rows: spw site chunks per warp
+    const int sites_for_fill = (int)(((long long)n_list * chunks + groups - 1) / groups);
     const int chunk = std::max(16, std::min(kEnergyChunk, sites_for_fill));
     const int site_chunks = (n_list + chunk - 1) / chunk;
     NLMC_CUDA(cudaMemsetAsync(M->E_acc, 0, sizeof(int32_t) * (size_t)M->W * 32, M->stream));
-    const long long warps = (long long)site_chunks * chunks;
+    long long warps = (long long)site_chunks * chunks;
+    if (M->W < 128) warps = (warps + d.spw - 1) / d.spw;  // short rows: spw site chunks per warp
     msc_energy_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, M->stream>>>(d, M->E_acc, chunk, n_list);
     msc_energy_finish_kernel<<<(M->W * 32 + 255) / 256, 256, 0, M->stream>>>(M->W, M->G, M->n_ladders, M->n_bonds,
                                                                             bipartite ? 2 : 1, M->E_acc, M->E);
@@ -496,15 +644,51 @@ static int launch_energy(nlmc_msc *M) {
     return NLMC_OK;
 }
 
+static int launch_thrbits(nlmc_msc *M) {
+    const int items = std::max(M->k_steps * 3, 32) * M->W;
+    msc_thrbits_kernel<<<(items + 127) / 128, 128, 0, M->stream>>>(
+        M->k_steps, M->W, M->G, M->labels + (size_t)M->slot_begin * M->n_ladders, M->thr_total, M->thrbits,
+        reinterpret_cast<uint4 *>(M->thr_lane));
+    NLMC_CUDA(cudaGetLastError());
+    return NLMC_OK;
+}
+
+// label mode: decisions on the energies of ALL slots (E_full [n_beta_total][n_ladders], device), then this handle's
+// threshold planes are rebuilt from the new labels
+static int launch_label_exchange(nlmc_msc *M, const double *E_full_dev, int num_pairs) {
+    const MscDev d = dev_view(M);
+    msc_clear_round_slot_kernel<<<1, 1, 0, M->stream>>>(M->accepted_rounds, M->d_counters);
+    if (M->n_beta_total >= 2 && num_pairs > 0) {
+        msc_label_swap_kernel<<<(M->n_ladders + 127) / 128, 128, 0, M->stream>>>(
+            M->n_beta_total, M->n_ladders, num_pairs, M->betas_total, E_full_dev, M->labels, M->slot_of, M->accepted,
+            M->accepted_rounds, d.seed_lo, d.seed_hi, M->d_counters, M->ladder_offset);
+        int rc = launch_thrbits(M);
+        if (rc) return rc;
+    }
+    msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 1);
+    NLMC_CUDA(cudaGetLastError());
+    return NLMC_OK;
+}
+
 static int launch_swap(nlmc_msc *M, int num_pairs) {
     const MscDev d = dev_view(M);
-    if (M->n_beta < 2 || num_pairs <= 0) return NLMC_OK;
-    NLMC_CUDA(cudaMemsetAsync(M->swapmask, 0, sizeof(uint32_t) * (size_t)(M->n_beta - 1) * M->G, M->stream));
-    msc_swap_decide_kernel<<<(M->n_ladders + 127) / 128, 128, 0, M->stream>>>(
-        M->n_beta, M->n_ladders, M->G, num_pairs, M->betas, M->E, M->swapmask, M->accepted, d.seed_lo, d.seed_hi,
-        M->d_counters, M->ladder_offset);
-    const size_t items = (size_t)M->n * M->G;
-    msc_swap_apply_kernel<<<(unsigned)((items + 255) / 256), 256, 0, M->stream>>>(d, M->swapmask);
+    if (M->label_mode) {
+        if (M->n_beta != M->n_beta_total) {
+            set_error("nlmc_msc: this handle holds a block of a sharded ladder; gather the energies of all blocks and call "
+                      "nlmc_msc_exchange_labels");
+            return NLMC_ERR_STATE;
+        }
+        return launch_label_exchange(M, M->E, num_pairs);
+    }
+    msc_clear_round_slot_kernel<<<1, 1, 0, M->stream>>>(M->accepted_rounds, M->d_counters);
+    if (M->n_beta >= 2 && num_pairs > 0) {
+        NLMC_CUDA(cudaMemsetAsync(M->swapmask, 0, sizeof(uint32_t) * (size_t)(M->n_beta - 1) * M->G, M->stream));
+        msc_swap_decide_kernel<<<(M->n_ladders + 127) / 128, 128, 0, M->stream>>>(
+            M->n_beta, M->n_ladders, M->G, num_pairs, M->betas, M->E, M->swapmask, M->accepted, M->accepted_rounds,
+            d.seed_lo, d.seed_hi, M->d_counters, M->ladder_offset);
+        const size_t items = (size_t)M->n * M->G;
+        msc_swap_apply_kernel<<<(unsigned)((items + 255) / 256), 256, 0, M->stream>>>(d, M->swapmask);
+    }
     msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 1);
     NLMC_CUDA(cudaGetLastError());
     return NLMC_OK;
@@ -585,17 +769,21 @@ int nlmc_msc_destroy(nlmc_msc *M) {
     cudaSetDevice(M->inst->device);
     nlmc::drop_graphs(M);
     void *ptrs[] = {M->S, M->rec, M->site_list, M->thr, M->betas, M->E_acc, M->E, M->swapmask, M->accepted,
-                    M->scratch_spins, M->d_counters, M->recM, M->recE};
+                    M->scratch_spins, M->d_counters, M->recM, M->recE, M->labels, M->slot_of, M->thr_total,
+                    M->betas_total, M->thrbits, M->thr_lane, M->accepted_rounds};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (M->ev0) cudaEventDestroy(M->ev0);
     if (M->ev1) cudaEventDestroy(M->ev1);
-    if (M->stream) cudaStreamDestroy(M->stream);
+    if (M->stream && M->own_stream) cudaStreamDestroy(M->stream);
     delete M;
     return NLMC_OK;
 }
 
-int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_ladders, int ladder_offset,
-                    unsigned long long seed, nlmc_msc **out) {
+// label mode when betas_total != NULL: the handle owns the slots [slot_begin, slot_begin + n_beta) of a ladder of
+// n_beta_total temperatures (betas = betas_total + slot_begin is what the slots start at)
+static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, int n_ladders, int ladder_offset,
+                           unsigned long long seed, int n_beta_total, const double *betas_total, int slot_begin,
+                           nlmc_msc **out) {
     using namespace nlmc;
     NLMC_REQUIRE(I && out && betas, "nlmc_msc_create: NULL argument");
     *out = nullptr;
@@ -680,7 +868,11 @@ int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_lad
     M->colour_ptr = colour_ptr;
     M->seed = seed;
     M->h_betas.assign(betas, betas + n_beta);
+    M->label_mode = betas_total ? 1 : 0;
+    M->n_beta_total = betas_total ? n_beta_total : n_beta;
+    M->slot_begin = betas_total ? slot_begin : 0;
     if (const char *e = getenv("NLMC_MSC_STEPS")) M->k_steps = atoi(e);
+    if (M->k_steps != 4 && M->k_steps != 5 && M->k_steps != 7 && M->k_steps != 8) M->k_steps = 6;
     if (const char *e = getenv("NLMC_MSC_GRAPHS")) M->use_graphs = atoi(e) != 0;
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(n_beta, betas);
     std::vector<int32_t> rec((size_t)n * 8, 0);  // records in site_list order: 6 neighbours, sign bits, site
@@ -702,6 +894,8 @@ int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_lad
               cudaMalloc(&M->E, sizeof(double) * (size_t)n_beta * M->n_ladders) == cudaSuccess &&
               cudaMalloc(&M->swapmask, sizeof(uint32_t) * (size_t)std::max(1, n_beta - 1) * M->G) == cudaSuccess &&
               cudaMalloc(&M->accepted, sizeof(int32_t)) == cudaSuccess &&
+              cudaMalloc(&M->accepted_rounds, sizeof(int32_t) * kRoundLog) == cudaSuccess &&
+              cudaMemset(M->accepted_rounds, 0, sizeof(int32_t) * kRoundLog) == cudaSuccess &&
               cudaMalloc(&M->d_counters, 4 * sizeof(uint32_t)) == cudaSuccess &&
               cudaMemset(M->d_counters, 0, 4 * sizeof(uint32_t)) == cudaSuccess &&
               cudaMalloc(&M->scratch_spins, (size_t)n) == cudaSuccess &&
@@ -715,8 +909,122 @@ int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_lad
         nlmc_msc_destroy(M);
         return NLMC_ERR_CUDA;
     }
+    if (M->label_mode) {
+        const std::vector<uint32_t> thr_t = nlmc::msc_thresholds(n_beta_total, betas_total);
+        const size_t nl = (size_t)n_beta_total * M->n_ladders;
+        ok = cudaMalloc(&M->labels, nl) == cudaSuccess && cudaMalloc(&M->slot_of, nl) == cudaSuccess &&
+             cudaMalloc(&M->thr_total, sizeof(uint32_t) * thr_t.size()) == cudaSuccess &&
+             cudaMalloc(&M->betas_total, sizeof(double) * (size_t)n_beta_total) == cudaSuccess &&
+             cudaMalloc(&M->thrbits, sizeof(uint32_t) * (size_t)M->k_steps * 3 * M->W) == cudaSuccess &&
+             cudaMalloc(&M->thr_lane, sizeof(uint32_t) * (size_t)M->W * 32 * 4) == cudaSuccess &&
+             cudaMemcpy(M->thr_total, thr_t.data(), sizeof(uint32_t) * thr_t.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(M->betas_total, betas_total, sizeof(double) * (size_t)n_beta_total, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!ok) {
+            set_error("nlmc_msc_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            nlmc_msc_destroy(M);
+            return NLMC_ERR_CUDA;
+        }
+        msc_labels_identity_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, M->stream>>>(n_beta_total, M->n_ladders, M->labels,
+                                                                                      M->slot_of);
+        const int rc = launch_thrbits(M);
+        if (rc) { nlmc_msc_destroy(M); return rc; }
+    }
     *out = M;
     return nlmc_msc_init_random(M, 0);
+}
+
+int nlmc_msc_create(nlmc_instance *I, int n_beta, const double *betas, int n_ladders, int ladder_offset,
+                    unsigned long long seed, nlmc_msc **out) {
+    return msc_create_impl(I, n_beta, betas, n_ladders, ladder_offset, seed, 0, nullptr, 0, out);
+}
+
+/* Beta-label form of the handle: slots [slot_begin, slot_begin + slot_count) of a ladder of n_beta_total temperatures
+ * (slot s starts at betas_total[s]); exchanges permute the labels, never the configurations.  With slot_count ==
+ * n_beta_total the handle is self-contained (nlmc_msc_round works); a block of a ladder sharded over GPUs is driven
+ * with nlmc_msc_sweep / nlmc_msc_energies_dev / [all-gather by the caller] / nlmc_msc_exchange_labels. */
+int nlmc_msc_create_labelled(nlmc_instance *I, int n_beta_total, const double *betas_total, int slot_begin, int slot_count,
+                             int n_ladders, int ladder_offset, unsigned long long seed, nlmc_msc **out) {
+    using namespace nlmc;
+    NLMC_REQUIRE(out && betas_total, "nlmc_msc_create_labelled: NULL argument");
+    NLMC_REQUIRE(n_beta_total >= 1 && n_beta_total <= kMaxBeta, "nlmc_msc_create_labelled: n_beta_total must be in [1, %d]", kMaxBeta);
+    NLMC_REQUIRE(slot_begin >= 0 && slot_count >= 1 && slot_begin + slot_count <= n_beta_total,
+                 "nlmc_msc_create_labelled: slot block [%d, %d) outside the ladder of %d", slot_begin, slot_begin + slot_count,
+                 n_beta_total);
+    return msc_create_impl(I, slot_count, betas_total + slot_begin, n_ladders, ladder_offset, seed, n_beta_total, betas_total,
+                           slot_begin, out);
+}
+
+/* Run the handle on the caller's CUDA stream (e.g. the stream torch's NCCL collectives are ordered on), so that
+ * sweeps, the energy all-gather and the label exchange queue up without host synchronisation.  NULL = back to the
+ * handle's own stream. */
+int nlmc_msc_set_stream(nlmc_msc *M, void *cuda_stream) {
+    NLMC_REQUIRE(M, "nlmc_msc_set_stream: NULL handle");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    nlmc::drop_graphs(M);
+    if (M->own_stream && M->stream) cudaStreamDestroy(M->stream);
+    if (cuda_stream) {
+        M->stream = static_cast<cudaStream_t>(cuda_stream);
+        M->own_stream = false;
+    } else {
+        NLMC_CUDA(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+        M->own_stream = true;
+    }
+    return NLMC_OK;
+}
+
+/* K4' into a DEVICE buffer: energies of this handle's slots, [slot_count][n_ladders] float64, queued on the handle's
+ * stream without synchronisation (the send buffer of the energy all-gather). */
+int nlmc_msc_energies_dev(nlmc_msc *M, double *out_E_dev) {
+    NLMC_REQUIRE(M && out_E_dev, "nlmc_msc_energies_dev: NULL argument");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    int rc = nlmc::launch_energy(M);
+    if (rc) return rc;
+    if (out_E_dev != M->E)
+        NLMC_CUDA(cudaMemcpyAsync(out_E_dev, M->E, sizeof(double) * (size_t)M->n_beta * M->n_ladders,
+                                  cudaMemcpyDeviceToDevice, M->stream));
+    return NLMC_OK;
+}
+
+/* K6 in label form on the gathered energies E_full_dev [n_beta_total][n_ladders] (device, slot-major): identical
+ * decisions on every rank, labels permuted, this handle's thresholds rebuilt.  No synchronisation. */
+int nlmc_msc_exchange_labels(nlmc_msc *M, const double *E_full_dev, int num_swapping_pairs) {
+    NLMC_REQUIRE(M && E_full_dev, "nlmc_msc_exchange_labels: NULL argument");
+    NLMC_REQUIRE(M->label_mode, "nlmc_msc_exchange_labels: the handle was not created with nlmc_msc_create_labelled");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    return nlmc::launch_label_exchange(M, E_full_dev, num_swapping_pairs);
+}
+
+/* labels[slot][ladder] = index of the temperature the configuration in (slot, ladder) is simulated at; identity for
+ * handles without label exchange.  [n_beta_total][n_ladders_padded] uint8. */
+int nlmc_msc_get_labels(nlmc_msc *M, uint8_t *out_labels) {
+    NLMC_REQUIRE(M && out_labels, "nlmc_msc_get_labels: NULL argument");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    if (!M->label_mode) {
+        for (int b = 0; b < M->n_beta; ++b)
+            for (int l = 0; l < M->n_ladders; ++l) out_labels[(size_t)b * M->n_ladders + l] = (uint8_t)b;
+        return NLMC_OK;
+    }
+    NLMC_CUDA(cudaMemcpyAsync(out_labels, M->labels, (size_t)M->n_beta_total * M->n_ladders, cudaMemcpyDeviceToHost, M->stream));
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    return NLMC_OK;
+}
+
+/* Accepted exchanges of each of the last n_rounds rounds (oldest first), counted on the device per round. */
+int nlmc_msc_swap_counts(nlmc_msc *M, int n_rounds, int *out_counts) {
+    using namespace nlmc;
+    NLMC_REQUIRE(M && out_counts && n_rounds >= 0 && n_rounds <= kRoundLog, "nlmc_msc_swap_counts: bad arguments");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    std::vector<int32_t> log((size_t)kRoundLog);
+    uint32_t counters[4];
+    NLMC_CUDA(cudaMemcpyAsync(log.data(), M->accepted_rounds, sizeof(int32_t) * kRoundLog, cudaMemcpyDeviceToHost, M->stream));
+    NLMC_CUDA(cudaMemcpyAsync(counters, M->d_counters, sizeof(counters), cudaMemcpyDeviceToHost, M->stream));
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    for (int k = 0; k < n_rounds; ++k) {
+        const long long r = (long long)counters[1] - n_rounds + k;
+        out_counts[k] = r >= 0 ? log[(size_t)(r % kRoundLog)] : 0;
+    }
+    return NLMC_OK;
 }
 
 int nlmc_msc_init_random(nlmc_msc *M, unsigned stream_id) {
@@ -740,6 +1048,7 @@ int nlmc_msc_info(const nlmc_msc *M, int *n_words, int *n_ladders_padded, int *n
 
 int nlmc_msc_set_betas(nlmc_msc *M, const double *betas) {
     NLMC_REQUIRE(M && betas, "nlmc_msc_set_betas: NULL argument");
+    NLMC_REQUIRE(!M->label_mode, "nlmc_msc_set_betas: not available on a labelled handle (the ladder is fixed at creation)");
     NLMC_CUDA(cudaSetDevice(M->inst->device));
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(M->n_beta, betas);
     M->h_betas.assign(betas, betas + M->n_beta);

@@ -77,6 +77,12 @@ _SIGNATURES = {
     "nlmc_msc_round_host": [_vp, _vp, _int, _int, _vp, _vp],
     "nlmc_msc_round_host_async": [_vp, _vp, _int, _int, _vp, _vp],
     "nlmc_msc_swap_count": [_vp, C.POINTER(_int), _int],
+    "nlmc_msc_swap_counts": [_vp, _int, _i32],
+    "nlmc_msc_create_labelled": [_vp, _int, _f64, _int, _int, _int, _int, C.c_ulonglong, C.POINTER(_vp)],
+    "nlmc_msc_set_stream": [_vp, _vp],
+    "nlmc_msc_energies_dev": [_vp, _vp],
+    "nlmc_msc_exchange_labels": [_vp, _vp, _int],
+    "nlmc_msc_get_labels": [_vp, _u8],
     "nlmc_msc_sync": [_vp],
     "nlmc_msc_timer_mark": [_vp, _int],
     "nlmc_msc_timer_elapsed_ms": [_vp, C.POINTER(C.c_float)],
@@ -358,15 +364,29 @@ class Replicas:
 class Msc:
     """Bit-packed production state (K2/K4'/K6): n_beta x n_ladders replicas of a +-J instance."""
 
-    def __init__(self, inst: Instance, betas, n_ladders: int, seed: int = 0, ladder_offset: int = 0):
+    def __init__(self, inst: Instance, betas, n_ladders: int, seed: int = 0, ladder_offset: int = 0,
+                 labelled: bool = False, slot_begin: int = 0, slot_count: int | None = None):
+        """labelled=False: slot b sits at betas[b] and exchanges move configuration bits.  labelled=True: `betas` is the
+        WHOLE ladder, the handle owns its slots [slot_begin, slot_begin + slot_count) and exchanges permute beta labels
+        (north_star 4); a block of a ladder sharded over GPUs is driven by distributed.ShardedBetaLadder."""
         self.inst = inst
         self.ladder_offset = int(ladder_offset)
         self.n = inst.n
-        self.betas = np.ascontiguousarray(betas, dtype=np.float64).reshape(-1)
+        self.labelled = bool(labelled)
+        self.betas_total = np.ascontiguousarray(betas, dtype=np.float64).reshape(-1)
+        self.n_beta_total = len(self.betas_total)
+        self.slot_begin = int(slot_begin) if labelled else 0
+        count = self.n_beta_total - self.slot_begin if slot_count is None else int(slot_count)
+        self.betas = self.betas_total[self.slot_begin:self.slot_begin + count] if labelled else self.betas_total
         self.n_beta = len(self.betas)
         handle = _vp()
-        check(lib().nlmc_msc_create(inst._h, self.n_beta, self.betas, int(n_ladders), self.ladder_offset,
-                                    int(seed) & (2**64 - 1), C.byref(handle)), "nlmc_msc_create")
+        if labelled:
+            check(lib().nlmc_msc_create_labelled(inst._h, self.n_beta_total, self.betas_total, self.slot_begin, self.n_beta,
+                                                 int(n_ladders), self.ladder_offset, int(seed) & (2**64 - 1),
+                                                 C.byref(handle)), "nlmc_msc_create_labelled")
+        else:
+            check(lib().nlmc_msc_create(inst._h, self.n_beta, self.betas, int(n_ladders), self.ladder_offset,
+                                        int(seed) & (2**64 - 1), C.byref(handle)), "nlmc_msc_create")
         self._h = handle
         w, lad, col, nb = _int(), _int(), _int(), C.c_longlong()
         check(lib().nlmc_msc_info(self._h, C.byref(w), C.byref(lad), C.byref(col), C.byref(nb)), "nlmc_msc_info")
@@ -445,6 +465,41 @@ class Msc:
         v = _int()
         check(lib().nlmc_msc_swap_count(self._h, C.byref(v), int(reset)), "nlmc_msc_swap_count")
         return v.value
+
+    def swap_counts(self, n_rounds: int) -> np.ndarray:
+        """Accepted exchanges of each of the last n_rounds rounds (oldest first), counted on the device."""
+        out = np.zeros(int(n_rounds), dtype=np.int32)
+        if n_rounds:
+            check(lib().nlmc_msc_swap_counts(self._h, int(n_rounds), out), "nlmc_msc_swap_counts")
+        return out
+
+    def set_stream(self, cuda_stream_ptr):
+        """Run on the caller's CUDA stream (an int/pointer, e.g. torch.cuda.Stream().cuda_stream); None = own stream."""
+        check(lib().nlmc_msc_set_stream(self._h, cuda_stream_ptr), "nlmc_msc_set_stream")
+
+    def energies_dev(self, out_dev_ptr):
+        """K4' into a device buffer [n_beta][n_ladders] float64 (no synchronisation)."""
+        check(lib().nlmc_msc_energies_dev(self._h, out_dev_ptr), "nlmc_msc_energies_dev")
+
+    def exchange_labels(self, E_full_dev_ptr, num_swapping_pairs: int):
+        """Label exchange on the gathered energies [n_beta_total][n_ladders] (device pointer; no synchronisation)."""
+        check(lib().nlmc_msc_exchange_labels(self._h, E_full_dev_ptr, int(num_swapping_pairs)), "nlmc_msc_exchange_labels")
+
+    def energies_into(self, t):
+        """energies_dev into a torch CUDA tensor [n_beta][n_ladders] float64 (contiguous)."""
+        assert t.is_cuda and t.is_contiguous() and tuple(t.shape) == (self.n_beta, self.n_ladders)
+        self.energies_dev(t.data_ptr())
+
+    def exchange_labels_from(self, E_full, num_swapping_pairs: int):
+        """exchange_labels on a torch CUDA tensor [n_beta_total][n_ladders] float64 (contiguous)."""
+        assert E_full.is_cuda and E_full.is_contiguous() and tuple(E_full.shape) == (self.n_beta_total, self.n_ladders)
+        self.exchange_labels(E_full.data_ptr(), num_swapping_pairs)
+
+    def labels(self) -> np.ndarray:
+        """labels[slot][ladder]: index of the temperature the configuration in (slot, ladder) is simulated at."""
+        out = np.empty((self.n_beta_total, self.n_ladders), dtype=np.uint8)
+        check(lib().nlmc_msc_get_labels(self._h, out), "nlmc_msc_get_labels")
+        return out
 
     def sync(self):
         check(lib().nlmc_msc_sync(self._h), "nlmc_msc_sync")
