@@ -3,20 +3,24 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Metric (BASELINE.json): spin-flip attempts/s.  Workload: config C5 -- 3D +-J Edwards-Anderson L=64
-(262,144 spins), NPT with 32 inverse temperatures x 128 independent ladders = 4096 replicas per GPU.
-A "step" is one swap round of NPT.run for all ladders: `spm` heat-bath sweeps of every replica, the
-energies of every replica, and the replica-exchange step (NPT/npt.py:617-680).
+Metric (BASELINE.json): spin-flip attempts/s.  Workload: config C5 as stated -- 3D +-J Edwards-Anderson L=64
+(262,144 spins), NPT with 32 inverse temperatures x 128 independent ladders = 4096 replicas IN TOTAL.  A "step" is one
+swap round of NPT.run for all ladders: `spm` heat-bath sweeps of every replica, the energies of every replica, and the
+replica-exchange step (NPT/npt.py:617-680).
 
-  value   attempts/s with the state resident in HBM, CUDA events on the library's stream, max over ranks.
-  e2e     the same step through the C-ABI entry point that takes HOST buffers (nlmc_msc_round_host):
-          packed spins in from pinned host memory, packed spins + energies back out, copies inside the
-          timed region (the reference ships m_start to its workers and M back every round, npt.py:625-644).
-  N > 1   one process per GPU (torchrun); ladders are independent, so every rank runs its own 128 ladders
-          (weak scaling, no data-path collective); only the timing is reduced (max) over NCCL.
-  --impl reference   the reference algorithm on the host cores: the oracle C port of MCMC
-          (oracle/nlmc_oracle.c; the reference itself is pure Python and cannot travel to the GPU box),
-          all host threads, a bounded sample of the same workload per step.
+  value      attempts/s with the state resident in HBM, CUDA events on the stream the kernels run on, max over ranks.
+             N > 1 (torchrun, one process per GPU): STRONG scaling -- the temperature range of the 128 ladders is sharded
+             over the GPUs; per round one float64 per replica is all-gathered over NCCL and every rank permutes the beta
+             labels identically (spins never move).  `weak` holds the weak-scaling figure beside it (every GPU runs the
+             whole stated C5 on its own ladders, no collective).
+  e2e        the same metric through the drop-in class, NPT(J, h, mode="production").run(...): host J in, numpy M and
+             Energy out, one call = K rounds; `e2e_host_buffers` is the C-ABI round that ships the packed state both ways.
+  roofline   the colour-sweep kernel against the measured HBM peak with the bit-packed layout's algorithmic bytes
+             (0.25 B/attempt); `roofline_issue` is the bound that applies (integer issue).
+  sustained  the same step for >= 5 s with clocks and power sampled under load.
+  time_to_target  median time to the shipped ground-state energy (Chimera droplet, DCL, Wishart), GPU vs the CPU port.
+  --impl reference   the reference algorithm on the host cores: the oracle C port of MCMC (oracle/nlmc_oracle.c; the
+             reference itself is pure Python and cannot travel to the GPU box), all host threads, a bounded sample.
 """
 from __future__ import annotations
 
@@ -149,7 +153,7 @@ def run_reference(args, rank, world):
     sample = f"{reps} replicas x {sweeps} sweeps of the L={L} lattice per step ({attempts:.3g} attempts)"
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": workload_config(args, world, reference=True),
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -158,26 +162,27 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, world, reference=False):
+    lad = ((args.n_ladders + 127) // 128) * 128
     return {"workload": f"C5: 3D +-J Edwards-Anderson L={args.L} ({args.L ** 3} spins) NPT, {args.n_beta} betas x "
-                        f"{args.n_ladders} ladders = {args.n_beta * args.n_ladders} replicas per GPU, "
+                        f"{lad} ladders = {args.n_beta * lad} replicas in total, "
                         f"{args.spm} sweeps per swap round, {args.pairs} swapping pairs per ladder",
-            "L": args.L, "n_beta": args.n_beta, "n_ladders_per_gpu": args.n_ladders, "sweeps_per_step": args.spm,
-            "replicas_total": args.n_beta * args.n_ladders * world, "beta_range": [0.2, 2.0],
-            "parallelism": f"replicas: {world} x {args.n_ladders} independent ladders, no data-path collective",
-            "l2": "state (n x words x 4 B = 134 MB at the default size) is larger than the 126 MB L2; no flush needed "
-                  "(ncu: 78 MB of DRAM reads per colour launch against 67 MB compulsory, profiles/r1c_sweep_kernel_summary.md)"
+            "L": args.L, "n_beta": args.n_beta, "n_ladders": lad, "sweeps_per_step": args.spm,
+            "replicas_total": args.n_beta * lad, "beta_range": [0.2, 2.0],
+            "parallelism": ("one GPU owns every temperature slot" if world == 1 else
+                            f"temperature range of every ladder sharded over {world} GPUs in contiguous blocks; per round one "
+                            "float64 energy per replica is all-gathered (NCCL) and every rank permutes the beta labels "
+                            "identically; spin configurations never move") if not reference else "host threads",
+            "l2": "state (n x words x 4 B = 134 MB at the default size) is larger than the 126 MB L2 on one GPU; a block of a "
+                  "sharded ladder (134 MB / N) fits, which is part of what the per-N numbers show; no flush"
             if not reference else "n/a (host)"}
 
 
 def bind_to_gpu_numa_node(device_index: int):
-    """Pin this rank to the CPUs of its GPU's NUMA node so that the pinned host buffers of the end-to-end leg are
-    first-touched next to the GPU's PCIe root (matters when 8 ranks stream 268 MB per step each)."""
+    """Pin this rank to the CPUs of its GPU's NUMA node (pinned host buffers are first-touched next to the GPU)."""
     try:
         import torch
-        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
-        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
-        dev = torch.cuda.get_device_properties(device_index).pci_device_id
-        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        pr = torch.cuda.get_device_properties(device_index)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/numa_node"
         node = int(open(path).read().strip())
         if node < 0:
             return None
@@ -194,9 +199,18 @@ def bind_to_gpu_numa_node(device_index: int):
     return None
 
 
+def load_ttt():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("time_to_target", os.path.join(ROOT, "tools", "time_to_target.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
-    from nlmc_b200 import _lib, host
+    from nlmc_b200 import NPT, _lib, host
+    from nlmc_b200.distributed import ShardedBetaLadder
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -204,81 +218,95 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank
+    torch.cuda.set_device(device)
     _lib.require_device(device)
     numa_node = bind_to_gpu_numa_node(device) if world > 1 else None
-    L, n_beta, n_ladders, spm, pairs = args.L, args.n_beta, args.n_ladders, args.spm, args.pairs
+    L, n_beta, spm, pairs = args.L, args.n_beta, args.spm, args.pairs
     betas = np.linspace(0.2, 2.0, n_beta)
     sampler = ClockSampler(device) if rank == 0 else None  # started early: nvidia-smi needs ~0.1 s before its first row
     A = ea3d_csr(L, 5)
-    prob = host.Problem(A, np.zeros(A.shape[0]), device=device)
-    # every rank owns its own block of ladders; streams are keyed by the global ladder index
-    msc = _lib.Msc(prob.inst, betas, n_ladders, seed=1000, ladder_offset=rank * (((n_ladders + 127) // 128) * 128))
-    n = prob.n
-    replicas = n_beta * msc.n_ladders
-    attempts_per_step = replicas * n * spm
+    n = A.shape[0]
+    prob = host.Problem(A, np.zeros(n), device=device)
+    stream = torch.cuda.Stream(device)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    # ---- device-resident throughput --------------------------------------------------------------
-    for _ in range(args.warmup):
-        msc.round(spm, pairs)
-    msc.sync()
-    barrier()
-    t_wall0 = time.perf_counter()
-    msc.timer_mark(0)
-    for _ in range(args.steps):
-        msc.round(spm, pairs)
-    msc.timer_mark(1)
-    msc.sync()
-    ms = msc.timer_elapsed_ms()
-    t_wall1 = time.perf_counter()
-    barrier()
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    if dist is not None:
-        t = torch.tensor([ms], device=f"cuda:{device}", dtype=torch.float64)
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=f"cuda:{device}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = attempts_per_step * world * args.steps / (ms * 1e-3)
-    # per step: spm x (colour kernels + sweep-counter bump) + energy (2) + exchange (2) + round-counter bump,
-    # replayed from one captured CUDA graph
-    launches = args.steps * (spm * (msc.n_colours + 1) + 5)
+        return float(t.item())
 
-    # ---- dominant kernel alone: the colour sweep ---------------------------------------------------
+    def timed(step, steps):
+        """ms for `steps` calls of step(), CUDA events on the stream the kernels are launched on, max over ranks."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        w0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        e1.synchronize()
+        w1 = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        return max_over_ranks(ms), w0, w1
+
+    # ---- headline: the stated C5 (n_beta x n_ladders replicas IN TOTAL), state resident in HBM ----------------------
+    if world == 1:
+        eng = _lib.Msc(prob.inst, betas, args.n_ladders, seed=1000)
+        eng.set_stream(stream.cuda_stream)
+        msc, step = eng, (lambda: eng.round(spm, pairs))
+        exchange = "configuration bits exchanged on the device (msc_swap_decide + msc_swap_apply)"
+        kernels_per_step = spm * (eng.n_colours + 1) + 2 + 4   # sweeps + counter bumps, energy (2), exchange (4)
+    else:
+        ens = ShardedBetaLadder(prob, betas, args.n_ladders, seed=1000, device=device)
+        stream = ens.stream
+        msc, step = ens.msc, (lambda: ens.round(spm, pairs))
+        exchange = ("beta labels: energies all-gathered over NCCL (8 B per replica), identical Philox-keyed decisions on every "
+                    "rank, thresholds rebuilt from the labels (msc_label_swap + msc_thrbits)")
+        kernels_per_step = spm * (msc.n_colours + 1) + 2 + 4   # sweeps + bumps, energy (2), clear/label_swap/thrbits/bump
+    n_ladders = msc.n_ladders
+    replicas_total = n_beta * n_ladders
+    attempts_per_step = replicas_total * n * spm
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+        ms, t_wall0, t_wall1 = timed(step, args.steps)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    value = attempts_per_step * args.steps / (ms * 1e-3)
+    launches = args.steps * kernels_per_step
+
+    # ---- dominant kernel alone: one colour of one sweep over this rank's slots -----------------------------------------
     n_time = max(4, spm)
-    msc.sweep(2)
-    msc.sync()
-    msc.timer_mark(0)
-    msc.sweep(n_time)
-    msc.timer_mark(1)
-    msc.sync()
-    sweep_ms = msc.timer_elapsed_ms() / (n_time * msc.n_colours)  # average launch duration
-    attempts_per_launch = replicas * n / msc.n_colours
+    with torch.cuda.stream(stream):
+        msc.sweep(2)
+        sweep_ms_total, _, _ = timed(lambda: msc.sweep(n_time), 1)
+    sweep_ms = sweep_ms_total / (n_time * msc.n_colours)             # average launch duration (incl. the 1-thread bumps)
+    local_replicas = msc.n_beta * n_ladders
+    attempts_per_launch = local_replicas * n / msc.n_colours
     peak, peak_src = measured_peaks()
-    survey_bytes = SURVEY_BYTES_PER_ATTEMPT * attempts_per_launch
-    packed_bytes = 2.0 * (n / msc.n_colours) * msc.n_words * 4  # read the other colour once + write this colour
+    packed_bytes = 2.0 * (n / msc.n_colours) * msc.n_words * 4        # read the other colour once + write this colour
     traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "msc_sweep_kernel (one colour of one sweep)",
-                "achieved": survey_bytes / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": survey_bytes / (sweep_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-                "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+    kernel_name = f"msc_sweep_kernel<6, {'bit planes' if world > 1 else 'scalar thresholds'}> (one colour of one sweep)"
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": packed_bytes / (sweep_ms * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": packed_bytes / (sweep_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                "traffic": (traffic or {}).get("dram_bytes_per_launch") if world == 1 else None,
+                "traffic_source": (traffic or {}).get("source") if world == 1 else None,
                 "launch_ms": sweep_ms, "attempts_per_launch": attempts_per_launch,
-                "bytes_per_attempt": SURVEY_BYTES_PER_ATTEMPT,
-                "note": "achieved uses SURVEY.md 8(d)'s generic-CSR figure (42 B/attempt); the kernel is bit-packed "
-                        "(32 ladders per word), so its own traffic is far lower -- see roofline_packed and DESIGN.md",
-                "share_of_step": (sweep_ms * spm * msc.n_colours) / (ms / args.steps)}
-    roofline_packed = {"bound": "hbm", "achieved": packed_bytes / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                       "frac": packed_bytes / (sweep_ms * 1e-3) / 1e9 / peak,
-                       "bytes_per_attempt": packed_bytes / attempts_per_launch,
-                       "note": "bit-packed layout: 0.25 B/attempt compulsory traffic; the kernel is ALU/issue bound "
-                               "(Philox + bit-sliced logic), not HBM bound"}
-
-    # what actually bounds the kernel: warp-instruction issue (integer pipes).  The instruction count per launch is a
-    # property of the code (ncu smsp__inst_executed.sum of the committed capture); the launch duration is measured here.
+                "bytes_per_attempt": packed_bytes / attempts_per_launch,
+                "share_of_step": (sweep_ms * spm * msc.n_colours) / (ms / args.steps),
+                "note": "algorithmic bytes of the bit-packed layout (SURVEY 8d: 0.25 B/attempt = read the other colour's rows + "
+                        "write this colour's, 1 bit per spin).  The kernel is bound by integer issue (Philox4x32-10 + bit-sliced "
+                        "compare), not by HBM: see roofline_issue.  SURVEY 8d's generic int8-CSR figure (42 B/attempt) does not "
+                        "describe this layout; against it the same launch would read as "
+                        f"{SURVEY_BYTES_PER_ATTEMPT * attempts_per_launch / (sweep_ms * 1e-3) / 1e9 / peak:.1f} x the HBM peak"}
     roofline_issue = None
-    if traffic and traffic.get("warp_instructions_per_launch") and traffic.get("attempts_per_launch") == attempts_per_launch:
+    if world == 1 and traffic and traffic.get("warp_instructions_per_launch") and traffic.get("attempts_per_launch") == attempts_per_launch:
         props = torch.cuda.get_device_properties(device)
         sm_clock_hz = 1e6 * (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965.0)
         issue_peak = props.multi_processor_count * 4 * sm_clock_hz          # one warp instruction per scheduler and clock
@@ -287,65 +315,112 @@ def run_ours(args, rank, world, local_rank):
                           "frac": achieved / issue_peak,
                           "warp_instructions_per_attempt": traffic["warp_instructions_per_launch"] / attempts_per_launch,
                           "note": "SMs x 4 schedulers x SM clock under load; instruction count from the committed ncu capture "
-                                  "(profiles/traffic.json), duration measured live"}
+                                  "of this kernel (profiles/traffic.json), duration measured live"}
 
-    # ---- end to end through the host-buffer entry point -------------------------------------------
-    # Every step ships one batch of packed states from pinned host memory to the device, runs the round and
-    # ships states + energies back.  NH handles are used in turn (nlmc_msc_round_host_async + nlmc_msc_sync), so
-    # the copies of one batch overlap the sweeps of the others; each handle works strictly in -> round -> out.
-    # Measured with tools/e2e_pipeline_probe.py: 11.1 / 7.6 / 6.2 / 6.1 ms per step with 1 / 2 / 3 / 4 handles.
-    shape = msc.packed_shape()
-    NH = max(1, args.e2e_handles)
-    handles = [msc] + [_lib.Msc(prob.inst, betas, n_ladders, seed=8919 + i,
-                                ladder_offset=rank * (((n_ladders + 127) // 128) * 128)) for i in range(NH - 1)]
-    h_in = [torch.empty(shape, dtype=torch.int32, pin_memory=True) for _ in range(NH)]
-    h_out = [torch.empty(shape, dtype=torch.int32, pin_memory=True) for _ in range(NH)]
-    h_E = [torch.empty((n_beta, msc.n_ladders), dtype=torch.float64, pin_memory=True) for _ in range(NH)]
-    msc.get_packed(h_in[0].numpy().view(np.uint32))  # current device state -> pinned host buffers
-    for k in range(1, NH):
-        h_in[k].copy_(h_in[0])
+    # ---- sustained: the same step for >= args.sustain seconds, clocks and power sampled under load ---------------------
+    sustained = None
+    if args.sustain > 0:
+        s2 = ClockSampler(device) if rank == 0 else None
+        chunk = max(1, int(0.5 / (ms / args.steps * 1e-3)))                  # about half a second per chunk
+        n_chunks = max(1, int(np.ceil(args.sustain / (chunk * ms / args.steps * 1e-3))))
+        with torch.cuda.stream(stream):
+            sms, w0, w1 = timed(step, chunk * n_chunks)
+        c2 = s2.stop(w0, w1) if s2 else None
+        sustained = {"seconds": sms * 1e-3, "steps": chunk * n_chunks, "value": attempts_per_step * chunk * n_chunks / (sms * 1e-3),
+                     "unit": UNIT, "clocks": c2}
 
-    def e2e_steps(count):
-        for i in range(count):
-            k = i % NH
-            handles[k].sync()                      # batch i-NH is complete: its outputs are on the host
-            h_in[k], h_out[k] = h_out[k], h_in[k]  # and become the next input of this handle
-            handles[k].round_host_async(h_in[k].data_ptr(), spm, pairs, h_out[k].data_ptr(), h_E[k].data_ptr())
-        for hdl in handles:
-            hdl.sync()
+    # ---- weak scaling beside the strong one (N > 1): every rank runs the WHOLE stated C5 on its own ladders -------------
+    weak = None
+    if world > 1:
+        own = _lib.Msc(prob.inst, betas, args.n_ladders, seed=1000, ladder_offset=rank * n_ladders)
+        own.set_stream(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            for _ in range(args.warmup):
+                own.round(spm, pairs)
+            wms, _, _ = timed(lambda: own.round(spm, pairs), args.steps)
+        weak = {"value": attempts_per_step * world * args.steps / (wms * 1e-3), "unit": UNIT, "scaling": "weak",
+                "replicas_total": replicas_total * world, "ms_per_step": wms / args.steps,
+                "note": "independent ladders per GPU (N x the stated C5), no data-path collective"}
+        own.close()
 
-    for k in range(NH):
-        h_out[k].copy_(h_in[k])
-    e2e_steps(max(NH, args.warmup))
+    # ---- end to end through the drop-in class: NPT(J, h, mode='production').run(...) ----------------------------------
+    # host J (scipy CSR) in, numpy (M, Energy) out; one call = args.steps swap rounds.  Inside the timed region: CSR
+    # upload, colouring, state initialisation, every round, the recorded last round and its float64 M on the host.
+    def api_run(rounds):
+        obj = NPT(A, np.zeros(n), mode="production", device=device)
+        obj.num_runs = args.n_ladders
+        return obj.run(betas, n_beta, [False] * n_beta, num_sweeps_MCMC=spm * rounds, num_sweeps_read=spm * rounds,
+                       num_swap_attempts=rounds, num_swapping_pairs=pairs)
+
+    api_run(max(1, args.warmup))
     barrier()
     t0 = time.perf_counter()
-    e2e_steps(args.steps)
+    M_out, E_out = api_run(args.steps)
     torch.cuda.synchronize(device)
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    if dist is not None:
-        t = torch.tensor([e2e_s], device=f"cuda:{device}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    # one batch alone, no overlap: the latency of a single host -> host round
-    handles[0].sync()
-    t1 = time.perf_counter()
-    handles[0].round_host(h_in[0].data_ptr(), spm, pairs, h_out[0].data_ptr(), h_E[0].data_ptr())
-    single_ms = 1e3 * (time.perf_counter() - t1)
-    e2e = {"value": attempts_per_step * world * args.steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(h_in[0].numel() * 4),
-           "d2h_bytes_per_step": int(h_out[0].numel() * 4 + h_E[0].numel() * 8),
-           "ms_per_step": 1e3 * e2e_s / args.steps,
-           "api": f"nlmc_msc_round_host_async + nlmc_msc_sync (C ABI, pinned host buffers, {NH} handles in turn)",
-           "single_batch_ms": single_ms,
-           "numa_node_rank0": numa_node,
-           "mean_energy_coldest": float(h_E[0][-1].mean())}
-    for hdl in handles[1:]:
-        hdl.close()
+    csr_bytes = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes + 8 * n
+    d2h = spm * msc.n_beta * n + spm * msc.n_beta * n_ladders * 8       # recorded int8 states of run 0 + energies, this rank
+    e2e = {"value": attempts_per_step * args.steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(csr_bytes / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
+           "ms_per_step": 1e3 * e2e_s / args.steps, "seconds_per_call": e2e_s, "rounds_per_call": args.steps,
+           "api": "NPT(J, h, mode='production').run(beta_list, 32, [False]*32, ..., num_swap_attempts=steps) with num_runs ladders "
+                  "side by side: host scipy J in, numpy M (float64, last round, run 0) and Energy out; state resident across rounds",
+           "returned": {"M_shape": list(M_out.shape), "Energy_coldest": float(E_out[-1])},
+           "numa_node_rank0": numa_node}
+    del M_out
 
-    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample --------------------
-    cpu = None
+    # second key: one swap round per call through HOST buffers (the C-ABI entry point that ships the packed state both ways)
+    e2e_host = None
+    if world == 1 and not args.no_host_round:
+        shape = msc.packed_shape()
+        NH = max(1, args.e2e_handles)
+        msc.set_stream(None)
+        handles = [msc] + [_lib.Msc(prob.inst, betas, args.n_ladders, seed=8919 + i) for i in range(NH - 1)]
+        h_in = [torch.empty(shape, dtype=torch.int32, pin_memory=True) for _ in range(NH)]
+        h_out = [torch.empty(shape, dtype=torch.int32, pin_memory=True) for _ in range(NH)]
+        h_E = [torch.empty((n_beta, n_ladders), dtype=torch.float64, pin_memory=True) for _ in range(NH)]
+        msc.get_packed(h_in[0].numpy().view(np.uint32))
+        for k in range(1, NH):
+            h_in[k].copy_(h_in[0])
+
+        def host_steps(count):
+            for i in range(count):
+                k = i % NH
+                handles[k].sync()
+                h_in[k], h_out[k] = h_out[k], h_in[k]
+                handles[k].round_host_async(h_in[k].data_ptr(), spm, pairs, h_out[k].data_ptr(), h_E[k].data_ptr())
+            for hdl in handles:
+                hdl.sync()
+
+        for k in range(NH):
+            h_out[k].copy_(h_in[k])
+        host_steps(max(NH, args.warmup))
+        t0 = time.perf_counter()
+        host_steps(args.steps)
+        torch.cuda.synchronize(device)
+        hs = time.perf_counter() - t0
+        e2e_host = {"value": attempts_per_step * args.steps / hs, "unit": UNIT, "ms_per_step": 1e3 * hs / args.steps,
+                    "h2d_bytes_per_step": int(h_in[0].numel() * 4),
+                    "d2h_bytes_per_step": int(h_out[0].numel() * 4 + h_E[0].numel() * 8),
+                    "api": f"nlmc_msc_round_host_async + nlmc_msc_sync (C ABI, pinned host buffers, {NH} handles in turn): the "
+                           "whole packed state crosses PCIe both ways every round"}
+        for hdl in handles[1:]:
+            hdl.close()
+
+    # ---- time to target (BASELINE metric, second half) and the CPU baseline: rank 0 at N = 1 -----------------------------
+    ttt_rows, cpu = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
+        ttt = load_ttt()
+        rows = ttt.measure(repeats=args.ttt_repeats, cpu=True)
+        ttt_rows = []
+        for name in ttt.ALL:
+            g = [r for r in rows if r["instance"] == name and r["arm"].startswith("gpu")][0]
+            c = [r for r in rows if r["instance"] == name and r["arm"].startswith("cpu")][0]
+            ttt_rows.append({"instance": g["what"].replace("time to ground state, ", ""), "engine": g["engine"],
+                             "gpu_median_s": g["median_seconds"], "cpu_median_s": c["median_seconds"],
+                             "cpu_over_gpu": c["median_seconds"] / g["median_seconds"], "repeats": args.ttt_repeats,
+                             "gpu_arm": g["arm"], "cpu_arm": c["arm"]})
         cores = os.cpu_count() or 1
         reps, sw = max(1, min(cores, 64)), max(1, args.ref_sweeps)
         once, attempts = cpu_port_rate(L, betas, reps, sw, cores)
@@ -356,13 +431,18 @@ def run_ours(args, rank, world, local_rank):
                          "oracle/nlmc_oracle.c (reference algorithm, injected MT19937 stream)"}
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "u32", "dtype_note": "bit planes: 1 bit per spin, 32 ladders per 32-bit word", "data": "synthetic",
-               "config": workload_config(args, world), "roofline": roofline, "roofline_packed": roofline_packed, "roofline_issue": roofline_issue,
-               "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-               "per_gpu_value": value / world, "ps_per_attempt": 1e12 / (value / world)}
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "u32", "dtype_note": "bit planes: 1 bit per spin, 32 ladders per 32-bit word",
+               "data": "synthetic", "config": workload_config(args, world), "exchange": exchange,
+               "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu, "e2e": e2e,
+               "e2e_host_buffers": e2e_host, "weak": weak, "sustained": sustained, "time_to_target": ttt_rows,
+               "gpu_launches": launches, "clocks": clocks, "per_gpu_value": value / world,
+               "ps_per_attempt": 1e12 / (value / world)}
         print(json.dumps(out), flush=True)
-    msc.close()
+    if world == 1:
+        msc.close()
+    else:
+        ens.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -381,7 +461,10 @@ def main():
     ap.add_argument("--ref-sweeps", dest="ref_sweeps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-handles", dest="e2e_handles", type=int, default=3,
-                    help="handles used in turn by the end-to-end leg (copies of one batch overlap the sweeps of the others)")
+                    help="handles used in turn by the host-buffer leg (copies of one batch overlap the sweeps of the others)")
+    ap.add_argument("--no-host-round", dest="no_host_round", action="store_true", help="skip the host-buffer leg")
+    ap.add_argument("--sustain", type=float, default=5.0, help="seconds of the sustained leg (0 = skip)")
+    ap.add_argument("--ttt-repeats", dest="ttt_repeats", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -46,6 +46,9 @@ int nlmc_device_count(void);
 int nlmc_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor,
                      uint64_t *free_bytes, uint64_t *total_bytes);
 
+/* host-side format helper: int8 spins -> the float64 arrays the reference's API returns (NMC/nmc.py:52,89), multi-threaded */
+int nlmc_host_widen_i8_f64(const int8_t *in, double *out, uint64_t count, int threads);
+
 /* ---- instance ---------------------------------------------------------------------------------
  * Replaces `J = csr_matrix(J)` + `h = asarray(h)` at the top of every MCMC call (NMC/nmc.py:53-54):
  * the CSR is uploaded once, entries in scipy's csr_matrix(J) order. */
@@ -200,6 +203,8 @@ int nlmc_msc_energies(nlmc_msc *msc, double *out_E);
  * M[:, jj] = m, NMC/nmc.py:89) and/or the energies of all replicas (out_E [n_sweeps][n_beta][n_ladders_padded],
  * NPT/npt.py:40-43, NPT/apt_preprocessor.py:107-110) on the device; one copy back at the end */
 int nlmc_msc_sweep_record(nlmc_msc *msc, int n_sweeps, int ladder, int8_t *out_M, double *out_E);
+/* the same with the recorded states laid out as the rows of the reference's M: m_layout 1 = [n_beta][n][n_sweeps] */
+int nlmc_msc_sweep_record_layout(nlmc_msc *msc, int n_sweeps, int ladder, int8_t *out_M, double *out_E, int m_layout);
 int nlmc_msc_round(nlmc_msc *msc, int n_sweeps, int num_swapping_pairs, double *out_E);
 int nlmc_msc_round_host(nlmc_msc *msc, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,
                         uint32_t *packed_out, double *out_E);

@@ -1,6 +1,7 @@
 // nlmc_api.cu -- handle management of the C ABI (instances, replicas) and error reporting.
 #include <algorithm>
 #include <cmath>
+#include <thread>
 #include <utility>
 
 #include "nlmc_common.cuh"
@@ -74,22 +75,38 @@ int nlmc_instance_create(int n, const int32_t *row_ptr, const int32_t *col, cons
     // accepts any J through J.dot(m), NMC/nmc.py:86).
     bool value_symmetric = true;
     {
-        std::vector<std::pair<int32_t, double>> row;
-        std::vector<std::vector<std::pair<int32_t, double>>> rows((size_t)n);
-        for (int i = 0; i < n; ++i) {
-            auto &r = rows[(size_t)i];
-            for (int p = row_ptr[i]; p < row_ptr[i + 1]; ++p) r.emplace_back(col[p], val[p]);
-            std::sort(r.begin(), r.end());
-            for (size_t q = 1; q < r.size() && value_symmetric; ++q)
-                if (r[q].first == r[q - 1].first) value_symmetric = false;
-        }
-        for (int i = 0; i < n && value_symmetric; ++i)
-            for (const auto &e : rows[(size_t)i]) {
-                if (e.second == 0.0) continue;
-                const auto &rj = rows[(size_t)e.first];
-                auto it = std::lower_bound(rj.begin(), rj.end(), std::make_pair((int32_t)i, -1e300));
-                if (it == rj.end() || it->first != i || it->second != e.second) { value_symmetric = false; break; }
+        // rows sorted by column (what scipy delivers for the lattices and dense matrices of the configs): binary search in
+        // place; otherwise sorted copies of the rows
+        bool sorted_rows = true;
+        for (int i = 0; i < n && sorted_rows; ++i)
+            for (int p = row_ptr[i] + 1; p < row_ptr[i + 1]; ++p)
+                if (col[p] <= col[p - 1]) { sorted_rows = false; break; }
+        if (sorted_rows) {
+            for (int i = 0; i < n && value_symmetric; ++i)
+                for (int p = row_ptr[i]; p < row_ptr[i + 1]; ++p) {
+                    if (val[p] == 0.0) continue;
+                    const int j = col[p];
+                    const int32_t *b = col + row_ptr[j], *e = col + row_ptr[j + 1];
+                    const int32_t *it = std::lower_bound(b, e, (int32_t)i);
+                    if (it == e || *it != i || val[it - col] != val[p]) { value_symmetric = false; break; }
+                }
+        } else {
+            std::vector<std::vector<std::pair<int32_t, double>>> rows((size_t)n);
+            for (int i = 0; i < n; ++i) {
+                auto &r = rows[(size_t)i];
+                for (int p = row_ptr[i]; p < row_ptr[i + 1]; ++p) r.emplace_back(col[p], val[p]);
+                std::sort(r.begin(), r.end());
+                for (size_t q = 1; q < r.size() && value_symmetric; ++q)
+                    if (r[q].first == r[q - 1].first) value_symmetric = false;
             }
+            for (int i = 0; i < n && value_symmetric; ++i)
+                for (const auto &e : rows[(size_t)i]) {
+                    if (e.second == 0.0) continue;
+                    const auto &rj = rows[(size_t)e.first];
+                    auto it = std::lower_bound(rj.begin(), rj.end(), std::make_pair((int32_t)i, -1e300));
+                    if (it == rj.end() || it->first != i || it->second != e.second) { value_symmetric = false; break; }
+                }
+        }
     }
     NLMC_CUDA(cudaSetDevice(device));
     auto *I = new nlmc_instance();
@@ -138,6 +155,27 @@ int nlmc_instance_create(int n, const int32_t *row_ptr, const int32_t *col, cons
         }
     }
     *out = I;
+    return NLMC_OK;
+}
+
+/* Host-side format helper of the boundary: widen int8 spins to the float64 arrays the reference's API returns
+ * (M is float64 +-1, NMC/nmc.py:52,89), on `threads` host threads (0 = hardware concurrency, at most 32). */
+int nlmc_host_widen_i8_f64(const int8_t *in, double *out, uint64_t count, int threads) {
+    NLMC_REQUIRE(count == 0 || (in && out), "nlmc_host_widen_i8_f64: NULL argument");
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, 32));
+    if (count < (1u << 20)) nt = 1;
+    auto work = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) out[i] = (double)in[i];
+    };
+    if (nt == 1) { work(0, count); return NLMC_OK; }
+    std::vector<std::thread> pool;
+    const uint64_t per = (count + (uint64_t)nt - 1) / (uint64_t)nt;
+    for (int t = 0; t < nt; ++t) {
+        const uint64_t lo = std::min(count, per * (uint64_t)t), hi = std::min(count, lo + per);
+        if (lo < hi) pool.emplace_back(work, lo, hi);
+    }
+    for (auto &th : pool) th.join();
     return NLMC_OK;
 }
 

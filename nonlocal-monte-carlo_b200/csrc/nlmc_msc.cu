@@ -60,7 +60,7 @@ struct nlmc_msc {
     int8_t *recM = nullptr;          // grow-only record buffers of nlmc_msc_sweep_record
     double *recE = nullptr;
     size_t recM_cap = 0, recE_cap = 0;
-    struct RecGraph { int ladder; bool has_M, has_E; cudaGraphExec_t exec; };
+    struct RecGraph { int ladder; bool has_M, has_E; int n_sweeps_T; cudaGraphExec_t exec; };
     std::vector<RecGraph> rec_graphs;  // one recorded sweep (sweep + unpack + energies + slot bump), replayed per sweep
     int k_steps = 6;  // unconditional bit steps of the Bernoulli comparison (tuning knob NLMC_MSC_STEPS)
     struct RoundGraph { int n_sweeps, pairs; bool with_energy_swap; cudaGraphExec_t exec; };
@@ -534,11 +534,15 @@ __global__ void msc_unpack_ladder_kernel(MscDev a, int g, int lane, int8_t *out)
 }
 
 // the same into slot counters[2] of a record buffer (captured once, replayed per recorded sweep)
+// n_sweeps_T == 0: slot-major record [sweep][beta][site]; n_sweeps_T > 0: [beta][site][sweep] -- the layout of the
+// reference's M ((R*N) x sweeps, NPT/npt.py:640-644), so the host only widens int8 to float64
 __global__ void msc_unpack_ladder_rec_kernel(MscDev a, int g, int lane, int8_t *base, size_t stride,
-                                             const uint32_t *__restrict__ counters) {
+                                             const uint32_t *__restrict__ counters, int n_sweeps_T) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    int8_t *out = base + (size_t)counters[2] * stride;
-    if (i < a.n) out[(size_t)b * a.n + i] = ((a.S[(size_t)i * a.W + b * a.G + g] >> lane) & 1u) ? 1 : -1;
+    if (i >= a.n) return;
+    const int8_t v = ((a.S[(size_t)i * a.W + b * a.G + g] >> lane) & 1u) ? 1 : -1;
+    if (n_sweeps_T) base[((size_t)b * a.n + i) * n_sweeps_T + counters[2]] = v;
+    else base[(size_t)counters[2] * stride + (size_t)b * a.n + i] = v;
 }
 
 __global__ void msc_record_energy_kernel(const double *__restrict__ E, double *base, size_t stride,
@@ -743,13 +747,14 @@ static void drop_graphs(nlmc_msc *M) {
 }
 
 // one recorded sweep: sweep, the ladder's states and / or all energies into slot counters[2] of the record buffers
-static int launch_recorded_sweep(nlmc_msc *M, int ladder, bool has_M, bool has_E, size_t m_stride, size_t e_stride) {
+static int launch_recorded_sweep(nlmc_msc *M, int ladder, bool has_M, bool has_E, size_t m_stride, size_t e_stride,
+                                 int n_sweeps_T) {
     const MscDev d = dev_view(M);
     int rc = launch_sweeps(M, 1);
     if (rc) return rc;
     if (has_M)
         msc_unpack_ladder_rec_kernel<<<dim3((unsigned)((M->n + 255) / 256), (unsigned)M->n_beta), 256, 0, M->stream>>>(
-            d, ladder / 32, ladder % 32, M->recM, m_stride, M->d_counters);
+            d, ladder / 32, ladder % 32, M->recM, m_stride, M->d_counters, n_sweeps_T);
     if (has_E) {
         if ((rc = launch_energy(M))) return rc;
         msc_record_energy_kernel<<<(unsigned)((e_stride + 255) / 256), 256, 0, M->stream>>>(M->E, M->recE, e_stride,
@@ -1149,7 +1154,14 @@ int nlmc_msc_round(nlmc_msc *M, int n_sweeps, int num_swapping_pairs, double *ou
  * every sweep ON THE DEVICE and copied back once: the reference's M[:, jj] = m (NMC/nmc.py:89) and per-sweep energy
  * loops (NPT/npt.py:40-43, NPT/apt_preprocessor.py:107-110) without a host round trip per sweep. */
 int nlmc_msc_sweep_record(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, double *out_E) {
+    return nlmc_msc_sweep_record_layout(M, n_sweeps, ladder, out_M, out_E, 0);
+}
+
+/* m_layout 0: out_M [n_sweeps][n_beta][n]; 1: out_M [n_beta][n][n_sweeps] (rows of the reference's M). */
+int nlmc_msc_sweep_record_layout(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, double *out_E, int m_layout) {
     using namespace nlmc;
+    NLMC_REQUIRE(m_layout == 0 || m_layout == 1, "nlmc_msc_sweep_record_layout: m_layout must be 0 or 1");
+    const int n_sweeps_T = m_layout == 1 ? n_sweeps : 0;
     NLMC_REQUIRE(M && n_sweeps >= 0, "nlmc_msc_sweep_record: bad arguments");
     NLMC_REQUIRE(!out_M || (ladder >= 0 && ladder < M->n_ladders), "nlmc_msc_sweep_record: ladder out of range");
     if (n_sweeps == 0) return NLMC_OK;
@@ -1180,11 +1192,11 @@ int nlmc_msc_sweep_record(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, 
     if (M->use_graphs && n_sweeps >= 4) {
         cudaGraphExec_t exec = nullptr;
         for (auto &g : M->rec_graphs)
-            if (g.ladder == (has_M ? ladder : -1) && g.has_M == has_M && g.has_E == has_E) exec = g.exec;
+            if (g.ladder == (has_M ? ladder : -1) && g.has_M == has_M && g.has_E == has_E && g.n_sweeps_T == n_sweeps_T) exec = g.exec;
         if (!exec) {
             cudaGraph_t graph = nullptr;
             NLMC_CUDA(cudaStreamBeginCapture(M->stream, cudaStreamCaptureModeThreadLocal));
-            rc = launch_recorded_sweep(M, ladder, has_M, has_E, m_stride, e_stride);
+            rc = launch_recorded_sweep(M, ladder, has_M, has_E, m_stride, e_stride, n_sweeps_T);
             const cudaError_t e = cudaStreamEndCapture(M->stream, &graph);
             if (rc || e != cudaSuccess) {
                 if (graph) cudaGraphDestroy(graph);
@@ -1201,11 +1213,11 @@ int nlmc_msc_sweep_record(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, 
                 cudaGraphExecDestroy(M->rec_graphs.front().exec);
                 M->rec_graphs.erase(M->rec_graphs.begin());
             }
-            M->rec_graphs.push_back({has_M ? ladder : -1, has_M, has_E, exec});
+            M->rec_graphs.push_back({has_M ? ladder : -1, has_M, has_E, n_sweeps_T, exec});
         }
         for (int s = 0; s < n_sweeps; ++s) NLMC_CUDA(cudaGraphLaunch(exec, M->stream));
     } else {
-        for (int s = 0; s < n_sweeps && !rc; ++s) rc = launch_recorded_sweep(M, ladder, has_M, has_E, m_stride, e_stride);
+        for (int s = 0; s < n_sweeps && !rc; ++s) rc = launch_recorded_sweep(M, ladder, has_M, has_E, m_stride, e_stride, n_sweeps_T);
         if (rc) return rc;
     }
     if (has_M) NLMC_CUDA(cudaMemcpyAsync(out_M, M->recM, need_M, cudaMemcpyDeviceToHost, M->stream));

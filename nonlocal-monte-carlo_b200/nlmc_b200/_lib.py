@@ -73,7 +73,9 @@ _SIGNATURES = {
     "nlmc_msc_sweep": [_vp, _int],
     "nlmc_msc_energies": [_vp, _vp],
     "nlmc_msc_sweep_record": [_vp, _int, _int, _vp, _vp],
+    "nlmc_msc_sweep_record_layout": [_vp, _int, _int, _vp, _vp, _int],
     "nlmc_msc_round": [_vp, _int, _int, _vp],
+    "nlmc_host_widen_i8_f64": [_vp, _vp, _u64, _int],
     "nlmc_msc_round_host": [_vp, _vp, _int, _int, _vp, _vp],
     "nlmc_msc_round_host_async": [_vp, _vp, _int, _int, _vp, _vp],
     "nlmc_msc_swap_count": [_vp, C.POINTER(_int), _int],
@@ -170,6 +172,16 @@ def np_arctanh(x, device: int = 0) -> np.ndarray:
 
 def _ptr(a):
     return None if a is None else a.ctypes.data
+
+
+def widen_to_f64(a: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+    """int8 spins -> float64 (the dtype of every array the reference's API returns), multi-threaded in the library."""
+    a = np.ascontiguousarray(a, dtype=np.int8)
+    if out is None:
+        out = np.empty(a.shape, dtype=np.float64)
+    assert out.flags.c_contiguous and out.size == a.size and out.dtype == np.float64
+    check(lib().nlmc_host_widen_i8_f64(a.ctypes.data, out.ctypes.data, a.size, 0), "nlmc_host_widen_i8_f64")
+    return out
 
 
 class Instance:
@@ -436,13 +448,15 @@ class Msc:
         check(lib().nlmc_msc_energies(self._h, _ptr(out)), "nlmc_msc_energies")
         return out
 
-    def sweep_record(self, n_sweeps: int, ladder: int | None = 0, energies: bool = True):
+    def sweep_record(self, n_sweeps: int, ladder: int | None = 0, energies: bool = True, rows_of_M: bool = False):
         """n_sweeps sweeps recorded on the device: (M int8 [n_sweeps][n_beta][n] of `ladder` or None,
-        E float64 [n_sweeps][n_beta][n_ladders] or None)."""
-        Mrec = np.empty((n_sweeps, self.n_beta, self.n), dtype=np.int8) if ladder is not None else None
+        E float64 [n_sweeps][n_beta][n_ladders] or None).  rows_of_M=True: M comes as [n_beta][n][n_sweeps], the
+        layout of the reference's M, so that the host only has to widen it."""
+        shape = (self.n_beta, self.n, n_sweeps) if rows_of_M else (n_sweeps, self.n_beta, self.n)
+        Mrec = np.empty(shape, dtype=np.int8) if ladder is not None else None
         Erec = np.empty((n_sweeps, self.n_beta, self.n_ladders), dtype=np.float64) if energies else None
-        check(lib().nlmc_msc_sweep_record(self._h, int(n_sweeps), int(ladder or 0), _ptr(Mrec), _ptr(Erec)),
-              "nlmc_msc_sweep_record")
+        check(lib().nlmc_msc_sweep_record_layout(self._h, int(n_sweeps), int(ladder or 0), _ptr(Mrec), _ptr(Erec),
+                                                 1 if rows_of_M else 0), "nlmc_msc_sweep_record_layout")
         return Mrec, Erec
 
     def round(self, n_sweeps: int, num_swapping_pairs: int, fetch_energies: bool = False):

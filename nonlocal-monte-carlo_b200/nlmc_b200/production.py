@@ -56,8 +56,24 @@ def npt_run_production(obj, beta_list, nmc_kw):
     return _npt_run_dense(obj, prob, beta_list, nmc_kw)
 
 
+def _process_group():
+    """(dist, world, rank) of an initialised torch.distributed default group with more than one rank, else None."""
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return None
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+        return None
+    return dist, dist.get_world_size(), dist.get_rank()
+
+
 def _npt_run_msc(obj, prob, beta_list):
+    """Bit-packed NPT.  In a multi-rank torch.distributed job (one process per GPU) the temperature range of the
+    ladders is sharded over the ranks (distributed.ShardedBetaLadder: only energies cross the GPUs, exchanges permute
+    beta labels) and every rank returns the full (M, Energy); otherwise one handle does everything on one GPU."""
     R = obj.num_replicas
+    if _process_group() is not None and R >= _process_group()[1] and getattr(obj, "distributed", True):
+        return _npt_run_msc_sharded(obj, prob, beta_list)
     spm, spr = obj.num_sweeps_MCMC_per_swap, obj.num_sweeps_read_per_swap
     num_runs = int(getattr(obj, "num_runs", 1))
     n = prob.n
@@ -66,20 +82,23 @@ def _npt_run_msc(obj, prob, beta_list):
     # all rounds but the last run fused on the device; nothing comes back to the host
     for ii in range(obj.num_swap_attempts - 1):
         msc.round(spm, obj.num_swapping_pairs)
-    before = msc.swap_count(reset=True) if obj.num_swap_attempts > 1 else 0
-    count[:max(obj.num_swap_attempts - 1, 0)] = before / max(obj.num_swap_attempts - 1, 1)
-    # last round: record the state after every sweep (the reference returns the last round's M)
+    # last round: record the state after every sweep (the reference returns the last round's M); the device writes the
+    # record in the layout of M's rows, the host only widens int8 to float64
     M = np.zeros((R * n, spm))
     E_cols = np.zeros((R, spm))
     E_all = None
     if spm > 0:
-        Mrec, Erec = msc.sweep_record(spm, ladder=0, energies=True)  # recorded on the device, one copy back
-        M[:] = Mrec.transpose(1, 2, 0).reshape(R * n, spm)
+        Mrec, Erec = msc.sweep_record(spm, ladder=0, energies=True, rows_of_M=True)  # [R][n][spm], one copy back
+        M = _lib.widen_to_f64(Mrec).reshape(R * n, spm)
         E_cols[:] = Erec[:, :, 0].T
         E_all = Erec[-1]
     if obj.num_swap_attempts > 0 and spm > 0:
         msc.round(0, obj.num_swapping_pairs)  # the reference still attempts the exchange after the last round
-        count[-1] = msc.swap_count(reset=True)
+    # accepted exchanges of every round, counted per round on the device (count[ii], NPT/npt.py:664-680); with
+    # num_runs ladders side by side the figure is the total over the ladders
+    k = min(obj.num_swap_attempts, 4096)
+    if k:
+        count[-k:] = msc.swap_counts(k)
     obj.energies_all_runs = None if E_all is None else E_all[:, :num_runs].copy()
     Energy = np.zeros(R)
     obj._EE1_list = []
@@ -88,6 +107,75 @@ def _npt_run_msc(obj, prob, beta_list):
         Energy[r] = np.min(EE1) if len(EE1) else 0.0
         obj._EE1_list.append(EE1)
     msc.close()
+    return M, Energy, count
+
+
+def _npt_run_msc_sharded(obj, prob, beta_list):
+    """NPT.run on N GPUs: slots [first, first + count) of every ladder live on this rank.  Per round the ranks
+    all-gather one float64 per replica and take identical label decisions; the last round's recorded states (int8,
+    run 0) and energies are all-gathered once and put into beta order through the labels."""
+    import torch
+    from .distributed import ShardedBetaLadder, beta_shard
+    dist, world, rank = _process_group()
+    R = obj.num_replicas
+    spm, spr = obj.num_sweeps_MCMC_per_swap, obj.num_sweeps_read_per_swap
+    num_runs = int(getattr(obj, "num_runs", 1))
+    n = prob.n
+    nccl = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", prob.inst.device) if nccl else torch.device("cpu")
+    seed_t = torch.tensor([_seed_from_numpy() & (2**62 - 1)], dtype=torch.int64, device=dev)
+    dist.broadcast(seed_t, 0)  # one seed for the whole job
+    try:
+        ens = ShardedBetaLadder(prob, beta_list[:R], num_runs, int(seed_t.item()), device=prob.inst.device if nccl else None)
+    except _lib.NlmcError as e:
+        raise NotImplementedError(f"mode='production' on several GPUs needs a +-J lattice instance ({e})") from e
+    msc = ens.msc
+    count = np.zeros(obj.num_swap_attempts)
+    for ii in range(obj.num_swap_attempts - 1):
+        ens.round(spm, obj.num_swapping_pairs)
+    M = np.zeros((R * n, spm))
+    E_cols = np.zeros((R, spm))
+    E_all = None
+    if spm > 0:
+        ens.synchronize()
+        labels = msc.labels().astype(np.int64)  # fixed during the round's sweeps
+        Mrec, Erec = msc.sweep_record(spm, ladder=0, energies=True, rows_of_M=True)  # [count][n][spm], [spm][count][ladders]
+        cmax = beta_shard(R, world, 0)[1]
+        send_M = torch.zeros((cmax, n, spm), dtype=torch.int8, device=dev)
+        send_E = torch.zeros((spm, cmax, msc.n_ladders), dtype=torch.float64, device=dev)
+        send_M[:ens.count] = torch.from_numpy(Mrec).to(dev)
+        send_E[:, :ens.count] = torch.from_numpy(Erec).to(dev)
+        recv_M = torch.empty((world,) + tuple(send_M.shape), dtype=torch.int8, device=dev)
+        recv_E = torch.empty((world,) + tuple(send_E.shape), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(recv_M.view(-1, spm), send_M.view(-1, spm))
+        dist.all_gather_into_tensor(recv_E.view(-1, msc.n_ladders), send_E.view(-1, msc.n_ladders))
+        recv_M, recv_E = recv_M.cpu().numpy(), recv_E.cpu().numpy()
+        Mi8 = np.empty((R, n, spm), dtype=np.int8)
+        E_slots = np.empty((spm, R, msc.n_ladders))
+        for r in range(world):
+            f, c = beta_shard(R, world, r)
+            E_slots[:, f:f + c] = recv_E[r, :, :c]
+            for s in range(c):
+                Mi8[labels[f + s, 0]] = recv_M[r, s]              # slot f+s of run 0 holds temperature labels[f+s, 0]
+        M = _lib.widen_to_f64(Mi8).reshape(R * n, spm)
+        E_by_beta = np.empty_like(E_slots)
+        np.put_along_axis(E_by_beta, np.broadcast_to(labels[None], E_slots.shape), E_slots, axis=1)
+        E_cols[:] = E_by_beta[:, :, 0].T
+        E_all = E_by_beta[-1]
+    if obj.num_swap_attempts > 0 and spm > 0:
+        ens.round(0, obj.num_swapping_pairs)
+    ens.synchronize()
+    k = min(obj.num_swap_attempts, 4096)
+    if k:
+        count[-k:] = msc.swap_counts(k)
+    obj.energies_all_runs = None if E_all is None else E_all[:, :num_runs].copy()
+    Energy = np.zeros(R)
+    obj._EE1_list = []
+    for r in range(R):
+        EE1 = E_cols[r, :spr].copy()
+        Energy[r] = np.min(EE1) if len(EE1) else 0.0
+        obj._EE1_list.append(EE1)
+    ens.close()
     return M, Energy, count
 
 

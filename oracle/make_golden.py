@@ -349,6 +349,17 @@ def case_dcl_known_answer():
          n_active=int(sol["nq"]))
 
 
+def case_wishart36_known_answer():
+    """Wishart planted instance N = 36, alpha = 0.50, instance 1 (hard enough that a one-core
+    parallel-tempering search needs thousands of sweeps, easy enough that it always gets there), with the planted ground-state
+    energy of its `gs_energies.txt`; convention J = -J_file, E = -(m^T J m / 2) (NMC/examples/wishart_example.py:8-60)."""
+    base = os.path.join(rl.REFERENCE_ROOT, "NMC", "examples", "wishart_small", "wishart_planting_N_36_alpha_0.50")
+    name = "wishart_planting_N_36_alpha_0.50_inst_1.txt"
+    gs = dict(line.split() for line in open(os.path.join(base, "gs_energies.txt")) if line.strip())
+    save("known_answer_wishart36", instance_text=np.array(open(os.path.join(base, name)).read()),
+         gs_energy=float(gs[name]))
+
+
 def case_contrived_generator():
     """contrived_instance_generator.py (Wishart backbone + trees): adjacency, weights, cross connections, edge removal,
     fields and the instance text, produced by the reference's own functions for one seed."""
@@ -395,5 +406,6 @@ if __name__ == "__main__":
     import warnings
     warnings.simplefilter("ignore")
     for fn in (case_mcmc, case_lbp, case_nmc_run, case_npt, case_npt_sk, case_icm, case_npt_sparse, case_known_answers,
-               case_chimera_known_answer, case_public_methods, case_contrived_generator, case_dcl_known_answer):
+               case_chimera_known_answer, case_public_methods, case_contrived_generator, case_dcl_known_answer,
+               case_wishart36_known_answer):
         fn()

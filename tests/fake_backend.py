@@ -215,6 +215,7 @@ class FakeMsc:
         self.rs = np.random.RandomState(seed % (2 ** 31))
         self.S = self.rs.choice([-1, 1], size=(self.n_beta, self.live, self.n)).astype(np.int8)
         self.accepted = 0
+        self.per_round = []
 
     def set_betas(self, betas):
         self.betas = np.asarray(betas, dtype=np.float64).reshape(-1).copy()
@@ -247,6 +248,7 @@ class FakeMsc:
     def round(self, n_sweeps, num_pairs, fetch_energies=False):
         self.sweep(n_sweeps)
         E = self.energies()
+        before = self.accepted
         for lad in range(self.live):
             avail = list(range(self.n_beta - 1))
             for _ in range(num_pairs):
@@ -258,7 +260,15 @@ class FakeMsc:
                     self.S[[i, i + 1], lad] = self.S[[i + 1, i], lad]
                     E[[i, i + 1], lad] = E[[i + 1, i], lad]
                     self.accepted += 1
+        self.per_round.append(self.accepted - before)
         return E if fetch_energies else None
+
+    def swap_counts(self, n_rounds):
+        out = np.zeros(int(n_rounds), dtype=np.int32)
+        tail = self.per_round[-int(n_rounds):] if n_rounds else []
+        if tail:
+            out[-len(tail):] = tail
+        return out
 
     def swap_count(self, reset=False):
         v = self.accepted
@@ -266,7 +276,7 @@ class FakeMsc:
             self.accepted = 0
         return v
 
-    def sweep_record(self, n_sweeps, ladder=0, energies=True):
+    def sweep_record(self, n_sweeps, ladder=0, energies=True, rows_of_M=False):
         Mrec = np.empty((n_sweeps, self.n_beta, self.n), dtype=np.int8) if ladder is not None else None
         Erec = np.empty((n_sweeps, self.n_beta, self.n_ladders)) if energies else None
         for j in range(int(n_sweeps)):
@@ -275,6 +285,8 @@ class FakeMsc:
                 Mrec[j] = self.S[:, ladder]
             if Erec is not None:
                 Erec[j] = self.energies()
+        if rows_of_M and Mrec is not None:
+            Mrec = np.ascontiguousarray(Mrec.transpose(1, 2, 0))
         return Mrec, Erec
 
     def close(self):

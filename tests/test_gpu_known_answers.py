@@ -19,7 +19,7 @@ def ttt():
     return mod
 
 
-@pytest.mark.parametrize("name,engine", [("chimera128", "Dense"), ("dcl_c8", "Col")])
+@pytest.mark.parametrize("name,engine", [("chimera128", "Dense"), ("dcl_c8", "Col"), ("wishart36", "Col")])
 def test_production_engines_reach_planted_ground_state(ttt, name, engine, monkeypatch):
     if engine == "Dense":
         monkeypatch.setenv("NLMC_FORCE_DENSE", "1")  # the 128-spin Chimera instance would otherwise take K2a as well

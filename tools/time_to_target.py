@@ -3,6 +3,7 @@
 Instances: planted problems whose ground-state energy ships with the reference (golden copies under tests/golden/):
   chimera128  Chimera droplet instance 001 (128 spins, real J, fields)      -> dense tensor-core engine (K3)
   dcl_c8      deceptive-cluster-loop instance C8/00 (463 active spins)      -> graph-coloured sparse engine (K2a)
+  wishart36   Wishart planted instance N = 36, alpha = 0.50, instance 1     -> graph-coloured sparse engine (K2a)
 Target: the ground state.  Both arms run the same algorithm -- parallel tempering over the same beta ladder, `spm`
 heat-bath sweeps per round, adjacent swaps with min(1, exp(dB*dE)) -- until the best energy reaches the target:
   GPU  : production engine chosen by the instance, `runs` independent ladders at once, swaps as beta-label exchanges;
@@ -40,6 +41,10 @@ def load(name):
         # the file rounds 1/7 to 0.14286: its couplings' ground state lies 0.00175 below the stated min_energy
         reader, target, betas = instances.read_dcl, float(g["min_energy"]), np.geomspace(0.3, 6.0, 16)
         what = "DCL C8 inst 00"
+    elif name == "wishart36":
+        g = np.load(os.path.join(ROOT, "tests", "golden", "known_answer_wishart36.npz"))
+        reader, target, betas = instances.read_wishart, float(g["gs_energy"]), np.geomspace(0.3, 8.0, 16)
+        what = "Wishart planted N=36 alpha=0.50 inst 1"
     else:
         raise SystemExit(f"unknown instance {name}")
     with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
@@ -103,16 +108,28 @@ def cpu_arm(inst, seed):
     return float("inf"), MAX_ROUNDS * SPM, "oracle"
 
 
+ALL = ["chimera128", "dcl_c8", "wishart36"]
+
+
+def measure(names=None, repeats=5, cpu=True):
+    """-> list of dicts, one per (instance, arm): median time to the shipped ground-state energy over `repeats` seeds."""
+    out = []
+    for name in names or ALL:
+        inst = load(name)
+        arms = [("gpu, 64 ladders x 16 betas", gpu_arm)]
+        if cpu:
+            arms.append(("cpu oracle port, 1 ladder x 16 betas, 1 core", cpu_arm))
+        for arm_name, arm in arms:
+            res = [arm(inst, 100 + i) for i in range(repeats)]
+            ts = sorted(r[0] for r in res)
+            out.append({"what": f"time to ground state, {inst[4]}", "instance": name, "arm": arm_name, "engine": res[0][2],
+                        "target_energy_normalised": inst[2], "median_seconds": ts[len(ts) // 2], "all_seconds": ts,
+                        "sweeps_per_ladder_median": sorted(r[1] for r in res)[len(res) // 2]})
+    return out
+
+
 if __name__ == "__main__":
     args = sys.argv[1:]
     repeats = int(args[0]) if args and args[0].isdigit() else 5
-    names = [a for a in args if not a.isdigit()] or ["chimera128", "dcl_c8"]
-    for name in names:
-        inst = load(name)
-        for arm_name, arm in (("gpu, 64 ladders x 16 betas", gpu_arm), ("cpu oracle port, 1 ladder x 16 betas, 1 core", cpu_arm)):
-            res = [arm(inst, 100 + i) for i in range(repeats)]
-            ts = sorted(r[0] for r in res)
-            print(json.dumps({"what": f"time to ground state, {inst[4]}", "arm": arm_name, "engine": res[0][2],
-                              "target_energy_normalised": inst[2], "median_seconds": ts[len(ts) // 2],
-                              "all_seconds": ts, "sweeps_per_ladder_median": sorted(r[1] for r in res)[len(res) // 2]}),
-                  flush=True)
+    for row in measure([a for a in args if not a.isdigit()] or ALL, repeats):
+        print(json.dumps(row), flush=True)
