@@ -266,6 +266,10 @@ int nlmc_dense_best_reset(nlmc_dense *d);
 int nlmc_dense_best_update(nlmc_dense *d, double *out_E /*[n_replicas] or NULL*/);
 int nlmc_dense_best_get(nlmc_dense *d, int8_t *out_spins /*[n_replicas][n] or NULL*/, double *out_E /*or NULL*/);
 int nlmc_dense_sync(nlmc_dense *d);
+/* the same for the dense engine (see nlmc_col_ladders) */
+int nlmc_dense_ladders(nlmc_dense *dense, int n_beta, const double *betas);
+int nlmc_dense_exchange(nlmc_dense *dense, int num_swapping_pairs);
+int nlmc_dense_labels(nlmc_dense *dense, int32_t *out_labels /*[R] or NULL*/, int n_rounds, int32_t *out_counts /*[n_rounds]*/);
 int nlmc_dense_time_fields(nlmc_dense *d, int repeats, float *out_ms);
 int nlmc_dense_time_sweeps(nlmc_dense *d, int n_sweeps, float *out_ms);
 
@@ -294,6 +298,17 @@ int nlmc_col_sweep(nlmc_col *c, int n_sweeps, const double *beta_sched, int reco
                    double *out_E, int track_best);
 int nlmc_col_energies(nlmc_col *c, double *out_E /*[R]*/);
 int nlmc_col_sync(nlmc_col *c);
+/* Replica exchange of the generic engines as a permutation of beta labels, entirely on the device (replaces the swap
+ * block NPT/npt.py:649-680 and the pair selection NPT/npt.py:514-533 in the label form of SURVEY D4): the rows are grouped
+ * into ladders, row = ladder * n_beta + slot, slot s starting at betas[s].
+ *   *_ladders   declares the grouping, resets the labels to the identity and sets the per-row betas;
+ *   *_exchange  energies of all rows (device), num_swapping_pairs non-overlapping adjacent temperature pairs per ladder,
+ *               accepted with min(1, exp(dB*dE)); labels and per-row betas updated; queued on the handle's stream;
+ *   *_labels    labels[row] = temperature index of the row (NULL = skip) and the accepted exchanges of each of the last
+ *               n_rounds rounds (oldest first). */
+int nlmc_col_ladders(nlmc_col *col, int n_beta, const double *betas);
+int nlmc_col_exchange(nlmc_col *col, int num_swapping_pairs);
+int nlmc_col_labels(nlmc_col *col, int32_t *out_labels /*[R] or NULL*/, int n_rounds, int32_t *out_counts /*[n_rounds]*/);
 
 #ifdef __cplusplus
 }

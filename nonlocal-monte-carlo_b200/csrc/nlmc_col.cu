@@ -23,6 +23,7 @@
 #include <cmath>
 
 #include "nlmc_common.cuh"
+#include "nlmc_exchange.cuh"
 
 struct nlmc_col {
     nlmc_instance *inst = nullptr;
@@ -50,6 +51,7 @@ struct nlmc_col {
     bool state_global = false;   // n too large for shared memory: fields / spins / modes of each replica live in global memory
     uint8_t *state_ws = nullptr; // [R][state_stride] workspace of that variant
     size_t state_stride = 0;
+    nlmc::LadderExchange xch;    // replica exchange by beta labels (nlmc_col_ladders / nlmc_col_exchange)
     cudaStream_t stream = nullptr;
 };
 
@@ -262,6 +264,7 @@ int nlmc_col_destroy(nlmc_col *Cc) {
     void *ptrs[] = {Cc->site_order, Cc->colour_ptr, Cc->col16, Cc->valfx, Cc->val8, Cc->spins, Cc->beta, Cc->modes, Cc->bestE, Cc->bestS,
                     Cc->state_ws};
     for (void *p : ptrs) if (p) cudaFree(p);
+    Cc->xch.release();
     if (Cc->stream) cudaStreamDestroy(Cc->stream);
     delete Cc;
     return NLMC_OK;
@@ -552,6 +555,29 @@ int nlmc_col_energies(nlmc_col *Cc, double *out_E) {
         return NLMC_ERR_CUDA;
     }
     return NLMC_OK;
+}
+
+/* ---- replica exchange by beta labels (nlmc_exchange.cuh) ---- */
+int nlmc_col_ladders(nlmc_col *Cc, int n_beta, const double *betas) {
+    NLMC_REQUIRE(Cc, "nlmc_col_ladders: NULL handle");
+    NLMC_CUDA(cudaSetDevice(Cc->inst->device));
+    return nlmc::exchange_setup<double>(Cc->xch, Cc->R, n_beta, betas, Cc->beta, Cc->stream);
+}
+
+int nlmc_col_exchange(nlmc_col *Cc, int num_swapping_pairs) {
+    using namespace nlmc;
+    NLMC_REQUIRE(Cc && Cc->xch.active(), "nlmc_col_exchange: call nlmc_col_ladders first");
+    nlmc_instance *I = Cc->inst;
+    NLMC_CUDA(cudaSetDevice(I->device));
+    col_energy_kernel<<<(unsigned)Cc->R, 256, 0, Cc->stream>>>(Cc->n, I->row_ptr, I->col, I->val, I->h, Cc->spins, Cc->xch.E);
+    NLMC_CUDA(cudaGetLastError());
+    return exchange_launch<double>(Cc->xch, num_swapping_pairs, Cc->beta, Cc->seed, Cc->replica_offset, Cc->stream);
+}
+
+int nlmc_col_labels(nlmc_col *Cc, int32_t *out_labels, int n_rounds, int32_t *out_counts) {
+    NLMC_REQUIRE(Cc, "nlmc_col_labels: NULL handle");
+    NLMC_CUDA(cudaSetDevice(Cc->inst->device));
+    return nlmc::exchange_fetch(Cc->xch, Cc->R, out_labels, n_rounds, out_counts, Cc->stream);
 }
 
 int nlmc_col_sync(nlmc_col *Cc) {

@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "nlmc_common.cuh"
+#include "nlmc_exchange.cuh"
 
 namespace nlmc {
 
@@ -275,6 +276,7 @@ struct nlmc_dense {
     unsigned long long seed = 0;
     uint32_t *d_sweep = nullptr;       // [1] sweep counter on the device (read by the kernels of the captured graph)
     cudaGraphExec_t sweep_graph = nullptr;  // one whole sweep: 1 memset + n/128 x (split-K GEMM, block update) + counter
+    nlmc::LadderExchange xch;          // replica exchange by beta labels (nlmc_dense_ladders / nlmc_dense_exchange)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -547,6 +549,7 @@ int nlmc_dense_destroy(nlmc_dense *D) {
     cudaSetDevice(D->inst->device);
     void *ptrs[] = {D->S, D->Jp[0], D->Jp[1], D->Jp[2], D->Jf, D->hf, D->Ht, D->beta, D->E, D->d_sweep, D->bestE, D->bestS, D->modes};
     for (void *p : ptrs) if (p) cudaFree(p);
+    D->xch.release();
     if (D->sweep_graph) cudaGraphExecDestroy(D->sweep_graph);
     if (D->ev0) cudaEventDestroy(D->ev0);
     if (D->ev1) cudaEventDestroy(D->ev1);
@@ -755,6 +758,31 @@ int nlmc_dense_energies(nlmc_dense *D, double *out_E) {
     NLMC_CUDA(cudaMemcpyAsync(out_E, D->E, sizeof(double) * (size_t)D->R, cudaMemcpyDeviceToHost, D->stream));
     NLMC_CUDA(cudaStreamSynchronize(D->stream));
     return NLMC_OK;
+}
+
+/* ---- replica exchange by beta labels (nlmc_exchange.cuh) ---- */
+int nlmc_dense_ladders(nlmc_dense *D, int n_beta, const double *betas) {
+    NLMC_REQUIRE(D, "nlmc_dense_ladders: NULL handle");
+    NLMC_CUDA(cudaSetDevice(D->inst->device));
+    return nlmc::exchange_setup<float>(D->xch, D->R, n_beta, betas, D->beta, D->stream);
+}
+
+int nlmc_dense_exchange(nlmc_dense *D, int num_swapping_pairs) {
+    using namespace nlmc;
+    NLMC_REQUIRE(D && D->xch.active(), "nlmc_dense_exchange: call nlmc_dense_ladders first");
+    NLMC_CUDA(cudaSetDevice(D->inst->device));
+    int rc = launch_fields(D, 0, D->n_pad, 1);
+    if (rc) return rc;
+    dense_energy_kernel<<<(D->R_pad + 127) / 128, 128, 0, D->stream>>>(D->n, D->n_pad, D->R_pad, D->Ht, D->hf, D->S, D->E);
+    NLMC_CUDA(cudaGetLastError());
+    NLMC_CUDA(cudaMemcpyAsync(D->xch.E, D->E, sizeof(double) * (size_t)D->R, cudaMemcpyDeviceToDevice, D->stream));
+    return exchange_launch<float>(D->xch, num_swapping_pairs, D->beta, D->seed, 0, D->stream);
+}
+
+int nlmc_dense_labels(nlmc_dense *D, int32_t *out_labels, int n_rounds, int32_t *out_counts) {
+    NLMC_REQUIRE(D, "nlmc_dense_labels: NULL handle");
+    NLMC_CUDA(cudaSetDevice(D->inst->device));
+    return nlmc::exchange_fetch(D->xch, D->R, out_labels, n_rounds, out_counts, D->stream);
 }
 
 int nlmc_dense_set_site_modes(nlmc_dense *D, const uint8_t *modes, double temp_x) {

@@ -100,6 +100,9 @@ _SIGNATURES = {
     "nlmc_col_sweep": [_vp, _int, _vp, _int, _vp, _vp, _int],
     "nlmc_col_energies": [_vp, _f64],
     "nlmc_col_sync": [_vp],
+    "nlmc_col_ladders": [_vp, _int, _f64],
+    "nlmc_col_exchange": [_vp, _int],
+    "nlmc_col_labels": [_vp, _vp, _int, _vp],
     "nlmc_dense_create": [_vp, _int, _f64, _int, C.c_ulonglong, C.POINTER(_vp)],
     "nlmc_dense_destroy": [_vp],
     "nlmc_dense_set_betas": [_vp, _f64],
@@ -113,6 +116,9 @@ _SIGNATURES = {
     "nlmc_dense_best_update": [_vp, _vp],
     "nlmc_dense_best_get": [_vp, _vp, _vp],
     "nlmc_dense_sync": [_vp],
+    "nlmc_dense_ladders": [_vp, _int, _f64],
+    "nlmc_dense_exchange": [_vp, _int],
+    "nlmc_dense_labels": [_vp, _vp, _int, _vp],
     "nlmc_dense_time_fields": [_vp, _int, C.POINTER(C.c_float)],
     "nlmc_dense_time_sweeps": [_vp, _int, C.POINTER(C.c_float)],
 }
@@ -538,7 +544,30 @@ class Msc:
             pass
 
 
-class Dense:
+class _LabelExchange:
+    """Device-side replica exchange of the generic engines (rows grouped into ladders, row = ladder*n_beta + slot)."""
+    _prefix = ""
+
+    def ladders(self, betas):
+        b = np.ascontiguousarray(betas, dtype=np.float64).reshape(-1)
+        check(getattr(lib(), f"nlmc_{self._prefix}_ladders")(self._h, len(b), b), f"nlmc_{self._prefix}_ladders")
+        self.ladder_betas = b
+
+    def exchange(self, num_swapping_pairs: int):
+        check(getattr(lib(), f"nlmc_{self._prefix}_exchange")(self._h, int(num_swapping_pairs)), f"nlmc_{self._prefix}_exchange")
+
+    def labels(self, n_rounds: int = 0):
+        """(labels int32 [R], accepted exchanges of each of the last n_rounds rounds)."""
+        lab = np.empty(self.R, dtype=np.int32)
+        cnt = np.zeros(max(int(n_rounds), 0), dtype=np.int32)
+        check(getattr(lib(), f"nlmc_{self._prefix}_labels")(self._h, lab.ctypes.data, int(n_rounds), _ptr(cnt) if n_rounds else None),
+              f"nlmc_{self._prefix}_labels")
+        return lab, cnt
+
+
+
+class Dense(_LabelExchange):
+    _prefix = "dense"
     """Dense-J production state (K3): R replicas, field contraction H = S.J on tcgen05 tensor cores."""
 
     def __init__(self, inst: Instance, betas, n_split: int = 3, seed: int = 0):
@@ -623,7 +652,8 @@ class Dense:
             pass
 
 
-class Col:
+class Col(_LabelExchange):
+    _prefix = "col"
     """Sparse production state (K2a): R replicas, graph-coloured parallel heat bath, one CTA per replica."""
 
     def __init__(self, inst: Instance, betas, seed: int = 0, replica_offset: int = 0):

@@ -284,9 +284,71 @@ def _nmc_cycles_dense(prob, d, m_star, nmc_kw, variant, record_run0=True, all_cl
     return out
 
 
+def _npt_run_generic_labels(obj, prob, beta_list):
+    """NPT.run without NMC replicas on the generic engines (K2a sparse / K3 dense): sweeps, energies and the replica
+    exchange stay on the device for every round -- the exchange permutes beta labels (nlmc_col_exchange /
+    nlmc_dense_exchange), no spin leaves the GPU until the last round's states are recorded.  `num_runs` independent
+    ladders ride as further rows (row = run * R + slot); the reference's tuple is that of run 0."""
+    R, n = obj.num_replicas, prob.n
+    spm, spr = obj.num_sweeps_MCMC_per_swap, obj.num_sweeps_read_per_swap
+    runs = max(1, int(getattr(obj, "num_runs", 1)))
+    betas = np.asarray(beta_list[:R], dtype=np.float64)
+    d = _generic_engine(prob, np.tile(betas, runs), _seed_from_numpy())
+    d.ladders(betas)
+    d.set_spins(np.sign(2 * np.random.rand(runs * R, n) - 1).astype(np.int8))  # NPT/npt.py:612, once per run
+    count = np.zeros(obj.num_swap_attempts)
+    for ii in range(obj.num_swap_attempts - 1):
+        d.sweep(spm)
+        d.exchange(obj.num_swapping_pairs)
+    M = np.zeros((R * n, spm))
+    E_cols = np.zeros((R, spm))
+    E_all = None
+    if spm > 0:
+        labels, _ = d.labels(0)                     # fixed during the round's sweeps
+        lab = labels.reshape(runs, R)
+        if hasattr(d, "sweep_record"):
+            states, E = d.sweep_record(spm, record_every=1)          # [spm][rows][n], [spm][rows]
+            states0 = states[:, :R]
+        else:
+            states0 = np.empty((spm, R, n), dtype=np.int8)
+            E = np.empty((spm, runs * R))
+            for j in range(spm):
+                d.sweep(1)
+                E[j] = d.energies()
+                states0[j] = d.get_spins()[:R]
+        if not _engine_energies_exact(prob):   # returned energies in fp64 from the returned states (K4)
+            E = E.copy()
+            E[:, :R] = prob.inst.energy_states(np.ascontiguousarray(states0).reshape(-1, n)).reshape(spm, R)
+        M3 = M.reshape(R, n, spm)
+        for s in range(R):                          # slot s of run 0 holds temperature index lab[0, s]
+            M3[lab[0, s]] = states0[:, s, :].T
+            E_cols[lab[0, s]] = E[:, s]
+        E_last = E[-1].reshape(runs, R)
+        E_all = np.empty((R, runs))
+        for r in range(runs):
+            E_all[lab[r], r] = E_last[r]
+    if obj.num_swap_attempts > 0 and spm > 0:
+        d.exchange(obj.num_swapping_pairs)  # the reference still attempts the exchange after the last round
+    k = min(obj.num_swap_attempts, 4096)
+    if k:
+        count[-k:] = d.labels(k)[1]
+    obj.energies_all_runs = E_all
+    Energy = np.zeros(R)
+    obj._EE1_list = []
+    for r in range(R):
+        EE1 = E_cols[r, :spr].copy()
+        Energy[r] = np.min(EE1) if len(EE1) else 0.0
+        obj._EE1_list.append(EE1)
+    d.close()
+    return M, Energy, count
+
+
 def _npt_run_dense(obj, prob, beta_list, nmc_kw):
-    """Dense-engine NPT: plain replicas and doNMC replicas live in two handles (their sweep counts per round
-    differ, NPT/npt.py:577-580); exchanges are done on the host on the 2 x n spins of each accepted pair."""
+    """Generic-engine NPT.  Without NMC replicas everything stays on the device (_npt_run_generic_labels).  With them,
+    plain replicas and doNMC replicas live in two handles (their sweep counts per round differ, NPT/npt.py:577-580) and an
+    exchange between the two kinds has to move the 2 x n spins of the accepted pair, which is done through the host."""
+    if not any(obj.doNMC):
+        return _npt_run_generic_labels(obj, prob, beta_list)
     R, n = obj.num_replicas, prob.n
     spm, spr = obj.num_sweeps_MCMC_per_swap, obj.num_sweeps_read_per_swap
     mc_ids = [r for r in range(R) if not obj.doNMC[r]]

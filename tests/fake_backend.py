@@ -148,6 +148,42 @@ class FakeEngine:
     def set_betas(self, betas):
         self.betas = np.asarray(betas, dtype=np.float64).reshape(-1).copy()
 
+    # replica exchange by beta labels (nlmc_col_ladders / _exchange / _labels): rows = ladders x n_beta
+    def ladders(self, betas):
+        self.lad_betas = np.asarray(betas, dtype=np.float64).reshape(-1).copy()
+        nb = len(self.lad_betas)
+        assert self.R % nb == 0
+        self.lab = np.tile(np.arange(nb, dtype=np.int32), self.R // nb)
+        self.betas = self.lad_betas[self.lab].copy()
+        self.x_counts = []
+
+    def exchange(self, num_pairs):
+        nb = len(self.lad_betas)
+        E = self.energies().reshape(-1, nb)
+        lab = self.lab.reshape(-1, nb)
+        acc = 0
+        for l in range(lab.shape[0]):
+            avail = list(range(nb - 1))
+            for _ in range(num_pairs):
+                if not avail:
+                    break
+                i = avail[self.rs.randint(len(avail))]
+                avail = [j for j in avail if abs(j - i) > 1]
+                sa, sb = int(np.where(lab[l] == i)[0][0]), int(np.where(lab[l] == i + 1)[0][0])
+                x = (self.lad_betas[i + 1] - self.lad_betas[i]) * (E[l, sb] - E[l, sa])
+                if self.rs.rand() < min(1.0, np.exp(x)):
+                    lab[l, sa], lab[l, sb] = i + 1, i
+                    acc += 1
+        self.betas = self.lad_betas[self.lab].copy()
+        self.x_counts.append(acc)
+
+    def labels(self, n_rounds=0):
+        cnt = np.zeros(int(n_rounds), dtype=np.int32)
+        tail = self.x_counts[-int(n_rounds):] if n_rounds else []
+        if tail:
+            cnt[-len(tail):] = tail
+        return self.lab.copy(), cnt
+
     def set_spins(self, spins):
         self.spins = np.asarray(spins, dtype=np.int8).reshape(self.R, self.n).copy()
 
