@@ -174,8 +174,13 @@ __global__ void __launch_bounds__(kColThreadsFew) col_sweep_kernel(ColArgs a) {
                 // backbone rows of J and h are divided by temp_x (nmc.py:379-380) <=> beta/temp_x for this site
                 const float x = (md == 1 ? m2b * inv_tx : m2b) * ((float)ld_fld(i) * inv_scale);
                 const uint4 rnd = rng(rid, (uint32_t)i, sweep, 0u);
-                const float u = ((float)(rnd.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
-                const int s_new = u * (1.0f + __expf(x)) < 1.0f ? 1 : -1;   // u < 1/(1+exp(-2 beta f))
+                // P(+1) = 1/(1+exp(x)), x = -2 beta f.  The LESS likely state has probability q = 1/(1+exp(|x|)) <= 1/2; it is
+                // drawn by comparing a 32-bit uniform with the integer threshold q 2^32 (relative accuracy of q kept down
+                // to 2^-32, both tails alike; a 24-bit float uniform rounded to 1.0 forced the spin down once in 2^24 draws)
+                const float q = __frcp_rn(1.0f + __expf(fabsf(x)));
+                const uint32_t thr = (uint32_t)fminf(q * 4294967296.0f, 4294967040.0f);
+                const bool minority = rnd.x < thr;
+                const int s_new = (minority != (x < 0.0f)) ? 1 : -1;        // majority state: +1 when x < 0 (field up)
                 const int s_old = ld_spin(i);
                 __syncwarp(gmask);  // every lane of the group has read spin[i] and fld[i]
                 if (s_new != s_old) {

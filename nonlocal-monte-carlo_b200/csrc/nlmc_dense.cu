@@ -419,8 +419,13 @@ __global__ void __launch_bounds__(128) dense_block_update_kernel(int n, int n_pa
         const uint32_t ub[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float u = ((float)(ub[i] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            theta[i] = (__logf(u) - __logf(1.0f - u)) * inv2b;
+            // logit of a uniform in (0,1) from all 32 bits, evaluated on the side of the nearer tail so that both tails
+            // are symmetric and reach 2^-33 (a 24-bit uniform rounded to 1.0 forced the spin down once in 2^24 draws)
+            const bool hi = (ub[i] >> 31) != 0u;
+            const uint32_t m = hi ? ~ub[i] : ub[i];
+            const float v = ((float)m + 0.5f) * (1.0f / 4294967296.0f);       // in (0, 1/2]
+            const float t = __logf(v) - __logf(1.0f - v);
+            theta[i] = (hi ? -t : t) * inv2b;
         }
         uint32_t frozen = 0;  // NMC phases: frozen sites keep their spin (the reference pins them with h = +-1e4)
         if (mrow != nullptr) {

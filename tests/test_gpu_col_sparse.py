@@ -68,7 +68,7 @@ def test_exact_boltzmann_real_couplings_with_field(nl):
         w /= w.sum()
         exact = (w * E_all).sum()
         mean, err = Em[b].mean(), Em[b].std(ddof=1) / np.sqrt(per)
-        assert abs(mean - exact) <= 4.5 * err + 1e-9, (beta, mean, exact, err)
+        assert abs(mean - exact) <= 3.0 * err + 1e-9, (beta, mean, exact, err)
 
 
 def test_site_modes_and_annealing_schedule(nl):
@@ -95,7 +95,7 @@ def test_site_modes_and_annealing_schedule(nl):
     _, Er = ref.sweep_record(200, want_states=False)
     E_ref = Er[::4].mean(axis=0)
     err = np.hypot(E_hot.std(ddof=1), E_ref.std(ddof=1)) / np.sqrt(per)
-    assert abs(E_hot.mean() - E_ref.mean()) <= 4.5 * err, (E_hot.mean(), E_ref.mean(), err)
+    assert abs(E_hot.mean() - E_ref.mean()) <= 3.0 * err, (E_hot.mean(), E_ref.mean(), err)
     # annealing schedule: beta_sched overrides the per-replica beta sweep by sweep
     c.set_site_modes(None)
     sched = np.repeat(np.linspace(0.0, 3.0, 150)[:, None], 2 * per, axis=1)
@@ -128,7 +128,7 @@ def test_statistical_equivalence_with_reference_sampler_c1_shape(nl):
             ms.append(np.abs(tail.sum(axis=1)).mean() / n)
         for gpu, ref in ((E_gpu[b], np.array(Es)), (m_gpu[b], np.array(ms))):
             err = np.hypot(gpu.std(ddof=1) / np.sqrt(gpu.size), ref.std(ddof=1) / np.sqrt(ref.size))
-            assert abs(gpu.mean() - ref.mean()) <= 3.5 * err, (beta, gpu.mean(), ref.mean(), err)
+            assert abs(gpu.mean() - ref.mean()) <= 3.0 * err, (beta, gpu.mean(), ref.mean(), err)
 
 
 def test_large_sparse_instance_csr_in_global(nl):
@@ -191,4 +191,37 @@ def test_global_workspace_variant_equals_shared_memory_variant(nl, monkeypatch):
     S = c.get_spins()
     assert set(np.unique(S)) <= {-1, 1} and np.all(E1 < E0)
     np.testing.assert_array_equal(E1, big.inst.energy_states(S))   # integer couplings: exact
+    c.close()
+
+
+def test_cold_tail_no_spurious_flips_and_small_probabilities(nl):
+    """global_beta = 13.6 (C2's NMC replicas run there).  (a) A ferromagnetic ring in its ground state: every flip has
+    probability 1/(1+exp(2*13.6*2)) ~ 1e-24, so 1.3e8 attempts must not produce a single excitation (a uniform rounded to
+    1.0 once in 2^24 draws used to force spins down).  (b) Independent spins in fields: minority-state probabilities of
+    1e-6 ... 1e-3 are reproduced within 3 sigma of the Poisson counts (32-bit threshold compare, both tails alike)."""
+    import scipy.sparse as sp
+    beta = 13.6
+    n = 64
+    idx = np.arange(n)
+    A = sp.coo_matrix((np.ones(2 * n), (np.r_[idx, (idx + 1) % n], np.r_[(idx + 1) % n, idx])), shape=(n, n)).tocsr()
+    prob = nl.host.Problem(A, np.zeros(n))
+    R, S = 1024, 2000
+    c = nl.lib.Col(prob.inst, np.full(R, beta), seed=11)
+    c.set_spins(np.ones((R, n), dtype=np.int8))
+    _, E = c.sweep_record(S, want_states=False)
+    assert E.shape == (S, R) and np.all(E == -float(n))          # never left the ground state
+    c.close()
+    # (b) independent spins: P(s = -1) = 1/(1+exp(2 beta h)) per attempt, P(s = +1) for negative fields
+    h = np.array([0.25, 0.3, 0.35, 0.4, 0.45, 0.5, -0.25, -0.3, -0.35, -0.4, -0.45, -0.5])
+    m = len(h)
+    prob = nl.host.Problem(sp.csr_matrix((m, m)), h)
+    R, S = 2048, 1500
+    c = nl.lib.Col(prob.inst, np.full(R, beta), seed=12)
+    states, _ = c.sweep_record(S, record_every=1, want_energies=False)
+    minority = (states * np.sign(h)[None, None, :] < 0).sum(axis=(0, 1))
+    q = 1.0 / (1.0 + np.exp(2 * beta * np.abs(h)))
+    expect = R * S * q
+    for k in range(m):
+        assert abs(minority[k] - expect[k]) <= 3.0 * np.sqrt(expect[k]) + 1.0, (h[k], minority[k], expect[k])
+    assert minority[:6].sum() > 0 and minority[6:].sum() > 0                # both tails are populated
     c.close()

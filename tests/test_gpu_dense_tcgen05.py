@@ -77,7 +77,7 @@ def test_sweep_exact_boltzmann_small(nl):
         w /= w.sum()
         exact = (w * E_all).sum()
         mean, err = E[b].mean(), E[b].std(ddof=1) / np.sqrt(per)
-        assert abs(mean - exact) <= 4.5 * err + 1e-4, (beta, mean, exact, err)
+        assert abs(mean - exact) <= 3.0 * err + 1e-4, (beta, mean, exact, err)
 
 
 def test_sweep_multi_block_vs_reference_sampler(nl):
@@ -107,7 +107,7 @@ def test_sweep_multi_block_vs_reference_sampler(nl):
             ref.append(O.energy(csr, h, M[150::10]).mean())
         ref = np.array(ref)
         err = np.hypot(E_gpu[b].std(ddof=1) / np.sqrt(per), ref.std(ddof=1) / np.sqrt(ref.size))
-        assert abs(E_gpu[b].mean() - ref.mean()) <= 3.5 * err, (beta, E_gpu[b].mean(), ref.mean(), err)
+        assert abs(E_gpu[b].mean() - ref.mean()) <= 3.0 * err, (beta, E_gpu[b].mean(), ref.mean(), err)
 
 
 def test_site_modes_frozen_and_hot(nl):
@@ -142,7 +142,7 @@ def test_site_modes_frozen_and_hot(nl):
         acc.append(ref.energies())
     E_ref = np.array(acc).mean(axis=0)
     err = np.hypot(E_hot.std(ddof=1), E_ref.std(ddof=1)) / np.sqrt(per)
-    assert abs(E_hot.mean() - E_ref.mean()) <= 4.5 * err, (E_hot.mean(), E_ref.mean(), err)
+    assert abs(E_hot.mean() - E_ref.mean()) <= 3.0 * err, (E_hot.mean(), E_ref.mean(), err)
     # modes off again: frozen sites move
     d.set_site_modes(None)
     d.sweep(20)
@@ -232,3 +232,18 @@ def test_full_size_c3_properties(nl):
     np.testing.assert_allclose(E1[rows], prob.inst.energy_states(Sa[rows]), rtol=1e-4)
     assert np.all(E1.reshape(32, 64).mean(axis=0) < E0.reshape(32, 64).mean(axis=0))
     a.close(); b.close()
+
+
+def test_cold_tail_no_spurious_flips():
+    """A dense ferromagnet in its ground state at beta = 13.6: flip probabilities are ~exp(-2*13.6*f) with f >= 0.9, so
+    2e8 attempts must leave every spin up (a 24-bit uniform rounded to 1.0 used to force a spin down once in 2^24)."""
+    from nlmc_b200 import _lib, host
+    n, R = 128, 1024
+    J = (np.ones((n, n)) - np.eye(n)) / (n - 1)
+    prob = host.Problem(J, np.zeros(n))
+    d = _lib.Dense(prob.inst, np.full(R, 13.6), n_split=3, seed=3)
+    d.set_spins(np.ones((R, n), dtype=np.int8))
+    for _ in range(15):
+        d.sweep(100)
+        assert np.all(d.get_spins() == 1)
+    d.close()

@@ -5,8 +5,10 @@ Instances: planted problems whose ground-state energy ships with the reference (
   dcl_c8      deceptive-cluster-loop instance C8/00 (463 active spins)      -> graph-coloured sparse engine (K2a)
   wishart36   Wishart planted instance N = 36, alpha = 0.50, instance 1     -> graph-coloured sparse engine (K2a)
 Target: the ground state.  Both arms run the same algorithm -- parallel tempering over the same beta ladder, `spm`
-heat-bath sweeps per round, adjacent swaps with min(1, exp(dB*dE)) -- until the best energy reaches the target:
-  GPU  : production engine chosen by the instance, `runs` independent ladders at once, swaps as beta-label exchanges;
+heat-bath sweeps per round, round(0.3 R) non-overlapping adjacent pairs per round accepted with min(1, exp(dB*dE))
+(NPT/npt.py:514-533,652-680) -- until the best energy reaches the target:
+  GPU  : production engine chosen by the instance, `runs` independent ladders at once, exchanges as beta-label
+         permutations on the device (nlmc_col_exchange / nlmc_dense_exchange);
   CPU  : the oracle C port of MCMC (reference algorithm) driven from Python, one ladder on one core.
 Prints one JSON line per (instance, arm) with the median over `repeats` seeds.
 
@@ -28,6 +30,11 @@ from nlmc_b200.production import _generic_engine  # noqa: E402
 from oracle import oracle as O  # noqa: E402  (CPU arm)
 
 SPM, MAX_ROUNDS, TOL = 5, 4000, 1e-6
+
+
+def PAIRS(nb):
+    """swapping pairs per round: round(0.3 * num_replicas), the README's choice (README.md:152)"""
+    return max(1, int(round(0.3 * nb)))
 
 
 def load(name):
@@ -59,8 +66,8 @@ def gpu_arm(inst, seed, runs=64):
     Jn, hn, target, betas, _ = inst
     prob = host.Problem(Jn, hn)
     n, nb = prob.n, len(betas)
-    lab = np.tile(np.arange(nb), runs)          # beta label of every row (row = run*nb + slot)
-    d = _generic_engine(prob, betas[lab], seed)
+    d = _generic_engine(prob, np.tile(betas, runs), seed)     # row = run * nb + slot
+    d.ladders(betas)
     rs = np.random.RandomState(seed)
     d.sweep(1); d.energies()                      # warm-up (graph capture)
     d.set_spins(rs.choice([-1, 1], size=(runs * nb, n)).astype(np.int8))
@@ -73,16 +80,7 @@ def gpu_arm(inst, seed, runs=64):
                 S = d.get_spins()
                 if prob.inst.energy_states(S[[int(np.argmin(E))]])[0] <= target + TOL:
                     return time.perf_counter() - t0, rnd * SPM, type(d).__name__
-            # adjacent exchanges, even/odd alternation, as label swaps
-            order = np.argsort(lab.reshape(runs, nb), axis=1)          # order[run][b] = slot holding beta b
-            Eb = np.take_along_axis(E.reshape(runs, nb), order, axis=1)
-            for b in range(rnd % 2, nb - 1, 2):
-                acc = rs.rand(runs) < np.minimum(1.0, np.exp((betas[b + 1] - betas[b]) * (Eb[:, b + 1] - Eb[:, b])))
-                lo, hi = order[:, b].copy(), order[:, b + 1].copy()
-                rows = np.arange(runs)[acc]
-                lab2 = lab.reshape(runs, nb)
-                lab2[rows, lo[acc]], lab2[rows, hi[acc]] = b + 1, b
-            d.set_betas(betas[lab])
+            d.exchange(PAIRS(nb))                 # beta-label exchange on the device (K6), the reference's pair selection
         return float("inf"), MAX_ROUNDS * SPM, type(d).__name__
     finally:
         d.close()
@@ -101,7 +99,12 @@ def cpu_arm(inst, seed):
         E = O.energy(csr, hn, S)
         if E.min() <= target + TOL:
             return time.perf_counter() - t0, rnd * SPM, "oracle"
-        for b in range(rnd % 2, nb - 1, 2):
+        avail = list(range(nb - 1))               # the reference's pair selection (NPT/npt.py:514-533)
+        for _ in range(PAIRS(nb)):
+            if not avail:
+                break
+            b = avail[rs.randint(len(avail))]
+            avail = [j for j in avail if abs(j - b) > 1]
             if rs.rand() < min(1.0, np.exp((betas[b + 1] - betas[b]) * (E[b + 1] - E[b]))):
                 S[[b, b + 1]] = S[[b + 1, b]]
                 E[[b, b + 1]] = E[[b + 1, b]]
