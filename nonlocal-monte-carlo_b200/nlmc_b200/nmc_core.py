@@ -63,9 +63,21 @@ def find_clusters(prob: host.Problem, magnetizations, threshold_initial, thresho
     return [np.array(c, dtype=int) for c in clusters]
 
 
+def backbone_indices(prob: host.Problem, marginal, threshold_initial, threshold_cutoff, threshold_step=0.01):
+    """The backbone as a sorted index set: what NMC_subroutine uses of find_clusters' result (J_c[all_clusters, :],
+    NMC/nmc.py:373-381).  With every shipped parameter set the growth loop never runs (threshold_initial - step <=
+    threshold_cutoff) and the set is simply {i : |marginal_i| >= threshold_initial}."""
+    if threshold_initial - threshold_step <= threshold_cutoff:
+        return np.flatnonzero(np.abs(np.asarray(marginal, dtype=np.float64)) >= threshold_initial).astype(int)
+    cl = find_clusters(prob, marginal, threshold_initial, threshold_cutoff, threshold_step)
+    return np.sort(np.concatenate(cl)).astype(int) if cl else np.array([], dtype=int)
+
+
 def lbp_convexified(prob: host.Problem, lbp: "_lib.Lbp", m_star, lambda_start, lambda_end, lambda_reduction_factor,
-                    tolerance, max_iterations, threshold_initial, threshold_cutoff, global_beta, trace=None):
-    """lambda-annealed LBP (NMC/nmc.py:93-166) around kernel K5.  Returns the list of clusters.
+                    tolerance, max_iterations, threshold_initial, threshold_cutoff, global_beta, trace=None,
+                    as_index_set=False):
+    """lambda-annealed LBP (NMC/nmc.py:93-166) around kernel K5.  Returns the list of clusters (or, with
+    as_index_set, the backbone as a sorted index array -- see backbone_indices).
     ``trace`` (optional list) receives (lambda, iteration, marginal) per step, for tests."""
     lbp.reset(m_star)
     lambda_val = lambda_start
@@ -89,6 +101,8 @@ def lbp_convexified(prob: host.Problem, lbp: "_lib.Lbp", m_star, lambda_start, l
             break
     if marginal is None:  # lambda_start < lambda_end: the reference fails on an unbound `marginal`
         raise UnboundLocalError("cannot access local variable 'marginal' where it is not associated with a value")
+    if as_index_set:
+        return backbone_indices(prob, marginal, threshold_initial, threshold_cutoff, 0.01)
     return find_clusters(prob, marginal, threshold_initial, threshold_cutoff, 0.01)
 
 

@@ -53,6 +53,8 @@ def npt_run_production(obj, beta_list, nmc_kw):
     prob = obj._problem()
     if _msc_eligible(prob) and not any(obj.doNMC):
         return _npt_run_msc(obj, prob, beta_list)
+    if _msc_eligible(prob) and not all(obj.doNMC) and not os.environ.get("NLMC_NO_HYBRID"):
+        return _npt_run_hybrid(obj, prob, beta_list, nmc_kw)
     return _npt_run_dense(obj, prob, beta_list, nmc_kw)
 
 
@@ -205,10 +207,10 @@ def _backbones(prob, states, global_beta, nmc_kw):
         lbp = prob._lbp_handle = _lib.Lbp(prob.lbp_instance())
     out = []
     for m_star in states:
-        cl = lbp_convexified(prob, lbp, m_star.astype(np.float64), nmc_kw["lambda_start"], nmc_kw["lambda_end"],
-                             nmc_kw["lambda_reduction_factor"], nmc_kw["tolerance"], nmc_kw["max_iterations"],
-                             nmc_kw["threshold_initial"], nmc_kw["threshold_cutoff"], global_beta)
-        out.append(np.concatenate(cl).astype(int) if cl else np.array([], dtype=int))
+        out.append(lbp_convexified(prob, lbp, m_star.astype(np.float64), nmc_kw["lambda_start"], nmc_kw["lambda_end"],
+                                   nmc_kw["lambda_reduction_factor"], nmc_kw["tolerance"], nmc_kw["max_iterations"],
+                                   nmc_kw["threshold_initial"], nmc_kw["threshold_cutoff"], global_beta,
+                                   as_index_set=True))
     return out
 
 
@@ -340,6 +342,80 @@ def _npt_run_generic_labels(obj, prob, beta_list):
         Energy[r] = np.min(EE1) if len(EE1) else 0.0
         obj._EE1_list.append(EE1)
     d.close()
+    return M, Energy, count
+
+
+def _npt_run_hybrid(obj, prob, beta_list, nmc_kw):
+    """NPT.run on a +-J lattice with NMC on some replicas (config C2 as stated): the plain replicas stay on the bit-packed
+    engine (K2, one ladder in the bit lanes), only the doNMC replicas run on the graph-coloured engine (K2a, per-site
+    phase modes) at global_beta.  The two kinds sweep concurrently on their own streams.  One set of pairs is drawn per
+    round as in the reference (NPT/npt.py:649-680, host RNG); an accepted exchange moves the two configurations -- between
+    two slots of the bit-packed handle, or between a slot and an NMC row (2 x n bytes through the host; the kinds differ,
+    so a label cannot stand in for the configuration)."""
+    R, n = obj.num_replicas, prob.n
+    spm, spr = obj.num_sweeps_MCMC_per_swap, obj.num_sweeps_read_per_swap
+    mc_ids = [r for r in range(R) if not obj.doNMC[r]]
+    nmc_ids = [r for r in range(R) if obj.doNMC[r]]
+    slot = {r: k for k, r in enumerate(mc_ids)}      # replica -> slot of the bit-packed handle
+    row = {r: k for k, r in enumerate(nmc_ids)}      # replica -> row of the NMC handle
+    seed = _seed_from_numpy()
+    msc = _require_msc(prob, np.asarray(beta_list, dtype=np.float64)[mc_ids], 1, seed)
+    d_nmc = _generic_engine(prob, np.full(len(nmc_ids), float(nmc_kw["global_beta"])), seed + 1)
+    state = np.sign(2 * np.random.rand(R, n) - 1).astype(np.int8)  # NPT/npt.py:612
+    for r in mc_ids:
+        msc.set_spins(slot[r], 0, state[r])
+    M = np.empty((R * n, spm))
+    M3 = M.reshape(R, n, spm)
+    E_cols = np.zeros((R, spm))
+    E_last = np.zeros(R)
+    count = np.zeros(obj.num_swap_attempts)
+    all_pairs = [(i, i + 1) for i in range(1, R)]
+    for ii in range(obj.num_swap_attempts):
+        last = ii == obj.num_swap_attempts - 1
+        if not last:
+            msc.sweep(spm)                       # queued on the handle's stream; the NMC cycles below run meanwhile
+        res = _nmc_cycles_dense(prob, d_nmc, state[nmc_ids], nmc_kw, "npt", keep_states=last)
+        for g, r in enumerate(nmc_ids):
+            Mo, Eo, _ = res[g]
+            if last:
+                M3[r] = Mo[:, -spm:]
+                E_cols[r] = Eo[-spm:]
+            E_last[r] = Eo[-1]
+            state[r] = Mo[:, -1].astype(np.int8)
+        if last and spm > 0:
+            Mrec, Erec = msc.sweep_record(spm, ladder=0, energies=True, rows_of_M=True)   # [slots][n][spm]
+            for r in mc_ids:
+                _lib.widen_to_f64(Mrec[slot[r]], out=M3[r])
+                E_cols[r] = Erec[:, slot[r], 0]
+            E_mc = Erec[-1][:, 0]
+        else:
+            E_mc = msc.energies()[:, 0]
+        for r in mc_ids:
+            E_last[r] = E_mc[slot[r]]
+        for sel, nxt in host.select_non_overlapping_pairs(all_pairs, obj.num_swapping_pairs):
+            a, b = sel - 1, nxt - 1
+            dE = E_last[b] - E_last[a]
+            dB = beta_list[b] - beta_list[a]
+            if np.random.rand() < min(1, np.exp(dB * dE)):
+                count[ii] += 1
+                if last:
+                    continue                     # nothing reads m_start after the last round
+                ca = msc.get_spins(slot[a], 0) if a in slot else state[a].copy()
+                cb = msc.get_spins(slot[b], 0) if b in slot else state[b].copy()
+                for r, c in ((a, cb), (b, ca)):
+                    if r in slot:
+                        msc.set_spins(slot[r], 0, c)
+                    else:
+                        state[r] = c
+    Energy = np.zeros(R)
+    obj._EE1_list = []
+    for r in range(R):
+        EE1 = E_cols[r, :spr].copy()
+        Energy[r] = np.min(EE1) if len(EE1) else 0.0
+        obj._EE1_list.append(EE1)
+    obj.energies_all_runs = None
+    msc.close()
+    d_nmc.close()
     return M, Energy, count
 
 
@@ -549,7 +625,8 @@ class _IcmEngine:
 def apt_icm_run_production(obj, beta_list):
     """APT_ICM.run (NPT/apt_ICM.py:145-305) in production mode, reference semantics: the Houdayer move edits the
     FIRST column of each sub-replica's block of M while the exchange reads the LAST one and the chains continue
-    from the unedited states, so the edits feed back only when there is one sweep per swap."""
+    from the unedited states, so the edits feed back only when there is one sweep per swap AND the exchange
+    of that pair is accepted (apt_ICM.py:213,282-283)."""
     S = 10  # num_subreplicas, apt_ICM.py:177
     R, spm, spr = obj.num_replicas, obj.num_sweeps_MCMC_per_swap, obj.num_sweeps_read_per_swap
     if spm < 1:
@@ -583,6 +660,7 @@ def apt_icm_run_production(obj, beta_list):
         else:
             eng.sweep(spm)
         E_last = eng.energies() if spm > 1 else None
+        unedited = first.copy() if (need_first and spm == 1 and not last_round) else None
         if need_first:  # Houdayer move on the first column (apt_ICM.py:216-246)
             for r in range(R):
                 shuffled = np.random.permutation(S)
@@ -616,11 +694,18 @@ def apt_icm_run_production(obj, beta_list):
                 if np.random.rand() < min(1, np.exp(dB * dE)):
                     accepted.append((sel - 1, nxt - 1, s))
         count[ii] = len(accepted)
-        if not last_round and (accepted or spm == 1):
-            # with one sweep per swap the (edited) first column IS the last column the chains continue from
-            X = first if spm == 1 else eng.get_states()
-            for a, b, s in accepted:
-                X[[a, b], s] = X[[b, a], s]
+        if not last_round and accepted:
+            if spm == 1:
+                # one sweep per swap: the exchange reads the (edited) first column, but m_start_matrix was taken before the
+                # edit (apt_ICM.py:213) -- only the accepted pairs receive edited states (apt_ICM.py:282-283), every other
+                # chain continues from its unedited state
+                X = unedited
+                for a, b, s in accepted:
+                    X[a, s], X[b, s] = first[b, s].copy(), first[a, s].copy()
+            else:
+                X = eng.get_states()
+                for a, b, s in accepted:
+                    X[[a, b], s] = X[[b, a], s]
             eng.set_states(X)
     eng.close()
     Energy = np.zeros(R)

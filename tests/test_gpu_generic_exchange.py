@@ -106,3 +106,40 @@ def test_npt_run_production_generic_engines(nl, kind, tmp_cwd):
         means.append(Er.mean())
     assert means[-1] < means[0]                       # rows are in beta order: the coldest is the lowest
     assert np.all(np.diff(means) < 0.15 * abs(means[-1]))   # and roughly monotone in between
+
+
+def test_hybrid_ladder_matches_single_engine_ladder(nl, tmp_cwd, monkeypatch):
+    """Config C2's shape on a small lattice: NPT.run with NMC on the 2 coldest of 6 replicas.  The hybrid path (plain replicas
+    bit-packed on K2, NMC replicas on K2a, exchanges between the two kinds) and the single-engine path (everything on K2a)
+    sample the same ladder: per-replica mean of the returned last-round energies over independent runs within 3 sigma
+    (two-sample), and the hybrid's returned energies belong to its returned states."""
+    from nlmc_b200 import NPT
+    from oracle import oracle as O
+    A, h = O.ea3d_pm_j(4, 6)
+    n, R = 64, 6
+    csr = O.Csr(A)
+    betas = np.linspace(0.3, 1.6, R)
+    kw = dict(num_sweeps_MCMC=240, num_sweeps_read=240, num_swap_attempts=8, num_swapping_pairs=2, num_cycles=2,
+              global_beta=2.5, lambda_start=3.0, lambda_end=0.01, threshold_initial=0.9999, threshold_cutoff=0.999,
+              max_iterations=100, tolerance=1e-9)
+    doNMC = [False] * 4 + [True] * 2
+
+    def sample(runs, seed0):
+        out = []
+        for k in range(runs):
+            np.random.seed(seed0 + k)
+            import random
+            random.seed(seed0 + k)
+            M, E = NPT(A, h, mode="production").run(betas, R, doNMC, **kw)
+            spm = M.shape[1]
+            Er = np.stack([O.energy(csr, h, M[r * n:(r + 1) * n].T.astype(np.int8)) for r in range(R)])
+            assert np.array_equal(E, Er.min(axis=1)) and spm == 30
+            out.append(Er.mean(axis=1))
+        return np.array(out)
+
+    hyb = sample(30, 100)
+    monkeypatch.setenv("NLMC_NO_HYBRID", "1")
+    ref = sample(30, 500)
+    for r in range(R):
+        err = np.sqrt(hyb[:, r].var(ddof=1) / len(hyb) + ref[:, r].var(ddof=1) / len(ref))
+        assert abs(hyb[:, r].mean() - ref[:, r].mean()) <= 3.0 * err + 1e-9, (r, hyb[:, r].mean(), ref[:, r].mean(), err)

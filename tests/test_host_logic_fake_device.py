@@ -256,3 +256,27 @@ def test_production_host_logic_bit_packed_paths(fake_device, monkeypatch):
     assert M.shape == (3 * n, 2 * 10) and np.all(np.abs(M) == 1)
     for r in range(3):
         assert E[r] == O.energy(csr, np.zeros(n), M[r * n:(r + 1) * n, :2].T.astype(np.int8)).min()
+
+
+def test_production_host_logic_hybrid_ladder(fake_device, monkeypatch):
+    """NPT.run on a +-J lattice with NMC on the coldest replicas (C2-shaped): plain replicas on the bit-packed stand-in,
+    NMC replicas on the generic stand-in, exchanges between the two kinds -- return contract and energies that belong to
+    the returned states."""
+    from nlmc_b200 import NPT, _lib, production
+    from oracle import oracle as O
+    monkeypatch.setattr(_lib, "Msc", fake_backend.FakeMsc)
+    monkeypatch.setattr(production, "_generic_engine", lambda prob, betas, seed: fake_backend.FakeEngine(prob, betas, seed))
+    A, h = O.ea3d_pm_j(3, 4)
+    n = 27
+    csr = O.Csr(A)
+    betas = np.array([0.3, 0.7, 1.1, 1.5])
+    seed_all(12)
+    obj = NPT(A.toarray(), h, mode="production")
+    M, E = obj.run(betas, 4, [False, False, True, True], num_sweeps_MCMC=36, num_sweeps_read=18, num_swap_attempts=3,
+                   num_swapping_pairs=1, num_cycles=2, global_beta=2.0, lambda_start=3, threshold_initial=0.99,
+                   threshold_cutoff=0.9, max_iterations=50, tolerance=1e-9)
+    spm, spr = 12, 6
+    assert M.shape == (4 * n, spm) and E.shape == (4,) and np.all(np.abs(M) == 1)
+    for r in range(4):
+        Er = O.energy(csr, h, M[r * n:(r + 1) * n].T.astype(np.int8))
+        assert E[r] == Er[:spr].min()

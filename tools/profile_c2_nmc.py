@@ -10,6 +10,7 @@ host.Problem(np.array([[0.0, 1.0], [1.0, 0.0]]), np.zeros(2))
 os.chdir("/tmp"); np.random.seed(5); random.seed(5)
 kw = dict(num_cycles=10, full_update_frequency=1, M_skip=1, temp_x=20, global_beta=1 / 0.366838 * 5, lambda_start=3, lambda_end=0.01,
           lambda_reduction_factor=0.9, threshold_initial=0.9999999, threshold_cutoff=0.999999, max_iterations=100, tolerance=np.finfo(float).eps)
+import time; t0 = time.perf_counter(); NPT(A, h, mode="production").run(betas, 30, [False] * 25 + [True] * 5, num_sweeps_MCMC=10000, num_sweeps_read=100, num_swap_attempts=10, num_swapping_pairs=9, **kw); print("first call", time.perf_counter() - t0); t0 = time.perf_counter(); NPT(A, h, mode="production").run(betas, 30, [False] * 25 + [True] * 5, num_sweeps_MCMC=10000, num_sweeps_read=100, num_swap_attempts=10, num_swapping_pairs=9, **kw); print("second call", time.perf_counter() - t0)
 pr = cProfile.Profile(); pr.enable()
 NPT(A, h, mode="production").run(betas, 30, [False] * 25 + [True] * 5, num_sweeps_MCMC=10000, num_sweeps_read=100, num_swap_attempts=10, num_swapping_pairs=9, **kw)
 pr.disable()
