@@ -31,10 +31,14 @@
 
 namespace nlmc {
 
-constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3, kMaxSplit = 3;
+constexpr int kBM = 128, kBN = 128, kBK = 64, kMaxSplit = 3;
 constexpr int kTileBytes = kBM * kBK * 2;  // one 128 x 64 bf16 tile = 16 KiB (A and each B piece)
 constexpr int kGemmThreads = 192;
-constexpr size_t kGemmSmem = (size_t)kStages * (1 + kMaxSplit) * kTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+// shared memory of the GEMM with kSt ring stages: 3 for the stand-alone contraction (192 KB), 2 inside the sweep, where a
+// GEMM CTA must fit on an SM next to a CTA of the block-update kernel it overlaps with (128 KB + 87 KB)
+__host__ __device__ constexpr size_t gemm_smem_bytes(int stages) {
+    return (size_t)stages * (1 + kMaxSplit) * kTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+}
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,10 +91,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 
 struct GemmParams {
     int M, N, n_base, k_blocks_total, k_splits, n_split, ldc;  // C^T is [N][ldc], ldc >= M; columns start at n_base
+    // the contraction runs over k_blocks_total blocks of 64 columns of K: block i is kb_offset + i, and blocks at or above
+    // skip_begin are shifted up by skip_count (look-ahead: the columns of the block being updated are left out of the main
+    // part and contracted afterwards)
+    int kb_offset, skip_begin, skip_count;
     float *Ct;
     int accumulate;  // 1: red.add into C^T (split-K or accumulate), 0: plain store
 };
 
+template <int kStages>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b0,
                     const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
@@ -136,7 +145,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 mbar_wait(empty + s, ph ^ 1u);
                 uint8_t *st = smem + (size_t)s * (1 + kMaxSplit) * kTileBytes;
                 mbar_expect_tx(full + s, (uint32_t)stage_bytes);
-                const int k0 = (kb_begin + i) * kBK;
+                int kb = kb_begin + i;
+                if (kb >= p.skip_begin) kb += p.skip_count;
+                const int k0 = (p.kb_offset + kb) * kBK;
                 tma_load_2d(st, &map_a, full + s, k0, m0);
                 for (int q = 0; q < p.n_split; ++q) tma_load_2d(st + (1 + q) * kTileBytes, maps_b[q], full + s, k0, n0);
             }
@@ -260,6 +271,7 @@ static inline float bf16_to_f32(uint16_t b) {
 struct nlmc_dense {
     nlmc_instance *inst = nullptr;
     int n = 0, n_pad = 0, R = 0, R_pad = 0, n_split = 1, block = 128;
+    int upd_rpc = 8;                   // replicas (warps) per CTA of the block-update kernel: one CTA per SM
     uint16_t *S = nullptr;             // [R_pad][n_pad] bf16 spins (+-1; 0 in the padding)
     uint16_t *Jp[3] = {nullptr, nullptr, nullptr};  // [n_pad][n_pad] bf16 pieces of J (row-major, J symmetric)
     float *Jf = nullptr;               // [n_pad][n_pad] fp32 J TRANSPOSED (JfT[a][b] = J[b][a]; in-block corrections)
@@ -278,31 +290,46 @@ struct nlmc_dense {
     cudaGraphExec_t sweep_graph = nullptr;  // one whole sweep: 1 memset + n/128 x (split-K GEMM, block update) + counter
     nlmc::LadderExchange xch;          // replica exchange by beta labels (nlmc_dense_ladders / nlmc_dense_exchange)
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;     // look-ahead GEMMs of the sweep (forked from / joined into `stream` inside the captured graph)
+    std::vector<cudaEvent_t> fork_ev;  // one event per fork / join point of the captured sweep
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 namespace nlmc {
 
-// fields of columns [col0, col0 + n_cols) for all replicas: Ht[col][r] = sum_k S[r][k] J[col][k]
-static int launch_fields(nlmc_dense *D, int col0, int n_cols, int k_splits, bool clear = true) {
+// fields of columns [col0, col0 + n_cols) for all replicas: Ht[col][r] = sum_k S[r][k] J[col][k], the sum running over
+// the k-blocks [kb_first, kb_first + kb_count) of 64 columns with the blocks [skip_first, skip_first + skip_count) left out
+static int launch_fields_part(nlmc_dense *D, cudaStream_t st, int col0, int n_cols, int k_splits, bool clear, int kb_first,
+                              int kb_count, int skip_first, int skip_count, int stages) {
     NLMC_REQUIRE(col0 % kBN == 0, "launch_fields: col0 must be a multiple of %d", kBN);
     GemmParams p;
     p.M = D->R_pad;
     p.N = std::min(D->n_pad, col0 + n_cols);
     p.n_base = col0;
-    p.k_blocks_total = D->n_pad / kBK;
-    p.k_splits = k_splits;
+    p.kb_offset = kb_first;
+    p.skip_begin = skip_count > 0 ? skip_first - kb_first : (1 << 30);
+    p.skip_count = skip_count;
+    p.k_blocks_total = kb_count - skip_count;
+    p.k_splits = std::max(1, std::min(k_splits, p.k_blocks_total));
     p.n_split = D->n_split;
     p.ldc = D->R_pad;
     p.Ct = D->Ht;
-    p.accumulate = k_splits > 1;
+    p.accumulate = k_splits > 1 || !clear;
     if (p.accumulate && clear)
-        NLMC_CUDA(cudaMemsetAsync(D->Ht + (size_t)col0 * D->R_pad, 0, sizeof(float) * (size_t)(p.N - col0) * D->R_pad, D->stream));
-    const dim3 grid((unsigned)(D->R_pad / kBM), (unsigned)((n_cols + kBN - 1) / kBN), (unsigned)k_splits);
-    gemm_bf16_tn_kernel<<<grid, kGemmThreads, kGemmSmem, D->stream>>>(
-        D->map_S, D->map_J[0], D->map_J[D->n_split > 1 ? 1 : 0], D->map_J[D->n_split > 2 ? 2 : 0], p);
+        NLMC_CUDA(cudaMemsetAsync(D->Ht + (size_t)col0 * D->R_pad, 0, sizeof(float) * (size_t)(p.N - col0) * D->R_pad, st));
+    const dim3 grid((unsigned)(D->R_pad / kBM), (unsigned)((n_cols + kBN - 1) / kBN), (unsigned)p.k_splits);
+    if (stages == 2)
+        gemm_bf16_tn_kernel<2><<<grid, kGemmThreads, gemm_smem_bytes(2), st>>>(
+            D->map_S, D->map_J[0], D->map_J[D->n_split > 1 ? 1 : 0], D->map_J[D->n_split > 2 ? 2 : 0], p);
+    else
+        gemm_bf16_tn_kernel<3><<<grid, kGemmThreads, gemm_smem_bytes(3), st>>>(
+            D->map_S, D->map_J[0], D->map_J[D->n_split > 1 ? 1 : 0], D->map_J[D->n_split > 2 ? 2 : 0], p);
     NLMC_CUDA(cudaGetLastError());
     return NLMC_OK;
+}
+
+static int launch_fields(nlmc_dense *D, int col0, int n_cols, int k_splits, bool clear = true) {
+    return launch_fields_part(D, D->stream, col0, n_cols, k_splits, clear, 0, D->n_pad / kBK, 0, 0, 3);
 }
 
 constexpr int kBlk = 128;  // sites per sequential block == kBN
@@ -324,164 +351,164 @@ struct PhiloxD {
     }
 };
 
-// Sequential heat-bath update of the sites [c0, c0+kBlk) for kRepPerCta replicas per CTA.
-// field_k = Ht[c0+k][r] (from the GEMM, spins as of the start of the block) + h_k
-//           + sum_{j<k} J[c0+k][c0+j] * (s_j^new - s_j^old)           (flips made earlier in this block)
+// Sequential heat-bath update of the sites [c0, c0+kBlk) for kRepPerCta replicas per CTA, one WARP per replica.
+// Ht holds the fields of the block from the current spins (GEMM); hf the external fields.
 // s_k <- +1 with probability 1/(1+exp(-2 beta_r field_k))  == sign(tanh(beta x) - 2u + 1), NMC/nmc.py:87
 //
-// The chain over k is sequential per replica and there are only R chains, so what matters is the latency
-// of one step (ncu on the first versions: ~1000 cycles/step, one warp per scheduler, every stall exposed).
-// The block is therefore processed in sub-blocks of 8 sites.  Each replica owns 8 lanes:
-//   1. the 8 fields of the sub-block and its 28 in-sub-block couplings are read by all 8 lanes (broadcast);
-//      the 8 decisions are then taken one after the other entirely in registers (no shuffles, no stores);
-//   2. the 8 flips are propagated to the fields of the later sites of the block, lane t taking the sites
-//      k' = 8m + t (conflict-free reads of the transposed J_bb, 8 FMAs each).
-constexpr int kRepPerCta = 16;
-constexpr int kFldStride = kBlk + 8;    // floats per replica row: the 4 replicas of a warp fall into disjoint bank groups
-constexpr int kSpinStride = kBlk + 32;  // bytes per replica row, same reason
-constexpr size_t kUpdateSmem = sizeof(float) * ((size_t)kBlk * kBlk + (size_t)kRepPerCta * kFldStride) + (size_t)kRepPerCta * kSpinStride;
+// The chain over k is sequential per replica and there are only R chains, so what matters is the latency of one
+// step.  Round 1 (8 lanes per replica, Philox + logit inside the chain): 20.5 us per block, 6 % of the warp slots, three
+// quarters of the C3 sweep.  Now:
+//   0. everything that does not depend on the chain is done up front, in parallel over the block: the thresholds
+//      theta_k = logit(u_k) / (2 beta) of all 128 sites (one Philox call and four logits per lane), with the NMC phase
+//      modes folded in (hot sites: theta * temp_x; frozen sites: theta = -+inf so that the spin keeps its value);
+//   1. the block is processed in sub-blocks of 8 sites: the 8 fields, thresholds and 28 in-sub-block couplings come in
+//      with 128-bit broadcast loads and the 8 decisions are taken one after the other in registers
+//      (compare, select, and the right-looking FMAs into the later fields of the sub-block);
+//   2. the 8 flips are propagated to the later sites of the block by all 32 lanes (lane t owns k' = 8m + t + 32 q,
+//      conflict-free reads of the transposed J_bb, two FMA chains of 4).
+// The random stream is the one of round 1 (same Philox keys, same logit), so trajectories are the same up to the
+// rounding of the propagation sums.
+// CTA size: one warp per replica, as many replicas per CTA as it takes to give every SM ONE CTA (ncu on the 8-warp
+// version: 256 CTAs on 148 SMs left the SMs with two CTAs as the critical path); the 64 KB coupling block is staged
+// once per SM.  The sub-block loop is fully unrolled (16 x 8 sites, every shared-memory address an immediate); sites
+// past the end of J are frozen through their threshold, so the trip count is a constant.
+constexpr int kMaxRepPerCta = 16;
+constexpr int kFldStride = kBlk + 8;    // floats per replica row (16-byte aligned rows, rows of a CTA in different banks)
+__host__ __device__ constexpr size_t update_smem_bytes(int rep_per_cta) {
+    return sizeof(float) * ((size_t)kBlk * kBlk + 3 * (size_t)rep_per_cta * kFldStride);
+}
 
-__global__ void __launch_bounds__(128) dense_block_update_kernel(int n, int n_pad, int R_pad, int c0, const float *__restrict__ Ht,
-                                                                 const float *__restrict__ Jf, const float *__restrict__ hf,
-                                                                 const float *__restrict__ beta, uint16_t *S,
-                                                                 uint32_t seed_lo, uint32_t seed_hi,
-                                                                 const uint32_t *__restrict__ sweep_ptr, float *Ht_zero,
-                                                                 const uint8_t *__restrict__ modes, float temp_x) {
+__global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(int n, int n_pad, int R_pad, int c0, const float *__restrict__ Ht,
+                                                                               const float *__restrict__ Jf, const float *__restrict__ hf,
+                                                                               const float *__restrict__ beta, uint16_t *S,
+                                                                               uint32_t seed_lo, uint32_t seed_hi,
+                                                                               const uint32_t *__restrict__ sweep_ptr, float *Ht_zero,
+                                                                               const uint8_t *__restrict__ modes, float temp_x) {
     extern __shared__ __align__(16) uint8_t dsm[];
     const uint32_t sweep = *sweep_ptr;
+    const int rpc = blockDim.x >> 5;                                   // replicas (warps) per CTA
     float *Jt = reinterpret_cast<float *>(dsm);                        // [kBlk j][kBlk k] = J[c0+k][c0+j] (transposed)
-    float *fld = Jt + (size_t)kBlk * kBlk;                             // [kRepPerCta][kBlk]   running fields
-    int8_t *spin = reinterpret_cast<int8_t *>(fld + (size_t)kRepPerCta * kFldStride);  // [kRepPerCta][kSpinStride]
+    float *fld = Jt + (size_t)kBlk * kBlk;                             // [rpc][kFldStride]  running fields
+    float *thr = fld + (size_t)rpc * kFldStride;                       // [rpc][kFldStride]  thresholds
+    float *spn = thr + (size_t)rpc * kFldStride;                       // [rpc][kFldStride]  spins as floats
     const int tid = threadIdx.x;
-    const int rep = tid >> 3, t = tid & 7;     // replica within the CTA, lane within the replica's group
-    const int r0 = blockIdx.x * kRepPerCta;
-    const int r = r0 + rep;
+    const int rep = tid >> 5, lane = tid & 31;   // replica within the CTA = warp
+    const int r = blockIdx.x * rpc + rep;
+    const int k_end = min(kBlk, n - c0);
     // stage J_bb transposed, Jt[j][k] = J[c0+k][c0+j], from the transposed copy of J kept in global memory
-    // (JfT[a][b] = J[b][a]): coalesced float4 reads, conflict-free float4 writes
-    // asynchronous 16-byte copies (no register staging): all 64 KB are in flight at once and overlap the field/spin
-    // loads below; ncu showed 40 % of this kernel's time in the prologue's load latency
-    for (int i = tid; i < kBlk * kBlk / 4; i += 128) {
+    // (JfT[a][b] = J[b][a]): asynchronous 16-byte copies, all 64 KB in flight while the thresholds are computed
+    for (int i = tid; i < kBlk * kBlk / 4; i += blockDim.x) {
         const int j = i / (kBlk / 4), k4 = i % (kBlk / 4);
         const uint32_t dst = smem_u32(reinterpret_cast<float4 *>(Jt) + i);
         const float *src = Jf + (size_t)(c0 + j) * n_pad + c0 + k4 * 4;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    {   // all 16 field / spin loads of a thread are issued before the first use (one exposed round trip, not 16)
-        constexpr int kPer = kRepPerCta * kBlk / 128;
-        float hv[kPer], fv[kPer];
-        uint16_t sv[kPer];
-#pragma unroll
-        for (int q = 0; q < kPer; ++q) {
-            const int i = tid + q * 128;
-            const int k = i / kRepPerCta, rr = i % kRepPerCta;  // consecutive threads -> consecutive replicas (coalesced Ht row)
-            hv[q] = Ht[(size_t)(c0 + k) * R_pad + r0 + rr];
-            fv[q] = hf[c0 + k];
-            sv[q] = S[(size_t)(r0 + rr) * n_pad + c0 + k];
-        }
-#pragma unroll
-        for (int q = 0; q < kPer; ++q) {
-            const int i = tid + q * 128;
-            const int k = i / kRepPerCta, rr = i % kRepPerCta;
-            fld[rr * kFldStride + k] = hv[q] + fv[q];
-            spin[rr * kSpinStride + k] = (sv[q] == 0) ? 0 : ((sv[q] & 0x8000u) ? -1 : 1);
-        }
-    }
-    // the next block's split-K GEMM accumulates with atomics: clear its field rows for this CTA's replicas
-    if (Ht_zero != nullptr)
-        for (int i = tid; i < kRepPerCta * kBlk; i += 128) Ht_zero[(size_t)(i / kRepPerCta) * R_pad + r0 + (i % kRepPerCta)] = 0.f;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    const float inv2b = 0.5f / beta[r];
-    const uint8_t *mrow = modes ? modes + (size_t)r * n_pad + c0 : nullptr;
-    const PhiloxD rng{seed_lo, seed_hi ^ 0x44454e53u};
-    const int k_end = min(kBlk, n - c0);
     float *frow = fld + rep * kFldStride;
-    int8_t *srow = spin + rep * kSpinStride;
-    for (int base = 0; base < k_end; base += 8) {
-        // ---- 1. the sub-block, sequentially, in registers (identical in the 8 lanes of the replica).
-        // up  <=>  u < 1/(1+exp(-2 beta f))  <=>  f > logit(u)/(2 beta) =: theta, which depends on the random
-        // number only: exp/log stay off the sequential chain, a decision is compare + select + FMA.
-        float F[8], Jss[28], d[8], theta[8], dp[8], dm[8];
+    float *trow = thr + rep * kFldStride;
+    float *srow = spn + rep * kFldStride;
+    const bool active = r < R_pad;
+    if (active) {
+        // fields of the replica: lane -> sites lane + 32 q (the warps of a CTA read the same 32-byte sectors of Ht)
+        float hv[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            F[i] = frow[base + i];
-            const float so = (float)srow[base + i];
-            dp[i] = 1.0f - so;    // delta if the site ends up +1
-            dm[i] = -1.0f - so;   // delta if it ends up -1
-        }
+        for (int q = 0; q < 4; ++q) hv[q] = Ht[(size_t)(c0 + lane + 32 * q) * R_pad + r] + hf[c0 + lane + 32 * q];
 #pragma unroll
-        for (int i = 1, q = 0; i < 8; ++i)
+        for (int q = 0; q < 4; ++q) frow[lane + 32 * q] = hv[q];
+        // the next block's split-K GEMM accumulates with atomics: clear its field rows for this replica
+        if (Ht_zero != nullptr)
 #pragma unroll
-            for (int j = 0; j < i; ++j, ++q) Jss[q] = Jt[(base + j) * kBlk + base + i];  // J[base+i][base+j]
-        const uint4 ra = rng((uint32_t)r, (uint32_t)(c0 + base), sweep, 0u);
-        const uint4 rb = rng((uint32_t)r, (uint32_t)(c0 + base), sweep, 1u);
-        const uint32_t ub[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+            for (int q = 0; q < 4; ++q) Ht_zero[(size_t)(lane + 32 * q) * R_pad + r] = 0.f;
+        // spins and thresholds of the lane's four sites 4*lane .. 4*lane+3
+        const uint2 sv = *reinterpret_cast<const uint2 *>(S + (size_t)r * n_pad + c0 + 4 * lane);   // 256 B per warp
+        const uint16_t s16[4] = {(uint16_t)(sv.x & 0xffffu), (uint16_t)(sv.x >> 16), (uint16_t)(sv.y & 0xffffu), (uint16_t)(sv.y >> 16)};
+        const float inv2b = 0.5f / beta[r];
+        const PhiloxD rng{seed_lo, seed_hi ^ 0x44454e53u};
+        // the stream of round 1: call (r, c0 + 8*(lane/2), sweep, lane & 1) serves the four sites 4*lane .. 4*lane+3
+        const uint4 rv = rng((uint32_t)r, (uint32_t)(c0 + 8 * (lane >> 1)), sweep, (uint32_t)(lane & 1));
+        const uint32_t ub[4] = {rv.x, rv.y, rv.z, rv.w};
+        uint32_t md4 = 0u;
+        if (modes != nullptr) md4 = *reinterpret_cast<const uint32_t *>(modes + (size_t)r * n_pad + c0 + 4 * lane);
+        float th[4], so[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
             // logit of a uniform in (0,1) from all 32 bits, evaluated on the side of the nearer tail so that both tails
             // are symmetric and reach 2^-33 (a 24-bit uniform rounded to 1.0 forced the spin down once in 2^24 draws)
             const bool hi = (ub[i] >> 31) != 0u;
             const uint32_t m = hi ? ~ub[i] : ub[i];
             const float v = ((float)m + 0.5f) * (1.0f / 4294967296.0f);       // in (0, 1/2]
             const float t = __logf(v) - __logf(1.0f - v);
-            theta[i] = (hi ? -t : t) * inv2b;
+            th[i] = (hi ? -t : t) * inv2b;
+            so[i] = (s16[i] == 0) ? 0.0f : ((s16[i] & 0x8000u) ? -1.0f : 1.0f);
+            const uint32_t md = (md4 >> (8 * i)) & 0xffu;
+            if (md == 1u) th[i] *= temp_x;                                      // hot backbone: beta / temp_x
+            if (md == 2u || 4 * lane + i >= k_end)                              // frozen (or padding): the spin keeps its value
+                th[i] = so[i] > 0.0f ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
         }
-        uint32_t frozen = 0;  // NMC phases: frozen sites keep their spin (the reference pins them with h = +-1e4)
-        if (mrow != nullptr) {
+        *reinterpret_cast<float4 *>(trow + 4 * lane) = make_float4(th[0], th[1], th[2], th[3]);
+        *reinterpret_cast<float4 *>(srow + 4 * lane) = make_float4(so[0], so[1], so[2], so[3]);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (!active) return;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint8_t md = mrow[base + i];
-                if (md == 1) theta[i] *= temp_x;
-                frozen |= (uint32_t)(md == 2) << i;
-            }
+    for (int sb = 0; sb < kBlk / 8; ++sb) {
+        const int base = sb * 8;
+        // ---- 1. the sub-block, sequentially, in registers (identical in all lanes of the warp)
+        float F[8], T[8], so[8], d[8];
+        {
+            const float4 f0 = *reinterpret_cast<const float4 *>(frow + base), f1 = *reinterpret_cast<const float4 *>(frow + base + 4);
+            const float4 t0 = *reinterpret_cast<const float4 *>(trow + base), t1 = *reinterpret_cast<const float4 *>(trow + base + 4);
+            const float4 s0 = *reinterpret_cast<const float4 *>(srow + base), s1 = *reinterpret_cast<const float4 *>(srow + base + 4);
+            F[0] = f0.x; F[1] = f0.y; F[2] = f0.z; F[3] = f0.w; F[4] = f1.x; F[5] = f1.y; F[6] = f1.z; F[7] = f1.w;
+            T[0] = t0.x; T[1] = t0.y; T[2] = t0.z; T[3] = t0.w; T[4] = t1.x; T[5] = t1.y; T[6] = t1.z; T[7] = t1.w;
+            so[0] = s0.x; so[1] = s0.y; so[2] = s0.z; so[3] = s0.w; so[4] = s1.x; so[5] = s1.y; so[6] = s1.z; so[7] = s1.w;
         }
-        uint32_t newbits = 0;
+        float sn[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const bool live = (base + i < k_end) && !((frozen >> i) & 1u);
-            const bool up = live ? (F[i] > theta[i]) : (dp[i] == 0.0f);  // not live: keep the old spin
-            d[i] = live ? (up ? dp[i] : dm[i]) : 0.0f;
-            newbits |= (uint32_t)up << i;
+            sn[i] = F[i] > T[i] ? 1.0f : -1.0f;
+            d[i] = sn[i] - so[i];
+            if (i < 7) {   // right-looking inside the sub-block: row base+i of the transposed block, columns base+i+1 .. base+7
+                const float4 lo = *reinterpret_cast<const float4 *>(Jt + (base + i) * kBlk + base);
+                const float4 hi4 = *reinterpret_cast<const float4 *>(Jt + (base + i) * kBlk + base + 4);
+                const float Ji[8] = {lo.x, lo.y, lo.z, lo.w, hi4.x, hi4.y, hi4.z, hi4.w};
 #pragma unroll
-            for (int i2 = i + 1; i2 < 8; ++i2) F[i2] = fmaf(Jss[i2 * (i2 - 1) / 2 + i], d[i], F[i2]);  // right-looking
-        }
-        if (t == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (base + i < k_end) srow[base + i] = (int8_t)(((newbits >> i) & 1u) ? 1 : -1);
-        }
-        // ---- 2. propagate the 8 flips to the later sites of the block: lane t owns k' = 8m + t
-        for (int kp = base + 8 + t; kp < k_end; kp += 8) {  // two independent FMA chains: half the dependent latency
-            float a = frow[kp], b = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                a = fmaf(Jt[(base + j) * kBlk + kp], d[j], a);
-                b = fmaf(Jt[(base + 4 + j) * kBlk + kp], d[4 + j], b);
+                for (int i2 = i + 1; i2 < 8; ++i2) F[i2] = fmaf(Ji[i2], d[i], F[i2]);
             }
-            frow[kp] = a + b;
+        }
+        if (lane == 0) {
+            *reinterpret_cast<float4 *>(srow + base) = make_float4(sn[0], sn[1], sn[2], sn[3]);
+            *reinterpret_cast<float4 *>(srow + base + 4) = make_float4(sn[4], sn[5], sn[6], sn[7]);
+        }
+        // ---- 2. propagate the 8 flips to the later sites of the block: lane t owns k' = base + 8 + t + 32 q
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int kp = base + 8 + lane + 32 * q;
+            if (base + 8 + 32 * q < kBlk && kp < kBlk) {   // two independent FMA chains: half the dependent latency
+                float a = frow[kp], b = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    a = fmaf(Jt[(base + j) * kBlk + kp], d[j], a);
+                    b = fmaf(Jt[(base + 4 + j) * kBlk + kp], d[4 + j], b);
+                }
+                frow[kp] = a + b;
+            }
         }
         __syncwarp();
     }
-    __syncthreads();
-    // write the block segments back as bf16 (+1 = 0x3F80, -1 = 0xBF80): thread -> (replica, 16 consecutive sites)
+    // write the replica's block segment back as bf16 (+1 = 0x3F80, -1 = 0xBF80): lane -> 4 consecutive sites, 256 B per warp
     {
-        const int seg = t * 16;
-        uint32_t w[8];
+        const float4 c = *reinterpret_cast<const float4 *>(srow + 4 * lane);
+        const float sv[4] = {c.x, c.y, c.z, c.w};
+        uint32_t w[2] = {0u, 0u};
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-            uint32_t pair = 0;
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-                const int k = seg + e + h2;
-                const int sv = k < k_end ? spin[rep * kSpinStride + k] : 0;
-                pair |= (sv > 0 ? 0x3F80u : (sv < 0 ? 0xBF80u : 0u)) << (16 * h2);
-            }
-            w[e >> 1] = pair;
+        for (int i = 0; i < 4; ++i) {
+            const int k = 4 * lane + i;
+            const uint32_t b16 = (k < k_end) ? (sv[i] > 0.0f ? 0x3F80u : (sv[i] < 0.0f ? 0xBF80u : 0u)) : 0u;
+            w[i >> 1] |= b16 << (16 * (i & 1));
         }
-        uint4 *dst = reinterpret_cast<uint4 *>(S + (size_t)r * n_pad + c0 + seg);
-        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        *reinterpret_cast<uint2 *>(S + (size_t)r * n_pad + c0 + 4 * lane) = make_uint2(w[0], w[1]);
     }
 }
 
@@ -558,6 +585,8 @@ int nlmc_dense_destroy(nlmc_dense *D) {
     if (D->sweep_graph) cudaGraphExecDestroy(D->sweep_graph);
     if (D->ev0) cudaEventDestroy(D->ev0);
     if (D->ev1) cudaEventDestroy(D->ev1);
+    for (cudaEvent_t e : D->fork_ev) cudaEventDestroy(e);
+    if (D->stream2) cudaStreamDestroy(D->stream2);
     if (D->stream) cudaStreamDestroy(D->stream);
     delete D;
     return NLMC_OK;
@@ -593,6 +622,12 @@ int nlmc_dense_create(nlmc_instance *I, int n_replicas, const double *betas, int
     D->n_pad = ((I->n + kBN - 1) / kBN) * kBN;
     D->R = n_replicas;
     D->R_pad = ((n_replicas + kBM - 1) / kBM) * kBM;
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, I->device);
+        D->upd_rpc = std::max(1, std::min(kMaxRepPerCta, (D->R_pad + sms - 1) / std::max(1, sms)));
+        if (const char *e = getenv("NLMC_DENSE_RPC")) D->upd_rpc = std::max(1, std::min(kMaxRepPerCta, atoi(e)));
+    }
     D->n_split = n_split;
     D->seed = seed;
     const size_t np = (size_t)D->n_pad, nn = np * np;
@@ -614,6 +649,7 @@ int nlmc_dense_create(nlmc_instance *I, int n_replicas, const double *betas, int
         }
     }
     bool ok = cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&D->stream2, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&D->ev0) == cudaSuccess && cudaEventCreate(&D->ev1) == cudaSuccess &&
               cudaMalloc(&D->S, sizeof(uint16_t) * (size_t)D->R_pad * np) == cudaSuccess &&
               cudaMalloc(&D->Jf, sizeof(float) * nn) == cudaSuccess && cudaMalloc(&D->hf, sizeof(float) * np) == cudaSuccess &&
@@ -634,8 +670,9 @@ int nlmc_dense_create(nlmc_instance *I, int n_replicas, const double *betas, int
     int rc = make_map(&D->map_S, D->S, (uint64_t)D->R_pad, np, np);
     for (int q = 0; !rc && q < n_split; ++q) rc = make_map(&D->map_J[q], D->Jp[q], np, np, np);
     if (!rc) {
-        if (cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem) != cudaSuccess ||
-            cudaFuncSetAttribute(dense_block_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmem) != cudaSuccess) {
+        if (cudaFuncSetAttribute(gemm_bf16_tn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(3)) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_bf16_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)) != cudaSuccess ||
+            cudaFuncSetAttribute(dense_block_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(kMaxRepPerCta)) != cudaSuccess) {
             set_error("nlmc_dense_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = NLMC_ERR_CUDA;
         }
@@ -708,15 +745,65 @@ int nlmc_dense_fields(nlmc_dense *D, float *out_H) {
     return NLMC_OK;
 }
 
+// One sweep = the blocks of 128 sites in order.  The fields of block b+1 need the spins AFTER the update of block b, but
+// only through the 128 columns of block b: the contraction over all other columns ("main part", 15/16 of the work) is
+// issued on a second stream as soon as the update of block b-1 is done and overlaps the latency-bound update of block b;
+// the two k-blocks of block b ("correction") follow the update.  Both parts accumulate atomically into the field rows of
+// block b+1, which the update of block b-1 cleared.
 static int enqueue_sweep(nlmc_dense *D, int k_splits) {
     using namespace nlmc;
-    for (int c0 = 0; c0 < D->n; c0 += kBlk) {
-        int rc = launch_fields(D, c0, kBlk, k_splits, /*clear=*/c0 == 0);  // later blocks are cleared by the update kernel
-        if (rc) return rc;
-        float *zero_next = (k_splits > 1 && c0 + kBlk < D->n) ? D->Ht + (size_t)(c0 + kBlk) * D->R_pad : nullptr;
-        dense_block_update_kernel<<<(unsigned)(D->R_pad / kRepPerCta), 128, kUpdateSmem, D->stream>>>(
-            D->n, D->n_pad, D->R_pad, c0, D->Ht, D->Jf, D->hf, D->beta, D->S, (uint32_t)D->seed, (uint32_t)(D->seed >> 32),
-            D->d_sweep, zero_next, D->modes_on ? D->modes : nullptr, D->temp_x);
+    const int nb = (D->n + kBlk - 1) / kBlk, kb_all = D->n_pad / kBK, kb_blk = kBlk / kBK;
+    // Measured on B200 at C3 size: 0.470 ms per sweep with the look-ahead against 0.355 ms without -- the third kernel per
+    // block (the correction, 16 CTAs for two k-blocks) and the extra dependency edges cost more than the overlap hides.
+    // Kept behind a switch; the default is the plain GEMM -> update chain.
+    const bool look_ahead = nb > 1 && getenv("NLMC_DENSE_LOOKAHEAD") != nullptr;
+    auto launch_update = [&](int b, float *zero_rows) {
+        dense_block_update_kernel<<<(unsigned)((D->R_pad + D->upd_rpc - 1) / D->upd_rpc), (unsigned)(32 * D->upd_rpc),
+                                    update_smem_bytes(D->upd_rpc), D->stream>>>(
+            D->n, D->n_pad, D->R_pad, b * kBlk, D->Ht, D->Jf, D->hf, D->beta, D->S, (uint32_t)D->seed, (uint32_t)(D->seed >> 32),
+            D->d_sweep, zero_rows, D->modes_on ? D->modes : nullptr, D->temp_x);
+    };
+    int rc;
+    if (!look_ahead) {
+        for (int b = 0; b < nb; ++b) {
+            if ((rc = launch_fields_part(D, D->stream, b * kBlk, kBlk, k_splits, /*clear=*/b == 0, 0, kb_all, 0, 0, 3))) return rc;
+            launch_update(b, (k_splits > 1 && b + 1 < nb) ? D->Ht + (size_t)(b + 1) * kBlk * D->R_pad : nullptr);
+        }
+    } else {
+        size_t ev = 0;
+        auto next_event = [&]() -> cudaEvent_t {
+            if (ev == D->fork_ev.size()) {
+                cudaEvent_t e = nullptr;
+                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+                D->fork_ev.push_back(e);
+            }
+            return D->fork_ev[ev++];
+        };
+        // field rows of blocks 0 and 1 start from zero (the later ones are cleared by the update two blocks before)
+        NLMC_CUDA(cudaMemsetAsync(D->Ht, 0, sizeof(float) * (size_t)std::min(2 * kBlk, D->n_pad) * D->R_pad, D->stream));
+        cudaEvent_t e_ready = next_event();          // "spins of all blocks before b are final, rows of block b+1 are clear"
+        if (!e_ready) return NLMC_ERR_CUDA;
+        NLMC_CUDA(cudaEventRecord(e_ready, D->stream));
+        if ((rc = launch_fields_part(D, D->stream, 0, kBlk, k_splits, /*clear=*/false, 0, kb_all, 0, 0, 2))) return rc;
+        for (int b = 0; b < nb; ++b) {
+            cudaEvent_t e_main = nullptr;
+            if (b + 1 < nb) {   // main part of block b+1 on the second stream: every column except those of block b
+                NLMC_CUDA(cudaStreamWaitEvent(D->stream2, e_ready, 0));
+                if ((rc = launch_fields_part(D, D->stream2, (b + 1) * kBlk, kBlk, k_splits, /*clear=*/false, 0, kb_all,
+                                             b * kb_blk, kb_blk, 2))) return rc;
+                if (!(e_main = next_event())) return NLMC_ERR_CUDA;
+                NLMC_CUDA(cudaEventRecord(e_main, D->stream2));
+            }
+            launch_update(b, b + 2 < nb ? D->Ht + (size_t)(b + 2) * kBlk * D->R_pad : nullptr);
+            if (b + 1 < nb) {
+                if (!(e_ready = next_event())) return NLMC_ERR_CUDA;
+                NLMC_CUDA(cudaEventRecord(e_ready, D->stream));
+                // correction: the columns of block b, now final
+                if ((rc = launch_fields_part(D, D->stream, (b + 1) * kBlk, kBlk, 1, /*clear=*/false, b * kb_blk, kb_blk, 0, 0, 2)))
+                    return rc;
+                NLMC_CUDA(cudaStreamWaitEvent(D->stream, e_main, 0));
+            }
+        }
     }
     dense_bump_kernel<<<1, 1, 0, D->stream>>>(D->d_sweep);
     NLMC_CUDA(cudaGetLastError());
