@@ -95,6 +95,7 @@ struct GemmParams {
     // skip_begin are shifted up by skip_count (look-ahead: the columns of the block being updated are left out of the main
     // part and contracted afterwards)
     int kb_offset, skip_begin, skip_count;
+    int pdl;  // launched with programmatic stream serialization: the prologue overlaps the tail of the preceding kernel
     float *Ct;
     int accumulate;  // 1: red.add into C^T (split-K or accumulate), 0: plain store
 };
@@ -135,6 +136,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    if (p.pdl) {
+        // barriers, TMEM and tensor-map prefetch are done: let the next kernel of the chain (the block update) start ITS
+        // prologue now, and wait here until the kernel before us (the previous block update: spins, cleared field rows)
+        // has completed and flushed
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
@@ -299,8 +307,20 @@ namespace nlmc {
 
 // fields of columns [col0, col0 + n_cols) for all replicas: Ht[col][r] = sum_k S[r][k] J[col][k], the sum running over
 // the k-blocks [kb_first, kb_first + kb_count) of 64 columns with the blocks [skip_first, skip_first + skip_count) left out
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 static int launch_fields_part(nlmc_dense *D, cudaStream_t st, int col0, int n_cols, int k_splits, bool clear, int kb_first,
-                              int kb_count, int skip_first, int skip_count, int stages) {
+                              int kb_count, int skip_first, int skip_count, int stages, bool pdl = false) {
     NLMC_REQUIRE(col0 % kBN == 0, "launch_fields: col0 must be a multiple of %d", kBN);
     GemmParams p;
     p.M = D->R_pad;
@@ -315,12 +335,13 @@ static int launch_fields_part(nlmc_dense *D, cudaStream_t st, int col0, int n_co
     p.ldc = D->R_pad;
     p.Ct = D->Ht;
     p.accumulate = k_splits > 1 || !clear;
+    p.pdl = pdl ? 1 : 0;
     if (p.accumulate && clear)
         NLMC_CUDA(cudaMemsetAsync(D->Ht + (size_t)col0 * D->R_pad, 0, sizeof(float) * (size_t)(p.N - col0) * D->R_pad, st));
     const dim3 grid((unsigned)(D->R_pad / kBM), (unsigned)((n_cols + kBN - 1) / kBN), (unsigned)p.k_splits);
     if (stages == 2)
-        gemm_bf16_tn_kernel<2><<<grid, kGemmThreads, gemm_smem_bytes(2), st>>>(
-            D->map_S, D->map_J[0], D->map_J[D->n_split > 1 ? 1 : 0], D->map_J[D->n_split > 2 ? 2 : 0], p);
+        NLMC_CUDA(launch_pdl(gemm_bf16_tn_kernel<2>, grid, dim3(kGemmThreads), gemm_smem_bytes(2), st, pdl, D->map_S, D->map_J[0],
+                             D->map_J[D->n_split > 1 ? 1 : 0], D->map_J[D->n_split > 2 ? 2 : 0], p));
     else
         gemm_bf16_tn_kernel<3><<<grid, kGemmThreads, gemm_smem_bytes(3), st>>>(
             D->map_S, D->map_J[0], D->map_J[D->n_split > 1 ? 1 : 0], D->map_J[D->n_split > 2 ? 2 : 0], p);
@@ -383,9 +404,9 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
                                                                                const float *__restrict__ beta, uint16_t *S,
                                                                                uint32_t seed_lo, uint32_t seed_hi,
                                                                                const uint32_t *__restrict__ sweep_ptr, float *Ht_zero,
-                                                                               const uint8_t *__restrict__ modes, float temp_x) {
+                                                                               const uint8_t *__restrict__ modes, float temp_x, int pdl) {
     extern __shared__ __align__(16) uint8_t dsm[];
-    const uint32_t sweep = *sweep_ptr;
+    const uint32_t sweep = *sweep_ptr;   // bumped by the kernel at the end of the previous sweep, several launches back
     const int rpc = blockDim.x >> 5;                                   // replicas (warps) per CTA
     float *Jt = reinterpret_cast<float *>(dsm);                        // [kBlk j][kBlk k] = J[c0+k][c0+j] (transposed)
     float *fld = Jt + (size_t)kBlk * kBlk;                             // [rpc][kFldStride]  running fields
@@ -409,16 +430,6 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
     float *srow = spn + rep * kFldStride;
     const bool active = r < R_pad;
     if (active) {
-        // fields of the replica: lane -> sites lane + 32 q (the warps of a CTA read the same 32-byte sectors of Ht)
-        float hv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) hv[q] = Ht[(size_t)(c0 + lane + 32 * q) * R_pad + r] + hf[c0 + lane + 32 * q];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) frow[lane + 32 * q] = hv[q];
-        // the next block's split-K GEMM accumulates with atomics: clear its field rows for this replica
-        if (Ht_zero != nullptr)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) Ht_zero[(size_t)(lane + 32 * q) * R_pad + r] = 0.f;
         // spins and thresholds of the lane's four sites 4*lane .. 4*lane+3
         const uint2 sv = *reinterpret_cast<const uint2 *>(S + (size_t)r * n_pad + c0 + 4 * lane);   // 256 B per warp
         const uint16_t s16[4] = {(uint16_t)(sv.x & 0xffffu), (uint16_t)(sv.x >> 16), (uint16_t)(sv.y & 0xffffu), (uint16_t)(sv.y >> 16)};
@@ -447,6 +458,24 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
         }
         *reinterpret_cast<float4 *>(trow + 4 * lane) = make_float4(th[0], th[1], th[2], th[3]);
         *reinterpret_cast<float4 *>(srow + 4 * lane) = make_float4(so[0], so[1], so[2], so[3]);
+    }
+    if (pdl) {
+        // everything above (coupling block, spins of this block, thresholds) is independent of the field GEMM that runs
+        // just before this kernel: with programmatic stream serialization it overlapped that GEMM.  The fields are not.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (pdl > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
+    if (active) {
+        // fields of the replica: lane -> sites lane + 32 q (the warps of a CTA read the same 32-byte sectors of Ht)
+        float hv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hv[q] = Ht[(size_t)(c0 + lane + 32 * q) * R_pad + r] + hf[c0 + lane + 32 * q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) frow[lane + 32 * q] = hv[q];
+        // the next block's split-K GEMM accumulates with atomics: clear its field rows for this replica
+        if (Ht_zero != nullptr)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Ht_zero[(size_t)(lane + 32 * q) * R_pad + r] = 0.f;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
@@ -757,17 +786,26 @@ static int enqueue_sweep(nlmc_dense *D, int k_splits) {
     // block (the correction, 16 CTAs for two k-blocks) and the extra dependency edges cost more than the overlap hides.
     // Kept behind a switch; the default is the plain GEMM -> update chain.
     const bool look_ahead = nb > 1 && getenv("NLMC_DENSE_LOOKAHEAD") != nullptr;
+    // Programmatic dependent launch of the GEMM -> update chain (the update's coupling-block staging and thresholds overlap
+    // the GEMM, a 2-stage GEMM CTA and an update CTA fit on one SM together): measured 0.455 ms per sweep against 0.357 ms
+    // with plain stream order on B200 at C3 size, so it is off unless NLMC_DENSE_PDL is set.
+    const bool pdl = getenv("NLMC_DENSE_PDL") != nullptr;
     auto launch_update = [&](int b, float *zero_rows) {
-        dense_block_update_kernel<<<(unsigned)((D->R_pad + D->upd_rpc - 1) / D->upd_rpc), (unsigned)(32 * D->upd_rpc),
-                                    update_smem_bytes(D->upd_rpc), D->stream>>>(
-            D->n, D->n_pad, D->R_pad, b * kBlk, D->Ht, D->Jf, D->hf, D->beta, D->S, (uint32_t)D->seed, (uint32_t)(D->seed >> 32),
-            D->d_sweep, zero_rows, D->modes_on ? D->modes : nullptr, D->temp_x);
+        launch_pdl(dense_block_update_kernel, dim3((unsigned)((D->R_pad + D->upd_rpc - 1) / D->upd_rpc)), dim3((unsigned)(32 * D->upd_rpc)),
+                   update_smem_bytes(D->upd_rpc), D->stream, pdl && !look_ahead, D->n, D->n_pad, D->R_pad, b * kBlk, (const float *)D->Ht,
+                   (const float *)D->Jf, (const float *)D->hf, (const float *)D->beta, D->S, (uint32_t)D->seed, (uint32_t)(D->seed >> 32),
+                   (const uint32_t *)D->d_sweep, zero_rows, (const uint8_t *)(D->modes_on ? D->modes : nullptr), D->temp_x,
+                   (int)((pdl && !look_ahead) ? (getenv("NLMC_DENSE_PDL_EARLY") ? 2 : 1) : 0));
     };
     int rc;
     if (!look_ahead) {
+        const char *skip = getenv("NLMC_DENSE_SKIP");   // timing experiments only: "gemm" or "update"
         for (int b = 0; b < nb; ++b) {
-            if ((rc = launch_fields_part(D, D->stream, b * kBlk, kBlk, k_splits, /*clear=*/b == 0, 0, kb_all, 0, 0, 3))) return rc;
-            launch_update(b, (k_splits > 1 && b + 1 < nb) ? D->Ht + (size_t)(b + 1) * kBlk * D->R_pad : nullptr);
+            if (!(skip && skip[0] == 'g'))
+                if ((rc = launch_fields_part(D, D->stream, b * kBlk, kBlk, k_splits, /*clear=*/b == 0, 0, kb_all, 0, 0, (pdl || getenv("NLMC_DENSE_STAGES2")) ? 2 : 3,
+                                             pdl && b > 0))) return rc;
+            if (!(skip && skip[0] == 'u'))
+                launch_update(b, (k_splits > 1 && b + 1 < nb) ? D->Ht + (size_t)(b + 1) * kBlk * D->R_pad : nullptr);
         }
     } else {
         size_t ev = 0;
