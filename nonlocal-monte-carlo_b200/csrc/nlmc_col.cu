@@ -11,7 +11,9 @@
 // CSR itself when it fits (uint16/int32 columns, int32 values).  Fields are INT32 FIXED POINT (scale 2^s with s
 // chosen so that max_i(|h_i| + sum_j |J_ij|) * 2^s < 2^30) and are maintained INCREMENTALLY: a flip adds
 // 2 J_ij s_i to its neighbours' fields with ATOMS.ADD -- the only shared-memory atomic add the hardware has
-// natively (fp64, u64 and fp32 adds compile to CAS spin loops; checked in SASS).  Integer arithmetic means no
+// natively (fp64, u64 and fp32 adds compile to CAS spin loops).  Checked in the SASS of this file: every shared-state
+// instantiation (kGlobalState = false) has `ATOMS.ADD RZ`, the global-workspace ones `REDG.E.ADD.STRONG.GPU`; in round 1
+// the state pointer was a run-time choice, which made it generic and turned every field update into a global atomic.  Integer arithmetic means no
 // drift and, for integer J, exact fields and energies.  Each site is served by a group of lanes (a power of two,
 // chosen so that one colour fills the CTA): every lane of the group takes the same decision and the lanes split
 // the neighbour list of a flip.  A whole batch of sweeps is one launch: per-sweep energies
@@ -102,16 +104,17 @@ struct ColArgs {
     int R;
 };
 
-template <bool kSmemCsr, typename ColT, typename ValT>
+// kGlobalState = false: the replica's state (fields, spins, modes, optionally the CSR) lives in SHARED memory and the
+// field updates compile to native shared atomics (ATOMS.ADD); true: instances too large for shared memory keep it in a
+// slice of a global workspace -- same code, the atomics go to L2 (ATOM.E.ADD) and reads bypass the incoherent L1.
+template <bool kSmemCsr, typename ColT, typename ValT, bool kGlobalState>
 __global__ void __launch_bounds__(kColThreadsFew) col_sweep_kernel(ColArgs a) {
     constexpr bool kVal8 = sizeof(ValT) == 1;  // integer couplings stored as int8 and shifted into fixed point at use
     extern __shared__ __align__(16) uint8_t sm[];
     __shared__ long long red[kColThreadsFew / 32];
     __shared__ double s_E;
     const int n = a.n, tid = threadIdx.x, r = blockIdx.x, nthr = (int)blockDim.x;
-    // state of this replica: shared memory, or (instances too large for it) a slice of a global workspace -- same code,
-    // the atomics on the fields then go to L2
-    uint8_t *state = a.state_ws ? a.state_ws + (size_t)blockIdx.x * a.state_stride : sm;
+    uint8_t *state = kGlobalState ? a.state_ws + (size_t)blockIdx.x * a.state_stride : sm;
     int32_t *fld = reinterpret_cast<int32_t *>(state);                 // [n] fixed-point local fields (incl. h)
     int32_t *hfx = fld + n;                                            // [n] fixed-point h
     int32_t *rp_s = hfx + n;
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(kColThreadsFew) col_sweep_kernel(ColArgs a) {
     }
     __syncthreads();
     // in the global-workspace variant other threads' atomics and stores land in L2: read around the (incoherent) L1
-    const bool gstate = a.state_ws != nullptr;
+    constexpr bool gstate = kGlobalState;
     auto ld_fld = [&](int i) -> int { return gstate ? __ldcg(fld + i) : fld[i]; };
     auto ld_spin = [&](int i) -> int { return gstate ? (int)__ldcg(reinterpret_cast<const signed char *>(spin) + i) : (int)spin[i]; };
     auto row_begin = [&](int i) { return kSmemCsr ? rp_s[i] : a.rp[i]; };
@@ -515,10 +518,15 @@ int nlmc_col_sweep(nlmc_col *Cc, int n_sweeps, const double *beta_sched, int rec
     a.out_spins = d_rec; a.out_E = d_E; a.bestE = track_best ? Cc->bestE : nullptr; a.bestS = Cc->bestS; a.R = Cc->R;
     cudaError_t e = cudaSuccess;
     const int smem = (int)Cc->smem_bytes;
-#define NLMC_COL_LAUNCH(SMEM, COLT, VALT)                                                                              \
+#define NLMC_COL_LAUNCH_G(SMEM, COLT, VALT, GST)                                                                       \
     do {                                                                                                              \
-        e = cudaFuncSetAttribute(col_sweep_kernel<SMEM, COLT, VALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-        if (e == cudaSuccess) col_sweep_kernel<SMEM, COLT, VALT><<<(unsigned)R, (unsigned)Cc->threads, smem, Cc->stream>>>(a);  \
+        e = cudaFuncSetAttribute(col_sweep_kernel<SMEM, COLT, VALT, GST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+        if (e == cudaSuccess) col_sweep_kernel<SMEM, COLT, VALT, GST><<<(unsigned)R, (unsigned)Cc->threads, smem, Cc->stream>>>(a);  \
+    } while (0)
+#define NLMC_COL_LAUNCH(SMEM, COLT, VALT)                                              \
+    do {                                                                              \
+        if (Cc->state_ws) NLMC_COL_LAUNCH_G(SMEM, COLT, VALT, true);                  \
+        else NLMC_COL_LAUNCH_G(SMEM, COLT, VALT, false);                              \
     } while (0)
     if (Cc->csr_in_smem && Cc->small_cols) {
         if (Cc->int8_vals) NLMC_COL_LAUNCH(true, uint16_t, int8_t); else NLMC_COL_LAUNCH(true, uint16_t, int32_t);
@@ -528,6 +536,7 @@ int nlmc_col_sweep(nlmc_col *Cc, int n_sweeps, const double *beta_sched, int rec
         if (Cc->int8_vals) NLMC_COL_LAUNCH(false, int32_t, int8_t); else NLMC_COL_LAUNCH(false, int32_t, int32_t);
     }
 #undef NLMC_COL_LAUNCH
+#undef NLMC_COL_LAUNCH_G
     if (e == cudaSuccess) e = cudaGetLastError();
     Cc->sweep_counter += (uint32_t)n_sweeps;
     if (e == cudaSuccess && d_rec) e = cudaMemcpyAsync(out_spins, d_rec, n_rec * R * n, cudaMemcpyDeviceToHost, Cc->stream);
