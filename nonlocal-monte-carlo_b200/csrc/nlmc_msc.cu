@@ -303,76 +303,95 @@ __global__ void msc_init_kernel(MscDev a, uint32_t stream_id) {
 constexpr int kEnergyChunk = 128;  // at most 128 sites per warp: 128 sites * 6 bonds < 2^10
 // On a two-colourable graph every bond joins the two colour classes, so the sites of ONE class see every bond exactly
 // once: the launcher then passes only that class (n_list sites of site_list) and the finish kernel doubles the sum.
-__global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_acc, int chunk, int n_list) {
-    int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
+// Work item = (chunk of `chunk` sites, 128-word chunk of the row); a warp takes one item (W >= 128) or, for short rows, one
+// item per sub-group of qpc lanes.  A CTA loops over items with a grid stride and gathers its counts in SHARED memory
+// (native shared atomics), so that every (word, lane) address of E_acc receives one global atomic per CTA instead of one
+// per item -- with 16-word rows (a block of a ladder sharded over 8 GPUs) the per-item global atomics of round 1 piled
+// 4.2 M updates onto 512 addresses and the kernel took longer than the 16 sweeps of the round.
+__global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_acc, int chunk, int n_list, int use_smem) {
+    extern __shared__ int32_t acc_s[];  // [W * 32] when use_smem
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (use_smem) {
+        for (int i = tid; i < a.W * 32; i += 128) acc_s[i] = 0;
+        __syncthreads();
+    }
     const int chunks = (a.W + 127) >> 7;
     const int site_chunks = (n_list + chunk - 1) / chunk;
-    int word0;
+    const long long n_items = (long long)site_chunks * chunks;
+    int sub = 0, spw = 1, word_in = lane * 4;
+    bool lane_on = true;
     if (a.W < 128) {  // short rows: the sub-groups of a warp take different site chunks (chunks == 1)
-        const int sub = lane / a.qpc;
-        if (sub >= a.spw) return;
-        warp = warp * a.spw + sub;
-        word0 = (lane - sub * a.qpc) * 4;
-    } else {
-        word0 = (warp % chunks) * 128 + lane * 4;
+        sub = lane / a.qpc;
+        spw = a.spw;
+        lane_on = sub < a.spw;
+        word_in = (lane - sub * a.qpc) * 4;
     }
-    if (warp >= site_chunks * chunks) return;
-    if (word0 >= a.W) return;
-    const int s_begin = (warp / chunks) * chunk, s_end = min(n_list, s_begin + chunk);
-    uint32_t v[4][10];
+    for (long long g = ((long long)blockIdx.x * 4 + warp) * spw + sub; lane_on && g < n_items; g += (long long)gridDim.x * 4 * spw) {
+        const int word0 = (a.W < 128) ? word_in : (int)(g % chunks) * 128 + word_in;
+        if (word0 >= a.W) continue;
+        const int s_begin = (int)(g / chunks) * chunk, s_end = min(n_list, s_begin + chunk);
+        uint32_t v[4][10];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int bb = 0; bb < 10; ++bb) v[k][bb] = 0u;
-    for (int s = s_begin; s < s_end; ++s) {
-        const int4 r0 = __ldg(a.rec + (size_t)s * 2), r1 = __ldg(a.rec + (size_t)s * 2 + 1);
-        const int nb[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
-        const uint32_t meta = (uint32_t)r1.z;
-        const int site = r1.w;
-        const uint4 own = *reinterpret_cast<const uint4 *>(a.S + (size_t)site * a.W + word0);
-        uint4 x[6];
+            for (int bb = 0; bb < 10; ++bb) v[k][bb] = 0u;
+        for (int s = s_begin; s < s_end; ++s) {
+            const int4 r0 = __ldg(a.rec + (size_t)s * 2), r1 = __ldg(a.rec + (size_t)s * 2 + 1);
+            const int nb[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+            const uint32_t meta = (uint32_t)r1.z;
+            const int site = r1.w;
+            const uint4 own = *reinterpret_cast<const uint4 *>(a.S + (size_t)site * a.W + word0);
+            uint4 x[6];
 #pragma unroll
-        for (int d = 0; d < 6; ++d) {
-            const int j = nb[d];
-            if (j >= 0) {
-                x[d] = *reinterpret_cast<const uint4 *>(a.S + (size_t)j * a.W + word0);
-                const uint32_t neg = ((meta >> d) & 1u) ? 0xffffffffu : 0u;
-                // unsatisfied <=> J*s_i*s_j = -1 <=> s_i xor s_j xor [J<0]
-                x[d].x ^= own.x ^ neg; x[d].y ^= own.y ^ neg; x[d].z ^= own.z ^ neg; x[d].w ^= own.w ^ neg;
-            } else {
-                x[d] = make_uint4(0u, 0u, 0u, 0u);
+            for (int d = 0; d < 6; ++d) {
+                const int j = nb[d];
+                if (j >= 0) {
+                    x[d] = *reinterpret_cast<const uint4 *>(a.S + (size_t)j * a.W + word0);
+                    const uint32_t neg = ((meta >> d) & 1u) ? 0xffffffffu : 0u;
+                    // unsatisfied <=> J*s_i*s_j = -1 <=> s_i xor s_j xor [J<0]
+                    x[d].x ^= own.x ^ neg; x[d].y ^= own.y ^ neg; x[d].z ^= own.z ^ neg; x[d].w ^= own.w ^ neg;
+                } else {
+                    x[d] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t c0, c1, c2;
+                count6(comp(x[0], k), comp(x[1], k), comp(x[2], k), comp(x[3], k), comp(x[4], k), comp(x[5], k), c0, c1, c2);
+                // ripple-add the 3-bit count into the 10-bit vertical counter
+                uint32_t carry = v[k][0] & c0;
+                v[k][0] ^= c0;
+                uint32_t t = v[k][1] ^ c1 ^ carry;
+                carry = maj3(v[k][1], c1, carry);
+                v[k][1] = t;
+                t = v[k][2] ^ c2 ^ carry;
+                carry = maj3(v[k][2], c2, carry);
+                v[k][2] = t;
+#pragma unroll
+                for (int bb = 3; bb < 10; ++bb) {
+                    t = v[k][bb] & carry;
+                    v[k][bb] ^= carry;
+                    carry = t;
+                }
             }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            uint32_t c0, c1, c2;
-            count6(comp(x[0], k), comp(x[1], k), comp(x[2], k), comp(x[3], k), comp(x[4], k), comp(x[5], k), c0, c1, c2);
-            // ripple-add the 3-bit count into the 10-bit vertical counter
-            uint32_t carry = v[k][0] & c0;
-            v[k][0] ^= c0;
-            uint32_t t = v[k][1] ^ c1 ^ carry;
-            carry = maj3(v[k][1], c1, carry);
-            v[k][1] = t;
-            t = v[k][2] ^ c2 ^ carry;
-            carry = maj3(v[k][2], c2, carry);
-            v[k][2] = t;
+            for (int l = 0; l < 32; ++l) {
+                int val = 0;
 #pragma unroll
-            for (int bb = 3; bb < 10; ++bb) {
-                t = v[k][bb] & carry;
-                v[k][bb] ^= carry;
-                carry = t;
+                for (int bb = 0; bb < 10; ++bb) val |= (int)((v[k][bb] >> l) & 1u) << bb;
+                if (val) {
+                    if (use_smem) atomicAdd(acc_s + (word0 + k) * 32 + l, val);
+                    else atomicAdd(E_acc + (size_t)(word0 + k) * 32 + l, val);
+                }
             }
         }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        for (int l = 0; l < 32; ++l) {
-            int val = 0;
-#pragma unroll
-            for (int bb = 0; bb < 10; ++bb) val |= (int)((v[k][bb] >> l) & 1u) << bb;
-            if (val) atomicAdd(E_acc + (size_t)(word0 + k) * 32 + l, val);
-        }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = tid; i < a.W * 32; i += 128)
+            if (acc_s[i]) atomicAdd(E_acc + i, acc_s[i]);
     }
 }
 
@@ -630,18 +649,21 @@ static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
 static int launch_energy(nlmc_msc *M) {
     const MscDev d = dev_view(M);
     const int chunks = (M->W + 127) / 128;
-    // sites per warp: as many as the 10-bit counters allow on big lattices, fewer on small ones so that the
-    // grid still fills the GPU (about 8 warps per SM)
     const bool bipartite = M->n_colours == 2;  // one colour class sees every bond once
     const int n_list = bipartite ? M->colour_ptr[1] : M->n;
-    const int groups = 148 * 8 * (M->W < 128 ? d.spw : 1);  // short rows: spw site chunks per warp
-    const int sites_for_fill = (int)(((long long)n_list * chunks + groups - 1) / groups);
-    const int chunk = std::max(16, std::min(kEnergyChunk, sites_for_fill));
+    const int spw = M->W < 128 ? d.spw : 1;
+    // sites per item: as many as the 10-bit counters allow on big lattices (fewer flushes), fewer on small ones so that
+    // there are still about two items per warp slot of a grid of 148 x 8 CTAs
+    const long long slots = 148LL * 8 * 4 * spw * 2;
+    const int chunk = (int)std::max(8LL, std::min((long long)kEnergyChunk, ((long long)n_list * chunks + slots - 1) / slots));
     const int site_chunks = (n_list + chunk - 1) / chunk;
+    const long long items = (long long)site_chunks * chunks;
+    const long long ctas_needed = (items + 4LL * spw - 1) / (4LL * spw);
+    const unsigned grid = (unsigned)std::max(1LL, std::min(ctas_needed, 148LL * 8));
+    const size_t smem = sizeof(int32_t) * (size_t)M->W * 32;
+    const int use_smem = smem <= 40 * 1024 ? 1 : 0;   // rows of up to 320 words; longer ones add straight into E_acc
     NLMC_CUDA(cudaMemsetAsync(M->E_acc, 0, sizeof(int32_t) * (size_t)M->W * 32, M->stream));
-    long long warps = (long long)site_chunks * chunks;
-    if (M->W < 128) warps = (warps + d.spw - 1) / d.spw;  // short rows: spw site chunks per warp
-    msc_energy_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, M->stream>>>(d, M->E_acc, chunk, n_list);
+    msc_energy_kernel<<<grid, 128, use_smem ? smem : 0, M->stream>>>(d, M->E_acc, chunk, n_list, use_smem);
     msc_energy_finish_kernel<<<(M->W * 32 + 255) / 256, 256, 0, M->stream>>>(M->W, M->G, M->n_ladders, M->n_bonds,
                                                                             bipartite ? 2 : 1, M->E_acc, M->E);
     NLMC_CUDA(cudaGetLastError());
