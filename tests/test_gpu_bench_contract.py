@@ -23,3 +23,10 @@ def test_bench_prints_the_contract_line():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
     assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["gpu_launches"] > 0 and "workload" in line["config"]
+    # a roofline fraction is a fraction; the strong-scaling line carries the sustained leg and the time-to-target rows
+    assert 0 < line["roofline"]["frac"] <= 1.2 and line["roofline"]["bound"] == "hbm"
+    assert line["scaling"] == "strong" and line["sustained"]["seconds"] >= 4.0 and line["sustained"]["clocks"] is not None
+    ttt = line["time_to_target"]
+    assert len(ttt) == 3 and all(r["gpu_median_s"] > 0 and r["cpu_median_s"] > 0 for r in ttt)
+    assert any("Wishart" in r["instance"] for r in ttt)
+    assert "NPT(J, h, mode='production').run" in line["e2e"]["api"] and line["e2e_host_buffers"]["value"] > 0
