@@ -22,6 +22,7 @@
 #include <stdint.h>
 #ifdef __CUDACC__
 #define NLMC_NPM_FN __device__ __forceinline__
+#define NLMC_NPM_UNROLL _Pragma("unroll")
 #define NLMC_NPM_TABLE static __device__ const
 #define NLMC_NPM_FMA(a, b, c) __fma_rn((a), (b), (c))
 #define NLMC_NPM_ADD(a, b) __dadd_rn((a), (b))
@@ -33,6 +34,7 @@
 #include <math.h>
 #include <string.h>
 #define NLMC_NPM_FN static inline
+#define NLMC_NPM_UNROLL
 #define NLMC_NPM_TABLE static const
 #define NLMC_NPM_FMA(a, b, c) fma((a), (b), (c))
 #define NLMC_NPM_ADD(a, b) ((a) + (b))
@@ -149,28 +151,32 @@ NLMC_NPM_TABLE uint32_t nlmc_npm_rcp_steps[16] = {
     0x5c990, 0x6c160, 0x7d070, 0x8f9d0, 0xa41a0, 0xbad10, 0xd41c0, 0xf0820,
 };
 
-/* np.tanh(x), float64 (simd_tanh_f64). */
-NLMC_NPM_FN double nlmc_np_tanh(double x)
+/* np.tanh(x), float64 (simd_tanh_f64); `lut` is nlmc_npm_tanh_lut or a copy of it (e.g. in shared memory). */
+NLMC_NPM_FN double nlmc_np_tanh_lut(double x, const uint64_t *lut)
 {
     const uint64_t u = NLMC_NPM_D2U(x);
     const uint64_t au = u & 0x7fffffffffffffffull;
     if (au > 0x7ff0000000000000ull) return NLMC_NPM_U2D(0x7ff8000000000000ull);
     const uint64_t top = u & 0x7ff8000000000000ull;            /* exponent + first mantissa bit */
     double r;
-    if (top > 0x7fe0000000000000ull) {
-        r = 1.0;                                                /* infinities and the top half-binade */
+    if (au >= 0x4038000000000000ull) {
+        /* |x| >= 24: the last interval's polynomial is the constant 1 (c0 = 1, c1..c16 = 0), as is the routine's answer for
+         * infinities and the top half-binade -- skip the 17 multiply-adds (frozen spins of the NMC phases sit at 1e4) */
+        r = 1.0;
     } else {
         int64_t d = (int64_t)top - (int64_t)0x3fc0000000000000ull;
         int32_t hi = (int32_t)(d >> 32);
         hi = hi < 0 ? 0 : (hi > 0x780000 ? 0x780000 : hi);
         const int idx = hi >> 19;                               /* 0: |x| < 3/16 ... 15: |x| >= 24 */
-        const double y = NLMC_NPM_SUB(NLMC_NPM_U2D(au), NLMC_NPM_U2D(nlmc_npm_tanh_lut[idx]));
-        r = NLMC_NPM_U2D(nlmc_npm_tanh_lut[17 * 16 + idx]);
-#pragma unroll
-        for (int k = 16; k >= 1; --k) r = NLMC_NPM_FMA(r, y, NLMC_NPM_U2D(nlmc_npm_tanh_lut[k * 16 + idx]));
+        const double y = NLMC_NPM_SUB(NLMC_NPM_U2D(au), NLMC_NPM_U2D(lut[idx]));
+        r = NLMC_NPM_U2D(lut[17 * 16 + idx]);
+NLMC_NPM_UNROLL
+        for (int k = 16; k >= 1; --k) r = NLMC_NPM_FMA(r, y, NLMC_NPM_U2D(lut[k * 16 + idx]));
     }
     return NLMC_NPM_U2D(NLMC_NPM_D2U(r) | (u & 0x8000000000000000ull));
 }
+
+NLMC_NPM_FN double nlmc_np_tanh(double x) { return nlmc_np_tanh_lut(x, nlmc_npm_tanh_lut); }
 
 /* VRCP14PD(y) rounded to 1+4 mantissa bits (add 2^47 to the bit pattern, keep the top 16 bits), y normal > 0.
  * k = number of steps at or below the top 20 mantissa bits of y; the rounded reciprocal is
@@ -179,7 +185,7 @@ NLMC_NPM_FN uint64_t nlmc_npm_rcp_1p4(uint64_t ybits)
 {
     const uint32_t p = (uint32_t)((ybits >> 32) & 0xfffffu);
     int k = 0;
-#pragma unroll
+NLMC_NPM_UNROLL
     for (int i = 0; i < 16; ++i) k += (p >= nlmc_npm_rcp_steps[i]) ? 1 : 0;
     const uint64_t e = (ybits >> 52) & 0x7ffu;
     return ((uint64_t)(2046u - e - (k > 0 ? 1u : 0u)) << 52) | ((uint64_t)((16 - k) & 15) << 48);
@@ -214,7 +220,7 @@ NLMC_NPM_FN double nlmc_np_arctanh(double x)
     const double th = NLMC_NPM_SUB(NLMC_NPM_U2D(nlmc_npm_atanh_thi[im]), NLMC_NPM_U2D(nlmc_npm_atanh_thi[ip]));
     double pp = NLMC_NPM_FMA(NLMC_NPM_U2D(nlmc_npm_atanh_poly[0]), qp, NLMC_NPM_U2D(nlmc_npm_atanh_poly[1]));
     double pm = NLMC_NPM_FMA(NLMC_NPM_U2D(nlmc_npm_atanh_poly[0]), qm, NLMC_NPM_U2D(nlmc_npm_atanh_poly[1]));
-#pragma unroll
+NLMC_NPM_UNROLL
     for (int k = 2; k < 9; ++k) {
         pp = NLMC_NPM_FMA(qp, pp, NLMC_NPM_U2D(nlmc_npm_atanh_poly[k]));
         pm = NLMC_NPM_FMA(qm, pm, NLMC_NPM_U2D(nlmc_npm_atanh_poly[k]));

@@ -52,7 +52,13 @@ __device__ __forceinline__ void st_spin(int8_t *m, int i, int v) {
 
 // np.tanh(y) in fp64, bit for bit (nlmc_npmath.h restates numpy's float64 routine).  For |y| >= 24 it is exactly
 // +-1, which is the case of every spin frozen by h = +-1e4 in the NMC phases (nmc.py:381,400).
-__device__ __forceinline__ double tanh_sat(double y) { return nlmc_np_tanh(y); }
+// The 288-entry table of the routine is staged in shared memory by the replay kernels: one warp per chain is latency
+// bound, and 18 dependent-address loads from global memory per attempt cost more than the whole rest of the step.
+__device__ __forceinline__ double tanh_sat(double y, const uint64_t *lut) { return nlmc_np_tanh_lut(y, lut); }
+__device__ __forceinline__ void stage_tanh_lut(uint64_t *dst) {
+    for (int i = threadIdx.x; i < 288; i += blockDim.x) dst[i] = nlmc_npm_tanh_lut[i];
+    __syncthreads();
+}
 
 // Storage-order accumulation of 32 per-lane products: the lanes park them in shared memory, then every lane
 // reads all 32 back (loads issued together, not interleaved with the adds) and runs the same dependent add chain
@@ -75,7 +81,9 @@ __device__ __forceinline__ double ordered_sum32(double acc, double prod, int cou
 template <bool kSmem>
 __global__ void __launch_bounds__(32) sweep_replay_kernel(ReplayArgs a) {
     __shared__ __align__(16) double scratch[32];
+    __shared__ uint64_t s_tlut[288];
     extern __shared__ __align__(16) int8_t smem_spins[];
+    stage_tanh_lut(s_tlut);
     const int r = blockIdx.x;
     const int lane = threadIdx.x;
     const int n = a.n;
@@ -146,7 +154,7 @@ __global__ void __launch_bounds__(32) sweep_replay_kernel(ReplayArgs a) {
                 if (lut != nullptr && exact && h_k == 0.0 && fabs(rowsum) <= (double)a.lut_half)
                     t = lut[(int)rowsum + a.lut_half];
                 else
-                    t = tanh_sat(__dmul_rn(beta, x));
+                    t = tanh_sat(__dmul_rn(beta, x), s_tlut);
                 // np.sign(np.tanh(beta*x) - 2*rand() + 1)   (nmc.py:87)
                 const double v = __dadd_rn(__dsub_rn(t, __dmul_rn(2.0, u_a)), 1.0);
                 const int nw = (v > 0.0) - (v < 0.0);
@@ -196,6 +204,8 @@ __global__ void __launch_bounds__(32) sweep_replay_int_kernel(ReplayArgs a, cons
     extern __shared__ __align__(16) uint8_t sm_raw[];
     __shared__ __align__(16) double scratch[32];
     __shared__ double div_tab[256];  // fl(v / temp_x) for every int8 coupling value v: no fp64 division per entry
+    __shared__ uint64_t s_tlut[288];
+    stage_tanh_lut(s_tlut);
     const int n = a.n;
     const int lut_w = 2 * a.lut_half + 1;
     // carve: lut (double) | fields (int32) | row_ptr (int32) | col | val (int8) | spins (int8) | mode (uint8)
@@ -253,14 +263,14 @@ __global__ void __launch_bounds__(32) sweep_replay_int_kernel(ReplayArgs a, cons
                     t = lut_s[f + a.lut_half];
                 } else if (!(md & 2)) {
                     const double h_k = (md & 1) ? h_eff[k] : 0.0;
-                    t = tanh_sat(__dmul_rn(beta, __dadd_rn((double)f, h_k)));
+                    t = tanh_sat(__dmul_rn(beta, __dadd_rn((double)f, h_k)), s_tlut);
                 } else {
                     // Rescaled row (NMC backbone at beta/temp_x).  The reference's field is the storage-order sum of
                     // fl(J/temp_x)*m; it differs from f/temp_x (f = the exact integer field) by a few ulps only, so the
                     // decision sign(t - 2u + 1) is screened with f/temp_x first and the dependent fp64 add chain over
                     // the row is walked only when u lies within 1e-9 of the threshold (where those ulps could matter).
                     const double xa = __dadd_rn(__ddiv_rn((double)f, temp_x), h_eff[k]);
-                    t = tanh_sat(__dmul_rn(beta, xa));
+                    t = tanh_sat(__dmul_rn(beta, xa), s_tlut);
                     if (fabs(__dadd_rn(__dsub_rn(t, __dmul_rn(2.0, u_a)), 1.0)) <= 1e-9) {
                         double x = 0.0;
                         const int re = rp_s[k + 1];
@@ -270,7 +280,7 @@ __global__ void __launch_bounds__(32) sweep_replay_int_kernel(ReplayArgs a, cons
                             if (p < re) prod = __dmul_rn(div_tab[(int)val_s[p] + 128], (double)m[col_s[p]]);
                             x = ordered_sum32(x, prod, min(32, re - pb), scratch, lane);
                         }
-                        t = tanh_sat(__dmul_rn(beta, __dadd_rn(x, h_eff[k])));
+                        t = tanh_sat(__dmul_rn(beta, __dadd_rn(x, h_eff[k])), s_tlut);
                     }
                 }
                 const double v = __dadd_rn(__dsub_rn(t, __dmul_rn(2.0, u_a)), 1.0);  // nmc.py:87
