@@ -1,11 +1,21 @@
-# DESIGN — nlmc_b200
+"""One-off editor used in round 2 to bring DESIGN.md up to date section by section (kept for the record; running it on
+an already updated file is a no-op because the section markers it looks for are gone)."""
+import sys
 
-B200-native (sm_100a CUDA) implementation of the Monte Carlo hot path behind
-`NMC(J,h).run`, `NPT(J,h).run`, `APT_preprocessor(J,h).run` and `APT_ICM(J,h).run` of
-usra-riacs/Nonlocal-Monte-Carlo, as a drop-in behind the reference's own class API.
-File:line citations are into the reference checkout (`/root/reference/`).
+p = "DESIGN.md"
+s = open(p).read()
 
-## 0. Scope and status after round 2
+
+def replace_section(s, start_marker, end_marker, new):
+    if start_marker not in s:
+        return s
+    a = s.index(start_marker)
+    b = s.index(end_marker, a + len(start_marker))
+    return s[:a] + new + s[b:]
+
+
+# ------------------------------------------------------------------ section 0
+s = replace_section(s, "## 0. Scope (SURVEY.md §8) and status after round 1", "## 1. The path and its boundary", '''## 0. Scope (SURVEY.md §8) and status after round 2
 
 | §8 row | What | Status |
 |---|---|---|
@@ -31,70 +41,10 @@ File:line citations are into the reference checkout (`/root/reference/`).
 
 Open items are listed in §9.
 
-## 1. The path and its boundary
+''')
 
-The reference is pure Python; its hot path is the heat-bath sweep
-`m[kk] = sign(tanh(beta*x[kk]) - 2*rand() + 1)` (`NMC/nmc.py:86-87`; identical copies at
-`NPT/npt.py:105-106`, `NPT/apt_preprocessor.py:69-70`, `NPT/apt_ICM.py:88-89`), the energy loops
-(`nmc.py:386-387`, `npt.py:40-43`), LBP (`nmc.py:168-228`), the PT swap (`npt.py:652-680`) and the
-Houdayer cluster search (`apt_ICM.py:116-143`).  There is no FFI in the reference: the drop-in boundary
-is the Python class API (`NMC/nmc.py:18,442`, `NPT/npt.py:21,535`, `NPT/apt_preprocessor.py:13,115`,
-`NPT/apt_ICM.py:19,145`).  Besides `run()` the classes expose the pieces of the path as public methods
-(`MCMC`, `LoopyBeliefPropagation`, `LBP_convexified`, `find_clusters`, `NMC_subroutine`, `MCMC_task`, `NMC_task`,
-`replica_energy`, `find_disagreement_clusters`); `path_methods.py` mirrors each with the reference's argument list and
-return tuple on the same kernels.  `LoopyBeliefPropagation` takes and returns the reference's dense N×N message
-matrices: the host maps them onto the stored entries of J plus one off-entry value per row (exactly the structure the
-reference's own matrices have) and adds explicit zero entries for any input message that does not fit that structure,
-so arbitrary dense inputs are reproduced too (`tests/test_gpu_public_methods.py`).  `h_tilde`/`J_tilde` are
-`atanh(x)/β` of saturating quantities; they are compared on `x` (last-place differences of `x` are amplified by
-`1/(1-x²)`).
-
-```
-user code / reference examples / reference unit tests
-        │  same classes, same run() kwargs, same numpy returns, same side-effect files
-nonlocal-monte-carlo_b200/nlmc_b200/{nmc,npt,apt_preprocessor,apt_ICM}.py      host mirror of the classes
-        │  host.py (RNG order, schedules, pair choice)  nmc_core.py (λ loop, find_clusters, phases)
-        │  ctypes  (_lib.py)
-include/nlmc_b200.h  ── C ABI: extern "C", plain pointers + sizes, opaque handles, no torch types
-        │
-nonlocal-monte-carlo_b200/csrc/*.cu  ── hand-written sm_100a kernels (libnlmc_b200.so, built in-tree)
-```
-
-No CPU fallback exists: `_lib.lib()` raises if the `.so` is missing, every entry point fails with
-`NLMC_ERR_CUDA` without a device (`tests/test_host_cpu.py::test_no_cpu_fallback`), and a CPU test greps the
-product tree to prove it never imports `oracle/` (`test_product_does_not_import_oracle`).
-PyTorch is used only in `bench.py`/`distributed.py` (pinned host buffers, `torch.distributed`).
-
-### Two modes
-
-* **replay** (`mode="replay"`, default): the host draws the reference's random stream in the reference's
-  order (global legacy `np.random` MT19937: per sweep one `permutation(N)` then N `rand()`; `random.randint`
-  for pair choice) and injects it into K1.  With `num_cores=1` semantics (one pool worker forked at the
-  first `submit`, emulated by cloning the generator state — SURVEY fact 5) a whole `run()` is
-  **bit-identical** to the reference for the same seeds.
-* **production** (`mode="production"`): Philox4x32-10, graph-coloured parallel updates.  Three engines, chosen by
-  the instance: bit-packed multi-spin coding for ±J lattices (K2), a graph-coloured shared-memory kernel for any
-  sparse J/h (K2a), and the tensor-core path for dense J (K3).  Same single-site conditional distribution and same
-  swap rule → statistically equivalent (tested against exact Boltzmann averages and the reference sampler).
-
-## 2. Oracle (`oracle/`) — parity PINNED
-
-* `oracle/ref_loader.py` imports the unmodified reference in the build container (matplotlib stubbed).
-* `oracle/nlmc_oracle.c` (+ `oracle.py`) is a CPU restatement: sweep, energy, disagreement clusters, and the
-  exact-summation half of LBP; each function cites the reference lines it follows.  The run-level
-  restatements of the four `run()` methods consume the global RNG in reference order.
-* Pinning: `tests/test_oracle_vs_reference.py` (live reference, this container) and
-  `tests/test_oracle_golden.py` (committed vectors, everywhere) are **bit-for-bit** at every level —
-  element (`MCMC`, LBP marginal + iteration count at every λ, clusters), and whole `run()`s of all four
-  classes on reduced versions of the five configs — plus known-answer Wishart ground states from the
-  reference's example data (`*/wishart_small/*/gs_energies.txt`).  Goldens are generated by
-  `oracle/make_golden.py` (committed).
-* numpy orders that matter are reproduced exactly (probed on numpy 2.3.5): `np.sum(u_msgs[:, i])` is a
-  pairwise sum over all N entries of the strided column; `np.sum(u_msgs, axis=0)` is sequential.
-* The reference is pure Python, so there is no `oracle/_ref` binary; it cannot travel to the GPU box, which
-  is why the goldens are committed.
-
-### LBP parity (numpy's `tanh` / `arctanh` restated on the device)
+# ------------------------------------------------------------------ LBP parity
+s = replace_section(s, '### LBP parity (the one place where "bit-exact" is not well defined)', "## 3. Data layout in HBM", '''### LBP parity (numpy's `tanh` / `arctanh` restated on the device)
 
 `LBP_convexified` is called with `tolerance = np.finfo(float).eps` (README, `nmc.py:445`): the loop stops only at an exact
 floating-point fixed point, and "diverged" (`iteration == max_iterations-1`, `nmc.py:142-146`) ends the λ schedule.  Whether a
@@ -127,20 +77,11 @@ oracle's `nmc_run` / `npt_run`); the round-1 backbone override hook and both xfa
 non-integer fields, so Gaussian-J decisions are bit-equal too.  On a host whose numpy takes another code path (no AVX-512)
 the oracle itself would differ from the goldens; the device would not.
 
-## 3. Data layout in HBM
+''')
 
-Exact path (K1/K4/K5/K7): CSR of the normalised J (`int32 row_ptr[n+1]`, `int32 col[nnz]`, `f64 val[nnz]`,
-scipy `csr_matrix(J)` order, uploaded once per instance), `f64 h[n]`; `int8 spins[R][n]` (values −1/0/+1:
-`np.sign` can return 0); per replica optional `f64 h_eff[n]` and `u8 row_scaled[n]` (NMC phases);
-staged `int32 perm[R][S][n]`, `f64 u[R][S][n]`, `f64 beta[R][S]`, optional `f64 tanh_lut[R][S][2·half+1]`.
-
-Production path (K2/K4'/K6): **bit planes**.  A *ladder* is one NPT run (one replica per β).  32 ladders
-share a 32-bit word (bit=1 ⇔ spin +1), all bits of a word at the same β.  `u32 S[site][w]`, `w = b·G + g`
-(β index b, ladder group g, G = ladders/32, ladders padded to a multiple of 128 so a thread's four
-consecutive words share one β).  C5: 262,144 sites × 128 words × 4 B = **134 MB** for 4096 replicas
-(0.125 B per spin), just above the 126 MB L2.  One 32-byte record per site, stored in colour order: six neighbour
-indices (−1 = padding), the coupling-sign bits and the site index (`int32 rec[n][8]`, two 16-byte loads);
-`u32 thr[n_beta][4]` thresholds (one 16-byte load), `f64 E[n_beta][ladders]`.
+# ------------------------------------------------------------------ data layout: add label mode
+s = s.replace('''`u32 thr[n_beta][4]` thresholds (one 16-byte load), `f64 E[n_beta][ladders]`.
+''', '''`u32 thr[n_beta][4]` thresholds (one 16-byte load), `f64 E[n_beta][ladders]`.
 
 β-label form of the same layout (`nlmc_msc_create_labelled`; north_star 4): a handle owns the *slots*
 [slot_begin, slot_begin+count) of a ladder of `n_beta_total` temperatures -- the whole ladder on one GPU, or one contiguous
@@ -153,64 +94,20 @@ GLOBAL slot and ladder indices, so any partition of the slots evolves bit for bi
 
 Generic engines (K2a/K3): `int8 spins[R][n]` / `bf16 S[R_pad][n_pad]`, one β per row; rows grouped into ladders
 (row = ladder·n_beta + slot) with `int32 label[R]`, `slot_of[R]`, `f64 E[R]` for the device-side exchange (`nlmc_exchange.cuh`).
+''')
 
-## 4. Kernels
-
-| Kernel | Replaces | Mapping | Bound | Algorithmic bytes / unit |
-|---|---|---|---|---|
-| K1 `sweep_replay_kernel` | `MCMC` `nmc.py:62-89` | 1 warp / replica; lanes over the row's entries; 32-attempt look-ahead of row extents; spins in SMEM (n ≤ 200 KiB) | latency (sequential by construction) | 12 B/attempt injected stream + (6+13·deg) |
-| K2 `msc_sweep_kernel<6, scalar>` | same, production | 1 warp / (site, 128 words), lane = 4 words (LDG.128/STG.128), one launch per colour, 2D grid (sites × row chunks), 5 CTAs/SM; one 32-byte record per site in colour order (6 neighbours, coupling signs, site) | **integer issue**: 896 warp-instructions per 4096 attempts (Philox 40 %, compare logic, bit-sliced counts), issue slots 62 %, ALU 67 % (ncu, round 2); HBM fraction 0.117 | 0.25 B/attempt (SURVEY 8d bit-packed bound) |
-| K2 `msc_sweep_kernel<6, bit planes[, short rows]>` | same, β-label form / blocks of a sharded ladder | as above with per-lane threshold planes (18 LDG.128 per thread, L1 hits) and, for rows < 128 words, several sites per warp | issue + load latency: 998 instructions per 4096 attempts, 20 % slower than the scalar form | 0.25 B/attempt |
-| K1-int `sweep_replay_int_kernel` | same, integer J that fits in SMEM | CSR (int16 col, int8 val), spins, tanh LUT and **incremental integer fields** in SMEM; row walked only on a flip | latency: 130 ns/attempt (C1) vs 640 ns for K1 | 12 B/attempt injected stream |
-| K3 `gemm_bf16_tn_kernel` | `J.dot(m)` for all replicas, `nmc.py:86` | tcgen05.mma 128×128×16 bf16→fp32 in TMEM, TMA SW128 3-stage ring, warp-specialised (TMA / MMA / 4 epilogue warps), J split in ≤3 bf16 pieces | **tensor pipe** | 2·R·N²·n_split flop per full recompute |
-| K3 `dense_block_update_kernel` | `MCMC` on dense J | 1 warp / replica, one CTA per SM (14 replicas), thresholds θ = logit(u)/2β of the whole block computed up front, 8-site sub-blocks in registers, fully unrolled | issue (R chains): 11.9 µs per block of 128 sites × 2048 replicas | — |
-| K2a `col_sweep_kernel` | `MCMC` on any sparse J, h (production) | 1 CTA / replica (1024 threads when replicas ≤ 2×SMs, else 256), state in SMEM (or in a global workspace above ≈22k spins); greedy colouring, sites of a colour in parallel, a power-of-two lane group per site; **int32 fixed-point fields updated with ATOMS.ADD** (the only native SMEM atomic add; the state location is a template parameter so that the shared-memory variant really compiles to it, checked in SASS); batch of sweeps = 1 launch with in-kernel energies, recording, argmin tracking, annealing schedule | SMEM latency / barriers (ncu: barrier stall 13.3 per issue, profiles/r1_other_kernels_summary.md): 0.9 µs per colour step on C1 with the CSR (int8 values, 16-bit columns) in SMEM and 1024-thread CTAs when replicas ≤ 2×SMs, L2-resident CSR + 8 small CTAs/SM otherwise | — |
-| K4 `energy_kernel` | `nmc.py:386`, `npt.py:40-43` | 1 CTA / state | HBM/L2; 6.4e5 states/s at C1 size incl. the H2D copy of the states (≈320 GB/s algorithmic) | nnz·13 B/state |
-| K4' `msc_energy_kernel` | same | bit-sliced 10-bit vertical counters, up to 128 sites per item, grid-stride over items, counts gathered in shared memory (one global atomic per address per CTA); on two-colourable graphs only one colour class is visited (it sees every bond once) | ALU: 0.21 ms at C5 size (round 1: 0.40 → 0.29), 0.05 ms on a 4-slot block (was 1.04 ms with per-item global atomics) | 1 B/spin-word (½ on bipartite lattices) |
-| K5 `lbp_kernel` | `nmc.py:168-228` | cooperative grid (≤ 1 CTA per SM), 2 grid syncs per iteration; gather: numpy's pairwise summation order is resolved on the host into a postfix program per row and replayed (thread per row, or a warp per row with shared-memory staging when rows have ≥ 12 entries); incoming messages stored contiguously per row; update: thread per edge, `tanh(βJ)` hoisted out of the iterations | grid-sync + fp64 transcendental latency: 14 µs per iteration at EA L=16, 19.5 µs on C1 (was 100), 28 µs at EA L=32 (`profiles/r1_kernel_rates.jsonl`) | 32·nnz B/iter |
-| K6 `msc_swap_decide/apply` | `npt.py:514-533,652-680` | thread/ladder decide; thread/(site,group) masked bit exchange; per-round acceptance log on the device | HBM | 2×state per round |
-| K6 label form: `msc_label_swap_kernel` + `msc_thrbits_kernel`; `ladder_label_swap_kernel` (K2a/K3) | same, SURVEY D4 | thread/ladder on the energies of all slots (gathered over the ranks), labels and inverse permuted; threshold planes / per-row βs rebuilt | latency: 34 µs per round | 8 B per replica cross the GPUs, no spin moves |
-| K7 `icm_components_kernel` | `apt_ICM.py:116-143` | 1 CTA / pair, min-label + pointer jumping, root ranking by scan | latency; 2.3e4 pairs/s at L=32 incl. copies (640 pairs per launch) | — |
-
-### K1 exactness rules
-Row sums follow scipy's `csr_matvec` (sequential over stored entries, then `+ h[k]`).  Integer J and unscaled
-row ⇒ partial sums are exact ⇒ lanes reduce in parallel; otherwise products are formed in parallel and
-accumulated **in storage order** by shuffles (same rounding as the reference).  `tanh(β·f)` for integer fields
-comes from a host LUT computed with numpy's own `tanh`, so ±J decisions are bit-equal; elsewhere the device restatement
+# ------------------------------------------------------------------ K1 exactness: tanh
+s = s.replace('''comes from a host LUT computed with numpy's own `tanh`, so ±J decisions are bit-equal; elsewhere CUDA `tanh`
+(a 1-ulp difference flips a decision only if the uniform lands in that ulp, ~1e-16 per attempt).''', '''comes from a host LUT computed with numpy's own `tanh`, so ±J decisions are bit-equal; elsewhere the device restatement
 of numpy's `tanh` (`nlmc_npmath.h`, table staged in shared memory), bit-equal as well.  A symmetric-J flag computed at
 instance creation guards the incremental-field kernel (K1-int pushes J_kj into field j on a flip of k): an asymmetric or
 duplicated-entry J -- which the reference accepts through `J.dot(m)` -- takes the general kernel
-(`test_k1_asymmetric_j`); the production engines refuse it.  NMC phases
-need no copies of J: a per-row flag divides entries by `temp_x` on the fly (`fl(J/temp_x)`, `nmc.py:379`) and
-frozen spins are carried by `h_eff = ±1e4` exactly as the reference does (`nmc.py:381,400`).
+(`test_k1_asymmetric_j`); the production engines refuse it.''')
 
-### K2 update rule
-With c = #neighbours with J_ij s_j = +1 (bit-sliced full adders, 8 LOP3 per 32 lanes) and f = 2c−6:
-`s_i ← [f>0] XOR g`, `g ~ Bernoulli(q(|f|))`, `q(0)=½`, `q(a)=1/(1+e^{2βa})` — the same conditional law as
-`sign(tanh(βx) − 2u + 1)`.  g is drawn for all lanes by a bit-serial comparison of a uniform with the
-32-bit threshold of each lane's |f| level, MSB first: 6 unconditional steps (fully unrolled; the per-step state is
-`und` = still equal on the prefix and `v` = the uniform's bit at the first difference, two 3-input logic ops per word;
-the level's threshold bit is selected by three integer multiply-adds on the FMA pipe), then the
-≈2 % still-undecided lanes get a fresh 32-bit uniform against the remaining threshold bits (exact
-conditional probability).  Random words: Philox4x32-10, counter = (site, (β, **global** ladder quad), sweep,
-step), key = seed ⇒ results are independent of launch geometry and of the GPU count.  Degrees 2/4 are padded
-with neutral (+1,−1) pairs.  Probabilities are quantised to 2⁻³².  Colouring: greedy in site order
-(checkerboard on even-L lattices).
-
-### K3: dense J on the tensor cores (config C3)
-R replicas share J, so the fields of a block of 128 sites for all replicas are one GEMM
-`H_blk[R×128] = S[R×N]·J[N×128]` (S = spins as bf16 ±1, exact; J = J1+J2+J3 in bf16, fp32 accumulation in TMEM —
-~2⁻¹⁷·√N absolute field error, limited by fp32 accumulation).  A sweep visits the blocks in order
-("left-looking"): split-K GEMM for the block from the **current** spins, then the block's 128 sites are updated
-sequentially per replica with the in-block flips corrected on CUDA cores — a fixed-order sequential heat-bath
-sweep, no drift, no separate "periodic recompute".  One sweep = one CUDA graph (1 memset + 16×(GEMM, update) at
-N=2000).  Measured on B200 at C3 size (2048 replicas × N=2000): full recompute **55 µs = 935 TFLOP/s**
-(58 % of the measured 1610 TF/s bf16 burst peak, tensor pipe 53 % active in ncu, `profiles/r1_gemm_kernel_summary.md`),
-sweep 0.355 ms = **1.15e10 attempts/s** (round 1: 0.44 ms).  In round 1 the update kernel went 193 → 14 µs per block through ncu-driven
-rewrites (8 lanes per replica; 8-site register sub-blocks with right-looking FMAs; `exp`/`rcp` replaced by a
-precomputed threshold so a decision is compare+select+FMA; then, when ncu showed 40 % of the remaining time in the
-prologue's load latency, `cp.async` staging of the 64 KB J block, batched field/spin loads and bank-conflict-free
-shared rows: 0.57 → 0.44 ms per sweep).  Round 2 (ncu: 6 % of the warp slots, three quarters of the sweep) rewrote it
+# ------------------------------------------------------------------ K3 section numbers
+s = s.replace('''sweep 0.44 ms = **9.3e9 attempts/s**.  The update kernel went 193 → 14 µs per block through ncu-driven''', '''sweep 0.355 ms = **1.15e10 attempts/s** (round 1: 0.44 ms).  In round 1 the update kernel went 193 → 14 µs per block through ncu-driven''')
+s = s.replace('''shared rows: 0.57 → 0.44 ms per sweep).  NMC phases are per-site modes of the same kernel
+(hot backbone at β/temp_x, frozen), and `m_init = M[:, argmin E]` is tracked on the device.''', '''shared rows: 0.57 → 0.44 ms per sweep).  Round 2 (ncu: 6 % of the warp slots, three quarters of the sweep) rewrote it
 again: one **warp** per replica; everything off the chain done up front in parallel over the block (one Philox call and four
 logits per lane give the thresholds of all 128 sites, NMC phase modes folded in as ±inf / ×temp_x); fully unrolled 8-site
 sub-blocks with 128-bit broadcast loads; one CTA per SM (14 replicas) so that the 64 KB coupling block is staged once per
@@ -221,9 +118,10 @@ the third kernel per block and the extra dependency edges cost more than the ove
 of the chain (`NLMC_DENSE_PDL`, 0.455 ms).  NMC phases are per-site modes of the same kernel (hot backbone at β/temp_x,
 frozen), and `m_init = M[:, argmin E]` is tracked on the device.  The heat-bath draw of K2a and K3 uses all 32 random bits with
 symmetric tails (a 24-bit uniform rounded to 1.0 used to force a spin down once in 2²⁴ draws; `test_cold_tail_*` at
-`global_beta` = 13.6).
+`global_beta` = 13.6).''')
 
-### K2 in β-label form, and what the label form costs
+# ------------------------------------------------------------------ roofline section
+s = replace_section(s, "### Why the headline roofline fraction is > 1", "## 5. Measurement (bench.py)", '''### K2 in β-label form, and what the label form costs
 `msc_sweep_kernel<kSteps, kPerBit, kSubWarp>`: `kPerBit` takes the threshold bit of every lane from the bit planes (18
 extra 16-byte loads per thread, all L1 hits, and three logic operations per word and step where the scalar form has three
 FMA-pipe multiply-adds); `kSubWarp` maps several sites to one warp when a site row is shorter than 128 words (a block of a
@@ -248,7 +146,10 @@ instruction bound by construction (round 1 measured every alternative it could t
 Philox-7 reaches 3.47e12/s and stays a build option).  The generic 42 B figure is demoted to a note in the JSON line (against
 it the same launch would read as ≈20 × the HBM peak, which is what bit-packing buys, not a roofline fraction).
 
-## 5. Measurement (bench.py)
+''')
+
+# ------------------------------------------------------------------ measurement
+s = replace_section(s, "## 5. Measurement (bench.py)", "## 7. Tests", '''## 5. Measurement (bench.py)
 
 Workload: C5 **as stated** -- 3D ±J EA L=64, 32 β (0.2…2.0) × 128 ladders = 4096 replicas in total; one step = one swap
 round (16 sweeps + energies + exchange with 10 pairs per ladder).  Round-2 numbers (`profiles/r2_bench_n{1,2,4,8}.json`, one
@@ -320,7 +221,10 @@ One process per GPU (`torch.distributed`, NCCL).  Two partitions, both without a
 
 `NPT(..., mode="production").run` picks the first form by itself when a process group with more than one rank is initialised.
 
-## 7. Tests
+''')
+
+# ------------------------------------------------------------------ tests
+s = replace_section(s, "## 7. Tests", "## 8. Out of scope (SURVEY §2) and why", '''## 7. Tests
 
 `-m "not gpu"` (69 tests, ≈1 min): oracle vs live reference and goldens; the restated `tanh`/`arctanh` against numpy (digests,
 vectors, live); host logic of all four classes in replay AND production mode (bit-packed, generic with device exchange,
@@ -338,12 +242,11 @@ line; oracle-free properties at the full size of C5.
 Memory checking: `compute-sanitizer` is refused on this GPU pool, so out-of-bounds checking was done by review of every
 indexed access plus guard tests (sizes that are not multiples of the tile, n = 1, empty rows, rows shorter than a warp).
 
-## 8. Out of scope and why
-Example scripts, plotting (kept as optional no-ops when matplotlib is absent),
-`use_hash_table` (CPU memoisation with no effect on results; accepted and ignored), `num_cores` (accepted and
-ignored): callers or cosmetics around the path, no arithmetic.
+''')
 
-## 9. Known gaps / next
+# ------------------------------------------------------------------ gaps
+a = s.index("## 9. Known gaps / next")
+s = s[:a] + '''## 9. Known gaps / next
 1. K2 in label form costs 20 % per sweep (bit planes instead of scalar thresholds); it is what makes the strong-scaling
    efficiency 0.70–0.79 instead of ≈0.95.  Ideas not yet tried: planes in shared memory for persistent CTAs, or a two-word
    per thread mapping with fewer live registers.
@@ -363,3 +266,6 @@ ignored): callers or cosmetics around the path, no arithmetic.
    move states through the host because K7 takes host buffers; the `find_clusters` growth loop is host-only.
 8. `e2e` through the class API carries ≈0.14 s of per-call fixed cost (instance upload, colouring, handle, building the
    float64 `M`), which dominates short calls and is replicated on every rank.
+'''
+open(p, "w").write(s)
+print("ok")
