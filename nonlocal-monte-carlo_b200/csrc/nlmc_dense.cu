@@ -95,6 +95,7 @@ struct GemmParams {
     // skip_begin are shifted up by skip_count (look-ahead: the columns of the block being updated are left out of the main
     // part and contracted afterwards)
     int kb_offset, skip_begin, skip_count;
+    int m_tile_base;  // first 128-row tile of this launch (a chain of the sweep owns a range of replica tiles)
     int pdl;  // launched with programmatic stream serialization: the prologue overlaps the tail of the preceding kernel
     float *Ct;
     int accumulate;  // 1: red.add into C^T (split-K or accumulate), 0: plain store
@@ -113,7 +114,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBM, n0 = p.n_base + blockIdx.y * kBN;
+    const int m0 = (blockIdx.x + p.m_tile_base) * kBM, n0 = p.n_base + blockIdx.y * kBN;
     const int kb_per = (p.k_blocks_total + p.k_splits - 1) / p.k_splits;
     const int kb_begin = blockIdx.z * kb_per, kb_end = min(p.k_blocks_total, kb_begin + kb_per);
     const int n_kb = kb_end - kb_begin;
@@ -300,6 +301,7 @@ struct nlmc_dense {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;     // look-ahead GEMMs of the sweep (forked from / joined into `stream` inside the captured graph)
     std::vector<cudaEvent_t> fork_ev;  // one event per fork / join point of the captured sweep
+    std::vector<cudaStream_t> chain_streams;  // streams of the independent replica chains of the sweep (beyond `stream`)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -320,7 +322,8 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 static int launch_fields_part(nlmc_dense *D, cudaStream_t st, int col0, int n_cols, int k_splits, bool clear, int kb_first,
-                              int kb_count, int skip_first, int skip_count, int stages, bool pdl = false) {
+                              int kb_count, int skip_first, int skip_count, int stages, bool pdl = false, int m_tile_base = 0,
+                              int m_tiles = 0) {
     NLMC_REQUIRE(col0 % kBN == 0, "launch_fields: col0 must be a multiple of %d", kBN);
     GemmParams p;
     p.M = D->R_pad;
@@ -336,9 +339,11 @@ static int launch_fields_part(nlmc_dense *D, cudaStream_t st, int col0, int n_co
     p.Ct = D->Ht;
     p.accumulate = k_splits > 1 || !clear;
     p.pdl = pdl ? 1 : 0;
+    p.m_tile_base = m_tile_base;
+    if (m_tiles <= 0) m_tiles = D->R_pad / kBM - m_tile_base;
     if (p.accumulate && clear)
         NLMC_CUDA(cudaMemsetAsync(D->Ht + (size_t)col0 * D->R_pad, 0, sizeof(float) * (size_t)(p.N - col0) * D->R_pad, st));
-    const dim3 grid((unsigned)(D->R_pad / kBM), (unsigned)((n_cols + kBN - 1) / kBN), (unsigned)p.k_splits);
+    const dim3 grid((unsigned)m_tiles, (unsigned)((n_cols + kBN - 1) / kBN), (unsigned)p.k_splits);
     if (stages == 2)
         NLMC_CUDA(launch_pdl(gemm_bf16_tn_kernel<2>, grid, dim3(kGemmThreads), gemm_smem_bytes(2), st, pdl, D->map_S, D->map_J[0],
                              D->map_J[D->n_split > 1 ? 1 : 0], D->map_J[D->n_split > 2 ? 2 : 0], p));
@@ -404,7 +409,8 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
                                                                                const float *__restrict__ beta, uint16_t *S,
                                                                                uint32_t seed_lo, uint32_t seed_hi,
                                                                                const uint32_t *__restrict__ sweep_ptr, float *Ht_zero,
-                                                                               const uint8_t *__restrict__ modes, float temp_x, int pdl) {
+                                                                               const uint8_t *__restrict__ modes, float temp_x, int pdl,
+                                                                               int r_base, int r_end) {
     extern __shared__ __align__(16) uint8_t dsm[];
     const uint32_t sweep = *sweep_ptr;   // bumped by the kernel at the end of the previous sweep, several launches back
     const int rpc = blockDim.x >> 5;                                   // replicas (warps) per CTA
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
     float *spn = thr + (size_t)rpc * kFldStride;                       // [rpc][kFldStride]  spins as floats
     const int tid = threadIdx.x;
     const int rep = tid >> 5, lane = tid & 31;   // replica within the CTA = warp
-    const int r = blockIdx.x * rpc + rep;
+    const int r = r_base + blockIdx.x * rpc + rep;   // the launch covers the replicas [r_base, r_end)
     const int k_end = min(kBlk, n - c0);
     // stage J_bb transposed, Jt[j][k] = J[c0+k][c0+j], from the transposed copy of J kept in global memory
     // (JfT[a][b] = J[b][a]): asynchronous 16-byte copies, all 64 KB in flight while the thresholds are computed
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
     float *frow = fld + rep * kFldStride;
     float *trow = thr + rep * kFldStride;
     float *srow = spn + rep * kFldStride;
-    const bool active = r < R_pad;
+    const bool active = r < r_end;
     if (active) {
         // spins and thresholds of the lane's four sites 4*lane .. 4*lane+3
         const uint2 sv = *reinterpret_cast<const uint2 *>(S + (size_t)r * n_pad + c0 + 4 * lane);   // 256 B per warp
@@ -615,6 +621,7 @@ int nlmc_dense_destroy(nlmc_dense *D) {
     if (D->ev0) cudaEventDestroy(D->ev0);
     if (D->ev1) cudaEventDestroy(D->ev1);
     for (cudaEvent_t e : D->fork_ev) cudaEventDestroy(e);
+    for (cudaStream_t st : D->chain_streams) cudaStreamDestroy(st);
     if (D->stream2) cudaStreamDestroy(D->stream2);
     if (D->stream) cudaStreamDestroy(D->stream);
     delete D;
@@ -795,10 +802,53 @@ static int enqueue_sweep(nlmc_dense *D, int k_splits) {
                    update_smem_bytes(D->upd_rpc), D->stream, pdl && !look_ahead, D->n, D->n_pad, D->R_pad, b * kBlk, (const float *)D->Ht,
                    (const float *)D->Jf, (const float *)D->hf, (const float *)D->beta, D->S, (uint32_t)D->seed, (uint32_t)(D->seed >> 32),
                    (const uint32_t *)D->d_sweep, zero_rows, (const uint8_t *)(D->modes_on ? D->modes : nullptr), D->temp_x,
-                   (int)((pdl && !look_ahead) ? (getenv("NLMC_DENSE_PDL_EARLY") ? 2 : 1) : 0));
+                   (int)((pdl && !look_ahead) ? (getenv("NLMC_DENSE_PDL_EARLY") ? 2 : 1) : 0), 0, D->R_pad);
     };
     int rc;
-    if (!look_ahead) {
+    // Replicas are independent, so the GEMM -> update chain of one range of replica tiles never has to wait for another
+    // range: the sweep can run as n_chains independent chains on their own streams (forked and joined inside the captured
+    // graph), the GEMM of one chain resident next to the update of another.  Measured on B200 at C3 size: 0.358 ms per
+    // sweep with one chain, 0.464 / 0.426 / 0.511 ms with 2 / 4 / 8 -- like the look-ahead and the dependent launch above,
+    // concurrency between these latency-bound kernels does not pay.  Default 1; NLMC_DENSE_CHAINS selects more.
+    const int m_tiles_all = D->R_pad / kBM;
+    int n_chains = 1;
+    if (const char *e = getenv("NLMC_DENSE_CHAINS")) n_chains = std::max(1, std::min(m_tiles_all, atoi(e)));
+    if (n_chains > 1 && !look_ahead && !pdl) {
+        while ((int)D->chain_streams.size() < n_chains - 1) {
+            cudaStream_t st = nullptr;
+            NLMC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            D->chain_streams.push_back(st);
+        }
+        while ((int)D->fork_ev.size() < n_chains) {
+            cudaEvent_t e = nullptr;
+            NLMC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            D->fork_ev.push_back(e);
+        }
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, D->inst->device);
+        NLMC_CUDA(cudaMemsetAsync(D->Ht, 0, sizeof(float) * (size_t)kBlk * D->R_pad, D->stream));   // field rows of block 0
+        NLMC_CUDA(cudaEventRecord(D->fork_ev[0], D->stream));
+        for (int c = 0; c < n_chains; ++c) {
+            cudaStream_t st = c == 0 ? D->stream : D->chain_streams[(size_t)c - 1];
+            if (c > 0) NLMC_CUDA(cudaStreamWaitEvent(st, D->fork_ev[0], 0));
+            const int t0 = (int)((long long)m_tiles_all * c / n_chains), t1 = (int)((long long)m_tiles_all * (c + 1) / n_chains);
+            const int r_base = t0 * kBM, r_end = t1 * kBM;
+            const int rpc = std::max(1, std::min(kMaxRepPerCta, (r_end - r_base + sms - 1) / sms));
+            int ks = std::max(1, std::min(kb_all / 2, sms / std::max(1, t1 - t0)));
+            if (const char *e = getenv("NLMC_DENSE_KSPLIT")) ks = std::max(1, atoi(e));
+            for (int b = 0; b < nb; ++b) {
+                if ((rc = launch_fields_part(D, st, b * kBlk, kBlk, ks, /*clear=*/false, 0, kb_all, 0, 0, 2, false, t0, t1 - t0))) return rc;
+                float *zero_rows = b + 1 < nb ? D->Ht + (size_t)(b + 1) * kBlk * D->R_pad : nullptr;
+                dense_block_update_kernel<<<(unsigned)((r_end - r_base + rpc - 1) / rpc), (unsigned)(32 * rpc), update_smem_bytes(rpc), st>>>(
+                    D->n, D->n_pad, D->R_pad, b * kBlk, D->Ht, D->Jf, D->hf, D->beta, D->S, (uint32_t)D->seed, (uint32_t)(D->seed >> 32),
+                    D->d_sweep, zero_rows, D->modes_on ? D->modes : nullptr, D->temp_x, 0, r_base, r_end);
+            }
+            if (c > 0) {
+                NLMC_CUDA(cudaEventRecord(D->fork_ev[(size_t)c], st));
+                NLMC_CUDA(cudaStreamWaitEvent(D->stream, D->fork_ev[(size_t)c], 0));
+            }
+        }
+    } else if (!look_ahead) {
         const char *skip = getenv("NLMC_DENSE_SKIP");   // timing experiments only: "gemm" or "update"
         for (int b = 0; b < nb; ++b) {
             if (!(skip && skip[0] == 'g'))
