@@ -162,8 +162,8 @@ template <int kSteps, bool kPerBit, bool kSubWarp>
 #ifndef NLMC_PERBIT_CTAS
 #define NLMC_PERBIT_CTAS 4  // resident CTAs per SM of the bit-plane variant (64 registers: no spills)
 #endif
-__global__ void __launch_bounds__(256, kPerBit ? NLMC_PERBIT_CTAS : 5) msc_sweep_kernel(MscDev a, int first, int n_sites, const uint32_t *__restrict__ counters) {
-    const uint32_t sweep = counters[0];
+__global__ void __launch_bounds__(256, kPerBit ? NLMC_PERBIT_CTAS : 5) msc_sweep_kernel(MscDev a, int first, int n_sites, const uint32_t *__restrict__ counters, uint32_t sweep_in_batch) {
+    const uint32_t sweep = counters[0] + sweep_in_batch;
     int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);  // site of this colour
     const int lane = threadIdx.x & 31;
     int word0;
@@ -544,7 +544,7 @@ __global__ void msc_clear_round_slot_kernel(int32_t *accepted_rounds, const uint
     accepted_rounds[counters[1] % kRoundLog] = 0;
 }
 
-__global__ void msc_bump_kernel(uint32_t *counters, int which) { counters[which] += 1u; }
+__global__ void msc_bump_kernel(uint32_t *counters, int which, uint32_t by = 1u) { counters[which] += by; }
 
 // all replicas (every beta) of one ladder as int8 +-1: out[b][site]
 __global__ void msc_unpack_ladder_kernel(MscDev a, int g, int lane, int8_t *out) {
@@ -612,36 +612,42 @@ static MscDev dev_view(const nlmc_msc *M) {
 }
 
 template <int kSteps>
-static void launch_colour(const nlmc_msc *M, const MscDev &d, int first, int cnt) {
+static void launch_colour(const nlmc_msc *M, const MscDev &d, int first, int cnt, uint32_t sweep_in_batch) {
     const bool sub = M->W < 128;
     const int chunks = (M->W + 127) / 128;
     const int warps = sub ? (cnt + d.spw - 1) / d.spw : cnt;
     const dim3 blocks((unsigned)((warps + 7) / 8), (unsigned)chunks);
     if (M->label_mode) {
-        if (sub) msc_sweep_kernel<kSteps, true, true><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters);
-        else msc_sweep_kernel<kSteps, true, false><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters);
+        if (sub) msc_sweep_kernel<kSteps, true, true><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters, sweep_in_batch);
+        else msc_sweep_kernel<kSteps, true, false><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters, sweep_in_batch);
     } else {
-        if (sub) msc_sweep_kernel<kSteps, false, true><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters);
-        else msc_sweep_kernel<kSteps, false, false><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters);
+        if (sub) msc_sweep_kernel<kSteps, false, true><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters, sweep_in_batch);
+        else msc_sweep_kernel<kSteps, false, false><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters, sweep_in_batch);
     }
 }
 
 static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
     const MscDev d = dev_view(M);
+    // The sweep index a kernel hashes into its random stream is counters[0] + its position in the batch.  Short site rows
+    // (a block of a sharded ladder: 28 us per colour launch at 16 words) bump the counter once per batch; full rows keep
+    // the 1-thread bump kernel after every sweep, which measured 2 % FASTER there (profiles/r1b_sweep_kernel_source.md).
+    const bool bump_once = M->W < 128 ? !getenv("NLMC_MSC_BUMP_EACH") : getenv("NLMC_MSC_BUMP_ONCE") != nullptr;
     for (int s = 0; s < n_sweeps; ++s) {
+        const uint32_t off = bump_once ? (uint32_t)s : 0u;
         for (int c = 0; c < M->n_colours; ++c) {
             const int first = M->colour_ptr[c], cnt = M->colour_ptr[c + 1] - first;
             if (cnt == 0) continue;
             switch (M->k_steps) {
-                case 4: launch_colour<4>(M, d, first, cnt); break;
-                case 5: launch_colour<5>(M, d, first, cnt); break;
-                case 7: launch_colour<7>(M, d, first, cnt); break;
-                case 8: launch_colour<8>(M, d, first, cnt); break;
-                default: launch_colour<6>(M, d, first, cnt); break;
+                case 4: launch_colour<4>(M, d, first, cnt, off); break;
+                case 5: launch_colour<5>(M, d, first, cnt, off); break;
+                case 7: launch_colour<7>(M, d, first, cnt, off); break;
+                case 8: launch_colour<8>(M, d, first, cnt, off); break;
+                default: launch_colour<6>(M, d, first, cnt, off); break;
             }
         }
-        msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 0);
+        if (!bump_once) msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 0);
     }
+    if (bump_once && n_sweeps > 0) msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 0, (uint32_t)n_sweeps);
     NLMC_CUDA(cudaGetLastError());
     return NLMC_OK;
 }
