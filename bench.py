@@ -292,7 +292,8 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     packed_bytes = 2.0 * (n / msc.n_colours) * msc.n_words * 4        # read the other colour once + write this colour
     traffic = ncu_traffic()
-    kernel_name = f"msc_sweep_kernel<6, {'bit planes' if world > 1 else 'scalar thresholds'}> (one colour of one sweep)"
+    kernel_name = (f"msc_sweep_kernel<{7 if world > 1 else 6} steps, {'bit planes' if world > 1 else 'scalar thresholds'}> "
+                   "(one colour of one sweep)")
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": packed_bytes / (sweep_ms * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": packed_bytes / (sweep_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
                 "traffic": (traffic or {}).get("dram_bytes_per_launch") if world == 1 else None,

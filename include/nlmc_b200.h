@@ -48,6 +48,8 @@ int nlmc_device_info(int device, char *name, int name_len, int *sm_count, int *c
 
 /* host-side format helper: int8 spins -> the float64 arrays the reference's API returns (NMC/nmc.py:52,89), multi-threaded */
 int nlmc_host_widen_i8_f64(const int8_t *in, double *out, uint64_t count, int threads);
+/* touch every page of a freshly allocated host result buffer (first-touch faults taken while the GPU is busy) */
+int nlmc_host_prefault(void *buf, uint64_t bytes, int threads);
 
 /* ---- instance ---------------------------------------------------------------------------------
  * Replaces `J = csr_matrix(J)` + `h = asarray(h)` at the top of every MCMC call (NMC/nmc.py:53-54):
@@ -205,6 +207,8 @@ int nlmc_msc_energies(nlmc_msc *msc, double *out_E);
 int nlmc_msc_sweep_record(nlmc_msc *msc, int n_sweeps, int ladder, int8_t *out_M, double *out_E);
 /* the same with the recorded states laid out as the rows of the reference's M: m_layout 1 = [n_beta][n][n_sweeps] */
 int nlmc_msc_sweep_record_layout(nlmc_msc *msc, int n_sweeps, int ladder, int8_t *out_M, double *out_E, int m_layout);
+/* the same with the states delivered as float64 rows of M ([n_beta][n][n_sweeps]) through a pinned staging buffer */
+int nlmc_msc_sweep_record_f64(nlmc_msc *msc, int n_sweeps, int ladder, double *out_M_f64, double *out_E);
 int nlmc_msc_round(nlmc_msc *msc, int n_sweeps, int num_swapping_pairs, double *out_E);
 int nlmc_msc_round_host(nlmc_msc *msc, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,
                         uint32_t *packed_out, double *out_E);

@@ -16,6 +16,57 @@ void set_error(const char *fmt, ...) {
 }
 }  // namespace nlmc
 
+namespace nlmc {
+// J_ij == J_ji with no repeated column in a row: what the incremental-field kernels (K1-int, K2a, K3) rely on when a flip
+// of site k pushes J_kj into the field of j.  The general replay kernel does not need it (the reference accepts any J
+// through J.dot(m), NMC/nmc.py:86).  Evaluated on first use from the host mirror of the CSR (31 ms at C5 size, which the
+// bit-packed path -- it checks its own six neighbours per site -- should not pay on every NPT.run call).
+bool instance_value_symmetric(nlmc_instance *I) {
+    if (I->symmetry_known) return I->value_symmetric;
+    const int n = I->n;
+    const int32_t *row_ptr = I->h_row_ptr.data(), *col = I->h_col.data();
+    const double *val = I->h_val.data();
+    bool value_symmetric = true;
+    {
+        // rows sorted by column (what scipy delivers for the lattices and dense matrices of the configs): binary search in
+        // place; otherwise sorted copies of the rows
+        bool sorted_rows = true;
+        for (int i = 0; i < n && sorted_rows; ++i)
+            for (int p = row_ptr[i] + 1; p < row_ptr[i + 1]; ++p)
+                if (col[p] <= col[p - 1]) { sorted_rows = false; break; }
+        if (sorted_rows) {
+            for (int i = 0; i < n && value_symmetric; ++i)
+                for (int p = row_ptr[i]; p < row_ptr[i + 1]; ++p) {
+                    if (val[p] == 0.0) continue;
+                    const int j = col[p];
+                    const int32_t *b = col + row_ptr[j], *e = col + row_ptr[j + 1];
+                    const int32_t *it = std::lower_bound(b, e, (int32_t)i);
+                    if (it == e || *it != i || val[it - col] != val[p]) { value_symmetric = false; break; }
+                }
+        } else {
+            std::vector<std::vector<std::pair<int32_t, double>>> rows((size_t)n);
+            for (int i = 0; i < n; ++i) {
+                auto &r = rows[(size_t)i];
+                for (int p = row_ptr[i]; p < row_ptr[i + 1]; ++p) r.emplace_back(col[p], val[p]);
+                std::sort(r.begin(), r.end());
+                for (size_t q = 1; q < r.size() && value_symmetric; ++q)
+                    if (r[q].first == r[q - 1].first) value_symmetric = false;
+            }
+            for (int i = 0; i < n && value_symmetric; ++i)
+                for (const auto &e : rows[(size_t)i]) {
+                    if (e.second == 0.0) continue;
+                    const auto &rj = rows[(size_t)e.first];
+                    auto it = std::lower_bound(rj.begin(), rj.end(), std::make_pair((int32_t)i, -1e300));
+                    if (it == rj.end() || it->first != i || it->second != e.second) { value_symmetric = false; break; }
+                }
+        }
+    }
+    I->value_symmetric = value_symmetric;
+    I->symmetry_known = true;
+    return value_symmetric;
+}
+}  // namespace nlmc
+
 extern "C" {
 
 const char *nlmc_last_error(void) { return nlmc::g_err; }
@@ -70,48 +121,9 @@ int nlmc_instance_create(int n, const int32_t *row_ptr, const int32_t *col, cons
         NLMC_REQUIRE(col[p] >= 0 && col[p] < n, "nlmc_instance_create: column index out of range at entry %d", p);
         if (val[p] != std::floor(val[p]) || std::fabs(val[p]) > 1e6) integer_j = false;
     }
-    // J_ij == J_ji with no repeated column in a row: what the incremental-field kernels (K1-int, K2a, K3) rely on when a
-    // flip of site k pushes J_kj into the field of j.  The general replay kernel does not need it (the reference
-    // accepts any J through J.dot(m), NMC/nmc.py:86).
-    bool value_symmetric = true;
-    {
-        // rows sorted by column (what scipy delivers for the lattices and dense matrices of the configs): binary search in
-        // place; otherwise sorted copies of the rows
-        bool sorted_rows = true;
-        for (int i = 0; i < n && sorted_rows; ++i)
-            for (int p = row_ptr[i] + 1; p < row_ptr[i + 1]; ++p)
-                if (col[p] <= col[p - 1]) { sorted_rows = false; break; }
-        if (sorted_rows) {
-            for (int i = 0; i < n && value_symmetric; ++i)
-                for (int p = row_ptr[i]; p < row_ptr[i + 1]; ++p) {
-                    if (val[p] == 0.0) continue;
-                    const int j = col[p];
-                    const int32_t *b = col + row_ptr[j], *e = col + row_ptr[j + 1];
-                    const int32_t *it = std::lower_bound(b, e, (int32_t)i);
-                    if (it == e || *it != i || val[it - col] != val[p]) { value_symmetric = false; break; }
-                }
-        } else {
-            std::vector<std::vector<std::pair<int32_t, double>>> rows((size_t)n);
-            for (int i = 0; i < n; ++i) {
-                auto &r = rows[(size_t)i];
-                for (int p = row_ptr[i]; p < row_ptr[i + 1]; ++p) r.emplace_back(col[p], val[p]);
-                std::sort(r.begin(), r.end());
-                for (size_t q = 1; q < r.size() && value_symmetric; ++q)
-                    if (r[q].first == r[q - 1].first) value_symmetric = false;
-            }
-            for (int i = 0; i < n && value_symmetric; ++i)
-                for (const auto &e : rows[(size_t)i]) {
-                    if (e.second == 0.0) continue;
-                    const auto &rj = rows[(size_t)e.first];
-                    auto it = std::lower_bound(rj.begin(), rj.end(), std::make_pair((int32_t)i, -1e300));
-                    if (it == rj.end() || it->first != i || it->second != e.second) { value_symmetric = false; break; }
-                }
-        }
-    }
     NLMC_CUDA(cudaSetDevice(device));
     auto *I = new nlmc_instance();
     I->device = device;
-    I->value_symmetric = value_symmetric;
     I->n = n;
     I->nnz = nnz;
     I->max_deg = max_deg;
@@ -179,6 +191,29 @@ int nlmc_host_widen_i8_f64(const int8_t *in, double *out, uint64_t count, int th
     return NLMC_OK;
 }
 
+/* Touch every page of a freshly allocated host buffer on `threads` host threads (0 = hardware concurrency, at most 32), so
+ * that the first-touch page faults of a large result array (the 1 GB float64 M of config C5) are taken while the GPU is
+ * still sweeping instead of inside the final widening. */
+int nlmc_host_prefault(void *buf, uint64_t bytes, int threads) {
+    NLMC_REQUIRE(bytes == 0 || buf, "nlmc_host_prefault: NULL argument");
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, 32));
+    if (bytes < (1u << 22)) nt = 1;
+    volatile char *p = static_cast<volatile char *>(buf);
+    auto work = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; i += 4096) p[i] = 0;
+    };
+    if (nt == 1) { work(0, bytes); return NLMC_OK; }
+    std::vector<std::thread> pool;
+    const uint64_t per = (((bytes + (uint64_t)nt - 1) / (uint64_t)nt) + 4095) & ~4095ull;
+    for (int t = 0; t < nt; ++t) {
+        const uint64_t lo = std::min(bytes, per * (uint64_t)t), hi = std::min(bytes, lo + per);
+        if (lo < hi) pool.emplace_back(work, lo, hi);
+    }
+    for (auto &th : pool) th.join();
+    return NLMC_OK;
+}
+
 int nlmc_instance_destroy(nlmc_instance *I) {
     if (!I) return NLMC_OK;
     cudaSetDevice(I->device);
@@ -196,7 +231,9 @@ int nlmc_instance_destroy(nlmc_instance *I) {
 
 int nlmc_instance_n(const nlmc_instance *I) { return I ? I->n : NLMC_ERR_ARG; }
 int nlmc_instance_is_integer(const nlmc_instance *I) { return I ? (I->integer_j ? 1 : 0) : NLMC_ERR_ARG; }
-int nlmc_instance_is_symmetric(const nlmc_instance *I) { return I ? (I->value_symmetric ? 1 : 0) : NLMC_ERR_ARG; }
+int nlmc_instance_is_symmetric(const nlmc_instance *I) {
+    return I ? (nlmc::instance_value_symmetric(const_cast<nlmc_instance *>(I)) ? 1 : 0) : NLMC_ERR_ARG;
+}
 
 int nlmc_replicas_create(nlmc_instance *I, int R, const int8_t *init_spins, nlmc_replicas **out) {
     NLMC_REQUIRE(out != nullptr, "nlmc_replicas_create: out is NULL");

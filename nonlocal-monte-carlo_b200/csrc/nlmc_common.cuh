@@ -54,6 +54,25 @@ struct Scratch {
     T *as() const { return static_cast<T *>(ptr); }
 };
 
+// Large device buffers come from the stream-ordered allocator with the pool kept (no release back to the driver), so that
+// creating and destroying handles call after call -- every NPT.run builds its own -- does not pay cudaMalloc / cudaFree
+// (65 ms per 134 MB state at C5 size) each time.
+inline cudaError_t pool_alloc(void **ptr, size_t bytes, int device, cudaStream_t st) {
+    static bool configured[64] = {};
+    if (device >= 0 && device < 64 && !configured[device]) {
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        configured[device] = true;
+    }
+    return cudaMallocAsync(ptr, bytes, st);
+}
+inline void pool_free(void *ptr, cudaStream_t st) {
+    if (ptr) cudaFreeAsync(ptr, st);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -79,6 +98,7 @@ struct nlmc_instance {
     bool integer_j = false;   // every stored value is an integer -> row sums exact in any order
     bool symmetric = false;   // pattern symmetric (rev index available)
     bool value_symmetric = false;  // J_ij == J_ji for every stored entry and no column appears twice in a row
+    bool symmetry_known = false;   // ... evaluated lazily by nlmc::instance_value_symmetric()
     int32_t *row_ptr = nullptr;  // [n+1]
     int32_t *col = nullptr;      // [nnz]
     double *val = nullptr;       // [nnz]
@@ -91,6 +111,8 @@ struct nlmc_instance {
     std::vector<int32_t> h_row_ptr, h_col;
     std::vector<double> h_val, h_h;
 };
+
+namespace nlmc { bool instance_value_symmetric(nlmc_instance *I); }
 
 struct nlmc_replicas {
     nlmc_instance *inst = nullptr;

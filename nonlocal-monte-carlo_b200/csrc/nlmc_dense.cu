@@ -644,7 +644,7 @@ int nlmc_dense_create(nlmc_instance *I, int n_replicas, const double *betas, int
     NLMC_REQUIRE(I && out && betas, "nlmc_dense_create: NULL argument");
     *out = nullptr;
     NLMC_REQUIRE(n_replicas >= 1 && n_split >= 1 && n_split <= 3, "nlmc_dense_create: n_replicas >= 1 and n_split in 1..3");
-    NLMC_REQUIRE(I->value_symmetric, "nlmc_dense_create: J must be symmetric (J_ij == J_ji) without repeated entries");
+    NLMC_REQUIRE(nlmc::instance_value_symmetric(I), "nlmc_dense_create: J must be symmetric (J_ij == J_ji) without repeated entries");
     int cc_major = 0;
     NLMC_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, I->device));
     if (cc_major != 10) {

@@ -801,8 +801,14 @@ int nlmc_msc_destroy(nlmc_msc *M) {
     if (!M) return NLMC_OK;
     cudaSetDevice(M->inst->device);
     nlmc::drop_graphs(M);
-    void *ptrs[] = {M->S, M->rec, M->site_list, M->thr, M->betas, M->E_acc, M->E, M->swapmask, M->accepted,
-                    M->scratch_spins, M->d_counters, M->recM, M->recE, M->labels, M->slot_of, M->thr_total,
+    if (M->stream) {   // the big buffers go back to the pool in stream order (after whatever is still queued)
+        nlmc::pool_free(M->S, M->stream);
+        nlmc::pool_free(M->recM, M->stream);
+        nlmc::pool_free(M->recE, M->stream);
+        cudaStreamSynchronize(M->stream);
+    }
+    void *ptrs[] = {M->rec, M->site_list, M->thr, M->betas, M->E_acc, M->E, M->swapmask, M->accepted,
+                    M->scratch_spins, M->d_counters, M->labels, M->slot_of, M->thr_total,
                     M->betas_total, M->thrbits, M->thr_lane, M->accepted_rounds};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (M->ev0) cudaEventDestroy(M->ev0);
@@ -904,6 +910,7 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
     M->label_mode = betas_total ? 1 : 0;
     M->n_beta_total = betas_total ? n_beta_total : n_beta;
     M->slot_begin = betas_total ? slot_begin : 0;
+    if (M->label_mode) M->k_steps = 7;  // stragglers cost a dependent table load in the bit-plane form: one more unconditional step pays (2 %)
     if (const char *e = getenv("NLMC_MSC_STEPS")) M->k_steps = atoi(e);
     if (M->k_steps != 4 && M->k_steps != 5 && M->k_steps != 7 && M->k_steps != 8) M->k_steps = 6;
     if (const char *e = getenv("NLMC_MSC_GRAPHS")) M->use_graphs = atoi(e) != 0;
@@ -918,7 +925,7 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
     const size_t words = (size_t)n * M->W;
     bool ok = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&M->ev0) == cudaSuccess && cudaEventCreate(&M->ev1) == cudaSuccess &&
-              cudaMalloc(&M->S, sizeof(uint32_t) * words) == cudaSuccess &&
+              nlmc::pool_alloc(reinterpret_cast<void **>(&M->S), sizeof(uint32_t) * words, I->device, M->stream) == cudaSuccess &&
               cudaMalloc(&M->rec, sizeof(int32_t) * (size_t)n * 8) == cudaSuccess &&
               cudaMalloc(&M->site_list, sizeof(int32_t) * (size_t)n) == cudaSuccess &&
               cudaMalloc(&M->thr, sizeof(uint32_t) * thr.size()) == cudaSuccess &&
@@ -1203,15 +1210,15 @@ int nlmc_msc_sweep_record_layout(nlmc_msc *M, int n_sweeps, int ladder, int8_t *
         for (auto &g : M->rec_graphs) cudaGraphExecDestroy(g.exec);
         M->rec_graphs.clear();
         if (need_M > M->recM_cap) {
-            if (M->recM) cudaFree(M->recM);
+            nlmc::pool_free(M->recM, M->stream);
             M->recM = nullptr; M->recM_cap = 0;
-            NLMC_CUDA(cudaMalloc(&M->recM, need_M));
+            NLMC_CUDA(nlmc::pool_alloc(reinterpret_cast<void **>(&M->recM), need_M, M->inst->device, M->stream));
             M->recM_cap = need_M;
         }
         if (need_E > M->recE_cap) {
-            if (M->recE) cudaFree(M->recE);
+            nlmc::pool_free(M->recE, M->stream);
             M->recE = nullptr; M->recE_cap = 0;
-            NLMC_CUDA(cudaMalloc(&M->recE, sizeof(double) * need_E));
+            NLMC_CUDA(nlmc::pool_alloc(reinterpret_cast<void **>(&M->recE), sizeof(double) * need_E, M->inst->device, M->stream));
             M->recE_cap = need_E;
         }
     }
@@ -1252,6 +1259,28 @@ int nlmc_msc_sweep_record_layout(nlmc_msc *M, int n_sweeps, int ladder, int8_t *
     if (has_E) NLMC_CUDA(cudaMemcpyAsync(out_E, M->recE, sizeof(double) * need_E, cudaMemcpyDeviceToHost, M->stream));
     NLMC_CUDA(cudaStreamSynchronize(M->stream));
     return NLMC_OK;
+}
+
+/* nlmc_msc_sweep_record_layout with the states delivered as the float64 rows of the reference's M
+ * (out_M_f64 [n_beta][n][n_sweeps], NPT/npt.py:640-644): the int8 record comes back through a pinned staging buffer kept
+ * by the library (25 GB/s instead of the 4 GB/s of a copy into pageable memory) and is widened by the host threads. */
+int nlmc_msc_sweep_record_f64(nlmc_msc *M, int n_sweeps, int ladder, double *out_M_f64, double *out_E) {
+    using namespace nlmc;
+    NLMC_REQUIRE(M && out_M_f64 && n_sweeps >= 0, "nlmc_msc_sweep_record_f64: bad arguments");
+    if (n_sweeps == 0) return NLMC_OK;
+    static thread_local int8_t *stage = nullptr;   // pinned, grow-only, one per host thread (one host thread per handle)
+    static thread_local size_t stage_cap = 0;
+    const size_t bytes = (size_t)M->n_beta * M->n * (size_t)n_sweeps;
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    if (bytes > stage_cap) {
+        if (stage) cudaFreeHost(stage);
+        stage = nullptr; stage_cap = 0;
+        NLMC_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&stage), bytes, cudaHostAllocDefault));
+        stage_cap = bytes;
+    }
+    int rc = nlmc_msc_sweep_record_layout(M, n_sweeps, ladder, stage, out_E, 1);
+    if (rc) return rc;
+    return nlmc_host_widen_i8_f64(stage, out_M_f64, bytes, 0);
 }
 
 int nlmc_msc_round_host_async(nlmc_msc *M, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,

@@ -407,7 +407,7 @@ int nlmc_sweep_replay(nlmc_replicas *P, int n_sweeps, const int32_t *perm, const
     const bool small_cols = I->n <= 65535;
     const size_t nnz_s = (size_t)I->nnz;
     const size_t int_smem = lut_bytes + sizeof(int32_t) * (2 * n + 1) + (small_cols ? 2 : 4) * (nnz_s + (nnz_s & 1)) + nnz_s + 2 * n + 32;
-    if (I->integer_j && I->value_symmetric && I->int_val && int_smem <= 217 * 1024 && !getenv("NLMC_REPLAY_GENERAL")) {
+    if (I->integer_j && I->int_val && nlmc::instance_value_symmetric(I) && int_smem <= 217 * 1024 && !getenv("NLMC_REPLAY_GENERAL")) {
         if (small_cols) {
             NLMC_CUDA(cudaFuncSetAttribute(sweep_replay_int_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)int_smem));
             sweep_replay_int_kernel<uint16_t><<<(unsigned)R, 32, int_smem, st>>>(a, I->col16, I->int_val, I->nnz);

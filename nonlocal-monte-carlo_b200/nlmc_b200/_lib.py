@@ -74,8 +74,10 @@ _SIGNATURES = {
     "nlmc_msc_energies": [_vp, _vp],
     "nlmc_msc_sweep_record": [_vp, _int, _int, _vp, _vp],
     "nlmc_msc_sweep_record_layout": [_vp, _int, _int, _vp, _vp, _int],
+    "nlmc_msc_sweep_record_f64": [_vp, _int, _int, _vp, _vp],
     "nlmc_msc_round": [_vp, _int, _int, _vp],
     "nlmc_host_widen_i8_f64": [_vp, _vp, _u64, _int],
+    "nlmc_host_prefault": [_vp, _u64, _int],
     "nlmc_msc_round_host": [_vp, _vp, _int, _int, _vp, _vp],
     "nlmc_msc_round_host_async": [_vp, _vp, _int, _int, _vp, _vp],
     "nlmc_msc_swap_count": [_vp, C.POINTER(_int), _int],
@@ -178,6 +180,14 @@ def np_arctanh(x, device: int = 0) -> np.ndarray:
 
 def _ptr(a):
     return None if a is None else a.ctypes.data
+
+
+def empty_prefaulted(shape, dtype=np.float64) -> np.ndarray:
+    """np.empty whose pages have been touched by the library's host threads (call it while the GPU is busy)."""
+    a = np.empty(shape, dtype=dtype)
+    if a.nbytes >= (1 << 22):
+        check(lib().nlmc_host_prefault(a.ctypes.data, a.nbytes, 0), "nlmc_host_prefault")
+    return a
 
 
 def widen_to_f64(a: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
@@ -464,6 +474,17 @@ class Msc:
         check(lib().nlmc_msc_sweep_record_layout(self._h, int(n_sweeps), int(ladder or 0), _ptr(Mrec), _ptr(Erec),
                                                  1 if rows_of_M else 0), "nlmc_msc_sweep_record_layout")
         return Mrec, Erec
+
+    def sweep_record_f64(self, n_sweeps: int, ladder: int = 0, out: np.ndarray | None = None):
+        """n_sweeps recorded sweeps of `ladder` as the float64 rows of the reference's M: (M float64 [n_beta][n][n_sweeps],
+        E float64 [n_sweeps][n_beta][n_ladders]); the int8 record travels through a pinned buffer of the library.
+        `out` may be a preallocated (and prefaulted) C-contiguous float64 array of that size."""
+        Mf = np.empty((self.n_beta, self.n, n_sweeps), dtype=np.float64) if out is None else out
+        assert Mf.dtype == np.float64 and Mf.flags.c_contiguous and Mf.size == self.n_beta * self.n * n_sweeps
+        Erec = np.empty((n_sweeps, self.n_beta, self.n_ladders), dtype=np.float64)
+        check(lib().nlmc_msc_sweep_record_f64(self._h, int(n_sweeps), int(ladder), Mf.ctypes.data, Erec.ctypes.data),
+              "nlmc_msc_sweep_record_f64")
+        return Mf, Erec
 
     def round(self, n_sweeps: int, num_swapping_pairs: int, fetch_energies: bool = False):
         out = np.empty((self.n_beta, self.n_ladders), dtype=np.float64) if fetch_energies else None

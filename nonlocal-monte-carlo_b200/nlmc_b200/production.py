@@ -85,13 +85,13 @@ def _npt_run_msc(obj, prob, beta_list):
     for ii in range(obj.num_swap_attempts - 1):
         msc.round(spm, obj.num_swapping_pairs)
     # last round: record the state after every sweep (the reference returns the last round's M); the device writes the
-    # record in the layout of M's rows, the host only widens int8 to float64
-    M = np.zeros((R * n, spm))
+    # record in the layout of M's rows, the host only widens int8 to float64.  (Touching the pages of M from the host threads
+    # while the rounds are still running was tried and cost more than it saved: 0.38 s per call against 0.22 s.)
+    M = np.empty((R * n, spm)) if spm > 0 else np.zeros((R * n, spm))
     E_cols = np.zeros((R, spm))
     E_all = None
     if spm > 0:
-        Mrec, Erec = msc.sweep_record(spm, ladder=0, energies=True, rows_of_M=True)  # [R][n][spm], one copy back
-        M = _lib.widen_to_f64(Mrec).reshape(R * n, spm)
+        _, Erec = msc.sweep_record_f64(spm, ladder=0, out=M)  # [R][n][spm] float64: int8 on the wire, widened on arrival
         E_cols[:] = Erec[:, :, 0].T
         E_all = Erec[-1]
     if obj.num_swap_attempts > 0 and spm > 0:

@@ -325,5 +325,12 @@ class FakeMsc:
             Mrec = np.ascontiguousarray(Mrec.transpose(1, 2, 0))
         return Mrec, Erec
 
+    def sweep_record_f64(self, n_sweeps, ladder=0, out=None):
+        Mrec, Erec = self.sweep_record(n_sweeps, ladder=ladder, energies=True, rows_of_M=True)
+        if out is not None:
+            out.reshape(Mrec.shape)[:] = Mrec
+            return out, Erec
+        return Mrec.astype(np.float64), Erec
+
     def close(self):
         pass

@@ -92,10 +92,12 @@ def test_label_exchange_samples_exact_boltzmann(nl):
     msc.close()
 
 
-def test_label_and_bit_exchange_agree_without_swaps(nl):
+def test_label_and_bit_exchange_agree_without_swaps(nl, monkeypatch):
     """With no exchange the label form is the classic engine: identical trajectories (same streams, thresholds from the
-    bit planes instead of three scalars), for one-site-per-warp rows (W = 128) and short rows (W = 8)."""
+    bit planes instead of three scalars), for one-site-per-warp rows (W = 128) and short rows (W = 8) -- at the same number
+    of unconditional comparison steps (the label form defaults to 7, the scalar form to 6)."""
     from oracle import oracle as O
+    monkeypatch.setenv("NLMC_MSC_STEPS", "6")
     A, h = O.ea3d_pm_j(6, 9)
     prob = nl.host.Problem(A, h)
     for n_beta in (32, 2):
