@@ -22,8 +22,13 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 FLAGS += os.environ.get("NLMC_NVCC_EXTRA", "").split()  # e.g. -DNLMC_PHILOX_ROUNDS=7 for an experiment build
 
 
+CXX = os.environ.get("CXX", "g++")
+CXXFLAGS = ["-O3", "-std=c++17", "-fPIC", "-pthread", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+
+
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    """CUDA sources (nvcc, sm_100a) and the plain C++ host helpers (g++)."""
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
 
 
 def _stale(target, deps):
@@ -40,12 +45,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     jobs = []
     objs = []
     for src in sources():
-        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(OBJ, os.path.splitext(os.path.basename(src))[0] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
-            if verbose:
-                cmd.insert(1, "-Xptxas=-v")
+            if src.endswith(".cpp"):
+                cmd = [CXX, *CXXFLAGS, "-c", src, "-o", obj]
+            else:
+                cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
+                if verbose:
+                    cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)
 
     def run(cmd):
@@ -61,7 +69,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
                 if rc:
                     raise RuntimeError(f"nvcc failed for {cmd[-3]}")
     if jobs or force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart"]
+        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-lpthread"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode:
             print(p.stdout + p.stderr)

@@ -5,6 +5,7 @@
 #include <utility>
 
 #include "nlmc_common.cuh"
+#include "nlmc_hostpar.h"
 
 namespace nlmc {
 static thread_local char g_err[512] = "";
@@ -112,15 +113,35 @@ int nlmc_instance_create(int n, const int32_t *row_ptr, const int32_t *col, cons
     const int nnz = row_ptr[n];
     NLMC_REQUIRE(nnz >= 0 && (nnz == 0 || (col && val)), "nlmc_instance_create: col/val missing");
     int max_deg = 0;
-    bool integer_j = true;
     for (int i = 0; i < n; ++i) {
         NLMC_REQUIRE(row_ptr[i + 1] >= row_ptr[i], "nlmc_instance_create: row_ptr not monotone at row %d", i);
         max_deg = std::max(max_deg, row_ptr[i + 1] - row_ptr[i]);
     }
-    for (int p = 0; p < nnz; ++p) {
-        NLMC_REQUIRE(col[p] >= 0 && col[p] < n, "nlmc_instance_create: column index out of range at entry %d", p);
-        if (val[p] != std::floor(val[p]) || std::fabs(val[p]) > 1e6) integer_j = false;
+    // one pass over the entries on the host workers: range check, integer / small-integer flags, and the compact
+    // int8 / uint16 copies the shared-memory replay kernel reads (integer J only)
+    const int parts = nnz >= (1 << 18) ? nlmc::host_threads() : 1;
+    std::vector<int> bad((size_t)parts, -1);
+    std::vector<char> not_int((size_t)parts, 0), not_small((size_t)parts, 0);
+    std::vector<int8_t> v8((size_t)nnz);
+    std::vector<uint16_t> c16(n <= 65535 ? (size_t)nnz : 0);
+    nlmc::parallel_for(parts, [&](int t, int np) {
+        const int per = (nnz + np - 1) / np, lo = std::min(nnz, per * t), hi = std::min(nnz, lo + per);
+        for (int p = lo; p < hi; ++p) {
+            if (col[p] < 0 || col[p] >= n) { if (bad[(size_t)t] < 0) bad[(size_t)t] = p; continue; }
+            const double v = val[p];
+            if (v != std::floor(v) || std::fabs(v) > 1e6) not_int[(size_t)t] = 1;
+            if (!(std::fabs(v) <= 127.0)) not_small[(size_t)t] = 1;
+            v8[(size_t)p] = (int8_t)(std::fabs(v) <= 127.0 ? v : 0.0);
+            if (!c16.empty()) c16[(size_t)p] = (uint16_t)col[p];
+        }
+    });
+    bool integer_j = true, small_int = nnz > 0;
+    for (int t = 0; t < parts; ++t) {
+        NLMC_REQUIRE(bad[(size_t)t] < 0, "nlmc_instance_create: column index out of range at entry %d", bad[(size_t)t]);
+        if (not_int[(size_t)t]) integer_j = false;
+        if (not_small[(size_t)t]) small_int = false;
     }
+    small_int = small_int && integer_j;
     NLMC_CUDA(cudaSetDevice(device));
     auto *I = new nlmc_instance();
     I->device = device;
@@ -133,39 +154,29 @@ int nlmc_instance_create(int n, const int32_t *row_ptr, const int32_t *col, cons
     I->h_val.assign(val, val + nnz);
     I->h_h.assign(h, h + n);
     auto fail = [&](void) {
+        nlmc::set_error("nlmc_instance_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         nlmc_instance_destroy(I);
         return NLMC_ERR_CUDA;
     };
+    // Device arrays come from the stream-ordered pool (every NPT.run builds its own instance: cudaMalloc / cudaFree of
+    // seven arrays was 10 ms per call at C5 size); the copies are queued on the instance's stream and waited for once.
     const size_t nz = (size_t)std::max(nnz, 1);
-    if (cudaStreamCreateWithFlags(&I->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&I->row_ptr, sizeof(int32_t) * (size_t)(n + 1)) != cudaSuccess ||
-        cudaMalloc(&I->col, sizeof(int32_t) * nz) != cudaSuccess ||
-        cudaMalloc(&I->val, sizeof(double) * nz) != cudaSuccess ||
-        cudaMalloc(&I->h, sizeof(double) * (size_t)n) != cudaSuccess ||
-        cudaMemcpy(I->row_ptr, row_ptr, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
-        (nnz && cudaMemcpy(I->col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice) != cudaSuccess) ||
-        (nnz && cudaMemcpy(I->val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice) != cudaSuccess) ||
-        cudaMemcpy(I->h, h, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
-        nlmc::set_error("nlmc_instance_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return fail();
-    }
-    // compact copies for the shared-memory replay kernel (integer J only)
-    bool small_int = integer_j && nnz > 0;
-    for (int p = 0; p < nnz && small_int; ++p) small_int = std::fabs(val[p]) <= 127.0;
-    if (small_int) {
-        std::vector<int8_t> v8((size_t)nnz);
-        std::vector<uint16_t> c16((size_t)nnz);
-        for (int p = 0; p < nnz; ++p) { v8[(size_t)p] = (int8_t)val[p]; c16[(size_t)p] = (uint16_t)col[p]; }
-        bool ok = cudaMalloc(&I->int_val, (size_t)nnz) == cudaSuccess &&
-                  cudaMemcpy(I->int_val, v8.data(), (size_t)nnz, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (cudaStreamCreateWithFlags(&I->stream, cudaStreamNonBlocking) != cudaSuccess) return fail();
+    cudaStream_t st = I->stream;
+    auto up = [&](void **dst, const void *src, size_t alloc_bytes, size_t copy_bytes) {
+        if (nlmc::pool_alloc(dst, alloc_bytes, device, st) != cudaSuccess) return false;
+        return copy_bytes == 0 || cudaMemcpyAsync(*dst, src, copy_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    };
+    bool ok = up(reinterpret_cast<void **>(&I->row_ptr), row_ptr, sizeof(int32_t) * (size_t)(n + 1), sizeof(int32_t) * (size_t)(n + 1)) &&
+              up(reinterpret_cast<void **>(&I->col), col, sizeof(int32_t) * nz, sizeof(int32_t) * (size_t)nnz) &&
+              up(reinterpret_cast<void **>(&I->val), val, sizeof(double) * nz, sizeof(double) * (size_t)nnz) &&
+              up(reinterpret_cast<void **>(&I->h), h, sizeof(double) * (size_t)n, sizeof(double) * (size_t)n);
+    if (ok && small_int) {
+        ok = up(reinterpret_cast<void **>(&I->int_val), v8.data(), (size_t)nnz, (size_t)nnz);
         if (ok && n <= 65535)
-            ok = cudaMalloc(&I->col16, sizeof(uint16_t) * (size_t)nnz) == cudaSuccess &&
-                 cudaMemcpy(I->col16, c16.data(), sizeof(uint16_t) * (size_t)nnz, cudaMemcpyHostToDevice) == cudaSuccess;
-        if (!ok) {
-            nlmc::set_error("nlmc_instance_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-            return fail();
-        }
+            ok = up(reinterpret_cast<void **>(&I->col16), c16.data(), sizeof(uint16_t) * (size_t)nnz, sizeof(uint16_t) * (size_t)nnz);
     }
+    if (!ok || cudaStreamSynchronize(st) != cudaSuccess) return fail();  // v8 / c16 and the caller's arrays may go away
     *out = I;
     return NLMC_OK;
 }
@@ -174,56 +185,30 @@ int nlmc_instance_create(int n, const int32_t *row_ptr, const int32_t *col, cons
  * (M is float64 +-1, NMC/nmc.py:52,89), on `threads` host threads (0 = hardware concurrency, at most 32). */
 int nlmc_host_widen_i8_f64(const int8_t *in, double *out, uint64_t count, int threads) {
     NLMC_REQUIRE(count == 0 || (in && out), "nlmc_host_widen_i8_f64: NULL argument");
-    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
-    nt = std::max(1, std::min(nt, 32));
-    if (count < (1u << 20)) nt = 1;
-    auto work = [&](uint64_t lo, uint64_t hi) {
-        for (uint64_t i = lo; i < hi; ++i) out[i] = (double)in[i];
-    };
-    if (nt == 1) { work(0, count); return NLMC_OK; }
-    std::vector<std::thread> pool;
-    const uint64_t per = (count + (uint64_t)nt - 1) / (uint64_t)nt;
-    for (int t = 0; t < nt; ++t) {
-        const uint64_t lo = std::min(count, per * (uint64_t)t), hi = std::min(count, lo + per);
-        if (lo < hi) pool.emplace_back(work, lo, hi);
-    }
-    for (auto &th : pool) th.join();
+    nlmc::widen_i8_f64(in, out, count, threads);
     return NLMC_OK;
 }
 
-/* Touch every page of a freshly allocated host buffer on `threads` host threads (0 = hardware concurrency, at most 32), so
- * that the first-touch page faults of a large result array (the 1 GB float64 M of config C5) are taken while the GPU is
- * still sweeping instead of inside the final widening. */
+/* Touch every page of a freshly allocated host buffer on `threads` host threads (0 = all), so that the first-touch page
+ * faults of a large result array (the 1 GB float64 M of config C5) are taken while the GPU is still sweeping instead of
+ * inside the final widening. */
 int nlmc_host_prefault(void *buf, uint64_t bytes, int threads) {
     NLMC_REQUIRE(bytes == 0 || buf, "nlmc_host_prefault: NULL argument");
-    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
-    nt = std::max(1, std::min(nt, 32));
-    if (bytes < (1u << 22)) nt = 1;
-    volatile char *p = static_cast<volatile char *>(buf);
-    auto work = [&](uint64_t lo, uint64_t hi) {
-        for (uint64_t i = lo; i < hi; i += 4096) p[i] = 0;
-    };
-    if (nt == 1) { work(0, bytes); return NLMC_OK; }
-    std::vector<std::thread> pool;
-    const uint64_t per = (((bytes + (uint64_t)nt - 1) / (uint64_t)nt) + 4095) & ~4095ull;
-    for (int t = 0; t < nt; ++t) {
-        const uint64_t lo = std::min(bytes, per * (uint64_t)t), hi = std::min(bytes, lo + per);
-        if (lo < hi) pool.emplace_back(work, lo, hi);
-    }
-    for (auto &th : pool) th.join();
+    nlmc::prefault(buf, bytes, threads);
     return NLMC_OK;
 }
 
 int nlmc_instance_destroy(nlmc_instance *I) {
     if (!I) return NLMC_OK;
     cudaSetDevice(I->device);
-    if (I->row_ptr) cudaFree(I->row_ptr);
-    if (I->col) cudaFree(I->col);
-    if (I->val) cudaFree(I->val);
-    if (I->h) cudaFree(I->h);
+    cudaDeviceSynchronize();  // handles built on this instance read its arrays from their own streams
+    void *ptrs[] = {I->row_ptr, I->col, I->val, I->h, I->int_val, I->col16};
+    if (I->stream) {  // back to the pool in stream order
+        for (void *p : ptrs) nlmc::pool_free(p, I->stream);
+    } else {
+        for (void *p : ptrs) if (p) cudaFree(p);
+    }
     if (I->rev) cudaFree(I->rev);
-    if (I->int_val) cudaFree(I->int_val);
-    if (I->col16) cudaFree(I->col16);
     if (I->stream) cudaStreamDestroy(I->stream);
     delete I;
     return NLMC_OK;

@@ -25,6 +25,7 @@
 #include <cstdlib>
 
 #include "nlmc_common.cuh"
+#include "nlmc_hostpar.h"
 
 struct nlmc_msc {
     nlmc_instance *inst = nullptr;
@@ -162,7 +163,10 @@ template <int kSteps, bool kPerBit, bool kSubWarp>
 #ifndef NLMC_PERBIT_CTAS
 #define NLMC_PERBIT_CTAS 4  // resident CTAs per SM of the bit-plane variant (64 registers: no spills)
 #endif
-__global__ void __launch_bounds__(256, kPerBit ? NLMC_PERBIT_CTAS : 5) msc_sweep_kernel(MscDev a, int first, int n_sites, const uint32_t *__restrict__ counters, uint32_t sweep_in_batch) {
+#ifndef NLMC_SCALAR_CTAS
+#define NLMC_SCALAR_CTAS 5  // resident CTAs per SM of the scalar-threshold variant
+#endif
+__global__ void __launch_bounds__(256, kPerBit ? NLMC_PERBIT_CTAS : NLMC_SCALAR_CTAS) msc_sweep_kernel(MscDev a, int first, int n_sites, const uint32_t *__restrict__ counters, uint32_t sweep_in_batch) {
     const uint32_t sweep = counters[0] + sweep_in_batch;
     int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);  // site of this colour
     const int lane = threadIdx.x & 31;
@@ -182,17 +186,23 @@ __global__ void __launch_bounds__(256, kPerBit ? NLMC_PERBIT_CTAS : 5) msc_sweep
     const int nb[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
     const uint32_t meta = (uint32_t)r1.z;
     const int site = r1.w;
+    // All six row loads are issued back to back (a padding slot reads row 0 and is masked below): with the sign flip
+    // predicated on each load's result the compiler serialised them -- one memory latency per neighbour (ncu, round 2:
+    // long-scoreboard 3.3 warps per issue, two thirds of a warp's lifetime in this prologue).
     uint4 x[6];
 #pragma unroll
+    for (int d = 0; d < 6; ++d)
+        x[d] = *reinterpret_cast<const uint4 *>(a.S + (size_t)max(nb[d], 0) * a.W + word0);
+#pragma unroll
     for (int d = 0; d < 6; ++d) {
-        const int j = nb[d];
-        if (j >= 0) {
-            x[d] = *reinterpret_cast<const uint4 *>(a.S + (size_t)j * a.W + word0);
-            if ((meta >> d) & 1u) { x[d].x = ~x[d].x; x[d].y = ~x[d].y; x[d].z = ~x[d].z; x[d].w = ~x[d].w; }
-        } else {  // padding comes in (+1, -1) pairs: even degrees only
-            const uint32_t v = (d & 1) ? 0u : 0xffffffffu;
-            x[d] = make_uint4(v, v, v, v);
-        }
+        // x <- (x & keep) ^ flip: a neighbour keeps its bits and is inverted when J < 0; padding comes in (+1, -1) pairs
+        // (even degrees only).  One three-input logic operation per word, no branch.
+        const uint32_t keep = nb[d] >= 0 ? 0xffffffffu : 0u;
+        const uint32_t flip = nb[d] >= 0 ? 0u - ((meta >> d) & 1u) : ((d & 1) ? 0u : 0xffffffffu);
+        x[d].x = (x[d].x & keep) ^ flip;
+        x[d].y = (x[d].y & keep) ^ flip;
+        x[d].z = (x[d].z & keep) ^ flip;
+        x[d].w = (x[d].w & keep) ^ flip;
     }
     // lane sets of the |f| levels 1..3 (|f| = 2, 4, 6), level 0 being the rest; sign plane pos = [c >= 4]
     uint32_t I1[4], I2[4], I3[4], pos[4], res[4], und[4];
@@ -801,16 +811,13 @@ int nlmc_msc_destroy(nlmc_msc *M) {
     if (!M) return NLMC_OK;
     cudaSetDevice(M->inst->device);
     nlmc::drop_graphs(M);
-    if (M->stream) {   // the big buffers go back to the pool in stream order (after whatever is still queued)
-        nlmc::pool_free(M->S, M->stream);
-        nlmc::pool_free(M->recM, M->stream);
-        nlmc::pool_free(M->recE, M->stream);
-        cudaStreamSynchronize(M->stream);
-    }
-    void *ptrs[] = {M->rec, M->site_list, M->thr, M->betas, M->E_acc, M->E, M->swapmask, M->accepted,
+    void *ptrs[] = {M->S, M->recM, M->recE, M->rec, M->site_list, M->thr, M->betas, M->E_acc, M->E, M->swapmask, M->accepted,
                     M->scratch_spins, M->d_counters, M->labels, M->slot_of, M->thr_total,
                     M->betas_total, M->thrbits, M->thr_lane, M->accepted_rounds};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    if (M->stream) {   // every buffer goes back to the pool in stream order (after whatever is still queued)
+        for (void *p : ptrs) nlmc::pool_free(p, M->stream);
+        cudaStreamSynchronize(M->stream);
+    }
     if (M->ev0) cudaEventDestroy(M->ev0);
     if (M->ev1) cudaEventDestroy(M->ev1);
     if (M->stream && M->own_stream) cudaStreamDestroy(M->stream);
@@ -830,38 +837,62 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
     NLMC_REQUIRE(n_ladders >= 1, "nlmc_msc_create: n_ladders must be >= 1");
     NLMC_REQUIRE(ladder_offset >= 0 && ladder_offset % 128 == 0, "nlmc_msc_create: ladder_offset must be a multiple of 128");
     const int n = I->n;
-    // eligibility: J in {-1,+1} off the diagonal, h = 0, even degrees <= 6
+    // eligibility: J in {-1,+1} off the diagonal, h = 0, even degrees <= 6 (site ranges on the host workers; the first
+    // offending site of each range is reported in site order)
     std::vector<int32_t> nbr((size_t)n * 6, -1);
     std::vector<uint32_t> meta((size_t)n, 0u);
+    const int parts = n >= (1 << 16) ? nlmc::host_threads() : 1;
+    struct Issue { int kind = 0, i = -1, j = -1; double v = 0.0; };   // 1: h != 0, 2: bad value, 3: degree > 6, 4: odd degree
+    std::vector<Issue> issues((size_t)parts);
+    std::vector<long long> entries((size_t)parts, 0);
+    nlmc::parallel_for(parts, [&](int t, int np) {
+        const int per = (n + np - 1) / np, lo = std::min(n, per * t), hi = std::min(n, lo + per);
+        Issue &is = issues[(size_t)t];
+        for (int i = lo; i < hi && !is.kind; ++i) {
+            if (I->h_h[(size_t)i] != 0.0) { is = {1, i, -1, I->h_h[(size_t)i]}; break; }
+            int d = 0;
+            for (int p = I->h_row_ptr[i]; p < I->h_row_ptr[i + 1]; ++p) {
+                const double v = I->h_val[(size_t)p];
+                const int j = I->h_col[(size_t)p];
+                if (v == 0.0) continue;
+                if (j == i || (v != 1.0 && v != -1.0)) { is = {2, i, j, v}; break; }
+                if (d == 6) { is = {3, i, -1, 0.0}; break; }
+                nbr[(size_t)i * 6 + d] = j;
+                if (v < 0) meta[(size_t)i] |= 1u << d;
+                ++d;
+            }
+            if (!is.kind && (d & 1)) is = {4, i, d, 0.0};
+            entries[(size_t)t] += d;
+        }
+    });
     long long n_entries = 0;
-    for (int i = 0; i < n; ++i) {
-        if (I->h_h[(size_t)i] != 0.0) {
-            set_error("nlmc_msc_create: the bit-packed path needs h = 0 (h[%d] = %g)", i, I->h_h[(size_t)i]);
-            return NLMC_ERR_UNSUPPORTED;
-        }
-        int d = 0;
-        for (int p = I->h_row_ptr[i]; p < I->h_row_ptr[i + 1]; ++p) {
-            const double v = I->h_val[(size_t)p];
-            const int j = I->h_col[(size_t)p];
-            if (v == 0.0) continue;
-            if (j == i || (v != 1.0 && v != -1.0)) {
-                set_error("nlmc_msc_create: the bit-packed path needs J in {-1,+1} with zero diagonal (J[%d,%d] = %g)", i, j, v);
-                return NLMC_ERR_UNSUPPORTED;
-            }
-            if (d == 6) {
-                set_error("nlmc_msc_create: the bit-packed path supports degrees <= 6 (site %d)", i);
-                return NLMC_ERR_UNSUPPORTED;
-            }
-            nbr[(size_t)i * 6 + d] = j;
-            if (v < 0) meta[(size_t)i] |= 1u << d;
-            ++d;
-        }
-        if (d & 1) {
-            set_error("nlmc_msc_create: the bit-packed path supports even degrees only (site %d has %d)", i, d);
-            return NLMC_ERR_UNSUPPORTED;
-        }
-        n_entries += d;
+    for (int t = 0; t < parts; ++t) {
+        const Issue &is = issues[(size_t)t];
+        if (is.kind == 1) set_error("nlmc_msc_create: the bit-packed path needs h = 0 (h[%d] = %g)", is.i, is.v);
+        if (is.kind == 2)
+            set_error("nlmc_msc_create: the bit-packed path needs J in {-1,+1} with zero diagonal (J[%d,%d] = %g)", is.i, is.j, is.v);
+        if (is.kind == 3) set_error("nlmc_msc_create: the bit-packed path supports degrees <= 6 (site %d)", is.i);
+        if (is.kind == 4)
+            set_error("nlmc_msc_create: the bit-packed path supports even degrees only (site %d has %d)", is.i, is.j);
+        if (is.kind) return NLMC_ERR_UNSUPPORTED;
+        n_entries += entries[(size_t)t];
     }
+    // symmetric adjacency is required for a valid colouring / detailed balance
+    std::vector<int> asym_i((size_t)parts, -1), asym_j((size_t)parts, -1);
+    nlmc::parallel_for(parts, [&](int t, int np) {
+        const int per = (n + np - 1) / np, lo = std::min(n, per * t), hi = std::min(n, lo + per);
+        for (int i = lo; i < hi && asym_i[(size_t)t] < 0; ++i)
+            for (int d = 0; d < 6; ++d) {
+                const int j = nbr[(size_t)i * 6 + d];
+                if (j < 0) continue;
+                bool back = false;
+                for (int e = 0; e < 6; ++e) back |= nbr[(size_t)j * 6 + e] == i;
+                if (!back) { asym_i[(size_t)t] = i; asym_j[(size_t)t] = j; break; }
+            }
+    });
+    for (int t = 0; t < parts; ++t)
+        NLMC_REQUIRE(asym_i[(size_t)t] < 0, "nlmc_msc_create: J must be symmetric (entry %d,%d has no transpose)",
+                     asym_i[(size_t)t], asym_j[(size_t)t]);
     // greedy colouring in site order (checkerboard on bipartite lattices with even L)
     std::vector<int> colour((size_t)n, -1);
     int n_colours = 0;
@@ -876,15 +907,6 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
         colour[(size_t)i] = c;
         n_colours = std::max(n_colours, c + 1);
     }
-    // symmetric adjacency is required for a valid colouring / detailed balance
-    for (int i = 0; i < n; ++i)
-        for (int d = 0; d < 6; ++d) {
-            const int j = nbr[(size_t)i * 6 + d];
-            if (j < 0) continue;
-            bool back = false;
-            for (int e = 0; e < 6; ++e) back |= nbr[(size_t)j * 6 + e] == i;
-            NLMC_REQUIRE(back, "nlmc_msc_create: J must be symmetric (entry %d,%d has no transpose)", i, j);
-        }
     std::vector<int32_t> site_list((size_t)n);
     std::vector<int> colour_ptr((size_t)n_colours + 1, 0);
     for (int i = 0; i < n; ++i) ++colour_ptr[(size_t)colour[(size_t)i] + 1];
@@ -916,54 +938,59 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
     if (const char *e = getenv("NLMC_MSC_GRAPHS")) M->use_graphs = atoi(e) != 0;
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(n_beta, betas);
     std::vector<int32_t> rec((size_t)n * 8, 0);  // records in site_list order: 6 neighbours, sign bits, site
-    for (int p = 0; p < n; ++p) {
-        const int i = site_list[(size_t)p];
-        for (int d = 0; d < 6; ++d) rec[(size_t)p * 8 + d] = nbr[(size_t)i * 6 + d];
-        rec[(size_t)p * 8 + 6] = (int32_t)meta[(size_t)i];
-        rec[(size_t)p * 8 + 7] = i;
-    }
+    nlmc::parallel_for(parts, [&](int t, int np) {
+        const int per = (n + np - 1) / np, lo = std::min(n, per * t), hi = std::min(n, lo + per);
+        for (int p = lo; p < hi; ++p) {
+            const int i = site_list[(size_t)p];
+            for (int d = 0; d < 6; ++d) rec[(size_t)p * 8 + d] = nbr[(size_t)i * 6 + d];
+            rec[(size_t)p * 8 + 6] = (int32_t)meta[(size_t)i];
+            rec[(size_t)p * 8 + 7] = i;
+        }
+    });
     const size_t words = (size_t)n * M->W;
+    // every buffer comes from the stream-ordered pool and every copy / memset is queued on the handle's stream: a
+    // handle per NPT.run call costs no cudaMalloc / cudaFree (19 -> 6 ms per create at C5 size)
     bool ok = cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreate(&M->ev0) == cudaSuccess && cudaEventCreate(&M->ev1) == cudaSuccess &&
-              nlmc::pool_alloc(reinterpret_cast<void **>(&M->S), sizeof(uint32_t) * words, I->device, M->stream) == cudaSuccess &&
-              cudaMalloc(&M->rec, sizeof(int32_t) * (size_t)n * 8) == cudaSuccess &&
-              cudaMalloc(&M->site_list, sizeof(int32_t) * (size_t)n) == cudaSuccess &&
-              cudaMalloc(&M->thr, sizeof(uint32_t) * thr.size()) == cudaSuccess &&
-              cudaMalloc(&M->betas, sizeof(double) * (size_t)n_beta) == cudaSuccess &&
-              cudaMalloc(&M->E_acc, sizeof(int32_t) * (size_t)M->W * 32) == cudaSuccess &&
-              cudaMalloc(&M->E, sizeof(double) * (size_t)n_beta * M->n_ladders) == cudaSuccess &&
-              cudaMalloc(&M->swapmask, sizeof(uint32_t) * (size_t)std::max(1, n_beta - 1) * M->G) == cudaSuccess &&
-              cudaMalloc(&M->accepted, sizeof(int32_t)) == cudaSuccess &&
-              cudaMalloc(&M->accepted_rounds, sizeof(int32_t) * kRoundLog) == cudaSuccess &&
-              cudaMemset(M->accepted_rounds, 0, sizeof(int32_t) * kRoundLog) == cudaSuccess &&
-              cudaMalloc(&M->d_counters, 4 * sizeof(uint32_t)) == cudaSuccess &&
-              cudaMemset(M->d_counters, 0, 4 * sizeof(uint32_t)) == cudaSuccess &&
-              cudaMalloc(&M->scratch_spins, (size_t)n) == cudaSuccess &&
-              cudaMemcpy(M->rec, rec.data(), sizeof(int32_t) * rec.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMemcpy(M->site_list, site_list.data(), sizeof(int32_t) * site_list.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMemcpy(M->thr, thr.data(), sizeof(uint32_t) * thr.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMemcpy(M->betas, betas, sizeof(double) * (size_t)n_beta, cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMemset(M->accepted, 0, sizeof(int32_t)) == cudaSuccess;
-    if (!ok) {
+              cudaEventCreate(&M->ev0) == cudaSuccess && cudaEventCreate(&M->ev1) == cudaSuccess;
+    cudaStream_t st = M->stream;
+    auto alloc = [&](auto **ptr, size_t bytes) {
+        return nlmc::pool_alloc(reinterpret_cast<void **>(ptr), bytes, I->device, st) == cudaSuccess;
+    };
+    auto put = [&](void *dst, const void *src, size_t bytes) {
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    };
+    ok = ok && alloc(&M->S, sizeof(uint32_t) * words) && alloc(&M->rec, sizeof(int32_t) * (size_t)n * 8) &&
+         alloc(&M->site_list, sizeof(int32_t) * (size_t)n) && alloc(&M->thr, sizeof(uint32_t) * thr.size()) &&
+         alloc(&M->betas, sizeof(double) * (size_t)n_beta) && alloc(&M->E_acc, sizeof(int32_t) * (size_t)M->W * 32) &&
+         alloc(&M->E, sizeof(double) * (size_t)n_beta * M->n_ladders) &&
+         alloc(&M->swapmask, sizeof(uint32_t) * (size_t)std::max(1, n_beta - 1) * M->G) && alloc(&M->accepted, sizeof(int32_t)) &&
+         alloc(&M->accepted_rounds, sizeof(int32_t) * kRoundLog) && alloc(&M->d_counters, 4 * sizeof(uint32_t)) &&
+         alloc(&M->scratch_spins, (size_t)n) &&
+         cudaMemsetAsync(M->accepted_rounds, 0, sizeof(int32_t) * kRoundLog, st) == cudaSuccess &&
+         cudaMemsetAsync(M->d_counters, 0, 4 * sizeof(uint32_t), st) == cudaSuccess &&
+         cudaMemsetAsync(M->accepted, 0, sizeof(int32_t), st) == cudaSuccess &&
+         put(M->rec, rec.data(), sizeof(int32_t) * rec.size()) &&
+         put(M->site_list, site_list.data(), sizeof(int32_t) * site_list.size()) &&
+         put(M->thr, thr.data(), sizeof(uint32_t) * thr.size()) && put(M->betas, betas, sizeof(double) * (size_t)n_beta);
+    std::vector<uint32_t> thr_t;
+    if (ok && M->label_mode) {
+        thr_t = nlmc::msc_thresholds(n_beta_total, betas_total);
+        const size_t nl = (size_t)n_beta_total * M->n_ladders;
+        ok = alloc(&M->labels, nl) && alloc(&M->slot_of, nl) && alloc(&M->thr_total, sizeof(uint32_t) * thr_t.size()) &&
+             alloc(&M->betas_total, sizeof(double) * (size_t)n_beta_total) &&
+             alloc(&M->thrbits, sizeof(uint32_t) * (size_t)M->k_steps * 3 * M->W) &&
+             alloc(&M->thr_lane, sizeof(uint32_t) * (size_t)M->W * 32 * 4) &&
+             put(M->thr_total, thr_t.data(), sizeof(uint32_t) * thr_t.size()) &&
+             put(M->betas_total, betas_total, sizeof(double) * (size_t)n_beta_total);
+    }
+    // the host vectors above (and the caller's betas) must outlive the queued copies
+    if (!ok || cudaStreamSynchronize(st) != cudaSuccess) {
         set_error("nlmc_msc_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         nlmc_msc_destroy(M);
         return NLMC_ERR_CUDA;
     }
     if (M->label_mode) {
-        const std::vector<uint32_t> thr_t = nlmc::msc_thresholds(n_beta_total, betas_total);
         const size_t nl = (size_t)n_beta_total * M->n_ladders;
-        ok = cudaMalloc(&M->labels, nl) == cudaSuccess && cudaMalloc(&M->slot_of, nl) == cudaSuccess &&
-             cudaMalloc(&M->thr_total, sizeof(uint32_t) * thr_t.size()) == cudaSuccess &&
-             cudaMalloc(&M->betas_total, sizeof(double) * (size_t)n_beta_total) == cudaSuccess &&
-             cudaMalloc(&M->thrbits, sizeof(uint32_t) * (size_t)M->k_steps * 3 * M->W) == cudaSuccess &&
-             cudaMalloc(&M->thr_lane, sizeof(uint32_t) * (size_t)M->W * 32 * 4) == cudaSuccess &&
-             cudaMemcpy(M->thr_total, thr_t.data(), sizeof(uint32_t) * thr_t.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaMemcpy(M->betas_total, betas_total, sizeof(double) * (size_t)n_beta_total, cudaMemcpyHostToDevice) == cudaSuccess;
-        if (!ok) {
-            set_error("nlmc_msc_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-            nlmc_msc_destroy(M);
-            return NLMC_ERR_CUDA;
-        }
         msc_labels_identity_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, M->stream>>>(n_beta_total, M->n_ladders, M->labels,
                                                                                       M->slot_of);
         const int rc = launch_thrbits(M);
@@ -1193,16 +1220,18 @@ int nlmc_msc_sweep_record(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, 
 }
 
 /* m_layout 0: out_M [n_sweeps][n_beta][n]; 1: out_M [n_beta][n][n_sweeps] (rows of the reference's M). */
-int nlmc_msc_sweep_record_layout(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, double *out_E, int m_layout) {
+// keep_M_on_device: the states are recorded into M->recM and left there (the caller fetches them itself)
+static int msc_record_impl(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, double *out_E, int m_layout,
+                           bool keep_M_on_device) {
     using namespace nlmc;
     NLMC_REQUIRE(m_layout == 0 || m_layout == 1, "nlmc_msc_sweep_record_layout: m_layout must be 0 or 1");
     const int n_sweeps_T = m_layout == 1 ? n_sweeps : 0;
     NLMC_REQUIRE(M && n_sweeps >= 0, "nlmc_msc_sweep_record: bad arguments");
-    NLMC_REQUIRE(!out_M || (ladder >= 0 && ladder < M->n_ladders), "nlmc_msc_sweep_record: ladder out of range");
+    const bool has_M = out_M != nullptr || keep_M_on_device, has_E = out_E != nullptr;
+    NLMC_REQUIRE(!has_M || (ladder >= 0 && ladder < M->n_ladders), "nlmc_msc_sweep_record: ladder out of range");
     if (n_sweeps == 0) return NLMC_OK;
     NLMC_CUDA(cudaSetDevice(M->inst->device));
     const size_t m_stride = (size_t)M->n_beta * M->n, e_stride = (size_t)M->n_beta * M->n_ladders;
-    const bool has_M = out_M != nullptr, has_E = out_E != nullptr;
     // grow-only record buffers; the captured graphs hold their addresses, so a reallocation drops the graphs
     const size_t need_M = has_M ? m_stride * (size_t)n_sweeps : 0, need_E = has_E ? e_stride * (size_t)n_sweeps : 0;
     if (need_M > M->recM_cap || need_E > M->recE_cap) {
@@ -1255,21 +1284,28 @@ int nlmc_msc_sweep_record_layout(nlmc_msc *M, int n_sweeps, int ladder, int8_t *
         for (int s = 0; s < n_sweeps && !rc; ++s) rc = launch_recorded_sweep(M, ladder, has_M, has_E, m_stride, e_stride, n_sweeps_T);
         if (rc) return rc;
     }
-    if (has_M) NLMC_CUDA(cudaMemcpyAsync(out_M, M->recM, need_M, cudaMemcpyDeviceToHost, M->stream));
+    if (has_M && !keep_M_on_device) NLMC_CUDA(cudaMemcpyAsync(out_M, M->recM, need_M, cudaMemcpyDeviceToHost, M->stream));
     if (has_E) NLMC_CUDA(cudaMemcpyAsync(out_E, M->recE, sizeof(double) * need_E, cudaMemcpyDeviceToHost, M->stream));
-    NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    if (!keep_M_on_device) NLMC_CUDA(cudaStreamSynchronize(M->stream));
     return NLMC_OK;
 }
 
+int nlmc_msc_sweep_record_layout(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, double *out_E, int m_layout) {
+    return msc_record_impl(M, n_sweeps, ladder, out_M, out_E, m_layout, false);
+}
+
 /* nlmc_msc_sweep_record_layout with the states delivered as the float64 rows of the reference's M
- * (out_M_f64 [n_beta][n][n_sweeps], NPT/npt.py:640-644): the int8 record comes back through a pinned staging buffer kept
- * by the library (25 GB/s instead of the 4 GB/s of a copy into pageable memory) and is widened by the host threads. */
+ * (out_M_f64 [n_beta][n][n_sweeps], NPT/npt.py:640-644).  The int8 record stays on the device; it comes back in chunks
+ * through a pinned staging buffer kept by the library (25 GB/s instead of the 4 GB/s of a copy into pageable memory), and
+ * the host workers widen chunk k (non-temporal stores) while chunk k+1 is still on the wire. */
 int nlmc_msc_sweep_record_f64(nlmc_msc *M, int n_sweeps, int ladder, double *out_M_f64, double *out_E) {
     using namespace nlmc;
     NLMC_REQUIRE(M && out_M_f64 && n_sweeps >= 0, "nlmc_msc_sweep_record_f64: bad arguments");
     if (n_sweeps == 0) return NLMC_OK;
     static thread_local int8_t *stage = nullptr;   // pinned, grow-only, one per host thread (one host thread per handle)
     static thread_local size_t stage_cap = 0;
+    constexpr int kChunks = 8;
+    static thread_local cudaEvent_t ev[kChunks] = {};
     const size_t bytes = (size_t)M->n_beta * M->n * (size_t)n_sweeps;
     NLMC_CUDA(cudaSetDevice(M->inst->device));
     if (bytes > stage_cap) {
@@ -1278,9 +1314,24 @@ int nlmc_msc_sweep_record_f64(nlmc_msc *M, int n_sweeps, int ladder, double *out
         NLMC_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&stage), bytes, cudaHostAllocDefault));
         stage_cap = bytes;
     }
-    int rc = nlmc_msc_sweep_record_layout(M, n_sweeps, ladder, stage, out_E, 1);
+    for (int k = 0; k < kChunks; ++k)
+        if (!ev[k]) NLMC_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+    // record on the device only (out_M = NULL keeps the copy out of the layout call), energies as before
+    int rc = msc_record_impl(M, n_sweeps, ladder, nullptr, out_E, 1, true);
     if (rc) return rc;
-    return nlmc_host_widen_i8_f64(stage, out_M_f64, bytes, 0);
+    const size_t per = ((bytes + kChunks - 1) / kChunks + 4095) & ~(size_t)4095;
+    for (int k = 0; k < kChunks; ++k) {
+        const size_t lo = std::min(bytes, per * (size_t)k), hi = std::min(bytes, lo + per);
+        if (lo < hi) NLMC_CUDA(cudaMemcpyAsync(stage + lo, M->recM + lo, hi - lo, cudaMemcpyDeviceToHost, M->stream));
+        NLMC_CUDA(cudaEventRecord(ev[k], M->stream));
+    }
+    for (int k = 0; k < kChunks; ++k) {
+        const size_t lo = std::min(bytes, per * (size_t)k), hi = std::min(bytes, lo + per);
+        NLMC_CUDA(cudaEventSynchronize(ev[k]));
+        if (lo < hi) nlmc::widen_i8_f64(stage + lo, out_M_f64 + lo, hi - lo, 0);
+    }
+    NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    return NLMC_OK;
 }
 
 int nlmc_msc_round_host_async(nlmc_msc *M, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnlmc_b200.so")
+# NLMC_LIB_PATH: an experiment build of the same library (tools/sweep_ab.py compares kernel variants); never a fallback
+LIB_PATH = os.environ.get("NLMC_LIB_PATH") or os.path.join(_HERE, "libnlmc_b200.so")
 _lib = None
 
 
@@ -188,6 +189,40 @@ def empty_prefaulted(shape, dtype=np.float64) -> np.ndarray:
     if a.nbytes >= (1 << 22):
         check(lib().nlmc_host_prefault(a.ctypes.data, a.nbytes, 0), "nlmc_host_prefault")
     return a
+
+
+class _ResultCache:
+    """Caching host allocator for the large float64 result arrays (the 1 GB M of config C5): a buffer handed out earlier
+    is reused once nothing outside the cache refers to it any more -- neither the array itself nor a view of it -- so a
+    loop of run() calls pays the page faults of a fresh gigabyte once instead of on every call.  An array the caller still
+    holds is never touched: the next request allocates a new one, and the cache keeps only the most recent buffer."""
+
+    def __init__(self):
+        self._buf = None
+
+    def take(self, shape, dtype=np.float64) -> np.ndarray:
+        import sys
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if nbytes < (1 << 26):
+            return np.empty(shape, dtype=dtype)
+        b = self._buf
+        # references to a free buffer: self._buf, the local b, getrefcount's argument
+        if b is not None and b.nbytes >= nbytes and sys.getrefcount(b) == 3:
+            return b[:nbytes].view(dtype).reshape(shape)
+        del b
+        self._buf = np.empty(nbytes, dtype=np.uint8)
+        return self._buf[:nbytes].view(dtype).reshape(shape)
+
+    def release(self):
+        self._buf = None
+
+
+result_cache = _ResultCache()
+
+
+def release_host_cache():
+    """Drop the cached result buffer (see _ResultCache)."""
+    result_cache.release()
 
 
 def widen_to_f64(a: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:

@@ -15,8 +15,21 @@ from . import _lib
 def max_abs(J) -> float:
     """np.max(np.abs(J)) for dense or scipy.sparse J (NMC/nmc.py:474)."""
     if sp.issparse(J):
-        return float(abs(J).max()) if J.nnz else 0.0
+        if not J.nnz:
+            return 0.0
+        data = getattr(J, "data", None)   # CSR / CSC / COO / BSR keep their entries in .data: no |J| copy of the matrix
+        if isinstance(data, np.ndarray) and J.format in ("csr", "csc", "coo", "bsr"):
+            return float(max(data.max(), -data.min(), 0.0))
+        return float(abs(J).max())
     return float(np.max(np.abs(J)))
+
+
+def normalised(J, h, norm_factor: float):
+    """J / norm_factor, h / norm_factor as new objects (the reference rebinds self.J / self.h, NPT/npt.py:588-590);
+    a factor of exactly 1 leaves every value unchanged, so the division is skipped."""
+    if norm_factor == 1.0 and getattr(J, "dtype", None) == np.float64 and getattr(h, "dtype", None) == np.float64:
+        return J, h
+    return J / norm_factor, h / norm_factor
 
 
 class Problem:
@@ -33,11 +46,25 @@ class Problem:
         self.h = np.ascontiguousarray(np.asarray(h, dtype=np.float64).reshape(-1))
         self.inst = _lib.Instance(self.rp, self.ci, self.val, self.h, device)
         self.is_integer = self.inst.is_integer
-        self.row_of = np.repeat(np.arange(self.n, dtype=np.int32), np.diff(self.rp))
-        if self.is_integer and len(self.val):
-            self.lut_half = int(np.bincount(self.row_of, weights=np.abs(self.val), minlength=self.n).max())
-        else:
-            self.lut_half = 0
+        self._row_of = None
+        self._lut_half = None
+
+    @property
+    def row_of(self) -> np.ndarray:
+        """Row index of every stored entry (built on first use: the production paths never need it)."""
+        if self._row_of is None:
+            self._row_of = np.repeat(np.arange(self.n, dtype=np.int32), np.diff(self.rp))
+        return self._row_of
+
+    @property
+    def lut_half(self) -> int:
+        """Largest |integer field| a site can see: half-width of the tanh table of the replay kernel."""
+        if self._lut_half is None:
+            if self.is_integer and len(self.val):
+                self._lut_half = int(np.bincount(self.row_of, weights=np.abs(self.val), minlength=self.n).max())
+            else:
+                self._lut_half = 0
+        return self._lut_half
 
     def lbp_instance(self):
         """Instance for the belief-propagation kernel (K5), which needs rows sorted by column (numpy sums the reference's

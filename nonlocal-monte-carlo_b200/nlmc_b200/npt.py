@@ -83,8 +83,7 @@ class NPT(SweepMethods, LbpMethods, EnergyMethods):
         self.hash_table = None
 
         norm_factor = host.max_abs(self.J)  # NPT/npt.py:588-590 (rebinds, never writes the caller's arrays)
-        self.J = self.J / norm_factor
-        self.h = self.h / norm_factor
+        self.J, self.h = host.normalised(self.J, self.h, norm_factor)
 
         if len(self.doNMC) != self.num_replicas:
             raise ValueError("The length of doNMC does not match the number of replicas.")

@@ -23,23 +23,32 @@ def _seed_from_numpy() -> int:
     return (int(hi) << 32) | int(lo)
 
 
+class _NotBitPackable(NotImplementedError):
+    """The instance is outside the bit-packed engine (raised by its create call); callers fall back to the generic engines."""
+
+
 def _require_msc(prob: host.Problem, betas, n_ladders: int, seed: int) -> "_lib.Msc":
     try:
         return _lib.Msc(prob.inst, betas, n_ladders, seed)
     except _lib.NlmcError as e:
-        raise NotImplementedError(
+        raise _NotBitPackable(
             "mode='production' currently covers +-J instances with h = 0 and even degrees <= 6 "
             f"(2D/3D lattices); use mode='replay' for this instance ({e})") from e
 
 
 def _msc_eligible(prob: host.Problem) -> bool:
     """+-J, h = 0, even degrees <= 6: the bit-packed path applies (csrc/nlmc_msc.cu)."""
-    if not prob.is_integer or np.any(prob.h != 0) or len(prob.val) == 0:
-        return False
-    if not np.all(np.abs(prob.val) == 1) or np.any(prob.ci == prob.row_of):
-        return False
-    deg = np.diff(prob.rp)
-    return bool(np.all(deg <= 6) and np.all(deg % 2 == 0))
+    cached = getattr(prob, "_msc_eligible", None)
+    if cached is None:
+        cached = False
+        if prob.is_integer and len(prob.val) and not np.any(prob.h):
+            deg = np.diff(prob.rp)
+            if deg.max() <= 6 and not np.any(deg & 1) and prob.val.max() == 1.0 and prob.val.min() == -1.0:
+                import scipy.sparse as sp
+                diag = sp.csr_matrix((prob.val, prob.ci, prob.rp), shape=(prob.n, prob.n), copy=False).diagonal()
+                cached = bool(np.all(prob.val * prob.val == 1.0)) and not np.any(diag)
+        prob._msc_eligible = cached
+    return cached
 
 
 def _engine_energies_exact(prob: host.Problem) -> bool:
@@ -51,8 +60,13 @@ def npt_run_production(obj, beta_list, nmc_kw):
     """NPT.run (NPT/npt.py:535-700) in production mode.  +-J lattices without NMC replicas take the bit-packed
     path; everything else (real-valued or dense J, fields, doNMC replicas) takes the dense tensor-core path."""
     prob = obj._problem()
-    if _msc_eligible(prob) and not any(obj.doNMC):
-        return _npt_run_msc(obj, prob, beta_list)
+    if not any(obj.doNMC) and prob.is_integer and getattr(prob, "_msc_eligible", None) is not False:
+        # no host-side pre-check of the instance (several passes over the CSR): the create call of the bit-packed engine
+        # checks it anyway and reports an instance it cannot hold
+        try:
+            return _npt_run_msc(obj, prob, beta_list)
+        except _NotBitPackable:
+            prob._msc_eligible = False
     if _msc_eligible(prob) and not all(obj.doNMC) and not os.environ.get("NLMC_NO_HYBRID"):
         return _npt_run_hybrid(obj, prob, beta_list, nmc_kw)
     return _npt_run_dense(obj, prob, beta_list, nmc_kw)
@@ -87,7 +101,7 @@ def _npt_run_msc(obj, prob, beta_list):
     # last round: record the state after every sweep (the reference returns the last round's M); the device writes the
     # record in the layout of M's rows, the host only widens int8 to float64.  (Touching the pages of M from the host threads
     # while the rounds are still running was tried and cost more than it saved: 0.38 s per call against 0.22 s.)
-    M = np.empty((R * n, spm)) if spm > 0 else np.zeros((R * n, spm))
+    M = _lib.result_cache.take((R * n, spm)) if spm > 0 else np.zeros((R * n, spm))
     E_cols = np.zeros((R, spm))
     E_all = None
     if spm > 0:
@@ -130,7 +144,7 @@ def _npt_run_msc_sharded(obj, prob, beta_list):
     try:
         ens = ShardedBetaLadder(prob, beta_list[:R], num_runs, int(seed_t.item()), device=prob.inst.device if nccl else None)
     except _lib.NlmcError as e:
-        raise NotImplementedError(f"mode='production' on several GPUs needs a +-J lattice instance ({e})") from e
+        raise _NotBitPackable(f"mode='production' on several GPUs needs a +-J lattice instance ({e})") from e
     msc = ens.msc
     count = np.zeros(obj.num_swap_attempts)
     for ii in range(obj.num_swap_attempts - 1):
