@@ -44,10 +44,13 @@ struct nlmc_msc {
     int32_t *accepted_rounds = nullptr;  // [kRoundLog] accepted exchanges of the last rounds (slot = round % kRoundLog)
     bool own_stream = true;
     long long n_bonds = 0;
-    uint32_t *S = nullptr;        // [n][W]
+    uint32_t *S = nullptr;        // quad-major, colour-sorted: uint4 S[W/4][n] (see MscDev)
     int32_t *rec = nullptr;       // [n][8] record of the site at position p of site_list (sites sorted by colour):
-                                  // 6 neighbours (-1 = padding), sign bits (bit d: J_{i,nbr d} < 0), site index
+                                  // positions of its 6 neighbours (-1 = padding), sign bits (bit d: J_{i,nbr d} < 0), site index
     int32_t *site_list = nullptr; // [n] sites sorted by colour
+    int32_t *pos_of = nullptr;    // [n] position of a site in site_list
+    uint32_t *thr_nz = nullptr;   // label mode: [W/4] steps at which the quad's threshold planes are not all zero
+    uint32_t *rows = nullptr;     // scratch [n][W]: the site-major packed state of the C ABI (nlmc_msc_get/set_packed)
     std::vector<int> colour_ptr;  // [n_colours+1]
     uint32_t *thr = nullptr;      // [n_beta][4] thresholds of |f| = 0,2,4,6
     double *betas = nullptr;      // [n_beta]
@@ -70,6 +73,7 @@ struct nlmc_msc {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<double> h_betas;
+    std::vector<uint32_t> h_thr;  // [n_beta][4] host copy of thr: the sweep kernel takes the thresholds as a launch argument
 };
 
 namespace nlmc {
@@ -85,12 +89,21 @@ struct Philox {
         uint32_t a = k0, b = k1;
 #pragma unroll
         for (int i = 0; i < NLMC_PHILOX_ROUNDS; ++i) {
+#ifdef NLMC_PHILOX_HILO
+            const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+            const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+            const uint32_t n0 = h1 ^ c1 ^ a;
+            const uint32_t n2 = h0 ^ c3 ^ b;
+            c1 = l1;
+            c3 = l0;
+#else
             const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
             const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
             const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ a;
             const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ b;
             c1 = (uint32_t)p1;
             c3 = (uint32_t)p0;
+#endif
             c0 = n0;
             c2 = n2;
             a += 0x9E3779B9u;
@@ -100,23 +113,35 @@ struct Philox {
     }
 };
 
+constexpr int kMaxBeta = 128;
+
+// Device view of a handle.  The state is stored QUAD-MAJOR and in COLOUR ORDER: uint4 S[quad][pos], quad = four
+// consecutive words (128 ladders of one slot), pos = position of the site in the colour-sorted site list.  A warp of the
+// sweep kernel owns 32 consecutive positions of one quad, so (a) every lane of a warp sits at the same slot -- thresholds,
+// their bits and the per-step "all threshold bits are zero" test live in uniform registers --, (b) rows of any length
+// (a block of a ladder sharded over GPUs has 16 words per site) fill warps completely, and (c) on a lattice the six
+// neighbour loads and the store of a warp are contiguous 512-byte runs (consecutive sites of a colour have consecutive
+// neighbours in the other colour).
 struct MscDev {
     int n, W, G, n_beta, quad_offset;  // quad_offset = ladder_offset / 128: global index of ladder quad 0
     int slot_begin;       // global index of slot 0 (label mode; 0 otherwise): random streams are keyed by the GLOBAL slot
-    int qpc, spw;         // sub-warp mapping for W < 128: quads (4 words) per site row, sites per warp
+    int qpb;              // quads per slot: G / 4
     const uint32_t *thrbits;    // label mode: [kSteps][3][W]
     const uint4 *thr_lane;      // label mode: [W][32] thresholds {-, T1, T2, T3} of every lane
+    const uint32_t *thr_nz;     // label mode: [W/4] bit p set <=> some threshold plane of the quad is non-zero at step p
     uint32_t *S;
-    const int4 *rec;      // [n][2] by position in site_list: {nbr0..3}, {nbr4, nbr5, sign bits, site} -- two 16-byte
-                          // loads replace the chain site_list -> neighbour table -> sign bits
-    uint32_t g_magic;     // ceil(2^32 / G): word / G == __umulhi(word, g_magic) for word * G < 2^32 (0: divide)
-    const int32_t *site_list;
-    const uint32_t *thr;
+    const int4 *rec;      // [n][2] by position: {nbr0..3}, {nbr4, nbr5, sign bits, site}; neighbours as POSITIONS (-1 = padding)
+    const int32_t *site_list;   // [n] site at a position
+    const int32_t *pos_of;      // [n] position of a site
     uint32_t seed_lo, seed_hi;
 };
 
-__device__ __forceinline__ int beta_index(const MscDev &a, int word0) {
-    return a.g_magic ? (int)__umulhi((uint32_t)word0, a.g_magic) : word0 / a.G;
+// thresholds of the handle's slots for the levels |f| = 2, 4, 6 as a kernel parameter: read through the constant bank
+// with a uniform index, they (and every bit test on them) stay in uniform registers
+struct MscThr { uint32_t t[kMaxBeta * 3]; };
+
+__device__ __forceinline__ size_t word_index(const MscDev &a, int pos, int w) {
+    return ((size_t)(w >> 2) * a.n + pos) * 4 + (w & 3);
 }
 
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
@@ -134,78 +159,78 @@ __device__ __forceinline__ void count6(uint32_t a0, uint32_t a1, uint32_t a2, ui
 
 // Threshold bit of every lane's |f| level: t = (p1 ? I1 : 0) | (p2 ? I2 : 0) | (p3 ? I3 : 0) with p in {0, 1}.  The lane
 // sets are disjoint, so the ORs are sums and the selects are products: three integer multiply-adds on the FMA pipe
-// instead of five select/logic operations on the ALU pipe, which is the limiter of this kernel (ncu: alu 68 %,
-// fma 26 % before the change).  Inline PTX so that the compiler does not turn them back into selects.
+// instead of select/logic operations on the ALU pipe, which is the busier one in this kernel.
 __device__ __forceinline__ uint32_t level_select(uint32_t i1, uint32_t i2, uint32_t i3, uint32_t p1, uint32_t p2,
                                                  uint32_t p3) {
-    uint32_t t;
+    uint32_t t;  // inline PTX so that the compiler does not turn the products back into selects
     asm("{\n\t.reg .u32 a;\n\tmul.lo.u32 a, %1, %4;\n\tmad.lo.u32 a, %2, %5, a;\n\tmad.lo.u32 %0, %3, %6, a;\n\t}"
         : "=r"(t) : "r"(i1), "r"(i2), "r"(i3), "r"(p1), "r"(p2), "r"(p3));
     return t;
 }
 
+// 0xffffffff for a negative argument, else 0 (opaque to the compiler, which would otherwise fold the mask into a predicate
+// and spend a select plus a logic operation per word where one three-input logic operation does)
+__device__ __forceinline__ uint32_t sign_mask(int x) {
+    uint32_t m;
+    asm("shr.s32 %0, %1, 31;" : "=r"(m) : "r"(x));
+    return m;
+}
+
 __device__ __forceinline__ uint32_t comp(const uint4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
 
-// One colour of one sweep: a warp per (site, 128-word chunk), a lane per four consecutive words.
+// One colour of one sweep: a warp per (quad of words, 32 consecutive positions of the colour), a lane per site.
 //
-// The Bernoulli draw g ~ B(q(|f|)) of all 128 lanes of a thread is a bit-serial comparison u < T_level,
-// most significant bit first.  kSteps steps run unconditionally (fully unrolled: no exit test, no
-// divergence); after them a lane is still undecided with probability 2^-kSteps, and those few lanes
-// are finished one by one against the remaining threshold bits with a fresh 32-bit uniform each
-// (exactly the conditional probability).  ncu on the first version (early-exit loop) showed the kernel
-// ALU-pipe bound with 29% of the lanes idle in the loop tail; see profiles/.
+// The Bernoulli draw g ~ B(q(|f|)) of the 128 ladders of a thread is a bit-serial comparison u < T_level, most
+// significant bit first.  kSteps steps run unconditionally (fully unrolled); after them a lane is still undecided with
+// probability 2^-kSteps, and those few lanes are finished one by one against the remaining threshold bits with a fresh
+// 32-bit uniform each (exactly the conditional probability).  The thresholds of a warp are uniform, so a step at which
+// all three levels have a zero threshold bit -- 4.6 of the 6 steps on average over the ladder of config C5, all six
+// above beta = 1.04 -- skips the level select: undecided lanes whose random bit is 1 are decided (u > T).
 //
-// kPerBit (beta-label exchange): the lanes of a word sit at DIFFERENT temperatures, so the threshold bit of a lane
-// comes from per-word bit planes thrbits[p][level][w] (rebuilt after every exchange) instead of three scalars;
-// stragglers look their threshold up through the lane's label.  kSubWarp: site rows shorter than 128 words (a beta
-// block of a ladder sharded over GPUs) put several sites into one warp, lane = (site of the warp, word quad).
-template <int kSteps, bool kPerBit, bool kSubWarp>
+// kPerBit (beta-label exchange): the ladders of a word sit at DIFFERENT temperatures, so the threshold bit of a ladder
+// comes from per-word bit planes thrbits[p][level][w] (rebuilt after every exchange) instead of three scalars; the planes
+// of a warp's quad are the same for all its lanes (broadcast loads), thr_nz says at which steps they are all zero, and
+// stragglers look their threshold up through the ladder's label.
+template <int kSteps, bool kPerBit>
 #ifndef NLMC_PERBIT_CTAS
-#define NLMC_PERBIT_CTAS 4  // resident CTAs per SM of the bit-plane variant (64 registers: no spills)
+#define NLMC_PERBIT_CTAS 4
 #endif
 #ifndef NLMC_SCALAR_CTAS
-#define NLMC_SCALAR_CTAS 5  // resident CTAs per SM of the scalar-threshold variant
+#define NLMC_SCALAR_CTAS 4
 #endif
-__global__ void __launch_bounds__(256, kPerBit ? NLMC_PERBIT_CTAS : NLMC_SCALAR_CTAS) msc_sweep_kernel(MscDev a, int first, int n_sites, const uint32_t *__restrict__ counters, uint32_t sweep_in_batch) {
+__global__ void __launch_bounds__(256, kPerBit ? NLMC_PERBIT_CTAS : NLMC_SCALAR_CTAS)
+msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const uint32_t *__restrict__ counters,
+                 uint32_t sweep_in_batch) {
+    const int idx = (int)(blockIdx.x * 256u + threadIdx.x);  // position within the colour
+    if (idx >= n_sites) return;
     const uint32_t sweep = counters[0] + sweep_in_batch;
-    int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);  // site of this colour
-    const int lane = threadIdx.x & 31;
-    int word0;
-    if (kSubWarp) {
-        const int sub = lane / a.qpc;
-        if (sub >= a.spw) return;
-        warp = warp * a.spw + sub;
-        word0 = (lane - sub * a.qpc) * 4;
-    } else {
-        word0 = (int)blockIdx.y * 128 + lane * 4;  // grid.y = 128-word chunks of the row
-    }
-    if (warp >= n_sites) return;
-    if (word0 >= a.W) return;
-
-    const int4 r0 = __ldg(a.rec + (size_t)(first + warp) * 2), r1 = __ldg(a.rec + (size_t)(first + warp) * 2 + 1);
+    const int b = (int)blockIdx.y, qin = (int)blockIdx.z;     // slot and quad within the slot: uniform over the CTA
+    const int qd = b * a.qpb + qin;
+    const int pos = first + idx;
+    const int4 r0 = __ldg(a.rec + (size_t)pos * 2), r1 = __ldg(a.rec + (size_t)pos * 2 + 1);
     const int nb[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
     const uint32_t meta = (uint32_t)r1.z;
     const int site = r1.w;
-    // All six row loads are issued back to back (a padding slot reads row 0 and is masked below): with the sign flip
-    // predicated on each load's result the compiler serialised them -- one memory latency per neighbour (ncu, round 2:
-    // long-scoreboard 3.3 warps per issue, two thirds of a warp's lifetime in this prologue).
+    uint4 *Sq = reinterpret_cast<uint4 *>(a.S) + (size_t)qd * a.n;
+    // all six loads are issued back to back (a padding slot reads position 0 and is masked below)
     uint4 x[6];
 #pragma unroll
-    for (int d = 0; d < 6; ++d)
-        x[d] = *reinterpret_cast<const uint4 *>(a.S + (size_t)max(nb[d], 0) * a.W + word0);
+    for (int d = 0; d < 6; ++d) x[d] = Sq[max(nb[d], 0)];
 #pragma unroll
     for (int d = 0; d < 6; ++d) {
         // x <- (x & keep) ^ flip: a neighbour keeps its bits and is inverted when J < 0; padding comes in (+1, -1) pairs
-        // (even degrees only).  One three-input logic operation per word, no branch.
-        const uint32_t keep = nb[d] >= 0 ? 0xffffffffu : 0u;
-        const uint32_t flip = nb[d] >= 0 ? 0u - ((meta >> d) & 1u) : ((d & 1) ? 0u : 0xffffffffu);
+        // (even degrees only; the record carries flip = 1 for the even padding slots).  One three-input logic operation
+        // per word; the masks are formed with shifts so that they stay in registers (as selects on predicates the
+        // compiler spent two instructions per word).
+        const uint32_t keep = sign_mask(~nb[d]);
+        const uint32_t flip = sign_mask((int)(meta << (31 - d)));
         x[d].x = (x[d].x & keep) ^ flip;
         x[d].y = (x[d].y & keep) ^ flip;
         x[d].z = (x[d].z & keep) ^ flip;
         x[d].w = (x[d].w & keep) ^ flip;
     }
     // lane sets of the |f| levels 1..3 (|f| = 2, 4, 6), level 0 being the rest; sign plane pos = [c >= 4]
-    uint32_t I1[4], I2[4], I3[4], pos[4], res[4], und[4];
+    uint32_t I1[4], I2[4], I3[4], sgn[4], res[4], und[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         uint32_t c0, c1, c2;
@@ -215,56 +240,67 @@ __global__ void __launch_bounds__(256, kPerBit ? NLMC_PERBIT_CTAS : NLMC_SCALAR_
         I1[k] = ~m1 & m0;
         I2[k] = m1 & ~m0;
         I3[k] = m1 & m0;
-        pos[k] = c2;
+        sgn[k] = c2;
     }
-    const int b = beta_index(a, word0);  // the four words of a lane share one slot (G % 4 == 0)
-    uint32_t T1 = 0, T2 = 0, T3 = 0;
-    if (!kPerBit) {
-        const uint4 thr4 = __ldg(reinterpret_cast<const uint4 *>(a.thr) + b);
-        T1 = thr4.y; T2 = thr4.z; T3 = thr4.w;
+    uint32_t T1 = 0, T2 = 0, T3 = 0, nzmask;
+    if (kPerBit) {
+        nzmask = __ldg(a.thr_nz + qd);
+    } else {
+        T1 = thr.t[b * 3]; T2 = thr.t[b * 3 + 1]; T3 = thr.t[b * 3 + 2];
+        nzmask = __brev(T1 | T2 | T3);  // bit p <=> some level has threshold bit 31 - p set
     }
     const Philox rng{a.seed_lo, a.seed_hi ^ kTagSweep};
     // stream id = (GLOBAL slot index, GLOBAL ladder quad): independent of how ladders / beta blocks are sharded
-    const uint32_t sid = ((uint32_t)(b + a.slot_begin) << 20) | (uint32_t)(a.quad_offset + ((word0 - b * a.G) >> 2));
+    const uint32_t sid = ((uint32_t)(b + a.slot_begin) << 20) | (uint32_t)(a.quad_offset + qin);
     // Bit-serial comparison state per word: und = lanes whose uniform still equals the threshold on the prefix seen so
     // far; v = the uniform's bit at the last step a lane was undecided, i.e. for a decided lane the bit at its first
-    // difference (v = 0 there <=> uniform < threshold <=> g = 1).  Two 3-input logic ops per word and step; the level
-    // select runs on the FMA pipe (scalar thresholds) or is three more logic ops (bit planes).
-    // g = ~v & ~und is formed once after the last step.
+    // difference (v = 0 there <=> uniform < threshold <=> g = 1).  g = ~v & ~und is formed once after the last step.
     uint32_t v[4];
 #pragma unroll
     for (int p = 0; p < kSteps; ++p) {
         const uint4 r4 = rng((uint32_t)site, sid, sweep, (uint32_t)p);
-        uint4 A1, A2, A3;
-        uint32_t p1 = 0, p2 = 0, p3 = 0;
-        if (kPerBit) {
-            const uint32_t *tb = a.thrbits + (size_t)p * 3 * a.W + word0;
-            A1 = __ldg(reinterpret_cast<const uint4 *>(tb));
-            A2 = __ldg(reinterpret_cast<const uint4 *>(tb + a.W));
-            A3 = __ldg(reinterpret_cast<const uint4 *>(tb + 2 * a.W));
-        } else {
-            p1 = (T1 >> (31 - p)) & 1u; p2 = (T2 >> (31 - p)) & 1u; p3 = (T3 >> (31 - p)) & 1u;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t r = comp(r4, k);
-            const uint32_t t = kPerBit ? ((I1[k] & comp(A1, k)) | (I2[k] & comp(A2, k)) | (I3[k] & comp(A3, k)))
-                                       : level_select(I1[k], I2[k], I3[k], p1, p2, p3);
-            if (p == 0) {  // level-0 lanes (q = 1/2) are decided by the first bit alone (g = ~r, so v = r fits them too)
-                const uint32_t I0 = ~(I1[k] | I2[k] | I3[k]);
-                v[k] = r;
-                und[k] = ~(r ^ t) & ~I0;
+        if ((nzmask >> p) & 1u) {
+            uint4 A1, A2, A3;
+            uint32_t p1 = 0, p2 = 0, p3 = 0;
+            if (kPerBit) {
+                const uint32_t *tb = a.thrbits + (size_t)p * 3 * a.W + qd * 4;
+                A1 = __ldg(reinterpret_cast<const uint4 *>(tb));
+                A2 = __ldg(reinterpret_cast<const uint4 *>(tb + a.W));
+                A3 = __ldg(reinterpret_cast<const uint4 *>(tb + 2 * a.W));
             } else {
-                v[k] = (und[k] & r) | (~und[k] & v[k]);  // undecided lanes take this step's bit
-                und[k] &= ~(r ^ t);                      // still equal on this prefix
+                p1 = (T1 >> (31 - p)) & 1u; p2 = (T2 >> (31 - p)) & 1u; p3 = (T3 >> (31 - p)) & 1u;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t r = comp(r4, k);
+                const uint32_t t = kPerBit ? ((I1[k] & comp(A1, k)) | (I2[k] & comp(A2, k)) | (I3[k] & comp(A3, k)))
+                                           : level_select(I1[k], I2[k], I3[k], p1, p2, p3);
+                if (p == 0) {  // level-0 lanes (q = 1/2) are decided by the first bit alone (g = ~r, so v = r fits them too)
+                    v[k] = r;
+                    und[k] = ~(r ^ t) & (I1[k] | I2[k] | I3[k]);
+                } else {
+                    v[k] = (und[k] & r) | (~und[k] & v[k]);  // undecided lanes take this step's bit
+                    und[k] &= ~(r ^ t);                      // still equal on this prefix
+                }
+            }
+        } else {  // every threshold bit of this step is zero: an undecided lane with random bit 1 is decided (u > T, v = 1)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t r = comp(r4, k);
+                if (p == 0) {
+                    v[k] = r;
+                    und[k] = ~r & (I1[k] | I2[k] | I3[k]);
+                } else {
+                    v[k] |= und[k];
+                    und[k] &= ~r;
+                }
             }
         }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) res[k] = ~v[k] & ~und[k];
     // stragglers: each gets a fresh 32-bit uniform against the remaining threshold bits.  One Philox call
-    // serves the lowest undecided lane of each of the four words, so the warp iterates
-    // max-over-threads-and-words(#undecided per word) times (about 1.3 at kSteps = 8).
+    // serves the lowest undecided lane of each of the four words.
     if (und[0] | und[1] | und[2] | und[3]) {
         const uint32_t R1 = T1 << kSteps, R2 = T2 << kSteps, R3 = T3 << kSteps;
         uint32_t call = 32u;
@@ -277,7 +313,7 @@ __global__ void __launch_bounds__(256, kPerBit ? NLMC_PERBIT_CTAS : NLMC_SCALAR_
                 if (kPerBit) {
                     rem = 0u;
                     if (bit) {
-                        const uint4 tl = __ldg(a.thr_lane + (size_t)(word0 + k) * 32 + (__ffs((int)bit) - 1));
+                        const uint4 tl = __ldg(a.thr_lane + (size_t)(qd * 4 + k) * 32 + (__ffs((int)bit) - 1));
                         rem = ((I3[k] & bit) ? tl.w : (I2[k] & bit) ? tl.z : tl.y) << kSteps;
                     }
                 } else {
@@ -289,35 +325,33 @@ __global__ void __launch_bounds__(256, kPerBit ? NLMC_PERBIT_CTAS : NLMC_SCALAR_
         } while (und[0] | und[1] | und[2] | und[3]);
     }
     uint4 out;
-    out.x = pos[0] ^ res[0];
-    out.y = pos[1] ^ res[1];
-    out.z = pos[2] ^ res[2];
-    out.w = pos[3] ^ res[3];
-    *reinterpret_cast<uint4 *>(a.S + (size_t)site * a.W + word0) = out;
+    out.x = sgn[0] ^ res[0];
+    out.y = sgn[1] ^ res[1];
+    out.z = sgn[2] ^ res[2];
+    out.w = sgn[3] ^ res[3];
+    Sq[pos] = out;
 }
 
 // Uniform random initial spins (the production counterpart of sign(2*rand-1), NPT/npt.py:612).
 __global__ void msc_init_kernel(MscDev a, uint32_t stream_id) {
-    const size_t quad = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // (site, word quad)
-    const int qpr = a.W / 4;  // quads per site row
-    if (quad >= (size_t)a.n * qpr) return;
-    const int site = (int)(quad / qpr), word0 = (int)(quad % qpr) * 4;
-    const int b = word0 / a.G;
-    const uint32_t sid = ((uint32_t)(b + a.slot_begin) << 20) | (uint32_t)(a.quad_offset + ((word0 - b * a.G) >> 2));
+    const size_t quad = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // (quad of words, position)
+    if (quad >= (size_t)a.n * (a.W / 4)) return;
+    const int qd = (int)(quad / a.n), pos = (int)(quad % a.n);
+    const int b = qd / a.qpb, qin = qd % a.qpb;
+    const uint32_t sid = ((uint32_t)(b + a.slot_begin) << 20) | (uint32_t)(a.quad_offset + qin);
     const Philox rng{a.seed_lo, a.seed_hi ^ kTagInit};
-    reinterpret_cast<uint4 *>(a.S)[quad] = rng((uint32_t)site, sid, stream_id, 0u);
+    reinterpret_cast<uint4 *>(a.S)[quad] = rng((uint32_t)__ldg(a.site_list + pos), sid, stream_id, 0u);
 }
 
-// K4': per (word, lane) sum over sites of the number of unsatisfied bonds at the site, with bit-sliced
+// K4': per (word, ladder) sum over sites of the number of unsatisfied bonds at the site, with bit-sliced
 // vertical counters (10 bit planes) flushed every kEnergyChunk sites.  E = sum_i unsat_i - n_bonds.
-constexpr int kEnergyChunk = 128;  // at most 128 sites per warp: 128 sites * 6 bonds < 2^10
+constexpr int kEnergyChunk = 128;  // at most 128 sites per lane: 128 sites * 6 bonds < 2^10
 // On a two-colourable graph every bond joins the two colour classes, so the sites of ONE class see every bond exactly
-// once: the launcher then passes only that class (n_list sites of site_list) and the finish kernel doubles the sum.
-// Work item = (chunk of `chunk` sites, 128-word chunk of the row); a warp takes one item (W >= 128) or, for short rows, one
-// item per sub-group of qpc lanes.  A CTA loops over items with a grid stride and gathers its counts in SHARED memory
-// (native shared atomics), so that every (word, lane) address of E_acc receives one global atomic per CTA instead of one
-// per item -- with 16-word rows (a block of a ladder sharded over 8 GPUs) the per-item global atomics of round 1 piled
-// 4.2 M updates onto 512 addresses and the kernel took longer than the 16 sweeps of the round.
+// once: the launcher then passes only that class (the first n_list positions) and the finish kernel doubles the sum.
+// Work item = (quad of words, 32 * chunk consecutive positions); a warp takes one item, a lane the positions
+// base + lane + 32 k (coalesced 512-byte rows of the quad-major layout).  A CTA loops over items with a grid stride and
+// gathers its counts in SHARED memory (native shared atomics), so that every (word, ladder) address of E_acc receives one
+// global atomic per CTA instead of one per item.
 __global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_acc, int chunk, int n_list, int use_smem) {
     extern __shared__ int32_t acc_s[];  // [W * 32] when use_smem
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -325,44 +359,34 @@ __global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_ac
         for (int i = tid; i < a.W * 32; i += 128) acc_s[i] = 0;
         __syncthreads();
     }
-    const int chunks = (a.W + 127) >> 7;
-    const int site_chunks = (n_list + chunk - 1) / chunk;
-    const long long n_items = (long long)site_chunks * chunks;
-    int sub = 0, spw = 1, word_in = lane * 4;
-    bool lane_on = true;
-    if (a.W < 128) {  // short rows: the sub-groups of a warp take different site chunks (chunks == 1)
-        sub = lane / a.qpc;
-        spw = a.spw;
-        lane_on = sub < a.spw;
-        word_in = (lane - sub * a.qpc) * 4;
-    }
-    for (long long g = ((long long)blockIdx.x * 4 + warp) * spw + sub; lane_on && g < n_items; g += (long long)gridDim.x * 4 * spw) {
-        const int word0 = (a.W < 128) ? word_in : (int)(g % chunks) * 128 + word_in;
-        if (word0 >= a.W) continue;
-        const int s_begin = (int)(g / chunks) * chunk, s_end = min(n_list, s_begin + chunk);
+    const int quads = a.W >> 2;
+    const int span = 32 * chunk;
+    const int site_chunks = (n_list + span - 1) / span;
+    const long long n_items = (long long)site_chunks * quads;
+    for (long long g = (long long)blockIdx.x * 4 + warp; g < n_items; g += (long long)gridDim.x * 4) {
+        const int qd = (int)(g % quads);
+        const int s_begin = (int)(g / quads) * span, s_end = min(n_list, s_begin + span);
+        const uint4 *Sq = reinterpret_cast<const uint4 *>(a.S) + (size_t)qd * a.n;
         uint32_t v[4][10];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
             for (int bb = 0; bb < 10; ++bb) v[k][bb] = 0u;
-        for (int s = s_begin; s < s_end; ++s) {
+        for (int s = s_begin + lane; s < s_end; s += 32) {
             const int4 r0 = __ldg(a.rec + (size_t)s * 2), r1 = __ldg(a.rec + (size_t)s * 2 + 1);
             const int nb[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
             const uint32_t meta = (uint32_t)r1.z;
-            const int site = r1.w;
-            const uint4 own = *reinterpret_cast<const uint4 *>(a.S + (size_t)site * a.W + word0);
+            const uint4 own = Sq[s];
             uint4 x[6];
 #pragma unroll
+            for (int d = 0; d < 6; ++d) x[d] = Sq[max(nb[d], 0)];
+#pragma unroll
             for (int d = 0; d < 6; ++d) {
-                const int j = nb[d];
-                if (j >= 0) {
-                    x[d] = *reinterpret_cast<const uint4 *>(a.S + (size_t)j * a.W + word0);
-                    const uint32_t neg = ((meta >> d) & 1u) ? 0xffffffffu : 0u;
-                    // unsatisfied <=> J*s_i*s_j = -1 <=> s_i xor s_j xor [J<0]
-                    x[d].x ^= own.x ^ neg; x[d].y ^= own.y ^ neg; x[d].z ^= own.z ^ neg; x[d].w ^= own.w ^ neg;
-                } else {
-                    x[d] = make_uint4(0u, 0u, 0u, 0u);
-                }
+                // unsatisfied <=> J*s_i*s_j = -1 <=> s_i xor s_j xor [J<0]; padding contributes nothing
+                const uint32_t keep = sign_mask(~nb[d]);
+                const uint32_t neg = sign_mask((int)(meta << (31 - d)));
+                x[d].x = (x[d].x ^ own.x ^ neg) & keep; x[d].y = (x[d].y ^ own.y ^ neg) & keep;
+                x[d].z = (x[d].z ^ own.z ^ neg) & keep; x[d].w = (x[d].w ^ own.w ^ neg) & keep;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -385,15 +409,18 @@ __global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_ac
                 }
             }
         }
+        // the 32 lanes of the warp hold partial counts of the SAME 128 (word, ladder) addresses: lane l starts at ladder
+        // l, so that the atomics of one instruction go to 32 different addresses
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            for (int l = 0; l < 32; ++l) {
+            for (int i = 0; i < 32; ++i) {
+                const int l = (i + lane) & 31;
                 int val = 0;
 #pragma unroll
                 for (int bb = 0; bb < 10; ++bb) val |= (int)((v[k][bb] >> l) & 1u) << bb;
                 if (val) {
-                    if (use_smem) atomicAdd(acc_s + (word0 + k) * 32 + l, val);
-                    else atomicAdd(E_acc + (size_t)(word0 + k) * 32 + l, val);
+                    if (use_smem) atomicAdd(acc_s + (qd * 4 + k) * 32 + l, val);
+                    else atomicAdd(E_acc + (size_t)(qd * 4 + k) * 32 + l, val);
                 }
             }
         }
@@ -419,7 +446,6 @@ __global__ void msc_energy_finish_kernel(int W, int G, int n_ladders, long long 
 // uniformly from the pairs still available; accept with min(1, exp((b_next-b_sel)*(E_next-E_sel))).
 // Accepted exchanges are recorded as lane masks per temperature boundary and applied to the
 // configurations by msc_swap_apply_kernel (the reference swaps configurations, not labels).
-constexpr int kMaxBeta = 128;
 constexpr int kRoundLog = 4096;  // per-round acceptance counts kept for the last kRoundLog rounds
 __global__ void msc_swap_decide_kernel(int n_beta, int n_ladders, int G, int num_pairs, const double *betas, double *E,
                                        uint32_t *swapmask, int32_t *accepted, int32_t *accepted_rounds, uint32_t seed_lo,
@@ -458,14 +484,13 @@ __global__ void msc_swap_decide_kernel(int n_beta, int n_ladders, int G, int num
 }
 
 __global__ void msc_swap_apply_kernel(MscDev a, const uint32_t *swapmask) {
-    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // (site, g)
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // (position, g)
     if (idx >= (size_t)a.n * a.G) return;
-    const int g = (int)(idx % a.G);
-    uint32_t *row = a.S + (idx / a.G) * (size_t)a.W + g;
-    uint32_t A = row[0];
+    const int g = (int)(idx % a.G), pos = (int)(idx / a.G);
+    uint32_t A = a.S[word_index(a, pos, g)];
     bool A_dirty = false;
     for (int b = 0; b + 1 < a.n_beta; ++b) {
-        uint32_t B = row[(size_t)(b + 1) * a.G];
+        uint32_t B = a.S[word_index(a, pos, (b + 1) * a.G + g)];
         bool B_dirty = false;
         const uint32_t mask = __ldg(swapmask + (size_t)b * a.G + g);
         if (mask) {
@@ -476,11 +501,11 @@ __global__ void msc_swap_apply_kernel(MscDev a, const uint32_t *swapmask) {
                 A_dirty = B_dirty = true;
             }
         }
-        if (A_dirty) row[(size_t)b * a.G] = A;
+        if (A_dirty) a.S[word_index(a, pos, b * a.G + g)] = A;
         A = B;
         A_dirty = B_dirty;
     }
-    if (A_dirty) row[(size_t)(a.n_beta - 1) * a.G] = A;
+    if (A_dirty) a.S[word_index(a, pos, (a.n_beta - 1) * a.G + g)] = A;
 }
 
 // K6, beta-label form (north_star 4): configurations stay in their slots, every (slot, ladder) carries the
@@ -544,6 +569,20 @@ __global__ void msc_thrbits_kernel(int k_steps, int W, int G, const uint8_t *__r
     thrbits[idx] = word;
 }
 
+// thr_nz[quad]: bit p set <=> at step p some level's plane of one of the quad's four words is non-zero
+__global__ void msc_thrnz_kernel(int k_steps, int W, const uint32_t *__restrict__ thrbits, uint32_t *thr_nz) {
+    const int qd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qd >= W / 4) return;
+    uint32_t nz = 0u;
+    for (int p = 0; p < k_steps; ++p) {
+        uint32_t any = 0u;
+        for (int lev = 0; lev < 3; ++lev)
+            for (int k = 0; k < 4; ++k) any |= thrbits[((size_t)p * 3 + lev) * W + qd * 4 + k];
+        if (any) nz |= 1u << p;
+    }
+    thr_nz[qd] = nz;
+}
+
 __global__ void msc_labels_identity_kernel(int n_beta, int n_ladders, uint8_t *labels, uint8_t *slot_of) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_beta * n_ladders) return;
@@ -559,7 +598,7 @@ __global__ void msc_bump_kernel(uint32_t *counters, int which, uint32_t by = 1u)
 // all replicas (every beta) of one ladder as int8 +-1: out[b][site]
 __global__ void msc_unpack_ladder_kernel(MscDev a, int g, int lane, int8_t *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (i < a.n) out[(size_t)b * a.n + i] = ((a.S[(size_t)i * a.W + b * a.G + g] >> lane) & 1u) ? 1 : -1;
+    if (i < a.n) out[(size_t)b * a.n + i] = ((a.S[word_index(a, __ldg(a.pos_of + i), b * a.G + g)] >> lane) & 1u) ? 1 : -1;
 }
 
 // the same into slot counters[2] of a record buffer (captured once, replayed per recorded sweep)
@@ -569,7 +608,7 @@ __global__ void msc_unpack_ladder_rec_kernel(MscDev a, int g, int lane, int8_t *
                                              const uint32_t *__restrict__ counters, int n_sweeps_T) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (i >= a.n) return;
-    const int8_t v = ((a.S[(size_t)i * a.W + b * a.G + g] >> lane) & 1u) ? 1 : -1;
+    const int8_t v = ((a.S[word_index(a, __ldg(a.pos_of + i), b * a.G + g)] >> lane) & 1u) ? 1 : -1;
     if (n_sweeps_T) base[((size_t)b * a.n + i) * n_sweeps_T + counters[2]] = v;
     else base[(size_t)counters[2] * stride + (size_t)b * a.n + i] = v;
 }
@@ -582,15 +621,32 @@ __global__ void msc_record_energy_kernel(const double *__restrict__ E, double *b
 
 __global__ void msc_unpack_kernel(MscDev a, int w, int lane, int8_t *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.n) out[i] = ((a.S[(size_t)i * a.W + w] >> lane) & 1u) ? 1 : -1;
+    if (i < a.n) out[i] = ((a.S[word_index(a, __ldg(a.pos_of + i), w)] >> lane) & 1u) ? 1 : -1;
 }
 
 __global__ void msc_pack_kernel(MscDev a, int w, int lane, const int8_t *in) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    uint32_t *p = a.S + (size_t)i * a.W + w;
+    uint32_t *p = a.S + word_index(a, __ldg(a.pos_of + i), w);
     const uint32_t bit = 1u << lane;
     *p = in[i] > 0 ? (*p | bit) : (*p & ~bit);  // one thread per site: no other writer of this word
+}
+
+// The packed state as the C ABI exchanges it -- rows[site][W], site-major -- from / to the quad-major device layout.
+__global__ void msc_to_rows_kernel(MscDev a, uint4 *rows) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // (site, quad), quad fastest
+    const int quads = a.W >> 2;
+    if (idx >= (size_t)a.n * quads) return;
+    const int i = (int)(idx / quads), qd = (int)(idx % quads);
+    rows[idx] = reinterpret_cast<const uint4 *>(a.S)[(size_t)qd * a.n + __ldg(a.pos_of + i)];
+}
+
+__global__ void msc_from_rows_kernel(MscDev a, const uint4 *rows) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const int quads = a.W >> 2;
+    if (idx >= (size_t)a.n * quads) return;
+    const int i = (int)(idx / quads), qd = (int)(idx % quads);
+    reinterpret_cast<uint4 *>(a.S)[(size_t)qd * a.n + __ldg(a.pos_of + i)] = rows[idx];
 }
 
 // 32-bit thresholds of q(|f|) = 1/(1 + exp(2*beta*|f|)) for |f| = 0, 2, 4, 6
@@ -609,35 +665,34 @@ static std::vector<uint32_t> msc_thresholds(int n_beta, const double *betas) {
 static MscDev dev_view(const nlmc_msc *M) {
     MscDev d;
     d.n = M->n; d.W = M->W; d.G = M->G; d.n_beta = M->n_beta; d.quad_offset = M->ladder_offset / 128;
-    d.S = M->S; d.rec = reinterpret_cast<const int4 *>(M->rec); d.site_list = M->site_list; d.thr = M->thr;
-    d.g_magic = ((unsigned long long)M->W * (unsigned long long)M->G < (1ull << 32))
-                    ? (uint32_t)(((1ull << 32) + (unsigned long long)M->G - 1) / (unsigned long long)M->G) : 0u;
+    d.S = M->S; d.rec = reinterpret_cast<const int4 *>(M->rec); d.site_list = M->site_list; d.pos_of = M->pos_of;
     d.seed_lo = (uint32_t)M->seed; d.seed_hi = (uint32_t)(M->seed >> 32);
     d.slot_begin = M->slot_begin;
-    d.qpc = std::min(M->W, 128) / 4;
-    d.spw = std::max(1, 32 / d.qpc);
+    d.qpb = M->G / 4;
     d.thrbits = M->thrbits;
     d.thr_lane = reinterpret_cast<const uint4 *>(M->thr_lane);
+    d.thr_nz = M->thr_nz;
     return d;
 }
 
+static MscThr thr_view(const nlmc_msc *M) {
+    MscThr t;
+    for (int b = 0; b < kMaxBeta; ++b)
+        for (int a = 0; a < 3; ++a)
+            t.t[b * 3 + a] = (!M->label_mode && b < M->n_beta) ? M->h_thr[(size_t)b * 4 + a + 1] : 0u;
+    return t;
+}
+
 template <int kSteps>
-static void launch_colour(const nlmc_msc *M, const MscDev &d, int first, int cnt, uint32_t sweep_in_batch) {
-    const bool sub = M->W < 128;
-    const int chunks = (M->W + 127) / 128;
-    const int warps = sub ? (cnt + d.spw - 1) / d.spw : cnt;
-    const dim3 blocks((unsigned)((warps + 7) / 8), (unsigned)chunks);
-    if (M->label_mode) {
-        if (sub) msc_sweep_kernel<kSteps, true, true><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters, sweep_in_batch);
-        else msc_sweep_kernel<kSteps, true, false><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters, sweep_in_batch);
-    } else {
-        if (sub) msc_sweep_kernel<kSteps, false, true><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters, sweep_in_batch);
-        else msc_sweep_kernel<kSteps, false, false><<<blocks, 256, 0, M->stream>>>(d, first, cnt, M->d_counters, sweep_in_batch);
-    }
+static void launch_colour(const nlmc_msc *M, const MscDev &d, const MscThr &t, int first, int cnt, uint32_t sweep_in_batch) {
+    const dim3 blocks((unsigned)((cnt + 255) / 256), (unsigned)M->n_beta, (unsigned)d.qpb);
+    if (M->label_mode) msc_sweep_kernel<kSteps, true><<<blocks, 256, 0, M->stream>>>(d, t, first, cnt, M->d_counters, sweep_in_batch);
+    else msc_sweep_kernel<kSteps, false><<<blocks, 256, 0, M->stream>>>(d, t, first, cnt, M->d_counters, sweep_in_batch);
 }
 
 static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
     const MscDev d = dev_view(M);
+    const MscThr t = thr_view(M);
     // The sweep index a kernel hashes into its random stream is counters[0] + its position in the batch.  Short site rows
     // (a block of a sharded ladder: 28 us per colour launch at 16 words) bump the counter once per batch; full rows keep
     // the 1-thread bump kernel after every sweep, which measured 2 % FASTER there (profiles/r1b_sweep_kernel_source.md).
@@ -648,11 +703,11 @@ static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
             const int first = M->colour_ptr[c], cnt = M->colour_ptr[c + 1] - first;
             if (cnt == 0) continue;
             switch (M->k_steps) {
-                case 4: launch_colour<4>(M, d, first, cnt, off); break;
-                case 5: launch_colour<5>(M, d, first, cnt, off); break;
-                case 7: launch_colour<7>(M, d, first, cnt, off); break;
-                case 8: launch_colour<8>(M, d, first, cnt, off); break;
-                default: launch_colour<6>(M, d, first, cnt, off); break;
+                case 4: launch_colour<4>(M, d, t, first, cnt, off); break;
+                case 5: launch_colour<5>(M, d, t, first, cnt, off); break;
+                case 7: launch_colour<7>(M, d, t, first, cnt, off); break;
+                case 8: launch_colour<8>(M, d, t, first, cnt, off); break;
+                default: launch_colour<6>(M, d, t, first, cnt, off); break;
             }
         }
         if (!bump_once) msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 0);
@@ -664,18 +719,17 @@ static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
 
 static int launch_energy(nlmc_msc *M) {
     const MscDev d = dev_view(M);
-    const int chunks = (M->W + 127) / 128;
+    const int quads = M->W / 4;
     const bool bipartite = M->n_colours == 2;  // one colour class sees every bond once
     const int n_list = bipartite ? M->colour_ptr[1] : M->n;
-    const int spw = M->W < 128 ? d.spw : 1;
-    // sites per item: as many as the 10-bit counters allow on big lattices (fewer flushes), fewer on small ones so that
-    // there are still about two items per warp slot of a grid of 148 x 8 CTAs
-    const long long slots = 148LL * 8 * 4 * spw * 2;
-    const int chunk = (int)std::max(8LL, std::min((long long)kEnergyChunk, ((long long)n_list * chunks + slots - 1) / slots));
-    const int site_chunks = (n_list + chunk - 1) / chunk;
-    const long long items = (long long)site_chunks * chunks;
-    const long long ctas_needed = (items + 4LL * spw - 1) / (4LL * spw);
-    const unsigned grid = (unsigned)std::max(1LL, std::min(ctas_needed, 148LL * 8));
+    // sites per lane and item: as many as the 10-bit counters allow on big lattices (fewer flushes), fewer on small ones
+    // so that there are still about two items per warp slot of a grid of 148 x 8 CTAs
+    const long long slots = 148LL * 8 * 4 * 2;
+    const long long per_item = ((long long)n_list * quads + slots - 1) / slots;          // positions per item
+    const int chunk = (int)std::max(4LL, std::min((long long)kEnergyChunk, (per_item + 31) / 32));
+    const int site_chunks = (n_list + 32 * chunk - 1) / (32 * chunk);
+    const long long items = (long long)site_chunks * quads;
+    const unsigned grid = (unsigned)std::max(1LL, std::min((items + 3) / 4, 148LL * 8));
     const size_t smem = sizeof(int32_t) * (size_t)M->W * 32;
     const int use_smem = smem <= 40 * 1024 ? 1 : 0;   // rows of up to 320 words; longer ones add straight into E_acc
     NLMC_CUDA(cudaMemsetAsync(M->E_acc, 0, sizeof(int32_t) * (size_t)M->W * 32, M->stream));
@@ -691,6 +745,7 @@ static int launch_thrbits(nlmc_msc *M) {
     msc_thrbits_kernel<<<(items + 127) / 128, 128, 0, M->stream>>>(
         M->k_steps, M->W, M->G, M->labels + (size_t)M->slot_begin * M->n_ladders, M->thr_total, M->thrbits,
         reinterpret_cast<uint4 *>(M->thr_lane));
+    msc_thrnz_kernel<<<(M->W / 4 + 127) / 128, 128, 0, M->stream>>>(M->k_steps, M->W, M->thrbits, M->thr_nz);
     NLMC_CUDA(cudaGetLastError());
     return NLMC_OK;
 }
@@ -811,7 +866,7 @@ int nlmc_msc_destroy(nlmc_msc *M) {
     if (!M) return NLMC_OK;
     cudaSetDevice(M->inst->device);
     nlmc::drop_graphs(M);
-    void *ptrs[] = {M->S, M->recM, M->recE, M->rec, M->site_list, M->thr, M->betas, M->E_acc, M->E, M->swapmask, M->accepted,
+    void *ptrs[] = {M->S, M->recM, M->recE, M->rec, M->site_list, M->pos_of, M->thr_nz, M->rows, M->thr, M->betas, M->E_acc, M->E, M->swapmask, M->accepted,
                     M->scratch_spins, M->d_counters, M->labels, M->slot_of, M->thr_total,
                     M->betas_total, M->thrbits, M->thr_lane, M->accepted_rounds};
     if (M->stream) {   // every buffer goes back to the pool in stream order (after whatever is still queued)
@@ -863,6 +918,7 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
             }
             if (!is.kind && (d & 1)) is = {4, i, d, 0.0};
             entries[(size_t)t] += d;
+            for (int e = d; e < 6; e += 2) meta[(size_t)i] |= 1u << e;  // padding pairs: even slot +1 (flip of a zeroed word), odd slot -1
         }
     });
     long long n_entries = 0;
@@ -937,12 +993,18 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
     if (M->k_steps != 4 && M->k_steps != 5 && M->k_steps != 7 && M->k_steps != 8) M->k_steps = 6;
     if (const char *e = getenv("NLMC_MSC_GRAPHS")) M->use_graphs = atoi(e) != 0;
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(n_beta, betas);
-    std::vector<int32_t> rec((size_t)n * 8, 0);  // records in site_list order: 6 neighbours, sign bits, site
+    M->h_thr = thr;
+    std::vector<int32_t> pos_of((size_t)n);
+    for (int p = 0; p < n; ++p) pos_of[(size_t)site_list[(size_t)p]] = p;
+    std::vector<int32_t> rec((size_t)n * 8, 0);  // records in site_list order: positions of the 6 neighbours, sign bits, site
     nlmc::parallel_for(parts, [&](int t, int np) {
         const int per = (n + np - 1) / np, lo = std::min(n, per * t), hi = std::min(n, lo + per);
         for (int p = lo; p < hi; ++p) {
             const int i = site_list[(size_t)p];
-            for (int d = 0; d < 6; ++d) rec[(size_t)p * 8 + d] = nbr[(size_t)i * 6 + d];
+            for (int d = 0; d < 6; ++d) {
+                const int j = nbr[(size_t)i * 6 + d];
+                rec[(size_t)p * 8 + d] = j >= 0 ? pos_of[(size_t)j] : -1;
+            }
             rec[(size_t)p * 8 + 6] = (int32_t)meta[(size_t)i];
             rec[(size_t)p * 8 + 7] = i;
         }
@@ -960,7 +1022,8 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
         return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
     };
     ok = ok && alloc(&M->S, sizeof(uint32_t) * words) && alloc(&M->rec, sizeof(int32_t) * (size_t)n * 8) &&
-         alloc(&M->site_list, sizeof(int32_t) * (size_t)n) && alloc(&M->thr, sizeof(uint32_t) * thr.size()) &&
+         alloc(&M->site_list, sizeof(int32_t) * (size_t)n) && alloc(&M->pos_of, sizeof(int32_t) * (size_t)n) &&
+         alloc(&M->thr, sizeof(uint32_t) * thr.size()) &&
          alloc(&M->betas, sizeof(double) * (size_t)n_beta) && alloc(&M->E_acc, sizeof(int32_t) * (size_t)M->W * 32) &&
          alloc(&M->E, sizeof(double) * (size_t)n_beta * M->n_ladders) &&
          alloc(&M->swapmask, sizeof(uint32_t) * (size_t)std::max(1, n_beta - 1) * M->G) && alloc(&M->accepted, sizeof(int32_t)) &&
@@ -971,6 +1034,7 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
          cudaMemsetAsync(M->accepted, 0, sizeof(int32_t), st) == cudaSuccess &&
          put(M->rec, rec.data(), sizeof(int32_t) * rec.size()) &&
          put(M->site_list, site_list.data(), sizeof(int32_t) * site_list.size()) &&
+         put(M->pos_of, pos_of.data(), sizeof(int32_t) * pos_of.size()) &&
          put(M->thr, thr.data(), sizeof(uint32_t) * thr.size()) && put(M->betas, betas, sizeof(double) * (size_t)n_beta);
     std::vector<uint32_t> thr_t;
     if (ok && M->label_mode) {
@@ -979,7 +1043,7 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
         ok = alloc(&M->labels, nl) && alloc(&M->slot_of, nl) && alloc(&M->thr_total, sizeof(uint32_t) * thr_t.size()) &&
              alloc(&M->betas_total, sizeof(double) * (size_t)n_beta_total) &&
              alloc(&M->thrbits, sizeof(uint32_t) * (size_t)M->k_steps * 3 * M->W) &&
-             alloc(&M->thr_lane, sizeof(uint32_t) * (size_t)M->W * 32 * 4) &&
+             alloc(&M->thr_lane, sizeof(uint32_t) * (size_t)M->W * 32 * 4) && alloc(&M->thr_nz, sizeof(uint32_t) * (size_t)(M->W / 4)) &&
              put(M->thr_total, thr_t.data(), sizeof(uint32_t) * thr_t.size()) &&
              put(M->betas_total, betas_total, sizeof(double) * (size_t)n_beta_total);
     }
@@ -1119,7 +1183,9 @@ int nlmc_msc_set_betas(nlmc_msc *M, const double *betas) {
     NLMC_CUDA(cudaSetDevice(M->inst->device));
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(M->n_beta, betas);
     M->h_betas.assign(betas, betas + M->n_beta);
+    M->h_thr = thr;
     NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    nlmc::drop_graphs(M);  // the thresholds are a launch argument of the captured sweeps
     NLMC_CUDA(cudaMemcpy(M->thr, thr.data(), sizeof(uint32_t) * thr.size(), cudaMemcpyHostToDevice));
     NLMC_CUDA(cudaMemcpy(M->betas, betas, sizeof(double) * (size_t)M->n_beta, cudaMemcpyHostToDevice));
     return NLMC_OK;
@@ -1162,17 +1228,49 @@ int nlmc_msc_get_spins(nlmc_msc *M, int beta_idx, int ladder, int8_t *out) {
     return NLMC_OK;
 }
 
+// scratch for the site-major image of the state (the layout the C ABI exchanges)
+static int msc_rows_scratch(nlmc_msc *M) {
+    if (!M->rows)
+        NLMC_CUDA(nlmc::pool_alloc(reinterpret_cast<void **>(&M->rows), sizeof(uint32_t) * (size_t)M->n * M->W, M->inst->device,
+                                   M->stream));
+    return NLMC_OK;
+}
+
+static int msc_set_packed_async(nlmc_msc *M, const uint32_t *packed) {
+    using namespace nlmc;
+    int rc = msc_rows_scratch(M);
+    if (rc) return rc;
+    const size_t quads = (size_t)M->n * (M->W / 4);
+    NLMC_CUDA(cudaMemcpyAsync(M->rows, packed, sizeof(uint32_t) * (size_t)M->n * M->W, cudaMemcpyHostToDevice, M->stream));
+    msc_from_rows_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, M->stream>>>(dev_view(M), reinterpret_cast<const uint4 *>(M->rows));
+    NLMC_CUDA(cudaGetLastError());
+    return NLMC_OK;
+}
+
+static int msc_get_packed_async(nlmc_msc *M, uint32_t *packed) {
+    using namespace nlmc;
+    int rc = msc_rows_scratch(M);
+    if (rc) return rc;
+    const size_t quads = (size_t)M->n * (M->W / 4);
+    msc_to_rows_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, M->stream>>>(dev_view(M), reinterpret_cast<uint4 *>(M->rows));
+    NLMC_CUDA(cudaGetLastError());
+    NLMC_CUDA(cudaMemcpyAsync(packed, M->rows, sizeof(uint32_t) * (size_t)M->n * M->W, cudaMemcpyDeviceToHost, M->stream));
+    return NLMC_OK;
+}
+
+/* The packed state, site-major: packed[site][W] (word w = slot * G + ladder group; bit = ladder within the group).  The
+ * device keeps it quad-major and colour-sorted; the transposition runs on the device. */
 int nlmc_msc_set_packed(nlmc_msc *M, const uint32_t *packed) {
     NLMC_REQUIRE(M && packed, "nlmc_msc_set_packed: NULL argument");
     NLMC_CUDA(cudaSetDevice(M->inst->device));
-    NLMC_CUDA(cudaMemcpyAsync(M->S, packed, sizeof(uint32_t) * (size_t)M->n * M->W, cudaMemcpyHostToDevice, M->stream));
-    return NLMC_OK;
+    return msc_set_packed_async(M, packed);
 }
 
 int nlmc_msc_get_packed(nlmc_msc *M, uint32_t *packed) {
     NLMC_REQUIRE(M && packed, "nlmc_msc_get_packed: NULL argument");
     NLMC_CUDA(cudaSetDevice(M->inst->device));
-    NLMC_CUDA(cudaMemcpyAsync(packed, M->S, sizeof(uint32_t) * (size_t)M->n * M->W, cudaMemcpyDeviceToHost, M->stream));
+    int rc = msc_get_packed_async(M, packed);
+    if (rc) return rc;
     NLMC_CUDA(cudaStreamSynchronize(M->stream));
     return NLMC_OK;
 }
@@ -1343,9 +1441,7 @@ int nlmc_msc_round_host_async(nlmc_msc *M, const uint32_t *packed_in, int n_swee
     if (out_E)
         NLMC_CUDA(cudaMemcpyAsync(out_E, M->E, sizeof(double) * (size_t)M->n_beta * M->n_ladders, cudaMemcpyDeviceToHost,
                                   M->stream));
-    if (packed_out)
-        NLMC_CUDA(cudaMemcpyAsync(packed_out, M->S, sizeof(uint32_t) * (size_t)M->n * M->W, cudaMemcpyDeviceToHost,
-                                  M->stream));
+    if (packed_out && (rc = msc_get_packed_async(M, packed_out))) return rc;
     return NLMC_OK;
 }
 
