@@ -66,7 +66,8 @@ struct nlmc_msc {
     size_t recM_cap = 0, recE_cap = 0;
     struct RecGraph { int ladder; bool has_M, has_E; int n_sweeps_T; cudaGraphExec_t exec; };
     std::vector<RecGraph> rec_graphs;  // one recorded sweep (sweep + unpack + energies + slot bump), replayed per sweep
-    int k_steps = 6;  // unconditional bit steps of the Bernoulli comparison (tuning knob NLMC_MSC_STEPS)
+    int k_steps = 5;  // unconditional bit steps of the Bernoulli comparison (tuning knob NLMC_MSC_STEPS)
+    int k_merged = 4; // further steps on the four words of a thread merged into one (0 or 4; NLMC_MSC_MERGED)
     struct RoundGraph { int n_sweeps, pairs; bool with_energy_swap; cudaGraphExec_t exec; };
     std::vector<RoundGraph> graphs;  // whole rounds captured once per (n_sweeps, pairs) and replayed
     bool use_graphs = true;
@@ -191,17 +192,26 @@ __device__ __forceinline__ uint32_t comp(const uint4 &v, int k) { return k == 0 
 // comes from per-word bit planes thrbits[p][level][w] (rebuilt after every exchange) instead of three scalars; the planes
 // of a warp's quad are the same for all its lanes (broadcast loads), thr_nz says at which steps they are all zero, and
 // stragglers look their threshold up through the ladder's label.
-template <int kSteps, bool kPerBit>
+//
+// kMerged (0 or 4): after the unconditional steps a thread's four words are nearly empty of undecided lanes (2^-kSteps
+// each), so they are OR-ed into ONE word -- a bit column goes to the first of the four words that is still undecided
+// there -- and kMerged further comparison steps run on that word with one Philox call; the results are scattered back.
+// A lane that lost its column to another word simply waits for the straggler loop.  Every random bit is still used by
+// at most one lane, chosen by the past only, so the draw stays exact.
+template <int kSteps, bool kPerBit, int kMerged>
 #ifndef NLMC_PERBIT_CTAS
 #define NLMC_PERBIT_CTAS 4
 #endif
 #ifndef NLMC_SCALAR_CTAS
 #define NLMC_SCALAR_CTAS 4
 #endif
-__global__ void __launch_bounds__(256, kPerBit ? NLMC_PERBIT_CTAS : NLMC_SCALAR_CTAS)
+#ifndef NLMC_SWEEP_THREADS
+#define NLMC_SWEEP_THREADS 256
+#endif
+__global__ void __launch_bounds__(NLMC_SWEEP_THREADS, (kPerBit ? NLMC_PERBIT_CTAS : NLMC_SCALAR_CTAS) * (256 / NLMC_SWEEP_THREADS))
 msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const uint32_t *__restrict__ counters,
                  uint32_t sweep_in_batch) {
-    const int idx = (int)(blockIdx.x * 256u + threadIdx.x);  // position within the colour
+    const int idx = (int)(blockIdx.x * (unsigned)NLMC_SWEEP_THREADS + threadIdx.x);  // position within the colour
     if (idx >= n_sites) return;
     const uint32_t sweep = counters[0] + sweep_in_batch;
     const int b = (int)blockIdx.y, qin = (int)blockIdx.z;     // slot and quad within the slot: uniform over the CTA
@@ -299,10 +309,53 @@ msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) res[k] = ~v[k] & ~und[k];
+    uint32_t adv[4] = {0u, 0u, 0u, 0u};  // lanes that took part in the merged steps (kSteps + kMerged threshold bits consumed)
+    if (kMerged > 0 && (und[0] | und[1] | und[2] | und[3])) {
+        const uint32_t t01 = und[0] | und[1], t012 = t01 | und[2];
+        adv[0] = und[0]; adv[1] = und[1] & ~und[0]; adv[2] = und[2] & ~t01; adv[3] = und[3] & ~t012;
+        const uint32_t U = t012 | und[3];
+        uint32_t um = U, vm = 0u;
+        const uint32_t J1 = (adv[0] & I1[0]) | (adv[1] & I1[1]) | (adv[2] & I1[2]) | (adv[3] & I1[3]);
+        const uint32_t J2 = (adv[0] & I2[0]) | (adv[1] & I2[1]) | (adv[2] & I2[2]) | (adv[3] & I2[3]);
+        const uint32_t J3 = (adv[0] & I3[0]) | (adv[1] & I3[1]) | (adv[2] & I3[2]) | (adv[3] & I3[3]);
+        const uint4 r4 = rng((uint32_t)site, sid, sweep, 16u);
+#pragma unroll
+        for (int q = 0; q < kMerged; ++q) {
+            const int p = kSteps + q;
+            const uint32_t r = comp(r4, q & 3);
+            if ((nzmask >> p) & 1u) {
+                uint32_t t;
+                if (kPerBit) {
+                    const uint32_t *tb = a.thrbits + (size_t)p * 3 * a.W + qd * 4;
+                    const uint4 A1 = __ldg(reinterpret_cast<const uint4 *>(tb));
+                    const uint4 A2 = __ldg(reinterpret_cast<const uint4 *>(tb + a.W));
+                    const uint4 A3 = __ldg(reinterpret_cast<const uint4 *>(tb + 2 * a.W));
+                    t = 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        t |= adv[k] & ((I1[k] & comp(A1, k)) | (I2[k] & comp(A2, k)) | (I3[k] & comp(A3, k)));
+                } else {
+                    t = level_select(J1, J2, J3, (T1 >> (31 - p)) & 1u, (T2 >> (31 - p)) & 1u, (T3 >> (31 - p)) & 1u);
+                }
+                vm = (um & r) | (~um & vm);
+                um &= ~(r ^ t);
+            } else {
+                vm |= um;
+                um &= ~r;
+            }
+        }
+        const uint32_t gm = U & ~um & ~vm;  // decided in the merged steps with uniform < threshold
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            res[k] |= adv[k] & gm;
+            und[k] &= ~adv[k] | um;
+        }
+    }
     // stragglers: each gets a fresh 32-bit uniform against the remaining threshold bits.  One Philox call
     // serves the lowest undecided lane of each of the four words.
     if (und[0] | und[1] | und[2] | und[3]) {
         const uint32_t R1 = T1 << kSteps, R2 = T2 << kSteps, R3 = T3 << kSteps;
+        const uint32_t Q1 = T1 << (kSteps + kMerged), Q2 = T2 << (kSteps + kMerged), Q3 = T3 << (kSteps + kMerged);
         uint32_t call = 32u;
         do {
             const uint4 r4 = rng((uint32_t)site, sid, sweep, call++);
@@ -314,8 +367,11 @@ msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const
                     rem = 0u;
                     if (bit) {
                         const uint4 tl = __ldg(a.thr_lane + (size_t)(qd * 4 + k) * 32 + (__ffs((int)bit) - 1));
-                        rem = ((I3[k] & bit) ? tl.w : (I2[k] & bit) ? tl.z : tl.y) << kSteps;
+                        rem = (I3[k] & bit) ? tl.w : (I2[k] & bit) ? tl.z : tl.y;
+                        rem <<= (kMerged > 0 && (adv[k] & bit)) ? kSteps + kMerged : kSteps;
                     }
+                } else if (kMerged > 0 && (adv[k] & bit)) {
+                    rem = (I3[k] & bit) ? Q3 : (I2[k] & bit) ? Q2 : Q1;
                 } else {
                     rem = (I3[k] & bit) ? R3 : (I2[k] & bit) ? R2 : R1;  // level 0 never gets here
                 }
@@ -352,18 +408,19 @@ constexpr int kEnergyChunk = 128;  // at most 128 sites per lane: 128 sites * 6 
 // base + lane + 32 k (coalesced 512-byte rows of the quad-major layout).  A CTA loops over items with a grid stride and
 // gathers its counts in SHARED memory (native shared atomics), so that every (word, ladder) address of E_acc receives one
 // global atomic per CTA instead of one per item.
-__global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_acc, int chunk, int n_list, int use_smem) {
+__global__ void __launch_bounds__(512) msc_energy_kernel(MscDev a, int32_t *E_acc, int chunk, int n_list, int use_smem) {
     extern __shared__ int32_t acc_s[];  // [W * 32] when use_smem
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (use_smem) {
-        for (int i = tid; i < a.W * 32; i += 128) acc_s[i] = 0;
+        for (int i = tid; i < a.W * 32; i += (int)blockDim.x) acc_s[i] = 0;
         __syncthreads();
     }
     const int quads = a.W >> 2;
     const int span = 32 * chunk;
     const int site_chunks = (n_list + span - 1) / span;
     const long long n_items = (long long)site_chunks * quads;
-    for (long long g = (long long)blockIdx.x * 4 + warp; g < n_items; g += (long long)gridDim.x * 4) {
+    const int wpc = (int)blockDim.x >> 5;  // warps per CTA
+    for (long long g = (long long)blockIdx.x * wpc + warp; g < n_items; g += (long long)gridDim.x * wpc) {
         const int qd = (int)(g % quads);
         const int s_begin = (int)(g / quads) * span, s_end = min(n_list, s_begin + span);
         const uint4 *Sq = reinterpret_cast<const uint4 *>(a.S) + (size_t)qd * a.n;
@@ -427,7 +484,7 @@ __global__ void __launch_bounds__(128) msc_energy_kernel(MscDev a, int32_t *E_ac
     }
     if (use_smem) {
         __syncthreads();
-        for (int i = tid; i < a.W * 32; i += 128)
+        for (int i = tid; i < a.W * 32; i += (int)blockDim.x)
             if (acc_s[i]) atomicAdd(E_acc + i, acc_s[i]);
     }
 }
@@ -685,9 +742,15 @@ static MscThr thr_view(const nlmc_msc *M) {
 
 template <int kSteps>
 static void launch_colour(const nlmc_msc *M, const MscDev &d, const MscThr &t, int first, int cnt, uint32_t sweep_in_batch) {
-    const dim3 blocks((unsigned)((cnt + 255) / 256), (unsigned)M->n_beta, (unsigned)d.qpb);
-    if (M->label_mode) msc_sweep_kernel<kSteps, true><<<blocks, 256, 0, M->stream>>>(d, t, first, cnt, M->d_counters, sweep_in_batch);
-    else msc_sweep_kernel<kSteps, false><<<blocks, 256, 0, M->stream>>>(d, t, first, cnt, M->d_counters, sweep_in_batch);
+    constexpr int kT = NLMC_SWEEP_THREADS;
+    const dim3 blocks((unsigned)((cnt + kT - 1) / kT), (unsigned)M->n_beta, (unsigned)d.qpb);
+    if (M->label_mode) {
+        if (M->k_merged) msc_sweep_kernel<kSteps, true, 4><<<blocks, kT, 0, M->stream>>>(d, t, first, cnt, M->d_counters, sweep_in_batch);
+        else msc_sweep_kernel<kSteps, true, 0><<<blocks, kT, 0, M->stream>>>(d, t, first, cnt, M->d_counters, sweep_in_batch);
+    } else {
+        if (M->k_merged) msc_sweep_kernel<kSteps, false, 4><<<blocks, kT, 0, M->stream>>>(d, t, first, cnt, M->d_counters, sweep_in_batch);
+        else msc_sweep_kernel<kSteps, false, 0><<<blocks, kT, 0, M->stream>>>(d, t, first, cnt, M->d_counters, sweep_in_batch);
+    }
 }
 
 static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
@@ -723,17 +786,23 @@ static int launch_energy(nlmc_msc *M) {
     const bool bipartite = M->n_colours == 2;  // one colour class sees every bond once
     const int n_list = bipartite ? M->colour_ptr[1] : M->n;
     // sites per lane and item: as many as the 10-bit counters allow on big lattices (fewer flushes), fewer on small ones
-    // so that there are still about two items per warp slot of a grid of 148 x 8 CTAs
-    const long long slots = 148LL * 8 * 4 * 2;
+    // so that there are still about two items per warp slot of the grid (measured at C5 size: 28 sites per lane, 256
+    // threads, 296 CTAs = 124 us against 195 us with 128-thread CTAs x 1184)
+    const long long slots = 148LL * 2 * 8 * 2;  // 2 CTAs of 8 warps per SM (the kernel needs 128 registers), 2 items per warp
     const long long per_item = ((long long)n_list * quads + slots - 1) / slots;          // positions per item
-    const int chunk = (int)std::max(4LL, std::min((long long)kEnergyChunk, (per_item + 31) / 32));
+    int chunk = (int)std::max(4LL, std::min((long long)kEnergyChunk, (per_item + 31) / 32));
+    if (const char *e = getenv("NLMC_ENERGY_CHUNK")) chunk = std::max(1, std::min(kEnergyChunk, atoi(e)));
     const int site_chunks = (n_list + 32 * chunk - 1) / (32 * chunk);
     const long long items = (long long)site_chunks * quads;
-    const unsigned grid = (unsigned)std::max(1LL, std::min((items + 3) / 4, 148LL * 8));
+    int threads = 256, max_ctas = 148 * 2;
+    if (const char *e = getenv("NLMC_ENERGY_THREADS")) threads = std::max(32, std::min(512, atoi(e) / 32 * 32));
+    if (const char *e = getenv("NLMC_ENERGY_CTAS")) max_ctas = std::max(1, atoi(e));
+    const int wpc = threads / 32;
+    const unsigned grid = (unsigned)std::max(1LL, std::min((items + wpc - 1) / wpc, (long long)max_ctas));
     const size_t smem = sizeof(int32_t) * (size_t)M->W * 32;
     const int use_smem = smem <= 40 * 1024 ? 1 : 0;   // rows of up to 320 words; longer ones add straight into E_acc
     NLMC_CUDA(cudaMemsetAsync(M->E_acc, 0, sizeof(int32_t) * (size_t)M->W * 32, M->stream));
-    msc_energy_kernel<<<grid, 128, use_smem ? smem : 0, M->stream>>>(d, M->E_acc, chunk, n_list, use_smem);
+    msc_energy_kernel<<<grid, threads, use_smem ? smem : 0, M->stream>>>(d, M->E_acc, chunk, n_list, use_smem);
     msc_energy_finish_kernel<<<(M->W * 32 + 255) / 256, 256, 0, M->stream>>>(M->W, M->G, M->n_ladders, M->n_bonds,
                                                                             bipartite ? 2 : 1, M->E_acc, M->E);
     NLMC_CUDA(cudaGetLastError());
@@ -741,11 +810,12 @@ static int launch_energy(nlmc_msc *M) {
 }
 
 static int launch_thrbits(nlmc_msc *M) {
-    const int items = std::max(M->k_steps * 3, 32) * M->W;
+    const int planes = M->k_steps + M->k_merged;
+    const int items = std::max(planes * 3, 32) * M->W;
     msc_thrbits_kernel<<<(items + 127) / 128, 128, 0, M->stream>>>(
-        M->k_steps, M->W, M->G, M->labels + (size_t)M->slot_begin * M->n_ladders, M->thr_total, M->thrbits,
+        planes, M->W, M->G, M->labels + (size_t)M->slot_begin * M->n_ladders, M->thr_total, M->thrbits,
         reinterpret_cast<uint4 *>(M->thr_lane));
-    msc_thrnz_kernel<<<(M->W / 4 + 127) / 128, 128, 0, M->stream>>>(M->k_steps, M->W, M->thrbits, M->thr_nz);
+    msc_thrnz_kernel<<<(M->W / 4 + 127) / 128, 128, 0, M->stream>>>(planes, M->W, M->thrbits, M->thr_nz);
     NLMC_CUDA(cudaGetLastError());
     return NLMC_OK;
 }
@@ -988,9 +1058,9 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
     M->label_mode = betas_total ? 1 : 0;
     M->n_beta_total = betas_total ? n_beta_total : n_beta;
     M->slot_begin = betas_total ? slot_begin : 0;
-    if (M->label_mode) M->k_steps = 7;  // stragglers cost a dependent table load in the bit-plane form: one more unconditional step pays (2 %)
     if (const char *e = getenv("NLMC_MSC_STEPS")) M->k_steps = atoi(e);
-    if (M->k_steps != 4 && M->k_steps != 5 && M->k_steps != 7 && M->k_steps != 8) M->k_steps = 6;
+    if (M->k_steps != 4 && M->k_steps != 6 && M->k_steps != 7 && M->k_steps != 8) M->k_steps = 5;
+    if (const char *e = getenv("NLMC_MSC_MERGED")) M->k_merged = atoi(e) ? 4 : 0;
     if (const char *e = getenv("NLMC_MSC_GRAPHS")) M->use_graphs = atoi(e) != 0;
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(n_beta, betas);
     M->h_thr = thr;
@@ -1042,7 +1112,7 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
         const size_t nl = (size_t)n_beta_total * M->n_ladders;
         ok = alloc(&M->labels, nl) && alloc(&M->slot_of, nl) && alloc(&M->thr_total, sizeof(uint32_t) * thr_t.size()) &&
              alloc(&M->betas_total, sizeof(double) * (size_t)n_beta_total) &&
-             alloc(&M->thrbits, sizeof(uint32_t) * (size_t)M->k_steps * 3 * M->W) &&
+             alloc(&M->thrbits, sizeof(uint32_t) * (size_t)(M->k_steps + M->k_merged) * 3 * M->W) &&
              alloc(&M->thr_lane, sizeof(uint32_t) * (size_t)M->W * 32 * 4) && alloc(&M->thr_nz, sizeof(uint32_t) * (size_t)(M->W / 4)) &&
              put(M->thr_total, thr_t.data(), sizeof(uint32_t) * thr_t.size()) &&
              put(M->betas_total, betas_total, sizeof(double) * (size_t)n_beta_total);
