@@ -350,6 +350,7 @@ def run_ours(args, rank, world, local_rank):
     def api_run(rounds):
         obj = NPT(A, np.zeros(n), mode="production", device=device)
         obj.num_runs = args.n_ladders
+        obj.m_on_ranks = (0,)   # N > 1: the float64 M is materialised on rank 0 only (every rank gets Energy)
         return obj.run(betas, n_beta, [False] * n_beta, num_sweeps_MCMC=spm * rounds, num_sweeps_read=spm * rounds,
                        num_swap_attempts=rounds, num_swapping_pairs=pairs)
 
@@ -361,13 +362,13 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     csr_bytes = A.indptr.nbytes + A.indices.nbytes + A.data.nbytes + 8 * n
-    d2h = spm * msc.n_beta * n + spm * msc.n_beta * n_ladders * 8       # recorded int8 states of run 0 + energies, this rank
+    d2h = spm * n_beta * n + spm * n_beta * n_ladders * 8               # rank 0: recorded int8 states of run 0 (all slots) + energies
     e2e = {"value": attempts_per_step * args.steps / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": int(csr_bytes / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
            "ms_per_step": 1e3 * e2e_s / args.steps, "seconds_per_call": e2e_s, "rounds_per_call": args.steps,
            "api": "NPT(J, h, mode='production').run(beta_list, 32, [False]*32, ..., num_swap_attempts=steps) with num_runs ladders "
-                  "side by side: host scipy J in, numpy M (float64, last round, run 0) and Energy out; state resident across rounds",
-           "returned": {"M_shape": list(M_out.shape), "Energy_coldest": float(E_out[-1])},
+                  "side by side: host scipy J in, numpy M (float64, last round, run 0; on rank 0 when N > 1) and Energy out; state resident across rounds",
+           "returned": {"M_shape": list(M_out.shape) if M_out is not None else None, "Energy_coldest": float(E_out[-1])},
            "numa_node_rank0": numa_node}
     del M_out
 

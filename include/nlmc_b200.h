@@ -50,6 +50,13 @@ int nlmc_device_info(int device, char *name, int name_len, int *sm_count, int *c
 int nlmc_host_widen_i8_f64(const int8_t *in, double *out, uint64_t count, int threads);
 /* touch every page of a freshly allocated host result buffer (first-touch faults taken while the GPU is busy) */
 int nlmc_host_prefault(void *buf, uint64_t bytes, int threads);
+/* Device int8 spins -> host float64 in blocks: block b of dev_src (block_elems values each) lands, widened, at
+ * host_dst + dst_block[b] * block_elems (dst_block NULL = identity).  The copy goes through a pinned staging buffer of the
+ * library in chunks, widened by the host workers while the next chunk is on the wire; `cuda_stream` (NULL = default stream)
+ * orders it after the kernels that produced dev_src.  This is how the recorded states of a run -- the reference's M,
+ * float64 (R*N) x sweeps, NPT/npt.py:640-644 -- reach the caller, in temperature order when exchanges permuted labels. */
+int nlmc_host_fetch_widen_blocks(const int8_t *dev_src, double *host_dst, int n_blocks, uint64_t block_elems,
+                                 const int32_t *dst_block, int device, void *cuda_stream);
 
 /* ---- instance ---------------------------------------------------------------------------------
  * Replaces `J = csr_matrix(J)` + `h = asarray(h)` at the top of every MCMC call (NMC/nmc.py:53-54):
@@ -209,6 +216,10 @@ int nlmc_msc_sweep_record(nlmc_msc *msc, int n_sweeps, int ladder, int8_t *out_M
 int nlmc_msc_sweep_record_layout(nlmc_msc *msc, int n_sweeps, int ladder, int8_t *out_M, double *out_E, int m_layout);
 /* the same with the states delivered as float64 rows of M ([n_beta][n][n_sweeps]) through a pinned staging buffer */
 int nlmc_msc_sweep_record_f64(nlmc_msc *msc, int n_sweeps, int ladder, double *out_M_f64, double *out_E);
+/* the same record left on the DEVICE (no synchronisation): *out_M_dev int8 in the layout m_layout selects, *out_E_dev
+ * float64 [n_sweeps][n_beta][n_ladders] (NULL pointer argument = not recorded).  The buffers belong to the handle and
+ * stay valid until its next record call; a rank of a sharded ladder all-gathers them from here. */
+int nlmc_msc_sweep_record_dev(nlmc_msc *msc, int n_sweeps, int ladder, int m_layout, int8_t **out_M_dev, double **out_E_dev);
 int nlmc_msc_round(nlmc_msc *msc, int n_sweeps, int num_swapping_pairs, double *out_E);
 int nlmc_msc_round_host(nlmc_msc *msc, const uint32_t *packed_in, int n_sweeps, int num_swapping_pairs,
                         uint32_t *packed_out, double *out_E);

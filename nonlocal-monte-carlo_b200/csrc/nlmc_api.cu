@@ -189,6 +189,60 @@ int nlmc_host_widen_i8_f64(const int8_t *in, double *out, uint64_t count, int th
     return NLMC_OK;
 }
 
+int nlmc_host_fetch_widen_blocks(const int8_t *dev_src, double *host_dst, int n_blocks, uint64_t block_elems,
+                                 const int32_t *dst_block, int device, void *cuda_stream) {
+    NLMC_REQUIRE(n_blocks >= 0 && (n_blocks == 0 || block_elems == 0 || (dev_src && host_dst)),
+                 "nlmc_host_fetch_widen_blocks: NULL argument");
+    if (n_blocks == 0 || block_elems == 0) return NLMC_OK;
+    static thread_local int8_t *stage = nullptr;   // pinned, grow-only, one per host thread
+    static thread_local size_t stage_cap = 0;
+    constexpr int kMaxChunks = 8;
+    static thread_local cudaEvent_t ev[kMaxChunks] = {};
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const size_t bytes = (size_t)n_blocks * block_elems;
+    NLMC_CUDA(cudaSetDevice(device));
+    if (bytes > stage_cap) {
+        if (stage) cudaFreeHost(stage);
+        stage = nullptr; stage_cap = 0;
+        NLMC_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&stage), bytes, cudaHostAllocDefault));
+        stage_cap = bytes;
+    }
+    for (int k = 0; k < kMaxChunks; ++k)
+        if (!ev[k]) NLMC_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+    // chunks of whole blocks (a single block is cut into pieces of its own)
+    if (n_blocks == 1) {
+        const size_t per = ((bytes + kMaxChunks - 1) / kMaxChunks + 4095) & ~(size_t)4095;
+        double *dst = host_dst + (dst_block ? (size_t)dst_block[0] * block_elems : 0);
+        for (int k = 0; k < kMaxChunks; ++k) {
+            const size_t lo = std::min(bytes, per * (size_t)k), hi = std::min(bytes, lo + per);
+            if (lo < hi) NLMC_CUDA(cudaMemcpyAsync(stage + lo, dev_src + lo, hi - lo, cudaMemcpyDeviceToHost, st));
+            NLMC_CUDA(cudaEventRecord(ev[k], st));
+        }
+        for (int k = 0; k < kMaxChunks; ++k) {
+            const size_t lo = std::min(bytes, per * (size_t)k), hi = std::min(bytes, lo + per);
+            NLMC_CUDA(cudaEventSynchronize(ev[k]));
+            if (lo < hi) nlmc::widen_i8_f64(stage + lo, dst + lo, hi - lo, 0);
+        }
+        return NLMC_OK;
+    }
+    const int per_blocks = (n_blocks + kMaxChunks - 1) / kMaxChunks;
+    for (int k = 0; k < kMaxChunks; ++k) {
+        const int b0 = std::min(n_blocks, per_blocks * k), b1 = std::min(n_blocks, b0 + per_blocks);
+        if (b0 < b1)
+            NLMC_CUDA(cudaMemcpyAsync(stage + (size_t)b0 * block_elems, dev_src + (size_t)b0 * block_elems,
+                                      (size_t)(b1 - b0) * block_elems, cudaMemcpyDeviceToHost, st));
+        NLMC_CUDA(cudaEventRecord(ev[k], st));
+    }
+    for (int k = 0; k < kMaxChunks; ++k) {
+        const int b0 = std::min(n_blocks, per_blocks * k), b1 = std::min(n_blocks, b0 + per_blocks);
+        NLMC_CUDA(cudaEventSynchronize(ev[k]));
+        for (int b = b0; b < b1; ++b)
+            nlmc::widen_i8_f64(stage + (size_t)b * block_elems, host_dst + (size_t)(dst_block ? dst_block[b] : b) * block_elems,
+                               block_elems, 0);
+    }
+    return NLMC_OK;
+}
+
 /* Touch every page of a freshly allocated host buffer on `threads` host threads (0 = all), so that the first-touch page
  * faults of a large result array (the 1 GB float64 M of config C5) are taken while the GPU is still sweeping instead of
  * inside the final widening. */

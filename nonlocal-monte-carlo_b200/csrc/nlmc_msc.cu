@@ -315,9 +315,12 @@ msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const
         adv[0] = und[0]; adv[1] = und[1] & ~und[0]; adv[2] = und[2] & ~t01; adv[3] = und[3] & ~t012;
         const uint32_t U = t012 | und[3];
         uint32_t um = U, vm = 0u;
-        const uint32_t J1 = (adv[0] & I1[0]) | (adv[1] & I1[1]) | (adv[2] & I1[2]) | (adv[3] & I1[3]);
-        const uint32_t J2 = (adv[0] & I2[0]) | (adv[1] & I2[1]) | (adv[2] & I2[2]) | (adv[3] & I2[3]);
-        const uint32_t J3 = (adv[0] & I3[0]) | (adv[1] & I3[1]) | (adv[2] & I3[2]) | (adv[3] & I3[3]);
+        uint32_t J1 = 0u, J2 = 0u, J3 = 0u;  // level planes of the merged word (not needed when every merged step is a zero step)
+        if (!kPerBit && ((nzmask >> kSteps) & ((1u << kMerged) - 1u))) {
+            J1 = (adv[0] & I1[0]) | (adv[1] & I1[1]) | (adv[2] & I1[2]) | (adv[3] & I1[3]);
+            J2 = (adv[0] & I2[0]) | (adv[1] & I2[1]) | (adv[2] & I2[2]) | (adv[3] & I2[3]);
+            J3 = (adv[0] & I3[0]) | (adv[1] & I3[1]) | (adv[2] & I3[2]) | (adv[3] & I3[3]);
+        }
         const uint4 r4 = rng((uint32_t)site, sid, sweep, 16u);
 #pragma unroll
         for (int q = 0; q < kMerged; ++q) {
@@ -352,7 +355,8 @@ msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const
         }
     }
     // stragglers: each gets a fresh 32-bit uniform against the remaining threshold bits.  One Philox call
-    // serves the lowest undecided lane of each of the four words.
+    // serves the lowest undecided lane of each of the four words.  (A select-only body measured 2 % slower than this
+    // one, whose branches skip the words without a straggler.)
     if (und[0] | und[1] | und[2] | und[3]) {
         const uint32_t R1 = T1 << kSteps, R2 = T2 << kSteps, R3 = T3 << kSteps;
         const uint32_t Q1 = T1 << (kSteps + kMerged), Q2 = T2 << (kSteps + kMerged), Q3 = T3 << (kSteps + kMerged);
@@ -498,6 +502,42 @@ __global__ void msc_energy_finish_kernel(int W, int G, int n_ladders, long long 
     E[(size_t)b * n_ladders + g * 32 + l] = (double)factor * (double)E_acc[idx] - (double)n_bonds;
 }
 
+// Pair selection of the exchange (NPT/npt.py:514-533): the pairs still selectable are kept as a bit mask (bit i <=> pair
+// (i, i+1)); the pick-th set bit is found with popcounts and __fns instead of a scan over a byte array in local memory.
+struct PairSet {
+    uint32_t m[kMaxBeta / 32];
+    int n_avail;
+    __device__ __forceinline__ void init(int n_pairs) {
+#pragma unroll
+        for (int w = 0; w < kMaxBeta / 32; ++w) {
+            const int lo = w * 32;
+            m[w] = n_pairs >= lo + 32 ? 0xffffffffu : (n_pairs > lo ? (1u << (n_pairs - lo)) - 1u : 0u);
+        }
+        n_avail = n_pairs;
+    }
+    // index of the pick-th (0-based) selectable pair; removes it and its two overlapping neighbours
+    __device__ __forceinline__ int take(int pick) {
+        int i = 0;
+#pragma unroll
+        for (int w = 0; w < kMaxBeta / 32; ++w) {
+            const int c = __popc(m[w]);
+            if (pick >= 0 && pick < c) { i = w * 32 + (int)__fns(m[w], 0u, pick + 1); pick = -1; }
+            else if (pick >= 0) pick -= c;
+        }
+#pragma unroll
+        for (int j = -1; j <= 1; ++j) {
+            const int q = i + j;
+            if (q >= 0 && q < kMaxBeta) {
+                const uint32_t bit = 1u << (q & 31);
+#pragma unroll
+                for (int w = 0; w < kMaxBeta / 32; ++w)
+                    if (w == (q >> 5) && (m[w] & bit)) { m[w] &= ~bit; --n_avail; }
+            }
+        }
+        return i;
+    }
+};
+
 // K6: replica exchange, one thread per ladder.  Pair selection and acceptance follow the reference
 // (NPT/npt.py:514-533,652-680): num_pairs non-overlapping adjacent pairs drawn one after the other
 // uniformly from the pairs still available; accept with min(1, exp((b_next-b_sel)*(E_next-E_sel))).
@@ -511,19 +551,12 @@ __global__ void msc_swap_decide_kernel(int n_beta, int n_ladders, int G, int num
     const int ladder = blockIdx.x * blockDim.x + threadIdx.x;
     if (ladder >= n_ladders) return;
     const Philox rng{seed_lo, seed_hi ^ kTagSwap};
-    uint8_t avail[kMaxBeta];  // avail[i] = 1: pair (i, i+1) still selectable
-    int n_avail = n_beta - 1;
-    for (int i = 0; i < n_beta - 1; ++i) avail[i] = 1;
+    PairSet avail;
+    avail.init(n_beta - 1);
     int acc = 0;
-    for (int k = 0; k < num_pairs && n_avail > 0; ++k) {
+    for (int k = 0; k < num_pairs && avail.n_avail > 0; ++k) {
         const uint4 r = rng((uint32_t)(ladder + ladder_offset), round, (uint32_t)k, 0u);
-        int pick = (int)(((unsigned long long)r.x * (unsigned)n_avail) >> 32);
-        int i = 0;
-        for (;; ++i)
-            if (avail[i] && pick-- == 0) break;
-        // remove the pair and its overlapping neighbours
-        for (int j = max(0, i - 1); j <= min(n_beta - 2, i + 1); ++j)
-            if (avail[j]) { avail[j] = 0; --n_avail; }
+        const int i = avail.take((int)(((unsigned long long)r.x * (unsigned)avail.n_avail) >> 32));
         const double E_sel = E[(size_t)i * n_ladders + ladder], E_next = E[(size_t)(i + 1) * n_ladders + ladder];
         const double x = (betas[i + 1] - betas[i]) * (E_next - E_sel);
         const double u = ((double)r.y * 4294967296.0 + (double)r.z + 0.5) * (1.0 / 18446744073709551616.0);
@@ -570,26 +603,17 @@ __global__ void msc_swap_apply_kernel(MscDev a, const uint32_t *swapmask) {
 // (gathered over the ranks when the beta range is sharded); every rank runs this kernel on identical inputs and
 // arrives at the identical permutation -- only 8 bytes per replica ever cross the GPUs.  Pair selection and
 // acceptance as in msc_swap_decide_kernel (NPT/npt.py:514-533,652-680), pairs being adjacent TEMPERATURES.
-__global__ void msc_label_swap_kernel(int n_beta, int n_ladders, int num_pairs, const double *betas, const double *E,
-                                      uint8_t *labels, uint8_t *slot_of, int32_t *accepted, int32_t *accepted_rounds,
-                                      uint32_t seed_lo, uint32_t seed_hi, const uint32_t *__restrict__ counters,
-                                      int ladder_offset) {
-    const uint32_t round = counters[1];
-    const int ladder = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ladder >= n_ladders) return;
+__device__ __forceinline__ void label_swap_ladder(int ladder, uint32_t round, int n_beta, int n_ladders, int num_pairs,
+                                                  const double *betas, const double *E, uint8_t *labels, uint8_t *slot_of,
+                                                  int32_t *accepted, int32_t *accepted_rounds, uint32_t seed_lo,
+                                                  uint32_t seed_hi, int ladder_offset) {
     const Philox rng{seed_lo, seed_hi ^ kTagSwap};
-    uint8_t avail[kMaxBeta];
-    int n_avail = n_beta - 1;
-    for (int i = 0; i < n_beta - 1; ++i) avail[i] = 1;
+    PairSet avail;
+    avail.init(n_beta - 1);
     int acc = 0;
-    for (int k = 0; k < num_pairs && n_avail > 0; ++k) {
+    for (int k = 0; k < num_pairs && avail.n_avail > 0; ++k) {
         const uint4 r = rng((uint32_t)(ladder + ladder_offset), round, (uint32_t)k, 0u);
-        int pick = (int)(((unsigned long long)r.x * (unsigned)n_avail) >> 32);
-        int i = 0;
-        for (;; ++i)
-            if (avail[i] && pick-- == 0) break;
-        for (int j = max(0, i - 1); j <= min(n_beta - 2, i + 1); ++j)
-            if (avail[j]) { avail[j] = 0; --n_avail; }
+        const int i = avail.take((int)(((unsigned long long)r.x * (unsigned)avail.n_avail) >> 32));
         const int sa = slot_of[(size_t)i * n_ladders + ladder], sb = slot_of[(size_t)(i + 1) * n_ladders + ladder];
         const double E_sel = E[(size_t)sa * n_ladders + ladder], E_next = E[(size_t)sb * n_ladders + ladder];
         const double x = (betas[i + 1] - betas[i]) * (E_next - E_sel);
@@ -608,16 +632,25 @@ __global__ void msc_label_swap_kernel(int n_beta, int n_ladders, int num_pairs, 
     }
 }
 
-// Threshold bit planes of this handle's slots from the labels: one thread per (step p, level, word).
-__global__ void msc_thrbits_kernel(int k_steps, int W, int G, const uint8_t *__restrict__ labels_local,
-                                   const uint32_t *__restrict__ thr_total, uint32_t *thrbits, uint4 *thr_lane) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void msc_label_swap_kernel(int n_beta, int n_ladders, int num_pairs, const double *betas, const double *E,
+                                      uint8_t *labels, uint8_t *slot_of, int32_t *accepted, int32_t *accepted_rounds,
+                                      uint32_t seed_lo, uint32_t seed_hi, const uint32_t *__restrict__ counters,
+                                      int ladder_offset) {
+    const uint32_t round = counters[1];
+    const int ladder = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ladder >= n_ladders) return;
+    label_swap_ladder(ladder, round, n_beta, n_ladders, num_pairs, betas, E, labels, slot_of, accepted, accepted_rounds,
+                      seed_lo, seed_hi, ladder_offset);
+}
+
+__device__ __forceinline__ void thrbits_item(int idx, int planes, int W, int G, const uint8_t *labels_local,
+                                             const uint32_t *thr_total, uint32_t *thrbits, uint4 *thr_lane) {
     if (idx < W * 32) {  // full thresholds of lane (w, l)
         const int w = idx >> 5, l = idx & 31;
         const int lab = labels_local[(size_t)(w / G) * (G * 32) + (w % G) * 32 + l];
         thr_lane[idx] = *reinterpret_cast<const uint4 *>(thr_total + lab * 4);
     }
-    if (idx >= k_steps * 3 * W) return;
+    if (idx >= planes * 3 * W) return;
     const int w = idx % W, lev = (idx / W) % 3 + 1, p = idx / (3 * W);
     const int b = w / G, g = w % G;
     const uint8_t *lab = labels_local + (size_t)b * (G * 32) + g * 32;
@@ -626,18 +659,55 @@ __global__ void msc_thrbits_kernel(int k_steps, int W, int G, const uint8_t *__r
     thrbits[idx] = word;
 }
 
-// thr_nz[quad]: bit p set <=> at step p some level's plane of one of the quad's four words is non-zero
-__global__ void msc_thrnz_kernel(int k_steps, int W, const uint32_t *__restrict__ thrbits, uint32_t *thr_nz) {
-    const int qd = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qd >= W / 4) return;
+__device__ __forceinline__ void thrnz_item(int qd, int planes, int W, const uint32_t *thrbits, uint32_t *thr_nz) {
     uint32_t nz = 0u;
-    for (int p = 0; p < k_steps; ++p) {
+    for (int p = 0; p < planes; ++p) {
         uint32_t any = 0u;
         for (int lev = 0; lev < 3; ++lev)
             for (int k = 0; k < 4; ++k) any |= thrbits[((size_t)p * 3 + lev) * W + qd * 4 + k];
         if (any) nz |= 1u << p;
     }
     thr_nz[qd] = nz;
+}
+
+// The whole label exchange of a round in ONE launch of one CTA (ladder sets of up to 1024 ladders): clear the round's
+// acceptance slot, decide and permute the labels, rebuild this handle's threshold planes, bump the round counter.  As five
+// tiny launches the same work took 39 us per round, which on a 4-slot block of a ladder sharded over 8 GPUs is 5 % of the
+// round.
+__global__ void __launch_bounds__(1024) msc_label_round_kernel(
+    int n_beta, int n_ladders, int num_pairs, const double *betas, const double *E, uint8_t *labels, uint8_t *slot_of,
+    int32_t *accepted, int32_t *accepted_rounds, uint32_t seed_lo, uint32_t seed_hi, uint32_t *counters, int ladder_offset,
+    int planes, int W, int G, int slot_begin, const uint32_t *thr_total, uint32_t *thrbits, uint4 *thr_lane, uint32_t *thr_nz) {
+    const uint32_t round = counters[1];
+    const int tid = threadIdx.x;
+    if (tid == 0) accepted_rounds[round % kRoundLog] = 0;
+    __syncthreads();
+    if (n_beta >= 2 && num_pairs > 0) {
+        if (tid < n_ladders)
+            label_swap_ladder(tid, round, n_beta, n_ladders, num_pairs, betas, E, labels, slot_of, accepted, accepted_rounds,
+                              seed_lo, seed_hi, ladder_offset);
+        __syncthreads();
+        const int items = max(planes * 3, 32) * W;
+        const uint8_t *labels_local = labels + (size_t)slot_begin * n_ladders;
+        for (int idx = tid; idx < items; idx += (int)blockDim.x)
+            thrbits_item(idx, planes, W, G, labels_local, thr_total, thrbits, thr_lane);
+        __syncthreads();
+        for (int qd = tid; qd < W / 4; qd += (int)blockDim.x) thrnz_item(qd, planes, W, thrbits, thr_nz);
+    }
+    __syncthreads();
+    if (tid == 0) counters[1] = round + 1u;
+}
+
+// Threshold bit planes of this handle's slots from the labels: one thread per (step p, level, word).
+__global__ void msc_thrbits_kernel(int planes, int W, int G, const uint8_t *__restrict__ labels_local,
+                                   const uint32_t *__restrict__ thr_total, uint32_t *thrbits, uint4 *thr_lane) {
+    thrbits_item(blockIdx.x * blockDim.x + threadIdx.x, planes, W, G, labels_local, thr_total, thrbits, thr_lane);
+}
+
+// thr_nz[quad]: bit p set <=> at step p some level's plane of one of the quad's four words is non-zero
+__global__ void msc_thrnz_kernel(int planes, int W, const uint32_t *__restrict__ thrbits, uint32_t *thr_nz) {
+    const int qd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qd < W / 4) thrnz_item(qd, planes, W, thrbits, thr_nz);
 }
 
 __global__ void msc_labels_identity_kernel(int n_beta, int n_ladders, uint8_t *labels, uint8_t *slot_of) {
@@ -790,7 +860,7 @@ static int launch_energy(nlmc_msc *M) {
     // threads, 296 CTAs = 124 us against 195 us with 128-thread CTAs x 1184)
     const long long slots = 148LL * 2 * 8 * 2;  // 2 CTAs of 8 warps per SM (the kernel needs 128 registers), 2 items per warp
     const long long per_item = ((long long)n_list * quads + slots - 1) / slots;          // positions per item
-    int chunk = (int)std::max(4LL, std::min((long long)kEnergyChunk, (per_item + 31) / 32));
+    int chunk = (int)std::max(16LL, std::min((long long)kEnergyChunk, (per_item + 31) / 32));
     if (const char *e = getenv("NLMC_ENERGY_CHUNK")) chunk = std::max(1, std::min(kEnergyChunk, atoi(e)));
     const int site_chunks = (n_list + 32 * chunk - 1) / (32 * chunk);
     const long long items = (long long)site_chunks * quads;
@@ -824,6 +894,14 @@ static int launch_thrbits(nlmc_msc *M) {
 // threshold planes are rebuilt from the new labels
 static int launch_label_exchange(nlmc_msc *M, const double *E_full_dev, int num_pairs) {
     const MscDev d = dev_view(M);
+    if (M->n_ladders <= 1024 && !getenv("NLMC_MSC_SPLIT_EXCHANGE")) {
+        msc_label_round_kernel<<<1, 1024, 0, M->stream>>>(
+            M->n_beta_total, M->n_ladders, num_pairs, M->betas_total, E_full_dev, M->labels, M->slot_of, M->accepted,
+            M->accepted_rounds, d.seed_lo, d.seed_hi, M->d_counters, M->ladder_offset, M->k_steps + M->k_merged, M->W, M->G,
+            M->slot_begin, M->thr_total, M->thrbits, reinterpret_cast<uint4 *>(M->thr_lane), M->thr_nz);
+        NLMC_CUDA(cudaGetLastError());
+        return NLMC_OK;
+    }
     msc_clear_round_slot_kernel<<<1, 1, 0, M->stream>>>(M->accepted_rounds, M->d_counters);
     if (M->n_beta_total >= 2 && num_pairs > 0) {
         msc_label_swap_kernel<<<(M->n_ladders + 127) / 128, 128, 0, M->stream>>>(
@@ -1390,12 +1468,12 @@ int nlmc_msc_sweep_record(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, 
 /* m_layout 0: out_M [n_sweeps][n_beta][n]; 1: out_M [n_beta][n][n_sweeps] (rows of the reference's M). */
 // keep_M_on_device: the states are recorded into M->recM and left there (the caller fetches them itself)
 static int msc_record_impl(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M, double *out_E, int m_layout,
-                           bool keep_M_on_device) {
+                           bool keep_M_on_device, bool keep_E_on_device = false) {
     using namespace nlmc;
     NLMC_REQUIRE(m_layout == 0 || m_layout == 1, "nlmc_msc_sweep_record_layout: m_layout must be 0 or 1");
     const int n_sweeps_T = m_layout == 1 ? n_sweeps : 0;
     NLMC_REQUIRE(M && n_sweeps >= 0, "nlmc_msc_sweep_record: bad arguments");
-    const bool has_M = out_M != nullptr || keep_M_on_device, has_E = out_E != nullptr;
+    const bool has_M = out_M != nullptr || keep_M_on_device, has_E = out_E != nullptr || keep_E_on_device;
     NLMC_REQUIRE(!has_M || (ladder >= 0 && ladder < M->n_ladders), "nlmc_msc_sweep_record: ladder out of range");
     if (n_sweeps == 0) return NLMC_OK;
     NLMC_CUDA(cudaSetDevice(M->inst->device));
@@ -1453,8 +1531,9 @@ static int msc_record_impl(nlmc_msc *M, int n_sweeps, int ladder, int8_t *out_M,
         if (rc) return rc;
     }
     if (has_M && !keep_M_on_device) NLMC_CUDA(cudaMemcpyAsync(out_M, M->recM, need_M, cudaMemcpyDeviceToHost, M->stream));
-    if (has_E) NLMC_CUDA(cudaMemcpyAsync(out_E, M->recE, sizeof(double) * need_E, cudaMemcpyDeviceToHost, M->stream));
-    if (!keep_M_on_device) NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    if (has_E && !keep_E_on_device)
+        NLMC_CUDA(cudaMemcpyAsync(out_E, M->recE, sizeof(double) * need_E, cudaMemcpyDeviceToHost, M->stream));
+    if (!keep_M_on_device && !keep_E_on_device) NLMC_CUDA(cudaStreamSynchronize(M->stream));
     return NLMC_OK;
 }
 
@@ -1470,35 +1549,24 @@ int nlmc_msc_sweep_record_f64(nlmc_msc *M, int n_sweeps, int ladder, double *out
     using namespace nlmc;
     NLMC_REQUIRE(M && out_M_f64 && n_sweeps >= 0, "nlmc_msc_sweep_record_f64: bad arguments");
     if (n_sweeps == 0) return NLMC_OK;
-    static thread_local int8_t *stage = nullptr;   // pinned, grow-only, one per host thread (one host thread per handle)
-    static thread_local size_t stage_cap = 0;
-    constexpr int kChunks = 8;
-    static thread_local cudaEvent_t ev[kChunks] = {};
-    const size_t bytes = (size_t)M->n_beta * M->n * (size_t)n_sweeps;
     NLMC_CUDA(cudaSetDevice(M->inst->device));
-    if (bytes > stage_cap) {
-        if (stage) cudaFreeHost(stage);
-        stage = nullptr; stage_cap = 0;
-        NLMC_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&stage), bytes, cudaHostAllocDefault));
-        stage_cap = bytes;
-    }
-    for (int k = 0; k < kChunks; ++k)
-        if (!ev[k]) NLMC_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
-    // record on the device only (out_M = NULL keeps the copy out of the layout call), energies as before
+    // record on the device only, then fetch chunk by chunk (nlmc_host_fetch_widen_blocks)
     int rc = msc_record_impl(M, n_sweeps, ladder, nullptr, out_E, 1, true);
     if (rc) return rc;
-    const size_t per = ((bytes + kChunks - 1) / kChunks + 4095) & ~(size_t)4095;
-    for (int k = 0; k < kChunks; ++k) {
-        const size_t lo = std::min(bytes, per * (size_t)k), hi = std::min(bytes, lo + per);
-        if (lo < hi) NLMC_CUDA(cudaMemcpyAsync(stage + lo, M->recM + lo, hi - lo, cudaMemcpyDeviceToHost, M->stream));
-        NLMC_CUDA(cudaEventRecord(ev[k], M->stream));
-    }
-    for (int k = 0; k < kChunks; ++k) {
-        const size_t lo = std::min(bytes, per * (size_t)k), hi = std::min(bytes, lo + per);
-        NLMC_CUDA(cudaEventSynchronize(ev[k]));
-        if (lo < hi) nlmc::widen_i8_f64(stage + lo, out_M_f64 + lo, hi - lo, 0);
-    }
+    rc = nlmc_host_fetch_widen_blocks(M->recM, out_M_f64, 1, (uint64_t)M->n_beta * M->n * (uint64_t)n_sweeps, nullptr,
+                                      M->inst->device, M->stream);
+    if (rc) return rc;
     NLMC_CUDA(cudaStreamSynchronize(M->stream));
+    return NLMC_OK;
+}
+
+int nlmc_msc_sweep_record_dev(nlmc_msc *M, int n_sweeps, int ladder, int m_layout, int8_t **out_M_dev, double **out_E_dev) {
+    NLMC_REQUIRE(M && n_sweeps > 0 && (out_M_dev || out_E_dev), "nlmc_msc_sweep_record_dev: bad arguments");
+    NLMC_CUDA(cudaSetDevice(M->inst->device));
+    const int rc = msc_record_impl(M, n_sweeps, ladder, nullptr, nullptr, m_layout, out_M_dev != nullptr, out_E_dev != nullptr);
+    if (rc) return rc;
+    if (out_M_dev) *out_M_dev = M->recM;
+    if (out_E_dev) *out_E_dev = M->recE;
     return NLMC_OK;
 }
 

@@ -76,9 +76,11 @@ _SIGNATURES = {
     "nlmc_msc_sweep_record": [_vp, _int, _int, _vp, _vp],
     "nlmc_msc_sweep_record_layout": [_vp, _int, _int, _vp, _vp, _int],
     "nlmc_msc_sweep_record_f64": [_vp, _int, _int, _vp, _vp],
+    "nlmc_msc_sweep_record_dev": [_vp, _int, _int, _int, C.POINTER(_vp), C.POINTER(_vp)],
     "nlmc_msc_round": [_vp, _int, _int, _vp],
     "nlmc_host_widen_i8_f64": [_vp, _vp, _u64, _int],
     "nlmc_host_prefault": [_vp, _u64, _int],
+    "nlmc_host_fetch_widen_blocks": [_vp, _vp, _int, _u64, _vp, _int, _vp],
     "nlmc_msc_round_host": [_vp, _vp, _int, _int, _vp, _vp],
     "nlmc_msc_round_host_async": [_vp, _vp, _int, _int, _vp, _vp],
     "nlmc_msc_swap_count": [_vp, C.POINTER(_int), _int],
@@ -223,6 +225,27 @@ result_cache = _ResultCache()
 def release_host_cache():
     """Drop the cached result buffer (see _ResultCache)."""
     result_cache.release()
+
+
+def fetch_widen_blocks(dev_ptr: int, out: np.ndarray, n_blocks: int, block_elems: int, dst_block=None, device: int = 0,
+                       cuda_stream=None):
+    """Device int8 (address dev_ptr, n_blocks x block_elems) -> host float64 `out`, block b landing at block dst_block[b]
+    (None = identity); chunked through pinned staging and widened by the library's host workers."""
+    assert out.dtype == np.float64 and out.flags.c_contiguous and out.size >= n_blocks * block_elems
+    perm = None if dst_block is None else np.ascontiguousarray(dst_block, dtype=np.int32)
+    check(lib().nlmc_host_fetch_widen_blocks(dev_ptr, out.ctypes.data, int(n_blocks), int(block_elems),
+                                             None if perm is None else perm.ctypes.data, int(device), cuda_stream),
+          "nlmc_host_fetch_widen_blocks")
+    return out
+
+
+class DevArray:
+    """A device buffer given by address as a __cuda_array_interface__ object (torch.as_tensor(DevArray(...), device=...)
+    wraps it without a copy).  The memory stays owned by whoever handed out the address."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
 
 
 def widen_to_f64(a: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
@@ -520,6 +543,17 @@ class Msc:
         check(lib().nlmc_msc_sweep_record_f64(self._h, int(n_sweeps), int(ladder), Mf.ctypes.data, Erec.ctypes.data),
               "nlmc_msc_sweep_record_f64")
         return Mf, Erec
+
+    def sweep_record_dev(self, n_sweeps: int, ladder: int = 0, rows_of_M: bool = True, states: bool = True,
+                         energies: bool = True):
+        """n_sweeps recorded sweeps left on the device, no synchronisation: (address of the int8 states -- [n_beta][n]
+        [n_sweeps] with rows_of_M, else [n_sweeps][n_beta][n] -- or None, address of the float64 energies [n_sweeps][n_beta]
+        [n_ladders] or None).  The buffers belong to the handle (valid until its next record call)."""
+        pm, pe = _vp(), _vp()
+        check(lib().nlmc_msc_sweep_record_dev(self._h, int(n_sweeps), int(ladder), 1 if rows_of_M else 0,
+                                              C.byref(pm) if states else None, C.byref(pe) if energies else None),
+              "nlmc_msc_sweep_record_dev")
+        return (pm.value if states else None), (pe.value if energies else None)
 
     def round(self, n_sweeps: int, num_swapping_pairs: int, fetch_energies: bool = False):
         out = np.empty((self.n_beta, self.n_ladders), dtype=np.float64) if fetch_energies else None

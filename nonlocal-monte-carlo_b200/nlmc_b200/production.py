@@ -128,8 +128,12 @@ def _npt_run_msc(obj, prob, beta_list):
 
 def _npt_run_msc_sharded(obj, prob, beta_list):
     """NPT.run on N GPUs: slots [first, first + count) of every ladder live on this rank.  Per round the ranks
-    all-gather one float64 per replica and take identical label decisions; the last round's recorded states (int8,
-    run 0) and energies are all-gathered once and put into beta order through the labels."""
+    all-gather one float64 per replica and take identical label decisions.  The last round is recorded on the device;
+    the int8 states of run 0 and the energies are all-gathered once (NCCL, device to device) and the ranks listed in
+    ``obj.m_on_ranks`` (default: every rank) fetch them and widen them into the reference's float64 M in temperature
+    order -- the other ranks return M = None and the same Energy.  With 8 ranks on one host, eight float64 copies of M
+    (1 GB each at C5 size) are pure host-memory traffic; ``m_on_ranks = (0,)`` is what a job that post-processes on one
+    rank wants."""
     import torch
     from .distributed import ShardedBetaLadder, beta_shard
     dist, world, rank = _process_group()
@@ -139,6 +143,8 @@ def _npt_run_msc_sharded(obj, prob, beta_list):
     n = prob.n
     nccl = dist.get_backend() == "nccl"
     dev = torch.device("cuda", prob.inst.device) if nccl else torch.device("cpu")
+    m_ranks = getattr(obj, "m_on_ranks", None)
+    want_M = m_ranks is None or rank in tuple(m_ranks)
     seed_t = torch.tensor([_seed_from_numpy() & (2**62 - 1)], dtype=torch.int64, device=dev)
     dist.broadcast(seed_t, 0)  # one seed for the whole job
     try:
@@ -146,34 +152,63 @@ def _npt_run_msc_sharded(obj, prob, beta_list):
     except _lib.NlmcError as e:
         raise _NotBitPackable(f"mode='production' on several GPUs needs a +-J lattice instance ({e})") from e
     msc = ens.msc
+    L = msc.n_ladders
     count = np.zeros(obj.num_swap_attempts)
     for ii in range(obj.num_swap_attempts - 1):
         ens.round(spm, obj.num_swapping_pairs)
-    M = np.zeros((R * n, spm))
+    M = np.zeros((R * n, spm)) if want_M else None
     E_cols = np.zeros((R, spm))
     E_all = None
     if spm > 0:
-        ens.synchronize()
-        labels = msc.labels().astype(np.int64)  # fixed during the round's sweeps
-        Mrec, Erec = msc.sweep_record(spm, ladder=0, energies=True, rows_of_M=True)  # [count][n][spm], [spm][count][ladders]
         cmax = beta_shard(R, world, 0)[1]
-        send_M = torch.zeros((cmax, n, spm), dtype=torch.int8, device=dev)
-        send_E = torch.zeros((spm, cmax, msc.n_ladders), dtype=torch.float64, device=dev)
-        send_M[:ens.count] = torch.from_numpy(Mrec).to(dev)
-        send_E[:, :ens.count] = torch.from_numpy(Erec).to(dev)
-        recv_M = torch.empty((world,) + tuple(send_M.shape), dtype=torch.int8, device=dev)
-        recv_E = torch.empty((world,) + tuple(send_E.shape), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(recv_M.view(-1, spm), send_M.view(-1, spm))
-        dist.all_gather_into_tensor(recv_E.view(-1, msc.n_ladders), send_E.view(-1, msc.n_ladders))
-        recv_M, recv_E = recv_M.cpu().numpy(), recv_E.cpu().numpy()
-        Mi8 = np.empty((R, n, spm), dtype=np.int8)
-        E_slots = np.empty((spm, R, msc.n_ladders))
-        for r in range(world):
-            f, c = beta_shard(R, world, r)
-            E_slots[:, f:f + c] = recv_E[r, :, :c]
-            for s in range(c):
-                Mi8[labels[f + s, 0]] = recv_M[r, s]              # slot f+s of run 0 holds temperature labels[f+s, 0]
-        M = _lib.widen_to_f64(Mi8).reshape(R * n, spm)
+        shards = [beta_shard(R, world, r) for r in range(world)]
+        blk = n * spm                                           # one slot of run 0: a block of rows of M
+        if nccl:
+            with ens._on_stream():
+                pM, pE = msc.sweep_record_dev(spm, ladder=0, rows_of_M=True)      # queued; buffers owned by the handle
+                rec_M = torch.as_tensor(_lib.DevArray(pM, (ens.count * blk,), "|i1"), device=dev)
+                rec_E = torch.as_tensor(_lib.DevArray(pE, (spm, ens.count, L), "<f8"), device=dev)
+                if ens.count == cmax:
+                    send_M = rec_M
+                else:
+                    send_M = torch.zeros(cmax * blk, dtype=torch.int8, device=dev)
+                    send_M[:ens.count * blk].copy_(rec_M)
+                send_E = torch.zeros((spm, cmax, L), dtype=torch.float64, device=dev)
+                send_E[:, :ens.count].copy_(rec_E)
+                recv_M = torch.empty(world * cmax * blk, dtype=torch.int8, device=dev)
+                recv_E = torch.empty((world, spm, cmax, L), dtype=torch.float64, device=dev)
+                dist.all_gather_into_tensor(recv_M, send_M)
+                dist.all_gather_into_tensor(recv_E.view(-1, L), send_E.view(-1, L))
+                recv_E_h = recv_E.cpu().numpy()                 # waits for the stream
+            labels = msc.labels().astype(np.int64)              # labels of the recorded round (the sweeps do not change them)
+            if want_M:
+                M = _lib.result_cache.take((R * n, spm))
+                for r, (f, c) in enumerate(shards):             # slot f+s of run 0 holds temperature labels[f+s, 0]
+                    _lib.fetch_widen_blocks(recv_M.data_ptr() + r * cmax * blk, M, c, blk, labels[f:f + c, 0],
+                                            device=prob.inst.device, cuda_stream=ens.stream.cuda_stream)
+                ens.synchronize()
+        else:  # host tensors (gloo): the same data flow without device buffers
+            ens.synchronize()
+            labels = msc.labels().astype(np.int64)
+            Mrec, Erec = msc.sweep_record(spm, ladder=0, energies=True, rows_of_M=True)  # [count][n][spm], [spm][count][ladders]
+            send_M = torch.zeros((cmax, n, spm), dtype=torch.int8)
+            send_E = torch.zeros((spm, cmax, L), dtype=torch.float64)
+            send_M[:ens.count] = torch.from_numpy(Mrec)
+            send_E[:, :ens.count] = torch.from_numpy(Erec)
+            recv_M = torch.empty((world,) + tuple(send_M.shape), dtype=torch.int8)
+            recv_E = torch.empty((world,) + tuple(send_E.shape), dtype=torch.float64)
+            dist.all_gather_into_tensor(recv_M.view(-1, spm), send_M.view(-1, spm))
+            dist.all_gather_into_tensor(recv_E.view(-1, L), send_E.view(-1, L))
+            recv_E_h = recv_E.numpy()
+            if want_M:
+                Mi8 = np.empty((R, n, spm), dtype=np.int8)
+                for r, (f, c) in enumerate(shards):
+                    for s in range(c):
+                        Mi8[labels[f + s, 0]] = recv_M[r, s].numpy()
+                M = _lib.widen_to_f64(Mi8).reshape(R * n, spm)
+        E_slots = np.empty((spm, R, L))
+        for r, (f, c) in enumerate(shards):
+            E_slots[:, f:f + c] = recv_E_h[r, :, :c]
         E_by_beta = np.empty_like(E_slots)
         np.put_along_axis(E_by_beta, np.broadcast_to(labels[None], E_slots.shape), E_slots, axis=1)
         E_cols[:] = E_by_beta[:, :, 0].T
