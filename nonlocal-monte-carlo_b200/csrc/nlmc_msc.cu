@@ -210,10 +210,11 @@ template <int kSteps, bool kPerBit, int kMerged>
 #endif
 __global__ void __launch_bounds__(NLMC_SWEEP_THREADS, (kPerBit ? NLMC_PERBIT_CTAS : NLMC_SCALAR_CTAS) * (256 / NLMC_SWEEP_THREADS))
 msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const uint32_t *__restrict__ counters,
-                 uint32_t sweep_in_batch) {
+                 uint32_t sweep_in_batch, int pdl) {
     const int idx = (int)(blockIdx.x * (unsigned)NLMC_SWEEP_THREADS + threadIdx.x);  // position within the colour
+    // programmatic dependent launch (pdl): the next colour's grid may be scheduled while this one drains
+    if (pdl & 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (idx >= n_sites) return;
-    const uint32_t sweep = counters[0] + sweep_in_batch;
     const int b = (int)blockIdx.y, qin = (int)blockIdx.z;     // slot and quad within the slot: uniform over the CTA
     const int qd = b * a.qpb + qin;
     const int pos = first + idx;
@@ -222,6 +223,9 @@ msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const
     const uint32_t meta = (uint32_t)r1.z;
     const int site = r1.w;
     uint4 *Sq = reinterpret_cast<uint4 *>(a.S) + (size_t)qd * a.n;
+    // the record above is constant data; the spins and the sweep counter are written by the launch before this one
+    if (pdl & 1) asm volatile("griddepcontrol.wait;" ::: "memory");
+    const uint32_t sweep = counters[0] + sweep_in_batch;
     // all six loads are issued back to back (a padding slot reads position 0 and is masked below)
     uint4 x[6];
 #pragma unroll
@@ -810,16 +814,31 @@ static MscThr thr_view(const nlmc_msc *M) {
     return t;
 }
 
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int kSteps>
-static void launch_colour(const nlmc_msc *M, const MscDev &d, const MscThr &t, int first, int cnt, uint32_t sweep_in_batch) {
+static void launch_colour(const nlmc_msc *M, const MscDev &d, const MscThr &t, int first, int cnt, uint32_t sweep_in_batch,
+                          bool pdl, bool trigger) {
     constexpr int kT = NLMC_SWEEP_THREADS;
     const dim3 blocks((unsigned)((cnt + kT - 1) / kT), (unsigned)M->n_beta, (unsigned)d.qpb);
+    const uint32_t *ctr = M->d_counters;
+    const int flag = (pdl ? 1 : 0) | (trigger ? 2 : 0);  // bit 0: wait for the launch before, bit 1: let the next one start early
     if (M->label_mode) {
-        if (M->k_merged) msc_sweep_kernel<kSteps, true, 4><<<blocks, kT, 0, M->stream>>>(d, t, first, cnt, M->d_counters, sweep_in_batch);
-        else msc_sweep_kernel<kSteps, true, 0><<<blocks, kT, 0, M->stream>>>(d, t, first, cnt, M->d_counters, sweep_in_batch);
+        if (M->k_merged) launch_maybe_pdl(msc_sweep_kernel<kSteps, true, 4>, blocks, dim3(kT), M->stream, pdl, d, t, first, cnt, ctr, sweep_in_batch, flag);
+        else launch_maybe_pdl(msc_sweep_kernel<kSteps, true, 0>, blocks, dim3(kT), M->stream, pdl, d, t, first, cnt, ctr, sweep_in_batch, flag);
     } else {
-        if (M->k_merged) msc_sweep_kernel<kSteps, false, 4><<<blocks, kT, 0, M->stream>>>(d, t, first, cnt, M->d_counters, sweep_in_batch);
-        else msc_sweep_kernel<kSteps, false, 0><<<blocks, kT, 0, M->stream>>>(d, t, first, cnt, M->d_counters, sweep_in_batch);
+        if (M->k_merged) launch_maybe_pdl(msc_sweep_kernel<kSteps, false, 4>, blocks, dim3(kT), M->stream, pdl, d, t, first, cnt, ctr, sweep_in_batch, flag);
+        else launch_maybe_pdl(msc_sweep_kernel<kSteps, false, 0>, blocks, dim3(kT), M->stream, pdl, d, t, first, cnt, ctr, sweep_in_batch, flag);
     }
 }
 
@@ -827,23 +846,31 @@ static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
     const MscDev d = dev_view(M);
     const MscThr t = thr_view(M);
     // The sweep index a kernel hashes into its random stream is counters[0] + its position in the batch.  Short site rows
-    // (a block of a sharded ladder: 28 us per colour launch at 16 words) bump the counter once per batch; full rows keep
-    // the 1-thread bump kernel after every sweep, which measured 2 % FASTER there (profiles/r1b_sweep_kernel_source.md).
-    const bool bump_once = M->W < 128 ? !getenv("NLMC_MSC_BUMP_EACH") : getenv("NLMC_MSC_BUMP_ONCE") != nullptr;
+    // (a block of a sharded ladder: 22 us per colour launch at 16 words) bump the counter once per batch; full rows keep
+    // the 1-thread bump kernel after every sweep, which measured 2 % FASTER there (round 1, and again in round 2).
+    // NLMC_MSC_PDL=1 chains the colour launches of a batch with programmatic dependent launch (the next grid is scheduled
+    // while the previous one drains and waits for it just before its first load of spins): +1 % on back-to-back sweeps,
+    // -2.5 % on whole C5 rounds (it implies the single bump), so it is off by default.
+    const char *e_pdl = getenv("NLMC_MSC_PDL");
+    const bool pdl = e_pdl ? atoi(e_pdl) != 0 : false;
+    const bool bump_once = pdl || (M->W < 128 ? !getenv("NLMC_MSC_BUMP_EACH") : getenv("NLMC_MSC_BUMP_ONCE") != nullptr);
+    bool chained = false;  // the launch before this one in the stream is a sweep kernel of this batch
     for (int s = 0; s < n_sweeps; ++s) {
         const uint32_t off = bump_once ? (uint32_t)s : 0u;
         for (int c = 0; c < M->n_colours; ++c) {
             const int first = M->colour_ptr[c], cnt = M->colour_ptr[c + 1] - first;
             if (cnt == 0) continue;
+            const bool p = pdl && chained;
             switch (M->k_steps) {
-                case 4: launch_colour<4>(M, d, t, first, cnt, off); break;
-                case 5: launch_colour<5>(M, d, t, first, cnt, off); break;
-                case 7: launch_colour<7>(M, d, t, first, cnt, off); break;
-                case 8: launch_colour<8>(M, d, t, first, cnt, off); break;
-                default: launch_colour<6>(M, d, t, first, cnt, off); break;
+                case 4: launch_colour<4>(M, d, t, first, cnt, off, p, pdl); break;
+                case 6: launch_colour<6>(M, d, t, first, cnt, off, p, pdl); break;
+                case 7: launch_colour<7>(M, d, t, first, cnt, off, p, pdl); break;
+                case 8: launch_colour<8>(M, d, t, first, cnt, off, p, pdl); break;
+                default: launch_colour<5>(M, d, t, first, cnt, off, p, pdl); break;
             }
+            chained = true;
         }
-        if (!bump_once) msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 0);
+        if (!bump_once) { msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 0); chained = false; }
     }
     if (bump_once && n_sweeps > 0) msc_bump_kernel<<<1, 1, 0, M->stream>>>(M->d_counters, 0, (uint32_t)n_sweeps);
     NLMC_CUDA(cudaGetLastError());
