@@ -407,3 +407,55 @@ def test_full_size_c5_properties(nl):
     assert np.array_equal(np.sort(E2, axis=0), np.sort(E, axis=0)) and a.swap_count() > 0
     assert int(np.unpackbits(a.get_packed().view(np.uint8)).sum()) == ones_before
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("steps,merged", [(6, 0), (4, 1), (5, 1), (8, 1)])
+def test_exact_boltzmann_for_every_form_of_the_bernoulli_draw(nl, monkeypatch, steps, merged):
+    """The draw g ~ B(q) has tuning knobs (unconditional steps, merged round); every setting must sample the same law.
+    The ladder reaches beta = 2.4 (all unconditional steps are zero steps there: thresholds below 2^-13) and beta = 0.05
+    (threshold bits set from the second step on), with exchanges, in both the scalar-threshold and the beta-label form."""
+    monkeypatch.setenv("NLMC_MSC_STEPS", str(steps))
+    monkeypatch.setenv("NLMC_MSC_MERGED", str(merged))
+    A, h = lattice_2d(4, 23)
+    betas = np.array([0.05, 0.4, 1.0, 2.4])
+    exact = exact_mean_energy(A, betas)
+    prob = nl.host.Problem(A, h)
+    for labelled in (False, True):
+        msc = nl.lib.Msc(prob.inst, betas, 1024, seed=77 + steps, labelled=labelled)
+        for _ in range(40):
+            msc.round(5, 2)
+        samples = []
+        for _ in range(60):
+            msc.round(4, 2)
+            E = msc.energies()
+            if labelled:  # energies come by slot; put them in temperature order
+                lab = msc.labels().astype(np.int64)
+                Eb = np.empty_like(E)
+                np.put_along_axis(Eb, lab, E, axis=0)
+                E = Eb
+            samples.append(E)
+        S = np.array(samples)
+        for b in range(len(betas)):
+            per_ladder = S[:, b, :].mean(axis=0)
+            mean, err = per_ladder.mean(), per_ladder.std(ddof=1) / np.sqrt(per_ladder.size)
+            assert abs(mean - exact[b][0]) <= 3.0 * err + 1e-9, (steps, merged, labelled, betas[b], mean, exact[b][0], err)
+        msc.close()
+
+
+def test_block_fetch_widens_in_the_requested_order(nl):
+    """nlmc_host_fetch_widen_blocks: device int8 blocks -> host float64 blocks through the pinned staging buffer, with
+    and without a block permutation (how the recorded states of a sharded ladder reach M in temperature order)."""
+    import torch
+    rs = np.random.RandomState(3)
+    for n_blocks, elems in ((1, 1000003), (7, 4099), (32, 65536)):
+        src = rs.randint(-1, 2, size=(n_blocks, elems)).astype(np.int8)
+        d = torch.from_numpy(src).cuda()
+        out = np.full((n_blocks, elems), np.nan)
+        nl.lib.fetch_widen_blocks(d.data_ptr(), out, n_blocks, elems)
+        torch.cuda.synchronize()
+        assert np.array_equal(out, src.astype(np.float64))
+        perm = rs.permutation(n_blocks).astype(np.int32)
+        out2 = np.full((n_blocks, elems), np.nan)
+        nl.lib.fetch_widen_blocks(d.data_ptr(), out2, n_blocks, elems, dst_block=perm)
+        torch.cuda.synchronize()
+        assert np.array_equal(out2[perm], src.astype(np.float64))

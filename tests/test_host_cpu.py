@@ -129,3 +129,29 @@ def test_bench_module_is_whole_and_reference_arm_runs():
                 "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_result_cache_never_hands_out_a_buffer_that_is_still_referenced():
+    """The caching allocator behind the large float64 results (NPT.run's M): a buffer is reused only when neither the array
+    handed out earlier nor a view of it is alive."""
+    from nlmc_b200 import _lib
+    _lib.release_host_cache()
+    shape = (1 << 20, 16)            # 128 MB: above the caching threshold
+    a = _lib.result_cache.take(shape)
+    a[0, 0] = 42.0
+    addr_a = a.ctypes.data
+    b = _lib.result_cache.take(shape)      # a is alive: a different buffer
+    assert b.ctypes.data != addr_a and a[0, 0] == 42.0
+    addr_b = b.ctypes.data
+    v = b[:10]                             # a view keeps the buffer busy
+    del b
+    c = _lib.result_cache.take(shape)
+    assert c.ctypes.data != addr_b
+    addr_c = c.ctypes.data
+    del c, v
+    d = _lib.result_cache.take((1 << 19, 16))   # free and large enough: reused
+    assert d.ctypes.data == addr_c and d.shape == (1 << 19, 16) and d.dtype == np.float64
+    small = _lib.result_cache.take((4, 4))      # small results are plain arrays
+    assert small.shape == (4, 4)
+    del d
+    _lib.release_host_cache()
