@@ -269,7 +269,8 @@ def run_ours(args, rank, world, local_rank):
         msc, step = ens.msc, (lambda: ens.round(spm, pairs))
         exchange = ("beta labels: energies all-gathered over NCCL (8 B per replica), identical Philox-keyed decisions on every "
                     "rank, thresholds rebuilt from the labels (msc_label_swap + msc_thrbits)")
-        kernels_per_step = spm * (msc.n_colours + 1) + 2 + 4   # sweeps + bumps, energy (2), clear/label_swap/thrbits/bump
+        bumps = 1 if msc.n_words < 128 else spm                  # short site rows bump the sweep counter once per batch
+        kernels_per_step = spm * msc.n_colours + bumps + 2 + 1   # sweeps + bumps, energy (2), label exchange (one fused launch)
     n_ladders = msc.n_ladders
     replicas_total = n_beta * n_ladders
     attempts_per_step = replicas_total * n * spm
@@ -292,7 +293,7 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     packed_bytes = 2.0 * (n / msc.n_colours) * msc.n_words * 4        # read the other colour once + write this colour
     traffic = ncu_traffic()
-    kernel_name = (f"msc_sweep_kernel<{7 if world > 1 else 6} steps, {'bit planes' if world > 1 else 'scalar thresholds'}> "
+    kernel_name = (f"msc_sweep_kernel<5 steps + 4 merged, {'bit planes' if world > 1 else 'scalar thresholds'}> "
                    "(one colour of one sweep)")
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": packed_bytes / (sweep_ms * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": packed_bytes / (sweep_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
@@ -303,7 +304,7 @@ def run_ours(args, rank, world, local_rank):
                 "share_of_step": (sweep_ms * spm * msc.n_colours) / (ms / args.steps),
                 "note": "algorithmic bytes of the bit-packed layout (SURVEY 8d: 0.25 B/attempt = read the other colour's rows + "
                         "write this colour's, 1 bit per spin).  The kernel is bound by integer issue (Philox4x32-10 + bit-sliced "
-                        "compare), not by HBM: see roofline_issue.  SURVEY 8d's generic int8-CSR figure (42 B/attempt) does not "
+                        "compare: the ALU pipe is the busiest unit), not by HBM: see roofline_issue.  SURVEY 8d's generic int8-CSR figure (42 B/attempt) does not "
                         "describe this layout; against it the same launch would read as "
                         f"{SURVEY_BYTES_PER_ATTEMPT * attempts_per_launch / (sweep_ms * 1e-3) / 1e9 / peak:.1f} x the HBM peak"}
     roofline_issue = None

@@ -52,6 +52,11 @@ struct nlmc_msc {
     uint32_t *thr_nz = nullptr;   // label mode: [W/4] steps at which the quad's threshold planes are not all zero
     uint32_t *rows = nullptr;     // scratch [n][W]: the site-major packed state of the C ABI (nlmc_msc_get/set_packed)
     std::vector<int> colour_ptr;  // [n_colours+1]
+    // launch classes: the sites of a colour, split by the parity of their degree (first position, count, odd flag);
+    // a launch of the sweep kernel covers one class, so the thresholds (|f| = 2,4,6 or 1,3,5) are uniform over it
+    struct SiteClass { int first, count, odd; };
+    std::vector<SiteClass> classes;
+    bool has_odd = false;         // some site has odd degree: the label form keeps a second set of threshold tables
     uint32_t *thr = nullptr;      // [n_beta][4] thresholds of |f| = 0,2,4,6
     double *betas = nullptr;      // [n_beta]
     int32_t *E_acc = nullptr;     // [W*32] sum_i (unsatisfied bonds at i) per (word, lane)
@@ -74,7 +79,7 @@ struct nlmc_msc {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<double> h_betas;
-    std::vector<uint32_t> h_thr;  // [n_beta][4] host copy of thr: the sweep kernel takes the thresholds as a launch argument
+    std::vector<uint32_t> h_thr, h_thr_odd;  // [n_beta][4] thresholds (even / odd degree): launch arguments of the sweep kernel
 };
 
 namespace nlmc {
@@ -130,6 +135,10 @@ struct MscDev {
     const uint32_t *thrbits;    // label mode: [kSteps][3][W]
     const uint4 *thr_lane;      // label mode: [W][32] thresholds {-, T1, T2, T3} of every lane
     const uint32_t *thr_nz;     // label mode: [W/4] bit p set <=> some threshold plane of the quad is non-zero at step p
+    // label mode, sites of odd degree: the same three tables for the levels |f| = 1, 3, 5 (NULL when every degree is even)
+    const uint32_t *thrbits_odd;
+    const uint4 *thr_lane_odd;
+    const uint32_t *thr_nz_odd;
     uint32_t *S;
     const int4 *rec;      // [n][2] by position: {nbr0..3}, {nbr4, nbr5, sign bits, site}; neighbours as POSITIONS (-1 = padding)
     const int32_t *site_list;   // [n] site at a position
@@ -139,7 +148,8 @@ struct MscDev {
 
 // thresholds of the handle's slots for the levels |f| = 2, 4, 6 as a kernel parameter: read through the constant bank
 // with a uniform index, they (and every bit test on them) stay in uniform registers
-struct MscThr { uint32_t t[kMaxBeta * 3]; };
+// (t: |f| = 2, 4, 6 for sites of even degree; t_odd: |f| = 1, 3, 5 for sites of odd degree)
+struct MscThr { uint32_t t[kMaxBeta * 3]; uint32_t t_odd[kMaxBeta * 3]; };
 
 __device__ __forceinline__ size_t word_index(const MscDev &a, int pos, int w) {
     return ((size_t)(w >> 2) * a.n + pos) * 4 + (w & 3);
@@ -198,7 +208,7 @@ __device__ __forceinline__ uint32_t comp(const uint4 &v, int k) { return k == 0 
 // there -- and kMerged further comparison steps run on that word with one Philox call; the results are scattered back.
 // A lane that lost its column to another word simply waits for the straggler loop.  Every random bit is still used by
 // at most one lane, chosen by the past only, so the draw stays exact.
-template <int kSteps, bool kPerBit, int kMerged>
+template <int kSteps, bool kPerBit, int kMerged, bool kOdd>
 #ifndef NLMC_PERBIT_CTAS
 #define NLMC_PERBIT_CTAS 4
 #endif
@@ -211,6 +221,7 @@ template <int kSteps, bool kPerBit, int kMerged>
 __global__ void __launch_bounds__(NLMC_SWEEP_THREADS, (kPerBit ? NLMC_PERBIT_CTAS : NLMC_SCALAR_CTAS) * (256 / NLMC_SWEEP_THREADS))
 msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const uint32_t *__restrict__ counters,
                  uint32_t sweep_in_batch, int pdl) {
+    constexpr bool odd = kOdd;  // the launch holds sites of odd degree (levels |f| = 1, 3, 5)
     const int idx = (int)(blockIdx.x * (unsigned)NLMC_SWEEP_THREADS + threadIdx.x);  // position within the colour
     // programmatic dependent launch (pdl): the next colour's grid may be scheduled while this one drains
     if (pdl & 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -243,24 +254,37 @@ msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const
         x[d].z = (x[d].z & keep) ^ flip;
         x[d].w = (x[d].w & keep) ^ flip;
     }
-    // lane sets of the |f| levels 1..3 (|f| = 2, 4, 6), level 0 being the rest; sign plane pos = [c >= 4]
+    // Lane sets of the |f| levels 1..3, level 0 being the rest, and the sign plane.  Sites of even degree (padded to six
+    // slots with neutral pairs): f = 2c - 6, levels |f| = 2, 4, 6, level 0 = zero field, sign = [c >= 4].  Sites of odd
+    // degree (neutral pairs plus one slot at -1; a launch holds sites of one parity, `odd` is uniform): f = 2c - 5 with
+    // c in 0..5, levels |f| = 1, 3, 5, no zero-field lanes, sign = [c >= 3].
     uint32_t I1[4], I2[4], I3[4], sgn[4], res[4], und[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         uint32_t c0, c1, c2;
         count6(comp(x[0], k), comp(x[1], k), comp(x[2], k), comp(x[3], k), comp(x[4], k), comp(x[5], k), c0, c1, c2);
-        const uint32_t m0 = ~c0;                                 // |c - 3| = (m1 m0)
-        const uint32_t m1 = (c2 & (c1 | c0)) | (~c2 & ~c1);
-        I1[k] = ~m1 & m0;
-        I2[k] = m1 & ~m0;
-        I3[k] = m1 & m0;
-        sgn[k] = c2;
+        if (!odd) {
+            const uint32_t m0 = ~c0;                                 // |c - 3| = (m1 m0)
+            const uint32_t m1 = (c2 & (c1 | c0)) | (~c2 & ~c1);
+            I1[k] = ~m1 & m0;
+            I2[k] = m1 & ~m0;
+            I3[k] = m1 & m0;
+            sgn[k] = c2;
+        } else {
+            I1[k] = ~c2 & c1;                                        // c in {2, 3}: |f| = 1
+            I2[k] = ~c1 & (c2 ^ c0);                                 // c in {1, 4}: |f| = 3
+            I3[k] = ~c1 & ~(c2 ^ c0);                                // c in {0, 5}: |f| = 5
+            sgn[k] = c2 | (c1 & c0);
+        }
     }
     uint32_t T1 = 0, T2 = 0, T3 = 0, nzmask;
+    const uint32_t *thrbits = odd ? a.thrbits_odd : a.thrbits;
+    const uint4 *thr_lane = odd ? a.thr_lane_odd : a.thr_lane;
     if (kPerBit) {
-        nzmask = __ldg(a.thr_nz + qd);
+        nzmask = __ldg((odd ? a.thr_nz_odd : a.thr_nz) + qd);
     } else {
-        T1 = thr.t[b * 3]; T2 = thr.t[b * 3 + 1]; T3 = thr.t[b * 3 + 2];
+        const uint32_t *tt = odd ? thr.t_odd : thr.t;
+        T1 = tt[b * 3]; T2 = tt[b * 3 + 1]; T3 = tt[b * 3 + 2];
         nzmask = __brev(T1 | T2 | T3);  // bit p <=> some level has threshold bit 31 - p set
     }
     const Philox rng{a.seed_lo, a.seed_hi ^ kTagSweep};
@@ -277,7 +301,7 @@ msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const
             uint4 A1, A2, A3;
             uint32_t p1 = 0, p2 = 0, p3 = 0;
             if (kPerBit) {
-                const uint32_t *tb = a.thrbits + (size_t)p * 3 * a.W + qd * 4;
+                const uint32_t *tb = thrbits + (size_t)p * 3 * a.W + qd * 4;
                 A1 = __ldg(reinterpret_cast<const uint4 *>(tb));
                 A2 = __ldg(reinterpret_cast<const uint4 *>(tb + a.W));
                 A3 = __ldg(reinterpret_cast<const uint4 *>(tb + 2 * a.W));
@@ -333,7 +357,7 @@ msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const
             if ((nzmask >> p) & 1u) {
                 uint32_t t;
                 if (kPerBit) {
-                    const uint32_t *tb = a.thrbits + (size_t)p * 3 * a.W + qd * 4;
+                    const uint32_t *tb = thrbits + (size_t)p * 3 * a.W + qd * 4;
                     const uint4 A1 = __ldg(reinterpret_cast<const uint4 *>(tb));
                     const uint4 A2 = __ldg(reinterpret_cast<const uint4 *>(tb + a.W));
                     const uint4 A3 = __ldg(reinterpret_cast<const uint4 *>(tb + 2 * a.W));
@@ -374,7 +398,7 @@ msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const
                 if (kPerBit) {
                     rem = 0u;
                     if (bit) {
-                        const uint4 tl = __ldg(a.thr_lane + (size_t)(qd * 4 + k) * 32 + (__ffs((int)bit) - 1));
+                        const uint4 tl = __ldg(thr_lane + (size_t)(qd * 4 + k) * 32 + (__ffs((int)bit) - 1));
                         rem = (I3[k] & bit) ? tl.w : (I2[k] & bit) ? tl.z : tl.y;
                         rem <<= (kMerged > 0 && (adv[k] & bit)) ? kSteps + kMerged : kSteps;
                     }
@@ -681,7 +705,8 @@ __device__ __forceinline__ void thrnz_item(int qd, int planes, int W, const uint
 __global__ void __launch_bounds__(1024) msc_label_round_kernel(
     int n_beta, int n_ladders, int num_pairs, const double *betas, const double *E, uint8_t *labels, uint8_t *slot_of,
     int32_t *accepted, int32_t *accepted_rounds, uint32_t seed_lo, uint32_t seed_hi, uint32_t *counters, int ladder_offset,
-    int planes, int W, int G, int slot_begin, const uint32_t *thr_total, uint32_t *thrbits, uint4 *thr_lane, uint32_t *thr_nz) {
+    int planes, int W, int G, int slot_begin, const uint32_t *thr_total, uint32_t *thrbits, uint4 *thr_lane, uint32_t *thr_nz,
+    int sets) {
     const uint32_t round = counters[1];
     const int tid = threadIdx.x;
     if (tid == 0) accepted_rounds[round % kRoundLog] = 0;
@@ -693,10 +718,16 @@ __global__ void __launch_bounds__(1024) msc_label_round_kernel(
         __syncthreads();
         const int items = max(planes * 3, 32) * W;
         const uint8_t *labels_local = labels + (size_t)slot_begin * n_ladders;
-        for (int idx = tid; idx < items; idx += (int)blockDim.x)
-            thrbits_item(idx, planes, W, G, labels_local, thr_total, thrbits, thr_lane);
+        for (int idx = tid; idx < items * sets; idx += (int)blockDim.x) {
+            const int set = idx / items;   // 0: even degree, 1: odd degree (tables of set 1 follow those of set 0)
+            thrbits_item(idx - set * items, planes, W, G, labels_local, thr_total + (size_t)set * n_beta * 4,
+                         thrbits + (size_t)set * planes * 3 * W, thr_lane + (size_t)set * W * 32);
+        }
         __syncthreads();
-        for (int qd = tid; qd < W / 4; qd += (int)blockDim.x) thrnz_item(qd, planes, W, thrbits, thr_nz);
+        for (int q = tid; q < (W / 4) * sets; q += (int)blockDim.x) {
+            const int set = q / (W / 4);
+            thrnz_item(q - set * (W / 4), planes, W, thrbits + (size_t)set * planes * 3 * W, thr_nz + (size_t)set * (W / 4));
+        }
     }
     __syncthreads();
     if (tid == 0) counters[1] = round + 1u;
@@ -780,13 +811,15 @@ __global__ void msc_from_rows_kernel(MscDev a, const uint4 *rows) {
     reinterpret_cast<uint4 *>(a.S)[(size_t)qd * a.n + __ldg(a.pos_of + i)] = rows[idx];
 }
 
-// 32-bit thresholds of q(|f|) = 1/(1 + exp(2*beta*|f|)) for |f| = 0, 2, 4, 6
-static std::vector<uint32_t> msc_thresholds(int n_beta, const double *betas) {
+// 32-bit thresholds of q(|f|) = 1/(1 + exp(2*beta*|f|)) for |f| = 0, 2, 4, 6 (sites of even degree) or, with odd = true,
+// for |f| = -, 1, 3, 5 (sites of odd degree; entry 0 unused)
+static std::vector<uint32_t> msc_thresholds(int n_beta, const double *betas, bool odd = false) {
     std::vector<uint32_t> thr((size_t)n_beta * 4);
     for (int b = 0; b < n_beta; ++b) {
         thr[(size_t)b * 4] = 0x80000000u;
         for (int a = 1; a < 4; ++a) {
-            const double q = 1.0 / (1.0 + std::exp(2.0 * betas[b] * (2.0 * a)));
+            const double f = odd ? 2.0 * a - 1.0 : 2.0 * a;
+            const double q = 1.0 / (1.0 + std::exp(2.0 * betas[b] * f));
             thr[(size_t)b * 4 + a] = (uint32_t)std::min(4294967295.0, std::floor(q * 4294967296.0));
         }
     }
@@ -803,14 +836,21 @@ static MscDev dev_view(const nlmc_msc *M) {
     d.thrbits = M->thrbits;
     d.thr_lane = reinterpret_cast<const uint4 *>(M->thr_lane);
     d.thr_nz = M->thr_nz;
+    // the tables of the odd-degree sites follow those of the even-degree ones
+    d.thrbits_odd = M->thrbits ? M->thrbits + (size_t)(M->k_steps + M->k_merged) * 3 * M->W : nullptr;
+    d.thr_lane_odd = M->thr_lane ? reinterpret_cast<const uint4 *>(M->thr_lane) + (size_t)M->W * 32 : nullptr;
+    d.thr_nz_odd = M->thr_nz ? M->thr_nz + M->W / 4 : nullptr;
     return d;
 }
 
 static MscThr thr_view(const nlmc_msc *M) {
     MscThr t;
     for (int b = 0; b < kMaxBeta; ++b)
-        for (int a = 0; a < 3; ++a)
-            t.t[b * 3 + a] = (!M->label_mode && b < M->n_beta) ? M->h_thr[(size_t)b * 4 + a + 1] : 0u;
+        for (int a = 0; a < 3; ++a) {
+            const bool on = !M->label_mode && b < M->n_beta;
+            t.t[b * 3 + a] = on ? M->h_thr[(size_t)b * 4 + a + 1] : 0u;
+            t.t_odd[b * 3 + a] = on ? M->h_thr_odd[(size_t)b * 4 + a + 1] : 0u;
+        }
     return t;
 }
 
@@ -828,17 +868,18 @@ static cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bl
 
 template <int kSteps>
 static void launch_colour(const nlmc_msc *M, const MscDev &d, const MscThr &t, int first, int cnt, uint32_t sweep_in_batch,
-                          bool pdl, bool trigger) {
+                          bool pdl, bool trigger, int odd) {
     constexpr int kT = NLMC_SWEEP_THREADS;
     const dim3 blocks((unsigned)((cnt + kT - 1) / kT), (unsigned)M->n_beta, (unsigned)d.qpb);
     const uint32_t *ctr = M->d_counters;
     const int flag = (pdl ? 1 : 0) | (trigger ? 2 : 0);  // bit 0: wait for the launch before, bit 1: let the next one start early
+    auto go = [&](auto kernel) { launch_maybe_pdl(kernel, blocks, dim3(kT), M->stream, pdl, d, t, first, cnt, ctr, sweep_in_batch, flag); };
     if (M->label_mode) {
-        if (M->k_merged) launch_maybe_pdl(msc_sweep_kernel<kSteps, true, 4>, blocks, dim3(kT), M->stream, pdl, d, t, first, cnt, ctr, sweep_in_batch, flag);
-        else launch_maybe_pdl(msc_sweep_kernel<kSteps, true, 0>, blocks, dim3(kT), M->stream, pdl, d, t, first, cnt, ctr, sweep_in_batch, flag);
+        if (M->k_merged) { if (odd) go(msc_sweep_kernel<kSteps, true, 4, true>); else go(msc_sweep_kernel<kSteps, true, 4, false>); }
+        else { if (odd) go(msc_sweep_kernel<kSteps, true, 0, true>); else go(msc_sweep_kernel<kSteps, true, 0, false>); }
     } else {
-        if (M->k_merged) launch_maybe_pdl(msc_sweep_kernel<kSteps, false, 4>, blocks, dim3(kT), M->stream, pdl, d, t, first, cnt, ctr, sweep_in_batch, flag);
-        else launch_maybe_pdl(msc_sweep_kernel<kSteps, false, 0>, blocks, dim3(kT), M->stream, pdl, d, t, first, cnt, ctr, sweep_in_batch, flag);
+        if (M->k_merged) { if (odd) go(msc_sweep_kernel<kSteps, false, 4, true>); else go(msc_sweep_kernel<kSteps, false, 4, false>); }
+        else { if (odd) go(msc_sweep_kernel<kSteps, false, 0, true>); else go(msc_sweep_kernel<kSteps, false, 0, false>); }
     }
 }
 
@@ -857,16 +898,16 @@ static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
     bool chained = false;  // the launch before this one in the stream is a sweep kernel of this batch
     for (int s = 0; s < n_sweeps; ++s) {
         const uint32_t off = bump_once ? (uint32_t)s : 0u;
-        for (int c = 0; c < M->n_colours; ++c) {
-            const int first = M->colour_ptr[c], cnt = M->colour_ptr[c + 1] - first;
+        for (const auto &cl : M->classes) {
+            const int first = cl.first, cnt = cl.count, odd = cl.odd;
             if (cnt == 0) continue;
             const bool p = pdl && chained;
             switch (M->k_steps) {
-                case 4: launch_colour<4>(M, d, t, first, cnt, off, p, pdl); break;
-                case 6: launch_colour<6>(M, d, t, first, cnt, off, p, pdl); break;
-                case 7: launch_colour<7>(M, d, t, first, cnt, off, p, pdl); break;
-                case 8: launch_colour<8>(M, d, t, first, cnt, off, p, pdl); break;
-                default: launch_colour<5>(M, d, t, first, cnt, off, p, pdl); break;
+                case 4: launch_colour<4>(M, d, t, first, cnt, off, p, pdl, odd); break;
+                case 6: launch_colour<6>(M, d, t, first, cnt, off, p, pdl, odd); break;
+                case 7: launch_colour<7>(M, d, t, first, cnt, off, p, pdl, odd); break;
+                case 8: launch_colour<8>(M, d, t, first, cnt, off, p, pdl, odd); break;
+                default: launch_colour<5>(M, d, t, first, cnt, off, p, pdl, odd); break;
             }
             chained = true;
         }
@@ -909,10 +950,13 @@ static int launch_energy(nlmc_msc *M) {
 static int launch_thrbits(nlmc_msc *M) {
     const int planes = M->k_steps + M->k_merged;
     const int items = std::max(planes * 3, 32) * M->W;
-    msc_thrbits_kernel<<<(items + 127) / 128, 128, 0, M->stream>>>(
-        planes, M->W, M->G, M->labels + (size_t)M->slot_begin * M->n_ladders, M->thr_total, M->thrbits,
-        reinterpret_cast<uint4 *>(M->thr_lane));
-    msc_thrnz_kernel<<<(M->W / 4 + 127) / 128, 128, 0, M->stream>>>(planes, M->W, M->thrbits, M->thr_nz);
+    for (int set = 0; set < (M->has_odd ? 2 : 1); ++set) {   // set 1: the tables of the odd-degree sites
+        uint32_t *tb = M->thrbits + (size_t)set * planes * 3 * M->W;
+        msc_thrbits_kernel<<<(items + 127) / 128, 128, 0, M->stream>>>(
+            planes, M->W, M->G, M->labels + (size_t)M->slot_begin * M->n_ladders, M->thr_total + (size_t)set * M->n_beta_total * 4,
+            tb, reinterpret_cast<uint4 *>(M->thr_lane) + (size_t)set * M->W * 32);
+        msc_thrnz_kernel<<<(M->W / 4 + 127) / 128, 128, 0, M->stream>>>(planes, M->W, tb, M->thr_nz + (size_t)set * (M->W / 4));
+    }
     NLMC_CUDA(cudaGetLastError());
     return NLMC_OK;
 }
@@ -925,7 +969,7 @@ static int launch_label_exchange(nlmc_msc *M, const double *E_full_dev, int num_
         msc_label_round_kernel<<<1, 1024, 0, M->stream>>>(
             M->n_beta_total, M->n_ladders, num_pairs, M->betas_total, E_full_dev, M->labels, M->slot_of, M->accepted,
             M->accepted_rounds, d.seed_lo, d.seed_hi, M->d_counters, M->ladder_offset, M->k_steps + M->k_merged, M->W, M->G,
-            M->slot_begin, M->thr_total, M->thrbits, reinterpret_cast<uint4 *>(M->thr_lane), M->thr_nz);
+            M->slot_begin, M->thr_total, M->thrbits, reinterpret_cast<uint4 *>(M->thr_lane), M->thr_nz, M->has_odd ? 2 : 1);
         NLMC_CUDA(cudaGetLastError());
         return NLMC_OK;
     }
@@ -968,7 +1012,7 @@ static int launch_swap(nlmc_msc *M, int num_pairs) {
 
 // sweeps [+ energies + exchange] as one graph launch; graphs are captured once per shape and cached
 static int run_round(nlmc_msc *M, int n_sweeps, int num_pairs, bool with_energy_swap) {
-    const long long launches = (long long)n_sweeps * (M->n_colours + 1);
+    const long long launches = (long long)n_sweeps * ((long long)M->classes.size() + 1);
     if (!M->use_graphs || launches < 4 || launches > 4096) {  // tiny or huge rounds: plain launches
         int rc = launch_sweeps(M, n_sweeps);
         if (!rc && with_energy_swap) rc = launch_energy(M);
@@ -1067,12 +1111,13 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
     NLMC_REQUIRE(n_ladders >= 1, "nlmc_msc_create: n_ladders must be >= 1");
     NLMC_REQUIRE(ladder_offset >= 0 && ladder_offset % 128 == 0, "nlmc_msc_create: ladder_offset must be a multiple of 128");
     const int n = I->n;
-    // eligibility: J in {-1,+1} off the diagonal, h = 0, even degrees <= 6 (site ranges on the host workers; the first
+    // eligibility: J in {-1,+1} off the diagonal, h = 0, degrees <= 6 (site ranges on the host workers; the first
     // offending site of each range is reported in site order)
     std::vector<int32_t> nbr((size_t)n * 6, -1);
     std::vector<uint32_t> meta((size_t)n, 0u);
+    std::vector<uint8_t> deg((size_t)n, 0);
     const int parts = n >= (1 << 16) ? nlmc::host_threads() : 1;
-    struct Issue { int kind = 0, i = -1, j = -1; double v = 0.0; };   // 1: h != 0, 2: bad value, 3: degree > 6, 4: odd degree
+    struct Issue { int kind = 0, i = -1, j = -1; double v = 0.0; };   // 1: h != 0, 2: bad value, 3: degree > 6
     std::vector<Issue> issues((size_t)parts);
     std::vector<long long> entries((size_t)parts, 0);
     nlmc::parallel_for(parts, [&](int t, int np) {
@@ -1091,9 +1136,11 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
                 if (v < 0) meta[(size_t)i] |= 1u << d;
                 ++d;
             }
-            if (!is.kind && (d & 1)) is = {4, i, d, 0.0};
             entries[(size_t)t] += d;
-            for (int e = d; e < 6; e += 2) meta[(size_t)i] |= 1u << e;  // padding pairs: even slot +1 (flip of a zeroed word), odd slot -1
+            deg[(size_t)i] = (uint8_t)d;
+            // padding: the even slots past the last neighbour count as +1 (flip of a zeroed word), the odd ones as -1 --
+            // neutral pairs, plus one slot at -1 when the degree is odd
+            for (int e = d + (d & 1); e < 6; e += 2) meta[(size_t)i] |= 1u << e;
         }
     });
     long long n_entries = 0;
@@ -1103,8 +1150,6 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
         if (is.kind == 2)
             set_error("nlmc_msc_create: the bit-packed path needs J in {-1,+1} with zero diagonal (J[%d,%d] = %g)", is.i, is.j, is.v);
         if (is.kind == 3) set_error("nlmc_msc_create: the bit-packed path supports degrees <= 6 (site %d)", is.i);
-        if (is.kind == 4)
-            set_error("nlmc_msc_create: the bit-packed path supports even degrees only (site %d has %d)", is.i, is.j);
         if (is.kind) return NLMC_ERR_UNSUPPORTED;
         n_entries += entries[(size_t)t];
     }
@@ -1138,13 +1183,28 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
         colour[(size_t)i] = c;
         n_colours = std::max(n_colours, c + 1);
     }
+    // sites sorted by (colour, parity of the degree): a launch class is uniform in both
     std::vector<int32_t> site_list((size_t)n);
     std::vector<int> colour_ptr((size_t)n_colours + 1, 0);
-    for (int i = 0; i < n; ++i) ++colour_ptr[(size_t)colour[(size_t)i] + 1];
-    for (int c = 0; c < n_colours; ++c) colour_ptr[(size_t)c + 1] += colour_ptr[(size_t)c];
+    std::vector<int> class_cnt((size_t)n_colours * 2, 0);
+    for (int i = 0; i < n; ++i) ++class_cnt[(size_t)colour[(size_t)i] * 2 + (deg[(size_t)i] & 1)];
+    std::vector<nlmc_msc::SiteClass> classes;
+    bool has_odd = false;
     {
-        std::vector<int> fill(colour_ptr.begin(), colour_ptr.end() - 1);
-        for (int i = 0; i < n; ++i) site_list[(size_t)fill[(size_t)colour[(size_t)i]]++] = i;
+        std::vector<int> fill((size_t)n_colours * 2, 0);
+        int at = 0;
+        for (int c = 0; c < n_colours; ++c) {
+            colour_ptr[(size_t)c] = at;
+            for (int par = 0; par < 2; ++par) {
+                fill[(size_t)c * 2 + par] = at;
+                const int cnt = class_cnt[(size_t)c * 2 + par];
+                if (cnt) classes.push_back({at, cnt, par});
+                if (cnt && par) has_odd = true;
+                at += cnt;
+            }
+        }
+        colour_ptr[(size_t)n_colours] = at;
+        for (int i = 0; i < n; ++i) site_list[(size_t)fill[(size_t)colour[(size_t)i] * 2 + (deg[(size_t)i] & 1)]++] = i;
     }
     NLMC_CUDA(cudaSetDevice(I->device));
     auto *M = new nlmc_msc();
@@ -1158,6 +1218,8 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
     M->n_colours = n_colours;
     M->n_bonds = n_entries / 2;
     M->colour_ptr = colour_ptr;
+    M->classes = classes;
+    M->has_odd = has_odd;
     M->seed = seed;
     M->h_betas.assign(betas, betas + n_beta);
     M->label_mode = betas_total ? 1 : 0;
@@ -1169,6 +1231,7 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
     if (const char *e = getenv("NLMC_MSC_GRAPHS")) M->use_graphs = atoi(e) != 0;
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(n_beta, betas);
     M->h_thr = thr;
+    M->h_thr_odd = nlmc::msc_thresholds(n_beta, betas, true);
     std::vector<int32_t> pos_of((size_t)n);
     for (int p = 0; p < n; ++p) pos_of[(size_t)site_list[(size_t)p]] = p;
     std::vector<int32_t> rec((size_t)n * 8, 0);  // records in site_list order: positions of the 6 neighbours, sign bits, site
@@ -1213,12 +1276,16 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
          put(M->thr, thr.data(), sizeof(uint32_t) * thr.size()) && put(M->betas, betas, sizeof(double) * (size_t)n_beta);
     std::vector<uint32_t> thr_t;
     if (ok && M->label_mode) {
+        // two sets of every threshold table: levels |f| = 2, 4, 6 (even degree), then |f| = 1, 3, 5 (odd degree)
         thr_t = nlmc::msc_thresholds(n_beta_total, betas_total);
+        const std::vector<uint32_t> thr_o = nlmc::msc_thresholds(n_beta_total, betas_total, true);
+        thr_t.insert(thr_t.end(), thr_o.begin(), thr_o.end());
         const size_t nl = (size_t)n_beta_total * M->n_ladders;
         ok = alloc(&M->labels, nl) && alloc(&M->slot_of, nl) && alloc(&M->thr_total, sizeof(uint32_t) * thr_t.size()) &&
              alloc(&M->betas_total, sizeof(double) * (size_t)n_beta_total) &&
-             alloc(&M->thrbits, sizeof(uint32_t) * (size_t)(M->k_steps + M->k_merged) * 3 * M->W) &&
-             alloc(&M->thr_lane, sizeof(uint32_t) * (size_t)M->W * 32 * 4) && alloc(&M->thr_nz, sizeof(uint32_t) * (size_t)(M->W / 4)) &&
+             alloc(&M->thrbits, sizeof(uint32_t) * 2 * (size_t)(M->k_steps + M->k_merged) * 3 * M->W) &&
+             alloc(&M->thr_lane, sizeof(uint32_t) * 2 * (size_t)M->W * 32 * 4) &&
+             alloc(&M->thr_nz, sizeof(uint32_t) * 2 * (size_t)(M->W / 4)) &&
              put(M->thr_total, thr_t.data(), sizeof(uint32_t) * thr_t.size()) &&
              put(M->betas_total, betas_total, sizeof(double) * (size_t)n_beta_total);
     }
@@ -1359,6 +1426,7 @@ int nlmc_msc_set_betas(nlmc_msc *M, const double *betas) {
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(M->n_beta, betas);
     M->h_betas.assign(betas, betas + M->n_beta);
     M->h_thr = thr;
+    M->h_thr_odd = nlmc::msc_thresholds(M->n_beta, betas, true);
     NLMC_CUDA(cudaStreamSynchronize(M->stream));
     nlmc::drop_graphs(M);  // the thresholds are a launch argument of the captured sweeps
     NLMC_CUDA(cudaMemcpy(M->thr, thr.data(), sizeof(uint32_t) * thr.size(), cudaMemcpyHostToDevice));

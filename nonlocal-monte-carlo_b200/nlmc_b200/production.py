@@ -32,18 +32,18 @@ def _require_msc(prob: host.Problem, betas, n_ladders: int, seed: int) -> "_lib.
         return _lib.Msc(prob.inst, betas, n_ladders, seed)
     except _lib.NlmcError as e:
         raise _NotBitPackable(
-            "mode='production' currently covers +-J instances with h = 0 and even degrees <= 6 "
-            f"(2D/3D lattices); use mode='replay' for this instance ({e})") from e
+            "the bit-packed engine covers +-J instances with h = 0 and degrees <= 6 (2D/3D lattices, periodic or open, "
+            f"Chimera-like graphs) ({e})") from e
 
 
 def _msc_eligible(prob: host.Problem) -> bool:
-    """+-J, h = 0, even degrees <= 6: the bit-packed path applies (csrc/nlmc_msc.cu)."""
+    """+-J, h = 0, degrees <= 6: the bit-packed path applies (csrc/nlmc_msc.cu)."""
     cached = getattr(prob, "_msc_eligible", None)
     if cached is None:
         cached = False
         if prob.is_integer and len(prob.val) and not np.any(prob.h):
             deg = np.diff(prob.rp)
-            if deg.max() <= 6 and not np.any(deg & 1) and prob.val.max() == 1.0 and prob.val.min() == -1.0:
+            if deg.max() <= 6 and prob.val.max() == 1.0 and prob.val.min() == -1.0:
                 import scipy.sparse as sp
                 diag = sp.csr_matrix((prob.val, prob.ci, prob.rp), shape=(prob.n, prob.n), copy=False).diagonal()
                 cached = bool(np.all(prob.val * prob.val == 1.0)) and not np.any(diag)

@@ -459,3 +459,129 @@ def test_block_fetch_widens_in_the_requested_order(nl):
         nl.lib.fetch_widen_blocks(d.data_ptr(), out2, n_blocks, elems, dst_block=perm)
         torch.cuda.synchronize()
         assert np.array_equal(out2[perm], src.astype(np.float64))
+
+
+def graph_from_edges(n, edges, seed):
+    rs = np.random.RandomState(seed)
+    rows, cols, vals = [], [], []
+    for (i, j) in edges:
+        v = rs.choice([-1.0, 1.0])
+        rows += [i, j]
+        cols += [j, i]
+        vals += [v, v]
+    return sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr(), np.zeros(n)
+
+
+def open_lattice_2d(Lx, Ly, seed):
+    """Open boundaries: corner sites have degree 2, edge sites 3, inner sites 4."""
+    edges = []
+    for y in range(Ly):
+        for x in range(Lx):
+            i = x + Lx * y
+            if x + 1 < Lx:
+                edges.append((i, i + 1))
+            if y + 1 < Ly:
+                edges.append((i, i + Lx))
+    return graph_from_edges(Lx * Ly, edges, seed)
+
+
+def chimera_cell_pair(seed):
+    """Two Chimera unit cells (K4,4 each) joined by four couplers: degrees 4 and 5; a path of three extra spins hangs off
+    (degrees 1, 2 and a degree-6 hub is made by three more pendant spins)."""
+    edges = [(a, 4 + b) for a in range(4) for b in range(4)]                    # cell 0: 0..3 | 4..7
+    edges += [(8 + a, 12 + b) for a in range(4) for b in range(4)]              # cell 1: 8..11 | 12..15
+    edges += [(4 + b, 12 + b) for b in range(4)]                                # inter-cell couplers: degree 5
+    return graph_from_edges(16, edges, seed)
+
+
+@pytest.mark.parametrize("case", ["open_4x4", "open_3x5", "chimera", "star"])
+def test_exact_boltzmann_with_odd_degrees(nl, case):
+    """Sites of odd degree (open boundaries, Chimera couplers, pendant spins): fields f = 2c - deg are odd there, with
+    their own threshold levels |f| = 1, 3, 5; sites of even and odd degree are separate launch classes.  <E>(beta) must
+    equal full enumeration, energies must be exact, in the scalar-threshold and the beta-label form."""
+    from oracle import oracle as O
+    if case == "open_4x4":
+        A, h = open_lattice_2d(4, 4, 3)
+    elif case == "open_3x5":
+        A, h = open_lattice_2d(3, 5, 4)
+    elif case == "chimera":
+        A, h = chimera_cell_pair(5)
+    else:  # a hub of degree 5 with pendant spins (degree 1) and a tail (degrees 2, 1)
+        A, h = graph_from_edges(8, [(0, 1), (0, 2), (0, 3), (0, 4), (0, 5), (5, 6), (6, 7)], 6)
+    deg = np.diff(A.indptr)
+    assert np.any(deg & 1)
+    betas = np.array([0.1, 0.45, 0.9, 1.7])
+    exact = exact_mean_energy(A, betas)
+    prob = nl.host.Problem(A, h)
+    csr = O.Csr(A)
+    for labelled in (False, True):
+        msc = nl.lib.Msc(prob.inst, betas, 1024, seed=31 + labelled, labelled=labelled)
+        E0 = msc.energies()
+        for b, lad in ((0, 0), (1, 33), (3, 1023)):
+            assert E0[b, lad] == O.energy(csr, h, msc.get_spins(b, lad))[0]
+        for _ in range(40):
+            msc.round(5, 2)
+        samples = []
+        for _ in range(60):
+            msc.round(4, 2)
+            E = msc.energies()
+            if labelled:
+                lab = msc.labels().astype(np.int64)
+                Eb = np.empty_like(E)
+                np.put_along_axis(Eb, lab, E, axis=0)
+                E = Eb
+            samples.append(E)
+        S = np.array(samples)
+        for b in range(len(betas)):
+            per_ladder = S[:, b, :].mean(axis=0)
+            mean, err = per_ladder.mean(), per_ladder.std(ddof=1) / np.sqrt(per_ladder.size)
+            assert abs(mean - exact[b][0]) <= 3.0 * err + 1e-9, (case, labelled, betas[b], mean, exact[b][0], err)
+        msc.close()
+
+
+def test_conditional_distribution_on_an_open_lattice(nl):
+    """Single-sweep conditional law on a 3D open-boundary lattice (degrees 3..6): colour-0 sites of every degree are drawn
+    from P(+1) = 1/(1 + exp(-2 beta f)) with f from the unchanged colour-1 neighbours."""
+    L = 6
+    edges = []
+    for z in range(L):
+        for y in range(L):
+            for x in range(L):
+                i = x + L * (y + L * z)
+                if x + 1 < L:
+                    edges.append((i, i + 1))
+                if y + 1 < L:
+                    edges.append((i, i + L))
+                if z + 1 < L:
+                    edges.append((i, i + L * L))
+    A, h = graph_from_edges(L ** 3, edges, 9)
+    n = L ** 3
+    betas = np.array([0.3, 0.8])
+    prob = nl.host.Problem(A, h)
+    msc = nl.lib.Msc(prob.inst, betas, 2048, seed=5)
+    assert msc.n_colours == 2
+    rs = np.random.RandomState(4)
+    s0 = rs.choice([-1, 1], size=n).astype(np.int8)
+    P = np.where(s0[:, None] > 0, np.uint32(0xffffffff), np.uint32(0)) * np.ones((1, msc.n_words), dtype=np.uint32)
+    msc.set_packed(np.ascontiguousarray(P.astype(np.uint32)))
+    msc.sweep(1)
+    out = msc.get_packed()
+    idx = np.arange(n)
+    colour0 = ((idx % L) + (idx // L) % L + idx // (L * L)) % 2 == 0
+    f0 = np.asarray(A @ s0.astype(float))
+    G = msc.n_ladders // 32
+    seen = set()
+    for b, beta in enumerate(betas):
+        ups = np.zeros(n)
+        for g in range(G):
+            ups += np.array([bin(int(v)).count("1") for v in out[:, b * G + g]])
+        for f in range(-6, 7):
+            sel = colour0 & (f0 == f)
+            trials = sel.sum() * msc.n_ladders
+            if trials == 0:
+                continue
+            seen.add(f)
+            p = 1.0 / (1.0 + np.exp(-2 * beta * f))
+            sigma = np.sqrt(trials * p * (1 - p))
+            assert abs(ups[sel].sum() - trials * p) <= 3.0 * sigma + 1, (beta, f, ups[sel].sum(), trials * p, sigma)
+    assert {-5, -3, -1, 1, 3, 5} & seen and {-4, -2, 0, 2, 4} & seen
