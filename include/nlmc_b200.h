@@ -168,9 +168,11 @@ int nlmc_icm_clusters(nlmc_instance *inst, int n_pairs, const int8_t *s1 /*[n_pa
                       int32_t *out_n_clusters /*[n_pairs]*/);
 
 /* ---- K2 / K4' / K6: production path (bit-packed multi-spin coding) ------------------------------
- * For +-J instances with h = 0 and even degrees <= 6 (the 3D EA configs).  n_ladders independent NPT
- * runs ("ladders", one replica per beta each) are packed 32 to a word, all bits of a word at the same
- * beta; n_ladders is rounded up to a multiple of 128 (nlmc_msc_info reports the padded count).
+ * For +-J instances with h = 0 and degrees <= 6 (periodic or open lattices, Chimera-like graphs; the 3D EA
+ * configs).  n_ladders independent NPT runs ("ladders", one replica per beta each) are packed 32 to a word, all bits
+ * of a word at the same beta; n_ladders is rounded up to a multiple of 128 (nlmc_msc_info reports the padded count).
+ * Packed states cross this boundary site-major, packed[site][n_words] (word = slot * G + ladder group); on the device
+ * they are kept quad-major in colour order.
  *
  *   nlmc_msc_sweep      heat-bath sweeps, graph-coloured parallel updates, Philox4x32-10 randoms.
  *                       Replaces MCMC (NMC/nmc.py:28-91 and copies) for every replica of every ladder;

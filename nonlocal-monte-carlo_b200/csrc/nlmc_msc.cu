@@ -1,23 +1,22 @@
 // nlmc_msc.cu -- K2 production path: multi-spin-coded heat-bath sweeps, bit-sliced energies (K4') and
-// replica-exchange swaps (K6) for +-J instances with h = 0 and even degrees <= 6 (2D/3D lattices,
-// the EA configs C2/C4/C5 of BASELINE.json).
+// replica-exchange swaps (K6) for +-J instances with h = 0 and degrees <= 6 (periodic and open 2D/3D lattices,
+// Chimera-like graphs; the EA configs C2/C4/C5 of BASELINE.json).
 //
 // Layout.  A "ladder" is one NPT run (one replica per inverse temperature).  32 independent ladders
-// share a 32-bit word, one bit each (bit = 1 <=> spin +1); all bits of a word sit at the SAME beta,
-// so the heat-bath thresholds are uniform across a word.  S[site][w], w = b*G + g (beta index b,
-// ladder group g, G = n_ladders/32, n_ladders a multiple of 128 so that a thread's four consecutive
-// words share one beta).  For C5 (L=64, 32 betas x 128 ladders = 4096 replicas) a site row is
-// 128 words = 512 B: one warp owns one site, each lane one uint4 (LDG.128, fully coalesced), and the
-// whole state is 134 MB.
+// share a 32-bit word, one bit each (bit = 1 <=> spin +1); word w = b*G + g (slot b, ladder group g,
+// G = n_ladders/32, n_ladders a multiple of 128 so that four consecutive words -- a quad -- share one slot).
+// The state is stored quad-major and in colour order, uint4 S[W/4][n] indexed by (quad, position of the site in
+// the colour-sorted site list): a warp of the sweep kernel owns 32 consecutive positions of one quad (see MscDev).
+// For C5 (L=64, 32 betas x 128 ladders = 4096 replicas) the whole state is 134 MB.  The C ABI exchanges the
+// packed state site-major, packed[site][W]; the transposition runs on the device.
 //
 // Update rule (same distribution as the reference's sign(tanh(beta*x) - 2u + 1), NMC/nmc.py:87):
-// with c = number of neighbours with J_ij*s_j = +1 and field f = 2c - 6,
+// with c = number of neighbours with J_ij*s_j = +1 and field f = 2c - 6 (even degree) or 2c - 5 (odd degree),
 //     s_i <- [f > 0] XOR g,   g ~ Bernoulli(q(|f|)),  q(0) = 1/2,  q(a) = 1/(1 + exp(2*beta*a)).
 // c is formed for 32 ladders at once with bit-sliced full adders (LOP3), and g is drawn for 32
-// ladders at once by a bit-serial comparison of a uniform with the 32-bit threshold of each lane's
-// |f| level, most significant bit first; lanes drop out as soon as their comparison is decided, so
-// on average ~2 random bits per attempt are consumed.  Random words are Philox4x32-10 keyed by
-// (seed; site, word-quad, sweep, bit step): results do not depend on the launch geometry or on how
+// ladders at once by a bit-serial comparison of a uniform with the 32-bit threshold of each ladder's
+// |f| level, most significant bit first (msc_sweep_kernel).  Random words are Philox4x32-10 keyed by
+// (seed; site, (slot, ladder quad), sweep, bit step): results do not depend on the launch geometry or on how
 // ladders are sharded over GPUs.  Sites are updated colour by colour (checkerboard on bipartite
 // lattices, greedy colouring otherwise), all sites of a colour in parallel.
 #include <algorithm>
@@ -244,7 +243,7 @@ msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const
 #pragma unroll
     for (int d = 0; d < 6; ++d) {
         // x <- (x & keep) ^ flip: a neighbour keeps its bits and is inverted when J < 0; padding comes in (+1, -1) pairs
-        // (even degrees only; the record carries flip = 1 for the even padding slots).  One three-input logic operation
+        // (plus one slot at -1 when the degree is odd; the record carries flip = 1 for the even padding slots).  One three-input logic operation
         // per word; the masks are formed with shifts so that they stay in registers (as selects on predicates the
         // compiler spent two instructions per word).
         const uint32_t keep = sign_mask(~nb[d]);
