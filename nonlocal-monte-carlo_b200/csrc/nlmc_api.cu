@@ -119,7 +119,7 @@ int nlmc_instance_create(int n, const int32_t *row_ptr, const int32_t *col, cons
     }
     // one pass over the entries on the host workers: range check, integer / small-integer flags, and the compact
     // int8 / uint16 copies the shared-memory replay kernel reads (integer J only)
-    const int parts = nnz >= (1 << 18) ? nlmc::host_threads() : 1;
+    const int parts = nnz >= (1 << 18) ? nlmc::host_threads_shared() : 1;
     std::vector<int> bad((size_t)parts, -1);
     std::vector<char> not_int((size_t)parts, 0), not_small((size_t)parts, 0);
     std::vector<int8_t> v8((size_t)nnz);

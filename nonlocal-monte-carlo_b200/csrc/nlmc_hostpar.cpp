@@ -8,6 +8,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -138,6 +139,18 @@ int clamp_threads(int threads) {
 }  // namespace
 
 int host_threads() { return pool().size(); }
+
+// Threads for work that EVERY rank of a multi-process job does at the same time (instance checks at handle creation):
+// the pool's width divided by the number of ranks on this host (LOCAL_WORLD_SIZE, as torchrun sets it), so that eight
+// ranks do not put 8 x 16 workers on 16 cores.  Work only one rank does (building M) uses the full pool.
+int host_threads_shared() {
+    static const int n = [] {
+        int local = 1;
+        if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) local = std::max(1, std::atoi(e));
+        return std::max(1, pool().size() / local);
+    }();
+    return n;
+}
 
 void parallel_for(int parts, const std::function<void(int, int)> &fn) {
     parts = std::max(1, std::min(parts, pool().size()));

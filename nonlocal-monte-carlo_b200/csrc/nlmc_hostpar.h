@@ -6,6 +6,7 @@
 namespace nlmc {
 
 int host_threads();
+int host_threads_shared();  // per-rank share of the pool in a multi-process job (LOCAL_WORLD_SIZE)
 // fn(part, parts) on min(parts, host_threads()) persistent workers; returns when every part is done
 void parallel_for(int parts, const std::function<void(int, int)> &fn);
 // out[i] = (double)in[i] on `threads` workers (0 = all), non-temporal stores where the CPU has AVX2

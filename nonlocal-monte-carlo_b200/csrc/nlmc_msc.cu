@@ -23,6 +23,8 @@
 #include <cmath>
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "nlmc_common.cuh"
 #include "nlmc_hostpar.h"
 
@@ -75,6 +77,8 @@ struct nlmc_msc {
     struct RoundGraph { int n_sweeps, pairs; bool with_energy_swap; cudaGraphExec_t exec; };
     std::vector<RoundGraph> graphs;  // whole rounds captured once per (n_sweeps, pairs) and replayed
     bool use_graphs = true;
+    bool batch_default = false;  // sweeps of a batch as one cooperative launch (short rows)
+    int batch_ctas = 0;          // co-resident CTAs of the batch kernel (0: not asked yet, -1: unavailable)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<double> h_betas;
@@ -207,7 +211,7 @@ __device__ __forceinline__ uint32_t comp(const uint4 &v, int k) { return k == 0 
 // there -- and kMerged further comparison steps run on that word with one Philox call; the results are scattered back.
 // A lane that lost its column to another word simply waits for the straggler loop.  Every random bit is still used by
 // at most one lane, chosen by the past only, so the draw stays exact.
-template <int kSteps, bool kPerBit, int kMerged, bool kOdd>
+template <int kSteps, bool kPerBit, int kMerged, bool kOdd, bool kClamp = false>
 #ifndef NLMC_PERBIT_CTAS
 #define NLMC_PERBIT_CTAS 4
 #endif
@@ -217,15 +221,15 @@ template <int kSteps, bool kPerBit, int kMerged, bool kOdd>
 #ifndef NLMC_SWEEP_THREADS
 #define NLMC_SWEEP_THREADS 256
 #endif
-__global__ void __launch_bounds__(NLMC_SWEEP_THREADS, (kPerBit ? NLMC_PERBIT_CTAS : NLMC_SCALAR_CTAS) * (256 / NLMC_SWEEP_THREADS))
-msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const uint32_t *__restrict__ counters,
-                 uint32_t sweep_in_batch, int pdl) {
+__device__ __forceinline__ void msc_sweep_site(const MscDev &a, const MscThr &thr, int first, int n_sites, int idx, int b,
+                                               int qin, const uint32_t *__restrict__ counters, uint32_t sweep_in_batch,
+                                               int pdl) {
     constexpr bool odd = kOdd;  // the launch holds sites of odd degree (levels |f| = 1, 3, 5)
-    const int idx = (int)(blockIdx.x * (unsigned)NLMC_SWEEP_THREADS + threadIdx.x);  // position within the colour
-    // programmatic dependent launch (pdl): the next colour's grid may be scheduled while this one drains
-    if (pdl & 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (idx >= n_sites) return;
-    const int b = (int)blockIdx.y, qin = (int)blockIdx.z;     // slot and quad within the slot: uniform over the CTA
+    // kClamp (the persistent batch kernel): a thread past the end recomputes the last site and skips the store, so the
+    // warp stays converged inside the tile loop and the compiler keeps the uniform values on the uniform datapath
+    const bool valid = idx < n_sites;
+    if (kClamp) idx = min(idx, n_sites - 1);
+    else if (!valid) return;
     const int qd = b * a.qpb + qin;
     const int pos = first + idx;
     const int4 r0 = __ldg(a.rec + (size_t)pos * 2), r1 = __ldg(a.rec + (size_t)pos * 2 + 1);
@@ -416,7 +420,55 @@ msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const
     out.y = sgn[1] ^ res[1];
     out.z = sgn[2] ^ res[2];
     out.w = sgn[3] ^ res[3];
-    Sq[pos] = out;
+    if (!kClamp || valid) Sq[pos] = out;
+}
+
+template <int kSteps, bool kPerBit, int kMerged, bool kOdd>
+__global__ void __launch_bounds__(NLMC_SWEEP_THREADS, (kPerBit ? NLMC_PERBIT_CTAS : NLMC_SCALAR_CTAS) * (256 / NLMC_SWEEP_THREADS))
+msc_sweep_kernel(const MscDev a, const MscThr thr, int first, int n_sites, const uint32_t *__restrict__ counters,
+                 uint32_t sweep_in_batch, int pdl) {
+    // programmatic dependent launch (pdl): the next colour's grid may be scheduled while this one drains
+    if (pdl & 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int idx = (int)(blockIdx.x * (unsigned)NLMC_SWEEP_THREADS + threadIdx.x);  // position within the colour
+    // slot and quad within the slot come from the block index: uniform over the CTA
+    msc_sweep_site<kSteps, kPerBit, kMerged, kOdd>(a, thr, first, n_sites, idx, (int)blockIdx.y, (int)blockIdx.z, counters,
+                                                   sweep_in_batch, pdl);
+}
+
+// A whole batch of sweeps in ONE cooperative launch (aimed at blocks of a ladder sharded over GPUs: a colour launch of a
+// 4-slot block is 20 us of work plus launch gap and drain).  The grid is persistent -- as many CTAs as are co-resident --,
+// a CTA takes the tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of a launch class (tile = 256 positions of one quad),
+// and a grid barrier (1.5 us on a B200, tools/micro/gridsync.cu) stands where the launch boundary was.  MEASURED SLOWER
+// than the launch chain (0.41 vs 0.29 ms per C5 sweep, 0.071 vs 0.044 ms on a 4-slot block): a quarter of the warp time
+// waits at the barrier (static tiles, SMs of unequal speed) and the compiler leaves the uniform datapath inside the tile
+// loop (+21 % instructions) -- profiles/r2d_batch_kernel_summary.md.  Off unless NLMC_MSC_BATCH=1; trajectories are
+// identical to the launch chain's.
+constexpr int kMaxClasses = 16;
+struct MscClasses { int n; int first[kMaxClasses], count[kMaxClasses], odd[kMaxClasses]; };
+
+#ifndef NLMC_BATCH_CTAS
+#define NLMC_BATCH_CTAS 4
+#endif
+template <int kSteps, bool kPerBit, int kMerged>
+__global__ void __launch_bounds__(NLMC_SWEEP_THREADS, NLMC_BATCH_CTAS * (256 / NLMC_SWEEP_THREADS))
+msc_sweep_batch_kernel(const MscDev a, const MscThr thr, const MscClasses cl, int n_sweeps, uint32_t *counters) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int s = 0; s < n_sweeps; ++s) {
+        for (int c = 0; c < cl.n; ++c) {
+            const int first = cl.first[c], cnt = cl.count[c];
+            const int nx = (cnt + NLMC_SWEEP_THREADS - 1) / NLMC_SWEEP_THREADS;
+            const int n_tiles = nx * a.n_beta * a.qpb;
+            for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
+                const int xb = t % nx, rest = t / nx;
+                const int b = rest % a.n_beta, qin = rest / a.n_beta;
+                const int idx = xb * NLMC_SWEEP_THREADS + (int)threadIdx.x;
+                if (cl.odd[c]) msc_sweep_site<kSteps, kPerBit, kMerged, true, true>(a, thr, first, cnt, idx, b, qin, counters, (uint32_t)s, 0);
+                else msc_sweep_site<kSteps, kPerBit, kMerged, false, true>(a, thr, first, cnt, idx, b, qin, counters, (uint32_t)s, 0);
+            }
+            grid.sync();
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[0] += (uint32_t)n_sweeps;   // after the last barrier: nobody reads it any more
 }
 
 // Uniform random initial spins (the production counterpart of sign(2*rand-1), NPT/npt.py:612).
@@ -882,6 +934,43 @@ static void launch_colour(const nlmc_msc *M, const MscDev &d, const MscThr &t, i
     }
 }
 
+// NLMC_MSC_BATCH = 1 selects the cooperative batch kernel (measured slower, see msc_sweep_batch_kernel; default off).
+static bool batch_mode(const nlmc_msc *M) {
+    if (M->k_steps != 5 || M->k_merged != 4) return false;
+    if ((int)M->classes.size() > kMaxClasses) return false;
+    if (const char *e = getenv("NLMC_MSC_BATCH")) return atoi(e) != 0;
+    return M->batch_default;
+}
+
+static int launch_sweep_batch(nlmc_msc *M, const MscDev &d, const MscThr &t, int n_sweeps) {
+    MscClasses cl;
+    cl.n = 0;
+    for (const auto &c : M->classes) {
+        if (c.count == 0) continue;
+        cl.first[cl.n] = c.first; cl.count[cl.n] = c.count; cl.odd[cl.n] = c.odd; ++cl.n;
+    }
+    if (cl.n == 0) return NLMC_OK;
+    void *kernel = M->label_mode ? (void *)msc_sweep_batch_kernel<5, true, 4> : (void *)msc_sweep_batch_kernel<5, false, 4>;
+    if (M->batch_ctas == 0) {   // co-resident CTAs of this kernel on this device, once per handle
+        int per_sm = 0, sms = 0, dev = 0;
+        NLMC_CUDA(cudaGetDevice(&dev));
+        NLMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        NLMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NLMC_SWEEP_THREADS, 0));
+        M->batch_ctas = per_sm * sms;
+        if (const char *e = getenv("NLMC_MSC_BATCH_CTAS")) M->batch_ctas = std::max(1, std::min(M->batch_ctas, atoi(e)));
+        if (M->batch_ctas <= 0) M->batch_ctas = -1;
+    }
+    if (M->batch_ctas < 0) return NLMC_ERR_STATE;
+    long long max_tiles = 0;
+    for (int c = 0; c < cl.n; ++c)
+        max_tiles = std::max(max_tiles, (long long)((cl.count[c] + NLMC_SWEEP_THREADS - 1) / NLMC_SWEEP_THREADS) * M->n_beta * d.qpb);
+    const unsigned grid = (unsigned)std::max(1LL, std::min((long long)M->batch_ctas, max_tiles));
+    uint32_t *ctr = M->d_counters;
+    void *args[] = {(void *)&d, (void *)&t, (void *)&cl, (void *)&n_sweeps, (void *)&ctr};
+    NLMC_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(NLMC_SWEEP_THREADS), args, 0, M->stream));
+    return NLMC_OK;
+}
+
 static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
     const MscDev d = dev_view(M);
     const MscThr t = thr_view(M);
@@ -893,6 +982,11 @@ static int launch_sweeps(nlmc_msc *M, int n_sweeps) {
     // -2.5 % on whole C5 rounds (it implies the single bump), so it is off by default.
     const char *e_pdl = getenv("NLMC_MSC_PDL");
     const bool pdl = e_pdl ? atoi(e_pdl) != 0 : false;
+    // A batch of sweeps as ONE cooperative launch (msc_sweep_batch_kernel): the default kernel shape only, on request
+    if (n_sweeps >= 1 && !pdl && batch_mode(M)) {
+        int rc = launch_sweep_batch(M, d, t, n_sweeps);
+        if (rc != NLMC_ERR_STATE) return rc;   // NLMC_ERR_STATE: the grid does not fit / too many classes -> launch chain
+    }
     const bool bump_once = pdl || (M->W < 128 ? !getenv("NLMC_MSC_BUMP_EACH") : getenv("NLMC_MSC_BUMP_ONCE") != nullptr);
     bool chained = false;  // the launch before this one in the stream is a sweep kernel of this batch
     for (int s = 0; s < n_sweeps; ++s) {
@@ -1115,7 +1209,7 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
     std::vector<int32_t> nbr((size_t)n * 6, -1);
     std::vector<uint32_t> meta((size_t)n, 0u);
     std::vector<uint8_t> deg((size_t)n, 0);
-    const int parts = n >= (1 << 16) ? nlmc::host_threads() : 1;
+    const int parts = n >= (1 << 16) ? nlmc::host_threads_shared() : 1;
     struct Issue { int kind = 0, i = -1, j = -1; double v = 0.0; };   // 1: h != 0, 2: bad value, 3: degree > 6
     std::vector<Issue> issues((size_t)parts);
     std::vector<long long> entries((size_t)parts, 0);

@@ -585,3 +585,28 @@ def test_conditional_distribution_on_an_open_lattice(nl):
             sigma = np.sqrt(trials * p * (1 - p))
             assert abs(ups[sel].sum() - trials * p) <= 3.0 * sigma + 1, (beta, f, ups[sel].sum(), trials * p, sigma)
     assert {-5, -3, -1, 1, 3, 5} & seen and {-4, -2, 0, 2, 4} & seen
+
+
+@pytest.mark.parametrize("labelled", [False, True])
+@pytest.mark.parametrize("case", ["periodic", "open"])
+def test_cooperative_batch_kernel_equals_launch_chain(nl, monkeypatch, labelled, case):
+    """NLMC_MSC_BATCH=1 runs a batch of sweeps as ONE cooperative launch (persistent CTAs, a grid barrier where the launch
+    boundary was): same random streams, so the packed state after the batch must equal the launch chain's bit for bit --
+    with a ragged last tile (n per colour not a multiple of 256) and with launch classes of both degree parities."""
+    from oracle import oracle as O
+    if case == "periodic":
+        A, h = O.ea3d_pm_j(10, 3)        # 500 sites per colour: one full tile + a ragged one
+    else:
+        A, h = open_lattice_2d(37, 19, 2)  # degrees 2, 3, 4: even and odd classes in both colours
+    prob = nl.host.Problem(A, h)
+    betas = np.linspace(0.3, 1.6, 6)
+    kw = dict(labelled=True, slot_begin=1, slot_count=4) if labelled else {}
+    out = []
+    for batch in ("0", "1"):
+        monkeypatch.setenv("NLMC_MSC_BATCH", batch)
+        m = nl.lib.Msc(prob.inst, betas, 256, seed=11, **kw)
+        m.sweep(5)
+        m.sweep(1)
+        out.append(m.get_packed())
+        m.close()
+    assert np.array_equal(out[0], out[1])
