@@ -303,6 +303,7 @@ struct nlmc_dense {
     std::vector<cudaEvent_t> fork_ev;  // one event per fork / join point of the captured sweep
     std::vector<cudaStream_t> chain_streams;  // streams of the independent replica chains of the sweep (beyond `stream`)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long *fused_prof = nullptr;   // NLMC_DENSE_FUSED_PROF: phase timestamps of the last fused sweep (printed at destroy)
 };
 
 namespace nlmc {
@@ -404,42 +405,16 @@ __host__ __device__ constexpr size_t update_smem_bytes(int rep_per_cta) {
     return sizeof(float) * ((size_t)kBlk * kBlk + 3 * (size_t)rep_per_cta * kFldStride);
 }
 
-__global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(int n, int n_pad, int R_pad, int c0, const float *__restrict__ Ht,
-                                                                               const float *__restrict__ Jf, const float *__restrict__ hf,
-                                                                               const float *__restrict__ beta, uint16_t *S,
-                                                                               uint32_t seed_lo, uint32_t seed_hi,
-                                                                               const uint32_t *__restrict__ sweep_ptr, float *Ht_zero,
-                                                                               const uint8_t *__restrict__ modes, float temp_x, int pdl,
-                                                                               int r_base, int r_end) {
-    extern __shared__ __align__(16) uint8_t dsm[];
-    const uint32_t sweep = *sweep_ptr;   // bumped by the kernel at the end of the previous sweep, several launches back
-    const int rpc = blockDim.x >> 5;                                   // replicas (warps) per CTA
-    float *Jt = reinterpret_cast<float *>(dsm);                        // [kBlk j][kBlk k] = J[c0+k][c0+j] (transposed)
-    float *fld = Jt + (size_t)kBlk * kBlk;                             // [rpc][kFldStride]  running fields
-    float *thr = fld + (size_t)rpc * kFldStride;                       // [rpc][kFldStride]  thresholds
-    float *spn = thr + (size_t)rpc * kFldStride;                       // [rpc][kFldStride]  spins as floats
-    const int tid = threadIdx.x;
-    const int rep = tid >> 5, lane = tid & 31;   // replica within the CTA = warp
-    const int r = r_base + blockIdx.x * rpc + rep;   // the launch covers the replicas [r_base, r_end)
-    const int k_end = min(kBlk, n - c0);
-    // stage J_bb transposed, Jt[j][k] = J[c0+k][c0+j], from the transposed copy of J kept in global memory
-    // (JfT[a][b] = J[b][a]): asynchronous 16-byte copies, all 64 KB in flight while the thresholds are computed
-    for (int i = tid; i < kBlk * kBlk / 4; i += blockDim.x) {
-        const int j = i / (kBlk / 4), k4 = i % (kBlk / 4);
-        const uint32_t dst = smem_u32(reinterpret_cast<float4 *>(Jt) + i);
-        const float *src = Jf + (size_t)(c0 + j) * n_pad + c0 + k4 * 4;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    float *frow = fld + rep * kFldStride;
-    float *trow = thr + rep * kFldStride;
-    float *srow = spn + rep * kFldStride;
-    const bool active = r < r_end;
-    if (active) {
+// Thresholds theta_k = logit(u_k) / (2 beta) and old spins of the block's 128 sites for one replica (one warp): lane ->
+// sites 4*lane .. 4*lane+3, one Philox call and four logits per lane; NMC phase modes folded in.
+__device__ __forceinline__ void block_thresholds(const uint16_t *S, const uint8_t *__restrict__ modes, int n_pad, int r, int c0,
+                                                 int k_end, int lane, float beta_r, uint32_t seed_lo, uint32_t seed_hi,
+                                                 uint32_t sweep, float temp_x, float *trow, float *srow) {
+    {
         // spins and thresholds of the lane's four sites 4*lane .. 4*lane+3
         const uint2 sv = *reinterpret_cast<const uint2 *>(S + (size_t)r * n_pad + c0 + 4 * lane);   // 256 B per warp
         const uint16_t s16[4] = {(uint16_t)(sv.x & 0xffffu), (uint16_t)(sv.x >> 16), (uint16_t)(sv.y & 0xffffu), (uint16_t)(sv.y >> 16)};
-        const float inv2b = 0.5f / beta[r];
+        const float inv2b = 0.5f / beta_r;
         const PhiloxD rng{seed_lo, seed_hi ^ 0x44454e53u};
         // the stream of round 1: call (r, c0 + 8*(lane/2), sweep, lane & 1) serves the four sites 4*lane .. 4*lane+3
         const uint4 rv = rng((uint32_t)r, (uint32_t)(c0 + 8 * (lane >> 1)), sweep, (uint32_t)(lane & 1));
@@ -465,27 +440,10 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
         *reinterpret_cast<float4 *>(trow + 4 * lane) = make_float4(th[0], th[1], th[2], th[3]);
         *reinterpret_cast<float4 *>(srow + 4 * lane) = make_float4(so[0], so[1], so[2], so[3]);
     }
-    if (pdl) {
-        // everything above (coupling block, spins of this block, thresholds) is independent of the field GEMM that runs
-        // just before this kernel: with programmatic stream serialization it overlapped that GEMM.  The fields are not.
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (pdl > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    }
-    if (active) {
-        // fields of the replica: lane -> sites lane + 32 q (the warps of a CTA read the same 32-byte sectors of Ht)
-        float hv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) hv[q] = Ht[(size_t)(c0 + lane + 32 * q) * R_pad + r] + hf[c0 + lane + 32 * q];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) frow[lane + 32 * q] = hv[q];
-        // the next block's split-K GEMM accumulates with atomics: clear its field rows for this replica
-        if (Ht_zero != nullptr)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) Ht_zero[(size_t)(lane + 32 * q) * R_pad + r] = 0.f;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    if (!active) return;
+}
+
+// The sequential chain over the 128 sites of a block for one replica (one warp), in sub-blocks of 8 (see the kernel below).
+__device__ __forceinline__ void block_update_chain(const float *Jt, float *frow, float *srow, const float *trow, int lane) {
 #pragma unroll
     for (int sb = 0; sb < kBlk / 8; ++sb) {
         const int base = sb * 8;
@@ -532,6 +490,9 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
         }
         __syncwarp();
     }
+}
+
+__device__ __forceinline__ void store_block_spins(uint16_t *S, const float *srow, int n_pad, int r, int c0, int k_end, int lane) {
     // write the replica's block segment back as bf16 (+1 = 0x3F80, -1 = 0xBF80): lane -> 4 consecutive sites, 256 B per warp
     {
         const float4 c = *reinterpret_cast<const float4 *>(srow + 4 * lane);
@@ -544,6 +505,502 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
             w[i >> 1] |= b16 << (16 * (i & 1));
         }
         *reinterpret_cast<uint2 *>(S + (size_t)r * n_pad + c0 + 4 * lane) = make_uint2(w[0], w[1]);
+    }
+}
+
+__global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(int n, int n_pad, int R_pad, int c0, const float *__restrict__ Ht,
+                                                                               const float *__restrict__ Jf, const float *__restrict__ hf,
+                                                                               const float *__restrict__ beta, uint16_t *S,
+                                                                               uint32_t seed_lo, uint32_t seed_hi,
+                                                                               const uint32_t *__restrict__ sweep_ptr, float *Ht_zero,
+                                                                               const uint8_t *__restrict__ modes, float temp_x, int pdl,
+                                                                               int r_base, int r_end) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    const uint32_t sweep = *sweep_ptr;   // bumped by the kernel at the end of the previous sweep, several launches back
+    const int rpc = blockDim.x >> 5;                                   // replicas (warps) per CTA
+    float *Jt = reinterpret_cast<float *>(dsm);                        // [kBlk j][kBlk k] = J[c0+k][c0+j] (transposed)
+    float *fld = Jt + (size_t)kBlk * kBlk;                             // [rpc][kFldStride]  running fields
+    float *thr = fld + (size_t)rpc * kFldStride;                       // [rpc][kFldStride]  thresholds
+    float *spn = thr + (size_t)rpc * kFldStride;                       // [rpc][kFldStride]  spins as floats
+    const int tid = threadIdx.x;
+    const int rep = tid >> 5, lane = tid & 31;   // replica within the CTA = warp
+    const int r = r_base + blockIdx.x * rpc + rep;   // the launch covers the replicas [r_base, r_end)
+    const int k_end = min(kBlk, n - c0);
+    // stage J_bb transposed, Jt[j][k] = J[c0+k][c0+j], from the transposed copy of J kept in global memory
+    // (JfT[a][b] = J[b][a]): asynchronous 16-byte copies, all 64 KB in flight while the thresholds are computed
+    for (int i = tid; i < kBlk * kBlk / 4; i += blockDim.x) {
+        const int j = i / (kBlk / 4), k4 = i % (kBlk / 4);
+        const uint32_t dst = smem_u32(reinterpret_cast<float4 *>(Jt) + i);
+        const float *src = Jf + (size_t)(c0 + j) * n_pad + c0 + k4 * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    float *frow = fld + rep * kFldStride;
+    float *trow = thr + rep * kFldStride;
+    float *srow = spn + rep * kFldStride;
+    const bool active = r < r_end;
+    if (active) {
+        block_thresholds(S, modes, n_pad, r, c0, k_end, lane, beta[r], seed_lo, seed_hi, sweep, temp_x, trow, srow);
+    }
+    if (pdl) {
+        // everything above (coupling block, spins of this block, thresholds) is independent of the field GEMM that runs
+        // just before this kernel: with programmatic stream serialization it overlapped that GEMM.  The fields are not.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (pdl > 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
+    if (active) {
+        // fields of the replica: lane -> sites lane + 32 q (the warps of a CTA read the same 32-byte sectors of Ht)
+        float hv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hv[q] = Ht[(size_t)(c0 + lane + 32 * q) * R_pad + r] + hf[c0 + lane + 32 * q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) frow[lane + 32 * q] = hv[q];
+        // the next block's split-K GEMM accumulates with atomics: clear its field rows for this replica
+        if (Ht_zero != nullptr)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Ht_zero[(size_t)(lane + 32 * q) * R_pad + r] = 0.f;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (!active) return;
+    block_update_chain(Jt, frow, srow, trow, lane);
+    store_block_spins(S, srow, n_pad, r, c0, k_end, lane);
+}
+
+// ---- the whole sweep as ONE kernel: clusters of 4 CTAs, split-K over the cluster, reduction through distributed shared memory
+//
+// Replicas are independent, so a tile of 128 replicas never has to wait for another tile: a CLUSTER of 4 CTAs owns one
+// tile for the whole sweep and synchronises only with itself (two cluster barriers per block of sites; no launch
+// boundaries, no global atomics, no field matrix in global memory).  33 clusters of 4 are co-resident on a B200 (15 of 8:
+// tools/micro/cluster_occupancy.cu), and 4 x 32 replicas puts one replica on every lane of a warp.  Per block of 128 sites:
+//   G  CTA c contracts its quarter of K (k-blocks [c KB/4, (c+1) KB/4)) for all 128 replicas of the tile:
+//      TMA -> 2-stage smem ring -> tcgen05.mma into a 128 x 128 fp32 TMEM accumulator (warp 0: producer, warp 1: issuer);
+//   R  warps 2-5 read the accumulator (tcgen05.ld: a warp holds the 32 replicas of ONE owner CTA) and PUSH the partial
+//      fields into the owner's receive buffer [source CTA][site][replica] with st.shared::cluster (128-byte runs);
+//      cluster barrier; every update thread adds the 4 partial values and h for its 8 sites;
+//   U  the sequential chain over the 128 sites.  Update warp w (2..17 -> w = 0..15) OWNS the sites 8w..8w+7 of the block
+//      for all 32 replicas of the CTA, lane = replica, their fields in registers.  It first applies the flips of the
+//      sub-blocks before it (d[s][8][32] in shared memory, published by their owners through a flag; couplings as
+//      broadcast loads from the staged J_bb), then takes its own 8 decisions one after the other with the right-looking
+//      corrections inside the sub-block, publishes its flips and writes its spins.  The critical path per sub-block is
+//      one propagation plus 8 decisions of ONE warp; the propagations into later sub-blocks run beside it.
+//      Same thresholds, same random stream and the same order of the floating-point corrections as
+//      dense_block_update_kernel: given equal fields the two paths take identical decisions.
+// The producer runs ahead: the operand tiles of block b+1 that do not touch the columns of block b (all but two k-blocks of
+// one CTA) are loaded and multiplied WHILE block b is being updated; only the two k-blocks of block b's own columns wait
+// for the barrier after the update (the spins are written with generic stores and read by TMA: fence.proxy.async on both
+// sides of the barrier).  The 64 KB receive buffer and the staged coupling block J_bb share one region: pushes for block
+// b+1 can only happen after every CTA of the cluster has finished the update of block b.
+constexpr int kFusedCluster = 4;
+constexpr int kFusedRep = kBM / kFusedCluster;             // 32 replicas per CTA = the lanes of a warp
+constexpr int kFusedSub = kBlk / 8;                        // 16 sub-blocks of 8 sites
+constexpr int kFusedUpdWarps = kFusedSub / 4;              // a warp = 4 sub-blocks (lane / 8) x 8 replica quads (lane % 8)
+constexpr int kFusedUpdThreads = 32 * kFusedUpdWarps;      // 128
+constexpr int kFusedThreads = 64 + kFusedUpdThreads;       // + producer warp + MMA warp
+constexpr int kFusedStages = 2;
+constexpr size_t kFusedRingBytes = (size_t)kFusedStages * (1 + kMaxSplit) * kTileBytes;     // 128 KB
+constexpr size_t kFusedXBytes = sizeof(float) * kBlk * kBlk;                                // 64 KB: receive buffer / J_bb
+constexpr size_t kFusedDBytes = sizeof(float) * kBlk * kFusedRep;                           // 16 KB: flips d[site][replica]
+constexpr size_t kFusedSmemBytes = 1024 + kFusedRingBytes + kFusedXBytes + kFusedDBytes + 256;
+static_assert(kFusedRep == 32, "one replica per lane");
+static_assert(kFusedCluster * kBlk * kFusedRep * sizeof(float) == kFusedXBytes, "receive buffer and J_bb share one region");
+
+struct FusedParams {
+    int n, n_pad, R_pad, n_blocks, kb_total, n_split;
+    const float *Jf, *hf, *beta;
+    uint16_t *S;
+    uint32_t seed_lo, seed_hi;
+    const uint32_t *sweep_ptr;
+    const uint8_t *modes;
+    float temp_x;
+    unsigned long long *prof;   // NLMC_DENSE_FUSED_PROF: %globaltimer at the phase boundaries of CTA 0, [n_blocks][10]
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define NLMC_FUSED_MARK(i) do { if (p.prof && blockIdx.x == 0 && threadIdx.x == kFusedThreads - 1) p.prof[b * 10 + (i)] = global_ns(); } while (0)
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// packed pairs of floats (FFMA2 / FMUL2 / FADD2 on sm_100: two fp32 operations per issue slot, each rounded like the scalar one)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo2(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float hi2(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// thresholds and old spins of the sites c0 + 8w .. c0 + 8w + 7 of replica r: the two Philox calls that serve these sites
+// in block_thresholds (lanes 2w and 2w+1 there)
+__device__ __forceinline__ void site_thresholds8(const uint16_t *S, const uint8_t *__restrict__ modes, int n_pad, int r, int c0, int w,
+                                                 int k_end, float beta_r, uint32_t seed_lo, uint32_t seed_hi, uint32_t sweep,
+                                                 float temp_x, float (&T)[8], float (&so)[8]) {
+    const uint4 sv = *reinterpret_cast<const uint4 *>(S + (size_t)r * n_pad + c0 + 8 * w);
+    const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+    uint2 md8 = make_uint2(0u, 0u);
+    if (modes != nullptr) md8 = *reinterpret_cast<const uint2 *>(modes + (size_t)r * n_pad + c0 + 8 * w);
+    const float inv2b = 0.5f / beta_r;
+    const PhiloxD rng{seed_lo, seed_hi ^ 0x44454e53u};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint4 rv = rng((uint32_t)r, (uint32_t)(c0 + 8 * w), sweep, (uint32_t)half);
+        const uint32_t ub[4] = {rv.x, rv.y, rv.z, rv.w};
+        const uint32_t md4 = half ? md8.y : md8.x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = 4 * half + i;
+            const uint32_t s16 = (sw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+            const bool hi = (ub[i] >> 31) != 0u;
+            const uint32_t m = hi ? ~ub[i] : ub[i];
+            const float v = ((float)m + 0.5f) * (1.0f / 4294967296.0f);       // in (0, 1/2]
+            const float t = __logf(v) - __logf(1.0f - v);
+            float th = (hi ? -t : t) * inv2b;
+            const float s = (s16 == 0u) ? 0.0f : ((s16 & 0x8000u) ? -1.0f : 1.0f);
+            const uint32_t md = (md4 >> (8 * i)) & 0xffu;
+            if (md == 1u) th *= temp_x;                                       // hot backbone: beta / temp_x
+            if (md == 2u || 8 * w + k >= k_end)                               // frozen (or padding): the spin keeps its value
+                th = s > 0.0f ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
+            T[k] = th;
+            so[k] = s;
+        }
+    }
+}
+
+__global__ void __cluster_dims__(kFusedCluster, 1, 1) __launch_bounds__(kFusedThreads, 1)
+dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b0,
+                         const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
+                         const FusedParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment as an OFFSET from the shared array, so that the compiler still knows these are shared-memory
+    // pointers (LDS / STS instead of generic loads and stores in the chain)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float *X = reinterpret_cast<float *>(smem + kFusedRingBytes);        // receive buffer [4][128][32]  /  Jt [128][128]
+    float *dbuf = X + (size_t)kBlk * kBlk;                               // flips d[site of the block][replica]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dbuf + (size_t)kBlk * kFusedRep);
+    uint64_t *full = bars, *empty = bars + kFusedStages, *tmem_full = bars + 2 * kFusedStages;
+    uint64_t *sub_done = bars + 2 * kFusedStages + 1;   // [16] one phase per block: the flips of sub-block s are published
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(sub_done + kFusedSub);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int tile = blockIdx.x / kFusedCluster;
+    const int m0 = tile * kBM;
+    const int kb_lo = (int)rank * p.kb_total / kFusedCluster, kb_hi = ((int)rank + 1) * p.kb_total / kFusedCluster;
+    const int n_kb = kb_hi - kb_lo;
+    const int stage_bytes = (1 + p.n_split) * kTileBytes;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b0) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kFusedStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+            mbar_init(tmem_full, 1);
+            for (int i = 0; i < kFusedSub; ++i) mbar_init(sub_done + i, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kBN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    // every CTA of the cluster is running before anybody touches a neighbour's shared memory
+    cluster_arrive();
+    cluster_wait();
+
+    // the k-blocks of this CTA in the order they are loaded and multiplied for block b: those outside the columns of block
+    // b-1 first (they do not depend on the update of block b-1), the one or two inside last
+    auto is_dep = [](int kb, int b) { return b > 0 && (kb >> 1) == b - 1; };   // kBlk / kBK == 2 k-blocks per site block
+
+    if (warp == 0) {  // ===== TMA producer =====
+        const CUtensorMap *maps_b[kMaxSplit] = {&map_b0, &map_b1, &map_b2};
+        uint32_t it = 0;
+        // part & 1: the coupling tiles (never depend on the update), part & 2: the spin tile
+        auto issue = [&](int kb, int b, uint32_t at, int part) {
+            const int s = (int)(at % kFusedStages);
+            const uint32_t ph = (at / kFusedStages) & 1u;
+            uint8_t *st = smem + (size_t)s * (1 + kMaxSplit) * kTileBytes;
+            if (part & 1) {
+                mbar_wait(empty + s, ph ^ 1u);
+                mbar_expect_tx(full + s, (uint32_t)stage_bytes);
+                for (int q = 0; q < p.n_split; ++q) tma_load_2d(st + (1 + q) * kTileBytes, maps_b[q], full + s, kb * kBK, b * kBlk);
+            }
+            if (part & 2) tma_load_2d(st, &map_a, full + s, kb * kBK, m0);
+        };
+        for (int b = 0; b < p.n_blocks; ++b) {
+            if (b > 0) cluster_arrive();                       // U(b-1): nothing of ours to publish
+            uint32_t it_dep = it;
+            if (lane == 0) {
+                for (int kb = kb_lo; kb < kb_hi; ++kb) if (!is_dep(kb, b)) issue(kb, b, it++, 3);
+                it_dep = it;
+                // the k-blocks inside the columns of block b-1: their coupling tiles now, their spin tiles after the barrier
+                for (int kb = kb_lo; kb < kb_hi; ++kb) if (is_dep(kb, b)) issue(kb, b, it++, 1);
+            }
+            __syncwarp();
+            if (b > 0) cluster_wait();                         // U(b-1): the spins of block b-1 are final
+            if (lane == 0) {
+                fence_proxy_async();
+                for (int kb = kb_lo; kb < kb_hi; ++kb) if (is_dep(kb, b)) issue(kb, b, it_dep++, 2);
+            }
+            __syncwarp();
+            cluster_arrive();                                  // R(b)
+            cluster_wait();
+        }
+        cluster_arrive();                                      // U(last)
+        cluster_wait();
+    } else if (warp == 1) {  // ===== MMA issuer =====
+        const uint32_t idesc = make_idesc_bf16(kBM, kBN);
+        uint32_t it = 0;
+        for (int b = 0; b < p.n_blocks; ++b) {
+            if (b > 0) cluster_arrive();                       // U(b-1)
+            if (lane == 0 && n_kb > 0) {
+                tcgen05_fence_after();
+                int done = 0;
+                for (int pass = 0; pass < 2; ++pass)
+                    for (int kb = kb_lo; kb < kb_hi; ++kb) {
+                        if (is_dep(kb, b) != (pass == 1)) continue;
+                        const int s = (int)(it % kFusedStages);
+                        const uint32_t ph = (it / kFusedStages) & 1u;
+                        mbar_wait(full + s, ph);
+                        tcgen05_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + (size_t)s * (1 + kMaxSplit) * kTileBytes);
+                        const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+                        for (int q = 0; q < p.n_split; ++q) {
+                            const uint64_t b_desc = make_smem_desc_sw128(a_addr + (1 + q) * kTileBytes);
+#pragma unroll
+                            for (int k = 0; k < kBK / 16; ++k)
+                                umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                          (uint32_t)((done | q | k) != 0));
+                        }
+                        umma_commit(empty + s);
+                        ++it;
+                        ++done;
+                    }
+                umma_commit(tmem_full);
+            }
+            __syncwarp();
+            if (b > 0) cluster_wait();                         // U(b-1)
+            cluster_arrive();                                  // R(b)
+            cluster_wait();
+        }
+        cluster_arrive();                                      // U(last)
+        cluster_wait();
+    } else {  // ===== update warps 2..5: thread = (sub-block 4 v + lane / 8, replicas 4 (lane % 8) .. + 3); they also drain =====
+        const int v = warp - 2;
+        const int g = lane >> 3, q = lane & 7;
+        const int sb = 4 * v + g;                              // the sub-block (sites 8 sb .. 8 sb + 7 of every block) this thread owns
+        const int ut = (int)threadIdx.x - 64;
+        const int rq = m0 + (int)rank * kFusedRep + 4 * q;     // its four replicas
+        float beta4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) beta4[e] = p.beta[rq + e];
+        const uint32_t sweep = *p.sweep_ptr;
+        for (int b = 0; b < p.n_blocks; ++b) {
+            const int c0 = b * kBlk;
+            const int k_end = min(kBlk, p.n - c0);
+            NLMC_FUSED_MARK(0);
+            // fields of the thread's 8 sites x 4 replicas as packed pairs over the SITES: F2[ip][e] = (F[2 ip][e], F[2 ip + 1][e])
+            float T[8][4], so[8][4];
+            f32x2 F2[4][4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float t8[8], s8[8];
+                site_thresholds8(p.S, p.modes, p.n_pad, rq + e, c0, sb, k_end, beta4[e], p.seed_lo, p.seed_hi, sweep, p.temp_x, t8, s8);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { T[i][e] = t8[i]; so[i][e] = s8[i]; }
+            }
+            NLMC_FUSED_MARK(1);
+            if (b > 0) cluster_wait();                         // U(b-1): every CTA is done with its J_bb, the receive buffers are free
+            NLMC_FUSED_MARK(2);
+            {
+                // TMEM lanes 32 k .. 32 k + 31 = the replicas of CTA k of the cluster: a warp (lane quarter warp % 4) pushes to ONE owner
+                const int quarter = warp & 3;
+                const uint32_t local = smem_u32(X) + (uint32_t)(((int)rank * kBlk) * kFusedRep + lane) * 4u;
+                uint32_t dst;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(local), "r"((uint32_t)quarter));
+                if (n_kb > 0) {
+                    mbar_wait(tmem_full, (uint32_t)(b & 1));
+                    tcgen05_fence_after();
+                }
+                NLMC_FUSED_MARK(3);
+#pragma unroll 1
+                for (int c = 0; c < kBN; c += 32) {
+                    uint32_t x[32];
+                    if (n_kb > 0) {
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c;
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                            : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]),
+                              "=r"(x[8]), "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15]),
+                              "=r"(x[16]), "=r"(x[17]), "=r"(x[18]), "=r"(x[19]), "=r"(x[20]), "=r"(x[21]), "=r"(x[22]), "=r"(x[23]),
+                              "=r"(x[24]), "=r"(x[25]), "=r"(x[26]), "=r"(x[27]), "=r"(x[28]), "=r"(x[29]), "=r"(x[30]), "=r"(x[31])
+                            : "r"(taddr));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = 0u;
+                    }
+                    // site c + j of this replica: the 32 lanes of the warp write 128 contiguous bytes
+                    if ((uint32_t)quarter == rank) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(local + (uint32_t)((c + j) * kFusedRep * 4)), "r"(x[j]) : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(dst + (uint32_t)((c + j) * kFusedRep * 4)), "r"(x[j]) : "memory");
+                    }
+                }
+                tcgen05_fence_before();
+            }
+            NLMC_FUSED_MARK(4);
+            cluster_arrive();                                  // R(b): the partial fields are in their owners' buffers
+            cluster_wait();
+            NLMC_FUSED_MARK(5);
+#pragma unroll
+            for (int ip = 0; ip < 4; ++ip) {
+                float4 f[2];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int i = 2 * ip + h2;
+                    float4 a = *reinterpret_cast<const float4 *>(X + (0 * kBlk + 8 * sb + i) * kFusedRep + 4 * q);
+#pragma unroll
+                    for (int src = 1; src < kFusedCluster; ++src) {
+                        const float4 t = *reinterpret_cast<const float4 *>(X + (src * kBlk + 8 * sb + i) * kFusedRep + 4 * q);
+                        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                    }
+                    const float hk = p.hf[c0 + 8 * sb + i];
+                    f[h2] = make_float4(a.x + hk, a.y + hk, a.z + hk, a.w + hk);
+                }
+                F2[ip][0] = pack2(f[0].x, f[1].x); F2[ip][1] = pack2(f[0].y, f[1].y);
+                F2[ip][2] = pack2(f[0].z, f[1].z); F2[ip][3] = pack2(f[0].w, f[1].w);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kFusedUpdThreads) : "memory");
+            NLMC_FUSED_MARK(6);
+            // J_bb transposed into the region the receive buffer occupied
+            for (int i = ut; i < kBlk * kBlk / 4; i += kFusedUpdThreads) {
+                const int j = i / (kBlk / 4), k4 = i % (kBlk / 4);
+                const uint32_t dj = smem_u32(reinterpret_cast<float4 *>(X) + i);
+                const float *src = p.Jf + (size_t)(c0 + j) * p.n_pad + c0 + k4 * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dj), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kFusedUpdThreads) : "memory");
+            NLMC_FUSED_MARK(7);
+            const float *Jt = X;
+            float dmine[8][4];
+            // The 16 sub-blocks in order.  Step s: its owners (8 lanes of warp s / 4) take the 8 decisions for their 4 replicas
+            // each and publish the flips; every thread whose sub-block comes later applies them to its 8 x 4 fields (two FMA
+            // chains of four, summed: the rounding of block_update_chain).  A coupling value is loaded once per 4 replicas, and
+            // the corrections run as packed FFMA2 over pairs of sites.
+            for (int s = 0; s < kFusedSub; ++s) {
+                const int vs = s >> 2;
+                if (v < vs) break;                             // every sub-block of this warp is done
+                if (v == vs) {
+                    if (g == (s & 3)) {
+                        if (p.prof && b == 2 && blockIdx.x == 0 && q == 7) p.prof[p.n_blocks * 10 + 4 * s] = global_ns();
+                        // the couplings inside the sub-block (rows i = 0..6, pairs of columns) before the sequential part
+                        f32x2 Jr[7][4];
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) {
+                            const ulonglong2 lo = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * sb + i) * kBlk + 8 * sb);
+                            const ulonglong2 hi4 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * sb + i) * kBlk + 8 * sb + 4);
+                            Jr[i][0] = lo.x; Jr[i][1] = lo.y; Jr[i][2] = hi4.x; Jr[i][3] = hi4.y;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float f = (i & 1) ? hi2(F2[i >> 1][e]) : lo2(F2[i >> 1][e]);
+                                const float sn = f > T[i][e] ? 1.0f : -1.0f;
+                                const float d = sn - so[i][e];
+                                dmine[i][e] = d;
+                                if (i < 7) {   // right-looking inside the sub-block; the pair that holds site i itself is updated too (its own half is dead)
+                                    const f32x2 dd = pack2(d, d);
+#pragma unroll
+                                    for (int ip = (i + 1) >> 1; ip < 4; ++ip) F2[ip][e] = fma2(Jr[i][ip], dd, F2[ip][e]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            *reinterpret_cast<float4 *>(dbuf + (8 * sb + i) * kFusedRep + 4 * q) = make_float4(dmine[i][0], dmine[i][1], dmine[i][2], dmine[i][3]);
+                        if (p.prof && b == 2 && blockIdx.x == 0 && q == 7) p.prof[p.n_blocks * 10 + 4 * s + 1] = global_ns() + (dmine[7][3] == 123.f);
+                    }
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sub_done + s)) : "memory");
+                } else {
+                    mbar_wait(sub_done + s, (uint32_t)(b & 1));    // hardware wait, no polling traffic on the shared-memory pipe
+                }
+                if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == kFusedThreads - 1) p.prof[p.n_blocks * 10 + 4 * s + 2] = global_ns();
+                if (sb > s) {
+                    f32x2 C2[4][4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 dl = *reinterpret_cast<const float4 *>(dbuf + (8 * s + j) * kFusedRep + 4 * q);
+                        const float4 dh = *reinterpret_cast<const float4 *>(dbuf + (8 * s + 4 + j) * kFusedRep + 4 * q);
+                        const ulonglong2 l0 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s + j) * kBlk + 8 * sb);
+                        const ulonglong2 l1 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s + j) * kBlk + 8 * sb + 4);
+                        const ulonglong2 h0 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s + 4 + j) * kBlk + 8 * sb);
+                        const ulonglong2 h1 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s + 4 + j) * kBlk + 8 * sb + 4);
+                        const f32x2 Jl[4] = {l0.x, l0.y, l1.x, l1.y}, Jh[4] = {h0.x, h0.y, h1.x, h1.y};
+                        const float dlo[4] = {dl.x, dl.y, dl.z, dl.w}, dhi[4] = {dh.x, dh.y, dh.z, dh.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const f32x2 ddl = pack2(dlo[e], dlo[e]), ddh = pack2(dhi[e], dhi[e]);
+#pragma unroll
+                            for (int ip = 0; ip < 4; ++ip) {
+                                F2[ip][e] = fma2(Jl[ip], ddl, F2[ip][e]);
+                                C2[ip][e] = j == 0 ? mul2(Jh[ip], ddh) : fma2(Jh[ip], ddh, C2[ip][e]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int ip = 0; ip < 4; ++ip)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) F2[ip][e] = add2(F2[ip][e], C2[ip][e]);
+                    if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == kFusedThreads - 1) p.prof[p.n_blocks * 10 + 4 * s + 3] = global_ns() + (F2[0][0] == 123ull);
+                }
+            }
+            // new spins = old spins + flips, as bf16 (+1 = 0x3F80, -1 = 0xBF80; 0 past the end of J)
+            uint32_t bits[4][4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float sn = so[i][e] + dmine[i][e];
+                    const uint32_t b16 = (8 * sb + i < k_end) ? (sn > 0.0f ? 0x3F80u : 0xBF80u) : 0u;
+                    if ((i & 1) == 0) bits[e][i >> 1] = b16; else bits[e][i >> 1] |= b16 << 16;
+                }
+            NLMC_FUSED_MARK(8);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                *reinterpret_cast<uint4 *>(p.S + (size_t)(rq + e) * p.n_pad + c0 + 8 * sb) = make_uint4(bits[e][0], bits[e][1], bits[e][2], bits[e][3]);
+            fence_proxy_async();                               // the spins are read by TMA (async proxy) in the next block
+            NLMC_FUSED_MARK(9);
+            cluster_arrive();                                  // U(b)
+        }
+        cluster_wait();                                        // U(last): nobody writes into this CTA's buffers any more
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kBN) : "memory");
     }
 }
 
@@ -614,6 +1071,29 @@ extern "C" {
 int nlmc_dense_destroy(nlmc_dense *D) {
     if (!D) return NLMC_OK;
     cudaSetDevice(D->inst->device);
+    if (D->fused_prof) {   // development aid: where one block step of the cluster sweep spends its time (CTA 0, first update warp)
+        const int nb = (D->n + nlmc::kBlk - 1) / nlmc::kBlk;
+        std::vector<unsigned long long> t((size_t)nb * 10 + 64);
+        cudaDeviceSynchronize();
+        cudaMemcpy(t.data(), D->fused_prof, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost);
+        static const char *names[9] = {"thresholds", "wait U(b-1)", "wait accumulator", "drain + push", "cluster barrier R", "sum",
+                                       "stage J_bb", "chain", "store"};
+        for (int b = 0; b < nb; ++b) {
+            fprintf(stderr, "fused block %2d:", b);
+            for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.2f us |", names[i], 1e-3 * (double)(t[(size_t)b * 10 + i + 1] - t[(size_t)b * 10 + i]));
+            if (b + 1 < nb) fprintf(stderr, " step %.2f us", 1e-3 * (double)(t[(size_t)(b + 1) * 10] - t[(size_t)b * 10]));
+            fprintf(stderr, "\n");
+        }
+        if (nb > 2) {
+            fprintf(stderr, "block 2, us after the chain started -- step: decisions start/end (owner), flips seen / applied by the last thread\n");
+            for (int i = 0; i < 16; ++i) {
+                const unsigned long long *x = &t[(size_t)nb * 10 + 4 * i];
+                fprintf(stderr, " %d: %.2f/%.2f %.2f/%.2f |", i, 1e-3 * (double)(x[0] - t[27]), 1e-3 * (double)(x[1] - t[27]), 1e-3 * (double)(x[2] - t[27]), 1e-3 * (double)(x[3] - t[27]));
+            }
+            fprintf(stderr, "\n");
+        }
+        cudaFree(D->fused_prof);
+    }
     void *ptrs[] = {D->S, D->Jp[0], D->Jp[1], D->Jp[2], D->Jf, D->hf, D->Ht, D->beta, D->E, D->d_sweep, D->bestE, D->bestS, D->modes};
     for (void *p : ptrs) if (p) cudaFree(p);
     D->xch.release();
@@ -708,7 +1188,8 @@ int nlmc_dense_create(nlmc_instance *I, int n_replicas, const double *betas, int
     if (!rc) {
         if (cudaFuncSetAttribute(gemm_bf16_tn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(3)) != cudaSuccess ||
             cudaFuncSetAttribute(gemm_bf16_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)) != cudaSuccess ||
-            cudaFuncSetAttribute(dense_block_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(kMaxRepPerCta)) != cudaSuccess) {
+            cudaFuncSetAttribute(dense_block_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(kMaxRepPerCta)) != cudaSuccess ||
+            cudaFuncSetAttribute(dense_fused_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes) != cudaSuccess) {
             set_error("nlmc_dense_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = NLMC_ERR_CUDA;
         }
@@ -805,6 +1286,26 @@ static int enqueue_sweep(nlmc_dense *D, int k_splits) {
                    (int)((pdl && !look_ahead) ? (getenv("NLMC_DENSE_PDL_EARLY") ? 2 : 1) : 0), 0, D->R_pad);
     };
     int rc;
+    // The whole sweep as one launch of the cluster kernel (dense_fused_sweep_kernel); NLMC_DENSE_FUSED=0 selects the
+    // GEMM -> update chain below.
+    {
+        const char *e = getenv("NLMC_DENSE_FUSED");
+        const bool fused = e ? atoi(e) != 0 : true;
+        if (fused && !look_ahead && !pdl && !getenv("NLMC_DENSE_CHAINS") && !getenv("NLMC_DENSE_SKIP")) {
+            FusedParams fp;
+            fp.n = D->n; fp.n_pad = D->n_pad; fp.R_pad = D->R_pad; fp.n_blocks = nb; fp.kb_total = kb_all; fp.n_split = D->n_split;
+            fp.Jf = D->Jf; fp.hf = D->hf; fp.beta = D->beta; fp.S = D->S;
+            fp.seed_lo = (uint32_t)D->seed; fp.seed_hi = (uint32_t)(D->seed >> 32);
+            fp.sweep_ptr = D->d_sweep; fp.modes = D->modes_on ? D->modes : nullptr; fp.temp_x = D->temp_x;
+            fp.prof = D->fused_prof;
+            dense_fused_sweep_kernel<<<(unsigned)(kFusedCluster * (D->R_pad / kBM)), kFusedThreads, kFusedSmemBytes, D->stream>>>(
+                D->map_S, D->map_J[0], D->map_J[D->n_split > 1 ? 1 : 0], D->map_J[D->n_split > 2 ? 2 : 0], fp);
+            NLMC_CUDA(cudaGetLastError());
+            dense_bump_kernel<<<1, 1, 0, D->stream>>>(D->d_sweep);
+            NLMC_CUDA(cudaGetLastError());
+            return NLMC_OK;
+        }
+    }
     // Replicas are independent, so the GEMM -> update chain of one range of replica tiles never has to wait for another
     // range: the sweep can run as n_chains independent chains on their own streams (forked and joined inside the captured
     // graph), the GEMM of one chain resident next to the update of another.  Measured on B200 at C3 size: 0.358 ms per
@@ -903,6 +1404,11 @@ int nlmc_dense_sweep(nlmc_dense *D, int n_sweeps) {
     NLMC_REQUIRE(D && n_sweeps >= 0, "nlmc_dense_sweep: bad arguments");
     NLMC_CUDA(cudaSetDevice(D->inst->device));
     if (!D->sweep_graph) {  // capture one sweep once; replays cost one launch each
+        if (getenv("NLMC_DENSE_FUSED_PROF") && !D->fused_prof) {
+            const size_t cnt = 10 * (size_t)((D->n + kBlk - 1) / kBlk) + 64;
+            NLMC_CUDA(cudaMalloc(&D->fused_prof, sizeof(unsigned long long) * cnt));
+            NLMC_CUDA(cudaMemset(D->fused_prof, 0, sizeof(unsigned long long) * cnt));
+        }
         const int m_tiles = D->R_pad / kBM;
         int k_splits = std::max(1, std::min(D->n_pad / kBK, 148 / std::max(1, m_tiles)));
         if (const char *e = getenv("NLMC_DENSE_KSPLIT")) k_splits = std::max(1, atoi(e));
