@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
 // tile for the whole sweep and synchronises only with itself (two cluster barriers per block of sites; no launch
 // boundaries, no global atomics, no field matrix in global memory).  33 clusters of 4 are co-resident on a B200 (15 of 8:
 // tools/micro/cluster_occupancy.cu), and 4 x 32 replicas puts one replica on every lane of a warp.  Per block of 128 sites:
-//   G  CTA c contracts its quarter of K (k-blocks [c KB/4, (c+1) KB/4)) for all 128 replicas of the tile:
+//   G  CTA c contracts its quarter of K (k-blocks c, c + 4, c + 8, ...) for all 128 replicas of the tile:
 //      TMA -> 2-stage smem ring -> tcgen05.mma into a 128 x 128 fp32 TMEM accumulator (warp 0: producer, warp 1: issuer);
 //   R  warps 2-5 read the accumulator (tcgen05.ld: a warp holds the 32 replicas of ONE owner CTA) and PUSH the partial
 //      fields into the owner's receive buffer [source CTA][site][replica] with st.shared::cluster (128-byte runs);
@@ -594,14 +594,20 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
 constexpr int kFusedCluster = 4;
 constexpr int kFusedRep = kBM / kFusedCluster;             // 32 replicas per CTA = the lanes of a warp
 constexpr int kFusedSub = kBlk / 8;                        // 16 sub-blocks of 8 sites
-constexpr int kFusedUpdWarps = kFusedSub / 4;              // a warp = 4 sub-blocks (lane / 8) x 8 replica quads (lane % 8)
+#ifndef NLMC_FUSED_E
+#define NLMC_FUSED_E 2
+#endif
+constexpr int kE = NLMC_FUSED_E;                           // replicas per update thread (2 or 4): a thread's tile is 8 sites x kE replicas
+constexpr int kLanesPerSub = 32 / kE;                      // lanes that share a sub-block; a warp holds kE sub-blocks
+constexpr int kFusedUpdWarps = kFusedSub / kE;
+static_assert(kE == 2 || kE == 4, "thread tile of 8 sites x 2 or 4 replicas");
 constexpr int kFusedUpdThreads = 32 * kFusedUpdWarps;      // 128
 constexpr int kFusedThreads = 64 + kFusedUpdThreads;       // + producer warp + MMA warp
 constexpr int kFusedStages = 2;
 constexpr size_t kFusedRingBytes = (size_t)kFusedStages * (1 + kMaxSplit) * kTileBytes;     // 128 KB
 constexpr size_t kFusedXBytes = sizeof(float) * kBlk * kBlk;                                // 64 KB: receive buffer / J_bb
 constexpr size_t kFusedDBytes = sizeof(float) * kBlk * kFusedRep;                           // 16 KB: flips d[site][replica]
-constexpr size_t kFusedSmemBytes = 1024 + kFusedRingBytes + kFusedXBytes + kFusedDBytes + 256;
+constexpr size_t kFusedSmemBytes = 1024 + kFusedRingBytes + kFusedXBytes + 2 * kFusedDBytes + 256;   // + thresholds [site][replica]
 static_assert(kFusedRep == 32, "one replica per lane");
 static_assert(kFusedCluster * kBlk * kFusedRep * sizeof(float) == kFusedXBytes, "receive buffer and J_bb share one region");
 
@@ -635,6 +641,16 @@ __device__ __forceinline__ float hi2(f32x2 v) { float lo, hi; asm("mov.b64 {%0, 
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// kE consecutive floats of shared memory
+__device__ __forceinline__ void ld_e(const float *ptr, float (&v)[kE]) {
+    if constexpr (kE == 4) { const float4 t = *reinterpret_cast<const float4 *>(ptr); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else { const float2 t = *reinterpret_cast<const float2 *>(ptr); v[0] = t.x; v[1] = t.y; }
+}
+__device__ __forceinline__ void st_e(float *ptr, const float (&v)[kE]) {
+    if constexpr (kE == 4) *reinterpret_cast<float4 *>(ptr) = make_float4(v[0], v[1], v[2], v[3]);
+    else *reinterpret_cast<float2 *>(ptr) = make_float2(v[0], v[1]);
+}
 
 // thresholds and old spins of the sites c0 + 8w .. c0 + 8w + 7 of replica r: the two Philox calls that serve these sites
 // in block_thresholds (lanes 2w and 2w+1 there)
@@ -682,7 +698,8 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float *X = reinterpret_cast<float *>(smem + kFusedRingBytes);        // receive buffer [4][128][32]  /  Jt [128][128]
     float *dbuf = X + (size_t)kBlk * kBlk;                               // flips d[site of the block][replica]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(dbuf + (size_t)kBlk * kFusedRep);
+    float *tbuf = dbuf + (size_t)kBlk * kFusedRep;                       // thresholds T[site of the block][replica]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tbuf + (size_t)kBlk * kFusedRep);
     uint64_t *full = bars, *empty = bars + kFusedStages, *tmem_full = bars + 2 * kFusedStages;
     uint64_t *sub_done = bars + 2 * kFusedStages + 1;   // [16] one phase per block: the flips of sub-block s are published
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(sub_done + kFusedSub);
@@ -692,8 +709,10 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int tile = blockIdx.x / kFusedCluster;
     const int m0 = tile * kBM;
-    const int kb_lo = (int)rank * p.kb_total / kFusedCluster, kb_hi = ((int)rank + 1) * p.kb_total / kFusedCluster;
-    const int n_kb = kb_hi - kb_lo;
+    // k-blocks rank, rank + 4, ...: the two k-blocks that hold the columns of a site block land on two different CTAs, so the
+    // part of the contraction that has to wait for the update is one k-block per CTA at most
+    const int kb_lo = (int)rank, kb_hi = p.kb_total;
+    const int n_kb = (p.kb_total - (int)rank + kFusedCluster - 1) / kFusedCluster;
     const int stage_bytes = (1 + p.n_split) * kTileBytes;
 
     if (warp == 0 && lane == 0) {
@@ -742,16 +761,16 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             if (b > 0) cluster_arrive();                       // U(b-1): nothing of ours to publish
             uint32_t it_dep = it;
             if (lane == 0) {
-                for (int kb = kb_lo; kb < kb_hi; ++kb) if (!is_dep(kb, b)) issue(kb, b, it++, 3);
+                for (int kb = kb_lo; kb < kb_hi; kb += kFusedCluster) if (!is_dep(kb, b)) issue(kb, b, it++, 3);
                 it_dep = it;
                 // the k-blocks inside the columns of block b-1: their coupling tiles now, their spin tiles after the barrier
-                for (int kb = kb_lo; kb < kb_hi; ++kb) if (is_dep(kb, b)) issue(kb, b, it++, 1);
+                for (int kb = kb_lo; kb < kb_hi; kb += kFusedCluster) if (is_dep(kb, b)) issue(kb, b, it++, 1);
             }
             __syncwarp();
             if (b > 0) cluster_wait();                         // U(b-1): the spins of block b-1 are final
             if (lane == 0) {
                 fence_proxy_async();
-                for (int kb = kb_lo; kb < kb_hi; ++kb) if (is_dep(kb, b)) issue(kb, b, it_dep++, 2);
+                for (int kb = kb_lo; kb < kb_hi; kb += kFusedCluster) if (is_dep(kb, b)) issue(kb, b, it_dep++, 2);
             }
             __syncwarp();
             cluster_arrive();                                  // R(b)
@@ -768,7 +787,7 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 tcgen05_fence_after();
                 int done = 0;
                 for (int pass = 0; pass < 2; ++pass)
-                    for (int kb = kb_lo; kb < kb_hi; ++kb) {
+                    for (int kb = kb_lo; kb < kb_hi; kb += kFusedCluster) {
                         if (is_dep(kb, b) != (pass == 1)) continue;
                         const int s = (int)(it % kFusedStages);
                         const uint32_t ph = (it / kFusedStages) & 1u;
@@ -796,29 +815,35 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         }
         cluster_arrive();                                      // U(last)
         cluster_wait();
-    } else {  // ===== update warps 2..5: thread = (sub-block 4 v + lane / 8, replicas 4 (lane % 8) .. + 3); they also drain =====
+    } else {  // ===== update warps: thread = (sub-block kE v + lane / kLanesPerSub, replicas kE (lane % kLanesPerSub) .. + kE - 1); they also drain =====
         const int v = warp - 2;
-        const int g = lane >> 3, q = lane & 7;
-        const int sb = 4 * v + g;                              // the sub-block (sites 8 sb .. 8 sb + 7 of every block) this thread owns
+        const int g = lane / kLanesPerSub, q = lane % kLanesPerSub;
+        const int sb = kE * v + g;                             // the sub-block (sites 8 sb .. 8 sb + 7 of every block) this thread owns
         const int ut = (int)threadIdx.x - 64;
-        const int rq = m0 + (int)rank * kFusedRep + 4 * q;     // its four replicas
-        float beta4[4];
+        const int rq = m0 + (int)rank * kFusedRep + kE * q;    // its kE replicas
+        float beta4[kE];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) beta4[e] = p.beta[rq + e];
+        for (int e = 0; e < kE; ++e) beta4[e] = p.beta[rq + e];
         const uint32_t sweep = *p.sweep_ptr;
         for (int b = 0; b < p.n_blocks; ++b) {
             const int c0 = b * kBlk;
             const int k_end = min(kBlk, p.n - c0);
             NLMC_FUSED_MARK(0);
             // fields of the thread's 8 sites x 4 replicas as packed pairs over the SITES: F2[ip][e] = (F[2 ip][e], F[2 ip + 1][e])
-            float T[8][4], so[8][4];
-            f32x2 F2[4][4];
+            // Thresholds go to shared memory until the thread's own decisions (they would hold 32 registers through every
+            // propagation before them); the old spins stay as one bit each (a site past the end of J counts as -1: its
+            // threshold is +inf, so it "stays" -1, its flip is 0 and its couplings are 0).
+            uint32_t so_up = 0u;   // bit kE i + e: site i of replica e is +1
+            f32x2 F2[4][kE];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < kE; ++e) {
                 float t8[8], s8[8];
                 site_thresholds8(p.S, p.modes, p.n_pad, rq + e, c0, sb, k_end, beta4[e], p.seed_lo, p.seed_hi, sweep, p.temp_x, t8, s8);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { T[i][e] = t8[i]; so[i][e] = s8[i]; }
+                for (int i = 0; i < 8; ++i) {
+                    tbuf[(8 * sb + i) * kFusedRep + kE * q + e] = t8[i];
+                    so_up |= (s8[i] > 0.0f ? 1u : 0u) << (kE * i + e);
+                }
             }
             NLMC_FUSED_MARK(1);
             if (b > 0) cluster_wait();                         // U(b-1): every CTA is done with its J_bb, the receive buffers are free
@@ -834,8 +859,9 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                     tcgen05_fence_after();
                 }
                 NLMC_FUSED_MARK(3);
+                constexpr int kColsPerWarp = kBN / (kFusedUpdWarps / 4);   // the warps of a lane quarter share the 128 columns
 #pragma unroll 1
-                for (int c = 0; c < kBN; c += 32) {
+                for (int c = (v >> 2) * kColsPerWarp; c < ((v >> 2) + 1) * kColsPerWarp; c += 32) {
                     uint32_t x[32];
                     if (n_kb > 0) {
                         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c;
@@ -872,21 +898,24 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             NLMC_FUSED_MARK(5);
 #pragma unroll
             for (int ip = 0; ip < 4; ++ip) {
-                float4 f[2];
+                float f[2][kE];
 #pragma unroll
                 for (int h2 = 0; h2 < 2; ++h2) {
                     const int i = 2 * ip + h2;
-                    float4 a = *reinterpret_cast<const float4 *>(X + (0 * kBlk + 8 * sb + i) * kFusedRep + 4 * q);
+                    ld_e(X + (0 * kBlk + 8 * sb + i) * kFusedRep + kE * q, f[h2]);
 #pragma unroll
                     for (int src = 1; src < kFusedCluster; ++src) {
-                        const float4 t = *reinterpret_cast<const float4 *>(X + (src * kBlk + 8 * sb + i) * kFusedRep + 4 * q);
-                        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                        float t[kE];
+                        ld_e(X + (src * kBlk + 8 * sb + i) * kFusedRep + kE * q, t);
+#pragma unroll
+                        for (int e = 0; e < kE; ++e) f[h2][e] += t[e];
                     }
                     const float hk = p.hf[c0 + 8 * sb + i];
-                    f[h2] = make_float4(a.x + hk, a.y + hk, a.z + hk, a.w + hk);
+#pragma unroll
+                    for (int e = 0; e < kE; ++e) f[h2][e] += hk;
                 }
-                F2[ip][0] = pack2(f[0].x, f[1].x); F2[ip][1] = pack2(f[0].y, f[1].y);
-                F2[ip][2] = pack2(f[0].z, f[1].z); F2[ip][3] = pack2(f[0].w, f[1].w);
+#pragma unroll
+                for (int e = 0; e < kE; ++e) F2[ip][e] = pack2(f[0][e], f[1][e]);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kFusedUpdThreads) : "memory");
             NLMC_FUSED_MARK(6);
@@ -902,17 +931,18 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             asm volatile("bar.sync 1, %0;" ::"n"(kFusedUpdThreads) : "memory");
             NLMC_FUSED_MARK(7);
             const float *Jt = X;
-            float dmine[8][4];
+            if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == 64 + kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 63] = global_ns();
+            float dmine[8][kE];
             // The 16 sub-blocks in order.  Step s: its owners (8 lanes of warp s / 4) take the 8 decisions for their 4 replicas
             // each and publish the flips; every thread whose sub-block comes later applies them to its 8 x 4 fields (two FMA
             // chains of four, summed: the rounding of block_update_chain).  A coupling value is loaded once per 4 replicas, and
             // the corrections run as packed FFMA2 over pairs of sites.
             for (int s = 0; s < kFusedSub; ++s) {
-                const int vs = s >> 2;
+                const int vs = s / kE;
                 if (v < vs) break;                             // every sub-block of this warp is done
                 if (v == vs) {
-                    if (g == (s & 3)) {
-                        if (p.prof && b == 2 && blockIdx.x == 0 && q == 7) p.prof[p.n_blocks * 10 + 4 * s] = global_ns();
+                    if (g == s % kE) {
+                        if (p.prof && b == 2 && blockIdx.x == 0 && q == kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 4 * s] = global_ns();
                         // the couplings inside the sub-block (rows i = 0..6, pairs of columns) before the sequential part
                         f32x2 Jr[7][4];
 #pragma unroll
@@ -921,13 +951,16 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                             const ulonglong2 hi4 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * sb + i) * kBlk + 8 * sb + 4);
                             Jr[i][0] = lo.x; Jr[i][1] = lo.y; Jr[i][2] = hi4.x; Jr[i][3] = hi4.y;
                         }
+                        float T[8][kE];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) ld_e(tbuf + (8 * sb + i) * kFusedRep + kE * q, T[i]);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
+                            for (int e = 0; e < kE; ++e) {
                                 const float f = (i & 1) ? hi2(F2[i >> 1][e]) : lo2(F2[i >> 1][e]);
                                 const float sn = f > T[i][e] ? 1.0f : -1.0f;
-                                const float d = sn - so[i][e];
+                                const float d = sn - (((so_up >> (kE * i + e)) & 1u) ? 1.0f : -1.0f);
                                 dmine[i][e] = d;
                                 if (i < 7) {   // right-looking inside the sub-block; the pair that holds site i itself is updated too (its own half is dead)
                                     const f32x2 dd = pack2(d, d);
@@ -938,8 +971,8 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            *reinterpret_cast<float4 *>(dbuf + (8 * sb + i) * kFusedRep + 4 * q) = make_float4(dmine[i][0], dmine[i][1], dmine[i][2], dmine[i][3]);
-                        if (p.prof && b == 2 && blockIdx.x == 0 && q == 7) p.prof[p.n_blocks * 10 + 4 * s + 1] = global_ns() + (dmine[7][3] == 123.f);
+                            st_e(dbuf + (8 * sb + i) * kFusedRep + kE * q, dmine[i]);
+                        if (p.prof && b == 2 && blockIdx.x == 0 && q == kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 4 * s + 1] = global_ns() + (dmine[7][kE - 1] == 123.f);
                     }
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sub_done + s)) : "memory");
@@ -948,19 +981,19 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 }
                 if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == kFusedThreads - 1) p.prof[p.n_blocks * 10 + 4 * s + 2] = global_ns();
                 if (sb > s) {
-                    f32x2 C2[4][4];
+                    f32x2 C2[4][kE];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 dl = *reinterpret_cast<const float4 *>(dbuf + (8 * s + j) * kFusedRep + 4 * q);
-                        const float4 dh = *reinterpret_cast<const float4 *>(dbuf + (8 * s + 4 + j) * kFusedRep + 4 * q);
+                        float dlo[kE], dhi[kE];
+                        ld_e(dbuf + (8 * s + j) * kFusedRep + kE * q, dlo);
+                        ld_e(dbuf + (8 * s + 4 + j) * kFusedRep + kE * q, dhi);
                         const ulonglong2 l0 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s + j) * kBlk + 8 * sb);
                         const ulonglong2 l1 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s + j) * kBlk + 8 * sb + 4);
                         const ulonglong2 h0 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s + 4 + j) * kBlk + 8 * sb);
                         const ulonglong2 h1 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s + 4 + j) * kBlk + 8 * sb + 4);
                         const f32x2 Jl[4] = {l0.x, l0.y, l1.x, l1.y}, Jh[4] = {h0.x, h0.y, h1.x, h1.y};
-                        const float dlo[4] = {dl.x, dl.y, dl.z, dl.w}, dhi[4] = {dh.x, dh.y, dh.z, dh.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
+                        for (int e = 0; e < kE; ++e) {
                             const f32x2 ddl = pack2(dlo[e], dlo[e]), ddh = pack2(dhi[e], dhi[e]);
 #pragma unroll
                             for (int ip = 0; ip < 4; ++ip) {
@@ -972,23 +1005,23 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 #pragma unroll
                     for (int ip = 0; ip < 4; ++ip)
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) F2[ip][e] = add2(F2[ip][e], C2[ip][e]);
+                        for (int e = 0; e < kE; ++e) F2[ip][e] = add2(F2[ip][e], C2[ip][e]);
                     if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == kFusedThreads - 1) p.prof[p.n_blocks * 10 + 4 * s + 3] = global_ns() + (F2[0][0] == 123ull);
                 }
             }
             // new spins = old spins + flips, as bf16 (+1 = 0x3F80, -1 = 0xBF80; 0 past the end of J)
-            uint32_t bits[4][4];
+            uint32_t bits[kE][4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
+            for (int e = 0; e < kE; ++e)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float sn = so[i][e] + dmine[i][e];
+                    const float sn = (((so_up >> (kE * i + e)) & 1u) ? 1.0f : -1.0f) + dmine[i][e];
                     const uint32_t b16 = (8 * sb + i < k_end) ? (sn > 0.0f ? 0x3F80u : 0xBF80u) : 0u;
                     if ((i & 1) == 0) bits[e][i >> 1] = b16; else bits[e][i >> 1] |= b16 << 16;
                 }
             NLMC_FUSED_MARK(8);
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
+            for (int e = 0; e < kE; ++e)
                 *reinterpret_cast<uint4 *>(p.S + (size_t)(rq + e) * p.n_pad + c0 + 8 * sb) = make_uint4(bits[e][0], bits[e][1], bits[e][2], bits[e][3]);
             fence_proxy_async();                               // the spins are read by TMA (async proxy) in the next block
             NLMC_FUSED_MARK(9);
@@ -1090,7 +1123,7 @@ int nlmc_dense_destroy(nlmc_dense *D) {
                 const unsigned long long *x = &t[(size_t)nb * 10 + 4 * i];
                 fprintf(stderr, " %d: %.2f/%.2f %.2f/%.2f |", i, 1e-3 * (double)(x[0] - t[27]), 1e-3 * (double)(x[1] - t[27]), 1e-3 * (double)(x[2] - t[27]), 1e-3 * (double)(x[3] - t[27]));
             }
-            fprintf(stderr, "\n");
+            fprintf(stderr, "\n the owner of step 0 left the barrier at %.2f us\n", 1e-3 * (double)(t[(size_t)nb * 10 + 63] - t[27]));
         }
         cudaFree(D->fused_prof);
     }
