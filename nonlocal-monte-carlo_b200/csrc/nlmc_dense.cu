@@ -607,7 +607,7 @@ constexpr int kFusedStages = 2;
 constexpr size_t kFusedRingBytes = (size_t)kFusedStages * (1 + kMaxSplit) * kTileBytes;     // 128 KB
 constexpr size_t kFusedXBytes = sizeof(float) * kBlk * kBlk;                                // 64 KB: receive buffer / J_bb
 constexpr size_t kFusedDBytes = sizeof(float) * kBlk * kFusedRep;                           // 16 KB: flips d[site][replica]
-constexpr size_t kFusedSmemBytes = 1024 + kFusedRingBytes + kFusedXBytes + 2 * kFusedDBytes + 256;   // + thresholds [site][replica]
+constexpr size_t kFusedSmemBytes = 1024 + kFusedRingBytes + kFusedXBytes + kFusedDBytes + 512;
 static_assert(kFusedRep == 32, "one replica per lane");
 static_assert(kFusedCluster * kBlk * kFusedRep * sizeof(float) == kFusedXBytes, "receive buffer and J_bb share one region");
 
@@ -688,6 +688,17 @@ __device__ __forceinline__ void site_thresholds8(const uint16_t *S, const uint8_
     }
 }
 
+#define NLMC_TMEM_LD32(x, taddr)                                                                                           \
+    asm volatile(                                                                                                          \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                          \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                          \
+        : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(x[8]),      \
+          "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15]), "=r"(x[16]),           \
+          "=r"(x[17]), "=r"(x[18]), "=r"(x[19]), "=r"(x[20]), "=r"(x[21]), "=r"(x[22]), "=r"(x[23]), "=r"(x[24]),          \
+          "=r"(x[25]), "=r"(x[26]), "=r"(x[27]), "=r"(x[28]), "=r"(x[29]), "=r"(x[30]), "=r"(x[31])                        \
+        : "r"(taddr))
+
 __global__ void __cluster_dims__(kFusedCluster, 1, 1) __launch_bounds__(kFusedThreads, 1)
 dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b0,
                          const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
@@ -698,10 +709,11 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float *X = reinterpret_cast<float *>(smem + kFusedRingBytes);        // receive buffer [4][128][32]  /  Jt [128][128]
     float *dbuf = X + (size_t)kBlk * kBlk;                               // flips d[site of the block][replica]
-    float *tbuf = dbuf + (size_t)kBlk * kFusedRep;                       // thresholds T[site of the block][replica]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tbuf + (size_t)kBlk * kFusedRep);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dbuf + (size_t)kBlk * kFusedRep);
     uint64_t *full = bars, *empty = bars + kFusedStages, *tmem_full = bars + 2 * kFusedStages;
-    uint64_t *sub_done = bars + 2 * kFusedStages + 1;   // [16] one phase per block: the flips of sub-block s are published
+    uint64_t *adep = tmem_full + 1;                     // the new spins of a block are in the spin slots of the ring (one phase per block)
+    uint64_t *slots_free = adep + 1;                    // the tiles before the two spin-slot stages of the next block have been multiplied
+    uint64_t *sub_done = slots_free + 1;                // [16] one phase per block: the flips of sub-block s are published
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(sub_done + kFusedSub);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -709,11 +721,20 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int tile = blockIdx.x / kFusedCluster;
     const int m0 = tile * kBM;
-    // k-blocks rank, rank + 4, ...: the two k-blocks that hold the columns of a site block land on two different CTAs, so the
-    // part of the contraction that has to wait for the update is one k-block per CTA at most
-    const int kb_lo = (int)rank, kb_hi = p.kb_total;
-    const int n_kb = (p.kb_total - (int)rank + kFusedCluster - 1) / kFusedCluster;
     const int stage_bytes = (1 + p.n_split) * kTileBytes;
+    // Work list of this CTA for block b.  (i) its share of the contraction over the columns OUTSIDE block b-1: the k-blocks
+    // rank, rank + 4, ... without the two of block b-1; spins and couplings come by TMA and the partial sums of all 128
+    // replicas go to accumulator 0.  (ii) b > 0: BOTH k-blocks of block b-1, for its OWN 32 replicas only: the update
+    // threads write the new spins straight into the spin slot of the ring stage (the rows of the other replicas hold
+    // whatever was there: rows are independent), the couplings come by TMA, the result goes to accumulator 1 and is added
+    // to this CTA's own partial rows.  So nothing the update produces has to travel through global memory and TMA before
+    // the next block's fields are complete.
+    auto is_dep = [](int kb, int b) { return b > 0 && (kb >> 1) == b - 1; };   // kBlk / kBK == 2 k-blocks per site block
+    auto n_indep = [&](int b) {
+        int c = 0;
+        for (int kb = (int)rank; kb < p.kb_total; kb += kFusedCluster) c += is_dep(kb, b) ? 0 : 1;
+        return c;
+    };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -723,11 +744,13 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         if (lane == 0) {
             for (int s = 0; s < kFusedStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
             mbar_init(tmem_full, 1);
+            mbar_init(adep, kFusedUpdWarps);
+            mbar_init(slots_free, 1);
             for (int i = 0; i < kFusedSub; ++i) mbar_init(sub_done + i, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kBN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(2 * kBN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
@@ -738,41 +761,34 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     cluster_arrive();
     cluster_wait();
 
-    // the k-blocks of this CTA in the order they are loaded and multiplied for block b: those outside the columns of block
-    // b-1 first (they do not depend on the update of block b-1), the one or two inside last
-    auto is_dep = [](int kb, int b) { return b > 0 && (kb >> 1) == b - 1; };   // kBlk / kBK == 2 k-blocks per site block
-
     if (warp == 0) {  // ===== TMA producer =====
         const CUtensorMap *maps_b[kMaxSplit] = {&map_b0, &map_b1, &map_b2};
         uint32_t it = 0;
-        // part & 1: the coupling tiles (never depend on the update), part & 2: the spin tile
-        auto issue = [&](int kb, int b, uint32_t at, int part) {
-            const int s = (int)(at % kFusedStages);
-            const uint32_t ph = (at / kFusedStages) & 1u;
+        auto issue = [&](int kb, int b, bool with_spins) {
+            const int s = (int)(it % kFusedStages);
+            const uint32_t ph = (it / kFusedStages) & 1u;
             uint8_t *st = smem + (size_t)s * (1 + kMaxSplit) * kTileBytes;
-            if (part & 1) {
-                mbar_wait(empty + s, ph ^ 1u);
-                mbar_expect_tx(full + s, (uint32_t)stage_bytes);
-                for (int q = 0; q < p.n_split; ++q) tma_load_2d(st + (1 + q) * kTileBytes, maps_b[q], full + s, kb * kBK, b * kBlk);
-            }
-            if (part & 2) tma_load_2d(st, &map_a, full + s, kb * kBK, m0);
+            mbar_wait(empty + s, ph ^ 1u);
+            mbar_expect_tx(full + s, (uint32_t)(with_spins ? stage_bytes : stage_bytes - kTileBytes));
+            if (with_spins) tma_load_2d(st, &map_a, full + s, kb * kBK, m0);
+            for (int q = 0; q < p.n_split; ++q) tma_load_2d(st + (1 + q) * kTileBytes, maps_b[q], full + s, kb * kBK, b * kBlk);
+            ++it;
         };
         for (int b = 0; b < p.n_blocks; ++b) {
             if (b > 0) cluster_arrive();                       // U(b-1): nothing of ours to publish
-            uint32_t it_dep = it;
             if (lane == 0) {
-                for (int kb = kb_lo; kb < kb_hi; kb += kFusedCluster) if (!is_dep(kb, b)) issue(kb, b, it++, 3);
-                it_dep = it;
-                // the k-blocks inside the columns of block b-1: their coupling tiles now, their spin tiles after the barrier
-                for (int kb = kb_lo; kb < kb_hi; kb += kFusedCluster) if (is_dep(kb, b)) issue(kb, b, it++, 1);
+                fence_proxy_async();                           // spins stored by the update threads before the last barrier we passed
+                for (int kb = (int)rank; kb < p.kb_total; kb += kFusedCluster) if (!is_dep(kb, b)) issue(kb, b, true);
+#ifndef NLMC_FUSED_DEBUG_TMA_A
+                if (b > 0) { issue(2 * (b - 1), b, false); issue(2 * (b - 1) + 1, b, false); }
+#endif
             }
             __syncwarp();
-            if (b > 0) cluster_wait();                         // U(b-1): the spins of block b-1 are final
-            if (lane == 0) {
-                fence_proxy_async();
-                for (int kb = kb_lo; kb < kb_hi; kb += kFusedCluster) if (is_dep(kb, b)) issue(kb, b, it_dep++, 2);
-            }
+            if (b > 0) cluster_wait();
+#ifdef NLMC_FUSED_DEBUG_TMA_A
+            if (lane == 0 && b > 0) { fence_proxy_async(); issue(2 * (b - 1), b, true); issue(2 * (b - 1) + 1, b, true); }
             __syncwarp();
+#endif
             cluster_arrive();                                  // R(b)
             cluster_wait();
         }
@@ -781,32 +797,38 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     } else if (warp == 1) {  // ===== MMA issuer =====
         const uint32_t idesc = make_idesc_bf16(kBM, kBN);
         uint32_t it = 0;
+        auto multiply = [&](uint32_t acc, bool first) {
+            const int s = (int)(it % kFusedStages);
+            const uint32_t ph = (it / kFusedStages) & 1u;
+            mbar_wait(full + s, ph);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(smem + (size_t)s * (1 + kMaxSplit) * kTileBytes);
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+            for (int q = 0; q < p.n_split; ++q) {
+                const uint64_t b_desc = make_smem_desc_sw128(a_addr + (1 + q) * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)
+                    umma_bf16(acc, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (uint32_t)(!first || q != 0 || k != 0));
+            }
+            umma_commit(empty + s);
+            ++it;
+        };
         for (int b = 0; b < p.n_blocks; ++b) {
             if (b > 0) cluster_arrive();                       // U(b-1)
-            if (lane == 0 && n_kb > 0) {
+            if (lane == 0) {
                 tcgen05_fence_after();
-                int done = 0;
-                for (int pass = 0; pass < 2; ++pass)
-                    for (int kb = kb_lo; kb < kb_hi; kb += kFusedCluster) {
-                        if (is_dep(kb, b) != (pass == 1)) continue;
-                        const int s = (int)(it % kFusedStages);
-                        const uint32_t ph = (it / kFusedStages) & 1u;
-                        mbar_wait(full + s, ph);
-                        tcgen05_fence_after();
-                        const uint32_t a_addr = smem_u32(smem + (size_t)s * (1 + kMaxSplit) * kTileBytes);
-                        const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-                        for (int q = 0; q < p.n_split; ++q) {
-                            const uint64_t b_desc = make_smem_desc_sw128(a_addr + (1 + q) * kTileBytes);
-#pragma unroll
-                            for (int k = 0; k < kBK / 16; ++k)
-                                umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                                          (uint32_t)((done | q | k) != 0));
-                        }
-                        umma_commit(empty + s);
-                        ++it;
-                        ++done;
-                    }
-                umma_commit(tmem_full);
+                const int ni = n_indep(b);
+                for (int i = 0; i < ni; ++i) multiply(tmem_base, i == 0);
+                if (b > 0) {
+                    // Both ring stages are now free of spin tiles that are still to be read: the update threads of block b-1 may
+                    // write the new spins into them.  (A parity wait on `empty` from their side could be a whole phase early.)
+                    umma_commit(slots_free);
+                    mbar_wait(adep, (uint32_t)((b - 1) & 1));  // the new spins of block b-1 are in the spin slots of the next two stages
+                    tcgen05_fence_after();
+                    multiply(tmem_base + (uint32_t)kBN, true);
+                    multiply(tmem_base + (uint32_t)kBN, false);
+                }
+                if (ni > 0 || b > 0) umma_commit(tmem_full);
             }
             __syncwarp();
             if (b > 0) cluster_wait();                         // U(b-1)
@@ -821,30 +843,38 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         const int sb = kE * v + g;                             // the sub-block (sites 8 sb .. 8 sb + 7 of every block) this thread owns
         const int ut = (int)threadIdx.x - 64;
         const int rq = m0 + (int)rank * kFusedRep + kE * q;    // its kE replicas
-        float beta4[kE];
+        float beta_e[kE];
 #pragma unroll
-        for (int e = 0; e < kE; ++e) beta4[e] = p.beta[rq + e];
+        for (int e = 0; e < kE; ++e) beta_e[e] = p.beta[rq + e];
         const uint32_t sweep = *p.sweep_ptr;
-        for (int b = 0; b < p.n_blocks; ++b) {
+        // thresholds of the thread's 8 sites x kE replicas and their old spins as one bit each (a site past the end of J counts
+        // as -1: its threshold is +inf, so it "stays" -1, its flip is 0 and its couplings are 0)
+        float T[8][kE];
+        uint32_t so_up = 0u;   // bit kE i + e: site i of replica e is +1
+        auto thresholds = [&](int b, float (&Tn)[8][kE], uint32_t &up) {
+            up = 0u;
             const int c0 = b * kBlk;
             const int k_end = min(kBlk, p.n - c0);
-            NLMC_FUSED_MARK(0);
-            // fields of the thread's 8 sites x 4 replicas as packed pairs over the SITES: F2[ip][e] = (F[2 ip][e], F[2 ip + 1][e])
-            // Thresholds go to shared memory until the thread's own decisions (they would hold 32 registers through every
-            // propagation before them); the old spins stay as one bit each (a site past the end of J counts as -1: its
-            // threshold is +inf, so it "stays" -1, its flip is 0 and its couplings are 0).
-            uint32_t so_up = 0u;   // bit kE i + e: site i of replica e is +1
-            f32x2 F2[4][kE];
 #pragma unroll
             for (int e = 0; e < kE; ++e) {
                 float t8[8], s8[8];
-                site_thresholds8(p.S, p.modes, p.n_pad, rq + e, c0, sb, k_end, beta4[e], p.seed_lo, p.seed_hi, sweep, p.temp_x, t8, s8);
+                site_thresholds8(p.S, p.modes, p.n_pad, rq + e, c0, sb, k_end, beta_e[e], p.seed_lo, p.seed_hi, sweep, p.temp_x, t8, s8);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    tbuf[(8 * sb + i) * kFusedRep + kE * q + e] = t8[i];
-                    so_up |= (s8[i] > 0.0f ? 1u : 0u) << (kE * i + e);
+                    Tn[i][e] = t8[i];
+                    up |= (s8[i] > 0.0f ? 1u : 0u) << (kE * i + e);
                 }
             }
+        };
+        thresholds(0, T, so_up);
+        uint32_t it_next = 0;      // ring iteration at which the NEXT block starts (the producer's count)
+        uint32_t tf_phase = 0;     // completed phases of tmem_full
+        for (int b = 0; b < p.n_blocks; ++b) {
+            const int c0 = b * kBlk;
+            const int k_end = min(kBlk, p.n - c0);
+            const int ni = n_indep(b);
+            it_next += (uint32_t)(ni + (b > 0 ? 2 : 0));
+            NLMC_FUSED_MARK(0);
             NLMC_FUSED_MARK(1);
             if (b > 0) cluster_wait();                         // U(b-1): every CTA is done with its J_bb, the receive buffers are free
             NLMC_FUSED_MARK(2);
@@ -854,8 +884,9 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 const uint32_t local = smem_u32(X) + (uint32_t)(((int)rank * kBlk) * kFusedRep + lane) * 4u;
                 uint32_t dst;
                 asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(local), "r"((uint32_t)quarter));
-                if (n_kb > 0) {
-                    mbar_wait(tmem_full, (uint32_t)(b & 1));
+                if (ni > 0 || b > 0) {
+                    mbar_wait(tmem_full, tf_phase & 1u);
+                    ++tf_phase;
                     tcgen05_fence_after();
                 }
                 NLMC_FUSED_MARK(3);
@@ -863,17 +894,9 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 #pragma unroll 1
                 for (int c = (v >> 2) * kColsPerWarp; c < ((v >> 2) + 1) * kColsPerWarp; c += 32) {
                     uint32_t x[32];
-                    if (n_kb > 0) {
-                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c;
-                        asm volatile(
-                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                            : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]),
-                              "=r"(x[8]), "=r"(x[9]), "=r"(x[10]), "=r"(x[11]), "=r"(x[12]), "=r"(x[13]), "=r"(x[14]), "=r"(x[15]),
-                              "=r"(x[16]), "=r"(x[17]), "=r"(x[18]), "=r"(x[19]), "=r"(x[20]), "=r"(x[21]), "=r"(x[22]), "=r"(x[23]),
-                              "=r"(x[24]), "=r"(x[25]), "=r"(x[26]), "=r"(x[27]), "=r"(x[28]), "=r"(x[29]), "=r"(x[30]), "=r"(x[31])
-                            : "r"(taddr));
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c;
+                    if (ni > 0) {
+                        NLMC_TMEM_LD32(x, taddr);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     } else {
 #pragma unroll
@@ -881,6 +904,13 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                     }
                     // site c + j of this replica: the 32 lanes of the warp write 128 contiguous bytes
                     if ((uint32_t)quarter == rank) {
+                        if (b > 0) {   // this CTA's own replicas: add the part contracted from the spin slots (accumulator 1)
+                            uint32_t y[32];
+                            NLMC_TMEM_LD32(y, taddr + (uint32_t)kBN);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) x[j] = __float_as_uint(__uint_as_float(x[j]) + __uint_as_float(y[j]));
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             asm volatile("st.shared.b32 [%0], %1;" ::"r"(local + (uint32_t)((c + j) * kFusedRep * 4)), "r"(x[j]) : "memory");
@@ -896,6 +926,8 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             cluster_arrive();                                  // R(b): the partial fields are in their owners' buffers
             cluster_wait();
             NLMC_FUSED_MARK(5);
+            // fields of the thread's 8 sites x kE replicas as packed pairs over the SITES: F2[ip][e] = (F[2 ip][e], F[2 ip + 1][e])
+            f32x2 F2[4][kE];
 #pragma unroll
             for (int ip = 0; ip < 4; ++ip) {
                 float f[2][kE];
@@ -932,11 +964,17 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             NLMC_FUSED_MARK(7);
             const float *Jt = X;
             if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == 64 + kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 63] = global_ns();
+            // The thresholds of the NEXT block are computed in the shadow of the chain: before it by the warps that have to wait
+            // for the first sub-blocks anyway, after their own sub-blocks by the first warp (which opens the chain).
+            float Tn[8][kE];
+            uint32_t so_up_n = 0u;
+            const bool more = b + 1 < p.n_blocks;
+            if (more && v > 0) thresholds(b + 1, Tn, so_up_n);
             float dmine[8][kE];
-            // The 16 sub-blocks in order.  Step s: its owners (8 lanes of warp s / 4) take the 8 decisions for their 4 replicas
-            // each and publish the flips; every thread whose sub-block comes later applies them to its 8 x 4 fields (two FMA
-            // chains of four, summed: the rounding of block_update_chain).  A coupling value is loaded once per 4 replicas, and
-            // the corrections run as packed FFMA2 over pairs of sites.
+            // The 16 sub-blocks in order.  Step s: its owners (kLanesPerSub lanes of warp s / kE) take the 8 decisions for their
+            // kE replicas each and publish the flips; every thread whose sub-block comes later applies them to its 8 x kE fields
+            // (two FMA chains of four, summed: the rounding of block_update_chain).  A coupling value is loaded once per kE
+            // replicas, and the corrections run as packed FFMA2 over pairs of sites.
             for (int s = 0; s < kFusedSub; ++s) {
                 const int vs = s / kE;
                 if (v < vs) break;                             // every sub-block of this warp is done
@@ -951,9 +989,6 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                             const ulonglong2 hi4 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * sb + i) * kBlk + 8 * sb + 4);
                             Jr[i][0] = lo.x; Jr[i][1] = lo.y; Jr[i][2] = hi4.x; Jr[i][3] = hi4.y;
                         }
-                        float T[8][kE];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) ld_e(tbuf + (8 * sb + i) * kFusedRep + kE * q, T[i]);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
 #pragma unroll
@@ -970,8 +1005,7 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                             }
                         }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            st_e(dbuf + (8 * sb + i) * kFusedRep + kE * q, dmine[i]);
+                        for (int i = 0; i < 8; ++i) st_e(dbuf + (8 * sb + i) * kFusedRep + kE * q, dmine[i]);
                         if (p.prof && b == 2 && blockIdx.x == 0 && q == kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 4 * s + 1] = global_ns() + (dmine[7][kE - 1] == 123.f);
                     }
                     __syncwarp();
@@ -1020,10 +1054,43 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                     if ((i & 1) == 0) bits[e][i >> 1] = b16; else bits[e][i >> 1] |= b16 << 16;
                 }
             NLMC_FUSED_MARK(8);
+            if (more) {
+                // the thread's 8 sites are one 16-byte chunk of a spin row of k-block sb / 8 of this block: into the spin slot of the
+                // ring stage that will hold that k-block for block b+1 (128-byte swizzle: chunk index XOR row % 8)
+                const uint32_t it_d = it_next + (uint32_t)n_indep(b + 1) + (uint32_t)(sb >> 3);
+                const int st = (int)(it_d % kFusedStages);
+                mbar_wait(slots_free, (uint32_t)(b & 1));   // the stages' previous tiles have been multiplied
+                uint8_t *slot = smem + (size_t)st * (1 + kMaxSplit) * kTileBytes;
+#ifndef NLMC_FUSED_DEBUG_TMA_A
+#pragma unroll
+#endif
+                for (int e = 0; e < (
+#ifdef NLMC_FUSED_DEBUG_TMA_A
+                    0
+#else
+                    kE
+#endif
+                    ); ++e) {
+                    const int row = (int)rank * kFusedRep + kE * q + e;
+                    *reinterpret_cast<uint4 *>(slot + (row >> 3) * 1024 + (row & 7) * 128 + (((sb & 7) ^ (row & 7)) << 4)) =
+                        make_uint4(bits[e][0], bits[e][1], bits[e][2], bits[e][3]);
+                }
+                fence_proxy_async();                           // generic stores -> read by the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(adep)) : "memory");
+            }
 #pragma unroll
             for (int e = 0; e < kE; ++e)
                 *reinterpret_cast<uint4 *>(p.S + (size_t)(rq + e) * p.n_pad + c0 + 8 * sb) = make_uint4(bits[e][0], bits[e][1], bits[e][2], bits[e][3]);
-            fence_proxy_async();                               // the spins are read by TMA (async proxy) in the next block
+            fence_proxy_async();                               // the spins are read by TMA (async proxy) in later blocks
+            if (more && v == 0) thresholds(b + 1, Tn, so_up_n);
+            if (more) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int e = 0; e < kE; ++e) T[i][e] = Tn[i][e];
+                so_up = so_up_n;
+            }
             NLMC_FUSED_MARK(9);
             cluster_arrive();                                  // U(b)
         }
@@ -1033,7 +1100,7 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kBN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * kBN) : "memory");
     }
 }
 

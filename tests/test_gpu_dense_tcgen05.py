@@ -247,3 +247,42 @@ def test_cold_tail_no_spurious_flips():
         d.sweep(100)
         assert np.all(d.get_spins() == 1)
     d.close()
+
+
+@pytest.mark.parametrize("n,R,with_field,modes", [(64, 128, False, False), (130, 64, True, False), (300, 200, True, True),
+                                                  (520, 130, False, False), (1000, 384, False, True)])
+def test_cluster_sweep_equals_launch_chain(nl, monkeypatch, n, R, with_field, modes):
+    """The one-launch cluster sweep (dense_fused_sweep_kernel: split-K over a cluster of 4 CTAs, partial fields through
+    distributed shared memory, the contraction over the block just updated from spins that never leave shared memory) against
+    the GEMM -> update chain of launches.  Same thresholds and random stream; only the summation order of the fields differs,
+    so after ONE sweep from the same state a spin differs only where its field is within rounding of its threshold (and what
+    follows from such a flip): >= 99.9 % of all spins and nearly every replica row must be identical -- a wrong tile, a stale
+    spin or a lost partial sum would move several per cent.  Sizes cover n below and across 128-site blocks, a ragged last
+    block, padded replica tiles, fewer k-blocks than CTAs in the cluster, external fields and NMC site modes."""
+    J, h = gaussian_instance(n, n + 1, with_field=with_field)
+    prob = nl.host.Problem(J, h)
+    rs = np.random.RandomState(5)
+    betas = np.linspace(0.3, 2.5, R)
+    s0 = rs.choice([-1, 1], size=(R, n)).astype(np.int8)
+    md = rs.choice([0, 1, 2], size=(R, n), p=[0.8, 0.1, 0.1]).astype(np.uint8) if modes else None
+    out = {}
+    for name, flag in (("chain", "0"), ("cluster", "1")):
+        monkeypatch.setenv("NLMC_DENSE_FUSED", flag)
+        d = nl.lib.Dense(prob.inst, betas, n_split=3, seed=11)
+        d.set_spins(s0)
+        if modes:
+            d.set_site_modes(md, temp_x=3.0)
+        d.sweep(1)
+        d.sync()
+        out[name] = d.get_spins()
+        d.sweep(3)
+        d.sync()
+        out[name + "_E"] = d.energies()
+        d.close()
+    same = out["chain"] == out["cluster"]
+    assert same.mean() >= 0.999, same.mean()
+    assert same.all(axis=1).mean() >= 0.97, same.all(axis=1).mean()
+    if modes:   # frozen sites never move on either path
+        assert np.array_equal(out["cluster"][md == 2], s0[md == 2])
+    # four sweeps on: replicas that never met a rounding tie have identical energies; the rest stay statistically alike
+    assert (np.abs(out["chain_E"] - out["cluster_E"]) < 1e-6 * n).mean() >= 0.9

@@ -39,6 +39,10 @@ for name, flag, ks in (("chain", "0", None), ("chain_ksplit4", "0", "4"), ("fuse
 print("moved by the first sweep:", float((out["chain"]["s1"] != s0).mean()), float((out["fused"]["s1"] != s0).mean()),
       "chain vs chain_ksplit4 after 1 sweep:", float((out["chain"]["s1"] == out["chain_ksplit4"]["s1"]).mean()),
       "E equal after 31:", float((out["chain"]["E"] == out["chain_ksplit4"]["E"]).mean()), float((out["chain"]["E"] == out["fused"]["E"]).mean()))
+per_block = [(float((out["chain"]["s1"][:, c:c + 128] == out["fused"]["s1"][:, c:c + 128]).mean())) for c in range(0, N, 128)]
+print("agreement per block of 128 sites:", [round(x, 4) for x in per_block])
+per_rep = (out["chain"]["s1"] == out["fused"]["s1"]).mean(axis=1)
+print("agreement per replica (first 40):", [round(float(x), 3) for x in per_rep[:40]])
 agree = float((out["chain"]["s1"] == out["fused"]["s1"]).mean())
 rows_equal = float((out["chain"]["s1"] == out["fused"]["s1"]).all(axis=1).mean())
 dE = out["chain"]["E"] - out["fused"]["E"]
