@@ -572,25 +572,32 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
 // Replicas are independent, so a tile of 128 replicas never has to wait for another tile: a CLUSTER of 4 CTAs owns one
 // tile for the whole sweep and synchronises only with itself (two cluster barriers per block of sites; no launch
 // boundaries, no global atomics, no field matrix in global memory).  33 clusters of 4 are co-resident on a B200 (15 of 8:
-// tools/micro/cluster_occupancy.cu), and 4 x 32 replicas puts one replica on every lane of a warp.  Per block of 128 sites:
-//   G  CTA c contracts its quarter of K (k-blocks c, c + 4, c + 8, ...) for all 128 replicas of the tile:
-//      TMA -> 2-stage smem ring -> tcgen05.mma into a 128 x 128 fp32 TMEM accumulator (warp 0: producer, warp 1: issuer);
-//   R  warps 2-5 read the accumulator (tcgen05.ld: a warp holds the 32 replicas of ONE owner CTA) and PUSH the partial
-//      fields into the owner's receive buffer [source CTA][site][replica] with st.shared::cluster (128-byte runs);
-//      cluster barrier; every update thread adds the 4 partial values and h for its 8 sites;
-//   U  the sequential chain over the 128 sites.  Update warp w (2..17 -> w = 0..15) OWNS the sites 8w..8w+7 of the block
-//      for all 32 replicas of the CTA, lane = replica, their fields in registers.  It first applies the flips of the
-//      sub-blocks before it (d[s][8][32] in shared memory, published by their owners through a flag; couplings as
-//      broadcast loads from the staged J_bb), then takes its own 8 decisions one after the other with the right-looking
-//      corrections inside the sub-block, publishes its flips and writes its spins.  The critical path per sub-block is
-//      one propagation plus 8 decisions of ONE warp; the propagations into later sub-blocks run beside it.
-//      Same thresholds, same random stream and the same order of the floating-point corrections as
-//      dense_block_update_kernel: given equal fields the two paths take identical decisions.
-// The producer runs ahead: the operand tiles of block b+1 that do not touch the columns of block b (all but two k-blocks of
-// one CTA) are loaded and multiplied WHILE block b is being updated; only the two k-blocks of block b's own columns wait
-// for the barrier after the update (the spins are written with generic stores and read by TMA: fence.proxy.async on both
-// sides of the barrier).  The 64 KB receive buffer and the staged coupling block J_bb share one region: pushes for block
-// b+1 can only happen after every CTA of the cluster has finished the update of block b.
+// tools/micro/cluster_occupancy.cu), and 4 x 32 replicas gives every CTA one warp's worth of replicas.  Per block b of 128 sites:
+//   G  the contraction, in two parts.  (i) Columns outside block b-1: CTA c takes the k-blocks c, c + 4, ... for all 128
+//      replicas of the tile -- TMA -> 2-stage smem ring -> tcgen05.mma into TMEM accumulator 0 (warp 0: producer, warp 1:
+//      issuer).  None of it depends on the update of block b-1, so it is loaded and multiplied WHILE block b-1 is being
+//      updated.  (ii) The two k-blocks of block b-1 itself, for the CTA's OWN 32 replicas: the update threads write the new
+//      spins (bf16, 128-byte swizzle) straight into the spin slot of the ring stage that already holds the coupling tiles,
+//      and the product goes to accumulator 1 (rows of other replicas hold whatever was in the slot: rows are independent
+//      and never read).  Nothing the update produces travels through global memory and TMA before the fields are complete.
+//   R  the update warps read the accumulators (tcgen05.ld: the warps of lane quarter k hold the 32 replicas of CTA k) and
+//      PUSH the partial fields into the owner's receive buffer [source CTA][site][replica] with st.shared::cluster
+//      (128-byte runs; the own quarter adds accumulator 1 and stores locally); cluster barrier; every update thread adds
+//      the 4 partial values and h for its sites.
+//   U  the sequential chain over the 128 sites.  An update thread owns ONE sub-block of 8 sites for kE replicas (fields in
+//      registers, packed in pairs of sites); a warp holds kE sub-blocks x 32 / kE replica groups.  Step s = 0..15: the
+//      owners of sub-block s take its 8 decisions one after the other with the right-looking corrections inside the
+//      sub-block and publish the flips d[s][8][32] (mbarrier per sub-block); every thread whose sub-block comes later
+//      applies them (couplings as quarter-warp broadcast loads from the staged J_bb, FFMA2).  Same thresholds, same random
+//      stream and the same order of the floating-point corrections as dense_block_update_kernel: given equal fields the
+//      two paths take identical decisions (tests/test_gpu_dense_tcgen05.py::test_cluster_sweep_equals_launch_chain).
+//      The thresholds of block b+1 (Philox + logits) are computed in the shadow of the chain.
+// The new spins also go to global memory (generic stores, fence.proxy.async, cluster barrier U) for the TMA loads of later
+// blocks.  The 64 KB receive buffer and the staged coupling block J_bb share one region: pushes for block b+1 can only
+// happen after every CTA of the cluster has finished the update of block b.
+// Measured at C3 size (N = 2000, 2048 replicas = 16 clusters on 64 SMs): 0.238 ms per sweep against 0.353 ms for the chain of
+// launches; per block 14.2 us = chain 9.4 + drain / push / barrier 2.5 + partial sums 0.4 + staging J_bb 0.6 + stores 0.7
+// (NLMC_DENSE_FUSED_PROF=1 prints these; profiles/r2d_dense_fused_summary.md).
 constexpr int kFusedCluster = 4;
 constexpr int kFusedRep = kBM / kFusedCluster;             // 32 replicas per CTA = the lanes of a warp
 constexpr int kFusedSub = kBlk / 8;                        // 16 sub-blocks of 8 sites
@@ -779,16 +786,10 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             if (lane == 0) {
                 fence_proxy_async();                           // spins stored by the update threads before the last barrier we passed
                 for (int kb = (int)rank; kb < p.kb_total; kb += kFusedCluster) if (!is_dep(kb, b)) issue(kb, b, true);
-#ifndef NLMC_FUSED_DEBUG_TMA_A
-                if (b > 0) { issue(2 * (b - 1), b, false); issue(2 * (b - 1) + 1, b, false); }
-#endif
+                if (b > 0) { issue(2 * (b - 1), b, false); issue(2 * (b - 1) + 1, b, false); }   // couplings only: the spins come from the update threads
             }
             __syncwarp();
             if (b > 0) cluster_wait();
-#ifdef NLMC_FUSED_DEBUG_TMA_A
-            if (lane == 0 && b > 0) { fence_proxy_async(); issue(2 * (b - 1), b, true); issue(2 * (b - 1) + 1, b, true); }
-            __syncwarp();
-#endif
             cluster_arrive();                                  // R(b)
             cluster_wait();
         }
@@ -964,12 +965,12 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             NLMC_FUSED_MARK(7);
             const float *Jt = X;
             if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == 64 + kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 63] = global_ns();
-            // The thresholds of the NEXT block are computed in the shadow of the chain: before it by the warps that have to wait
-            // for the first sub-blocks anyway, after their own sub-blocks by the first warp (which opens the chain).
+            // The thresholds of the NEXT block are computed in the shadow of the chain: by the last warp before it (it is on the
+            // critical path only at the very end), by the others once their own sub-blocks are decided.
             float Tn[8][kE];
             uint32_t so_up_n = 0u;
             const bool more = b + 1 < p.n_blocks;
-            if (more && v > 0) thresholds(b + 1, Tn, so_up_n);
+            if (more && v == kFusedUpdWarps - 1) thresholds(b + 1, Tn, so_up_n);
             float dmine[8][kE];
             // The 16 sub-blocks in order.  Step s: its owners (kLanesPerSub lanes of warp s / kE) take the 8 decisions for their
             // kE replicas each and publish the flips; every thread whose sub-block comes later applies them to its 8 x kE fields
@@ -1061,29 +1062,23 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 const int st = (int)(it_d % kFusedStages);
                 mbar_wait(slots_free, (uint32_t)(b & 1));   // the stages' previous tiles have been multiplied
                 uint8_t *slot = smem + (size_t)st * (1 + kMaxSplit) * kTileBytes;
-#ifndef NLMC_FUSED_DEBUG_TMA_A
 #pragma unroll
-#endif
-                for (int e = 0; e < (
-#ifdef NLMC_FUSED_DEBUG_TMA_A
-                    0
-#else
-                    kE
-#endif
-                    ); ++e) {
+                for (int e = 0; e < kE; ++e) {
                     const int row = (int)rank * kFusedRep + kE * q + e;
                     *reinterpret_cast<uint4 *>(slot + (row >> 3) * 1024 + (row & 7) * 128 + (((sb & 7) ^ (row & 7)) << 4)) =
                         make_uint4(bits[e][0], bits[e][1], bits[e][2], bits[e][3]);
                 }
-                fence_proxy_async();                           // generic stores -> read by the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(adep)) : "memory");
             }
 #pragma unroll
             for (int e = 0; e < kE; ++e)
                 *reinterpret_cast<uint4 *>(p.S + (size_t)(rq + e) * p.n_pad + c0 + 8 * sb) = make_uint4(bits[e][0], bits[e][1], bits[e][2], bits[e][3]);
-            fence_proxy_async();                               // the spins are read by TMA (async proxy) in later blocks
-            if (more && v == 0) thresholds(b + 1, Tn, so_up_n);
+            // one proxy fence for both: the spin slots are read by the tensor core, the global rows by TMA in later blocks
+            fence_proxy_async();
+            if (more) {
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(adep)) : "memory");
+            }
+            if (more && v != kFusedUpdWarps - 1) thresholds(b + 1, Tn, so_up_n);
             if (more) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
