@@ -953,8 +953,10 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             asm volatile("bar.sync 1, %0;" ::"n"(kFusedUpdThreads) : "memory");
             NLMC_FUSED_MARK(6);
             // J_bb transposed into the region the receive buffer occupied
+            // (row j is read at the columns of its own sub-block and of the later ones only: about half of the 64 KB)
             for (int i = ut; i < kBlk * kBlk / 4; i += kFusedUpdThreads) {
                 const int j = i / (kBlk / 4), k4 = i % (kBlk / 4);
+                if (4 * k4 < (j & ~7)) continue;
                 const uint32_t dj = smem_u32(reinterpret_cast<float4 *>(X) + i);
                 const float *src = p.Jf + (size_t)(c0 + j) * p.n_pad + c0 + k4 * 4;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dj), "l"(src) : "memory");
@@ -990,13 +992,23 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                             const ulonglong2 hi4 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * sb + i) * kBlk + 8 * sb + 4);
                             Jr[i][0] = lo.x; Jr[i][1] = lo.y; Jr[i][2] = hi4.x; Jr[i][3] = hi4.y;
                         }
+                        // the flip of a site is one of two values known beforehand: (+1 - s_old) if its field clears the threshold,
+                        // (-1 - s_old) otherwise -- compare, select, FFMA2 is the whole dependent chain of a decision
+                        float dup[8][kE], ddn[8][kE];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+#pragma unroll
+                            for (int e = 0; e < kE; ++e) {
+                                const bool up = ((so_up >> (kE * i + e)) & 1u) != 0u;
+                                dup[i][e] = up ? 0.0f : 2.0f;
+                                ddn[i][e] = up ? -2.0f : 0.0f;
+                            }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
 #pragma unroll
                             for (int e = 0; e < kE; ++e) {
                                 const float f = (i & 1) ? hi2(F2[i >> 1][e]) : lo2(F2[i >> 1][e]);
-                                const float sn = f > T[i][e] ? 1.0f : -1.0f;
-                                const float d = sn - (((so_up >> (kE * i + e)) & 1u) ? 1.0f : -1.0f);
+                                const float d = f > T[i][e] ? dup[i][e] : ddn[i][e];
                                 dmine[i][e] = d;
                                 if (i < 7) {   // right-looking inside the sub-block; the pair that holds site i itself is updated too (its own half is dead)
                                     const f32x2 dd = pack2(d, d);
