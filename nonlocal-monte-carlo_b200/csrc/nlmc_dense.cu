@@ -601,12 +601,23 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
 constexpr int kFusedCluster = 4;
 constexpr int kFusedRep = kBM / kFusedCluster;             // 32 replicas per CTA = the lanes of a warp
 constexpr int kFusedSub = kBlk / 8;                        // 16 sub-blocks of 8 sites
+#ifndef NLMC_FUSED_H
+#define NLMC_FUSED_H 1
+#endif
+// sub-blocks per update thread (1 or 2): its tile is 8 kH sites x kE replicas.  Measured at C3 size: kH = 1, kE = 2 (8 update
+// warps) 0.234 ms per sweep; kH = 2, kE = 2 (4 warps, the flips of a thread's first sub-block enter its second without a
+// hand-off) 0.244 ms -- the chain gets shorter (8.5 vs 9.1 us per block) but the 4 warps stage J_bb and store more slowly;
+// kH = 1, kE = 4 (4 warps) 0.265 ms.
+constexpr int kH = NLMC_FUSED_H;
+constexpr int kTiles = kFusedSub / kH;                     // steps of the chain per block
+static_assert(kH == 1 || kH == 2, "one or two sub-blocks of 8 sites per thread");
 #ifndef NLMC_FUSED_E
 #define NLMC_FUSED_E 2
 #endif
 constexpr int kE = NLMC_FUSED_E;                           // replicas per update thread (2 or 4): a thread's tile is 8 sites x kE replicas
-constexpr int kLanesPerSub = 32 / kE;                      // lanes that share a sub-block; a warp holds kE sub-blocks
-constexpr int kFusedUpdWarps = kFusedSub / kE;
+constexpr int kLanesPerSub = 32 / kE;                      // lanes that share a tile of sites; a warp holds kE tiles
+constexpr int kFusedUpdWarps = kTiles / kE;
+static_assert(kFusedUpdWarps % 4 == 0, "the update warps cover the four TMEM lane quarters evenly");
 static_assert(kE == 2 || kE == 4, "thread tile of 8 sites x 2 or 4 replicas");
 constexpr int kFusedUpdThreads = 32 * kFusedUpdWarps;      // 128
 constexpr int kFusedThreads = 64 + kFusedUpdThreads;       // + producer warp + MMA warp
@@ -838,32 +849,35 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         }
         cluster_arrive();                                      // U(last)
         cluster_wait();
-    } else {  // ===== update warps: thread = (sub-block kE v + lane / kLanesPerSub, replicas kE (lane % kLanesPerSub) .. + kE - 1); they also drain =====
+    } else {  // ===== update warps: thread = (tile kE v + lane / kLanesPerSub of 8 kH sites, replicas kE (lane % kLanesPerSub) .. + kE - 1); they also drain =====
         const int v = warp - 2;
         const int g = lane / kLanesPerSub, q = lane % kLanesPerSub;
-        const int sb = kE * v + g;                             // the sub-block (sites 8 sb .. 8 sb + 7 of every block) this thread owns
+        const int tb = kE * v + g;                             // the tile (sub-blocks kH tb .. kH tb + kH - 1 of every block) this thread owns
         const int ut = (int)threadIdx.x - 64;
         const int rq = m0 + (int)rank * kFusedRep + kE * q;    // its kE replicas
         float beta_e[kE];
 #pragma unroll
         for (int e = 0; e < kE; ++e) beta_e[e] = p.beta[rq + e];
         const uint32_t sweep = *p.sweep_ptr;
-        // thresholds of the thread's 8 sites x kE replicas and their old spins as one bit each (a site past the end of J counts
+        // thresholds of the thread's sites x kE replicas and their old spins as one bit each (a site past the end of J counts
         // as -1: its threshold is +inf, so it "stays" -1, its flip is 0 and its couplings are 0)
-        float T[8][kE];
-        uint32_t so_up = 0u;   // bit kE i + e: site i of replica e is +1
-        auto thresholds = [&](int b, float (&Tn)[8][kE], uint32_t &up) {
-            up = 0u;
+        float T[kH][8][kE];
+        uint32_t so_up[kH];   // bit kE i + e: site i of replica e is +1
+        auto thresholds = [&](int b, float (&Tn)[kH][8][kE], uint32_t (&up)[kH]) {
             const int c0 = b * kBlk;
             const int k_end = min(kBlk, p.n - c0);
 #pragma unroll
-            for (int e = 0; e < kE; ++e) {
-                float t8[8], s8[8];
-                site_thresholds8(p.S, p.modes, p.n_pad, rq + e, c0, sb, k_end, beta_e[e], p.seed_lo, p.seed_hi, sweep, p.temp_x, t8, s8);
+            for (int h = 0; h < kH; ++h) {
+                up[h] = 0u;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    Tn[i][e] = t8[i];
-                    up |= (s8[i] > 0.0f ? 1u : 0u) << (kE * i + e);
+                for (int e = 0; e < kE; ++e) {
+                    float t8[8], s8[8];
+                    site_thresholds8(p.S, p.modes, p.n_pad, rq + e, c0, kH * tb + h, k_end, beta_e[e], p.seed_lo, p.seed_hi, sweep, p.temp_x, t8, s8);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        Tn[h][i][e] = t8[i];
+                        up[h] |= (s8[i] > 0.0f ? 1u : 0u) << (kE * i + e);
+                    }
                 }
             }
         };
@@ -927,29 +941,31 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             cluster_arrive();                                  // R(b): the partial fields are in their owners' buffers
             cluster_wait();
             NLMC_FUSED_MARK(5);
-            // fields of the thread's 8 sites x kE replicas as packed pairs over the SITES: F2[ip][e] = (F[2 ip][e], F[2 ip + 1][e])
-            f32x2 F2[4][kE];
+            // fields of the thread's sites x kE replicas as packed pairs over the SITES: F2[h][ip][e] = (F[2 ip][e], F[2 ip + 1][e]) of sub-block kH tb + h
+            f32x2 F2[kH][4][kE];
 #pragma unroll
-            for (int ip = 0; ip < 4; ++ip) {
-                float f[2][kE];
+            for (int h = 0; h < kH; ++h)
 #pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                    const int i = 2 * ip + h2;
-                    ld_e(X + (0 * kBlk + 8 * sb + i) * kFusedRep + kE * q, f[h2]);
+                for (int ip = 0; ip < 4; ++ip) {
+                    float f[2][kE];
 #pragma unroll
-                    for (int src = 1; src < kFusedCluster; ++src) {
-                        float t[kE];
-                        ld_e(X + (src * kBlk + 8 * sb + i) * kFusedRep + kE * q, t);
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int site = 8 * (kH * tb + h) + 2 * ip + h2;
+                        ld_e(X + (0 * kBlk + site) * kFusedRep + kE * q, f[h2]);
 #pragma unroll
-                        for (int e = 0; e < kE; ++e) f[h2][e] += t[e];
+                        for (int src = 1; src < kFusedCluster; ++src) {
+                            float t[kE];
+                            ld_e(X + (src * kBlk + site) * kFusedRep + kE * q, t);
+#pragma unroll
+                            for (int e = 0; e < kE; ++e) f[h2][e] += t[e];
+                        }
+                        const float hk = p.hf[c0 + site];
+#pragma unroll
+                        for (int e = 0; e < kE; ++e) f[h2][e] += hk;
                     }
-                    const float hk = p.hf[c0 + 8 * sb + i];
 #pragma unroll
-                    for (int e = 0; e < kE; ++e) f[h2][e] += hk;
+                    for (int e = 0; e < kE; ++e) F2[h][ip][e] = pack2(f[0][e], f[1][e]);
                 }
-#pragma unroll
-                for (int e = 0; e < kE; ++e) F2[ip][e] = pack2(f[0][e], f[1][e]);
-            }
             asm volatile("bar.sync 1, %0;" ::"n"(kFusedUpdThreads) : "memory");
             NLMC_FUSED_MARK(6);
             // J_bb transposed into the region the receive buffer occupied
@@ -969,57 +985,99 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == 64 + kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 63] = global_ns();
             // The thresholds of the NEXT block are computed in the shadow of the chain: by the last warp before it (it is on the
             // critical path only at the very end), by the others once their own sub-blocks are decided.
-            float Tn[8][kE];
-            uint32_t so_up_n = 0u;
+            float Tn[kH][8][kE];
+            uint32_t so_up_n[kH];
             const bool more = b + 1 < p.n_blocks;
             if (more && v == kFusedUpdWarps - 1) thresholds(b + 1, Tn, so_up_n);
-            float dmine[8][kE];
-            // The 16 sub-blocks in order.  Step s: its owners (kLanesPerSub lanes of warp s / kE) take the 8 decisions for their
-            // kE replicas each and publish the flips; every thread whose sub-block comes later applies them to its 8 x kE fields
-            // (two FMA chains of four, summed: the rounding of block_update_chain).  A coupling value is loaded once per kE
-            // replicas, and the corrections run as packed FFMA2 over pairs of sites.
-            for (int s = 0; s < kFusedSub; ++s) {
+            float dmine[kH][8][kE];
+            // the flips dl (sites 0..3) / dh (sites 4..7) of sub-block s8 applied to the 8 x kE fields Fh of sub-block my8: two FMA
+            // chains of four, summed (the rounding of block_update_chain); a coupling value is loaded once per kE replicas,
+            // packed FFMA2 over pairs of sites
+            auto apply = [&](int s8, int my8, const float (&dl)[4][kE], const float (&dh)[4][kE], f32x2 (&Fh)[4][kE]) {
+                f32x2 C2[4][kE];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const ulonglong2 l0 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s8 + j) * kBlk + 8 * my8);
+                    const ulonglong2 l1 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s8 + j) * kBlk + 8 * my8 + 4);
+                    const ulonglong2 h0 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s8 + 4 + j) * kBlk + 8 * my8);
+                    const ulonglong2 h1 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s8 + 4 + j) * kBlk + 8 * my8 + 4);
+                    const f32x2 Jl[4] = {l0.x, l0.y, l1.x, l1.y}, Jh[4] = {h0.x, h0.y, h1.x, h1.y};
+#pragma unroll
+                    for (int e = 0; e < kE; ++e) {
+                        const f32x2 ddl = pack2(dl[j][e], dl[j][e]), ddh = pack2(dh[j][e], dh[j][e]);
+#pragma unroll
+                        for (int ip = 0; ip < 4; ++ip) {
+                            Fh[ip][e] = fma2(Jl[ip], ddl, Fh[ip][e]);
+                            C2[ip][e] = j == 0 ? mul2(Jh[ip], ddh) : fma2(Jh[ip], ddh, C2[ip][e]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int ip = 0; ip < 4; ++ip)
+#pragma unroll
+                    for (int e = 0; e < kE; ++e) Fh[ip][e] = add2(Fh[ip][e], C2[ip][e]);
+            };
+            // the 8 decisions of sub-block my8, one after the other, right-looking inside the sub-block
+            auto decide = [&](int my8, f32x2 (&Fh)[4][kE], const float (&Th)[8][kE], uint32_t up_bits, float (&dm)[8][kE]) {
+                // the couplings inside the sub-block (rows i = 0..6, pairs of columns) before the sequential part
+                f32x2 Jr[7][4];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    const ulonglong2 lo = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * my8 + i) * kBlk + 8 * my8);
+                    const ulonglong2 hi4 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * my8 + i) * kBlk + 8 * my8 + 4);
+                    Jr[i][0] = lo.x; Jr[i][1] = lo.y; Jr[i][2] = hi4.x; Jr[i][3] = hi4.y;
+                }
+                // the flip of a site is one of two values known beforehand: (+1 - s_old) if its field clears the threshold,
+                // (-1 - s_old) otherwise -- compare, select, FFMA2 is the whole dependent chain of a decision
+                float dup[8][kE], ddn[8][kE];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int e = 0; e < kE; ++e) {
+                        const bool up = ((up_bits >> (kE * i + e)) & 1u) != 0u;
+                        dup[i][e] = up ? 0.0f : 2.0f;
+                        ddn[i][e] = up ? -2.0f : 0.0f;
+                    }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                    for (int e = 0; e < kE; ++e) {
+                        const float f = (i & 1) ? hi2(Fh[i >> 1][e]) : lo2(Fh[i >> 1][e]);
+                        const float d = f > Th[i][e] ? dup[i][e] : ddn[i][e];
+                        dm[i][e] = d;
+                        if (i < 7) {   // the pair that holds site i itself is updated too (its own half is dead)
+                            const f32x2 dd = pack2(d, d);
+#pragma unroll
+                            for (int ip = (i + 1) >> 1; ip < 4; ++ip) Fh[ip][e] = fma2(Jr[i][ip], dd, Fh[ip][e]);
+                        }
+                    }
+                }
+            };
+            // The tiles in order.  Step s: the owners of tile s (kLanesPerSub lanes of warp s / kE) decide its sub-blocks -- the
+            // flips of the first go into the fields of the second without leaving the thread -- and publish the flips; every
+            // thread whose tile comes later applies them.
+            for (int s = 0; s < kTiles; ++s) {
                 const int vs = s / kE;
-                if (v < vs) break;                             // every sub-block of this warp is done
+                if (v < vs) break;                             // every tile of this warp is done
                 if (v == vs) {
                     if (g == s % kE) {
                         if (p.prof && b == 2 && blockIdx.x == 0 && q == kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 4 * s] = global_ns();
-                        // the couplings inside the sub-block (rows i = 0..6, pairs of columns) before the sequential part
-                        f32x2 Jr[7][4];
 #pragma unroll
-                        for (int i = 0; i < 7; ++i) {
-                            const ulonglong2 lo = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * sb + i) * kBlk + 8 * sb);
-                            const ulonglong2 hi4 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * sb + i) * kBlk + 8 * sb + 4);
-                            Jr[i][0] = lo.x; Jr[i][1] = lo.y; Jr[i][2] = hi4.x; Jr[i][3] = hi4.y;
-                        }
-                        // the flip of a site is one of two values known beforehand: (+1 - s_old) if its field clears the threshold,
-                        // (-1 - s_old) otherwise -- compare, select, FFMA2 is the whole dependent chain of a decision
-                        float dup[8][kE], ddn[8][kE];
+                        for (int h = 0; h < kH; ++h) {
+                            decide(kH * tb + h, F2[h], T[h], so_up[h], dmine[h]);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
+                            for (int i = 0; i < 8; ++i) st_e(dbuf + (8 * (kH * tb + h) + i) * kFusedRep + kE * q, dmine[h][i]);
 #pragma unroll
-                            for (int e = 0; e < kE; ++e) {
-                                const bool up = ((so_up >> (kE * i + e)) & 1u) != 0u;
-                                dup[i][e] = up ? 0.0f : 2.0f;
-                                ddn[i][e] = up ? -2.0f : 0.0f;
-                            }
+                            for (int h2 = h + 1; h2 < kH; ++h2) {
+                                float dl[4][kE], dh[4][kE];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
+                                for (int j = 0; j < 4; ++j)
 #pragma unroll
-                            for (int e = 0; e < kE; ++e) {
-                                const float f = (i & 1) ? hi2(F2[i >> 1][e]) : lo2(F2[i >> 1][e]);
-                                const float d = f > T[i][e] ? dup[i][e] : ddn[i][e];
-                                dmine[i][e] = d;
-                                if (i < 7) {   // right-looking inside the sub-block; the pair that holds site i itself is updated too (its own half is dead)
-                                    const f32x2 dd = pack2(d, d);
-#pragma unroll
-                                    for (int ip = (i + 1) >> 1; ip < 4; ++ip) F2[ip][e] = fma2(Jr[i][ip], dd, F2[ip][e]);
-                                }
+                                    for (int e = 0; e < kE; ++e) { dl[j][e] = dmine[h][j][e]; dh[j][e] = dmine[h][4 + j][e]; }
+                                apply(kH * tb + h, kH * tb + h2, dl, dh, F2[h2]);
                             }
                         }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) st_e(dbuf + (8 * sb + i) * kFusedRep + kE * q, dmine[i]);
-                        if (p.prof && b == 2 && blockIdx.x == 0 && q == kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 4 * s + 1] = global_ns() + (dmine[7][kE - 1] == 123.f);
+                        if (p.prof && b == 2 && blockIdx.x == 0 && q == kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 4 * s + 1] = global_ns() + (dmine[kH - 1][7][kE - 1] == 123.f);
                     }
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sub_done + s)) : "memory");
@@ -1027,63 +1085,59 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                     mbar_wait(sub_done + s, (uint32_t)(b & 1));    // hardware wait, no polling traffic on the shared-memory pipe
                 }
                 if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == kFusedThreads - 1) p.prof[p.n_blocks * 10 + 4 * s + 2] = global_ns();
-                if (sb > s) {
-                    f32x2 C2[4][kE];
+                if (tb > s) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float dlo[kE], dhi[kE];
-                        ld_e(dbuf + (8 * s + j) * kFusedRep + kE * q, dlo);
-                        ld_e(dbuf + (8 * s + 4 + j) * kFusedRep + kE * q, dhi);
-                        const ulonglong2 l0 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s + j) * kBlk + 8 * sb);
-                        const ulonglong2 l1 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s + j) * kBlk + 8 * sb + 4);
-                        const ulonglong2 h0 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s + 4 + j) * kBlk + 8 * sb);
-                        const ulonglong2 h1 = *reinterpret_cast<const ulonglong2 *>(Jt + (8 * s + 4 + j) * kBlk + 8 * sb + 4);
-                        const f32x2 Jl[4] = {l0.x, l0.y, l1.x, l1.y}, Jh[4] = {h0.x, h0.y, h1.x, h1.y};
+                    for (int hs = 0; hs < kH; ++hs) {
+                        const int s8 = kH * s + hs;
+                        float dl[4][kE], dh[4][kE];
 #pragma unroll
-                        for (int e = 0; e < kE; ++e) {
-                            const f32x2 ddl = pack2(dlo[e], dlo[e]), ddh = pack2(dhi[e], dhi[e]);
-#pragma unroll
-                            for (int ip = 0; ip < 4; ++ip) {
-                                F2[ip][e] = fma2(Jl[ip], ddl, F2[ip][e]);
-                                C2[ip][e] = j == 0 ? mul2(Jh[ip], ddh) : fma2(Jh[ip], ddh, C2[ip][e]);
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            ld_e(dbuf + (8 * s8 + j) * kFusedRep + kE * q, dl[j]);
+                            ld_e(dbuf + (8 * s8 + 4 + j) * kFusedRep + kE * q, dh[j]);
                         }
+#pragma unroll
+                        for (int h = 0; h < kH; ++h) apply(s8, kH * tb + h, dl, dh, F2[h]);
                     }
-#pragma unroll
-                    for (int ip = 0; ip < 4; ++ip)
-#pragma unroll
-                        for (int e = 0; e < kE; ++e) F2[ip][e] = add2(F2[ip][e], C2[ip][e]);
-                    if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == kFusedThreads - 1) p.prof[p.n_blocks * 10 + 4 * s + 3] = global_ns() + (F2[0][0] == 123ull);
+                    if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == kFusedThreads - 1) p.prof[p.n_blocks * 10 + 4 * s + 3] = global_ns() + (F2[0][0][0] == 123ull);
                 }
             }
             // new spins = old spins + flips, as bf16 (+1 = 0x3F80, -1 = 0xBF80; 0 past the end of J)
-            uint32_t bits[kE][4];
+            uint32_t bits[kH][kE][4];
 #pragma unroll
-            for (int e = 0; e < kE; ++e)
+            for (int h = 0; h < kH; ++h)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float sn = (((so_up >> (kE * i + e)) & 1u) ? 1.0f : -1.0f) + dmine[i][e];
-                    const uint32_t b16 = (8 * sb + i < k_end) ? (sn > 0.0f ? 0x3F80u : 0xBF80u) : 0u;
-                    if ((i & 1) == 0) bits[e][i >> 1] = b16; else bits[e][i >> 1] |= b16 << 16;
-                }
+                for (int e = 0; e < kE; ++e)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float sn = (((so_up[h] >> (kE * i + e)) & 1u) ? 1.0f : -1.0f) + dmine[h][i][e];
+                        const uint32_t b16 = (8 * (kH * tb + h) + i < k_end) ? (sn > 0.0f ? 0x3F80u : 0xBF80u) : 0u;
+                        if ((i & 1) == 0) bits[h][e][i >> 1] = b16; else bits[h][e][i >> 1] |= b16 << 16;
+                    }
             NLMC_FUSED_MARK(8);
             if (more) {
-                // the thread's 8 sites are one 16-byte chunk of a spin row of k-block sb / 8 of this block: into the spin slot of the
+                // a sub-block's 8 sites are one 16-byte chunk of a spin row of k-block sb / 8 of this block: into the spin slot of the
                 // ring stage that will hold that k-block for block b+1 (128-byte swizzle: chunk index XOR row % 8)
-                const uint32_t it_d = it_next + (uint32_t)n_indep(b + 1) + (uint32_t)(sb >> 3);
-                const int st = (int)(it_d % kFusedStages);
                 mbar_wait(slots_free, (uint32_t)(b & 1));   // the stages' previous tiles have been multiplied
-                uint8_t *slot = smem + (size_t)st * (1 + kMaxSplit) * kTileBytes;
+                const uint32_t it_d0 = it_next + (uint32_t)n_indep(b + 1);
 #pragma unroll
-                for (int e = 0; e < kE; ++e) {
-                    const int row = (int)rank * kFusedRep + kE * q + e;
-                    *reinterpret_cast<uint4 *>(slot + (row >> 3) * 1024 + (row & 7) * 128 + (((sb & 7) ^ (row & 7)) << 4)) =
-                        make_uint4(bits[e][0], bits[e][1], bits[e][2], bits[e][3]);
+                for (int h = 0; h < kH; ++h) {
+                    const int sb = kH * tb + h;
+                    const int st = (int)((it_d0 + (uint32_t)(sb >> 3)) % kFusedStages);
+                    uint8_t *slot = smem + (size_t)st * (1 + kMaxSplit) * kTileBytes;
+#pragma unroll
+                    for (int e = 0; e < kE; ++e) {
+                        const int row = (int)rank * kFusedRep + kE * q + e;
+                        *reinterpret_cast<uint4 *>(slot + (row >> 3) * 1024 + (row & 7) * 128 + (((sb & 7) ^ (row & 7)) << 4)) =
+                            make_uint4(bits[h][e][0], bits[h][e][1], bits[h][e][2], bits[h][e][3]);
+                    }
                 }
             }
 #pragma unroll
-            for (int e = 0; e < kE; ++e)
-                *reinterpret_cast<uint4 *>(p.S + (size_t)(rq + e) * p.n_pad + c0 + 8 * sb) = make_uint4(bits[e][0], bits[e][1], bits[e][2], bits[e][3]);
+            for (int h = 0; h < kH; ++h)
+#pragma unroll
+                for (int e = 0; e < kE; ++e)
+                    *reinterpret_cast<uint4 *>(p.S + (size_t)(rq + e) * p.n_pad + c0 + 8 * (kH * tb + h)) =
+                        make_uint4(bits[h][e][0], bits[h][e][1], bits[h][e][2], bits[h][e][3]);
             // one proxy fence for both: the spin slots are read by the tensor core, the global rows by TMA in later blocks
             fence_proxy_async();
             if (more) {
@@ -1093,10 +1147,13 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             if (more && v != kFusedUpdWarps - 1) thresholds(b + 1, Tn, so_up_n);
             if (more) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int h = 0; h < kH; ++h) {
 #pragma unroll
-                    for (int e = 0; e < kE; ++e) T[i][e] = Tn[i][e];
-                so_up = so_up_n;
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int e = 0; e < kE; ++e) T[h][i][e] = Tn[h][i][e];
+                    so_up[h] = so_up_n[h];
+                }
             }
             NLMC_FUSED_MARK(9);
             cluster_arrive();                                  // U(b)
