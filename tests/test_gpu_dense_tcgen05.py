@@ -286,3 +286,25 @@ def test_cluster_sweep_equals_launch_chain(nl, monkeypatch, n, R, with_field, mo
         assert np.array_equal(out["cluster"][md == 2], s0[md == 2])
     # four sweeps on: replicas that never met a rounding tie have identical energies; the rest stay statistically alike
     assert (np.abs(out["chain_E"] - out["cluster_E"]) < 1e-6 * n).mean() >= 0.9
+
+
+def test_cluster_sweep_is_reproducible(nl, monkeypatch):
+    """The cluster sweep has no atomics and a fixed summation order: two handles with the same seed and start state must agree
+    bit for bit after several sweeps (the chain of launches, with its atomic split-K reduction, does not).  A race between the
+    producer, the tensor core and the update threads on the ring stages, the receive buffers or the flip buffer would show here."""
+    monkeypatch.setenv("NLMC_DENSE_FUSED", "1")
+    J, h = gaussian_instance(900, 17, with_field=True)
+    prob = nl.host.Problem(J, h)
+    R = 640
+    betas = np.linspace(0.2, 3.0, R)
+    s0 = np.random.RandomState(3).choice([-1, 1], size=(R, 900)).astype(np.int8)
+    outs = []
+    for _ in range(3):
+        d = nl.lib.Dense(prob.inst, betas, n_split=3, seed=21)
+        d.set_spins(s0)
+        d.sweep(6)
+        d.sync()
+        outs.append(d.get_spins())
+        d.close()
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert (outs[0] != s0).mean() > 0.2
