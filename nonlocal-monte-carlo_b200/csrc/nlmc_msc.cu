@@ -212,11 +212,14 @@ __device__ __forceinline__ uint32_t comp(const uint4 &v, int k) { return k == 0 
 // A lane that lost its column to another word simply waits for the straggler loop.  Every random bit is still used by
 // at most one lane, chosen by the past only, so the draw stays exact.
 template <int kSteps, bool kPerBit, int kMerged, bool kOdd, bool kClamp = false>
+// CTAs of 256 threads per SM.  5 (47-48 registers) measured 1.6-2.1 % faster than 4 (56-60 registers) on the quad-major layout
+// in all three forms -- C5 sweep 0.2906 -> 0.2859 ms, label form 0.3137 -> 0.3072, 4-slot block 0.0441 -> 0.0434, identical
+// trajectories (profiles/r2d_occupancy_ab.log); the label form and the odd-degree classes spill 12-24 bytes at 48 registers.
 #ifndef NLMC_PERBIT_CTAS
-#define NLMC_PERBIT_CTAS 4
+#define NLMC_PERBIT_CTAS 5
 #endif
 #ifndef NLMC_SCALAR_CTAS
-#define NLMC_SCALAR_CTAS 4
+#define NLMC_SCALAR_CTAS 5
 #endif
 #ifndef NLMC_SWEEP_THREADS
 #define NLMC_SWEEP_THREADS 256
