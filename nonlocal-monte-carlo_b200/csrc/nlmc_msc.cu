@@ -28,6 +28,13 @@
 #include "nlmc_common.cuh"
 #include "nlmc_hostpar.h"
 
+// comparison steps of the merged round (4 or 8: one or two Philox calls), see msc_sweep_kernel.  8 measured slower: C5 sweep
+// 0.2932 vs 0.2859 ms, label form 0.3399 vs 0.3073, 4-slot block 0.0482 vs 0.0434 (the second Philox call and its four steps
+// cost more than the shorter straggler loop saves)
+#ifndef NLMC_MERGED_STEPS
+#define NLMC_MERGED_STEPS 4
+#endif
+
 struct nlmc_msc {
     nlmc_instance *inst = nullptr;
     int n = 0, W = 0, n_beta = 0, n_ladders = 0, G = 0, n_colours = 0;
@@ -73,7 +80,7 @@ struct nlmc_msc {
     struct RecGraph { int ladder; bool has_M, has_E; int n_sweeps_T; cudaGraphExec_t exec; };
     std::vector<RecGraph> rec_graphs;  // one recorded sweep (sweep + unpack + energies + slot bump), replayed per sweep
     int k_steps = 5;  // unconditional bit steps of the Bernoulli comparison (tuning knob NLMC_MSC_STEPS)
-    int k_merged = 4; // further steps on the four words of a thread merged into one (0 or 4; NLMC_MSC_MERGED)
+    int k_merged = NLMC_MERGED_STEPS; // further steps on the four words of a thread merged into one (0 or NLMC_MERGED_STEPS; NLMC_MSC_MERGED)
     struct RoundGraph { int n_sweeps, pairs; bool with_energy_swap; cudaGraphExec_t exec; };
     std::vector<RoundGraph> graphs;  // whole rounds captured once per (n_sweeps, pairs) and replayed
     bool use_graphs = true;
@@ -356,10 +363,12 @@ __device__ __forceinline__ void msc_sweep_site(const MscDev &a, const MscThr &th
             J3 = (adv[0] & I3[0]) | (adv[1] & I3[1]) | (adv[2] & I3[2]) | (adv[3] & I3[3]);
         }
         const uint4 r4 = rng((uint32_t)site, sid, sweep, 16u);
+        uint4 r4b = r4;
+        if (kMerged > 4) r4b = rng((uint32_t)site, sid, sweep, 17u);   // steps 5..8 of the merged round
 #pragma unroll
         for (int q = 0; q < kMerged; ++q) {
             const int p = kSteps + q;
-            const uint32_t r = comp(r4, q & 3);
+            const uint32_t r = comp(q < 4 ? r4 : r4b, q & 3);
             if ((nzmask >> p) & 1u) {
                 uint32_t t;
                 if (kPerBit) {
@@ -929,17 +938,17 @@ static void launch_colour(const nlmc_msc *M, const MscDev &d, const MscThr &t, i
     const int flag = (pdl ? 1 : 0) | (trigger ? 2 : 0);  // bit 0: wait for the launch before, bit 1: let the next one start early
     auto go = [&](auto kernel) { launch_maybe_pdl(kernel, blocks, dim3(kT), M->stream, pdl, d, t, first, cnt, ctr, sweep_in_batch, flag); };
     if (M->label_mode) {
-        if (M->k_merged) { if (odd) go(msc_sweep_kernel<kSteps, true, 4, true>); else go(msc_sweep_kernel<kSteps, true, 4, false>); }
+        if (M->k_merged) { if (odd) go(msc_sweep_kernel<kSteps, true, NLMC_MERGED_STEPS, true>); else go(msc_sweep_kernel<kSteps, true, NLMC_MERGED_STEPS, false>); }
         else { if (odd) go(msc_sweep_kernel<kSteps, true, 0, true>); else go(msc_sweep_kernel<kSteps, true, 0, false>); }
     } else {
-        if (M->k_merged) { if (odd) go(msc_sweep_kernel<kSteps, false, 4, true>); else go(msc_sweep_kernel<kSteps, false, 4, false>); }
+        if (M->k_merged) { if (odd) go(msc_sweep_kernel<kSteps, false, NLMC_MERGED_STEPS, true>); else go(msc_sweep_kernel<kSteps, false, NLMC_MERGED_STEPS, false>); }
         else { if (odd) go(msc_sweep_kernel<kSteps, false, 0, true>); else go(msc_sweep_kernel<kSteps, false, 0, false>); }
     }
 }
 
 // NLMC_MSC_BATCH = 1 selects the cooperative batch kernel (measured slower, see msc_sweep_batch_kernel; default off).
 static bool batch_mode(const nlmc_msc *M) {
-    if (M->k_steps != 5 || M->k_merged != 4) return false;
+    if (M->k_steps != 5 || M->k_merged != NLMC_MERGED_STEPS) return false;
     if ((int)M->classes.size() > kMaxClasses) return false;
     if (const char *e = getenv("NLMC_MSC_BATCH")) return atoi(e) != 0;
     return M->batch_default;
@@ -953,7 +962,7 @@ static int launch_sweep_batch(nlmc_msc *M, const MscDev &d, const MscThr &t, int
         cl.first[cl.n] = c.first; cl.count[cl.n] = c.count; cl.odd[cl.n] = c.odd; ++cl.n;
     }
     if (cl.n == 0) return NLMC_OK;
-    void *kernel = M->label_mode ? (void *)msc_sweep_batch_kernel<5, true, 4> : (void *)msc_sweep_batch_kernel<5, false, 4>;
+    void *kernel = M->label_mode ? (void *)msc_sweep_batch_kernel<5, true, NLMC_MERGED_STEPS> : (void *)msc_sweep_batch_kernel<5, false, NLMC_MERGED_STEPS>;
     if (M->batch_ctas == 0) {   // co-resident CTAs of this kernel on this device, once per handle
         int per_sm = 0, sms = 0, dev = 0;
         NLMC_CUDA(cudaGetDevice(&dev));
@@ -1323,7 +1332,7 @@ static int msc_create_impl(nlmc_instance *I, int n_beta, const double *betas, in
     M->slot_begin = betas_total ? slot_begin : 0;
     if (const char *e = getenv("NLMC_MSC_STEPS")) M->k_steps = atoi(e);
     if (M->k_steps != 4 && M->k_steps != 6 && M->k_steps != 7 && M->k_steps != 8) M->k_steps = 5;
-    if (const char *e = getenv("NLMC_MSC_MERGED")) M->k_merged = atoi(e) ? 4 : 0;
+    if (const char *e = getenv("NLMC_MSC_MERGED")) M->k_merged = atoi(e) ? NLMC_MERGED_STEPS : 0;
     if (const char *e = getenv("NLMC_MSC_GRAPHS")) M->use_graphs = atoi(e) != 0;
     const std::vector<uint32_t> thr = nlmc::msc_thresholds(n_beta, betas);
     M->h_thr = thr;
