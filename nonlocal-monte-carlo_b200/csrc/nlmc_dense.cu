@@ -36,8 +36,8 @@ constexpr int kTileBytes = kBM * kBK * 2;  // one 128 x 64 bf16 tile = 16 KiB (A
 constexpr int kGemmThreads = 192;
 // shared memory of the GEMM with kSt ring stages: 3 for the stand-alone contraction (192 KB), 2 inside the sweep, where a
 // GEMM CTA must fit on an SM next to a CTA of the block-update kernel it overlaps with (128 KB + 87 KB)
-__host__ __device__ constexpr size_t gemm_smem_bytes(int stages) {
-    return (size_t)stages * (1 + kMaxSplit) * kTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+__host__ __device__ constexpr size_t gemm_smem_bytes(int stages, int wide = 1) {   // wide = 2: 128 x 256 output tiles (B tiles of 256 rows)
+    return (size_t)stages * (1 + kMaxSplit * wide) * kTileBytes + 1024 /*align*/ + 256 /*barriers*/;
 }
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -101,20 +101,26 @@ struct GemmParams {
     int accumulate;  // 1: red.add into C^T (split-K or accumulate), 0: plain store
 };
 
-template <int kStages>
+// kWide = 2: 128 x 256 output tiles.  A 128 x 128 x 16 MMA reads 4 KB + 4 KB of operands from shared memory for 64 cycles of
+// tensor work -- exactly the 128 B/clk of the shared-memory port --, a 128 x 256 x 16 one reads 4 + 8 KB for 128 cycles (96 B/clk):
+// the wide tile is what lets the tensor pipe run ahead of its operand supply.  Used by the stand-alone contraction when the
+// column count is a multiple of 256 (2 ring stages of 112 KB).
+template <int kStages, int kWide = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b0,
                     const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
                     GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int stage_bytes = (1 + p.n_split) * kTileBytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)kStages * (1 + kMaxSplit) * kTileBytes);
+    constexpr int kBNt = kBN * kWide;                                   // columns of the output tile
+    constexpr size_t kStageBytes = (size_t)(1 + kMaxSplit * kWide) * kTileBytes;
+    const int stage_bytes = (1 + p.n_split * kWide) * kTileBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)kStages * kStageBytes);
     uint64_t *full = bars, *empty = bars + kStages, *tmem_full = bars + 2 * kStages;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = (blockIdx.x + p.m_tile_base) * kBM, n0 = p.n_base + blockIdx.y * kBN;
+    const int m0 = (blockIdx.x + p.m_tile_base) * kBM, n0 = p.n_base + blockIdx.y * kBNt;
     const int kb_per = (p.k_blocks_total + p.k_splits - 1) / p.k_splits;
     const int kb_begin = blockIdx.z * kb_per, kb_end = min(p.k_blocks_total, kb_begin + kb_per);
     const int n_kb = kb_end - kb_begin;
@@ -130,7 +136,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kBN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kBNt) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
@@ -152,27 +158,29 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int s = i % kStages;
                 const uint32_t ph = (uint32_t)(i / kStages) & 1u;
                 mbar_wait(empty + s, ph ^ 1u);
-                uint8_t *st = smem + (size_t)s * (1 + kMaxSplit) * kTileBytes;
+                uint8_t *st = smem + (size_t)s * kStageBytes;
                 mbar_expect_tx(full + s, (uint32_t)stage_bytes);
                 int kb = kb_begin + i;
                 if (kb >= p.skip_begin) kb += p.skip_count;
                 const int k0 = (p.kb_offset + kb) * kBK;
                 tma_load_2d(st, &map_a, full + s, k0, m0);
-                for (int q = 0; q < p.n_split; ++q) tma_load_2d(st + (1 + q) * kTileBytes, maps_b[q], full + s, k0, n0);
+                for (int q = 0; q < p.n_split; ++q)   // a piece of B: kWide boxes of 128 rows, back to back (rows 128 B apart)
+                    for (int w = 0; w < kWide; ++w)
+                        tma_load_2d(st + (size_t)(1 + q * kWide + w) * kTileBytes, maps_b[q], full + s, k0, n0 + w * kBN);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer (single thread) =====
-            const uint32_t idesc = make_idesc_bf16(kBM, kBN);
+            const uint32_t idesc = make_idesc_bf16(kBM, kBNt);
             for (int i = 0; i < n_kb; ++i) {
                 const int s = i % kStages;
                 const uint32_t ph = (uint32_t)(i / kStages) & 1u;
                 mbar_wait(full + s, ph);
                 tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * (1 + kMaxSplit) * kTileBytes);
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * kStageBytes);
                 const uint64_t a_desc = make_smem_desc_sw128(a_addr);
                 for (int q = 0; q < p.n_split; ++q) {
-                    const uint64_t b_desc = make_smem_desc_sw128(a_addr + (1 + q) * kTileBytes);
+                    const uint64_t b_desc = make_smem_desc_sw128(a_addr + (uint32_t)((1 + q * kWide) * kTileBytes));
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle atom
                         umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
@@ -189,7 +197,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tcgen05_fence_after();
         const int m = m0 + row;
 #pragma unroll 1
-        for (int c = 0; c < kBN; c += 32) {
+        for (int c = 0; c < kBNt; c += 32) {
             uint32_t v[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c;
             asm volatile(
@@ -219,7 +227,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kBN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kBNt) : "memory");
     }
 }
 
@@ -344,6 +352,15 @@ static int launch_fields_part(nlmc_dense *D, cudaStream_t st, int col0, int n_co
     if (m_tiles <= 0) m_tiles = D->R_pad / kBM - m_tile_base;
     if (p.accumulate && clear)
         NLMC_CUDA(cudaMemsetAsync(D->Ht + (size_t)col0 * D->R_pad, 0, sizeof(float) * (size_t)(p.N - col0) * D->R_pad, st));
+    // stand-alone contraction over a multiple of 256 columns: 128 x 256 tiles (NLMC_DENSE_WIDE=0 keeps the 128 x 128 ones)
+    static const bool wide_ok = [] { const char *e = getenv("NLMC_DENSE_WIDE"); return e ? atoi(e) != 0 : true; }();
+    if (wide_ok && stages == 3 && !pdl && n_cols % (2 * kBN) == 0 && col0 % (2 * kBN) == 0 && p.N == col0 + n_cols) {
+        const dim3 wgrid((unsigned)m_tiles, (unsigned)(n_cols / (2 * kBN)), (unsigned)p.k_splits);
+        gemm_bf16_tn_kernel<2, 2><<<wgrid, kGemmThreads, gemm_smem_bytes(2, 2), st>>>(
+            D->map_S, D->map_J[0], D->map_J[D->n_split > 1 ? 1 : 0], D->map_J[D->n_split > 2 ? 2 : 0], p);
+        NLMC_CUDA(cudaGetLastError());
+        return NLMC_OK;
+    }
     const dim3 grid((unsigned)m_tiles, (unsigned)((n_cols + kBN - 1) / kBN), (unsigned)p.k_splits);
     if (stages == 2)
         NLMC_CUDA(launch_pdl(gemm_bf16_tn_kernel<2>, grid, dim3(kGemmThreads), gemm_smem_bytes(2), st, pdl, D->map_S, D->map_J[0],
@@ -1352,6 +1369,7 @@ int nlmc_dense_create(nlmc_instance *I, int n_replicas, const double *betas, int
     if (!rc) {
         if (cudaFuncSetAttribute(gemm_bf16_tn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(3)) != cudaSuccess ||
             cudaFuncSetAttribute(gemm_bf16_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_bf16_tn_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2, 2)) != cudaSuccess ||
             cudaFuncSetAttribute(dense_block_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(kMaxRepPerCta)) != cudaSuccess ||
             cudaFuncSetAttribute(dense_fused_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes) != cudaSuccess) {
             set_error("nlmc_dense_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
