@@ -105,7 +105,12 @@ struct GemmParams {
 // tensor work -- exactly the 128 B/clk of the shared-memory port --, a 128 x 256 x 16 one reads 4 + 8 KB for 128 cycles (96 B/clk):
 // the wide tile is what lets the tensor pipe run ahead of its operand supply.  Used by the stand-alone contraction when the
 // column count is a multiple of 256 (2 ring stages of 112 KB).
-template <int kStages, int kWide = 1>
+// kPair (experiment, off by default): launched as clusters of 2 CTAs along M.  The two CTAs need the same B tiles, so each loads
+// half of them (one of the two 128-row boxes of every piece) and TMA MULTICASTS it into both shared memories: the L2 -> SM
+// traffic of B (470 MB per C3 contraction at ~10 TB/s) halves.  A ring stage may be refilled once BOTH CTAs have multiplied it,
+// so the MMA threads commit to the `empty` barrier of both CTAs (multicast commit, count 2).  Correct, but not faster: every SM
+// still takes in 112 KB per k-block, and that is the bound (see launch_fields_part).
+template <int kStages, int kWide = 1, bool kPair = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b0,
                     const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
@@ -120,6 +125,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t pair_rank = 0;
+    if (kPair) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(pair_rank));
     const int m0 = (blockIdx.x + p.m_tile_base) * kBM, n0 = p.n_base + blockIdx.y * kBNt;
     const int kb_per = (p.k_blocks_total + p.k_splits - 1) / p.k_splits;
     const int kb_begin = blockIdx.z * kb_per, kb_end = min(p.k_blocks_total, kb_begin + kb_per);
@@ -131,7 +138,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+            for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kPair ? 2 : 1); }
             mbar_init(tmem_full, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -143,6 +150,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    if (kPair) {   // both CTAs have their barriers ready before either multicasts into the other
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     if (p.pdl) {
         // barriers, TMEM and tensor-map prefetch are done: let the next kernel of the chain (the block update) start ITS
         // prologue now, and wait here until the kernel before us (the previous block update: spins, cleared field rows)
@@ -165,8 +176,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int k0 = (p.kb_offset + kb) * kBK;
                 tma_load_2d(st, &map_a, full + s, k0, m0);
                 for (int q = 0; q < p.n_split; ++q)   // a piece of B: kWide boxes of 128 rows, back to back (rows 128 B apart)
-                    for (int w = 0; w < kWide; ++w)
-                        tma_load_2d(st + (size_t)(1 + q * kWide + w) * kTileBytes, maps_b[q], full + s, k0, n0 + w * kBN);
+                    for (int w = 0; w < kWide; ++w) {
+                        uint8_t *dst = st + (size_t)(1 + q * kWide + w) * kTileBytes;
+                        if (!kPair) {
+                            tma_load_2d(dst, maps_b[q], full + s, k0, n0 + w * kBN);
+                        } else if ((uint32_t)w == pair_rank) {   // this CTA's half, into both CTAs (same offsets, each one's own barrier)
+                            asm volatile(
+                                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                                ::"r"(smem_u32(dst)), "l"(maps_b[q]), "r"(smem_u32(full + s)), "r"(k0), "r"(n0 + w * kBN), "h"((uint16_t)3) : "memory");
+                        }
+                    }
             }
         }
     } else if (warp == 1) {
@@ -186,7 +205,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
                                   (uint32_t)((i | q | k) != 0));
                 }
-                umma_commit(empty + s);  // smem stage reusable once these MMAs have read it
+                // smem stage reusable once these MMAs have read it (kPair: told to both CTAs, either may write into it)
+                if (kPair)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(smem_u32(empty + s)), "h"((uint16_t)3) : "memory");
+                else
+                    umma_commit(empty + s);
             }
             umma_commit(tmem_full);      // accumulator complete
         }
@@ -225,6 +249,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (kPair) {   // neither CTA leaves while the other may still write into it or arrive on its barriers
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kBNt) : "memory");
@@ -356,6 +384,21 @@ static int launch_fields_part(nlmc_dense *D, cudaStream_t st, int col0, int n_co
     static const bool wide_ok = [] { const char *e = getenv("NLMC_DENSE_WIDE"); return e ? atoi(e) != 0 : true; }();
     if (wide_ok && stages == 3 && !pdl && n_cols % (2 * kBN) == 0 && col0 % (2 * kBN) == 0 && p.N == col0 + n_cols) {
         const dim3 wgrid((unsigned)m_tiles, (unsigned)(n_cols / (2 * kBN)), (unsigned)p.k_splits);
+        // NLMC_DENSE_PAIR=1: clusters of 2 CTAs along M share their B tiles by TMA multicast.  Measured at C3 size: 48.4 us against
+        // 46.6 us without (29.2 / 31.0 us with one piece of J) -- halving the L2 traffic does not help, the fill rate of each SM's
+        // shared memory (112 KB per k-block either way) is what bounds the wide kernel; off by default.
+        static const bool pair_ok = [] { const char *e = getenv("NLMC_DENSE_PAIR"); return e ? atoi(e) != 0 : false; }();
+        if (pair_ok && m_tiles % 2 == 0) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = wgrid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = gemm_smem_bytes(2, 2); cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            NLMC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<2, 2, true>, D->map_S, D->map_J[0], D->map_J[D->n_split > 1 ? 1 : 0],
+                                         D->map_J[D->n_split > 2 ? 2 : 0], p));
+            return NLMC_OK;
+        }
         gemm_bf16_tn_kernel<2, 2><<<wgrid, kGemmThreads, gemm_smem_bytes(2, 2), st>>>(
             D->map_S, D->map_J[0], D->map_J[D->n_split > 1 ? 1 : 0], D->map_J[D->n_split > 2 ? 2 : 0], p);
         NLMC_CUDA(cudaGetLastError());
@@ -1370,6 +1413,7 @@ int nlmc_dense_create(nlmc_instance *I, int n_replicas, const double *betas, int
         if (cudaFuncSetAttribute(gemm_bf16_tn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(3)) != cudaSuccess ||
             cudaFuncSetAttribute(gemm_bf16_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2)) != cudaSuccess ||
             cudaFuncSetAttribute(gemm_bf16_tn_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2, 2)) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_bf16_tn_kernel<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(2, 2)) != cudaSuccess ||
             cudaFuncSetAttribute(dense_block_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes(kMaxRepPerCta)) != cudaSuccess ||
             cudaFuncSetAttribute(dense_fused_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes) != cudaSuccess) {
             set_error("nlmc_dense_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
