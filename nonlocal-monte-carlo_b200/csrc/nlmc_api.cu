@@ -117,69 +117,109 @@ int nlmc_instance_create(int n, const int32_t *row_ptr, const int32_t *col, cons
         NLMC_REQUIRE(row_ptr[i + 1] >= row_ptr[i], "nlmc_instance_create: row_ptr not monotone at row %d", i);
         max_deg = std::max(max_deg, row_ptr[i + 1] - row_ptr[i]);
     }
-    // one pass over the entries on the host workers: range check, integer / small-integer flags, and the compact
-    // int8 / uint16 copies the shared-memory replay kernel reads (integer J only)
+    // one pass over the entries on the host workers: range check, integer / small-integer flags, and the host mirrors
     const int parts = nnz >= (1 << 18) ? nlmc::host_threads_shared() : 1;
     std::vector<int> bad((size_t)parts, -1);
     std::vector<char> not_int((size_t)parts, 0), not_small((size_t)parts, 0);
-    std::vector<int8_t> v8((size_t)nnz);
-    std::vector<uint16_t> c16(n <= 65535 ? (size_t)nnz : 0);
+    auto *I = new nlmc_instance();
+    I->h_col.resize((size_t)nnz);
+    I->h_val.resize((size_t)nnz);
     nlmc::parallel_for(parts, [&](int t, int np) {
         const int per = (nnz + np - 1) / np, lo = std::min(nnz, per * t), hi = std::min(nnz, lo + per);
         for (int p = lo; p < hi; ++p) {
+            I->h_col[(size_t)p] = col[p];
+            I->h_val[(size_t)p] = val[p];
             if (col[p] < 0 || col[p] >= n) { if (bad[(size_t)t] < 0) bad[(size_t)t] = p; continue; }
             const double v = val[p];
             if (v != std::floor(v) || std::fabs(v) > 1e6) not_int[(size_t)t] = 1;
             if (!(std::fabs(v) <= 127.0)) not_small[(size_t)t] = 1;
-            v8[(size_t)p] = (int8_t)(std::fabs(v) <= 127.0 ? v : 0.0);
-            if (!c16.empty()) c16[(size_t)p] = (uint16_t)col[p];
         }
     });
     bool integer_j = true, small_int = nnz > 0;
     for (int t = 0; t < parts; ++t) {
-        NLMC_REQUIRE(bad[(size_t)t] < 0, "nlmc_instance_create: column index out of range at entry %d", bad[(size_t)t]);
+        if (bad[(size_t)t] >= 0) {
+            const int b = bad[(size_t)t];
+            delete I;
+            NLMC_REQUIRE(false, "nlmc_instance_create: column index out of range at entry %d", b);
+        }
         if (not_int[(size_t)t]) integer_j = false;
         if (not_small[(size_t)t]) small_int = false;
     }
     small_int = small_int && integer_j;
-    NLMC_CUDA(cudaSetDevice(device));
-    auto *I = new nlmc_instance();
+    if (cudaSetDevice(device) != cudaSuccess) {
+        nlmc::set_error("nlmc_instance_create: cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(cudaGetLastError()));
+        delete I;
+        return NLMC_ERR_CUDA;
+    }
     I->device = device;
     I->n = n;
     I->nnz = nnz;
     I->max_deg = max_deg;
     I->integer_j = integer_j;
+    I->small_int = small_int;
     I->h_row_ptr.assign(row_ptr, row_ptr + n + 1);
-    I->h_col.assign(col, col + nnz);
-    I->h_val.assign(val, val + nnz);
     I->h_h.assign(h, h + n);
-    auto fail = [&](void) {
-        nlmc::set_error("nlmc_instance_create: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (cudaStreamCreateWithFlags(&I->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        nlmc::set_error("nlmc_instance_create: stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         nlmc_instance_destroy(I);
         return NLMC_ERR_CUDA;
-    };
-    // Device arrays come from the stream-ordered pool (every NPT.run builds its own instance: cudaMalloc / cudaFree of
-    // seven arrays was 10 ms per call at C5 size); the copies are queued on the instance's stream and waited for once.
-    const size_t nz = (size_t)std::max(nnz, 1);
-    if (cudaStreamCreateWithFlags(&I->stream, cudaStreamNonBlocking) != cudaSuccess) return fail();
-    cudaStream_t st = I->stream;
-    auto up = [&](void **dst, const void *src, size_t alloc_bytes, size_t copy_bytes) {
-        if (nlmc::pool_alloc(dst, alloc_bytes, device, st) != cudaSuccess) return false;
-        return copy_bytes == 0 || cudaMemcpyAsync(*dst, src, copy_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
-    };
-    bool ok = up(reinterpret_cast<void **>(&I->row_ptr), row_ptr, sizeof(int32_t) * (size_t)(n + 1), sizeof(int32_t) * (size_t)(n + 1)) &&
-              up(reinterpret_cast<void **>(&I->col), col, sizeof(int32_t) * nz, sizeof(int32_t) * (size_t)nnz) &&
-              up(reinterpret_cast<void **>(&I->val), val, sizeof(double) * nz, sizeof(double) * (size_t)nnz) &&
-              up(reinterpret_cast<void **>(&I->h), h, sizeof(double) * (size_t)n, sizeof(double) * (size_t)n);
-    if (ok && small_int) {
-        ok = up(reinterpret_cast<void **>(&I->int_val), v8.data(), (size_t)nnz, (size_t)nnz);
-        if (ok && n <= 65535)
-            ok = up(reinterpret_cast<void **>(&I->col16), c16.data(), sizeof(uint16_t) * (size_t)nnz, sizeof(uint16_t) * (size_t)nnz);
     }
-    if (!ok || cudaStreamSynchronize(st) != cudaSuccess) return fail();  // v8 / c16 and the caller's arrays may go away
     *out = I;
     return NLMC_OK;
 }
+
+}  // extern "C"
+
+namespace nlmc {
+
+// The CSR on the device, uploaded on first use from the host mirrors (thread-safe; the engines that never read it -- the
+// bit-packed and the dense one -- do not pay for it).  Device arrays come from the stream-ordered pool; the copies are queued
+// on the instance's stream and waited for once.
+int instance_device(nlmc_instance *I) {
+    NLMC_REQUIRE(I != nullptr, "instance_device: NULL instance");
+    std::lock_guard<std::mutex> lock(I->device_mu);
+    if (I->device_ready) return NLMC_OK;
+    NLMC_CUDA(cudaSetDevice(I->device));
+    const int n = I->n, nnz = I->nnz;
+    const size_t nz = (size_t)std::max(nnz, 1);
+    cudaStream_t st = I->stream;
+    // the compact int8 / uint16 copies the shared-memory replay kernel reads (small integer J only)
+    std::vector<int8_t> v8(I->small_int ? (size_t)nnz : 0);
+    std::vector<uint16_t> c16(I->small_int && n <= 65535 ? (size_t)nnz : 0);
+    if (I->small_int) {
+        const int parts = nnz >= (1 << 18) ? host_threads_shared() : 1;
+        parallel_for(parts, [&](int t, int np) {
+            const int per = (nnz + np - 1) / np, lo = std::min(nnz, per * t), hi = std::min(nnz, lo + per);
+            for (int p = lo; p < hi; ++p) {
+                v8[(size_t)p] = (int8_t)I->h_val[(size_t)p];
+                if (!c16.empty()) c16[(size_t)p] = (uint16_t)I->h_col[(size_t)p];
+            }
+        });
+    }
+    auto up = [&](void **dst, const void *src, size_t alloc_bytes, size_t copy_bytes) {
+        if (pool_alloc(dst, alloc_bytes, I->device, st) != cudaSuccess) return false;
+        return copy_bytes == 0 || cudaMemcpyAsync(*dst, src, copy_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    };
+    bool ok = up(reinterpret_cast<void **>(&I->row_ptr), I->h_row_ptr.data(), sizeof(int32_t) * (size_t)(n + 1), sizeof(int32_t) * (size_t)(n + 1)) &&
+              up(reinterpret_cast<void **>(&I->col), I->h_col.data(), sizeof(int32_t) * nz, sizeof(int32_t) * (size_t)nnz) &&
+              up(reinterpret_cast<void **>(&I->val), I->h_val.data(), sizeof(double) * nz, sizeof(double) * (size_t)nnz) &&
+              up(reinterpret_cast<void **>(&I->h), I->h_h.data(), sizeof(double) * (size_t)n, sizeof(double) * (size_t)n);
+    if (ok && I->small_int) {
+        ok = up(reinterpret_cast<void **>(&I->int_val), v8.data(), (size_t)nnz, (size_t)nnz);
+        if (ok && !c16.empty())
+            ok = up(reinterpret_cast<void **>(&I->col16), c16.data(), sizeof(uint16_t) * (size_t)nnz, sizeof(uint16_t) * (size_t)nnz);
+    }
+    if (!ok || cudaStreamSynchronize(st) != cudaSuccess) {   // v8 / c16 go away; other streams read the arrays afterwards
+        set_error("instance_device: CUDA allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return NLMC_ERR_CUDA;
+    }
+    I->device_ready = true;
+    return NLMC_OK;
+}
+
+}  // namespace nlmc
+
+extern "C" {
 
 /* Host-side format helper of the boundary: widen int8 spins to the float64 arrays the reference's API returns
  * (M is float64 +-1, NMC/nmc.py:52,89), on `threads` host threads (0 = hardware concurrency, at most 32). */

@@ -291,6 +291,7 @@ int nlmc_col_create(nlmc_instance *I, int n_replicas, const double *betas, int r
     using namespace nlmc;
     NLMC_REQUIRE(I && out && betas && n_replicas >= 1, "nlmc_col_create: bad arguments");
     *out = nullptr;
+    { const int rc_dev = nlmc::instance_device(I); if (rc_dev) return rc_dev; }   // the CSR on the device (uploaded on first use)
     NLMC_REQUIRE(nlmc::instance_value_symmetric(I), "nlmc_col_create: J must be symmetric (J_ij == J_ji) without repeated entries; "
                                      "the coloured sweep updates the neighbours' fields from the flipped site's own row");
     const int n = I->n, nnz = I->nnz;

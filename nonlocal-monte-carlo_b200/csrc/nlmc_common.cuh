@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "nlmc_b200.h"
@@ -110,9 +111,18 @@ struct nlmc_instance {
     // host mirrors (colouring, validation, MSC packing)
     std::vector<int32_t> h_row_ptr, h_col;
     std::vector<double> h_val, h_h;
+    // The device arrays above are uploaded on first use (nlmc::instance_device): the bit-packed and the dense engine build
+    // their own layouts from the host mirrors and never read the CSR on the device (23 MB of pageable copies per NPT.run at
+    // the size of config C5).
+    bool device_ready = false;
+    bool small_int = false;        // every value is an integer in [-127, 127]: int_val (and col16) exist on the device
+    std::mutex device_mu;
 };
 
-namespace nlmc { bool instance_value_symmetric(nlmc_instance *I); }
+namespace nlmc {
+bool instance_value_symmetric(nlmc_instance *I);
+int instance_device(nlmc_instance *I);   // NLMC_OK once row_ptr / col / val / h (and int_val / col16) are on the device
+}
 
 struct nlmc_replicas {
     nlmc_instance *inst = nullptr;

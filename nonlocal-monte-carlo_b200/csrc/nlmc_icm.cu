@@ -99,6 +99,7 @@ int nlmc_icm_clusters(nlmc_instance *I, int n_pairs, const int8_t *s1, const int
     NLMC_REQUIRE(I && n_pairs >= 0, "nlmc_icm_clusters: bad arguments");
     if (n_pairs == 0) return NLMC_OK;
     NLMC_REQUIRE(s1 && s2 && out_labels && out_n_clusters, "nlmc_icm_clusters: NULL buffer");
+    { const int rc_dev = nlmc::instance_device(I); if (rc_dev) return rc_dev; }   // the CSR on the device (uploaded on first use)
     NLMC_CUDA(cudaSetDevice(I->device));
     const size_t n = (size_t)I->n, P = (size_t)n_pairs;
     int8_t *d_s = nullptr;

@@ -419,6 +419,7 @@ int nlmc_lbp_create(nlmc_instance *I, nlmc_lbp **out) {
     using namespace nlmc;
     NLMC_REQUIRE(I && out, "nlmc_lbp_create: NULL argument");
     *out = nullptr;
+    { const int rc_dev = nlmc::instance_device(I); if (rc_dev) return rc_dev; }   // the CSR on the device (uploaded on first use)
     const int n = I->n, nnz = I->nnz;
     // reverse-entry index (requires a symmetric sparsity pattern, as the reference's J is)
     std::vector<int32_t> rev((size_t)std::max(nnz, 1));

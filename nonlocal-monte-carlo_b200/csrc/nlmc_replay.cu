@@ -361,6 +361,7 @@ int nlmc_sweep_replay(nlmc_replicas *P, int n_sweeps, const int32_t *perm, const
     NLMC_REQUIRE(perm && u && beta, "nlmc_sweep_replay: perm, u and beta are required");
     NLMC_REQUIRE(record_from >= 0 && record_from <= n_sweeps, "nlmc_sweep_replay: record_from out of range");
     NLMC_REQUIRE(!tanh_lut || lut_half >= 0, "nlmc_sweep_replay: negative lut_half");
+    { const int rc_dev = nlmc::instance_device(P->inst); if (rc_dev) return rc_dev; }   // the CSR on the device (uploaded on first use)
     nlmc_instance *I = P->inst;
     NLMC_CUDA(cudaSetDevice(I->device));
     const size_t R = (size_t)P->R, n = (size_t)I->n, S = (size_t)n_sweeps;
@@ -433,6 +434,7 @@ int nlmc_energy(nlmc_replicas *P, double *out_E) {
     using namespace nlmc;
     NLMC_REQUIRE(P && out_E, "nlmc_energy: NULL argument");
     nlmc_instance *I = P->inst;
+    { const int rc_dev = nlmc::instance_device(I); if (rc_dev) return rc_dev; }   // the CSR on the device (uploaded on first use)
     NLMC_CUDA(cudaSetDevice(I->device));
     int rc;
     if ((rc = P->s_E.reserve(sizeof(double) * (size_t)P->R))) return rc;
@@ -449,6 +451,7 @@ int nlmc_energy_states(nlmc_instance *I, int n_states, const int8_t *states, dou
     NLMC_REQUIRE(I && n_states >= 0, "nlmc_energy_states: bad arguments");
     if (n_states == 0) return NLMC_OK;
     NLMC_REQUIRE(states && out_E, "nlmc_energy_states: NULL buffer");
+    { const int rc_dev = nlmc::instance_device(I); if (rc_dev) return rc_dev; }   // the CSR on the device (uploaded on first use)
     NLMC_CUDA(cudaSetDevice(I->device));
     int8_t *d_states = nullptr;
     double *d_E = nullptr;
