@@ -1042,7 +1042,6 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             asm volatile("bar.sync 1, %0;" ::"n"(kFusedUpdThreads) : "memory");
             NLMC_FUSED_MARK(7);
             const float *Jt = X;
-            if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == 64 + kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 63] = global_ns();
             // The thresholds of the NEXT block are computed in the shadow of the chain: by the last warp before it (it is on the
             // critical path only at the very end), by the others once their own sub-blocks are decided.
             float Tn[kH][8][kE];
@@ -1121,7 +1120,6 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 if (v < vs) break;                             // every tile of this warp is done
                 if (v == vs) {
                     if (g == s % kE) {
-                        if (p.prof && b == 2 && blockIdx.x == 0 && q == kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 4 * s] = global_ns();
 #pragma unroll
                         for (int h = 0; h < kH; ++h) {
                             decide(kH * tb + h, F2[h], T[h], so_up[h], dmine[h]);
@@ -1137,14 +1135,12 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                                 apply(kH * tb + h, kH * tb + h2, dl, dh, F2[h2]);
                             }
                         }
-                        if (p.prof && b == 2 && blockIdx.x == 0 && q == kLanesPerSub - 1) p.prof[p.n_blocks * 10 + 4 * s + 1] = global_ns() + (dmine[kH - 1][7][kE - 1] == 123.f);
                     }
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sub_done + s)) : "memory");
                 } else {
                     mbar_wait(sub_done + s, (uint32_t)(b & 1));    // hardware wait, no polling traffic on the shared-memory pipe
                 }
-                if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == kFusedThreads - 1) p.prof[p.n_blocks * 10 + 4 * s + 2] = global_ns();
                 if (tb > s) {
 #pragma unroll
                     for (int hs = 0; hs < kH; ++hs) {
@@ -1158,7 +1154,6 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 #pragma unroll
                         for (int h = 0; h < kH; ++h) apply(s8, kH * tb + h, dl, dh, F2[h]);
                     }
-                    if (p.prof && b == 2 && blockIdx.x == 0 && threadIdx.x == kFusedThreads - 1) p.prof[p.n_blocks * 10 + 4 * s + 3] = global_ns() + (F2[0][0][0] == 123ull);
                 }
             }
             // new spins = old spins + flips, as bf16 (+1 = 0x3F80, -1 = 0xBF80; 0 past the end of J)
@@ -1191,19 +1186,21 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                             make_uint4(bits[h][e][0], bits[h][e][1], bits[h][e][2], bits[h][e][3]);
                     }
                 }
+                fence_proxy_async();                           // generic stores -> read by the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(adep)) : "memory");
             }
+            NLMC_FUSED_MARK(9);
+            cluster_arrive();                                  // U(b): this thread is done with the chain, J_bb and the flip buffer
+            // Off the critical path: the new spins to global memory, for the TMA loads of LATER blocks (block b+2 at the earliest,
+            // issued after barrier R(b+1), which these stores and their proxy fence precede in program order) and the next sweep.
 #pragma unroll
             for (int h = 0; h < kH; ++h)
 #pragma unroll
                 for (int e = 0; e < kE; ++e)
                     *reinterpret_cast<uint4 *>(p.S + (size_t)(rq + e) * p.n_pad + c0 + 8 * (kH * tb + h)) =
                         make_uint4(bits[h][e][0], bits[h][e][1], bits[h][e][2], bits[h][e][3]);
-            // one proxy fence for both: the spin slots are read by the tensor core, the global rows by TMA in later blocks
             fence_proxy_async();
-            if (more) {
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(adep)) : "memory");
-            }
             if (more && v != kFusedUpdWarps - 1) thresholds(b + 1, Tn, so_up_n);
             if (more) {
 #pragma unroll
@@ -1215,8 +1212,6 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                     so_up[h] = so_up_n[h];
                 }
             }
-            NLMC_FUSED_MARK(9);
-            cluster_arrive();                                  // U(b)
         }
         cluster_wait();                                        // U(last): nobody writes into this CTA's buffers any more
     }
@@ -1297,7 +1292,7 @@ int nlmc_dense_destroy(nlmc_dense *D) {
     cudaSetDevice(D->inst->device);
     if (D->fused_prof) {   // development aid: where one block step of the cluster sweep spends its time (CTA 0, first update warp)
         const int nb = (D->n + nlmc::kBlk - 1) / nlmc::kBlk;
-        std::vector<unsigned long long> t((size_t)nb * 10 + 64);
+        std::vector<unsigned long long> t((size_t)nb * 10);
         cudaDeviceSynchronize();
         cudaMemcpy(t.data(), D->fused_prof, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost);
         static const char *names[9] = {"thresholds", "wait U(b-1)", "wait accumulator", "drain + push", "cluster barrier R", "sum",
@@ -1307,14 +1302,6 @@ int nlmc_dense_destroy(nlmc_dense *D) {
             for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.2f us |", names[i], 1e-3 * (double)(t[(size_t)b * 10 + i + 1] - t[(size_t)b * 10 + i]));
             if (b + 1 < nb) fprintf(stderr, " step %.2f us", 1e-3 * (double)(t[(size_t)(b + 1) * 10] - t[(size_t)b * 10]));
             fprintf(stderr, "\n");
-        }
-        if (nb > 2) {
-            fprintf(stderr, "block 2, us after the chain started -- step: decisions start/end (owner), flips seen / applied by the last thread\n");
-            for (int i = 0; i < 16; ++i) {
-                const unsigned long long *x = &t[(size_t)nb * 10 + 4 * i];
-                fprintf(stderr, " %d: %.2f/%.2f %.2f/%.2f |", i, 1e-3 * (double)(x[0] - t[27]), 1e-3 * (double)(x[1] - t[27]), 1e-3 * (double)(x[2] - t[27]), 1e-3 * (double)(x[3] - t[27]));
-            }
-            fprintf(stderr, "\n the owner of step 0 left the barrier at %.2f us\n", 1e-3 * (double)(t[(size_t)nb * 10 + 63] - t[27]));
         }
         cudaFree(D->fused_prof);
     }
@@ -1631,7 +1618,7 @@ int nlmc_dense_sweep(nlmc_dense *D, int n_sweeps) {
     NLMC_CUDA(cudaSetDevice(D->inst->device));
     if (!D->sweep_graph) {  // capture one sweep once; replays cost one launch each
         if (getenv("NLMC_DENSE_FUSED_PROF") && !D->fused_prof) {
-            const size_t cnt = 10 * (size_t)((D->n + kBlk - 1) / kBlk) + 64;
+            const size_t cnt = 10 * (size_t)((D->n + kBlk - 1) / kBlk);
             NLMC_CUDA(cudaMalloc(&D->fused_prof, sizeof(unsigned long long) * cnt));
             NLMC_CUDA(cudaMemset(D->fused_prof, 0, sizeof(unsigned long long) * cnt));
         }
