@@ -1186,7 +1186,7 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                             make_uint4(bits[h][e][0], bits[h][e][1], bits[h][e][2], bits[h][e][3]);
                     }
                 }
-                fence_proxy_async();                           // generic stores -> read by the tensor core (async proxy)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores to shared memory -> read by the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(adep)) : "memory");
             }
