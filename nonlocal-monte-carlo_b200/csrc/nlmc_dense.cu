@@ -998,6 +998,9 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 tcgen05_fence_before();
             }
             NLMC_FUSED_MARK(4);
+            // the spins of block b-1 went to global memory after barrier U(b-1): by now the stores have long been performed, so the
+            // proxy fence that the TMA loads behind barrier R(b) need costs nothing here (right after the stores it cost 0.5 us)
+            asm volatile("fence.proxy.async.global;" ::: "memory");
             cluster_arrive();                                  // R(b): the partial fields are in their owners' buffers
             cluster_wait();
             NLMC_FUSED_MARK(5);
@@ -1192,15 +1195,15 @@ dense_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             }
             NLMC_FUSED_MARK(9);
             cluster_arrive();                                  // U(b): this thread is done with the chain, J_bb and the flip buffer
-            // Off the critical path: the new spins to global memory, for the TMA loads of LATER blocks (block b+2 at the earliest,
-            // issued after barrier R(b+1), which these stores and their proxy fence precede in program order) and the next sweep.
+            // The new spins to global memory, for the TMA loads of LATER blocks (block b+2 at the earliest, issued after barrier
+            // R(b+1), which these stores and their proxy fence -- executed just before that arrive -- precede in program order)
+            // and for the next sweep.
 #pragma unroll
             for (int h = 0; h < kH; ++h)
 #pragma unroll
                 for (int e = 0; e < kE; ++e)
                     *reinterpret_cast<uint4 *>(p.S + (size_t)(rq + e) * p.n_pad + c0 + 8 * (kH * tb + h)) =
                         make_uint4(bits[h][e][0], bits[h][e][1], bits[h][e][2], bits[h][e][3]);
-            fence_proxy_async();
             if (more && v != kFusedUpdWarps - 1) thresholds(b + 1, Tn, so_up_n);
             if (more) {
 #pragma unroll
