@@ -655,8 +655,8 @@ __global__ void __launch_bounds__(kMaxRepPerCta * 32) dense_block_update_kernel(
 // The new spins also go to global memory (generic stores, fence.proxy.async, cluster barrier U) for the TMA loads of later
 // blocks.  The 64 KB receive buffer and the staged coupling block J_bb share one region: pushes for block b+1 can only
 // happen after every CTA of the cluster has finished the update of block b.
-// Measured at C3 size (N = 2000, 2048 replicas = 16 clusters on 64 SMs): 0.235 ms per sweep against 0.353 ms for the chain of
-// launches; per block 13.9 us = chain 9.1 + drain / push / barrier 2.5 + partial sums 0.4 + staging J_bb 0.6 + stores 0.7
+// Measured at C3 size (N = 2000, 2048 replicas = 16 clusters on 64 SMs): 0.2175 ms per sweep against 0.353 ms for the chain of
+// launches; per block 13.0 us = chain 8.4 + drain / push / barrier 2.5 + partial sums 0.4 + staging J_bb 0.6 + stores 0.7
 // (NLMC_DENSE_FUSED_PROF=1 prints these; profiles/r2d_dense_fused_summary.md).
 constexpr int kFusedCluster = 4;
 constexpr int kFusedRep = kBM / kFusedCluster;             // 32 replicas per CTA = the lanes of a warp
